@@ -1,0 +1,139 @@
+/* include/liloc_gpu.h -- C ABI of the B200-native scan-to-map registration path of LiLoc.
+ *
+ * The reference (Yixin-F/LiLoc, /root/reference) has no plugin or FFI layer: the path is a set of
+ * member functions of `class mapOptimization` (src/mapOptmization.cpp:18) that call PCL, Eigen and
+ * OpenCV in-process, plus the pcl::Registration virtual interface for NDT (:118).  This header is
+ * the boundary a maintainer would bind instead: each entry point names the reference lines it
+ * replaces.  Plain pointers and sizes only; no C++ types, no exceptions, no global state.
+ *
+ * Conventions
+ *   point        {x, y, z, intensity} float32, 16 bytes (pcl::PointXYZI without its padding,
+ *                include/utility.h:83).  All input coordinates must be finite.
+ *   pose6        [roll, pitch, yaw, x, y, z] float32 = transformTobeMapped (src/mapOptmization.cpp:85),
+ *                R = Rz(yaw) Ry(pitch) Rx(roll)  (pcl::getTransformation, :404-406).
+ *   return code  0 success; > 0 benign status (LILOC_SKIPPED ...); < 0 error, text from
+ *                liloc_last_error().  A context is NOT thread-safe (the reference serialises the
+ *                path under `mtx`, :255); use one context per calling thread / per GPU.
+ *   host/device  pointers are HOST pointers unless the name ends in _dev.
+ *
+ * There is no CPU fallback: every compute entry point fails with LILOC_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef LILOC_GPU_H
+#define LILOC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LILOC_OK              0
+#define LILOC_SKIPPED         1   /* scan2map gate Q_all <= min_points (src/mapOptmization.cpp:1187,1205) */
+#define LILOC_ERR_ARG        -1
+#define LILOC_ERR_CUDA       -2
+#define LILOC_ERR_OOM        -3
+#define LILOC_ERR_STATE      -4   /* e.g. scan2map before a map / scan exists */
+#define LILOC_ERR_CAPACITY   -5
+
+typedef struct { float x, y, z, intensity; } liloc_point;
+
+typedef struct liloc_ctx liloc_ctx;
+
+typedef struct {
+    int device;             /* CUDA device ordinal */
+    int max_scan_points;    /* N_SCAN * Horizon_SCAN, sizes scratch like allocateMemory() :228-230 */
+    int max_raw_points;     /* initial capacity of the concatenated local map (grows on demand) */
+    int reserved[5];
+} liloc_config;
+
+/* scan2MapOptimization knobs.  Reference values in brackets. */
+typedef struct {
+    int max_iters;          /* [20]  loop bound, src/mapOptmization.cpp:1190 */
+    int stride;             /* [2]   every 2nd down-sampled point, :985 */
+    int min_sel;            /* [50]  LMOptimization bail-out, :1080 */
+    int min_points;         /* [30]  gate is Q_all > min_points, :1187 */
+    int reserved[4];
+} liloc_s2m_opts;
+
+typedef struct {
+    int   iters;            /* loop iterations executed (1..max_iters) */
+    int   converged;        /* LMOptimization returned true, :1177-1179 */
+    int   n_sel;            /* correspondences in the last executed iteration (laserCloudSelNum, :1079) */
+    int   is_degenerate;    /* member isDegenerate (:90), consumed by publishOdometry (:1573) */
+    int   too_few;          /* last iteration had fewer than min_sel correspondences */
+    int   skipped;          /* gate failed: pose untouched */
+    int   q_all;            /* laserCloudSurfLastDSNum */
+    int   map_points;       /* laserCloudSurfFromMapDSNum */
+    float matP[36];         /* member matP (:91), row-major */
+    float AtA0[36];         /* J^T J of iteration 0 (diagnostic; input of the degeneracy check) */
+} liloc_s2m_result;
+
+/* ---- lifetime: allocateMemory() :213-244, VoxelGrid set-up :158-160 ------------------------- */
+int  liloc_create(const liloc_config* cfg, liloc_ctx** out);
+void liloc_destroy(liloc_ctx* ctx);
+const char* liloc_last_error(const liloc_ctx* ctx);   /* ctx may be NULL: last create() error */
+const char* liloc_version(void);
+
+/* ---- keyframe store: surfCloudKeyFrames.push_back :1385,1457 + laserCloudMapContainer :69 -------
+ * The library keeps a device copy of every keyframe cloud (body frame); the caller keeps its own. */
+int liloc_keyframe_put(liloc_ctx* ctx, int kf_id, const liloc_point* pts_body, int n);
+/* thisSurfKeyFrame = copy of laserCloudSurfLastDS (:1382,1454): device-to-device, no host traffic */
+int liloc_keyframe_put_from_scan(liloc_ctx* ctx, int kf_id);
+int liloc_keyframe_size(liloc_ctx* ctx, int kf_id);    /* points, or <0 if unknown id */
+int liloc_keyframe_clear(liloc_ctx* ctx);              /* laserCloudMapContainer.clear() + new session */
+
+/* ---- local map: extractCloud :936-961 + transformPointCloud include/utility.h:388-407 -----------
+ * Transforms the K selected keyframes by their poses and concatenates them IN THE GIVEN ORDER
+ * (duplicates allowed, :924-931), applies pcl::VoxelGrid semantics at `leaf`
+ * (surroundingKeyframeMapLeafSize) and builds the search structure that replaces
+ * kdtreeSurfFromMap->setInputCloud (:1188).  The map stays on the device.
+ * M_out / n_raw_out may be NULL (then no host synchronisation happens here). */
+int liloc_localmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf,
+                         int* M_out, int* n_raw_out);
+/* Same, from an explicit map-frame cloud (tests; prior submaps): VoxelGrid + search structure. */
+int liloc_localmap_set(liloc_ctx* ctx, const liloc_point* pts_map, int n, float leaf, int* M_out);
+int liloc_localmap_get(liloc_ctx* ctx, liloc_point* out, int cap, int* M_out);   /* laserCloudSurfFromMapDS */
+
+/* ---- current scan: downsampleCurrentScan :970-975 ---------------------------------------------- */
+int liloc_scan_put(liloc_ctx* ctx, const liloc_point* pts_body, int n, float leaf, int* Q_all_out);
+int liloc_scan_put_dev(liloc_ctx* ctx, const liloc_point* pts_body_dev, int n, float leaf, int* Q_all_out);
+int liloc_scan_ds_get(liloc_ctx* ctx, liloc_point* out, int cap, int* Q_all_out);  /* laserCloudSurfLastDS */
+
+/* ---- registration: scan2MapOptimization :1183-1201 (everything except transformUpdate :1202) -----
+ * pose6: in = initial guess (updateInitialGuess :831-900), out = optimised transformTobeMapped.
+ * All iterations run on the device without a host round trip.  isDegenerate / matP persist in the
+ * context across calls exactly like the class members (:90-91). */
+int liloc_scan2map(liloc_ctx* ctx, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res);
+
+/* One frame in one call: extractCloud + downsampleCurrentScan + scan2MapOptimization with a single
+ * host synchronisation at the end (laserCloudInfoHandler :311-315).  scan may be a host pointer
+ * (scan_on_device = 0) or a device pointer (1). */
+int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K, float map_leaf,
+                const liloc_point* scan, int n_scan, int scan_on_device, float scan_leaf,
+                float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res);
+
+/* ---- kernel-level entry points (used by the parity tests; no reference caller) ------------------ */
+/* pcl::VoxelGrid<PointXYZI>::filter on a host cloud -> host cloud (cap >= n). */
+int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, liloc_point* out, int cap, int* m_out);
+/* Exact sorted 5-NN of nq map-frame queries against the current local map
+ * (kdtreeSurfFromMap->nearestKSearch :992).  Ties broken by ascending index.  Only neighbours with
+ * d2 < 1.0 are searched for (the reference discards everything else at :1002): for a query whose
+ * 5th neighbour is not within 1 m, idx5[5*i+4] == -1 and found[i] < 5. */
+int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries_map, int nq, int* idx5, float* d2_5, int* found);
+/* surfOptimization at a fixed pose (:981-1048): per scan point i (multiples of stride) the flag
+ * laserCloudOriSurfFlag[i] and coefficient coeffSelSurfVec[i]; arrays have Q_all entries. */
+int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag);
+/* pcl::getTransformation as the device evaluates it: top 3x4 block, row-major. */
+int liloc_pose_to_T(liloc_ctx* ctx, const float* pose6, float* T12);
+
+/* ---- timing: CUDA-event milliseconds of the phases of the last liloc_frame / call sequence ------ */
+typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;
+int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t);
+int liloc_set_timing(liloc_ctx* ctx, int enabled);
+long long liloc_kernel_launches(const liloc_ctx* ctx);   /* kernels launched by this context so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LILOC_GPU_H */

@@ -1,0 +1,264 @@
+"""ctypes binding of include/liloc_gpu.h (the same stub a maintainer of the reference would write
+in C++ -- see INTEGRATION.md).  Every call goes through the C ABI; nothing here computes."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libliloc_gpu.so")
+
+LILOC_OK = 0
+LILOC_SKIPPED = 1
+
+POINT_DTYPE = np.dtype(np.float32)   # clouds are (n, 4) float32 arrays: x, y, z, intensity
+
+
+class LilocError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"liloc error {code}: {msg}")
+        self.code = code
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_scan_points", C.c_int), ("max_raw_points", C.c_int),
+                ("reserved", C.c_int * 5)]
+
+
+class S2mOpts(C.Structure):
+    """liloc_s2m_opts; defaults are the reference's constants (src/mapOptmization.cpp:1190,985,1080,1187)."""
+    _fields_ = [("max_iters", C.c_int), ("stride", C.c_int), ("min_sel", C.c_int), ("min_points", C.c_int),
+                ("reserved", C.c_int * 4)]
+
+    def __init__(self, max_iters: int = 20, stride: int = 2, min_sel: int = 50, min_points: int = 30):
+        super().__init__(max_iters, stride, min_sel, min_points)
+
+
+class S2mResult(C.Structure):
+    _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("n_sel", C.c_int), ("is_degenerate", C.c_int),
+                ("too_few", C.c_int), ("skipped", C.c_int), ("q_all", C.c_int), ("map_points", C.c_int),
+                ("matP", C.c_float * 36), ("AtA0", C.c_float * 36)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k in ("iters", "converged", "n_sel", "is_degenerate", "too_few",
+                                               "skipped", "q_all", "map_points")}
+
+
+class Timing(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("assemble_ms", "map_voxel_ms", "grid_ms", "scan_ms", "s2m_ms", "total_ms")]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(lib_path):
+        raise ImportError(
+            f"{lib_path} is missing: build it with `python -m liloc_b200._build` (nvcc, sm_100a). "
+            "liloc_b200 has no CPU fallback.")
+    L = C.CDLL(lib_path)
+    P = C.c_void_p
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    sig = {
+        "liloc_create": (C.c_int, [C.POINTER(_Config), C.POINTER(P)]),
+        "liloc_destroy": (None, [P]),
+        "liloc_last_error": (C.c_char_p, [P]),
+        "liloc_version": (C.c_char_p, []),
+        "liloc_keyframe_put": (C.c_int, [P, C.c_int, P, C.c_int]),
+        "liloc_keyframe_put_from_scan": (C.c_int, [P, C.c_int]),
+        "liloc_keyframe_size": (C.c_int, [P, C.c_int]),
+        "liloc_keyframe_clear": (C.c_int, [P]),
+        "liloc_localmap_build": (C.c_int, [P, P, P, C.c_int, C.c_float, ip, ip]),
+        "liloc_localmap_set": (C.c_int, [P, P, C.c_int, C.c_float, ip]),
+        "liloc_localmap_get": (C.c_int, [P, P, C.c_int, ip]),
+        "liloc_scan_put": (C.c_int, [P, P, C.c_int, C.c_float, ip]),
+        "liloc_scan_put_dev": (C.c_int, [P, P, C.c_int, C.c_float, ip]),
+        "liloc_scan_ds_get": (C.c_int, [P, P, C.c_int, ip]),
+        "liloc_scan2map": (C.c_int, [P, P, C.POINTER(S2mOpts), C.POINTER(S2mResult)]),
+        "liloc_frame": (C.c_int, [P, P, P, C.c_int, C.c_float, P, C.c_int, C.c_int, C.c_float, P,
+                                  C.POINTER(S2mOpts), C.POINTER(S2mResult)]),
+        "liloc_voxelgrid": (C.c_int, [P, P, C.c_int, C.c_float, P, C.c_int, ip]),
+        "liloc_knn5": (C.c_int, [P, P, C.c_int, P, P, P]),
+        "liloc_surf_pass": (C.c_int, [P, P, C.c_int, P, P]),
+        "liloc_pose_to_T": (C.c_int, [P, P, P]),
+        "liloc_last_timing": (C.c_int, [P, C.POINTER(Timing)]),
+        "liloc_set_timing": (C.c_int, [P, C.c_int]),
+        "liloc_kernel_launches": (C.c_longlong, [P]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    return L
+
+
+lib = _load()
+EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyframe_put "
+           "liloc_keyframe_put_from_scan liloc_keyframe_size liloc_keyframe_clear liloc_localmap_build "
+           "liloc_localmap_set liloc_localmap_get liloc_scan_put liloc_scan_put_dev liloc_scan_ds_get "
+           "liloc_scan2map liloc_frame liloc_voxelgrid liloc_knn5 liloc_surf_pass liloc_pose_to_T "
+           "liloc_last_timing liloc_set_timing liloc_kernel_launches").split()
+
+
+def _cloud(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("cloud must have shape (n, 4): x, y, z, intensity")
+    return a
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One liloc_ctx (one GPU, one stream).  Mirrors the calls mapOptimization makes per frame."""
+
+    def __init__(self, device: int = 0, max_scan_points: int = 32 * 1800, max_raw_points: int = 1 << 20):
+        cfg = _Config(device, max_scan_points, max_raw_points)
+        h = C.c_void_p()
+        rc = lib.liloc_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise LilocError(rc, (lib.liloc_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.liloc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc: int) -> int:
+        if rc < 0:
+            raise LilocError(rc, (lib.liloc_last_error(self._h) or b"").decode())
+        return rc
+
+    # ---- keyframes ----
+    def keyframe_put(self, kf_id: int, pts) -> None:
+        p = _cloud(pts)
+        self._chk(lib.liloc_keyframe_put(self._h, kf_id, _ptr(p), len(p)))
+
+    def keyframe_put_from_scan(self, kf_id: int) -> None:
+        self._chk(lib.liloc_keyframe_put_from_scan(self._h, kf_id))
+
+    def keyframe_size(self, kf_id: int) -> int:
+        return lib.liloc_keyframe_size(self._h, kf_id)
+
+    def keyframe_clear(self) -> None:
+        self._chk(lib.liloc_keyframe_clear(self._h))
+
+    # ---- local map ----
+    def localmap_build(self, kf_ids, poses6, leaf: float) -> tuple[int, int]:
+        ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
+        assert len(ids) == len(poses)
+        M, n_raw = C.c_int(), C.c_int()
+        self._chk(lib.liloc_localmap_build(self._h, _ptr(ids), _ptr(poses), len(ids), leaf, C.byref(M), C.byref(n_raw)))
+        return M.value, n_raw.value
+
+    def localmap_set(self, pts_map, leaf: float) -> int:
+        p = _cloud(pts_map)
+        M = C.c_int()
+        self._chk(lib.liloc_localmap_set(self._h, _ptr(p), len(p), leaf, C.byref(M)))
+        return M.value
+
+    def localmap_get(self) -> np.ndarray:
+        M = C.c_int()
+        self._chk(lib.liloc_localmap_get(self._h, None, 0, C.byref(M)))
+        out = np.empty((M.value, 4), np.float32)
+        self._chk(lib.liloc_localmap_get(self._h, _ptr(out), M.value, C.byref(M)))
+        return out
+
+    # ---- scan ----
+    def scan_put(self, pts_body, leaf: float) -> int:
+        p = _cloud(pts_body)
+        Q = C.c_int()
+        self._chk(lib.liloc_scan_put(self._h, _ptr(p), len(p), leaf, C.byref(Q)))
+        return Q.value
+
+    def scan_put_dev(self, dev_ptr: int, n: int, leaf: float) -> int:
+        Q = C.c_int()
+        self._chk(lib.liloc_scan_put_dev(self._h, C.c_void_p(dev_ptr), n, leaf, C.byref(Q)))
+        return Q.value
+
+    def scan_ds_get(self) -> np.ndarray:
+        Q = C.c_int()
+        self._chk(lib.liloc_scan_ds_get(self._h, None, 0, C.byref(Q)))
+        out = np.empty((Q.value, 4), np.float32)
+        self._chk(lib.liloc_scan_ds_get(self._h, _ptr(out), Q.value, C.byref(Q)))
+        return out
+
+    # ---- registration ----
+    def scan2map(self, pose6, opts: S2mOpts | None = None) -> tuple[np.ndarray, S2mResult, int]:
+        pose = np.array(pose6, dtype=np.float32).reshape(6).copy()
+        res = S2mResult()
+        o = opts or S2mOpts()
+        rc = self._chk(lib.liloc_scan2map(self._h, _ptr(pose), C.byref(o), C.byref(res)))
+        return pose, res, rc
+
+    def frame(self, kf_ids, poses6, map_leaf: float, scan, scan_leaf: float, pose6, opts: S2mOpts | None = None,
+              scan_dev_ptr: int | None = None, n_scan: int | None = None) -> tuple[np.ndarray, S2mResult, int]:
+        ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
+        pose = np.array(pose6, dtype=np.float32).reshape(6).copy()
+        res = S2mResult()
+        o = opts or S2mOpts()
+        if scan_dev_ptr is not None:
+            sp, n, on_dev = C.c_void_p(scan_dev_ptr), int(n_scan), 1
+        else:
+            s = _cloud(scan)
+            sp, n, on_dev = _ptr(s), len(s), 0
+        rc = self._chk(lib.liloc_frame(self._h, _ptr(ids), _ptr(poses), len(ids), map_leaf, sp, n, on_dev, scan_leaf,
+                                       _ptr(pose), C.byref(o), C.byref(res)))
+        return pose, res, rc
+
+    # ---- kernel-level ----
+    def voxelgrid(self, pts, leaf: float) -> np.ndarray:
+        p = _cloud(pts)
+        out = np.empty_like(p)
+        m = C.c_int()
+        self._chk(lib.liloc_voxelgrid(self._h, _ptr(p), len(p), leaf, _ptr(out), len(p), C.byref(m)))
+        return out[: m.value].copy()
+
+    def knn5(self, queries_map) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        q = _cloud(queries_map)
+        idx = np.empty((len(q), 5), np.int32)
+        d2 = np.empty((len(q), 5), np.float32)
+        found = np.empty(len(q), np.int32)
+        self._chk(lib.liloc_knn5(self._h, _ptr(q), len(q), _ptr(idx), _ptr(d2), _ptr(found)))
+        return idx, d2, found
+
+    def surf_pass(self, pose6, stride: int, q_all: int) -> tuple[np.ndarray, np.ndarray]:
+        pose = np.ascontiguousarray(pose6, dtype=np.float32).reshape(6)
+        coeff = np.zeros((q_all, 4), np.float32)
+        flag = np.zeros(q_all, np.uint8)
+        self._chk(lib.liloc_surf_pass(self._h, _ptr(pose), stride, _ptr(coeff), _ptr(flag)))
+        return coeff, flag
+
+    def pose_to_T(self, pose6) -> np.ndarray:
+        pose = np.ascontiguousarray(pose6, dtype=np.float32).reshape(6)
+        T = np.empty(12, np.float32)
+        self._chk(lib.liloc_pose_to_T(self._h, _ptr(pose), _ptr(T)))
+        return T.reshape(3, 4)
+
+    # ---- instrumentation ----
+    def set_timing(self, on: bool) -> None:
+        lib.liloc_set_timing(self._h, int(on))
+
+    def last_timing(self) -> dict:
+        t = Timing()
+        lib.liloc_last_timing(self._h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def kernel_launches(self) -> int:
+        return int(lib.liloc_kernel_launches(self._h))

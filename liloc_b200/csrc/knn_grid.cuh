@@ -1,0 +1,227 @@
+// liloc_b200/csrc/knn_grid.cuh -- uniform search grid over the down-sampled local map and the exact
+// warp-cooperative 5-NN query that replaces pcl::KdTreeFLANN.
+//
+// Replaces (reference): kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS)  src/mapOptmization.cpp:1188
+//                       kdtreeSurfFromMap->nearestKSearch(pointSel, 5, ...)         src/mapOptmization.cpp:992
+//
+// Exactness argument.  The reference keeps a correspondence only if d2[4] < 1.0 (:1002), i.e. only
+// if all five neighbours lie strictly within 1 m.  Cells are cubes of edge c = 2^k >= 1 m and cell
+// coordinates are floor(x * (1/c)) with 1/c a power of two, so the coordinate is computed without
+// rounding; two points closer than 1 m therefore sit in cells that differ by at most 1 per axis, and
+// scanning the 27-cell neighbourhood with the (d2, index) total order returns exactly the reference's
+// neighbour set whenever that set can pass the gate.  Otherwise fewer than 5 candidates below 1.0
+// are found and the query is rejected -- the same decision the reference takes.
+//
+// Layout in HBM: map points sorted by cell (x fastest) as float4 {x, y, z, bitcast(original index)};
+// cell_start[ncells + 1] exclusive offsets.  The three x-adjacent cells of a (y, z) row are one
+// contiguous range, so a query reads 9 ranges with coalesced 16-byte loads, one lane per point.
+#pragma once
+#include "common.cuh"
+
+namespace liloc {
+
+struct GridParams {
+    float inv_cell;        // 1 / cell edge (power of two)
+    int g0[3];             // cell coordinate of the grid origin
+    int dim[3];
+    int ncells;
+};
+
+struct GridView {
+    const int* __restrict__ cell_start;
+    const float4* __restrict__ cpts;
+    GridParams p;
+};
+
+LILOC_DEV int cell_coord(float v, float inv_cell, int g0) { return (int)floorf(v * inv_cell) - g0; }
+
+__global__ void __launch_bounds__(256) k_zero_int(int* __restrict__ a, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_count(const float4* __restrict__ map, int M, GridParams gp, int* __restrict__ counts) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(&map[i]);
+        const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
+        const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
+        const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
+        atomicAdd(&counts[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
+    }
+}
+
+// cursor[] starts as a copy of cell_start[]; order inside a cell is arbitrary, which is harmless
+// because the query uses the (d2, index) total order.
+__global__ void __launch_bounds__(256)
+k_grid_scatter(const float4* __restrict__ map, int M, GridParams gp, int* __restrict__ cursor, float4* __restrict__ cpts) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(&map[i]);
+        const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
+        const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
+        const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
+        const int pos = atomicAdd(&cursor[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
+        cpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    }
+}
+
+// ---- generic multi-tile exclusive scan of an int array (cell counts -> cell_start) ---------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_reduce(const int* __restrict__ in, int n, int* __restrict__ tile_sums) {
+    __shared__ int s_w[kScanThreads / 32];
+    const int base = blockIdx.x * kScanTile;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        const int i = base + j * kScanThreads + threadIdx.x;
+        if (i < n) c += in[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) t += s_w[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// out[i] = exclusive prefix; out has n + 1 entries when write_total (out[n] = grand total);
+// copy (optional) receives the same values (the scatter cursor).
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_down(const int* __restrict__ in, int n, const int* __restrict__ tile_offsets, int* __restrict__ out, int* __restrict__ copy) {
+    __shared__ int s_w[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+    int v[kScanPerThread];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? in[base + j] : 0; c += v[j]; }
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int run = tile_offsets[blockIdx.x] + inc - c;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) run += s_w[w];
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        if (base + j < n) { out[base + j] = run; if (copy) copy[base + j] = run; }
+        run += v[j];
+        if (base + j == n - 1) { out[n] = run; }
+    }
+}
+
+// ---- exact 5-NN, one warp per query ---------------------------------------------------------------
+struct Knn5 { float d[5]; int i[5]; };     // ascending (d2, index); i == INT_MAX marks "none"
+
+LILOC_DEV void top5_insert(Knn5& t, float d, int i) {
+    if (!nn_less(d, i, t.d[4], t.i[4])) return;
+    t.d[4] = d; t.i[4] = i;
+#pragma unroll
+    for (int k = 4; k > 0; --k) {
+        if (nn_less(t.d[k], t.i[k], t.d[k - 1], t.i[k - 1])) {
+            const float td = t.d[k]; t.d[k] = t.d[k - 1]; t.d[k - 1] = td;
+            const int ti = t.i[k]; t.i[k] = t.i[k - 1]; t.i[k - 1] = ti;
+        }
+    }
+}
+
+// All 32 lanes call this with the same q; on return every lane holds the same result.
+LILOC_DEV Knn5 knn5_warp(const GridView& g, const float4 q, const int lane) {
+    const int cx = cell_coord(q.x, g.p.inv_cell, g.p.g0[0]);
+    const int cy = cell_coord(q.y, g.p.inv_cell, g.p.g0[1]);
+    const int cz = cell_coord(q.z, g.p.inv_cell, g.p.g0[2]);
+    // lanes 0..8 fetch the 9 (y, z) rows
+    int r_s = 0, r_len = 0;
+    if (lane < 9) {
+        const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.p.dim[0] - 1);
+        if (yy >= 0 && yy < g.p.dim[1] && zz >= 0 && zz < g.p.dim[2] && x0 <= x1) {
+            const int base = (zz * g.p.dim[1] + yy) * g.p.dim[0];
+            r_s = __ldg(&g.cell_start[base + x0]);
+            r_len = __ldg(&g.cell_start[base + x1 + 1]) - r_s;
+        }
+    }
+    int r_off = r_len;                        // inclusive prefix over lanes 0..8 -> exclusive below
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, r_off, o); if (lane >= o) r_off += t; }
+    const int total = __shfl_sync(0xffffffffu, r_off, 8);
+    r_off -= r_len;
+    int row_s[9], row_o[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) { row_s[r] = __shfl_sync(0xffffffffu, r_s, r); row_o[r] = __shfl_sync(0xffffffffu, r_off, r); }
+
+    Knn5 t;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { t.d[k] = 3.4e38f; t.i[k] = 0x7fffffff; }
+
+    auto fetch = [&](int v) -> float4 {
+        int s = row_s[0], o = row_o[0];
+#pragma unroll
+        for (int r = 1; r < 9; ++r) if (v >= row_o[r]) { s = row_s[r]; o = row_o[r]; }
+        return __ldg(&g.cpts[s + (v - o)]);
+    };
+    int v = lane;
+    bool have = v < total;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have) p = fetch(v);
+    while (have) {
+        const int vn = v + 32;
+        const bool have_n = vn < total;
+        float4 pn = p;
+        if (have_n) pn = fetch(vn);
+        const float d = dist2(q, p);
+        if (d < 1.0f) top5_insert(t, d, __float_as_int(p.w));
+        p = pn; v = vn; have = have_n;
+    }
+    // merge the 32 sorted lists: five rounds of warp arg-min on (d2, index)
+    Knn5 out;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float md = t.d[0]; int mi = t.i[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, md, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (nn_less(od, oi, md, mi)) { md = od; mi = oi; }
+        }
+        out.d[k] = md; out.i[k] = mi;
+        if (mi != 0x7fffffff && t.i[0] == mi) {          // the winning lane pops its head
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { t.d[j] = t.d[j + 1]; t.i[j] = t.i[j + 1]; }
+            t.d[4] = 3.4e38f; t.i[4] = 0x7fffffff;
+        }
+    }
+    return out;
+}
+
+// Standalone kNN kernel behind liloc_knn5 (kernel-level parity tests).
+__global__ void __launch_bounds__(256)
+k_knn5(const float4* __restrict__ queries, int nq, GridView g, int* __restrict__ idx5, float* __restrict__ d2, int* __restrict__ found) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < nq; qi += warps_per_grid) {
+        const float4 q = __ldg(&queries[qi]);
+        const Knn5 r = knn5_warp(g, q, lane);
+        if (lane == 0) {
+            int f = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const bool ok = r.i[k] != 0x7fffffff;
+                idx5[5 * qi + k] = ok ? r.i[k] : -1;
+                d2[5 * qi + k] = ok ? r.d[k] : 3.4e38f;
+                f += ok ? 1 : 0;
+            }
+            found[qi] = f;
+        }
+    }
+}
+
+}  // namespace liloc

@@ -1,0 +1,532 @@
+// liloc_b200/csrc/s2m.cuh -- scan2MapOptimization as ONE persistent cooperative kernel.
+//
+// Replaces (reference, src/mapOptmization.cpp): surfOptimization :981-1048, combineOptimizationCoeffs
+// :1050-1059, LMOptimization :1061-1181 and the iteration loop of scan2MapOptimization :1190-1200.
+// The pose, the 6x6 normal equations, the degeneracy projector and the convergence test never leave
+// the device: one grid barrier per Gauss-Newton iteration, zero host round trips.
+//
+// Per iteration, per tile of kQPB scan points:
+//   A  one warp per query: transform by the current pose, exact 5-NN in the search grid (knn_grid.cuh)
+//   B  one thread per query: 5x3 pivoted-Householder plane fit (Eigen colPivHouseholderQr semantics),
+//      validity gates, weight, Jacobian row (LOAM Euler form)            -> shared memory
+//   C  28 threads: the 21 + 6 unique J^T J | J^T r sums and the correspondence count, accumulated in
+//      double from exact float*float products in ascending query order  -> one partial per block
+//   -- grid barrier --
+//   D  every block redundantly: fixed-order reduction of the block partials, float32 Householder QR
+//      solve of the 6x6, (iteration 0) Jacobi eigen-decomposition + degeneracy projector, pose update,
+//      convergence test.  Redundant evaluation is bit-identical in every block, so no second barrier.
+// No intermediate (point, coefficient) array ever reaches HBM.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "knn_grid.cuh"
+
+namespace liloc {
+
+namespace cg = cooperative_groups;
+
+constexpr int kS2mThreads = 512;
+constexpr int kS2mWarps = kS2mThreads / 32;
+constexpr int kQPB = 32;                 // queries per tile
+constexpr int kNSums = 28;               // 21 (upper J^T J) + 6 (J^T r) + 1 (count)
+
+struct S2mState {                        // members isDegenerate / matP (src/mapOptmization.cpp:90-91)
+    int is_degenerate;
+    float matP[36];
+};
+
+struct S2mResult {                       // device mirror of liloc_s2m_result (same field order)
+    int iters, converged, n_sel, is_degenerate, too_few, skipped, q_all, map_points;
+    float matP[36];
+    float AtA0[36];
+    float pose[6];
+};
+
+struct S2mArgs {
+    const float4* scan;                  // down-sampled scan, body frame
+    const int* q_all;                    // device count
+    const float4* map;                   // down-sampled local map, original (voxel) order
+    const int* map_count;
+    GridView grid;
+    int stride, max_iters, min_sel, min_points;
+    double* partial;                     // [2][gridDim.x][kNSums]
+    float* pose_io;                      // 6 floats: in = initial guess, out = result
+    S2mState* state;
+    S2mResult* result;
+};
+
+// ---- 5x3 least squares  A x = -1  (Eigen::colPivHouseholderQr().solve, src/mapOptmization.cpp:1009) --
+// Same operation sequence as oracle plane_lsq_5x3.  Register-only: every array index is static.
+LILOC_DEV void plane_lsq_5x3(const float (&P)[5][3], float (&x)[3]) {
+    float q[3][5];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) q[j][i] = P[i][j];
+    int perm[3] = {0, 1, 2};
+    float hco[3] = {0.f, 0.f, 0.f};
+    float nUpd[3], nDir[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s += q[j][i] * q[j][i];
+        nDir[j] = nUpd[j] = sqrtf(s);
+    }
+    const float eps = 1.1920929e-07f;
+    float mxn = nUpd[0]; if (nUpd[1] > mxn) mxn = nUpd[1]; if (nUpd[2] > mxn) mxn = nUpd[2];
+    const float thr_helper = ((mxn * eps) * (mxn * eps)) / 5.0f;
+    const float downdate_thr = sqrtf(eps);
+    int nonzero = 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int big = k; float bign = nUpd[k];
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j) if (nUpd[j] > bign) { bign = nUpd[j]; big = j; }
+        if (nonzero == 3 && bign * bign < thr_helper * (float)(5 - k)) nonzero = k;
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j) {
+            if (big == j) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { const float t = q[k][i]; q[k][i] = q[j][i]; q[j][i] = t; }
+                { const float t = nUpd[k]; nUpd[k] = nUpd[j]; nUpd[j] = t; }
+                { const float t = nDir[k]; nDir[k] = nDir[j]; nDir[j] = t; }
+                { const int t = perm[k]; perm[k] = perm[j]; perm[j] = t; }
+            }
+        }
+        float tailSq = 0.f;
+#pragma unroll
+        for (int i = k + 1; i < 5; ++i) tailSq += q[k][i] * q[k][i];
+        const float c0 = q[k][k];
+        float beta, tau;
+        if (tailSq <= 1.17549435e-38f) {
+            tau = 0.f; beta = c0;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) q[k][i] = 0.f;
+        } else {
+            beta = sqrtf(c0 * c0 + tailSq);
+            if (c0 >= 0.f) beta = -beta;
+            const float den = c0 - beta;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) q[k][i] = q[k][i] / den;
+            tau = (beta - c0) / beta;
+        }
+        q[k][k] = beta; hco[k] = tau;
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j) {
+            float tmp = 0.f;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) tmp += q[k][i] * q[j][i];
+            tmp += q[j][k];
+            q[j][k] -= tau * tmp;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) q[j][i] -= (tau * q[k][i]) * tmp;
+        }
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j) {
+            if (nUpd[j] != 0.f) {
+                float temp = fabsf(q[j][k]) / nUpd[j];
+                temp = (1.0f + temp) * (1.0f - temp);
+                if (temp < 0.f) temp = 0.f;
+                const float r = nUpd[j] / nDir[j];
+                const float temp2 = temp * (r * r);
+                if (temp2 <= downdate_thr) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = k + 1; i < 5; ++i) s += q[j][i] * q[j][i];
+                    nDir[j] = sqrtf(s); nUpd[j] = nDir[j];
+                } else {
+                    nUpd[j] *= sqrtf(temp);
+                }
+            }
+        }
+    }
+    float c[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k < nonzero) {
+            float tmp = 0.f;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) tmp += q[k][i] * c[i];
+            tmp += c[k];
+            c[k] -= hco[k] * tmp;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) c[i] -= (hco[k] * q[k][i]) * tmp;
+        }
+    }
+#pragma unroll
+    for (int i = 2; i >= 0; --i) {
+        if (i < nonzero) {
+            c[i] = c[i] / q[i][i];
+#pragma unroll
+            for (int r = 0; r < i; ++r) c[r] -= q[i][r] * c[i];
+        }
+    }
+    x[0] = x[1] = x[2] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < nonzero) {
+            if (perm[i] == 0) x[0] = c[i];
+            else if (perm[i] == 1) x[1] = c[i];
+            else x[2] = c[i];
+        }
+    }
+}
+
+// Loop body of surfOptimization after the kNN (src/mapOptmization.cpp:1002-1045).
+// nb[j] = j-th neighbour (map frame).  Returns true when the correspondence is kept.
+LILOC_DEV bool surf_residual(const float (&nb)[5][3], const float d2_4, const float4 ori, const float4 sel, float4* coeff) {
+    if (!(d2_4 < 1.0f)) return false;
+    float X[3];
+    plane_lsq_5x3(nb, X);
+    float pa = X[0], pb = X[1], pc = X[2], pd = 1.f;
+    const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+    pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+    bool valid = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float r = pa * nb[j][0] + pb * nb[j][1] + pc * nb[j][2] + pd;
+        if ((double)fabsf(r) > 0.2) valid = false;
+    }
+    if (!valid) return false;
+    const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+    const float rng = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z));
+    const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / (double)rng);
+    *coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+    return (double)s > 0.1;
+}
+
+struct Trig { float srx, crx, sry, cry, srz, crz; };
+LILOC_DEV Trig pose_trig(const float* pose6) {
+    Trig t;
+    t.srx = (float)sin((double)pose6[2]); t.crx = (float)cos((double)pose6[2]);
+    t.sry = (float)sin((double)pose6[1]); t.cry = (float)cos((double)pose6[1]);
+    t.srz = (float)sin((double)pose6[0]); t.crz = (float)cos((double)pose6[0]);
+    return t;
+}
+
+// Jacobian row of LMOptimization (src/mapOptmization.cpp:1093-1125): [d/droll, d/dpitch, d/dyaw, cx, cy, cz | -c.w]
+LILOC_DEV void jacobian_row(const Trig& g, const float4 p, const float4 c, float (&row)[7]) {
+    const float srx = g.srx, crx = g.crx, sry = g.sry, cry = g.cry, srz = g.srz, crz = g.crz;
+    const float arx = (-srx * cry * p.x - (srx * sry * srz + crx * crz) * p.y + (crx * srz - srx * sry * crz) * p.z) * c.x
+                    + (crx * cry * p.x - (srx * crz - crx * sry * srz) * p.y + (crx * sry * crz + srx * srz) * p.z) * c.y;
+    const float ary = (-crx * sry * p.x + crx * cry * srz * p.y + crx * cry * crz * p.z) * c.x
+                    + (-srx * sry * p.x + srx * sry * srz * p.y + srx * cry * crz * p.z) * c.y
+                    + (-cry * p.x - sry * srz * p.y - sry * crz * p.z) * c.z;
+    const float arz = ((crx * sry * crz + srx * srz) * p.y + (srx * crz - crx * sry * srz) * p.z) * c.x
+                    + ((-crx * srz + srx * sry * crz) * p.y + (-srx * sry * srz - crx * crz) * p.z) * c.y
+                    + (cry * crz * p.y - cry * srz * p.z) * c.z;
+    row[0] = arz; row[1] = ary; row[2] = arx; row[3] = c.x; row[4] = c.y; row[5] = c.z; row[6] = -c.w;
+}
+
+// ---- 6x6 float32 linear algebra (OpenCV stand-ins); same operation order as the oracle ----
+__device__ void solve6_qr(const float* A_in, const float* b_in, float* x) {
+    float A[6][6], b[6];
+    for (int i = 0; i < 6; ++i) { b[i] = b_in[i]; for (int j = 0; j < 6; ++j) A[i][j] = A_in[i * 6 + j]; }
+    for (int k = 0; k < 6; ++k) {
+        float tailSq = 0.f;
+        for (int i = k + 1; i < 6; ++i) tailSq += A[i][k] * A[i][k];
+        const float c0 = A[k][k];
+        if (tailSq <= 1.17549435e-38f) continue;
+        float beta = sqrtf(c0 * c0 + tailSq);
+        if (c0 >= 0.f) beta = -beta;
+        const float den = c0 - beta;
+        float v[6];
+        for (int i = k + 1; i < 6; ++i) v[i] = A[i][k] / den;
+        const float tau = (beta - c0) / beta;
+        A[k][k] = beta;
+        for (int i = k + 1; i < 6; ++i) A[i][k] = 0.f;
+        for (int j = k + 1; j < 6; ++j) {
+            float tmp = 0.f;
+            for (int i = k + 1; i < 6; ++i) tmp += v[i] * A[i][j];
+            tmp += A[k][j];
+            A[k][j] -= tau * tmp;
+            for (int i = k + 1; i < 6; ++i) A[i][j] -= (tau * v[i]) * tmp;
+        }
+        float tmp = 0.f;
+        for (int i = k + 1; i < 6; ++i) tmp += v[i] * b[i];
+        tmp += b[k];
+        b[k] -= tau * tmp;
+        for (int i = k + 1; i < 6; ++i) b[i] -= (tau * v[i]) * tmp;
+    }
+    for (int i = 5; i >= 0; --i) {
+        float s = b[i];
+        for (int j = i + 1; j < 6; ++j) s -= A[i][j] * x[j];
+        x[i] = s / A[i][i];
+    }
+}
+
+__device__ void eigen6_jacobi(const float* A_in, float* w, float* V) {
+    float A[6][6], U[6][6];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { A[i][j] = A_in[i * 6 + j]; U[i][j] = (i == j) ? 1.f : 0.f; }
+    const float eps = 1.1920929e-07f;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        float off = 0.f, diag = 0.f;
+        for (int i = 0; i < 6; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 6; ++j) off += A[i][j] * A[i][j]; }
+        if (off <= (eps * eps) * diag || off == 0.f) break;
+        for (int p = 0; p < 5; ++p) for (int q = p + 1; q < 6; ++q) {
+            const float apq = A[p][q];
+            if (apq == 0.f) continue;
+            const float theta = (A[q][q] - A[p][p]) / (2.0f * apq);
+            const float t = (theta >= 0.f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+            const float c = 1.0f / sqrtf(t * t + 1.0f);
+            const float s = t * c;
+            for (int k = 0; k < 6; ++k) {
+                const float akp = A[k][p], akq = A[k][q];
+                A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
+            }
+            for (int k = 0; k < 6; ++k) {
+                const float apk = A[p][k], aqk = A[q][k];
+                A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
+            }
+            A[p][q] = 0.f; A[q][p] = 0.f;
+            for (int k = 0; k < 6; ++k) {
+                const float upk = U[p][k], uqk = U[q][k];
+                U[p][k] = c * upk - s * uqk; U[q][k] = s * upk + c * uqk;
+            }
+        }
+    }
+    int ord[6] = {0, 1, 2, 3, 4, 5};
+    for (int i = 0; i < 5; ++i) {
+        int m = i;
+        for (int j = i + 1; j < 6; ++j) if (A[ord[j]][ord[j]] > A[ord[m]][ord[m]]) m = j;
+        const int t = ord[m]; for (int j = m; j > i; --j) ord[j] = ord[j - 1]; ord[i] = t;
+    }
+    for (int i = 0; i < 6; ++i) { w[i] = A[ord[i]][ord[i]]; for (int k = 0; k < 6; ++k) V[i * 6 + k] = U[ord[i]][k]; }
+}
+
+// src/mapOptmization.cpp:1132-1154
+__device__ int degeneracy_projector(const float* AtA, float* matP) {
+    float w[6], V[36], V2[36];
+    eigen6_jacobi(AtA, w, V);
+    for (int i = 0; i < 36; ++i) V2[i] = V[i];
+    int degenerate = 0;
+    for (int i = 5; i >= 0; --i) {
+        if (w[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; degenerate = 1; }
+        else break;
+    }
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += (double)V[k * 6 + i] * (double)V2[k * 6 + j];
+        matP[i * 6 + j] = (float)s;
+    }
+    return degenerate;
+}
+
+// which (a, c) pair of the row feeds sum t: t < 21 upper triangle row-major, 21..26 (a, rhs), 27 count
+__constant__ unsigned char c_sum_a[kNSums] = {0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5, 0,1,2,3,4,5, 7};
+__constant__ unsigned char c_sum_c[kNSums] = {0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5, 6,6,6,6,6,6, 7};
+
+struct S2mShared {
+    float T[12];
+    float pose[6];
+    Trig trig;
+    int idx[kQPB][5];
+    float d4[kQPB];
+    float row[kQPB][8];        // 6 Jacobian entries, rhs, valid (1.0 / 0.0)
+    double sums[kNSums];
+    float matP[36];
+    int is_degenerate;
+    int done;                  // 0 continue, 1 converged, 2 too few
+    int n_sel;
+};
+
+// Residual rows for one tile of queries into shared memory (phases A and B).
+LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, const int nq, const int q_all) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // A: warp-cooperative kNN
+    for (int s = warp; s < kQPB; s += kS2mWarps) {
+        const int qk = tile * kQPB + s;
+        if (qk < nq) {
+            const float4 ori = __ldg(&a.scan[qk * a.stride]);
+            const float4 sel = apply_T(sh.T, ori);
+            const Knn5 r = knn5_warp(a.grid, sel, lane);
+            if (lane < 5) sh.idx[s][lane] = (lane == 0) ? r.i[0] : (lane == 1) ? r.i[1] : (lane == 2) ? r.i[2] : (lane == 3) ? r.i[3] : r.i[4];
+            if (lane == 0) sh.d4[s] = (r.i[4] != 0x7fffffff) ? r.d[4] : 3.4e38f;
+        }
+    }
+    __syncthreads();
+    // B: one thread per query
+    if (threadIdx.x < kQPB) {
+        const int s = threadIdx.x;
+        const int qk = tile * kQPB + s;
+        float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float valid = 0.f;
+        if (qk < nq) {
+            const float d4 = sh.d4[s];
+            if (d4 < 1.0f) {
+                const float4 ori = __ldg(&a.scan[qk * a.stride]);
+                const float4 sel = apply_T(sh.T, ori);
+                float nb[5][3];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float4 p = __ldg(&a.map[sh.idx[s][j]]);
+                    nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
+                }
+                float4 coeff;
+                if (surf_residual(nb, d4, ori, sel, &coeff)) { jacobian_row(sh.trig, ori, coeff, row); valid = 1.f; }
+            }
+        }
+        if (valid == 0.f) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) row[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sh.row[s][j] = row[j];
+        sh.row[s][7] = valid;
+    }
+    __syncthreads();
+    (void)q_all;
+}
+
+__global__ void __launch_bounds__(kS2mThreads, 1) k_scan2map(S2mArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ S2mShared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q_all = *a.q_all;
+    const int M = *a.map_count;
+    const int nq = (q_all + a.stride - 1) / a.stride;
+    const int n_tiles = (nq + kQPB - 1) / kQPB;
+
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; ++k) sh.pose[k] = a.pose_io[k];
+        pose_to_T(sh.pose, sh.T);
+        sh.trig = pose_trig(sh.pose);
+        sh.is_degenerate = a.state->is_degenerate;
+        for (int k = 0; k < 36; ++k) sh.matP[k] = a.state->matP[k];
+        sh.done = 0; sh.n_sel = 0;
+    }
+    __syncthreads();
+
+    const bool skipped = !(q_all > a.min_points);             // :1187
+    int iters = 0, converged = 0, too_few = 0;
+    if (!skipped) {
+        for (int iter = 0; iter < a.max_iters; ++iter) {
+            double acc = 0.0;                               // threads < kNSums: running sum over this block's tiles
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                s2m_tile_rows(a, sh, tile, nq, q_all);
+                if (threadIdx.x < kNSums) {                 // C
+                    const int ia = c_sum_a[threadIdx.x], ic = c_sum_c[threadIdx.x];
+#pragma unroll 8
+                    for (int s = 0; s < kQPB; ++s) acc += (double)sh.row[s][ia] * (double)sh.row[s][ic];
+                }
+                __syncthreads();
+            }
+            double* part = a.partial + (size_t)(iter & 1) * gridDim.x * kNSums;
+            if (threadIdx.x < kNSums) part[(size_t)blockIdx.x * kNSums + threadIdx.x] = acc;
+            grid.sync();
+            // D: fixed-order reduction of the block partials, identical in every block
+            for (int t = warp; t < kNSums; t += kS2mWarps) {
+                double s = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&part[(size_t)b * kNSums + t]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += shfl_xor_d(s, o);
+                if (lane == 0) sh.sums[t] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int n_sel = (int)sh.sums[27];
+                sh.n_sel = n_sel;
+                if (n_sel < a.min_sel) {
+                    sh.done = 2;                            // :1079-1082 (pose unchanged: later iterations identical)
+                } else {
+                    float AtA[36], AtB[6], X[6];
+                    int k = 0;
+                    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { AtA[r * 6 + c] = AtA[c * 6 + r] = (float)sh.sums[k++]; }
+                    for (int r = 0; r < 6; ++r) AtB[r] = (float)sh.sums[21 + r];
+                    solve6_qr(AtA, AtB, X);                                             // :1130
+                    if (iter == 0) {
+                        sh.is_degenerate = degeneracy_projector(AtA, sh.matP);          // :1132-1154
+                        if (blockIdx.x == 0) for (int i = 0; i < 36; ++i) a.result->AtA0[i] = AtA[i];
+                    }
+                    if (sh.is_degenerate) {                                             // :1156-1160
+                        float X2[6];
+                        for (int i = 0; i < 6; ++i) {
+                            double s = 0.0;
+                            for (int j = 0; j < 6; ++j) s += (double)sh.matP[i * 6 + j] * (double)X[j];
+                            X2[i] = (float)s;
+                        }
+                        for (int i = 0; i < 6; ++i) X[i] = X2[i];
+                    }
+                    for (int i = 0; i < 6; ++i) sh.pose[i] += X[i];                     // :1162-1167
+                    const float r0 = X[0] * 57.29578f, r1 = X[1] * 57.29578f, r2 = X[2] * 57.29578f;
+                    const float t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
+                    const float deltaR = (float)sqrt((double)r0 * (double)r0 + (double)r1 * (double)r1 + (double)r2 * (double)r2);
+                    const float deltaT = (float)sqrt((double)t0 * (double)t0 + (double)t1 * (double)t1 + (double)t2 * (double)t2);
+                    if ((double)deltaR < 0.05 && (double)deltaT < 0.05) sh.done = 1;    // :1177
+                    pose_to_T(sh.pose, sh.T);
+                    sh.trig = pose_trig(sh.pose);
+                }
+            }
+            __syncthreads();
+            iters = iter + 1;
+            if (sh.done == 1) { converged = 1; break; }
+            if (sh.done == 2) { too_few = 1; break; }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S2mResult* r = a.result;
+        r->iters = iters; r->converged = converged; r->n_sel = sh.n_sel; r->is_degenerate = sh.is_degenerate;
+        r->too_few = too_few; r->skipped = skipped ? 1 : 0; r->q_all = q_all; r->map_points = M;
+        for (int i = 0; i < 36; ++i) r->matP[i] = sh.matP[i];
+        for (int i = 0; i < 6; ++i) { r->pose[i] = sh.pose[i]; a.pose_io[i] = sh.pose[i]; }
+        a.state->is_degenerate = sh.is_degenerate;
+        for (int i = 0; i < 36; ++i) a.state->matP[i] = sh.matP[i];
+    }
+}
+
+// surfOptimization at a fixed pose for the residual-level parity test (liloc_surf_pass).
+__global__ void __launch_bounds__(kS2mThreads)
+k_surf_pass(S2mArgs a, const float* __restrict__ pose6, float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
+    __shared__ S2mShared sh;
+    const int q_all = *a.q_all;
+    const int nq = (q_all + a.stride - 1) / a.stride;
+    const int n_tiles = (nq + kQPB - 1) / kQPB;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; ++k) sh.pose[k] = pose6[k];
+        pose_to_T(sh.pose, sh.T);
+        sh.trig = pose_trig(sh.pose);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = warp; s < kQPB; s += kS2mWarps) {
+            const int qk = tile * kQPB + s;
+            if (qk < nq) {
+                const float4 ori = __ldg(&a.scan[qk * a.stride]);
+                const float4 sel = apply_T(sh.T, ori);
+                const Knn5 r = knn5_warp(a.grid, sel, lane);
+                if (lane < 5) sh.idx[s][lane] = (lane == 0) ? r.i[0] : (lane == 1) ? r.i[1] : (lane == 2) ? r.i[2] : (lane == 3) ? r.i[3] : r.i[4];
+                if (lane == 0) sh.d4[s] = (r.i[4] != 0x7fffffff) ? r.d[4] : 3.4e38f;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kQPB) {
+            const int s = threadIdx.x;
+            const int qk = tile * kQPB + s;
+            if (qk < nq) {
+                const int i = qk * a.stride;
+                float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned char ok = 0;
+                const float d4 = sh.d4[s];
+                if (d4 < 1.0f) {
+                    const float4 ori = __ldg(&a.scan[i]);
+                    const float4 sel = apply_T(sh.T, ori);
+                    float nb[5][3];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 p = __ldg(&a.map[sh.idx[s][j]]);
+                        nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
+                    }
+                    float4 c;
+                    if (surf_residual(nb, d4, ori, sel, &c)) { coeff = c; ok = 1; }
+                }
+                coeff_out[i] = coeff;
+                flag_out[i] = ok;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace liloc

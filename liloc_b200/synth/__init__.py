@@ -1,0 +1,133 @@
+"""Seeded synthetic worlds, sensors, trajectories and scans.
+
+Inputs only -- nothing here is on the measured path.  The ray caster is native
+(``libliloc_synth.so``, built from ``synth.cpp``); worlds and trajectories are numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libliloc_synth.so")
+
+
+class _Sensor(C.Structure):
+    _fields_ = [("pattern", C.c_int), ("n_rings", C.c_int), ("n_az", C.c_int),
+                ("el_min_deg", C.c_float), ("el_max_deg", C.c_float),
+                ("range_min", C.c_float), ("range_max", C.c_float), ("noise_sigma", C.c_float)]
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} missing: run `python -m liloc_b200._build`")
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.synth_scan.restype = C.c_int
+        _lib.synth_scan.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_Sensor), C.c_uint64, C.c_void_p]
+    return _lib
+
+
+@dataclass(frozen=True)
+class Sensor:
+    name: str
+    pattern: int            # 0 spinning, 1 random
+    n_rings: int
+    n_az: int
+    el_min_deg: float
+    el_max_deg: float
+    range_min: float
+    range_max: float
+    noise_sigma: float = 0.02
+
+    @property
+    def max_points(self) -> int:
+        return self.n_rings * self.n_az if self.pattern == 0 else self.n_az
+
+
+# config/lio_sam_default.yaml: N_SCAN 16, Horizon_SCAN 1800, range 2..100 m
+VLP16 = Sensor("vlp16", 0, 16, 1800, -15.0, 15.0, 2.0, 100.0)
+# config/nclt.yaml: N_SCAN 32, Horizon_SCAN 1800, range 1..100 m
+HDL32 = Sensor("hdl32e", 0, 32, 1800, -30.67, 10.67, 1.0, 100.0)
+# config/lio_sam_mid360.yaml: non-repetitive pattern approximated by 20 000 uniform rays / frame
+MID360 = Sensor("mid360", 1, 1, 20000, -7.0, 52.0, 0.5, 100.0)
+
+
+def make_world(size_xy=(60.0, 40.0), height=12.0, n_pillars=12, seed=0) -> np.ndarray:
+    """Box room centred on the origin with the floor at z=0, plus box pillars.  (n_boxes, 6) float32."""
+    rng = np.random.default_rng(seed)
+    sx, sy = size_xy
+    boxes = [[-sx / 2, -sy / 2, 0.0, sx / 2, sy / 2, height]]
+    for _ in range(n_pillars):
+        w, d = rng.uniform(0.6, 2.5, 2)
+        h = rng.uniform(2.0, height)
+        cx = rng.uniform(-sx / 2 + 3, sx / 2 - 3)
+        cy = rng.uniform(-sy / 2 + 3, sy / 2 - 3)
+        if abs(cy) < 2.5:                       # keep a corridor for the trajectory
+            cy = np.sign(cy if cy != 0 else 1.0) * (2.5 + abs(cy))
+        boxes.append([cx - w / 2, cy - d / 2, 0.0, cx + w / 2, cy + d / 2, h])
+    return np.asarray(boxes, dtype=np.float32)
+
+
+def trajectory_line(n: int, step=1.0, x0=-25.0, height=1.8) -> np.ndarray:
+    """advance along +x with a 0.5*sin(k/8) lateral weave and 0.02 rad/step yaw drift.
+    Returns (n, 6) float64 [roll, pitch, yaw, x, y, z]."""
+    k = np.arange(n, dtype=np.float64)
+    pose = np.zeros((n, 6))
+    pose[:, 0] = 0.01 * np.sin(k / 5.0)
+    pose[:, 1] = 0.01 * np.cos(k / 7.0)
+    pose[:, 2] = 0.02 * k * np.cos(k / 20.0) * 0.3
+    pose[:, 3] = x0 + step * k
+    pose[:, 4] = 0.5 * np.sin(k / 8.0)
+    pose[:, 5] = height + 0.02 * np.sin(k / 3.0)
+    return pose
+
+
+def trajectory_loop(n: int, radius_xy=(35.0, 20.0), laps=1.0, height=1.8) -> np.ndarray:
+    """Closed elliptical loop (cfg 2: 1000 frames at 10 Hz along a loop inside a 120 x 80 m world)."""
+    s = np.linspace(0.0, 2 * np.pi * laps, n, endpoint=False)
+    pose = np.zeros((n, 6))
+    pose[:, 3] = radius_xy[0] * np.cos(s)
+    pose[:, 4] = radius_xy[1] * np.sin(s)
+    dx = -radius_xy[0] * np.sin(s)
+    dy = radius_xy[1] * np.cos(s)
+    pose[:, 2] = np.arctan2(dy, dx)
+    pose[:, 0] = 0.01 * np.sin(7 * s)
+    pose[:, 1] = 0.01 * np.cos(5 * s)
+    pose[:, 5] = height + 0.03 * np.sin(11 * s)
+    return pose
+
+
+def scan(world: np.ndarray, pose6, sensor: Sensor, seed: int) -> np.ndarray:
+    """One body-frame scan (n, 4) float32 = cloud_deskewed."""
+    lib = _load()
+    w = np.ascontiguousarray(world, dtype=np.float32)
+    p = np.ascontiguousarray(pose6, dtype=np.float32).reshape(6)
+    out = np.empty((sensor.max_points, 4), np.float32)
+    s = _Sensor(sensor.pattern, sensor.n_rings, sensor.n_az, sensor.el_min_deg, sensor.el_max_deg,
+                sensor.range_min, sensor.range_max, sensor.noise_sigma)
+    n = lib.synth_scan(w.ctypes.data, len(w), p.ctypes.data, C.byref(s), C.c_uint64(seed), out.ctypes.data)
+    return out[:n].copy()
+
+
+def perturb(pose6, seed: int, dt=0.10, dr=0.02) -> np.ndarray:
+    """Initial guess = ground truth + U(+-dt m, +-dr rad) per axis."""
+    rng = np.random.default_rng(seed)
+    p = np.asarray(pose6, dtype=np.float64).copy()
+    p[:3] += rng.uniform(-dr, dr, 3)
+    p[3:] += rng.uniform(-dt, dt, 3)
+    return p.astype(np.float32)
+
+
+def rot_zyx(roll, pitch, yaw) -> np.ndarray:
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, sy * sr + cy * sp * cr],
+                     [sy * cp, cy * cr + sy * sp * sr, sy * sp * cr - cy * sr],
+                     [-sp, cp * sr, cp * cr]])

@@ -1,0 +1,208 @@
+"""ctypes binding of the CPU parity oracle (oracle/libliloc_oracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "libliloc_oracle.so")
+
+
+class LmState(C.Structure):
+    _fields_ = [("is_degenerate", C.c_int), ("matP", C.c_float * 36)]
+
+
+class S2mOpts(C.Structure):
+    _fields_ = [("max_iters", C.c_int), ("stride", C.c_int), ("min_sel", C.c_int), ("min_points", C.c_int),
+                ("knn", C.c_int), ("threads", C.c_int)]
+
+    def __init__(self, max_iters=20, stride=2, min_sel=50, min_points=30, knn=1, threads=1):
+        super().__init__(max_iters, stride, min_sel, min_points, knn, threads)
+
+
+class S2mResult(C.Structure):
+    _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("n_sel", C.c_int), ("is_degenerate", C.c_int),
+                ("too_few", C.c_int), ("skipped", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} missing: run `make -C oracle` or `python -m liloc_b200._build`")
+    L = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    L.orc_num_threads.restype = C.c_int
+    L.orc_voxelgrid.restype = C.c_int
+    L.orc_voxelgrid.argtypes = [P, C.c_int, C.c_float, P]
+    L.orc_pose_to_T.argtypes = [P, P]
+    L.orc_transform_cloud.argtypes = [P, C.c_int, P, P, C.c_int]
+    L.orc_apply_T.argtypes = [P, C.c_int, P, P]
+    L.orc_knn5_brute.argtypes = [P, C.c_int, P, C.c_int, P, P, C.c_int]
+    L.orc_knn5_kdtree.argtypes = [P, C.c_int, P, C.c_int, P, P, C.c_int]
+    L.orc_plane_lsq.argtypes = [P, P]
+    L.orc_solve6.argtypes = [P, P, P]
+    L.orc_eigen6.argtypes = [P, P, P]
+    L.orc_degeneracy.restype = C.c_int
+    L.orc_degeneracy.argtypes = [P, P]
+    L.orc_jacobian_row.argtypes = [P, P, P, P, P]
+    L.orc_surf_pass.restype = C.c_int
+    L.orc_surf_pass.argtypes = [P, C.c_int, P, C.c_int, C.c_int, P, C.c_int, C.c_int, P, P, P, P, P]
+    L.orc_lm_step.restype = C.c_int
+    L.orc_lm_step.argtypes = [P, P, C.c_int, C.c_int, C.c_int, P, C.POINTER(LmState), P, P]
+    L.orc_scan2map.restype = C.c_int
+    L.orc_scan2map.argtypes = [P, C.c_int, P, C.c_int, P, C.POINTER(S2mOpts), C.POINTER(LmState), C.POINTER(S2mResult)]
+    L.orc_localmap_build.restype = C.c_int
+    L.orc_localmap_build.argtypes = [P, P, P, C.c_int, C.c_float, C.c_int, P, P]
+    L.orc_frame.restype = C.c_int
+    L.orc_frame.argtypes = [P, P, P, C.c_int, C.c_float, P, C.c_int, C.c_float, P, C.POINTER(S2mOpts),
+                            C.POINTER(LmState), C.POINTER(S2mResult), P, P, P]
+    return L
+
+
+lib = _load()
+
+
+def _c(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4
+    return a
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def num_threads() -> int:
+    return lib.orc_num_threads()
+
+
+def pose_to_T(pose6) -> np.ndarray:
+    p = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    T = np.empty(12, np.float32)
+    lib.orc_pose_to_T(_p(p), _p(T))
+    return T.reshape(3, 4)
+
+
+def transform_cloud(pts, pose6, threads=1) -> np.ndarray:
+    a = _c(pts)
+    p = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    out = np.empty_like(a)
+    lib.orc_transform_cloud(_p(a), len(a), _p(p), _p(out), threads)
+    return out
+
+
+def voxelgrid(pts, leaf) -> np.ndarray:
+    a = _c(pts)
+    out = np.empty_like(a)
+    m = lib.orc_voxelgrid(_p(a), len(a), leaf, _p(out))
+    return out[:m].copy()
+
+
+def knn5(map_pts, queries, kdtree=False, threads=1):
+    m, q = _c(map_pts), _c(queries)
+    idx = np.empty((len(q), 5), np.int32)
+    d2 = np.empty((len(q), 5), np.float32)
+    f = lib.orc_knn5_kdtree if kdtree else lib.orc_knn5_brute
+    f(_p(m), len(m), _p(q), len(q), _p(idx), _p(d2), threads)
+    return idx, d2
+
+
+def plane_lsq(pts5x3) -> np.ndarray:
+    a = np.ascontiguousarray(pts5x3, np.float32).reshape(15)
+    x = np.empty(3, np.float32)
+    lib.orc_plane_lsq(_p(a), _p(x))
+    return x
+
+
+def solve6(A, b) -> np.ndarray:
+    A = np.ascontiguousarray(A, np.float32).reshape(36)
+    b = np.ascontiguousarray(b, np.float32).reshape(6)
+    x = np.empty(6, np.float32)
+    lib.orc_solve6(_p(A), _p(b), _p(x))
+    return x
+
+
+def eigen6(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(36)
+    w = np.empty(6, np.float32)
+    V = np.empty(36, np.float32)
+    lib.orc_eigen6(_p(A), _p(w), _p(V))
+    return w, V.reshape(6, 6)
+
+
+def degeneracy(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(36)
+    P = np.empty(36, np.float32)
+    d = lib.orc_degeneracy(_p(A), _p(P))
+    return bool(d), P.reshape(6, 6)
+
+
+def jacobian_row(pose6, ori, coef):
+    p = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    o = np.ascontiguousarray(ori, np.float32).reshape(4)
+    c = np.ascontiguousarray(coef, np.float32).reshape(4)
+    row = np.empty(6, np.float32)
+    rhs = np.empty(1, np.float32)
+    lib.orc_jacobian_row(_p(p), _p(o), _p(c), _p(row), _p(rhs))
+    return row, float(rhs[0])
+
+
+def surf_pass(map_pts, scan_ds, pose6, stride=2, kdtree=False, threads=1, want_knn=False):
+    """Returns (coeff[Q_all,4], flag[Q_all], ori_sel, coef_sel, sel_index[, idx5, d2])."""
+    m, s = _c(map_pts), _c(scan_ds)
+    p = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    Q = len(s)
+    ori = np.empty((Q, 4), np.float32)
+    coef = np.empty((Q, 4), np.float32)
+    sel = np.empty(Q, np.int32)
+    idx5 = np.full((Q, 5), -1, np.int32) if want_knn else None
+    d2 = np.full((Q, 5), np.float32(3.4e38), np.float32) if want_knn else None
+    n = lib.orc_surf_pass(_p(m), len(m), _p(s), Q, stride, _p(p), 1 if kdtree else 0, threads, _p(ori), _p(coef), _p(sel),
+                          _p(idx5) if want_knn else None, _p(d2) if want_knn else None)
+    full = np.zeros((Q, 4), np.float32)
+    flag = np.zeros(Q, np.uint8)
+    full[sel[:n]] = coef[:n]
+    flag[sel[:n]] = 1
+    out = (full, flag, ori[:n].copy(), coef[:n].copy(), sel[:n].copy())
+    return out + ((idx5, d2) if want_knn else ())
+
+
+def scan2map(map_pts, scan_ds, pose6, opts: S2mOpts | None = None, state: LmState | None = None):
+    m, s = _c(map_pts), _c(scan_ds)
+    p = np.array(pose6, np.float32).reshape(6).copy()
+    o = opts or S2mOpts()
+    st = state if state is not None else LmState()
+    res = S2mResult()
+    rc = lib.orc_scan2map(_p(m), len(m), _p(s), len(s), _p(p), C.byref(o), C.byref(st), C.byref(res))
+    return p, res, rc, st
+
+
+def localmap_build(kf_clouds, poses6, leaf, threads=1):
+    pts = np.ascontiguousarray(np.concatenate([_c(c) for c in kf_clouds], axis=0)) if kf_clouds else np.zeros((0, 4), np.float32)
+    offs = np.zeros(len(kf_clouds) + 1, np.int64)
+    offs[1:] = np.cumsum([len(c) for c in kf_clouds])
+    poses = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
+    out = np.empty((max(len(pts), 1), 4), np.float32)
+    M = lib.orc_localmap_build(_p(pts), _p(offs), _p(poses), len(kf_clouds), leaf, threads, _p(out), None)
+    return out[:M].copy()
+
+
+def frame(kf_pts, kf_offs, poses6, map_leaf, scan_raw, scan_leaf, pose6, opts: S2mOpts, state: LmState | None = None):
+    """Whole reference frame on the CPU with timing. kf_pts: concatenated (N,4); kf_offs: int64 (K+1)."""
+    pts = _c(kf_pts)
+    offs = np.ascontiguousarray(kf_offs, np.int64)
+    poses = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
+    s = _c(scan_raw)
+    p = np.array(pose6, np.float32).reshape(6).copy()
+    st = state if state is not None else LmState()
+    res = S2mResult()
+    M, Q = C.c_int(), C.c_int()
+    ms = np.zeros(4, np.float64)
+    rc = lib.orc_frame(_p(pts), _p(offs), _p(poses), len(offs) - 1, map_leaf, _p(s), len(s), scan_leaf, _p(p),
+                       C.byref(opts), C.byref(st), C.byref(res), C.byref(M), C.byref(Q), _p(ms))
+    return p, res, rc, M.value, Q.value, ms

@@ -127,11 +127,20 @@ int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point*
 /* pcl::getTransformation as the device evaluates it: top 3x4 block, row-major. */
 int liloc_pose_to_T(liloc_ctx* ctx, const float* pose6, float* T12);
 
+/* The small dense algebra as the device evaluates it, n independent systems (one thread each):
+ * cv::solve(DECOMP_QR) :1130, cv::eigen :1138 (w descending) and the degeneracy projector :1141-1153. */
+int liloc_debug_lm6(liloc_ctx* ctx, const float* A36, const float* b6, int n, float* x6, float* w6, float* P36, int* deg);
+/* Eigen colPivHouseholderQr().solve of n 5x3 systems A x = -1 (:1009); pts15 = n x 5 x 3 row-major. */
+int liloc_debug_plane(liloc_ctx* ctx, const float* pts15, int n, float* x3);
+
 /* ---- timing: CUDA-event milliseconds of the phases of the last liloc_frame / call sequence ------ */
 typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t);
 int liloc_set_timing(liloc_ctx* ctx, int enabled);
 long long liloc_kernel_launches(const liloc_ctx* ctx);   /* kernels launched by this context so far */
+/* Per-iteration trace of the last scan2map: rows of 16 floats {n_sel, X[6], pose_after[6], AtB[0..2]}
+ * for the first min(max_iters, 32) iterations; returns the number of rows copied. */
+int liloc_last_trace(liloc_ctx* ctx, float* out, int max_iters);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,9 @@ def _load() -> C.CDLL:
         "liloc_last_timing": (C.c_int, [P, C.POINTER(Timing)]),
         "liloc_set_timing": (C.c_int, [P, C.c_int]),
         "liloc_kernel_launches": (C.c_longlong, [P]),
+        "liloc_last_trace": (C.c_int, [P, P, C.c_int]),
+        "liloc_debug_lm6": (C.c_int, [P, P, P, C.c_int, P, P, P, P]),
+        "liloc_debug_plane": (C.c_int, [P, P, C.c_int, P]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -95,7 +98,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_keyframe_put_from_scan liloc_keyframe_size liloc_keyframe_clear liloc_localmap_build "
            "liloc_localmap_set liloc_localmap_get liloc_scan_put liloc_scan_put_dev liloc_scan_ds_get "
            "liloc_scan2map liloc_frame liloc_voxelgrid liloc_knn5 liloc_surf_pass liloc_pose_to_T "
-           "liloc_last_timing liloc_set_timing liloc_kernel_launches").split()
+           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_debug_lm6 liloc_debug_plane").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -259,6 +262,26 @@ class Context:
         t = Timing()
         lib.liloc_last_timing(self._h, C.byref(t))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def debug_lm6(self, A, b):
+        A = np.ascontiguousarray(A, np.float32).reshape(-1, 36)
+        b = np.ascontiguousarray(b, np.float32).reshape(-1, 6)
+        n = len(A)
+        x, w = np.empty((n, 6), np.float32), np.empty((n, 6), np.float32)
+        P, deg = np.empty((n, 36), np.float32), np.empty(n, np.int32)
+        self._chk(lib.liloc_debug_lm6(self._h, _ptr(A), _ptr(b), n, _ptr(x), _ptr(w), _ptr(P), _ptr(deg)))
+        return x, w, P.reshape(n, 6, 6), deg
+
+    def debug_plane(self, pts):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 15)
+        x = np.empty((len(pts), 3), np.float32)
+        self._chk(lib.liloc_debug_plane(self._h, _ptr(pts), len(pts), _ptr(x)))
+        return x
+
+    def last_trace(self, iters: int = 32) -> np.ndarray:
+        out = np.zeros((32, 16), np.float32)
+        n = lib.liloc_last_trace(self._h, _ptr(out), iters)
+        return out[:n]
 
     def kernel_launches(self) -> int:
         return int(lib.liloc_kernel_launches(self._h))

@@ -169,6 +169,24 @@ __global__ void k_init_enc(unsigned* enc) {
 __global__ void k_set_int(int* p, int v) { *p = v; }
 __global__ void k_pose_to_T(const float* pose6, float* T) { if (threadIdx.x == 0) pose_to_T(pose6, T); }
 
+// device-side evaluation of the small dense algebra, one system per thread (kernel-level parity tests)
+__global__ void k_debug_lm6(const float* A, const float* b, int n, float* x, float* w, float* P, int* deg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float V[36];
+    solve6_qr(A + 36 * i, b + 6 * i, x + 6 * i);
+    eigen6_jacobi(A + 36 * i, w + 6 * i, V);
+    deg[i] = degeneracy_projector(A + 36 * i, P + 36 * i);
+}
+__global__ void k_debug_plane(const float* pts, int n, float* x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float P[5][3], X[3];
+    for (int r = 0; r < 5; ++r) for (int c = 0; c < 3; ++c) P[r][c] = pts[15 * i + 3 * r + c];
+    plane_lsq_5x3(P, X);
+    x[3 * i] = X[0]; x[3 * i + 1] = X[1]; x[3 * i + 2] = X[2];
+}
+
 // VoxelGrid of a device cloud.  Bounding box must already be in ctx->d_enc when have_minmax.
 int vg_run(liloc_ctx* ctx, const float4* d_pts, int n, float leaf, bool have_minmax, DevBuf<float4>& out,
            int* d_count, VgParams* d_vp) {
@@ -657,6 +675,36 @@ int liloc_pose_to_T(liloc_ctx* ctx, const float* pose6, float* T12) {
     return LILOC_OK;
 }
 
+int liloc_debug_lm6(liloc_ctx* ctx, const float* A36, const float* b6, int n, float* x6, float* w6, float* P36, int* deg) {
+    ENTER(ctx);
+    if (n <= 0 || !A36 || !b6 || !x6 || !w6 || !P36 || !deg) return fail(ctx, LILOC_ERR_ARG, "debug_lm6: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_f, (size_t)n * (36 + 6 + 6 + 6 + 36)))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_i, (size_t)n))) return rc;
+    float* dA = ctx->tmp_f.p; float* db = dA + 36 * (size_t)n; float* dx = db + 6 * (size_t)n; float* dw = dx + 6 * (size_t)n; float* dP = dw + 6 * (size_t)n;
+    CU(cudaMemcpyAsync(dA, A36, (size_t)n * 36 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(db, b6, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_debug_lm6<<<(n + 31) / 32, 32, 0, ctx->stream>>>(dA, db, n, dx, dw, dP, ctx->tmp_i.p); KCHECK();
+    CU(cudaMemcpyAsync(x6, dx, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(w6, dw, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(P36, dP, (size_t)n * 36 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(deg, ctx->tmp_i.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LILOC_OK;
+}
+
+int liloc_debug_plane(liloc_ctx* ctx, const float* pts15, int n, float* x3) {
+    ENTER(ctx);
+    if (n <= 0 || !pts15 || !x3) return fail(ctx, LILOC_ERR_ARG, "debug_plane: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_f, (size_t)n * 18))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_f.p, pts15, (size_t)n * 15 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_debug_plane<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->tmp_f.p, n, ctx->tmp_f.p + 15 * (size_t)n); KCHECK();
+    CU(cudaMemcpyAsync(x3, ctx->tmp_f.p + 15 * (size_t)n, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LILOC_OK;
+}
+
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t) {
     if (!ctx || !t) return LILOC_ERR_ARG;
     *t = ctx->last_timing;
@@ -670,5 +718,12 @@ int liloc_set_timing(liloc_ctx* ctx, int enabled) {
 }
 
 long long liloc_kernel_launches(const liloc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int liloc_last_trace(liloc_ctx* ctx, float* out, int max_iters) {
+    if (!ctx || !out || max_iters < 0) return LILOC_ERR_ARG;
+    const int n = max_iters < 32 ? max_iters : 32;
+    std::memcpy(out, ctx->h_info->res.trace, (size_t)n * 16 * sizeof(float));
+    return n;
+}
 
 }  // extern "C"

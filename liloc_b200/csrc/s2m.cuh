@@ -40,6 +40,7 @@ struct S2mResult {                       // device mirror of liloc_s2m_result (s
     float matP[36];
     float AtA0[36];
     float pose[6];
+    float trace[32][16];                 // per iteration: n_sel, X[6], pose_after[6], AtB[0..2]
 };
 
 struct S2mArgs {
@@ -220,9 +221,14 @@ LILOC_DEV void jacobian_row(const Trig& g, const float4 p, const float4 c, float
 }
 
 // ---- 6x6 float32 linear algebra (OpenCV stand-ins); same operation order as the oracle ----
-__device__ void solve6_qr(const float* A_in, const float* b_in, float* x) {
+__host__ __device__ inline void solve6_qr(const float* A_in, const float* b_in, float* x) {
     float A[6][6], b[6];
-    for (int i = 0; i < 6; ++i) { b[i] = b_in[i]; for (int j = 0; j < 6; ++j) A[i][j] = A_in[i * 6 + j]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        b[i] = b_in[i];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = A_in[i * 6 + j];
+    }
     for (int k = 0; k < 6; ++k) {
         float tailSq = 0.f;
         for (int i = k + 1; i < 6; ++i) tailSq += A[i][k] * A[i][k];
@@ -256,47 +262,73 @@ __device__ void solve6_qr(const float* A_in, const float* b_in, float* x) {
     }
 }
 
-__device__ void eigen6_jacobi(const float* A_in, float* w, float* V) {
+// cv::eigen stand-in: cyclic Jacobi, float32, eigenvalues descending, eigenvectors as rows of V.
+// Every matrix index is a compile-time constant (template parameters + full unrolling) so A and U
+// live in registers; the loop form of the same operation sequence is the oracle's eigen6_jacobi.
+template <int P, int Q>
+__host__ __device__ __forceinline__ void jacobi_rotate(float (&A)[6][6], float (&U)[6][6]) {
+    const float apq = A[P][Q];
+    if (apq == 0.f) return;
+    const float theta = (A[Q][Q] - A[P][P]) / (2.0f * apq);
+    const float t = (theta >= 0.f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+    const float c = 1.0f / sqrtf(t * t + 1.0f);
+    const float s = t * c;
+    const float h = t * apq;
+    A[P][P] -= h; A[Q][Q] += h; A[P][Q] = 0.f; A[Q][P] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (k == P || k == Q) continue;
+        const float akp = A[k][P], akq = A[k][Q];
+        const float np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+        A[k][P] = np_; A[P][k] = np_; A[k][Q] = nq_; A[Q][k] = nq_;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float upk = U[P][k], uqk = U[Q][k];
+        U[P][k] = c * upk - s * uqk; U[Q][k] = s * upk + c * uqk;
+    }
+}
+
+__host__ __device__ inline void eigen6_jacobi(const float* A_in, float* w, float* V) {
     float A[6][6], U[6][6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { A[i][j] = A_in[i * 6 + j]; U[i][j] = (i == j) ? 1.f : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { A[i][j] = A_in[i * 6 + j]; U[i][j] = (i == j) ? 1.f : 0.f; }
     const float eps = 1.1920929e-07f;
+#pragma unroll 1
     for (int sweep = 0; sweep < 30; ++sweep) {
         float off = 0.f, diag = 0.f;
-        for (int i = 0; i < 6; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 6; ++j) off += A[i][j] * A[i][j]; }
-        if (off <= (eps * eps) * diag || off == 0.f) break;
-        for (int p = 0; p < 5; ++p) for (int q = p + 1; q < 6; ++q) {
-            const float apq = A[p][q];
-            if (apq == 0.f) continue;
-            const float theta = (A[q][q] - A[p][p]) / (2.0f * apq);
-            const float t = (theta >= 0.f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
-            const float c = 1.0f / sqrtf(t * t + 1.0f);
-            const float s = t * c;
-            for (int k = 0; k < 6; ++k) {
-                const float akp = A[k][p], akq = A[k][q];
-                A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
-            }
-            for (int k = 0; k < 6; ++k) {
-                const float apk = A[p][k], aqk = A[q][k];
-                A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
-            }
-            A[p][q] = 0.f; A[q][p] = 0.f;
-            for (int k = 0; k < 6; ++k) {
-                const float upk = U[p][k], uqk = U[q][k];
-                U[p][k] = c * upk - s * uqk; U[q][k] = s * upk + c * uqk;
-            }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            diag += A[i][i] * A[i][i];
+#pragma unroll
+            for (int j = i + 1; j < 6; ++j) off += A[i][j] * A[i][j];
         }
+        if (off <= (eps * eps) * diag || off == 0.f) break;
+        jacobi_rotate<0, 1>(A, U); jacobi_rotate<0, 2>(A, U); jacobi_rotate<0, 3>(A, U); jacobi_rotate<0, 4>(A, U); jacobi_rotate<0, 5>(A, U);
+        jacobi_rotate<1, 2>(A, U); jacobi_rotate<1, 3>(A, U); jacobi_rotate<1, 4>(A, U); jacobi_rotate<1, 5>(A, U);
+        jacobi_rotate<2, 3>(A, U); jacobi_rotate<2, 4>(A, U); jacobi_rotate<2, 5>(A, U);
+        jacobi_rotate<3, 4>(A, U); jacobi_rotate<3, 5>(A, U);
+        jacobi_rotate<4, 5>(A, U);
     }
-    int ord[6] = {0, 1, 2, 3, 4, 5};
-    for (int i = 0; i < 5; ++i) {
-        int m = i;
-        for (int j = i + 1; j < 6; ++j) if (A[ord[j]][ord[j]] > A[ord[m]][ord[m]]) m = j;
-        const int t = ord[m]; for (int j = m; j > i; --j) ord[j] = ord[j - 1]; ord[i] = t;
+    // stable descending selection on the diagonal; rank[i] = output position of eigenpair i
+    float d[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[i] = A[i][i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) r += (d[j] > d[i] || (d[j] == d[i] && j < i)) ? 1 : 0;
+        w[r] = d[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[r * 6 + k] = U[i][k];
     }
-    for (int i = 0; i < 6; ++i) { w[i] = A[ord[i]][ord[i]]; for (int k = 0; k < 6; ++k) V[i * 6 + k] = U[ord[i]][k]; }
 }
 
 // src/mapOptmization.cpp:1132-1154
-__device__ int degeneracy_projector(const float* AtA, float* matP) {
+__host__ __device__ inline int degeneracy_projector(const float* AtA, float* matP) {
     float w[6], V[36], V2[36];
     eigen6_jacobi(AtA, w, V);
     for (int i = 0; i < 36; ++i) V2[i] = V[i];
@@ -449,6 +481,12 @@ __global__ void __launch_bounds__(kS2mThreads, 1) k_scan2map(S2mArgs a) {
                         for (int i = 0; i < 6; ++i) X[i] = X2[i];
                     }
                     for (int i = 0; i < 6; ++i) sh.pose[i] += X[i];                     // :1162-1167
+                    if (blockIdx.x == 0 && iter < 32) {
+                        float* tr = a.result->trace[iter];
+                        tr[0] = (float)n_sel;
+                        for (int i = 0; i < 6; ++i) { tr[1 + i] = X[i]; tr[7 + i] = sh.pose[i]; }
+                        tr[13] = AtB[0]; tr[14] = AtB[1]; tr[15] = AtB[2];
+                    }
                     const float r0 = X[0] * 57.29578f, r1 = X[1] * 57.29578f, r2 = X[2] * 57.29578f;
                     const float t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
                     const float deltaR = (float)sqrt((double)r0 * (double)r0 + (double)r1 * (double)r1 + (double)r2 * (double)r2);

@@ -396,15 +396,14 @@ void eigen6_jacobi(const float A_in[36], float w[6], float V[36]) {
             const float t = (theta >= 0.f ? 1.0f : -1.0f) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0f));
             const float c = 1.0f / std::sqrt(t * t + 1.0f);
             const float s = t * c;
-            for (int k = 0; k < 6; ++k) {                 // A <- A * G
+            const float h = t * apq;
+            A[p][p] -= h; A[q][q] += h; A[p][q] = 0.f; A[q][p] = 0.f;
+            for (int k = 0; k < 6; ++k) {                 // symmetric update of the off-diagonal rows/columns
+                if (k == p || k == q) continue;
                 const float akp = A[k][p], akq = A[k][q];
-                A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
+                const float np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+                A[k][p] = np_; A[p][k] = np_; A[k][q] = nq_; A[q][k] = nq_;
             }
-            for (int k = 0; k < 6; ++k) {                 // A <- G^T * A
-                const float apk = A[p][k], aqk = A[q][k];
-                A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
-            }
-            A[p][q] = 0.f; A[q][p] = 0.f;
             for (int k = 0; k < 6; ++k) {                 // rows of U are the eigenvectors
                 const float upk = U[p][k], uqk = U[q][k];
                 U[p][k] = c * upk - s * uqk; U[q][k] = s * upk + c * uqk;

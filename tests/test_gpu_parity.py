@@ -26,6 +26,27 @@ def test_pose_to_T_bit_exact(gpu_ctx, orc):
         assert np.array_equal(gpu_ctx.pose_to_T(pose), orc.pose_to_T(pose))
 
 
+def test_small_dense_algebra_bit_exact(gpu_ctx, orc):
+    """6x6 QR solve, Jacobi eigen and degeneracy projector, and the 5x3 plane fit, evaluated on the
+    device, against the oracle on the golden systems: same float32 operation sequence -> same bits."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "lm6x6_cv2.npz"))
+    x, w, P, deg = gpu_ctx.debug_lm6(g["A"], g["b"])
+    for i, (A, b) in enumerate(zip(g["A"], g["b"])):
+        assert np.array_equal(x[i], orc.solve6(A, b))
+        assert np.array_equal(w[i], orc.eigen6(A)[0])
+        d, Pi = orc.degeneracy(A)
+        assert bool(deg[i]) == d and np.array_equal(P[i], Pi)
+    pg = np.load(os.path.join(gold, "plane5x3_lstsq.npz"))["P"]
+    rng = np.random.default_rng(3)
+    extra = np.concatenate([pg, np.repeat(np.array([[[1, 2, 3]] * 5], np.float32), 2, 0),      # rank 1
+                            (rng.normal(size=(500, 5, 3)) * np.array([30, 30, 3]) + np.array([50, -80, 2])).astype(np.float32)])
+    xs = gpu_ctx.debug_plane(extra)
+    for i, pts in enumerate(extra):
+        assert np.array_equal(xs[i], orc.plane_lsq(pts)), i
+
+
 @pytest.mark.parametrize("n,leaf,seed", [(1, 0.2, 0), (2, 0.2, 1), (31, 0.5, 2), (2049, 0.4, 3), (60000, 0.2, 4), (500000, 0.4, 5)])
 def test_voxelgrid_bit_exact_random(gpu_ctx, orc, n, leaf, seed):
     rng = np.random.default_rng(seed)
@@ -122,6 +143,7 @@ def test_knn5_exact_ties_by_index(gpu_ctx, orc):
     map_ds = gpu_ctx.localmap_get()
     assert M == len(cloud)
     q = np.c_[rng.integers(-12, 13, (400, 3)) * 0.25 + 0.125 * rng.integers(0, 2, (400, 3)), np.zeros(400)].astype(np.float32)
+    q[:, 2] = (rng.integers(-12, -6, 400) * 0.25 + 0.125 * rng.integers(0, 2, 400)).astype(np.float32)
     assert _knn_compare(gpu_ctx, orc, map_ds, q) > 300
 
 

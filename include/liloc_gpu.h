@@ -137,10 +137,26 @@ int liloc_debug_plane(liloc_ctx* ctx, const float* pts15, int n, float* x3);
 typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t);
 int liloc_set_timing(liloc_ctx* ctx, int enabled);
+/* Cumulative counters since liloc_create / liloc_stats_reset.  Phase times are CUDA-event milliseconds
+ * summed over liloc_frame calls made while timing is enabled; alg_bytes_* are the ALGORITHMIC bytes of
+ * assemble+map VoxelGrid 16 N_raw + 16 M, scan VoxelGrid 16 N_scan + 16 Q_all,
+ * scan2map I (96 Q + 216) with Q = ceil(Q_all / stride) and I the iterations actually executed. */
+typedef struct {
+    long long frames, launches, s2m_launches, s2m_iters;
+    long long h2d_bytes, d2h_bytes;
+    double assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms;
+    double alg_bytes_map, alg_bytes_scan, alg_bytes_s2m;
+} liloc_stats;
+int liloc_stats_get(const liloc_ctx* ctx, liloc_stats* out);
+int liloc_stats_reset(liloc_ctx* ctx);
+void* liloc_stream(liloc_ctx* ctx);                       /* the context's cudaStream_t */
 long long liloc_kernel_launches(const liloc_ctx* ctx);   /* kernels launched by this context so far */
 /* Per-iteration trace of the last scan2map: rows of 16 floats {n_sel, X[6], pose_after[6], AtB[0..2]}
  * for the first min(max_iters, 32) iterations; returns the number of rows copied. */
 int liloc_last_trace(liloc_ctx* ctx, float* out, int max_iters);
+/* SM-clock deltas of the phases of each iteration of the last scan2map (rows of 8 ints: tiles, grid barrier,
+ * reduction, solve, transform refresh); all zero unless the library was built with -DLILOC_S2M_PROFILE. */
+int liloc_last_clocks(liloc_ctx* ctx, int* out, int max_iters);
 
 #ifdef __cplusplus
 }

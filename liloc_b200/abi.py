@@ -50,6 +50,21 @@ class Timing(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("assemble_ms", "map_voxel_ms", "grid_ms", "scan_ms", "s2m_ms", "total_ms")]
 
 
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_longlong) for k in ("frames", "launches", "s2m_launches", "s2m_iters", "h2d_bytes", "d2h_bytes")] + \
+               [(k, C.c_double) for k in ("assemble_ms", "map_voxel_ms", "grid_ms", "scan_ms", "s2m_ms", "total_ms",
+                                          "alg_bytes_map", "alg_bytes_scan", "alg_bytes_s2m")]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def stats_of(ctx_handle) -> dict:
+    st = Stats()
+    lib.liloc_stats_get(C.c_void_p(ctx_handle), C.byref(st))
+    return st.as_dict()
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(lib_path):
         raise ImportError(
@@ -84,6 +99,10 @@ def _load() -> C.CDLL:
         "liloc_set_timing": (C.c_int, [P, C.c_int]),
         "liloc_kernel_launches": (C.c_longlong, [P]),
         "liloc_last_trace": (C.c_int, [P, P, C.c_int]),
+        "liloc_last_clocks": (C.c_int, [P, P, C.c_int]),
+        "liloc_stats_get": (C.c_int, [P, C.POINTER(Stats)]),
+        "liloc_stats_reset": (C.c_int, [P]),
+        "liloc_stream": (C.c_void_p, [P]),
         "liloc_debug_lm6": (C.c_int, [P, P, P, C.c_int, P, P, P, P]),
         "liloc_debug_plane": (C.c_int, [P, P, C.c_int, P]),
     }
@@ -98,7 +117,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_keyframe_put_from_scan liloc_keyframe_size liloc_keyframe_clear liloc_localmap_build "
            "liloc_localmap_set liloc_localmap_get liloc_scan_put liloc_scan_put_dev liloc_scan_ds_get "
            "liloc_scan2map liloc_frame liloc_voxelgrid liloc_knn5 liloc_surf_pass liloc_pose_to_T "
-           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_debug_lm6 liloc_debug_plane").split()
+           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -282,6 +301,17 @@ class Context:
         out = np.zeros((32, 16), np.float32)
         n = lib.liloc_last_trace(self._h, _ptr(out), iters)
         return out[:n]
+
+    def last_clocks(self, iters: int = 32) -> np.ndarray:
+        out = np.zeros((32, 8), np.int32)
+        n = lib.liloc_last_clocks(self._h, _ptr(out), iters)
+        return out[:n]
+
+    def stats(self) -> dict:
+        return stats_of(self._h.value)
+
+    def stats_reset(self) -> None:
+        lib.liloc_stats_reset(self._h)
 
     def kernel_launches(self) -> int:
         return int(lib.liloc_kernel_launches(self._h))

@@ -133,61 +133,58 @@ LILOC_DEV void top5_insert(Knn5& t, float d, int i) {
     }
 }
 
-// All 32 lanes call this with the same q; on return every lane holds the same result.
-LILOC_DEV Knn5 knn5_warp(const GridView& g, const float4 q, const int lane) {
+// Exact 5-NN by a group of L lanes (L = 1, 2, 4, 8 ...; groups are aligned inside a warp, and ALL 32 lanes of
+// the warp must call this together -- lanes without a query pass active = false).  Lane `sub` of the group
+// scans every L-th point of the 9 cell rows with its own sorted top-5 in registers; the L lists are then
+// merged with five rounds of (d2, index) arg-min over xor-shuffles.  On return every lane of the group
+// holds the same result.  Far fewer instructions than one warp per query: the map is a surface, so a
+// 27-cell neighbourhood holds only ~100-250 candidates.
+template <int L>
+LILOC_DEV Knn5 knn5_group(const GridView& g, const float4 q, const int sub, const bool active) {
     const int cx = cell_coord(q.x, g.p.inv_cell, g.p.g0[0]);
     const int cy = cell_coord(q.y, g.p.inv_cell, g.p.g0[1]);
     const int cz = cell_coord(q.z, g.p.inv_cell, g.p.g0[2]);
-    // lanes 0..8 fetch the 9 (y, z) rows
-    int r_s = 0, r_len = 0;
-    if (lane < 9) {
-        const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.p.dim[0] - 1);
-        if (yy >= 0 && yy < g.p.dim[1] && zz >= 0 && zz < g.p.dim[2] && x0 <= x1) {
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.p.dim[0] - 1);
+    int rs[9], re[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
+        rs[r] = 0; re[r] = 0;
+        if (active && yy >= 0 && yy < g.p.dim[1] && zz >= 0 && zz < g.p.dim[2] && x0 <= x1) {
             const int base = (zz * g.p.dim[1] + yy) * g.p.dim[0];
-            r_s = __ldg(&g.cell_start[base + x0]);
-            r_len = __ldg(&g.cell_start[base + x1 + 1]) - r_s;
+            rs[r] = __ldg(&g.cell_start[base + x0]);
+            re[r] = __ldg(&g.cell_start[base + x1 + 1]);
         }
     }
-    int r_off = r_len;                        // inclusive prefix over lanes 0..8 -> exclusive below
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, r_off, o); if (lane >= o) r_off += t; }
-    const int total = __shfl_sync(0xffffffffu, r_off, 8);
-    r_off -= r_len;
-    int row_s[9], row_o[9];
-#pragma unroll
-    for (int r = 0; r < 9; ++r) { row_s[r] = __shfl_sync(0xffffffffu, r_s, r); row_o[r] = __shfl_sync(0xffffffffu, r_off, r); }
-
     Knn5 t;
 #pragma unroll
     for (int k = 0; k < 5; ++k) { t.d[k] = 3.4e38f; t.i[k] = 0x7fffffff; }
-
-    auto fetch = [&](int v) -> float4 {
-        int s = row_s[0], o = row_o[0];
+    // Row-parallel scan: every pass issues one load per row (up to 9 independent 16-byte loads in
+    // flight per lane) before any distance is evaluated, so a pass costs one memory latency, not nine.
+    for (int k = sub;; k += L) {
+        float4 p[9];
+        bool any = false;
 #pragma unroll
-        for (int r = 1; r < 9; ++r) if (v >= row_o[r]) { s = row_s[r]; o = row_o[r]; }
-        return __ldg(&g.cpts[s + (v - o)]);
-    };
-    int v = lane;
-    bool have = v < total;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have) p = fetch(v);
-    while (have) {
-        const int vn = v + 32;
-        const bool have_n = vn < total;
-        float4 pn = p;
-        if (have_n) pn = fetch(vn);
-        const float d = dist2(q, p);
-        if (d < 1.0f) top5_insert(t, d, __float_as_int(p.w));
-        p = pn; v = vn; have = have_n;
+        for (int r = 0; r < 9; ++r) {
+            const int j = rs[r] + k;
+            if (j < re[r]) { p[r] = __ldg(&g.cpts[j]); any = true; }
+        }
+        if (!any) break;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            if (rs[r] + k < re[r]) {
+                const float d = dist2(q, p[r]);
+                if (d < 1.0f) top5_insert(t, d, __float_as_int(p[r].w));
+            }
+        }
     }
-    // merge the 32 sorted lists: five rounds of warp arg-min on (d2, index)
+    __syncwarp();
     Knn5 out;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         float md = t.d[0]; int mi = t.i[0];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = L / 2; o > 0; o >>= 1) {
             const float od = __shfl_xor_sync(0xffffffffu, md, o);
             const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
             if (nn_less(od, oi, md, mi)) { md = od; mi = oi; }
@@ -202,15 +199,20 @@ LILOC_DEV Knn5 knn5_warp(const GridView& g, const float4 q, const int lane) {
     return out;
 }
 
-// Standalone kNN kernel behind liloc_knn5 (kernel-level parity tests).
+constexpr int kKnnLanes = 8;     // lanes per query in the registration kernels
+
+// Standalone kNN kernel behind liloc_knn5 (kernel-level parity tests): the same group search the
+// registration kernel uses.
 __global__ void __launch_bounds__(256)
 k_knn5(const float4* __restrict__ queries, int nq, GridView g, int* __restrict__ idx5, float* __restrict__ d2, int* __restrict__ found) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < nq; qi += warps_per_grid) {
-        const float4 q = __ldg(&queries[qi]);
-        const Knn5 r = knn5_warp(g, q, lane);
-        if (lane == 0) {
+    const int sub = threadIdx.x % kKnnLanes;
+    const int groups_per_grid = (gridDim.x * blockDim.x) / kKnnLanes;
+    const int nq_pad = ((nq + groups_per_grid - 1) / groups_per_grid) * groups_per_grid;   // keep warps converged
+    for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kKnnLanes; qi < nq_pad; qi += groups_per_grid) {
+        const bool active = qi < nq;
+        const float4 q = active ? __ldg(&queries[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const Knn5 r = knn5_group<kKnnLanes>(g, q, sub, active);
+        if (active && sub == 0) {
             int f = 0;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {

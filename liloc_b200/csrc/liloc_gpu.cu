@@ -35,6 +35,17 @@ struct DevBuf {
     size_t cap = 0;       // elements
 };
 
+struct VgInst {            // scratch of one VoxelGrid instance (the reference has three filters, :78-80)
+    DevBuf<unsigned> keys_a, keys_b, vals_a, vals_b;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<int> tile_counts;
+    unsigned* d_enc = nullptr;     // 6 ordered-uint min/max
+    VgParams* d_vp = nullptr;
+    int* d_count = nullptr;
+    int bits_hint = 32;            // radix-sort key bits expected for the next frame (verified after the fact)
+    int bits_used = 32;
+};
+
 struct HostFrameInfo {     // pinned, written by async D2H
     VgParams map_vp;
     VgParams scan_vp;
@@ -73,17 +84,19 @@ struct liloc_ctx {
     DevBuf<float4> scan_raw;
     DevBuf<float4> scan;           // down-sampled
     int Q_all = -1;
+    int n_scan_last = 0;
+    const float4* scan_src_last = nullptr;
+    float scan_leaf_last = 0.f, map_leaf_last = 0.f;
+    long long sort_redos = 0;
     bool have_scan = false;
 
-    // voxel grid scratch (shared by both VoxelGrid instances)
-    DevBuf<unsigned> keys_a, keys_b, vals_a, vals_b;
-    DevBuf<unsigned char> cub_tmp;
-    DevBuf<int> tile_counts;
-    unsigned* d_enc = nullptr;     // 6
-    VgParams* d_map_vp = nullptr;
-    VgParams* d_scan_vp = nullptr;
-    int* d_M = nullptr;
-    int* d_Q = nullptr;
+    // VoxelGrid instances: local map (main stream) and current scan (second stream, overlaps the map branch)
+    VgInst vg_map, vg_scan;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int* d_M = nullptr;            // = vg_map.d_count
+    int* d_Q = nullptr;            // = vg_scan.d_count
+    DevBuf<int> tile_counts;       // search-grid scan scratch
 
     // search grid
     GridParams gp{};
@@ -97,6 +110,7 @@ struct liloc_ctx {
     S2mState* d_state = nullptr;
     S2mResult* d_result = nullptr;
     int s2m_max_blocks = 0;
+    int s2m_nq_last = 0;
 
     // kernel-level test scratch
     DevBuf<float4> tmp_pts;
@@ -110,6 +124,8 @@ struct liloc_ctx {
     bool timing = false;
     cudaEvent_t ev[8]{};
     liloc_timing last_timing{};
+    liloc_stats stats{};
+    long long launches_at_reset = 0;
 };
 
 namespace {
@@ -146,6 +162,7 @@ int ensure(liloc_ctx* ctx, DevBuf<T>& b, size_t n, bool keep = false) {
     T* np = nullptr;
     CU(cudaMalloc(&np, cap * sizeof(T)));
     if (b.p) {
+        if (ctx->stream2) CU(cudaStreamSynchronize(ctx->stream2));
         if (keep) CU(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaFree(b.p));
@@ -187,37 +204,47 @@ __global__ void k_debug_plane(const float* pts, int n, float* x) {
     x[3 * i] = X[0]; x[3 * i + 1] = X[1]; x[3 * i + 2] = X[2];
 }
 
-// VoxelGrid of a device cloud.  Bounding box must already be in ctx->d_enc when have_minmax.
-int vg_run(liloc_ctx* ctx, const float4* d_pts, int n, float leaf, bool have_minmax, DevBuf<float4>& out,
-           int* d_count, VgParams* d_vp) {
+// VoxelGrid of a device cloud on stream `st`.  The bounding box must already be in vi.d_enc when have_minmax.
+// `bits` = radix-sort key bits (32 = always safe; fewer = one 8-bit pass less, verified by the caller against
+// VgParams.key_bits after the fact).
+int vg_run(liloc_ctx* ctx, VgInst& vi, cudaStream_t st, const float4* d_pts, int n, float leaf, bool have_minmax,
+           DevBuf<float4>& out, int bits) {
     if (n <= 0) {
-        k_set_int<<<1, 1, 0, ctx->stream>>>(d_count, 0); KCHECK();
+        k_set_int<<<1, 1, 0, st>>>(vi.d_count, 0); KCHECK();
         return 0;
     }
     int rc;
     if ((rc = ensure(ctx, out, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, ctx->keys_a, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, ctx->keys_b, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, ctx->vals_a, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, ctx->vals_b, (size_t)n))) return rc;
+    if ((rc = ensure(ctx, vi.keys_a, (size_t)n))) return rc;
+    if ((rc = ensure(ctx, vi.keys_b, (size_t)n))) return rc;
+    if ((rc = ensure(ctx, vi.vals_a, (size_t)n))) return rc;
+    if ((rc = ensure(ctx, vi.vals_b, (size_t)n))) return rc;
     const int n_tiles = (n + kRunTile - 1) / kRunTile;
-    if ((rc = ensure(ctx, ctx->tile_counts, (size_t)n_tiles + 1))) return rc;
+    if ((rc = ensure(ctx, vi.tile_counts, (size_t)n_tiles + 1))) return rc;
+    if (bits < 1) bits = 1;
+    if (bits > 32) bits = 32;
+    vi.bits_used = bits;
     size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys_a.p, ctx->keys_b.p, ctx->vals_a.p, ctx->vals_b.p, n, 0, 32, ctx->stream));
-    if ((rc = ensure(ctx, ctx->cub_tmp, tmp_bytes))) return rc;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, vi.keys_a.p, vi.keys_b.p, vi.vals_a.p, vi.vals_b.p, n, 0, 32, st));
+    if ((rc = ensure(ctx, vi.cub_tmp, tmp_bytes))) return rc;
 
     if (!have_minmax) {
-        k_init_enc<<<1, 32, 0, ctx->stream>>>(ctx->d_enc); KCHECK();
-        k_minmax<<<blocks_for(ctx, n, kMinMaxThreads * 4), kMinMaxThreads, 0, ctx->stream>>>(d_pts, n, ctx->d_enc); KCHECK();
+        k_init_enc<<<1, 32, 0, st>>>(vi.d_enc); KCHECK();
+        k_minmax<<<blocks_for(ctx, n, kMinMaxThreads * 4), kMinMaxThreads, 0, st>>>(d_pts, n, vi.d_enc); KCHECK();
     }
-    k_vg_params<<<1, 1, 0, ctx->stream>>>(ctx->d_enc, leaf, n, d_vp); KCHECK();
-    k_vg_keys<<<blocks_for(ctx, n, 256 * 4), 256, 0, ctx->stream>>>(d_pts, n, d_vp, ctx->keys_a.p, ctx->vals_a.p); KCHECK();
-    size_t tb = ctx->cub_tmp.cap;
-    CU(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, ctx->keys_a.p, ctx->keys_b.p, ctx->vals_a.p, ctx->vals_b.p, n, 0, 32, ctx->stream));
-    k_run_count<<<n_tiles, kRunThreads, 0, ctx->stream>>>(ctx->keys_b.p, n, ctx->tile_counts.p); KCHECK();
-    k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(ctx->tile_counts.p, n_tiles, d_count); KCHECK();
-    k_run_centroids<<<n_tiles, kRunThreads, 0, ctx->stream>>>(ctx->keys_b.p, ctx->vals_b.p, n, ctx->tile_counts.p, d_pts, out.p); KCHECK();
+    k_vg_params<<<1, 1, 0, st>>>(vi.d_enc, leaf, n, vi.d_vp); KCHECK();
+    k_vg_keys<<<blocks_for(ctx, n, 256 * 4), 256, 0, st>>>(d_pts, n, vi.d_vp, vi.keys_a.p, vi.vals_a.p); KCHECK();
+    size_t tb = vi.cub_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(vi.cub_tmp.p, tb, vi.keys_a.p, vi.keys_b.p, vi.vals_a.p, vi.vals_b.p, n, 0, bits, st));
+    k_run_count<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, n, vi.tile_counts.p); KCHECK();
+    k_scan_tiles<<<1, 1024, 0, st>>>(vi.tile_counts.p, n_tiles, vi.d_count); KCHECK();
+    k_run_centroids<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, vi.vals_b.p, n, vi.tile_counts.p, d_pts, out.p); KCHECK();
     return 0;
+}
+
+inline int next_bits_hint(int key_bits) {       // one bit of head-room, rounded up to whole 8-bit radix passes
+    int b = ((key_bits + 1 + 7) / 8) * 8;
+    return b > 32 ? 32 : b;
 }
 
 // Search-grid geometry from the local map's bounding box: cell edge 2^k >= 1 m, one cell of padding.
@@ -271,7 +298,7 @@ GridView grid_view(const liloc_ctx* ctx) {
 void tick(liloc_ctx* ctx, int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], ctx->stream); }
 
 // enqueue: keyframe descriptors -> transform + concat + bbox -> VoxelGrid; async D2H of {params, M}
-int localmap_enqueue(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf) {
+int localmap_enqueue(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf, int bits = 32) {
     if (K < 0 || (K > 0 && (!kf_ids || !poses6)) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap: bad arguments");
     int rc;
     ctx->have_map = false; ctx->have_grid = false; ctx->M = -1;
@@ -299,14 +326,17 @@ int localmap_enqueue(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int
         if ((rc = ensure(ctx, ctx->descs, (size_t)K))) return rc;
         if ((rc = ensure(ctx, ctx->raw, (size_t)total))) return rc;
         CU(cudaMemcpyAsync(ctx->descs.p, ctx->h_descs, (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, ctx->stream));
-        k_init_enc<<<1, 32, 0, ctx->stream>>>(ctx->d_enc); KCHECK();
-        k_assemble<<<blocks_for(ctx, total, kAsmTile), kMinMaxThreads, 0, ctx->stream>>>(ctx->arena.p, ctx->descs.p, K, (int)total, ctx->raw.p, ctx->d_enc); KCHECK();
+        ctx->stats.h2d_bytes += (long long)K * (long long)sizeof(KfDesc);
+        k_init_enc<<<1, 32, 0, ctx->stream>>>(ctx->vg_map.d_enc); KCHECK();
+        k_assemble<<<blocks_for(ctx, total, kAsmTile), kMinMaxThreads, 0, ctx->stream>>>(ctx->arena.p, ctx->descs.p, K, (int)total, ctx->raw.p, ctx->vg_map.d_enc); KCHECK();
     }
     tick(ctx, 1);
-    if ((rc = vg_run(ctx, ctx->raw.p, (int)total, leaf, true, ctx->map, ctx->d_M, ctx->d_map_vp))) return rc;
+    ctx->map_leaf_last = leaf;
+    if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->raw.p, (int)total, leaf, true, ctx->map, bits))) return rc;
     tick(ctx, 2);
-    if (total > 0) CU(cudaMemcpyAsync(&ctx->h_info->map_vp, ctx->d_map_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
+    if (total > 0) CU(cudaMemcpyAsync(&ctx->h_info->map_vp, ctx->vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&ctx->h_info->M, ctx->d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += (long long)sizeof(VgParams) + 4;
     ctx->have_map = true;
     return 0;
 }
@@ -317,18 +347,24 @@ int localmap_finish(liloc_ctx* ctx) {
     return grid_build(ctx, ctx->M, ctx->h_info->map_vp.mn, ctx->h_info->map_vp.mx);
 }
 
-int scan_enqueue(liloc_ctx* ctx, const liloc_point* pts, int n, bool on_device, float leaf) {
+int scan_enqueue(liloc_ctx* ctx, const liloc_point* pts, int n, bool on_device, float leaf, cudaStream_t st = nullptr, int bits = 32) {
+    if (!st) st = ctx->stream;
     if (n < 0 || (n > 0 && !pts) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad arguments");
     int rc;
     ctx->have_scan = false; ctx->Q_all = -1;
     const float4* src = reinterpret_cast<const float4*>(pts);
     if (!on_device && n > 0) {
         if ((rc = ensure(ctx, ctx->scan_raw, (size_t)n))) return rc;
-        CU(cudaMemcpyAsync(ctx->scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += (long long)n * (long long)sizeof(float4);
         src = ctx->scan_raw.p;
     }
-    if ((rc = vg_run(ctx, src, n, leaf, false, ctx->scan, ctx->d_Q, ctx->d_scan_vp))) return rc;
-    CU(cudaMemcpyAsync(&ctx->h_info->Q_all, ctx->d_Q, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->scan_src_last = src; ctx->scan_leaf_last = leaf;
+    if ((rc = vg_run(ctx, ctx->vg_scan, st, src, n, leaf, false, ctx->scan, bits))) return rc;
+    if (n > 0) CU(cudaMemcpyAsync(&ctx->h_info->scan_vp, ctx->vg_scan.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ctx->h_info->Q_all, ctx->d_Q, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ctx->stats.d2h_bytes += 4 + (long long)sizeof(VgParams);
+    ctx->n_scan_last = n;
     ctx->have_scan = true;
     return 0;
 }
@@ -344,6 +380,8 @@ int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     if (blocks < 1) blocks = 1;
     if ((rc = ensure(ctx, ctx->partial, (size_t)2 * blocks * kNSums))) return rc;
     CU(cudaMemcpyAsync(ctx->d_pose, pose6, 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += 24;
+    ctx->s2m_nq_last = nq;
     S2mArgs a{};
     a.scan = ctx->scan.p; a.q_all = ctx->d_Q; a.map = ctx->map.p; a.map_count = ctx->d_M;
     a.grid = grid_view(ctx);
@@ -353,6 +391,8 @@ int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     CU(cudaLaunchCooperativeKernel((void*)k_scan2map, dim3(blocks), dim3(kS2mThreads), args, 0, ctx->stream));
     ++ctx->launches;
     CU(cudaMemcpyAsync(&ctx->h_info->res, ctx->d_result, sizeof(S2mResult), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += (long long)sizeof(S2mResult);
+    ++ctx->stats.s2m_launches;
     return 0;
 }
 
@@ -361,6 +401,8 @@ int s2m_collect(liloc_ctx* ctx, float* pose6, liloc_s2m_result* res) {
     static_assert(sizeof(liloc_s2m_result) == 8 * sizeof(int) + 72 * sizeof(float), "result layout");
     if (res) std::memcpy(res, &r, sizeof(liloc_s2m_result));
     if (!r.skipped) std::memcpy(pose6, r.pose, 6 * sizeof(float));
+    ctx->stats.s2m_iters += r.iters;
+    ctx->stats.alg_bytes_s2m += (double)r.iters * (96.0 * ctx->s2m_nq_last + 216.0);
     return r.skipped ? LILOC_SKIPPED : LILOC_OK;
 }
 
@@ -392,11 +434,16 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     auto bail = [&](int rc) { g_create_error = c->err; liloc_destroy(c); return rc; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
     CUB_(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUB_(cudaMalloc(&c->d_enc, 6 * sizeof(unsigned)));
-    CUB_(cudaMalloc(&c->d_map_vp, sizeof(VgParams)));
-    CUB_(cudaMalloc(&c->d_scan_vp, sizeof(VgParams)));
-    CUB_(cudaMalloc(&c->d_M, sizeof(int)));
-    CUB_(cudaMalloc(&c->d_Q, sizeof(int)));
+    CUB_(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUB_(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (VgInst* vi : {&c->vg_map, &c->vg_scan}) {
+        CUB_(cudaMalloc(&vi->d_enc, 6 * sizeof(unsigned)));
+        CUB_(cudaMalloc(&vi->d_vp, sizeof(VgParams)));
+        CUB_(cudaMalloc(&vi->d_count, sizeof(int)));
+    }
+    c->d_M = c->vg_map.d_count;
+    c->d_Q = c->vg_scan.d_count;
     CUB_(cudaMalloc(&c->d_pose, 6 * sizeof(float)));
     CUB_(cudaMalloc(&c->d_state, sizeof(S2mState)));
     CUB_(cudaMalloc(&c->d_result, sizeof(S2mResult)));
@@ -417,8 +464,10 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     int rc;
     if ((rc = ensure(c, c->scan_raw, (size_t)scan_cap)) || (rc = ensure(c, c->scan, (size_t)scan_cap)) ||
         (rc = ensure(c, c->raw, (size_t)raw_cap)) || (rc = ensure(c, c->map, (size_t)raw_cap)) ||
-        (rc = ensure(c, c->keys_a, (size_t)raw_cap)) || (rc = ensure(c, c->keys_b, (size_t)raw_cap)) ||
-        (rc = ensure(c, c->vals_a, (size_t)raw_cap)) || (rc = ensure(c, c->vals_b, (size_t)raw_cap)) ||
+        (rc = ensure(c, c->vg_map.keys_a, (size_t)raw_cap)) || (rc = ensure(c, c->vg_map.keys_b, (size_t)raw_cap)) ||
+        (rc = ensure(c, c->vg_map.vals_a, (size_t)raw_cap)) || (rc = ensure(c, c->vg_map.vals_b, (size_t)raw_cap)) ||
+        (rc = ensure(c, c->vg_scan.keys_a, (size_t)scan_cap)) || (rc = ensure(c, c->vg_scan.keys_b, (size_t)scan_cap)) ||
+        (rc = ensure(c, c->vg_scan.vals_a, (size_t)scan_cap)) || (rc = ensure(c, c->vg_scan.vals_b, (size_t)scan_cap)) ||
         (rc = ensure(c, c->arena, (size_t)raw_cap)) || (rc = ensure(c, c->cpts, (size_t)raw_cap)) ||
         (rc = ensure(c, c->partial, (size_t)2 * c->s2m_max_blocks * kNSums)))
         return bail(rc);
@@ -432,8 +481,14 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(c->arena.p); fr(c->raw.p); fr(c->map.p); fr(c->descs.p); fr(c->scan_raw.p); fr(c->scan.p);
-    fr(c->keys_a.p); fr(c->keys_b.p); fr(c->vals_a.p); fr(c->vals_b.p); fr(c->cub_tmp.p); fr(c->tile_counts.p);
-    fr(c->d_enc); fr(c->d_map_vp); fr(c->d_scan_vp); fr(c->d_M); fr(c->d_Q);
+    for (VgInst* vi : {&c->vg_map, &c->vg_scan}) {
+        fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->cub_tmp.p); fr(vi->tile_counts.p);
+        fr(vi->d_enc); fr(vi->d_vp); fr(vi->d_count);
+    }
+    fr(c->tile_counts.p);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     fr(c->cell_counts.p); fr(c->cell_start.p); fr(c->cell_cursor.p); fr(c->cpts.p);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
@@ -505,8 +560,8 @@ int liloc_localmap_set(liloc_ctx* ctx, const liloc_point* pts, int n, float leaf
     if ((rc = ensure(ctx, ctx->raw, (size_t)(n > 0 ? n : 1)))) return rc;
     if (n > 0) CU(cudaMemcpyAsync(ctx->raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_raw = n;
-    if ((rc = vg_run(ctx, ctx->raw.p, n, leaf, false, ctx->map, ctx->d_M, ctx->d_map_vp))) return rc;
-    if (n > 0) CU(cudaMemcpyAsync(&ctx->h_info->map_vp, ctx->d_map_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->raw.p, n, leaf, false, ctx->map, 32))) return rc;
+    if (n > 0) CU(cudaMemcpyAsync(&ctx->h_info->map_vp, ctx->vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&ctx->h_info->M, ctx->d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_map = true;
@@ -579,10 +634,32 @@ int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K
     if (!pose6) return fail(ctx, LILOC_ERR_ARG, "frame: null pose");
     const liloc_s2m_opts* o = opts ? opts : &kDefaultOpts;
     int rc;
-    if ((rc = localmap_enqueue(ctx, kf_ids, kf_poses6, K, map_leaf))) return rc;    // ev 0,1,2
-    if ((rc = scan_enqueue(ctx, scan, n_scan, scan_on_device != 0, scan_leaf))) return rc;
+    // fork: the scan branch (H2D + VoxelGrid) runs on stream2 while the map branch runs on the main stream
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
+    if ((rc = scan_enqueue(ctx, scan, n_scan, scan_on_device != 0, scan_leaf, ctx->stream2, ctx->vg_scan.bits_hint))) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
+    CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    if ((rc = localmap_enqueue(ctx, kf_ids, kf_poses6, K, map_leaf, ctx->vg_map.bits_hint))) return rc;    // ev 0,1,2
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));                                              // join
     tick(ctx, 3);
     CU(cudaStreamSynchronize(ctx->stream));          // sync 1: M, bounding box, Q_all
+    // The sorts used the previous frame's key width; if this frame needed more bits, redo with the full 32.
+    if (ctx->n_raw > 0 && ctx->h_info->map_vp.key_bits > ctx->vg_map.bits_used) {
+        ++ctx->sort_redos;
+        if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->raw.p, ctx->n_raw, map_leaf, true, ctx->map, 32))) return rc;
+        CU(cudaMemcpyAsync(&ctx->h_info->M, ctx->d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_scan > 0 && ctx->h_info->scan_vp.key_bits > ctx->vg_scan.bits_used) {
+        ++ctx->sort_redos;
+        if ((rc = vg_run(ctx, ctx->vg_scan, ctx->stream, ctx->scan_src_last, n_scan, scan_leaf, true, ctx->scan, 32))) return rc;
+        CU(cudaMemcpyAsync(&ctx->h_info->Q_all, ctx->d_Q, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->n_raw > 0) ctx->vg_map.bits_hint = next_bits_hint(ctx->h_info->map_vp.key_bits);
+    if (n_scan > 0) ctx->vg_scan.bits_hint = next_bits_hint(ctx->h_info->scan_vp.key_bits);
     ctx->Q_all = ctx->h_info->Q_all;
     if ((rc = localmap_finish(ctx))) return rc;
     tick(ctx, 4);
@@ -593,11 +670,17 @@ int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K
         liloc_timing& t = ctx->last_timing;
         cudaEventElapsedTime(&t.assemble_ms, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&t.map_voxel_ms, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&t.scan_ms, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&t.scan_ms, ctx->ev[6], ctx->ev[7]);
         cudaEventElapsedTime(&t.grid_ms, ctx->ev[3], ctx->ev[4]);
         cudaEventElapsedTime(&t.s2m_ms, ctx->ev[4], ctx->ev[5]);
         cudaEventElapsedTime(&t.total_ms, ctx->ev[0], ctx->ev[5]);
+        liloc_stats& st = ctx->stats;
+        st.assemble_ms += t.assemble_ms; st.map_voxel_ms += t.map_voxel_ms; st.scan_ms += t.scan_ms;
+        st.grid_ms += t.grid_ms; st.s2m_ms += t.s2m_ms; st.total_ms += t.total_ms;
     }
+    ++ctx->stats.frames;
+    ctx->stats.alg_bytes_map += 16.0 * ctx->n_raw + 16.0 * (ctx->M > 0 ? ctx->M : 0);
+    ctx->stats.alg_bytes_scan += 16.0 * ctx->n_scan_last + 16.0 * (ctx->Q_all > 0 ? ctx->Q_all : 0);
     return s2m_collect(ctx, pose6, res);
 }
 
@@ -609,7 +692,13 @@ int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, li
     DevBuf<float4> outb; outb.p = ctx->tmp_pts.p + n; outb.cap = (size_t)(n > 0 ? n : 1);
     if (n > 0) CU(cudaMemcpyAsync(ctx->tmp_pts.p, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = ensure(ctx, ctx->tmp_i, 1))) return rc;
-    if ((rc = vg_run(ctx, ctx->tmp_pts.p, n, leaf, false, outb, ctx->tmp_i.p, ctx->d_scan_vp))) return rc;
+    {   // run on the scan instance's scratch but keep its result count (d_Q) untouched
+        int* keep = ctx->vg_scan.d_count;
+        ctx->vg_scan.d_count = ctx->tmp_i.p;
+        rc = vg_run(ctx, ctx->vg_scan, ctx->stream, ctx->tmp_pts.p, n, leaf, false, outb, 32);
+        ctx->vg_scan.d_count = keep;
+        if (rc) return rc;
+    }
     int m = 0;
     CU(cudaMemcpyAsync(&m, ctx->tmp_i.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -630,7 +719,7 @@ int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries, int nq, int* idx5, fl
     if ((rc = ensure(ctx, ctx->tmp_i, (size_t)nq * 6))) return rc;
     if ((rc = ensure(ctx, ctx->tmp_f, (size_t)nq * 5))) return rc;
     CU(cudaMemcpyAsync(ctx->tmp_pts.p, queries, (size_t)nq * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    k_knn5<<<blocks_for(ctx, (long long)nq * 32, 256), 256, 0, ctx->stream>>>(ctx->tmp_pts.p, nq, grid_view(ctx), ctx->tmp_i.p, ctx->tmp_f.p, ctx->tmp_i.p + (size_t)nq * 5); KCHECK();
+    k_knn5<<<blocks_for(ctx, (long long)nq * kKnnLanes, 256), 256, 0, ctx->stream>>>(ctx->tmp_pts.p, nq, grid_view(ctx), ctx->tmp_i.p, ctx->tmp_f.p, ctx->tmp_i.p + (size_t)nq * 5); KCHECK();
     CU(cudaMemcpyAsync(idx5, ctx->tmp_i.p, (size_t)nq * 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(found, ctx->tmp_i.p + (size_t)nq * 5, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(d2_5, ctx->tmp_f.p, (size_t)nq * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -718,6 +807,29 @@ int liloc_set_timing(liloc_ctx* ctx, int enabled) {
 }
 
 long long liloc_kernel_launches(const liloc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int liloc_last_clocks(liloc_ctx* ctx, int* out, int max_iters) {
+    if (!ctx || !out || max_iters < 0) return LILOC_ERR_ARG;
+    const int n = max_iters < 32 ? max_iters : 32;
+    std::memcpy(out, ctx->h_info->res.clk, (size_t)n * 8 * sizeof(int));
+    return n;
+}
+
+int liloc_stats_get(const liloc_ctx* ctx, liloc_stats* out) {
+    if (!ctx || !out) return LILOC_ERR_ARG;
+    *out = ctx->stats;
+    out->launches = ctx->launches - ctx->launches_at_reset;
+    return LILOC_OK;
+}
+
+int liloc_stats_reset(liloc_ctx* ctx) {
+    if (!ctx) return LILOC_ERR_ARG;
+    ctx->stats = liloc_stats{};
+    ctx->launches_at_reset = ctx->launches;
+    return LILOC_OK;
+}
+
+void* liloc_stream(liloc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int liloc_last_trace(liloc_ctx* ctx, float* out, int max_iters) {
     if (!ctx || !out || max_iters < 0) return LILOC_ERR_ARG;

@@ -25,10 +25,11 @@ namespace liloc {
 
 namespace cg = cooperative_groups;
 
-constexpr int kS2mThreads = 512;
+constexpr int kS2mThreads = 256;
 constexpr int kS2mWarps = kS2mThreads / 32;
-constexpr int kQPB = 32;                 // queries per tile
+constexpr int kQPB = kS2mThreads / kKnnLanes;   // queries per tile: one group of kKnnLanes lanes per query
 constexpr int kNSums = 28;               // 21 (upper J^T J) + 6 (J^T r) + 1 (count)
+constexpr int kRedGroups = kS2mThreads / kNSums;   // 18 groups of 28 threads for the cross-block reduction
 
 struct S2mState {                        // members isDegenerate / matP (src/mapOptmization.cpp:90-91)
     int is_degenerate;
@@ -41,6 +42,7 @@ struct S2mResult {                       // device mirror of liloc_s2m_result (s
     float AtA0[36];
     float pose[6];
     float trace[32][16];                 // per iteration: n_sel, X[6], pose_after[6], AtB[0..2]
+    int clk[32][8];                      // LILOC_S2M_PROFILE: SM-clock deltas of the iteration phases (block 0)
 };
 
 struct S2mArgs {
@@ -229,37 +231,52 @@ __host__ __device__ inline void solve6_qr(const float* A_in, const float* b_in, 
 #pragma unroll
         for (int j = 0; j < 6; ++j) A[i][j] = A_in[i * 6 + j];
     }
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         float tailSq = 0.f;
+#pragma unroll
         for (int i = k + 1; i < 6; ++i) tailSq += A[i][k] * A[i][k];
         const float c0 = A[k][k];
-        if (tailSq <= 1.17549435e-38f) continue;
-        float beta = sqrtf(c0 * c0 + tailSq);
-        if (c0 >= 0.f) beta = -beta;
-        const float den = c0 - beta;
-        float v[6];
-        for (int i = k + 1; i < 6; ++i) v[i] = A[i][k] / den;
-        const float tau = (beta - c0) / beta;
-        A[k][k] = beta;
-        for (int i = k + 1; i < 6; ++i) A[i][k] = 0.f;
-        for (int j = k + 1; j < 6; ++j) {
+        if (tailSq > 1.17549435e-38f) {
+            float beta = sqrtf(c0 * c0 + tailSq);
+            if (c0 >= 0.f) beta = -beta;
+            const float den = c0 - beta;
+            float v[6];
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) v[i] = A[i][k] / den;
+            const float tau = (beta - c0) / beta;
+            A[k][k] = beta;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) A[i][k] = 0.f;
+#pragma unroll
+            for (int j = k + 1; j < 6; ++j) {
+                float tmp = 0.f;
+#pragma unroll
+                for (int i = k + 1; i < 6; ++i) tmp += v[i] * A[i][j];
+                tmp += A[k][j];
+                A[k][j] -= tau * tmp;
+#pragma unroll
+                for (int i = k + 1; i < 6; ++i) A[i][j] -= (tau * v[i]) * tmp;
+            }
             float tmp = 0.f;
-            for (int i = k + 1; i < 6; ++i) tmp += v[i] * A[i][j];
-            tmp += A[k][j];
-            A[k][j] -= tau * tmp;
-            for (int i = k + 1; i < 6; ++i) A[i][j] -= (tau * v[i]) * tmp;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) tmp += v[i] * b[i];
+            tmp += b[k];
+            b[k] -= tau * tmp;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) b[i] -= (tau * v[i]) * tmp;
         }
-        float tmp = 0.f;
-        for (int i = k + 1; i < 6; ++i) tmp += v[i] * b[i];
-        tmp += b[k];
-        b[k] -= tau * tmp;
-        for (int i = k + 1; i < 6; ++i) b[i] -= (tau * v[i]) * tmp;
     }
+    float xr[6];
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         float s = b[i];
-        for (int j = i + 1; j < 6; ++j) s -= A[i][j] * x[j];
-        x[i] = s / A[i][i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) s -= A[i][j] * xr[j];
+        xr[i] = s / A[i][i];
     }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xr[i];
 }
 
 // cv::eigen stand-in: cyclic Jacobi, float32, eigenvalues descending, eigenvectors as rows of V.
@@ -345,6 +362,40 @@ __host__ __device__ inline int degeneracy_projector(const float* AtA, float* mat
     return degenerate;
 }
 
+// True when every eigenvalue of the symmetric 6x6 A is provably above `bound`: Cholesky of (A - bound*I)
+// in double succeeds.  Used to skip the Jacobi sweep in the common non-degenerate case: with
+// bound = 100 + 1e-4 * max|diag| the float32 Jacobi (error ~1e-6 * |A|) would reach the same decision.
+__host__ __device__ inline bool eigenvalues_above(const float* A, double bound) {
+    double L[6][6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = (double)A[j * 6 + j] - bound;
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0)) return false;
+        const double inv = 1.0 / sqrt(d);
+        L[j][j] = d;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = (double)A[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v * inv;
+        }
+    }
+    return true;
+}
+
+// T (3x4) and the LOAM trig set from sc = {sin roll, sin pitch, sin yaw, cos roll, cos pitch, cos yaw}
+// (each evaluated in double and rounded to float; identical to pose_to_T / pose_trig).
+LILOC_DEV void T_from_sincos(const float* pose6, const float* sc, float* T) {
+    const float A = sc[5], B = sc[2], C = sc[4], D = sc[1], E = sc[3], F = sc[0];
+    const float DE = D * E, DF = D * F;
+    T[0] = A * C;  T[1] = A * DF - B * E;  T[2]  = B * F + A * DE;  T[3]  = pose6[3];
+    T[4] = B * C;  T[5] = A * E + B * DF;  T[6]  = B * DE - A * F;  T[7]  = pose6[4];
+    T[8] = -D;     T[9] = C * F;           T[10] = C * E;           T[11] = pose6[5];
+}
+
 // which (a, c) pair of the row feeds sum t: t < 21 upper triangle row-major, 21..26 (a, rhs), 27 count
 __constant__ unsigned char c_sum_a[kNSums] = {0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5, 0,1,2,3,4,5, 7};
 __constant__ unsigned char c_sum_c[kNSums] = {0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5, 6,6,6,6,6,6, 7};
@@ -352,52 +403,49 @@ __constant__ unsigned char c_sum_c[kNSums] = {0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3
 struct S2mShared {
     float T[12];
     float pose[6];
+    float sc[6];
     Trig trig;
-    int idx[kQPB][5];
-    float d4[kQPB];
     float row[kQPB][8];        // 6 Jacobian entries, rhs, valid (1.0 / 0.0)
     double sums[kNSums];
+    double red[kRedGroups][kNSums];
+    float X[6];
+    long long dbg[4];
     float matP[36];
     int is_degenerate;
     int done;                  // 0 continue, 1 converged, 2 too few
     int n_sel;
 };
 
-// Residual rows for one tile of queries into shared memory (phases A and B).
-LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, const int nq, const int q_all) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // A: warp-cooperative kNN
-    for (int s = warp; s < kQPB; s += kS2mWarps) {
-        const int qk = tile * kQPB + s;
-        if (qk < nq) {
-            const float4 ori = __ldg(&a.scan[qk * a.stride]);
-            const float4 sel = apply_T(sh.T, ori);
-            const Knn5 r = knn5_warp(a.grid, sel, lane);
-            if (lane < 5) sh.idx[s][lane] = (lane == 0) ? r.i[0] : (lane == 1) ? r.i[1] : (lane == 2) ? r.i[2] : (lane == 3) ? r.i[3] : r.i[4];
-            if (lane == 0) sh.d4[s] = (r.i[4] != 0x7fffffff) ? r.d[4] : 3.4e38f;
-        }
-    }
-    __syncthreads();
-    // B: one thread per query
-    if (threadIdx.x < kQPB) {
-        const int s = threadIdx.x;
-        const int qk = tile * kQPB + s;
+// Residual rows for one tile of queries into shared memory (phases A and B).  A group of kKnnLanes lanes
+// owns one query: cooperative kNN, then lane 0 of the group does the plane fit and the Jacobian row.
+// Returns through coeff_out/flag_out as well when they are non-null (k_surf_pass).
+LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, const int nq,
+                             float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
+    const int s = threadIdx.x / kKnnLanes, sub = threadIdx.x % kKnnLanes;
+    const int qk = tile * kQPB + s;
+    const bool active = qk < nq;
+    float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
+    if (active) { ori = __ldg(&a.scan[qk * a.stride]); sel = apply_T(sh.T, ori); }
+#ifdef LILOC_S2M_PROFILE
+    if (threadIdx.x == 0) sh.dbg[0] = clock64();
+#endif
+    const Knn5 r = knn5_group<kKnnLanes>(a.grid, sel, sub, active);
+#ifdef LILOC_S2M_PROFILE
+    if (threadIdx.x == 0) sh.dbg[1] = clock64();
+#endif
+    if (sub == 0) {
         float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float valid = 0.f;
-        if (qk < nq) {
-            const float d4 = sh.d4[s];
-            if (d4 < 1.0f) {
-                const float4 ori = __ldg(&a.scan[qk * a.stride]);
-                const float4 sel = apply_T(sh.T, ori);
-                float nb[5][3];
+        float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && r.i[4] != 0x7fffffff && r.d[4] < 1.0f) {
+            float nb[5][3];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const float4 p = __ldg(&a.map[sh.idx[s][j]]);
-                    nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
-                }
-                float4 coeff;
-                if (surf_residual(nb, d4, ori, sel, &coeff)) { jacobian_row(sh.trig, ori, coeff, row); valid = 1.f; }
+            for (int j = 0; j < 5; ++j) {
+                const float4 p = __ldg(&a.map[r.i[j]]);
+                nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
             }
+            float4 c;
+            if (surf_residual(nb, r.d[4], ori, sel, &c)) { coeff = c; jacobian_row(sh.trig, ori, c, row); valid = 1.f; }
         }
         if (valid == 0.f) {
 #pragma unroll
@@ -406,37 +454,63 @@ LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, co
 #pragma unroll
         for (int j = 0; j < 7; ++j) sh.row[s][j] = row[j];
         sh.row[s][7] = valid;
+        if (coeff_out && active) { coeff_out[qk * a.stride] = coeff; flag_out[qk * a.stride] = valid != 0.f ? 1 : 0; }
     }
+#ifdef LILOC_S2M_PROFILE
+    if (threadIdx.x == 0) sh.dbg[2] = clock64();
+#endif
     __syncthreads();
-    (void)q_all;
+#ifdef LILOC_S2M_PROFILE
+    if (threadIdx.x == 0) sh.dbg[3] = clock64();
+#endif
 }
 
-__global__ void __launch_bounds__(kS2mThreads, 1) k_scan2map(S2mArgs a) {
+// sin/cos of the three angles on six lanes in parallel, then T and the trig set by one thread.
+LILOC_DEV void s2m_refresh_transform(S2mShared& sh) {
+    if (threadIdx.x < 6) {
+        const double ang = (double)sh.pose[threadIdx.x % 3];
+        sh.sc[threadIdx.x] = (float)(threadIdx.x < 3 ? sin(ang) : cos(ang));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T_from_sincos(sh.pose, sh.sc, sh.T);
+        sh.trig.srx = sh.sc[2]; sh.trig.crx = sh.sc[5]; sh.trig.sry = sh.sc[1]; sh.trig.cry = sh.sc[4];
+        sh.trig.srz = sh.sc[0]; sh.trig.crz = sh.sc[3];
+    }
+    __syncthreads();
+}
+
+#ifndef LILOC_S2M_MINBLOCKS
+#define LILOC_S2M_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S2mArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ S2mShared sh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q_all = *a.q_all;
     const int M = *a.map_count;
     const int nq = (q_all + a.stride - 1) / a.stride;
     const int n_tiles = (nq + kQPB - 1) / kQPB;
 
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < 6; ++k) sh.pose[k] = a.pose_io[k];
-        pose_to_T(sh.pose, sh.T);
-        sh.trig = pose_trig(sh.pose);
-        sh.is_degenerate = a.state->is_degenerate;
-        for (int k = 0; k < 36; ++k) sh.matP[k] = a.state->matP[k];
-        sh.done = 0; sh.n_sel = 0;
-    }
+    if (threadIdx.x < 6) sh.pose[threadIdx.x] = a.pose_io[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 68) sh.matP[threadIdx.x - 32] = a.state->matP[threadIdx.x - 32];
+    if (threadIdx.x == 0) { sh.is_degenerate = a.state->is_degenerate; sh.done = 0; sh.n_sel = 0; }
     __syncthreads();
+    s2m_refresh_transform(sh);
 
     const bool skipped = !(q_all > a.min_points);             // :1187
     int iters = 0, converged = 0, too_few = 0;
+#ifdef LILOC_S2M_PROFILE
+    long long clk[8];
+#define S2M_CLK(i) if (blockIdx.x == 0 && threadIdx.x == 0) clk[i] = clock64();
+#else
+#define S2M_CLK(i)
+#endif
     if (!skipped) {
         for (int iter = 0; iter < a.max_iters; ++iter) {
+            S2M_CLK(0)
             double acc = 0.0;                               // threads < kNSums: running sum over this block's tiles
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                s2m_tile_rows(a, sh, tile, nq, q_all);
+                s2m_tile_rows(a, sh, tile, nq, nullptr, nullptr);
                 if (threadIdx.x < kNSums) {                 // C
                     const int ia = c_sum_a[threadIdx.x], ic = c_sum_c[threadIdx.x];
 #pragma unroll 8
@@ -444,39 +518,80 @@ __global__ void __launch_bounds__(kS2mThreads, 1) k_scan2map(S2mArgs a) {
                 }
                 __syncthreads();
             }
+            S2M_CLK(1)
             double* part = a.partial + (size_t)(iter & 1) * gridDim.x * kNSums;
             if (threadIdx.x < kNSums) part[(size_t)blockIdx.x * kNSums + threadIdx.x] = acc;
             grid.sync();
-            // D: fixed-order reduction of the block partials, identical in every block
-            for (int t = warp; t < kNSums; t += kS2mWarps) {
-                double s = 0.0;
-                for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&part[(size_t)b * kNSums + t]);
+            S2M_CLK(2)
+            // D: fixed-order reduction of the block partials, identical in every block.  Thread (j, c) sums
+            // blocks j, j + kRedGroups, ... of column c (coalesced 224-byte rows, loads batched ahead of
+            // the dependent adds), then column c adds its kRedGroups group sums in order.
+            if (threadIdx.x < kRedGroups * kNSums) {
+                const int c = threadIdx.x % kNSums, j = threadIdx.x / kNSums;
+                const int nb = (int)gridDim.x;
+                double sacc = 0.0;
+                int b = j;
+                for (; b + 3 * kRedGroups < nb; b += 4 * kRedGroups) {
+                    const double v0 = __ldcg(&part[(size_t)b * kNSums + c]);
+                    const double v1 = __ldcg(&part[(size_t)(b + kRedGroups) * kNSums + c]);
+                    const double v2 = __ldcg(&part[(size_t)(b + 2 * kRedGroups) * kNSums + c]);
+                    const double v3 = __ldcg(&part[(size_t)(b + 3 * kRedGroups) * kNSums + c]);
+                    sacc += v0; sacc += v1; sacc += v2; sacc += v3;
+                }
+                for (; b < nb; b += kRedGroups) sacc += __ldcg(&part[(size_t)b * kNSums + c]);
+                sh.red[j][c] = sacc;
+            }
+            __syncthreads();
+            if (threadIdx.x < kNSums) {
+                double sacc = 0.0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += shfl_xor_d(s, o);
-                if (lane == 0) sh.sums[t] = s;
+                for (int j = 0; j < kRedGroups; ++j) sacc += sh.red[j][threadIdx.x];
+                sh.sums[threadIdx.x] = sacc;
+            }
+            __syncthreads();
+            S2M_CLK(3)
+            const int n_sel = (int)sh.sums[27];
+            const bool few = n_sel < a.min_sel;             // :1079-1082 (pose unchanged: later iterations identical)
+            if (!few && (threadIdx.x == 0 || (threadIdx.x == 32 && iter == 0))) {
+                float AtA[36];
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = r; c < 6; ++c) { AtA[r * 6 + c] = AtA[c * 6 + r] = (float)sh.sums[k++]; }
+                if (threadIdx.x == 0) {                     // cv::solve(DECOMP_QR), :1130
+                    float AtB[6];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) AtB[r] = (float)sh.sums[21 + r];
+                    solve6_qr(AtA, AtB, sh.X);
+                    if (iter == 0 && blockIdx.x == 0) for (int i = 0; i < 36; ++i) a.result->AtA0[i] = AtA[i];
+                } else {                                    // iteration 0, second warp: degeneracy check :1132-1154
+                    float mxd = AtA[0];
+#pragma unroll
+                    for (int i = 1; i < 6; ++i) mxd = fmaxf(mxd, AtA[i * 7]);
+                    if (eigenvalues_above(AtA, 100.0 + 1e-4 * (double)mxd)) {
+                        sh.is_degenerate = 0;               // all eigenvalues >= 100: matP is never read
+                        for (int i = 0; i < 36; ++i) sh.matP[i] = (i % 7 == 0) ? 1.f : 0.f;
+                    } else {
+                        sh.is_degenerate = degeneracy_projector(AtA, sh.matP);
+                    }
+                }
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                const int n_sel = (int)sh.sums[27];
                 sh.n_sel = n_sel;
-                if (n_sel < a.min_sel) {
-                    sh.done = 2;                            // :1079-1082 (pose unchanged: later iterations identical)
+                if (few) {
+                    sh.done = 2;
                 } else {
-                    float AtA[36], AtB[6], X[6];
-                    int k = 0;
-                    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { AtA[r * 6 + c] = AtA[c * 6 + r] = (float)sh.sums[k++]; }
-                    for (int r = 0; r < 6; ++r) AtB[r] = (float)sh.sums[21 + r];
-                    solve6_qr(AtA, AtB, X);                                             // :1130
-                    if (iter == 0) {
-                        sh.is_degenerate = degeneracy_projector(AtA, sh.matP);          // :1132-1154
-                        if (blockIdx.x == 0) for (int i = 0; i < 36; ++i) a.result->AtA0[i] = AtA[i];
-                    }
+                    float X[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) X[i] = sh.X[i];
                     if (sh.is_degenerate) {                                             // :1156-1160
                         float X2[6];
                         for (int i = 0; i < 6; ++i) {
-                            double s = 0.0;
-                            for (int j = 0; j < 6; ++j) s += (double)sh.matP[i * 6 + j] * (double)X[j];
-                            X2[i] = (float)s;
+                            double sd = 0.0;
+                            for (int j = 0; j < 6; ++j) sd += (double)sh.matP[i * 6 + j] * (double)X[j];
+                            X2[i] = (float)sd;
                         }
                         for (int i = 0; i < 6; ++i) X[i] = X2[i];
                     }
@@ -485,18 +600,28 @@ __global__ void __launch_bounds__(kS2mThreads, 1) k_scan2map(S2mArgs a) {
                         float* tr = a.result->trace[iter];
                         tr[0] = (float)n_sel;
                         for (int i = 0; i < 6; ++i) { tr[1 + i] = X[i]; tr[7 + i] = sh.pose[i]; }
-                        tr[13] = AtB[0]; tr[14] = AtB[1]; tr[15] = AtB[2];
+                        tr[13] = (float)sh.sums[21]; tr[14] = (float)sh.sums[22]; tr[15] = (float)sh.sums[23];
                     }
                     const float r0 = X[0] * 57.29578f, r1 = X[1] * 57.29578f, r2 = X[2] * 57.29578f;
                     const float t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
                     const float deltaR = (float)sqrt((double)r0 * (double)r0 + (double)r1 * (double)r1 + (double)r2 * (double)r2);
                     const float deltaT = (float)sqrt((double)t0 * (double)t0 + (double)t1 * (double)t1 + (double)t2 * (double)t2);
                     if ((double)deltaR < 0.05 && (double)deltaT < 0.05) sh.done = 1;    // :1177
-                    pose_to_T(sh.pose, sh.T);
-                    sh.trig = pose_trig(sh.pose);
                 }
             }
             __syncthreads();
+            S2M_CLK(4)
+            if (sh.done == 0) s2m_refresh_transform(sh);
+            S2M_CLK(5)
+#ifdef LILOC_S2M_PROFILE
+            if (blockIdx.x == 0 && threadIdx.x == 0 && iter < 32)
+            {
+                for (int i = 0; i < 5; ++i) a.result->clk[iter][i] = (int)(clk[i + 1] - clk[i]);
+                a.result->clk[iter][5] = (int)(sh.dbg[1] - sh.dbg[0]);     // kNN
+                a.result->clk[iter][6] = (int)(sh.dbg[2] - sh.dbg[1]);     // fit + row (thread 0)
+                a.result->clk[iter][7] = (int)(sh.dbg[3] - sh.dbg[2]);     // wait for the slowest group
+            }
+#endif
             iters = iter + 1;
             if (sh.done == 1) { converged = 1; break; }
             if (sh.done == 2) { too_few = 1; break; }
@@ -513,56 +638,19 @@ __global__ void __launch_bounds__(kS2mThreads, 1) k_scan2map(S2mArgs a) {
     }
 }
 
-// surfOptimization at a fixed pose for the residual-level parity test (liloc_surf_pass).
+// surfOptimization at a fixed pose for the residual-level parity test (liloc_surf_pass): the same tile
+// function as the registration kernel, with the coefficients written out instead of reduced.
 __global__ void __launch_bounds__(kS2mThreads)
 k_surf_pass(S2mArgs a, const float* __restrict__ pose6, float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
     __shared__ S2mShared sh;
     const int q_all = *a.q_all;
     const int nq = (q_all + a.stride - 1) / a.stride;
     const int n_tiles = (nq + kQPB - 1) / kQPB;
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < 6; ++k) sh.pose[k] = pose6[k];
-        pose_to_T(sh.pose, sh.T);
-        sh.trig = pose_trig(sh.pose);
-    }
+    if (threadIdx.x < 6) sh.pose[threadIdx.x] = pose6[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s2m_refresh_transform(sh);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int s = warp; s < kQPB; s += kS2mWarps) {
-            const int qk = tile * kQPB + s;
-            if (qk < nq) {
-                const float4 ori = __ldg(&a.scan[qk * a.stride]);
-                const float4 sel = apply_T(sh.T, ori);
-                const Knn5 r = knn5_warp(a.grid, sel, lane);
-                if (lane < 5) sh.idx[s][lane] = (lane == 0) ? r.i[0] : (lane == 1) ? r.i[1] : (lane == 2) ? r.i[2] : (lane == 3) ? r.i[3] : r.i[4];
-                if (lane == 0) sh.d4[s] = (r.i[4] != 0x7fffffff) ? r.d[4] : 3.4e38f;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < kQPB) {
-            const int s = threadIdx.x;
-            const int qk = tile * kQPB + s;
-            if (qk < nq) {
-                const int i = qk * a.stride;
-                float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-                unsigned char ok = 0;
-                const float d4 = sh.d4[s];
-                if (d4 < 1.0f) {
-                    const float4 ori = __ldg(&a.scan[i]);
-                    const float4 sel = apply_T(sh.T, ori);
-                    float nb[5][3];
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const float4 p = __ldg(&a.map[sh.idx[s][j]]);
-                        nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
-                    }
-                    float4 c;
-                    if (surf_residual(nb, d4, ori, sel, &c)) { coeff = c; ok = 1; }
-                }
-                coeff_out[i] = coeff;
-                flag_out[i] = ok;
-            }
-        }
+        s2m_tile_rows(a, sh, tile, nq, coeff_out, flag_out);
         __syncthreads();
     }
 }

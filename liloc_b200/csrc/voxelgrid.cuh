@@ -159,7 +159,7 @@ k_vg_keys(const float4* __restrict__ pts, int n, const VgParams* __restrict__ vp
 
 // ---- run heads -> ranks -> centroids ------------------------------------------------------------
 constexpr int kRunThreads = 256;
-constexpr int kRunPerThread = 8;
+constexpr int kRunPerThread = 4;
 constexpr int kRunTile = kRunThreads * kRunPerThread;
 
 LILOC_DEV int block_exclusive_scan_256(int v, int* total) {   // 256 threads
@@ -181,19 +181,19 @@ LILOC_DEV int block_exclusive_scan_256(int v, int* total) {   // 256 threads
 // number of run heads (sorted_keys[i] != sorted_keys[i-1]) per tile
 __global__ void __launch_bounds__(kRunThreads)
 k_run_count(const unsigned* __restrict__ skeys, int n, int* __restrict__ tile_counts) {
-    const int base = blockIdx.x * kRunTile + threadIdx.x * kRunPerThread;
+    const int base = blockIdx.x * kRunTile;
     int c = 0;
 #pragma unroll
     for (int j = 0; j < kRunPerThread; ++j) {
-        const int i = base + j;
-        if (i < n) c += (i == 0 || skeys[i] != skeys[i - 1]) ? 1 : 0;
+        const int i = base + j * kRunThreads + threadIdx.x;
+        if (i < n) c += (i == 0 || __ldg(&skeys[i]) != __ldg(&skeys[i - 1])) ? 1 : 0;
     }
     int total;
     block_exclusive_scan_256(c, &total);
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
-// exclusive scan of up to 1024*64 tile counts by one block; total -> *total_out
+// exclusive scan of the tile counts by one block; total -> *total_out
 __global__ void __launch_bounds__(1024)
 k_scan_tiles(int* __restrict__ tile_counts, int n_tiles, int* __restrict__ total_out) {
     __shared__ int s_w[32];
@@ -220,18 +220,38 @@ k_scan_tiles(int* __restrict__ tile_counts, int n_tiles, int* __restrict__ total
     if (threadIdx.x == 0) *total_out = s_carry;
 }
 
-// One centroid per run, written at the run's rank (ascending voxel index).  The thread that owns a
-// run head walks the run sequentially: float sums in ascending source index (the canonical order).
+// One centroid per run, written at the run's rank (ascending voxel index).  The tile's points are
+// gathered into shared memory by all threads in parallel (coalesced key/index loads, 16-byte point
+// gathers); the thread that owns a run head then walks the run sequentially out of shared memory:
+// float sums in ascending source index (the canonical order).  Runs that cross the tile end continue
+// from global memory.
 __global__ void __launch_bounds__(kRunThreads)
 k_run_centroids(const unsigned* __restrict__ skeys, const unsigned* __restrict__ svals, int n,
                 const int* __restrict__ tile_offsets, const float4* __restrict__ pts, float4* __restrict__ out) {
-    const int base = blockIdx.x * kRunTile + threadIdx.x * kRunPerThread;
+    __shared__ unsigned s_key[kRunTile];
+    __shared__ float4 s_pt[kRunTile];
+    __shared__ unsigned s_prev;
+    const int base = blockIdx.x * kRunTile;
+    const int cnt = min(kRunTile, n - base);
+#pragma unroll
+    for (int j = 0; j < kRunPerThread; ++j) {
+        const int l = j * kRunThreads + threadIdx.x;
+        if (l < cnt) {
+            s_key[l] = __ldg(&skeys[base + l]);
+            s_pt[l] = __ldg(&pts[__ldg(&svals[base + l])]);
+        }
+    }
+    if (threadIdx.x == 0) s_prev = (base > 0) ? __ldg(&skeys[base - 1]) : 0u;
+    __syncthreads();
+    const int l0 = threadIdx.x * kRunPerThread;
     unsigned char head[kRunPerThread];
     int c = 0;
 #pragma unroll
     for (int j = 0; j < kRunPerThread; ++j) {
-        const int i = base + j;
-        head[j] = (i < n && (i == 0 || skeys[i] != skeys[i - 1])) ? 1 : 0;
+        const int l = l0 + j;
+        bool h = false;
+        if (l < cnt) h = (l == 0) ? (base == 0 || s_key[0] != s_prev) : (s_key[l] != s_key[l - 1]);
+        head[j] = h ? 1 : 0;
         c += head[j];
     }
     int total;
@@ -239,17 +259,26 @@ k_run_centroids(const unsigned* __restrict__ skeys, const unsigned* __restrict__
 #pragma unroll
     for (int j = 0; j < kRunPerThread; ++j) {
         if (!head[j]) continue;
-        const int i = base + j;
-        const unsigned key = skeys[i];
+        const int l = l0 + j;
+        const unsigned key = s_key[l];
         float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
-        int e = i;
+        int e = l;
         do {
-            const float4 p = __ldg(&pts[svals[e]]);
+            const float4 p = s_pt[e];
             sx += p.x; sy += p.y; sz += p.z; sw += p.w;
             ++e;
-        } while (e < n && skeys[e] == key);
-        const float cnt = (float)(e - i);
-        out[rank] = make_float4(sx / cnt, sy / cnt, sz / cnt, sw / cnt);
+        } while (e < cnt && s_key[e] == key);
+        int len = e - l;
+        if (e == cnt) {                              // run may continue in the next tile(s)
+            int g = base + cnt;
+            while (g < n && __ldg(&skeys[g]) == key) {
+                const float4 p = __ldg(&pts[__ldg(&svals[g])]);
+                sx += p.x; sy += p.y; sz += p.z; sw += p.w;
+                ++g; ++len;
+            }
+        }
+        const float fc = (float)len;
+        out[rank] = make_float4(sx / fc, sy / fc, sz / fc, sw / fc);
         ++rank;
     }
 }

@@ -1,0 +1,83 @@
+// liloc_b200/host/affine.hpp -- the few Eigen::Affine3f / PCL / tf helpers the host class needs
+// (Eigen, PCL and tf are not available here).  Conventions: SURVEY.md A.3.
+#pragma once
+#include <cmath>
+
+namespace liloc_host {
+
+struct Affine3f {
+    float m[3][4];      // top 3x4 of the homogeneous matrix, row-major
+
+    static Affine3f Identity() { Affine3f a{}; a.m[0][0] = a.m[1][1] = a.m[2][2] = 1.f; return a; }
+
+    Affine3f operator*(const Affine3f& b) const {
+        Affine3f r{};
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) r.m[i][j] = m[i][0] * b.m[0][j] + m[i][1] * b.m[1][j] + m[i][2] * b.m[2][j];
+            r.m[i][3] = m[i][0] * b.m[0][3] + m[i][1] * b.m[1][3] + m[i][2] * b.m[2][3] + m[i][3];
+        }
+        return r;
+    }
+
+    // Eigen::Transform<float,3,Affine>::inverse(): general 3x3 inverse of the linear part
+    Affine3f inverse() const {
+        const float a = m[0][0], b = m[0][1], c = m[0][2], d = m[1][0], e = m[1][1], f = m[1][2], g = m[2][0], h = m[2][1], i = m[2][2];
+        const float det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+        const float inv = 1.0f / det;
+        Affine3f r{};
+        r.m[0][0] = (e * i - f * h) * inv; r.m[0][1] = (c * h - b * i) * inv; r.m[0][2] = (b * f - c * e) * inv;
+        r.m[1][0] = (f * g - d * i) * inv; r.m[1][1] = (a * i - c * g) * inv; r.m[1][2] = (c * d - a * f) * inv;
+        r.m[2][0] = (d * h - e * g) * inv; r.m[2][1] = (b * g - a * h) * inv; r.m[2][2] = (a * e - b * d) * inv;
+        for (int k = 0; k < 3; ++k) r.m[k][3] = -(r.m[k][0] * m[0][3] + r.m[k][1] * m[1][3] + r.m[k][2] * m[2][3]);
+        return r;
+    }
+};
+
+// pcl::getTransformation(x, y, z, roll, pitch, yaw) -- same evaluation as the device (common.cuh pose_to_T):
+// sin/cos in double, rounded to float.
+inline Affine3f getTransformation(float x, float y, float z, float roll, float pitch, float yaw) {
+    const float A = (float)std::cos((double)yaw), B = (float)std::sin((double)yaw);
+    const float C = (float)std::cos((double)pitch), D = (float)std::sin((double)pitch);
+    const float E = (float)std::cos((double)roll), F = (float)std::sin((double)roll);
+    const float DE = D * E, DF = D * F;
+    Affine3f t{};
+    t.m[0][0] = A * C; t.m[0][1] = A * DF - B * E; t.m[0][2] = B * F + A * DE; t.m[0][3] = x;
+    t.m[1][0] = B * C; t.m[1][1] = A * E + B * DF; t.m[1][2] = B * DE - A * F; t.m[1][3] = y;
+    t.m[2][0] = -D;    t.m[2][1] = C * F;          t.m[2][2] = C * E;          t.m[2][3] = z;
+    return t;
+}
+
+// pcl::getTranslationAndEulerAngles
+inline void getTranslationAndEulerAngles(const Affine3f& t, float& x, float& y, float& z, float& roll, float& pitch, float& yaw) {
+    x = t.m[0][3]; y = t.m[1][3]; z = t.m[2][3];
+    roll = std::atan2(t.m[2][1], t.m[2][2]);
+    pitch = std::asin(-t.m[2][0]);
+    yaw = std::atan2(t.m[1][0], t.m[0][0]);
+}
+
+// tf::Quaternion::setRPY / slerp and tf::Matrix3x3::getRPY, double precision, as used by transformUpdate
+struct Quat { double x, y, z, w; };
+inline Quat quatFromRPY(double roll, double pitch, double yaw) {
+    const double hr = roll * 0.5, hp = pitch * 0.5, hy = yaw * 0.5;
+    const double cr = std::cos(hr), sr = std::sin(hr), cp = std::cos(hp), sp = std::sin(hp), cy = std::cos(hy), sy = std::sin(hy);
+    return Quat{sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+}
+inline Quat slerp(const Quat& a, const Quat& b, double t) {
+    const double dot = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    const double len2 = std::sqrt((a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) * (b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w));
+    const double theta = std::acos(std::fmin(1.0, std::fmax(-1.0, dot / len2)));
+    if (theta == 0.0) return a;
+    const double d = 1.0 / std::sin(theta), s0 = std::sin((1.0 - t) * theta), s1 = std::sin(t * theta);
+    if (dot < 0) return Quat{(a.x * s0 - b.x * s1) * d, (a.y * s0 - b.y * s1) * d, (a.z * s0 - b.z * s1) * d, (a.w * s0 - b.w * s1) * d};
+    return Quat{(a.x * s0 + b.x * s1) * d, (a.y * s0 + b.y * s1) * d, (a.z * s0 + b.z * s1) * d, (a.w * s0 + b.w * s1) * d};
+}
+inline void quatToRPY(const Quat& q, double& roll, double& pitch, double& yaw) {
+    const double n = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w, s = 2.0 / n;
+    const double r00 = 1 - s * (q.y * q.y + q.z * q.z), r10 = s * (q.x * q.y + q.w * q.z);
+    const double r20 = s * (q.x * q.z - q.w * q.y), r21 = s * (q.y * q.z + q.w * q.x), r22 = 1 - s * (q.x * q.x + q.y * q.y);
+    pitch = std::asin(std::fmin(1.0, std::fmax(-1.0, -r20)));
+    roll = std::atan2(r21, r22);
+    yaw = std::atan2(r10, r00);
+}
+
+}  // namespace liloc_host

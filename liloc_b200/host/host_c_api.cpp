@@ -1,0 +1,168 @@
+// liloc_b200/host/host_c_api.cpp -- C wrapper around the host class so that tests and bench.py can drive
+// the same per-frame callback the reference's ROS spinner drives (src/mapOptmization.cpp:246, :1628).
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "map_optimization.hpp"
+
+using liloc_host::mapOptimization;
+
+extern "C" {
+
+struct liloc_host_cloud_info {           // mirror of liloc_host::CloudInfo (plain C layout)
+    double stamp;
+    int imuAvailable, odomAvailable;
+    float imuRollInit, imuPitchInit, imuYawInit;
+    float initialGuessX, initialGuessY, initialGuessZ, initialGuessRoll, initialGuessPitch, initialGuessYaw;
+    const liloc_point* cloud_deskewed;
+    int cloud_size;
+    int cloud_on_device;
+};
+
+struct liloc_host_report {               // mirror of liloc_host::FrameReport
+    int processed, status;
+    float pose[6];
+    float guess[6];
+    int is_degenerate, iters, converged, n_sel, q_all, map_points, n_raw, n_selected_keyframes, keyframe_id;
+    double reg_ms;
+};
+
+static thread_local std::string g_err;
+
+void* liloc_host_create(const char* yaml_path, const char* mode_override, int device) {
+    auto* h = new (std::nothrow) mapOptimization(yaml_path ? yaml_path : "", mode_override, device);
+    if (!h) { g_err = "out of memory"; return nullptr; }
+    if (!h->ok()) { g_err = h->error(); delete h; return nullptr; }
+    return h;
+}
+void liloc_host_destroy(void* h) { delete static_cast<mapOptimization*>(h); }
+const char* liloc_host_error(void* h) { return h ? static_cast<mapOptimization*>(h)->error().c_str() : g_err.c_str(); }
+void* liloc_host_ctx(void* h) { return static_cast<mapOptimization*>(h)->context(); }
+
+static void to_report(const liloc_host::FrameReport& r, liloc_host_report* o) {
+    o->processed = r.processed; o->status = r.status; std::memcpy(o->pose, r.pose, sizeof(o->pose)); std::memcpy(o->guess, r.guess, sizeof(o->guess));
+    o->is_degenerate = r.is_degenerate; o->iters = r.iters; o->converged = r.converged; o->n_sel = r.n_sel;
+    o->q_all = r.q_all; o->map_points = r.map_points; o->n_raw = r.n_raw; o->n_selected_keyframes = r.n_selected_keyframes;
+    o->keyframe_id = r.keyframe_id; o->reg_ms = r.reg_ms;
+}
+
+static liloc_host::CloudInfo to_info(const liloc_host_cloud_info& m) {
+    liloc_host::CloudInfo c;
+    c.stamp = m.stamp; c.imuAvailable = m.imuAvailable; c.odomAvailable = m.odomAvailable;
+    c.imuRollInit = m.imuRollInit; c.imuPitchInit = m.imuPitchInit; c.imuYawInit = m.imuYawInit;
+    c.initialGuessX = m.initialGuessX; c.initialGuessY = m.initialGuessY; c.initialGuessZ = m.initialGuessZ;
+    c.initialGuessRoll = m.initialGuessRoll; c.initialGuessPitch = m.initialGuessPitch; c.initialGuessYaw = m.initialGuessYaw;
+    c.cloud_deskewed = m.cloud_deskewed; c.cloud_size = m.cloud_size; c.cloud_on_device = m.cloud_on_device;
+    return c;
+}
+
+// one callback (laserCloudInfoHandler).  Returns 0, or <0 when the registration reported an error.
+int liloc_host_handle(void* h, const liloc_host_cloud_info* msg, liloc_host_report* out) {
+    auto* m = static_cast<mapOptimization*>(h);
+    const liloc_host::FrameReport r = m->laserCloudInfoHandler(to_info(*msg));
+    if (out) to_report(r, out);
+    return r.status < 0 ? r.status : 0;
+}
+
+// F callbacks back to back (what ros::spin() does with a queue of messages)
+int liloc_host_run(void* h, const liloc_host_cloud_info* msgs, int F, liloc_host_report* outs) {
+    for (int i = 0; i < F; ++i) {
+        const int rc = liloc_host_handle(h, msgs + i, outs ? outs + i : nullptr);
+        if (rc < 0) return rc;
+    }
+    return 0;
+}
+
+void liloc_host_reset(void* h) { static_cast<mapOptimization*>(h)->reset(); }
+
+void liloc_host_set_s2m_opts(void* h, int max_iters, int stride, int min_sel, int min_points) {
+    auto* m = static_cast<mapOptimization*>(h);
+    m->s2m_opts.max_iters = max_iters; m->s2m_opts.stride = stride; m->s2m_opts.min_sel = min_sel; m->s2m_opts.min_points = min_points;
+}
+
+int liloc_host_num_keyframes(void* h) { return (int)static_cast<mapOptimization*>(h)->cloudKeyPoses6D.size(); }
+
+// key poses as rows [roll, pitch, yaw, x, y, z, time]
+int liloc_host_keyposes(void* h, double* out7, int cap) {
+    auto* m = static_cast<mapOptimization*>(h);
+    const int n = (int)m->cloudKeyPoses6D.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        const auto& p = m->cloudKeyPoses6D[i];
+        double* o = out7 + 7 * i;
+        o[0] = p.roll; o[1] = p.pitch; o[2] = p.yaw; o[3] = p.x; o[4] = p.y; o[5] = p.z; o[6] = p.time;
+    }
+    return n;
+}
+
+int liloc_host_last_selection(void* h, int* ids, int cap) {
+    const auto& s = static_cast<mapOptimization*>(h)->lastSelection();
+    for (int i = 0; i < (int)s.size() && i < cap; ++i) ids[i] = s[i];
+    return (int)s.size();
+}
+
+// parsed parameters, for the config tests: returns 0 and writes *out, or -1 for an unknown key
+static int param_of(const liloc_host::ParamServer* m, const char* key, double* out) {
+    const std::string k(key);
+#define P(name) if (k == #name) { *out = (double)m->name; return 0; }
+    P(numberOfCores) P(N_SCAN) P(Horizon_SCAN) P(downsampleRate) P(point_filter_num) P(lidarMinRange) P(lidarMaxRange)
+    P(imuType) P(imuRate) P(imuAccNoise) P(imuGyrNoise) P(imuAccBiasN) P(imuGyrBiasN) P(imuGravity) P(imuRPYWeight)
+    P(z_tollerance) P(rotation_tollerance) P(ndtResolution) P(ndtEpsilon)
+    P(timeInterval) P(mappingProcessInterval) P(mappingSurfLeafSize) P(surroundingKeyframeMapLeafSize)
+    P(surroundingkeyframeAddingDistThreshold) P(surroundingkeyframeAddingAngleThreshold) P(surroundingKeyframeDensity)
+    P(surroundingKeyframeSearchRadius) P(globalMapVisualizationSearchRadius) P(globalMapVisualizationPoseDensity)
+    P(globalMapVisualizationLeafSize) P(have_ring_time_channel) P(correct)
+#undef P
+    if (k == "mode") { *out = m->mode == liloc_host::ModeType::LIO ? 0 : 1; return 0; }
+    if (k == "sensor") { *out = (double)(int)m->sensor; return 0; }
+    if (k == "regMethod.DIRECT1") { *out = m->regMethod == "DIRECT1"; return 0; }
+    if (k.rfind("extrinsicRot.", 0) == 0) { const size_t i = std::stoul(k.substr(13)); if (i < m->extRotV.size()) { *out = m->extRotV[i]; return 0; } return -1; }
+    if (k.rfind("extrinsicRPY.", 0) == 0) { const size_t i = std::stoul(k.substr(13)); if (i < m->extRPYV.size()) { *out = m->extRPYV[i]; return 0; } return -1; }
+    if (k.rfind("extrinsicTrans.", 0) == 0) { const size_t i = std::stoul(k.substr(15)); if (i < m->extTransV.size()) { *out = m->extTransV[i]; return 0; } return -1; }
+    return -1;
+}
+int liloc_host_param(void* h, const char* key, double* out) { return param_of(static_cast<mapOptimization*>(h), key, out); }
+
+// ParamServer alone (no GPU needed): parse `yaml_path` and read one parameter. -2: yaml unusable.
+int liloc_host_yaml_param(const char* yaml_path, const char* key, double* out) {
+    liloc_host::ParamServer ps;
+    if (!ps.load(yaml_path)) { g_err = ps.param_error; return -2; }
+    return param_of(&ps, key, out);
+}
+
+// ---- host-logic hooks for the CPU tests (no device work) ----
+void liloc_host_debug_add_keypose(void* h, const float* pose6, double time) {
+    auto* m = static_cast<mapOptimization*>(h);
+    const float id = (float)m->cloudKeyPoses3D.size();
+    m->cloudKeyPoses3D.push_back(liloc_host::PointType{pose6[3], pose6[4], pose6[5], id});
+    m->cloudKeyPoses6D.push_back(liloc_host::PointTypePose{pose6[3], pose6[4], pose6[5], id, pose6[0], pose6[1], pose6[2], time});
+}
+int liloc_host_debug_extract_nearby(void* h, double stamp, int* ids, int cap) {
+    auto* m = static_cast<mapOptimization*>(h);
+    m->timeLaserInfoCur = stamp;
+    m->extractSurroundingKeyFrames();
+    return liloc_host_last_selection(h, ids, cap);
+}
+void liloc_host_debug_set_pose(void* h, const float* pose6) { std::memcpy(static_cast<mapOptimization*>(h)->transformTobeMapped, pose6, 24); }
+void liloc_host_debug_get_pose(void* h, float* pose6) { std::memcpy(pose6, static_cast<mapOptimization*>(h)->transformTobeMapped, 24); }
+void liloc_host_debug_update_initial_guess(void* h, const liloc_host_cloud_info* msg) {
+    auto* m = static_cast<mapOptimization*>(h);
+    m->cloudInfo = to_info(*msg); m->timeLaserInfoCur = msg->stamp;
+    m->updateInitialGuess();
+}
+int liloc_host_debug_save_frame(void* h) { return static_cast<mapOptimization*>(h)->saveFrame() ? 1 : 0; }
+void liloc_host_debug_transform_update(void* h, const liloc_host_cloud_info* msg) {
+    auto* m = static_cast<mapOptimization*>(h);
+    m->cloudInfo = to_info(*msg);
+    m->transformUpdate();
+}
+int liloc_host_debug_voxelgrid_small(const float* in4, int n, float leaf, float* out4) {
+    std::vector<liloc_host::PointType> v(n);
+    std::memcpy(v.data(), in4, sizeof(float) * 4 * (size_t)n);
+    const auto o = liloc_host::voxelGridSmall(v, leaf);
+    std::memcpy(out4, o.data(), sizeof(float) * 4 * o.size());
+    return (int)o.size();
+}
+
+}  // extern "C"

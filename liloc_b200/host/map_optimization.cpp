@@ -1,0 +1,287 @@
+// liloc_b200/host/map_optimization.cpp -- see map_optimization.hpp.
+#include "map_optimization.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+namespace liloc_host {
+
+namespace {
+inline float pointDistance(const PointType& a, const PointType& b) {       // include/utility.h pointDistance(p1, p2)
+    return std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z));
+}
+inline float sqDist(const PointType& a, const PointType& b) {
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    return ((dx * dx) + (dy * dy)) + (dz * dz);
+}
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+std::vector<PointType> voxelGridSmall(const std::vector<PointType>& in, float leaf) {
+    std::vector<PointType> out;
+    if (in.empty()) return out;
+    const float inv = 1.0f / leaf;
+    float mn[3] = {in[0].x, in[0].y, in[0].z}, mx[3] = {in[0].x, in[0].y, in[0].z};
+    for (const auto& p : in) {
+        mn[0] = std::min(mn[0], p.x); mx[0] = std::max(mx[0], p.x);
+        mn[1] = std::min(mn[1], p.y); mx[1] = std::max(mx[1], p.y);
+        mn[2] = std::min(mn[2], p.z); mx[2] = std::max(mx[2], p.z);
+    }
+    const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+    if (dx * dy * dz > (long long)INT_MAX) return in;
+    int minb[3], divb[3];
+    for (int a = 0; a < 3; ++a) { minb[a] = (int)std::floor(mn[a] * inv); divb[a] = (int)std::floor(mx[a] * inv) - minb[a] + 1; }
+    std::vector<std::pair<int, int>> keys(in.size());
+    for (size_t i = 0; i < in.size(); ++i) {
+        const int i0 = (int)(std::floor(in[i].x * inv) - (float)minb[0]);
+        const int i1 = (int)(std::floor(in[i].y * inv) - (float)minb[1]);
+        const int i2 = (int)(std::floor(in[i].z * inv) - (float)minb[2]);
+        keys[i] = {i0 + i1 * divb[0] + i2 * divb[0] * divb[1], (int)i};
+    }
+    std::sort(keys.begin(), keys.end());
+    for (size_t i = 0; i < keys.size();) {
+        size_t j = i; float sx = 0, sy = 0, sz = 0, sw = 0;
+        for (; j < keys.size() && keys[j].first == keys[i].first; ++j) { const auto& p = in[keys[j].second]; sx += p.x; sy += p.y; sz += p.z; sw += p.intensity; }
+        const float c = (float)(j - i);
+        out.push_back(PointType{sx / c, sy / c, sz / c, sw / c});
+        i = j;
+    }
+    return out;
+}
+
+mapOptimization::mapOptimization(const std::string& yaml_path, const char* mode_override, int device) {
+    if (!load(yaml_path)) { error_ = param_error; return; }
+    if (mode_override && *mode_override) {
+        const std::string m(mode_override);
+        if (m == "lio") mode = ModeType::LIO; else if (m == "relo") mode = ModeType::RELO;
+        else { error_ = "Invalid Mode Type (must be either 'lio' or 'relo'): " + m; return; }
+    }
+    if (device < 0) return;                                  // host logic only (CPU tests): no device context
+    liloc_config cfg{};
+    cfg.device = device;
+    cfg.max_scan_points = N_SCAN * Horizon_SCAN;          // allocateMemory() :228-230
+    cfg.max_raw_points = 1 << 21;
+    if (liloc_create(&cfg, &ctx_) != LILOC_OK) { error_ = liloc_last_error(nullptr); ctx_ = nullptr; }
+}
+
+void mapOptimization::reset() {
+    cloudKeyPoses3D.clear(); cloudKeyPoses6D.clear(); laserCloudMapContainer.clear(); reg_time.clear();
+    for (float& v : transformTobeMapped) v = 0.f;
+    for (float& v : transformTobeMappedInit) v = 0.f;
+    isDegenerate = false; systemInitialized = false; poseInitialized = false;
+    timeLastProcessing_ = -1; lastImuPreTransAvailable_ = false;
+    lastImuTransformation_ = Affine3f::Identity(); lastImuPreTransformation_ = Affine3f::Identity();
+    sel_ids_.clear(); sel_poses_.clear(); have_selection_ = false;
+    if (ctx_) liloc_keyframe_clear(ctx_);
+}
+
+mapOptimization::~mapOptimization() { if (ctx_) liloc_destroy(ctx_); }
+
+FrameReport mapOptimization::laserCloudInfoHandler(const CloudInfo& msgIn) {
+    rep_ = FrameReport{};
+    timeLaserInfoCur = msgIn.stamp;
+    cloudInfo = msgIn;                                                         // :252-253
+    if (timeLaserInfoCur - timeLastProcessing_ < timeInterval) return rep_;    // :257
+    const double t0 = now_ms();
+    have_selection_ = false;
+    updateInitialGuess();                  // :309
+    std::memcpy(rep_.guess, transformTobeMapped, sizeof(rep_.guess));
+    extractSurroundingKeyFrames();         // :311
+    downsampleCurrentScan();               // :313
+    scan2MapOptimization();                // :315
+    rep_.reg_ms = now_ms() - t0;           // :317-318
+    reg_time.push_back(rep_.reg_ms);
+    if (mode == ModeType::LIO) saveLIOKeyFramesAndFactor();                    // :327-330
+    rep_.processed = 1;
+    std::memcpy(rep_.pose, transformTobeMapped, sizeof(rep_.pose));
+    rep_.is_degenerate = isDegenerate ? 1 : 0;                                 // publishOdometry :1573
+    timeLastProcessing_ = timeLaserInfoCur;                                    // :352
+    return rep_;
+}
+
+void mapOptimization::updateInitialGuess() {
+    incrementalOdometryAffineFront = trans2Affine3f(transformTobeMapped);      // :832
+    if (cloudKeyPoses3D.empty()) {                                             // :835
+        if (mode == ModeType::LIO) {
+            transformTobeMapped[0] = cloudInfo.imuRollInit;
+            transformTobeMapped[1] = cloudInfo.imuPitchInit;
+            transformTobeMapped[2] = cloudInfo.imuYawInit;
+            lastImuTransformation_ = getTransformation(0, 0, 0, cloudInfo.imuRollInit, cloudInfo.imuPitchInit, cloudInfo.imuYawInit);
+        } else {
+            const Affine3f transImuInit = getTransformation(0, 0, 0, cloudInfo.initialGuessRoll, cloudInfo.initialGuessPitch, cloudInfo.initialGuessYaw);
+            const Affine3f transCbInit = getTransformation(transformTobeMappedInit[3], transformTobeMappedInit[4], transformTobeMappedInit[5],
+                                                           transformTobeMappedInit[0], transformTobeMappedInit[1], transformTobeMappedInit[2]);
+            const Affine3f transInit = transCbInit * transImuInit;
+            getTranslationAndEulerAngles(transInit, transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5],
+                                         transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2]);
+            lastImuTransformation_ = getTransformation(0, 0, 0, transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2]);
+        }
+        return;
+    }
+    if (cloudInfo.odomAvailable) {                                             // :865-884
+        const Affine3f transBack = getTransformation(cloudInfo.initialGuessX, cloudInfo.initialGuessY, cloudInfo.initialGuessZ,
+                                                     cloudInfo.initialGuessRoll, cloudInfo.initialGuessPitch, cloudInfo.initialGuessYaw);
+        if (!lastImuPreTransAvailable_) {
+            lastImuPreTransformation_ = transBack;
+            lastImuPreTransAvailable_ = true;
+        } else {
+            const Affine3f transIncre = lastImuPreTransformation_.inverse() * transBack;
+            const Affine3f transFinal = trans2Affine3f(transformTobeMapped) * transIncre;
+            getTranslationAndEulerAngles(transFinal, transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5],
+                                         transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2]);
+            lastImuPreTransformation_ = transBack;
+            lastImuTransformation_ = getTransformation(0, 0, 0, cloudInfo.imuRollInit, cloudInfo.imuPitchInit, cloudInfo.imuYawInit);
+            return;
+        }
+    }
+    if (cloudInfo.imuAvailable && imuType) {                                   // :887-899
+        const Affine3f transBack = getTransformation(0, 0, 0, cloudInfo.imuRollInit, cloudInfo.imuPitchInit, cloudInfo.imuYawInit);
+        const Affine3f transIncre = lastImuTransformation_.inverse() * transBack;
+        const Affine3f transFinal = trans2Affine3f(transformTobeMapped) * transIncre;
+        getTranslationAndEulerAngles(transFinal, transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5],
+                                     transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2]);
+        lastImuTransformation_ = transBack;
+    }
+}
+
+void mapOptimization::extractSurroundingKeyFrames() {
+    if (cloudKeyPoses3D.empty()) return;       // :964-965
+    extractNearby();
+}
+
+void mapOptimization::extractNearby() {
+    const PointType& last = cloudKeyPoses3D.back();
+    // radiusSearch(last, R): d2 < R^2, ascending distance (:908-914)
+    const float r2 = surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius;
+    std::vector<std::pair<float, int>> hits;
+    for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
+        const float d = sqDist(last, cloudKeyPoses3D[i]);
+        if (d < r2) hits.push_back({d, i});
+    }
+    std::sort(hits.begin(), hits.end());
+    std::vector<PointType> surroundingKeyPoses;
+    surroundingKeyPoses.reserve(hits.size());
+    for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
+    std::vector<PointType> surroundingKeyPosesDS = voxelGridSmall(surroundingKeyPoses, surroundingKeyframeDensity);   // :916-917
+    for (auto& pt : surroundingKeyPosesDS) {   // nearestKSearch(pt, 1): recover the keyframe index (:918-922)
+        int best = 0; float bd = sqDist(pt, cloudKeyPoses3D[0]);
+        for (int i = 1; i < (int)cloudKeyPoses3D.size(); ++i) { const float d = sqDist(pt, cloudKeyPoses3D[i]); if (d < bd) { bd = d; best = i; } }
+        pt.intensity = cloudKeyPoses3D[best].intensity;
+    }
+    for (int i = (int)cloudKeyPoses3D.size() - 1; i >= 0; --i) {               // :924-931 (duplicates possible)
+        if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 5.0) surroundingKeyPosesDS.push_back(cloudKeyPoses3D[i]);
+        else break;
+    }
+    extractCloud(surroundingKeyPosesDS);
+}
+
+void mapOptimization::extractCloud(const std::vector<PointType>& cloudToExtract) {
+    sel_ids_.clear(); sel_poses_.clear();
+    for (const auto& p : cloudToExtract) {
+        if (pointDistance(p, cloudKeyPoses3D.back()) > surroundingKeyframeSearchRadius) continue;      // :939
+        const int thisKeyInd = (int)p.intensity;
+        auto it = laserCloudMapContainer.find(thisKeyInd);
+        if (it == laserCloudMapContainer.end())                                                       // :946-951 cache miss
+            it = laserCloudMapContainer.emplace(thisKeyInd, cloudKeyPoses6D[thisKeyInd]).first;
+        const PointTypePose& kp = it->second;      // the pose the cached transformed cloud was made with
+        sel_ids_.push_back(thisKeyInd);
+        const float pose6[6] = {kp.roll, kp.pitch, kp.yaw, kp.x, kp.y, kp.z};
+        sel_poses_.insert(sel_poses_.end(), pose6, pose6 + 6);
+    }
+    have_selection_ = true;                        // transform + concat + VoxelGrid (:944-956) run in scan2MapOptimization's device call
+    if (laserCloudMapContainer.size() > 1000) laserCloudMapContainer.clear();                          // :959-960
+}
+
+void mapOptimization::downsampleCurrentScan() {
+    if (!ctx_) { error_ = "no device context"; rep_.status = LILOC_ERR_STATE; return; }
+    // VoxelGrid(mappingSurfLeafSize) of cloud_deskewed (:970-975).  With keyframes present it is fused into the
+    // device call issued by scan2MapOptimization(); without, it runs here because the first keyframe needs it.
+    if (!have_selection_) {
+        int q = 0;
+        const int rc = cloudInfo.cloud_on_device
+            ? liloc_scan_put_dev(ctx_, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, mappingSurfLeafSize, &q)
+            : liloc_scan_put(ctx_, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, mappingSurfLeafSize, &q);
+        if (rc < 0) { error_ = liloc_last_error(ctx_); rep_.status = rc; return; }
+        laserCloudSurfLastDSNum = q;
+        rep_.q_all = q;
+    }
+}
+
+void mapOptimization::scan2MapOptimization() {
+    if (cloudKeyPoses3D.empty()) return;           // :1184
+    if (!ctx_) { error_ = "no device context"; rep_.status = LILOC_ERR_STATE; return; }
+    liloc_s2m_result res{};
+    const int K = (int)sel_ids_.size();
+    const int rc = liloc_frame(ctx_, sel_ids_.data(), sel_poses_.data(), K, surroundingKeyframeMapLeafSize,
+                               cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device, mappingSurfLeafSize,
+                               transformTobeMapped, &s2m_opts, &res);
+    rep_.status = rc;
+    if (rc < 0) { error_ = liloc_last_error(ctx_); return; }
+    laserCloudSurfLastDSNum = res.q_all;
+    laserCloudSurfFromMapDSNum = res.map_points;
+    rep_.q_all = res.q_all; rep_.map_points = res.map_points; rep_.n_selected_keyframes = K;
+    rep_.iters = res.iters; rep_.converged = res.converged; rep_.n_sel = res.n_sel;
+    if (rc == LILOC_SKIPPED) return;               // "Not enough features" (:1205): no transformUpdate
+    isDegenerate = res.is_degenerate != 0;
+    std::memcpy(matP, res.matP, sizeof(matP));
+    transformUpdate();                             // :1202
+}
+
+void mapOptimization::transformUpdate() {
+    if (cloudInfo.imuAvailable && imuType) {       // :1210-1227
+        if (std::abs(cloudInfo.imuPitchInit) < 1.4f) {
+            const double imuWeight = imuRPYWeight;
+            double rollMid, pitchMid, yawMid;
+            Quat tq = quatFromRPY(transformTobeMapped[0], 0, 0), iq = quatFromRPY(cloudInfo.imuRollInit, 0, 0);
+            quatToRPY(slerp(tq, iq, imuWeight), rollMid, pitchMid, yawMid);
+            transformTobeMapped[0] = (float)rollMid;
+            tq = quatFromRPY(0, transformTobeMapped[1], 0); iq = quatFromRPY(0, cloudInfo.imuPitchInit, 0);
+            quatToRPY(slerp(tq, iq, imuWeight), rollMid, pitchMid, yawMid);
+            transformTobeMapped[1] = (float)pitchMid;
+        }
+    }
+    transformTobeMapped[0] = constraintTransformation(transformTobeMapped[0], rotation_tollerance);    // :1229-1231
+    transformTobeMapped[1] = constraintTransformation(transformTobeMapped[1], rotation_tollerance);
+    transformTobeMapped[5] = constraintTransformation(transformTobeMapped[5], z_tollerance);
+    incrementalOdometryAffineBack = trans2Affine3f(transformTobeMapped);                               // :1233
+}
+
+float mapOptimization::constraintTransformation(float value, float limit) {
+    if (value < -limit) value = -limit;
+    if (value > limit) value = limit;
+    return value;
+}
+
+bool mapOptimization::saveFrame() {
+    if (cloudKeyPoses3D.empty()) return true;
+    const PointTypePose& b = cloudKeyPoses6D.back();
+    const Affine3f transStart = getTransformation(b.x, b.y, b.z, b.roll, b.pitch, b.yaw);
+    const Affine3f transFinal = trans2Affine3f(transformTobeMapped);
+    const Affine3f transBetween = transStart.inverse() * transFinal;
+    float x, y, z, roll, pitch, yaw;
+    getTranslationAndEulerAngles(transBetween, x, y, z, roll, pitch, yaw);
+    if (std::abs(roll) < surroundingkeyframeAddingAngleThreshold && std::abs(pitch) < surroundingkeyframeAddingAngleThreshold &&
+        std::abs(yaw) < surroundingkeyframeAddingAngleThreshold && std::sqrt(x * x + y * y + z * z) < surroundingkeyframeAddingDistThreshold)
+        return false;
+    return true;
+}
+
+void mapOptimization::saveLIOKeyFramesAndFactor() {
+    if (!saveFrame()) return;                      // :1392
+    if (rep_.status < 0) return;
+    const int id = (int)cloudKeyPoses3D.size();
+    PointType p3{transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5], (float)id};   // :1423-1427
+    PointTypePose p6{p3.x, p3.y, p3.z, p3.intensity, transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2], timeLaserInfoCur};
+    if (liloc_keyframe_put_from_scan(ctx_, id) < 0) { error_ = liloc_last_error(ctx_); return; }       // :1453-1457
+    cloudKeyPoses3D.push_back(p3);
+    cloudKeyPoses6D.push_back(p6);
+    rep_.keyframe_id = id;
+}
+
+}  // namespace liloc_host

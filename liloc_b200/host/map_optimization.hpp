@@ -1,0 +1,112 @@
+// liloc_b200/host/map_optimization.hpp -- ROS-free host side of `class mapOptimization`
+// (src/mapOptmization.cpp:18): same member names, same per-frame call order, same parameters; every
+// PCL / Eigen / OpenCV call on the scan-to-map path is replaced by a call into the C ABI
+// (include/liloc_gpu.h).  What stays on the host is exactly what SURVEY.md 8(a) marks "stays on host":
+// updateInitialGuess (a10), extractNearby keyframe selection (a11), transformUpdate (a9), saveFrame.
+//
+// Out of scope here: ROS publishers/services, GTSAM.  In lio mode the
+// reference's ISAM2 graph holds one prior and a chain of odometry BetweenFactors with no loop
+// closures (correctPoses() is commented out, :346), whose unique optimum is the chain of measured
+// poses, so saveLIOKeyFramesAndFactor stores transformTobeMapped itself as the key pose.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/liloc_gpu.h"
+#include "affine.hpp"
+#include "param_server.hpp"
+
+namespace liloc_host {
+
+struct PointType { float x, y, z, intensity; };                                     // pcl::PointXYZI
+struct PointTypePose { float x, y, z, intensity, roll, pitch, yaw; double time; };  // PointXYZIRPYT
+
+// The fields of msg/cloud_info.msg that mapOptimization reads.
+struct CloudInfo {
+    double stamp = 0.0;                          // header.stamp
+    int imuAvailable = 0, odomAvailable = 0;
+    float imuRollInit = 0, imuPitchInit = 0, imuYawInit = 0;
+    float initialGuessX = 0, initialGuessY = 0, initialGuessZ = 0, initialGuessRoll = 0, initialGuessPitch = 0, initialGuessYaw = 0;
+    const liloc_point* cloud_deskewed = nullptr; // host pointer, or device pointer when cloud_on_device
+    int cloud_size = 0;
+    int cloud_on_device = 0;
+};
+
+struct FrameReport {                             // what the reference would publish / log for one frame
+    int processed = 0;                           // 0: dropped by the timeInterval gate (:257)
+    int status = 0;                              // liloc return code of the registration (LILOC_SKIPPED ...)
+    float pose[6] = {0, 0, 0, 0, 0, 0};          // transformTobeMapped after the frame
+    float guess[6] = {0, 0, 0, 0, 0, 0};         // transformTobeMapped after updateInitialGuess (LM start point)
+    int is_degenerate = 0;
+    int iters = 0, converged = 0, n_sel = 0;
+    int q_all = 0, map_points = 0, n_raw = 0, n_selected_keyframes = 0;
+    int keyframe_id = -1;                        // id if this frame became a keyframe
+    double reg_ms = 0.0;                         // reg_time (:307-318): init guess + map + downsample + scan2map
+};
+
+class mapOptimization : public ParamServer {
+public:
+    // ---- state with the reference's names ----
+    std::vector<PointType> cloudKeyPoses3D;
+    std::vector<PointTypePose> cloudKeyPoses6D;
+    std::map<int, PointTypePose> laserCloudMapContainer;   // keyframe id -> pose its cached transform was made with (:69)
+    float transformTobeMapped[6] = {0, 0, 0, 0, 0, 0};
+    float transformTobeMappedInit[6] = {0, 0, 0, 0, 0, 0};
+    bool isDegenerate = false;
+    float matP[36] = {0};
+    bool systemInitialized = false, poseInitialized = false;
+    int laserCloudSurfFromMapDSNum = 0, laserCloudSurfLastDSNum = 0;
+    Affine3f incrementalOdometryAffineFront = Affine3f::Identity(), incrementalOdometryAffineBack = Affine3f::Identity();
+    CloudInfo cloudInfo;
+    double timeLaserInfoCur = 0.0;
+    std::vector<double> reg_time;
+
+    explicit mapOptimization(const std::string& yaml_path, const char* mode_override, int device);
+    ~mapOptimization();
+    mapOptimization(const mapOptimization&) = delete;
+    mapOptimization& operator=(const mapOptimization&) = delete;
+
+    void reset();                               // forget the session: key poses, cache, device keyframes
+    bool ok() const { return error_.empty(); }
+    const std::string& error() const { return error_; }
+    liloc_ctx* context() { return ctx_; }
+
+    // ---- the reference's per-frame methods (src/mapOptmization.cpp:246-353) ----
+    FrameReport laserCloudInfoHandler(const CloudInfo& msgIn);
+    void updateInitialGuess();                 // :831-900
+    void extractSurroundingKeyFrames();        // :963-968
+    void extractNearby();                      // :902-934
+    void extractCloud(const std::vector<PointType>& cloudToExtract);   // :936-961
+    void downsampleCurrentScan();              // :970-975
+    void scan2MapOptimization();               // :1183-1207
+    void transformUpdate();                    // :1209-1234
+    float constraintTransformation(float value, float limit);          // :1236-1243
+    bool saveFrame();                          // :1245-1264
+    void saveLIOKeyFramesAndFactor();          // :1391-1461
+
+    Affine3f trans2Affine3f(const float t[6]) { return getTransformation(t[3], t[4], t[5], t[0], t[1], t[2]); }   // :404-406
+
+    liloc_s2m_opts s2m_opts{20, 2, 50, 30, {0, 0, 0, 0}};
+    const std::vector<int>& lastSelection() const { return sel_ids_; }
+
+private:
+    liloc_ctx* ctx_ = nullptr;
+    std::string error_;
+    // function-static state of the reference, kept as members
+    double timeLastProcessing_ = -1;
+    Affine3f lastImuTransformation_ = Affine3f::Identity();
+    bool lastImuPreTransAvailable_ = false;
+    Affine3f lastImuPreTransformation_ = Affine3f::Identity();
+    // staged inputs of the fused device call
+    std::vector<int> sel_ids_;
+    std::vector<float> sel_poses_;
+    bool have_selection_ = false;
+    FrameReport rep_;
+};
+
+// pcl::VoxelGrid on a handful of key positions (extractNearby :916-917); host-side because it is part of
+// keyframe *selection* (SURVEY 8a a11), not of the point-cloud path.
+std::vector<PointType> voxelGridSmall(const std::vector<PointType>& in, float leaf);
+
+}  // namespace liloc_host

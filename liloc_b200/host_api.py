@@ -1,0 +1,215 @@
+"""ctypes binding of libliloc_host.so: the ROS-free `mapOptimization` host class (liloc_b200/host/)
+driven through its per-frame callback, exactly as the reference's ROS spinner drives it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libliloc_host.so")
+CONFIG_DIR = os.path.join(os.path.dirname(_HERE), "config")
+
+
+class CloudInfo(C.Structure):
+    """msg/cloud_info.msg fields read by mapOptimization."""
+    _fields_ = [("stamp", C.c_double), ("imuAvailable", C.c_int), ("odomAvailable", C.c_int),
+                ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float), ("imuYawInit", C.c_float),
+                ("initialGuessX", C.c_float), ("initialGuessY", C.c_float), ("initialGuessZ", C.c_float),
+                ("initialGuessRoll", C.c_float), ("initialGuessPitch", C.c_float), ("initialGuessYaw", C.c_float),
+                ("cloud_deskewed", C.c_void_p), ("cloud_size", C.c_int), ("cloud_on_device", C.c_int)]
+
+
+class Report(C.Structure):
+    _fields_ = [("processed", C.c_int), ("status", C.c_int), ("pose", C.c_float * 6), ("guess", C.c_float * 6),
+                ("is_degenerate", C.c_int), ("iters", C.c_int), ("converged", C.c_int), ("n_sel", C.c_int),
+                ("q_all", C.c_int), ("map_points", C.c_int), ("n_raw", C.c_int), ("n_selected_keyframes", C.c_int),
+                ("keyframe_id", C.c_int), ("reg_ms", C.c_double)]
+
+
+def _load():
+    if not os.path.exists(lib_path):
+        raise ImportError(f"{lib_path} missing: run `python -m liloc_b200._build`")
+    L = C.CDLL(lib_path)
+    P = C.c_void_p
+    L.liloc_host_create.restype = P
+    L.liloc_host_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.liloc_host_destroy.argtypes = [P]
+    L.liloc_host_error.restype = C.c_char_p
+    L.liloc_host_error.argtypes = [P]
+    L.liloc_host_ctx.restype = P
+    L.liloc_host_ctx.argtypes = [P]
+    L.liloc_host_handle.restype = C.c_int
+    L.liloc_host_handle.argtypes = [P, C.POINTER(CloudInfo), C.POINTER(Report)]
+    L.liloc_host_run.restype = C.c_int
+    L.liloc_host_run.argtypes = [P, C.POINTER(CloudInfo), C.c_int, C.POINTER(Report)]
+    L.liloc_host_reset.argtypes = [P]
+    L.liloc_host_set_s2m_opts.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.liloc_host_num_keyframes.restype = C.c_int
+    L.liloc_host_num_keyframes.argtypes = [P]
+    L.liloc_host_keyposes.restype = C.c_int
+    L.liloc_host_keyposes.argtypes = [P, P, C.c_int]
+    L.liloc_host_last_selection.restype = C.c_int
+    L.liloc_host_last_selection.argtypes = [P, P, C.c_int]
+    L.liloc_host_param.restype = C.c_int
+    L.liloc_host_param.argtypes = [P, C.c_char_p, C.POINTER(C.c_double)]
+    L.liloc_host_yaml_param.restype = C.c_int
+    L.liloc_host_yaml_param.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
+    L.liloc_host_debug_add_keypose.argtypes = [P, P, C.c_double]
+    L.liloc_host_debug_extract_nearby.restype = C.c_int
+    L.liloc_host_debug_extract_nearby.argtypes = [P, C.c_double, P, C.c_int]
+    L.liloc_host_debug_set_pose.argtypes = [P, P]
+    L.liloc_host_debug_get_pose.argtypes = [P, P]
+    L.liloc_host_debug_update_initial_guess.argtypes = [P, C.POINTER(CloudInfo)]
+    L.liloc_host_debug_save_frame.restype = C.c_int
+    L.liloc_host_debug_save_frame.argtypes = [P]
+    L.liloc_host_debug_transform_update.argtypes = [P, C.POINTER(CloudInfo)]
+    L.liloc_host_debug_voxelgrid_small.restype = C.c_int
+    L.liloc_host_debug_voxelgrid_small.argtypes = [P, C.c_int, C.c_float, P]
+    return L
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def yaml_param(yaml: str, key: str) -> float:
+    v = C.c_double()
+    rc = lib().liloc_host_yaml_param(config_path(yaml).encode(), key.encode(), C.byref(v))
+    if rc != 0:
+        raise KeyError(f"{yaml}:{key} ({rc})")
+    return v.value
+
+
+def config_path(name: str) -> str:
+    return name if os.path.isabs(name) else os.path.join(CONFIG_DIR, name)
+
+
+class MapOptimization:
+    """Handle on one host `mapOptimization` object (one GPU context inside)."""
+
+    def __init__(self, yaml: str, mode: str | None = None, device: int = 0):
+        L = lib()
+        self._h = L.liloc_host_create(config_path(yaml).encode(), (mode or "").encode(), device)
+        if not self._h:
+            raise RuntimeError("mapOptimization: " + (L.liloc_host_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().liloc_host_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def param(self, key: str) -> float:
+        v = C.c_double()
+        if lib().liloc_host_param(self._h, key.encode(), C.byref(v)) != 0:
+            raise KeyError(key)
+        return v.value
+
+    def reset(self):
+        lib().liloc_host_reset(self._h)
+
+    def set_s2m_opts(self, max_iters=20, stride=2, min_sel=50, min_points=30):
+        lib().liloc_host_set_s2m_opts(self._h, max_iters, stride, min_sel, min_points)
+
+    def handle(self, info: CloudInfo) -> Report:
+        r = Report()
+        rc = lib().liloc_host_handle(self._h, C.byref(info), C.byref(r))
+        if rc < 0:
+            raise RuntimeError(f"laserCloudInfoHandler failed ({rc}): " + (lib().liloc_host_error(self._h) or b"").decode())
+        return r
+
+    def run(self, infos) -> list:
+        """infos: ctypes array of CloudInfo.  Processes them back to back natively."""
+        n = len(infos)
+        reps = (Report * n)()
+        rc = lib().liloc_host_run(self._h, infos, n, reps)
+        if rc < 0:
+            raise RuntimeError(f"liloc_host_run failed ({rc}): " + (lib().liloc_host_error(self._h) or b"").decode())
+        return reps
+
+    def num_keyframes(self) -> int:
+        return lib().liloc_host_num_keyframes(self._h)
+
+    def keyposes(self) -> np.ndarray:
+        n = self.num_keyframes()
+        out = np.zeros((max(n, 1), 7), np.float64)
+        lib().liloc_host_keyposes(self._h, out.ctypes.data, n)
+        return out[:n]
+
+    def last_selection(self) -> np.ndarray:
+        ids = np.zeros(4096, np.int32)
+        n = lib().liloc_host_last_selection(self._h, ids.ctypes.data, len(ids))
+        return ids[:n].copy()
+
+    # ---- host-logic hooks (CPU tests) ----
+    def debug_add_keypose(self, pose6, time: float):
+        p = np.ascontiguousarray(pose6, np.float32)
+        lib().liloc_host_debug_add_keypose(self._h, p.ctypes.data, float(time))
+
+    def debug_extract_nearby(self, stamp: float) -> np.ndarray:
+        ids = np.zeros(8192, np.int32)
+        n = lib().liloc_host_debug_extract_nearby(self._h, float(stamp), ids.ctypes.data, len(ids))
+        return ids[:n].copy()
+
+    def debug_set_pose(self, pose6):
+        p = np.ascontiguousarray(pose6, np.float32)
+        lib().liloc_host_debug_set_pose(self._h, p.ctypes.data)
+
+    def debug_get_pose(self) -> np.ndarray:
+        p = np.zeros(6, np.float32)
+        lib().liloc_host_debug_get_pose(self._h, p.ctypes.data)
+        return p
+
+    def debug_update_initial_guess(self, info: CloudInfo) -> np.ndarray:
+        lib().liloc_host_debug_update_initial_guess(self._h, C.byref(info))
+        return self.debug_get_pose()
+
+    def debug_save_frame(self) -> bool:
+        return bool(lib().liloc_host_debug_save_frame(self._h))
+
+    def debug_transform_update(self, info: CloudInfo) -> np.ndarray:
+        lib().liloc_host_debug_transform_update(self._h, C.byref(info))
+        return self.debug_get_pose()
+
+    def ctx_handle(self) -> int:
+        return lib().liloc_host_ctx(self._h)
+
+
+def make_infos(scans, odom_poses6, stamps, device_ptrs=None):
+    """Build a ctypes array of CloudInfo.  scans: list of (n,4) float32 host arrays (kept alive by the
+    caller); odom_poses6: (F,6) [roll,pitch,yaw,x,y,z] 'IMU pre-integration' poses (initialGuess*);
+    device_ptrs: optional list of (ptr, n) for device-resident clouds."""
+    F = len(stamps)
+    arr = (CloudInfo * F)()
+    for i in range(F):
+        ci = arr[i]
+        ci.stamp = float(stamps[i])
+        ci.imuAvailable, ci.odomAvailable = 0, 1
+        r, p, y, x, yy, z = [float(v) for v in odom_poses6[i]]
+        ci.imuRollInit, ci.imuPitchInit, ci.imuYawInit = r, p, y
+        ci.initialGuessX, ci.initialGuessY, ci.initialGuessZ = x, yy, z
+        ci.initialGuessRoll, ci.initialGuessPitch, ci.initialGuessYaw = r, p, y
+        if device_ptrs is not None:
+            ci.cloud_deskewed, ci.cloud_size, ci.cloud_on_device = int(device_ptrs[i][0]), int(device_ptrs[i][1]), 1
+        else:
+            ci.cloud_deskewed, ci.cloud_size, ci.cloud_on_device = scans[i].ctypes.data, len(scans[i]), 0
+    return arr

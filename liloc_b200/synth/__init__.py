@@ -131,3 +131,40 @@ def rot_zyx(roll, pitch, yaw) -> np.ndarray:
     return np.array([[cy * cp, cy * sp * sr - sy * cr, sy * sr + cy * sp * cr],
                      [sy * cp, cy * cr + sy * sp * sr, sy * sp * cr - cy * sr],
                      [-sp, cp * sr, cp * cr]])
+
+
+@dataclass
+class Sequence:
+    """A synthetic lio sequence: what three ROS nodes would deliver to mapOptimization frame by frame."""
+    sensor: Sensor
+    world: np.ndarray
+    truth: np.ndarray          # (F, 6) float64 ground-truth sensor poses
+    odom: np.ndarray           # (F, 6) float32 'IMU pre-integration' poses (cloud_info.initialGuess*)
+    stamps: np.ndarray         # (F,) seconds
+    scans: list                # F body-frame clouds (n_i, 4) float32
+
+
+def make_sequence(sensor: Sensor, n_frames: int, seed: int, world_size=(120.0, 80.0), n_pillars=40,
+                  loop_radius=(45.0, 25.0), dt=0.2, odom_sigma=(0.01, 0.002), start_frac=0.0, n_total=None) -> Sequence:
+    """cfg 2 of SURVEY 8d: frames along a closed loop inside a box world with pillars; `dt` is the stamp
+    spacing (use the yaml's timeInterval so that every frame passes the rate gate, :257)."""
+    world = make_world(size_xy=world_size, height=12.0, n_pillars=n_pillars, seed=seed)
+    # keep pillars off the path
+    keep = [0]
+    for b in range(1, len(world)):
+        cx, cy = 0.5 * (world[b, 0] + world[b, 3]), 0.5 * (world[b, 1] + world[b, 4])
+        rr = (cx / loop_radius[0]) ** 2 + (cy / loop_radius[1]) ** 2
+        if abs(np.sqrt(rr) - 1.0) > 0.12:
+            keep.append(b)
+    world = world[keep]
+    n_total = n_frames if n_total is None else max(n_total, n_frames)   # trajectory spacing of an n_total-frame loop
+    truth = trajectory_loop(n_total, radius_xy=loop_radius)
+    if start_frac:
+        truth = np.roll(truth, -int(start_frac * n_total), axis=0)
+    truth = truth[:n_frames]
+    rng = np.random.default_rng(seed + 77)
+    odom = truth.copy()
+    odom[:, 3:] += rng.normal(0, odom_sigma[0], (n_frames, 3))
+    odom[:, :3] += rng.normal(0, odom_sigma[1], (n_frames, 3))
+    scans = [scan(world, truth[k], sensor, seed * 100003 + k) for k in range(n_frames)]
+    return Sequence(sensor, world, truth, odom.astype(np.float32), np.arange(n_frames) * dt + 100.0, scans)

@@ -80,3 +80,28 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def reference_params():
+    """tests/golden/reference_params.json: the values of every ParamServer key (include/utility.h:195-304)
+    as written in the reference's own config/*.yaml, parsed with pyyaml in this container."""
+    import json
+    import yaml
+    ref = "/root/reference/config"
+    out = {}
+    for name in ("lio_sam_default.yaml", "nclt.yaml", "m2dgr.yaml", "lio_sam_mid360.yaml"):
+        with open(os.path.join(ref, name)) as f:
+            y = yaml.safe_load(f)
+        flat = {}
+        for sec in ("System", "Sensors", "Mapping"):
+            for k, v in y[sec].items():
+                if k in ("savePCDDirectory", "saveSessionDirectory"):
+                    continue
+                flat[f"{sec}/{k}"] = v
+        out[name] = flat
+    with open(os.path.join(HERE, "reference_params.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and os.path.isdir("/root/reference/config"):
+    reference_params()

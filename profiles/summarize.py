@@ -1,0 +1,51 @@
+"""Turns ncu outputs brought back in gpurun_out/ into the small text summaries committed here.
+
+  python profiles/summarize.py launches gpurun_out/launches_r01.csv  > profiles/launches_r01.txt
+  python profiles/summarize.py raw      gpurun_out/top_r01.ncu-rep   > profiles/top_r01.txt
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(list)
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
+        agg[re.sub(r"\(.*", "", row["Kernel Name"])[:80]].append(v)
+    tot = sum(sum(v) for v in agg.values())
+    print(f"# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none` ({path})")
+    print("# (serialised, cold-cache launches: compare SHARES, not absolutes)")
+    print(f"# total {tot:.1f} us over {sum(len(v) for v in agg.values())} launches")
+    print(f"{'kernel':82s} {'n':>5s} {'mean_us':>9s} {'share':>7s}")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{k:82s} {len(v):5d} {sum(v) / len(v):9.2f} {100 * sum(v) / tot:6.1f}%")
+
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def raw(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# selected metrics from `ncu --set full --clock-control none` ({path}); one block per captured launch")
+    for row in rows[2:]:
+        print("kernel:", re.sub(r"\(.*", "", row[hdr.index("Kernel Name")])[:90])
+        for w in WANT:
+            if w in hdr:
+                print(f"    {w:62s} {row[hdr.index(w)]:>16s} {units[hdr.index(w)]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])

@@ -113,6 +113,42 @@ int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K
                 const liloc_point* scan, int n_scan, int scan_on_device, float scan_leaf,
                 float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res);
 
+/* ---- relo-mode NDT registration: pcl::Registration interface of `registration` (:118) ----------------
+ * Replaces ndt_omp's pclomp::NormalDistributionsTransform as LiLoc configures it (:175-199): a target is a
+ * prior-session submap (setInputTarget, :273, anchorOptimize.hpp:394), a source is the full de-skewed scan
+ * (setInputSource, :274, anchorOptimize.hpp:395), a job is one align() from an initial guess (:284,
+ * anchorOptimize.hpp:404).  Jobs are independent and run batched; n_align = 2 reproduces the two
+ * back-to-back align calls of the relocalisation init (:282-290).  The voxel-covariance grid of a target is
+ * built once per id and cached (the reference rebuilds it on every setInputTarget). */
+#define LILOC_NDT_DIRECT1 0
+#define LILOC_NDT_DIRECT7 1
+typedef struct {
+    double step_size;       /* [0.1]  pclomp default */
+    double outlier_ratio;   /* [0.55] pclomp default */
+    double trans_eps;       /* ndtEpsilon (:178) */
+    int max_iterations;     /* [35]   pclomp default */
+    int search;             /* LILOC_NDT_DIRECT1 | LILOC_NDT_DIRECT7  (regMethod, :181-190) */
+    int n_align;            /* [1]; 2 for the relocalisation init */
+    int reserved;
+} liloc_ndt_opts;
+typedef struct { int target_id, source_id; float guess[16]; } liloc_ndt_job;     /* guess: row-major 4x4 (init_guess, :276-280) */
+typedef struct {
+    float T[16];            /* getFinalTransformation(), row-major 4x4 */
+    double score;           /* sum of per-point scores; trans_probability = score / n_source */
+    int iterations;         /* nr_iterations_, summed over the n_align passes */
+    int converged;
+    int sweeps;             /* derivative sweeps executed (incl. line-search evaluations) */
+    int n_source;
+} liloc_ndt_out;
+int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts_map, int n, float resolution, int* n_leaves_out);
+int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts_body, int n, int on_device);
+int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs);
+int liloc_ndt_clear(liloc_ctx* ctx);
+/* leaf records of a target (tests): means[3n] double, icovs[9n] float, counts[n], keys[n] (voxel index) */
+int liloc_ndt_target_get(liloc_ctx* ctx, int target_id, double* means, float* icovs, int* counts, int* keys, int cap);
+/* one derivative sweep at pose p6 = [tx,ty,tz,rx,ry,rz] (tests): out28 = score, gradient[6], Hessian upper[21] */
+int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const double* p6, const liloc_ndt_opts* opts, double* out28);
+
 /* ---- kernel-level entry points (used by the parity tests; no reference caller) ------------------ */
 /* pcl::VoxelGrid<PointXYZI>::filter on a host cloud -> host cloud (cap >= n). */
 int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, liloc_point* out, int cap, int* m_out);

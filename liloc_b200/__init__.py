@@ -5,9 +5,9 @@ Python binding used by the tests and ``bench.py``.  There is no CPU fallback: im
 ``liloc_b200.abi`` raises if the shared library has not been built (``python -m liloc_b200._build``).
 """
 from .abi import (  # noqa: F401
-    Context, LilocError, S2mOpts, S2mResult, lib, lib_path, POINT_DTYPE,
+    Context, LilocError, S2mOpts, S2mResult, NdtOpts, lib, lib_path, POINT_DTYPE,
     LILOC_OK, LILOC_SKIPPED,
 )
 
-__all__ = ["Context", "LilocError", "S2mOpts", "S2mResult", "lib", "lib_path", "POINT_DTYPE",
+__all__ = ["Context", "LilocError", "S2mOpts", "S2mResult", "NdtOpts", "lib", "lib_path", "POINT_DTYPE",
            "LILOC_OK", "LILOC_SKIPPED"]

@@ -65,6 +65,24 @@ def stats_of(ctx_handle) -> dict:
     return st.as_dict()
 
 
+class NdtOpts(C.Structure):
+    """liloc_ndt_opts; defaults = ndt_omp defaults + LiLoc's yaml (ndtEpsilon 0.01, regMethod DIRECT1)."""
+    _fields_ = [("step_size", C.c_double), ("outlier_ratio", C.c_double), ("trans_eps", C.c_double),
+                ("max_iterations", C.c_int), ("search", C.c_int), ("n_align", C.c_int), ("reserved", C.c_int)]
+
+    def __init__(self, trans_eps=0.01, search=0, n_align=1, step_size=0.1, outlier_ratio=0.55, max_iterations=35):
+        super().__init__(step_size, outlier_ratio, float(np.float32(trans_eps)), max_iterations, search, n_align, 0)
+
+
+class NdtJob(C.Structure):
+    _fields_ = [("target_id", C.c_int), ("source_id", C.c_int), ("guess", C.c_float * 16)]
+
+
+class NdtOut(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("score", C.c_double), ("iterations", C.c_int), ("converged", C.c_int),
+                ("sweeps", C.c_int), ("n_source", C.c_int)]
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(lib_path):
         raise ImportError(
@@ -99,6 +117,12 @@ def _load() -> C.CDLL:
         "liloc_set_timing": (C.c_int, [P, C.c_int]),
         "liloc_kernel_launches": (C.c_longlong, [P]),
         "liloc_last_trace": (C.c_int, [P, P, C.c_int]),
+        "liloc_ndt_target_put": (C.c_int, [P, C.c_int, P, C.c_int, C.c_float, ip]),
+        "liloc_ndt_source_put": (C.c_int, [P, C.c_int, P, C.c_int, C.c_int]),
+        "liloc_ndt_align_batch": (C.c_int, [P, C.POINTER(NdtJob), C.c_int, C.POINTER(NdtOpts), C.POINTER(NdtOut)]),
+        "liloc_ndt_clear": (C.c_int, [P]),
+        "liloc_ndt_target_get": (C.c_int, [P, C.c_int, P, P, P, P, C.c_int]),
+        "liloc_ndt_derivatives": (C.c_int, [P, C.c_int, C.c_int, P, C.POINTER(NdtOpts), P]),
         "liloc_last_clocks": (C.c_int, [P, P, C.c_int]),
         "liloc_stats_get": (C.c_int, [P, C.POINTER(Stats)]),
         "liloc_stats_reset": (C.c_int, [P]),
@@ -117,7 +141,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_keyframe_put_from_scan liloc_keyframe_size liloc_keyframe_clear liloc_localmap_build "
            "liloc_localmap_set liloc_localmap_get liloc_scan_put liloc_scan_put_dev liloc_scan_ds_get "
            "liloc_scan2map liloc_frame liloc_voxelgrid liloc_knn5 liloc_surf_pass liloc_pose_to_T "
-           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane").split()
+           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -272,6 +296,55 @@ class Context:
         T = np.empty(12, np.float32)
         self._chk(lib.liloc_pose_to_T(self._h, _ptr(pose), _ptr(T)))
         return T.reshape(3, 4)
+
+    # ---- NDT (relo mode) ----
+    def ndt_target_put(self, target_id: int, pts_map, resolution: float) -> int:
+        p = _cloud(pts_map)
+        n = C.c_int()
+        self._chk(lib.liloc_ndt_target_put(self._h, target_id, _ptr(p), len(p), resolution, C.byref(n)))
+        return n.value
+
+    def ndt_source_put(self, source_id: int, pts_body=None, dev_ptr: int | None = None, n: int | None = None) -> None:
+        if dev_ptr is not None:
+            self._chk(lib.liloc_ndt_source_put(self._h, source_id, C.c_void_p(dev_ptr), int(n), 1))
+        else:
+            p = _cloud(pts_body)
+            self._chk(lib.liloc_ndt_source_put(self._h, source_id, _ptr(p), len(p), 0))
+
+    def ndt_clear(self) -> None:
+        self._chk(lib.liloc_ndt_clear(self._h))
+
+    def ndt_align_batch(self, target_ids, source_ids, guesses, opts: NdtOpts | None = None):
+        """guesses: (J, 4, 4) or (J, 3, 4) float32 row-major.  Returns (T (J,4,4), score, iterations, converged, sweeps)."""
+        g = np.asarray(guesses, np.float32)
+        J = len(g)
+        jobs = (NdtJob * J)()
+        for j in range(J):
+            jobs[j].target_id, jobs[j].source_id = int(target_ids[j]), int(source_ids[j])
+            m = np.eye(4, dtype=np.float32)
+            m[: g[j].shape[0], :] = g[j]
+            jobs[j].guess[:] = m.reshape(16).tolist()
+        outs = (NdtOut * J)()
+        o = opts or NdtOpts()
+        self._chk(lib.liloc_ndt_align_batch(self._h, jobs, J, C.byref(o), outs))
+        T = np.array([list(r.T) for r in outs], np.float32).reshape(J, 4, 4)
+        return (T, np.array([r.score for r in outs]), np.array([r.iterations for r in outs]),
+                np.array([r.converged for r in outs]), np.array([r.sweeps for r in outs]))
+
+    def ndt_target_get(self, target_id: int):
+        n = lib.liloc_ndt_target_get(self._h, target_id, None, None, None, None, 0)
+        means, icovs = np.zeros((max(n, 1), 3)), np.zeros((max(n, 1), 9), np.float32)
+        counts, keys = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        self._chk(lib.liloc_ndt_target_get(self._h, target_id, _ptr(means), _ptr(icovs), _ptr(counts), _ptr(keys), n))
+        o = np.argsort(keys[:n], kind="stable")
+        return means[:n][o], icovs[:n][o], counts[:n][o], keys[:n][o]
+
+    def ndt_derivatives(self, target_id: int, source_id: int, p6, opts: NdtOpts | None = None) -> np.ndarray:
+        p = np.ascontiguousarray(p6, np.float64).reshape(6)
+        out = np.zeros(28)
+        o = opts or NdtOpts()
+        self._chk(lib.liloc_ndt_derivatives(self._h, target_id, source_id, _ptr(p), C.byref(o), _ptr(out)))
+        return out
 
     # ---- instrumentation ----
     def set_timing(self, on: bool) -> None:

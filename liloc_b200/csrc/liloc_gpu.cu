@@ -22,6 +22,7 @@
 #include "voxelgrid.cuh"
 #include "knn_grid.cuh"
 #include "s2m.cuh"
+#include "ndt.cuh"
 
 using namespace liloc;
 
@@ -111,6 +112,18 @@ struct liloc_ctx {
     S2mResult* d_result = nullptr;
     int s2m_max_blocks = 0;
     int s2m_nq_last = 0;
+
+    // NDT: cached targets (prior submaps), sources (scans), job state
+    struct NdtTargetHost { DevBuf<int> table; DevBuf<NdtLeaf> leaves; NdtTargetView view; int n_leaves; float resolution; int slot; };
+    struct NdtSourceHost { DevBuf<float4> own; NdtSourceView view; int slot; };
+    std::unordered_map<int, NdtTargetHost> ndt_targets;
+    std::unordered_map<int, NdtSourceHost> ndt_sources;
+    DevBuf<NdtTargetView> d_tviews;
+    DevBuf<NdtSourceView> d_sviews;
+    DevBuf<NdtJob> d_jobs;
+    DevBuf<double> ndt_partial;
+    int* d_ndt_active = nullptr;
+    bool ndt_views_dirty = true;
 
     // kernel-level test scratch
     DevBuf<float4> tmp_pts;
@@ -208,13 +221,13 @@ __global__ void k_debug_plane(const float* pts, int n, float* x) {
 // `bits` = radix-sort key bits (32 = always safe; fewer = one 8-bit pass less, verified by the caller against
 // VgParams.key_bits after the fact).
 int vg_run(liloc_ctx* ctx, VgInst& vi, cudaStream_t st, const float4* d_pts, int n, float leaf, bool have_minmax,
-           DevBuf<float4>& out, int bits) {
+           DevBuf<float4>& out, int bits, bool sort_only = false) {
     if (n <= 0) {
         k_set_int<<<1, 1, 0, st>>>(vi.d_count, 0); KCHECK();
         return 0;
     }
     int rc;
-    if ((rc = ensure(ctx, out, (size_t)n))) return rc;
+    if (!sort_only && (rc = ensure(ctx, out, (size_t)n))) return rc;
     if ((rc = ensure(ctx, vi.keys_a, (size_t)n))) return rc;
     if ((rc = ensure(ctx, vi.keys_b, (size_t)n))) return rc;
     if ((rc = ensure(ctx, vi.vals_a, (size_t)n))) return rc;
@@ -236,6 +249,7 @@ int vg_run(liloc_ctx* ctx, VgInst& vi, cudaStream_t st, const float4* d_pts, int
     k_vg_keys<<<blocks_for(ctx, n, 256 * 4), 256, 0, st>>>(d_pts, n, vi.d_vp, vi.keys_a.p, vi.vals_a.p); KCHECK();
     size_t tb = vi.cub_tmp.cap;
     CU(cub::DeviceRadixSort::SortPairs(vi.cub_tmp.p, tb, vi.keys_a.p, vi.keys_b.p, vi.vals_a.p, vi.vals_b.p, n, 0, bits, st));
+    if (sort_only) return 0;
     k_run_count<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, n, vi.tile_counts.p); KCHECK();
     k_scan_tiles<<<1, 1024, 0, st>>>(vi.tile_counts.p, n_tiles, vi.d_count); KCHECK();
     k_run_centroids<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, vi.vals_b.p, n, vi.tile_counts.p, d_pts, out.p); KCHECK();
@@ -451,6 +465,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaMemset(c->d_result, 0, sizeof(S2mResult)));
     CUB_(cudaMemset(c->d_M, 0, sizeof(int)));
     CUB_(cudaMemset(c->d_Q, 0, sizeof(int)));
+    CUB_(cudaMalloc(&c->d_ndt_active, sizeof(int)));
     CUB_(cudaMallocHost(&c->h_info, sizeof(HostFrameInfo)));
     std::memset(c->h_info, 0, sizeof(HostFrameInfo));
     for (auto& e : c->ev) CUB_(cudaEventCreate(&e));
@@ -492,6 +507,9 @@ void liloc_destroy(liloc_ctx* c) {
     fr(c->cell_counts.p); fr(c->cell_start.p); fr(c->cell_cursor.p); fr(c->cpts.p);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
+    for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
+    for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
+    fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
     if (c->h_descs) cudaFreeHost(c->h_descs);
     if (c->h_info) cudaFreeHost(c->h_info);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -793,6 +811,214 @@ int liloc_debug_plane(liloc_ctx* ctx, const float* pts15, int n, float* x3) {
     CU(cudaStreamSynchronize(ctx->stream));
     return LILOC_OK;
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// NDT
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+NdtOptsDev ndt_opts_dev(const liloc_ndt_opts* o, float resolution) {
+    NdtOptsDev d{};
+    const double c1 = 10.0 * (1.0 - o->outlier_ratio), c2 = o->outlier_ratio / pow((double)resolution, 3);
+    const double d3 = -log(c2);
+    d.d1 = -log(c1 + c2) - d3;
+    d.d2 = -2.0 * log((-log(c1 * exp(-0.5) + c2) - d3) / d.d1);
+    d.step_max = o->step_size; d.step_min = o->trans_eps / 2.0; d.eps = o->trans_eps;
+    d.max_iterations = o->max_iterations; d.search7 = o->search == LILOC_NDT_DIRECT7 ? 1 : 0;
+    d.n_align = o->n_align > 0 ? o->n_align : 1;
+    return d;
+}
+
+const liloc_ndt_opts kDefaultNdtOpts = {0.1, 0.55, 0.01, 35, LILOC_NDT_DIRECT1, 1, 0};
+
+int ndt_sync_views(liloc_ctx* ctx) {
+    if (!ctx->ndt_views_dirty) return 0;
+    int rc;
+    std::vector<NdtTargetView> tv(ctx->ndt_targets.size());
+    std::vector<NdtSourceView> sv(ctx->ndt_sources.size());
+    int i = 0;
+    for (auto& kv : ctx->ndt_targets) { kv.second.slot = i; tv[i++] = kv.second.view; }
+    i = 0;
+    for (auto& kv : ctx->ndt_sources) { kv.second.slot = i; sv[i++] = kv.second.view; }
+    if ((rc = ensure(ctx, ctx->d_tviews, tv.size() ? tv.size() : 1))) return rc;
+    if ((rc = ensure(ctx, ctx->d_sviews, sv.size() ? sv.size() : 1))) return rc;
+    if (!tv.empty()) CU(cudaMemcpyAsync(ctx->d_tviews.p, tv.data(), tv.size() * sizeof(NdtTargetView), cudaMemcpyHostToDevice, ctx->stream));
+    if (!sv.empty()) CU(cudaMemcpyAsync(ctx->d_sviews.p, sv.data(), sv.size() * sizeof(NdtSourceView), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));      // the staging vectors die here
+    ctx->ndt_views_dirty = false;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, int n, float resolution, int* n_leaves_out) {
+    ENTER(ctx);
+    if (n <= 0 || !pts || !(resolution > 0.f)) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<float4> none;
+    if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->tmp_pts.p, n, resolution, false, none, 32, true))) return rc;
+    VgParams vp;
+    CU(cudaMemcpyAsync(&vp, ctx->vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (vp.overflow) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_target_put: leaf size too small for the target extent (PCL overflow guard)");
+    liloc_ctx::NdtTargetHost& T = ctx->ndt_targets[target_id];
+    int divb[3];
+    divb[0] = vp.mul[1]; divb[1] = vp.mul[1] ? vp.mul[2] / vp.mul[1] : 1;
+    divb[2] = (int)floorf(vp.mx[2] * vp.inv_leaf) - vp.minb[2] + 1;
+    const long long ncell = (long long)divb[0] * divb[1] * divb[2];
+    if (ncell > (1LL << 28)) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_target_put: %lld voxels exceed the dense table limit", ncell);
+    if ((rc = ensure(ctx, T.table, (size_t)ncell))) return rc;
+    if ((rc = ensure(ctx, T.leaves, (size_t)(n / 6 + 1)))) return rc;
+    k_fill_int<<<blocks_for(ctx, ncell, 256 * 4), 256, 0, ctx->stream>>>(T.table.p, ncell, -1); KCHECK();
+    CU(cudaMemsetAsync(ctx->d_ndt_active, 0, sizeof(int), ctx->stream));
+    k_ndt_leaves<<<blocks_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->vg_map.keys_b.p, ctx->vg_map.vals_b.p, n, ctx->tmp_pts.p, T.leaves.p, T.table.p, ctx->d_ndt_active); KCHECK();
+    int nl = 0;
+    CU(cudaMemcpyAsync(&nl, ctx->d_ndt_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    T.n_leaves = nl; T.resolution = resolution;
+    T.view.table = T.table.p; T.view.leaves = T.leaves.p; T.view.inv_leaf = vp.inv_leaf;
+    for (int a = 0; a < 3; ++a) { T.view.minb[a] = vp.minb[a]; T.view.divb[a] = divb[a]; T.view.maxb[a] = vp.minb[a] + divb[a] - 1; }
+    ctx->ndt_views_dirty = true;
+    if (n_leaves_out) *n_leaves_out = nl;
+    return LILOC_OK;
+}
+
+int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts, int n, int on_device) {
+    ENTER(ctx);
+    if (n <= 0 || !pts) return fail(ctx, LILOC_ERR_ARG, "ndt_source_put: bad arguments");
+    liloc_ctx::NdtSourceHost& S = ctx->ndt_sources[source_id];
+    if (on_device) {
+        S.view.pts = reinterpret_cast<const float4*>(pts);
+    } else {
+        int rc;
+        if ((rc = ensure(ctx, S.own, (size_t)n))) return rc;
+        CU(cudaMemcpyAsync(S.own.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (long long)n * 16;
+        S.view.pts = S.own.p;
+    }
+    S.view.n = n;
+    ctx->ndt_views_dirty = true;
+    return LILOC_OK;
+}
+
+int liloc_ndt_clear(liloc_ctx* ctx) {
+    ENTER(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& kv : ctx->ndt_targets) { if (kv.second.table.p) cudaFree(kv.second.table.p); if (kv.second.leaves.p) cudaFree(kv.second.leaves.p); }
+    for (auto& kv : ctx->ndt_sources) if (kv.second.own.p) cudaFree(kv.second.own.p);
+    ctx->ndt_targets.clear(); ctx->ndt_sources.clear(); ctx->ndt_views_dirty = true;
+    return LILOC_OK;
+}
+
+int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs) {
+    ENTER(ctx);
+    if (n_jobs <= 0 || !jobs || !outs) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: bad arguments");
+    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
+    int rc;
+    if ((rc = ndt_sync_views(ctx))) return rc;
+    std::vector<NdtJob> hj((size_t)n_jobs);
+    int max_n = 0;
+    float resolution = -1.f;
+    for (int j = 0; j < n_jobs; ++j) {
+        auto ti = ctx->ndt_targets.find(jobs[j].target_id);
+        auto si = ctx->ndt_sources.find(jobs[j].source_id);
+        if (ti == ctx->ndt_targets.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown target id %d", jobs[j].target_id);
+        if (si == ctx->ndt_sources.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown source id %d", jobs[j].source_id);
+        if (resolution < 0.f) resolution = ti->second.resolution;
+        else if (resolution != ti->second.resolution) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: all targets of one batch must share the resolution");
+        std::memset(&hj[j], 0, sizeof(NdtJob));
+        hj[j].target = ti->second.slot; hj[j].source = si->second.slot;
+        std::memcpy(hj[j].guess, jobs[j].guess, 12 * sizeof(float));     // top 3 rows of the row-major 4x4
+        if (si->second.view.n > max_n) max_n = si->second.view.n;
+    }
+    const NdtOptsDev od = ndt_opts_dev(o, resolution);
+    const int tiles = (max_n + kNdtThreads - 1) / kNdtThreads;
+    if ((rc = ensure(ctx, ctx->d_jobs, (size_t)n_jobs))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_partial, (size_t)n_jobs * tiles * kNdtSums))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
+    k_ndt_begin<<<(n_jobs + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_jobs.p, n_jobs); KCHECK();
+    // worst case per align pass: first sweep + (max_iterations + 2) x (1 + 10) line-search sweeps
+    const int max_sweeps = od.n_align * (1 + (od.max_iterations + 2) * 11);
+    const int check_every = 4;
+    int* h_active = &ctx->h_info->Q_all;                   // pinned scratch int
+    int done_sweeps = 0;
+    while (done_sweeps < max_sweeps) {
+        for (int k = 0; k < check_every; ++k) {
+            k_ndt_sweep<<<dim3(tiles, n_jobs), kNdtThreads, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_tviews.p, ctx->d_sviews.p, od, tiles, ctx->ndt_partial.p); KCHECK();
+            CU(cudaMemsetAsync(ctx->d_ndt_active, 0, sizeof(int), ctx->stream));
+            k_ndt_update<<<n_jobs, 32, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_sviews.p, od, tiles, ctx->ndt_partial.p, ctx->d_ndt_active); KCHECK();
+            ++done_sweeps;
+        }
+        CU(cudaMemcpyAsync(h_active, ctx->d_ndt_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (*h_active == 0) break;
+    }
+    CU(cudaMemcpyAsync(hj.data(), ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
+    for (int j = 0; j < n_jobs; ++j) {
+        liloc_ndt_out& r = outs[j];
+        std::memcpy(r.T, hj[j].Tfinal, 12 * sizeof(float));
+        r.T[12] = 0.f; r.T[13] = 0.f; r.T[14] = 0.f; r.T[15] = 1.f;
+        r.score = hj[j].score; r.iterations = hj[j].total_iterations; r.converged = hj[j].converged; r.sweeps = hj[j].total_sweeps;
+        r.n_source = ctx->ndt_sources[jobs[j].source_id].view.n;
+    }
+    return LILOC_OK;
+}
+
+int liloc_ndt_target_get(liloc_ctx* ctx, int target_id, double* means, float* icovs, int* counts, int* keys, int cap) {
+    ENTER(ctx);
+    auto ti = ctx->ndt_targets.find(target_id);
+    if (ti == ctx->ndt_targets.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_target_get: unknown target id %d", target_id);
+    const int n = ti->second.n_leaves;
+    if (!means) return n;
+    std::vector<NdtLeaf> h((size_t)(n > 0 ? n : 1));
+    if (n > 0) CU(cudaMemcpyAsync(h.data(), ti->second.leaves.p, (size_t)n * sizeof(NdtLeaf), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n && i < cap; ++i) {
+        for (int a = 0; a < 3; ++a) means[3 * i + a] = h[i].mean[a];
+        for (int q = 0; q < 9; ++q) icovs[9 * i + q] = h[i].icov[q];
+        counts[i] = h[i].n; keys[i] = h[i].pad;
+    }
+    return n;
+}
+
+int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const double* p6, const liloc_ndt_opts* opts, double* out28) {
+    ENTER(ctx);
+    if (!p6 || !out28) return fail(ctx, LILOC_ERR_ARG, "ndt_derivatives: null argument");
+    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
+    int rc;
+    if ((rc = ndt_sync_views(ctx))) return rc;
+    auto ti = ctx->ndt_targets.find(target_id);
+    auto si = ctx->ndt_sources.find(source_id);
+    if (ti == ctx->ndt_targets.end() || si == ctx->ndt_sources.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_derivatives: unknown target or source id");
+    NdtJob J;
+    std::memset(&J, 0, sizeof(J));
+    J.target = ti->second.slot; J.source = si->second.slot; J.phase = NDT_AWAIT_FIRST;
+    for (int i = 0; i < 6; ++i) { J.p[i] = p6[i]; J.x_t[i] = p6[i]; }
+    const NdtOptsDev od = ndt_opts_dev(o, ti->second.resolution);
+    const int n = si->second.view.n, tiles = (n + kNdtThreads - 1) / kNdtThreads;
+    if ((rc = ensure(ctx, ctx->d_jobs, 1))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_partial, (size_t)tiles * kNdtSums))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_jobs.p, &J, sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
+    k_ndt_sweep<<<dim3(tiles, 1), kNdtThreads, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_tviews.p, ctx->d_sviews.p, od, tiles, ctx->ndt_partial.p); KCHECK();
+    std::vector<double> part((size_t)tiles * kNdtSums);
+    CU(cudaMemcpyAsync(part.data(), ctx->ndt_partial.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < kNdtSums; ++k) { double v = 0.0; for (int t = 0; t < tiles; ++t) v += part[(size_t)t * kNdtSums + k]; out28[k] = v; }
+    return LILOC_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t) {
     if (!ctx || !t) return LILOC_ERR_ARG;

@@ -1,0 +1,572 @@
+// liloc_b200/csrc/ndt.cuh -- relo-mode NDT registration on the device, batched over independent jobs.
+//
+// Replaces (reference): registration->setInputTarget / setInputSource / align / getFinalTransformation
+//   src/mapOptmization.cpp:273-287 (relocalisation init, 2 x align) and
+//   include/egoOptimization/anchorOptimize.hpp:394-407 (per-frame scan-matching factor),
+// which the reference delegates to ndt_omp (pclomp::NormalDistributionsTransform, un-vendored; algorithm
+// restated in SURVEY.md A.6 and oracle/ndt_oracle.cpp, whose operation order this file follows).
+//
+// Layout in HBM per target (prior submap): a dense cell -> leaf table (int32) over the target's voxel
+// bounding box and one 64-byte leaf record {mean double3, inverse covariance float9, count}.  A job is one
+// (target, source scan, initial guess) alignment; jobs never interact, which is what the multi-hypothesis
+// relocalisation (cfg 4) and the multi-submap JFGO matching (cfg 5) batch over.
+//
+// Kernels:  k_ndt_leaves   voxel runs -> Gaussian leaf records (sequential double sums in source order)
+//           k_ndt_sweep    one derivative sweep (score, gradient 6, Hessian 21) for every active job:
+//                          block = 256 points of one job, float per-point terms, double accumulation,
+//                          warp-shuffle + shared-memory reduction -> one partial per block
+//           k_ndt_update   per job: fixed-order reduction of the partials, then ONE step of the Newton /
+//                          More-Thuente state machine (all in double on the device; the host only polls
+//                          the number of unfinished jobs every few sweeps)
+#pragma once
+#include "common.cuh"
+#include "voxelgrid.cuh"
+
+namespace liloc {
+
+struct NdtLeaf { double mean[3]; float icov[9]; int n; int pad; };   // 64 bytes
+
+struct NdtTargetView {
+    const int* table;          // dense cell -> leaf index, -1 none
+    const NdtLeaf* leaves;
+    float inv_leaf;
+    int minb[3], maxb[3], divb[3];
+};
+
+struct NdtSourceView { const float4* pts; int n; };
+
+struct NdtOptsDev {
+    double d1, d2;             // gauss_d1_, gauss_d2_
+    double step_max, step_min, eps;
+    int max_iterations, search7, n_align;
+};
+
+enum { NDT_AWAIT_FIRST = 0, NDT_LS_FIRST = 1, NDT_LS_LOOP = 2, NDT_DONE = 3 };
+
+struct NdtJob {
+    int target, source, phase, align_pass;
+    int nr_iterations, converged, sweeps, step_iterations, open_interval, interval_converged;
+    double p[6], x_t[6], dir[6];
+    double score, phi_0, d_phi_0, a_l, f_l, g_l, a_u, f_u, g_u, a_t;
+    float Tfinal[12];
+    float guess[12];
+    int total_iterations, total_sweeps;
+};
+
+constexpr int kNdtThreads = 256;
+constexpr int kNdtSums = 28;      // score, gradient[6], Hessian upper triangle[21]
+
+// ---- small dense algebra in double, static indices only -------------------------------------------------
+template <int N, int P, int Q>
+__host__ __device__ __forceinline__ void jacobi_rotate_d(double (&A)[N][N], double (&U)[N][N]) {
+    const double apq = A[P][Q];
+    if (apq == 0.0) return;
+    const double theta = (A[Q][Q] - A[P][P]) / (2.0 * apq);
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c, h = t * apq;
+    A[P][P] -= h; A[Q][Q] += h; A[P][Q] = 0.0; A[Q][P] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (k == P || k == Q) continue;
+        const double akp = A[k][P], akq = A[k][Q];
+        const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+        A[k][P] = np_; A[P][k] = np_; A[k][Q] = nq_; A[Q][k] = nq_;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double ukp = U[k][P], ukq = U[k][Q];
+        U[k][P] = c * ukp - s * ukq; U[k][Q] = s * ukp + c * ukq;
+    }
+}
+
+template <int N>
+__host__ __device__ __forceinline__ bool jacobi_converged_d(const double (&A)[N][N]) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        diag += A[i][i] * A[i][i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) off += A[i][j] * A[i][j];
+    }
+    return off <= 1e-300 || off <= (2.220446049250313e-16 * 2.220446049250313e-16) * diag;
+}
+
+// eigenvalues w, eigenvectors = columns of U
+__host__ __device__ inline void jacobi3_d(double (&A)[3][3], double (&U)[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) U[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (jacobi_converged_d<3>(A)) break;
+        jacobi_rotate_d<3, 0, 1>(A, U); jacobi_rotate_d<3, 0, 2>(A, U); jacobi_rotate_d<3, 1, 2>(A, U);
+    }
+}
+
+__host__ __device__ inline void jacobi6_d(double (&A)[6][6], double (&U)[6][6]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) U[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (jacobi_converged_d<6>(A)) break;
+        jacobi_rotate_d<6, 0, 1>(A, U); jacobi_rotate_d<6, 0, 2>(A, U); jacobi_rotate_d<6, 0, 3>(A, U); jacobi_rotate_d<6, 0, 4>(A, U); jacobi_rotate_d<6, 0, 5>(A, U);
+        jacobi_rotate_d<6, 1, 2>(A, U); jacobi_rotate_d<6, 1, 3>(A, U); jacobi_rotate_d<6, 1, 4>(A, U); jacobi_rotate_d<6, 1, 5>(A, U);
+        jacobi_rotate_d<6, 2, 3>(A, U); jacobi_rotate_d<6, 2, 4>(A, U); jacobi_rotate_d<6, 2, 5>(A, U);
+        jacobi_rotate_d<6, 3, 4>(A, U); jacobi_rotate_d<6, 3, 5>(A, U);
+        jacobi_rotate_d<6, 4, 5>(A, U);
+    }
+}
+
+// ---- pose algebra at the 4x4 boundary (same operation order as the oracle) ------------------------------
+__host__ __device__ inline void ndt_pose_to_matrix(const double* p, float* T) {
+    const float a = (float)p[3], b = (float)p[4], c = (float)p[5];
+    const float ca = (float)cos((double)a), sa = (float)sin((double)a);
+    const float cb = (float)cos((double)b), sb = (float)sin((double)b);
+    const float cc = (float)cos((double)c), sc = (float)sin((double)c);
+    const float Rx[9] = {1, 0, 0, 0, ca, -sa, 0, sa, ca}, Ry[9] = {cb, 0, sb, 0, 1, 0, -sb, 0, cb}, Rz[9] = {cc, -sc, 0, sc, cc, 0, 0, 0, 1};
+    float M[9], R[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) M[i * 3 + j] = Rx[i * 3] * Ry[j] + Rx[i * 3 + 1] * Ry[3 + j] + Rx[i * 3 + 2] * Ry[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = M[i * 3] * Rz[j] + M[i * 3 + 1] * Rz[3 + j] + M[i * 3 + 2] * Rz[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { T[i * 4] = R[i * 3]; T[i * 4 + 1] = R[i * 3 + 1]; T[i * 4 + 2] = R[i * 3 + 2]; T[i * 4 + 3] = (float)p[i]; }
+}
+
+__host__ __device__ inline float ndt_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+__host__ __device__ inline void ndt_matrix_to_pose(const float* T, double* p) {
+    const float m00 = T[0], m01 = T[1], m02 = T[2], m10 = T[4], m11 = T[5], m12 = T[6], m20 = T[8], m21 = T[9], m22 = T[10];
+    float r0 = ndt_atan2f(m12, m22);
+    const float c2 = sqrtf(m00 * m00 + m01 * m01);
+    float r1;
+    if (r0 > 0.f) { r0 -= 3.14159265358979323846f; r1 = ndt_atan2f(-m02, -c2); }
+    else r1 = ndt_atan2f(-m02, c2);
+    const float s1 = (float)sin((double)r0), c1 = (float)cos((double)r0);
+    const float r2 = ndt_atan2f(s1 * m20 - c1 * m10, c1 * m11 - s1 * m21);
+    p[0] = T[3]; p[1] = T[7]; p[2] = T[11];
+    p[3] = -r0; p[4] = -r1; p[5] = -r2;
+}
+
+struct NdtAng { float j[8][3]; float h[15][3]; };
+
+__host__ __device__ inline void ndt_angle_derivatives(const double* p, NdtAng* A) {
+    double cx, cy, cz, sx, sy, sz;
+    if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
+    if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
+    if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
+    const double J[8][3] = {
+        {-sx * sz + cx * sy * cz, -sx * cz - cx * sy * sz, -cx * cy}, {cx * sz + sx * sy * cz, cx * cz - sx * sy * sz, -sx * cy},
+        {-sy * cz, sy * sz, cy}, {sx * cy * cz, -sx * cy * sz, sx * sy}, {-cx * cy * cz, cx * cy * sz, -cx * sy},
+        {-cy * sz, -cy * cz, 0}, {cx * cz - sx * sy * sz, -cx * sz - sx * sy * cz, 0}, {sx * cz + cx * sy * sz, cx * sy * cz - sx * sz, 0}};
+    const double H[15][3] = {
+        {-cx * sz - sx * sy * cz, -cx * cz + sx * sy * sz, sx * cy}, {-sx * sz + cx * sy * cz, -cx * sy * sz - sx * cz, -cx * cy},
+        {cx * cy * cz, -cx * cy * sz, cx * sy}, {sx * cy * cz, -sx * cy * sz, sx * sy},
+        {-sx * cz - cx * sy * sz, sx * sz - cx * sy * cz, 0}, {cx * cz - sx * sy * sz, -sx * sy * cz - cx * sz, 0},
+        {-cy * cz, cy * sz, sy}, {-sx * sy * cz, sx * sy * sz, sx * cy}, {cx * sy * cz, -cx * sy * sz, -cx * cy},
+        {sy * sz, sy * cz, 0}, {-sx * cy * sz, -sx * cy * cz, 0}, {cx * cy * sz, cx * cy * cz, 0},
+        {-cy * cz, cy * sz, 0}, {-cx * sz - sx * sy * cz, -cx * cz + sx * sy * sz, 0}, {-sx * sz + cx * sy * cz, -cx * sy * sz - sx * cz, 0}};
+    for (int r = 0; r < 8; ++r) for (int c = 0; c < 3; ++c) A->j[r][c] = (float)J[r][c];
+    for (int r = 0; r < 15; ++r) for (int c = 0; c < 3; ++c) A->h[r][c] = (float)H[r][c];
+}
+
+// ---- target build: one Gaussian leaf per voxel run ---------------------------------------------------------
+// skeys / svals: voxel keys sorted (stable) with their source indices.  One thread per run head walks its
+// run (double sums of p and p p^T in ascending source index), builds the leaf (ndt_omp VoxelGridCovariance,
+// SURVEY A.6) and publishes it in the dense table when it is usable (>= 6 points, finite inverse).
+__global__ void __launch_bounds__(256)
+k_ndt_leaves(const unsigned* __restrict__ skeys, const unsigned* __restrict__ svals, int n, const float4* __restrict__ pts,
+             NdtLeaf* __restrict__ leaves, int* __restrict__ table, int* __restrict__ n_leaves) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned key = skeys[i];
+        if (i > 0 && skeys[i - 1] == key) continue;
+        double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};      // xx xy xz yy yz zz
+        int e = i;
+        do {
+            const float4 p = __ldg(&pts[svals[e]]);
+            const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+            s[0] += x; s[1] += y; s[2] += z;
+            ss[0] += x * x; ss[1] += x * y; ss[2] += x * z; ss[3] += y * y; ss[4] += y * z; ss[5] += z * z;
+            ++e;
+        } while (e < n && skeys[e] == key);
+        const int cnt = e - i;
+        if (cnt < 6) continue;
+        const double nn = (double)cnt;
+        const double mean[3] = {s[0] / nn, s[1] / nn, s[2] / nn};
+        const double S[3][3] = {{ss[0], ss[1], ss[2]}, {ss[1], ss[3], ss[4]}, {ss[2], ss[4], ss[5]}};
+        double cov[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) cov[a][b] = ((S[a][b] - 2.0 * (s[a] * mean[b])) / nn + mean[a] * mean[b]) * ((nn - 1.0) / nn);
+        double A[3][3], U[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) A[a][b] = 0.5 * (cov[a][b] + cov[b][a]);
+        jacobi3_d(A, U);
+        // ascending eigenvalues, ties by index
+        double w[3] = {A[0][0], A[1][1], A[2][2]};
+        int o0 = 0, o1 = 1, o2 = 2;
+        if (w[o1] < w[o0]) { const int t = o0; o0 = o1; o1 = t; }
+        if (w[o2] < w[o1]) { const int t = o1; o1 = o2; o2 = t; }
+        if (w[o1] < w[o0]) { const int t = o0; o0 = o1; o1 = t; }
+        double ev0 = (o0 == 0 ? w[0] : o0 == 1 ? w[1] : w[2]), ev1 = (o1 == 0 ? w[0] : o1 == 1 ? w[1] : w[2]), ev2 = (o2 == 0 ? w[0] : o2 == 1 ? w[1] : w[2]);
+        if (ev0 < 0 || ev1 < 0 || ev2 <= 0) continue;
+        const double min_ev = 0.01 * ev2;
+        if (ev0 < min_ev) {
+            ev0 = min_ev;
+            if (ev1 < min_ev) ev1 = min_ev;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    const double va0 = (o0 == 0 ? U[a][0] : o0 == 1 ? U[a][1] : U[a][2]), vb0 = (o0 == 0 ? U[b][0] : o0 == 1 ? U[b][1] : U[b][2]);
+                    const double va1 = (o1 == 0 ? U[a][0] : o1 == 1 ? U[a][1] : U[a][2]), vb1 = (o1 == 0 ? U[b][0] : o1 == 1 ? U[b][1] : U[b][2]);
+                    const double va2 = (o2 == 0 ? U[a][0] : o2 == 1 ? U[a][1] : U[a][2]), vb2 = (o2 == 0 ? U[b][0] : o2 == 1 ? U[b][1] : U[b][2]);
+                    double acc = 0.0;
+                    acc += va0 * ev0 * vb0; acc += va1 * ev1 * vb1; acc += va2 * ev2 * vb2;
+                    cov[a][b] = acc;
+                }
+        }
+        const double a = cov[0][0], b = cov[0][1], c = cov[0][2], d = cov[1][0], e2 = cov[1][1], f = cov[1][2], g = cov[2][0], h = cov[2][1], k = cov[2][2];
+        const double det = a * (e2 * k - f * h) - b * (d * k - f * g) + c * (d * h - e2 * g);
+        const double id = 1.0 / det;
+        const double inv[9] = {(e2 * k - f * h) * id, (c * h - b * k) * id, (b * f - c * e2) * id,
+                               (f * g - d * k) * id, (a * k - c * g) * id, (c * d - a * f) * id,
+                               (d * h - e2 * g) * id, (b * g - a * h) * id, (a * e2 - b * d) * id};
+        bool finite = true;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) finite = finite && isfinite(inv[q]);
+        if (!finite) continue;
+        const int slot = atomicAdd(n_leaves, 1);
+        NdtLeaf L;
+        L.mean[0] = mean[0]; L.mean[1] = mean[1]; L.mean[2] = mean[2];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) L.icov[q] = (float)inv[q];
+        L.n = cnt; L.pad = (int)key;
+        leaves[slot] = L;
+        table[key] = slot;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_int(int* __restrict__ a, long long n, int v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = v;
+}
+
+// ---- derivative sweep ------------------------------------------------------------------------------------------
+LILOC_DEV int ndt_lookup(const NdtTargetView& t, float x, float y, float z, int dx, int dy, int dz) {
+    const int i = (int)floorf(x * t.inv_leaf) + dx, j = (int)floorf(y * t.inv_leaf) + dy, k = (int)floorf(z * t.inv_leaf) + dz;
+    if (i < t.minb[0] || i > t.maxb[0] || j < t.minb[1] || j > t.maxb[1] || k < t.minb[2] || k > t.maxb[2]) return -1;
+    return __ldg(&t.table[(size_t)(i - t.minb[0]) + (size_t)(j - t.minb[1]) * t.divb[0] + (size_t)(k - t.minb[2]) * t.divb[0] * t.divb[1]]);
+}
+
+// updateDerivatives (compute_hessian = true) for one (point, cell) pair, added into acc[28] (double).
+LILOC_DEV void ndt_point_cell(const float (&x)[3], const float (&xt)[3], const NdtLeaf* __restrict__ L, const NdtAng& A,
+                              const double d1, const float d2, double (&acc)[kNdtSums]) {
+    const double m0 = L->mean[0], m1 = L->mean[1], m2 = L->mean[2];
+    float C[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) C[q] = L->icov[q];
+    const float q0 = (float)((double)xt[0] - m0), q1 = (float)((double)xt[1] - m1), q2 = (float)((double)xt[2] - m2);
+    const float qC[3] = {q0 * C[0] + q1 * C[3] + q2 * C[6], q0 * C[1] + q1 * C[4] + q2 * C[7], q0 * C[2] + q1 * C[5] + q2 * C[8]};
+    const float qCq = q0 * qC[0] + q1 * qC[1] + q2 * qC[2];
+    float e = (float)exp((double)(-d2 * qCq * 0.5f));
+    const float score_inc = (float)(-d1 * (double)e);
+    e = d2 * e;
+    if (e > 1.f || e < 0.f || e != e) return;
+    e = (float)((double)e * d1);
+    acc[0] += (double)score_inc;
+    float g[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) g[r][c] = (r == c) ? 1.f : 0.f;
+    float xj[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) xj[r] = A.j[r][0] * x[0] + A.j[r][1] * x[1] + A.j[r][2] * x[2];
+    g[1][3] = xj[0]; g[2][3] = xj[1];
+    g[0][4] = xj[2]; g[1][4] = xj[3]; g[2][4] = xj[4];
+    g[0][5] = xj[5]; g[1][5] = xj[6]; g[2][5] = xj[7];
+    float xh[15];
+#pragma unroll
+    for (int r = 0; r < 15; ++r) xh[r] = A.h[r][0] * x[0] + A.h[r][1] * x[1] + A.h[r][2] * x[2];
+    // H_E blocks (i, j) for i, j in {3, 4, 5}: a b c / b d e / c e f, each a 3-vector
+    const float hv[6][3] = {{0.f, xh[0], xh[1]}, {0.f, xh[2], xh[3]}, {0.f, xh[4], xh[5]},
+                            {xh[6], xh[7], xh[8]}, {xh[9], xh[10], xh[11]}, {xh[12], xh[13], xh[14]}};
+    float Cg[3][6], qCg[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Cg[r][c] = C[r * 3] * g[0][c] + C[r * 3 + 1] * g[1][c] + C[r * 3 + 2] * g[2][c];
+        qCg[c] = q0 * Cg[0][c] + q1 * Cg[1][c] + q2 * Cg[2][c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[1 + c] += (double)(e * qCg[c]);
+    int k = 7;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+            float hterm = 0.f;
+            if (i >= 3 && j >= 3) {
+                // block index in {a,b,c,d,e,f}: (3,3)=0 (3,4)=1 (3,5)=2 (4,4)=3 (4,5)=4 (5,5)=5
+                const int bi = (i == 3) ? (j - 3) : (i == 4) ? (j - 1) : 5;
+                hterm = qC[0] * hv[bi][0] + qC[1] * hv[bi][1] + qC[2] * hv[bi][2];
+            }
+            const float gCg = g[0][j] * Cg[0][i] + g[1][j] * Cg[1][i] + g[2][j] * Cg[2][i];
+            acc[k] += (double)(e * (-d2 * qCg[i] * qCg[j] + hterm + gCg));
+            ++k;
+        }
+}
+
+struct NdtSweepShared { float T[12]; NdtAng ang; double red[kNdtThreads / 32][kNdtSums]; };
+
+// grid = (point tiles, jobs).  partial[(job * tiles_max + tile) * 28 + k]
+__global__ void __launch_bounds__(kNdtThreads)
+k_ndt_sweep(const NdtJob* __restrict__ jobs, const NdtTargetView* __restrict__ targets, const NdtSourceView* __restrict__ sources,
+            NdtOptsDev o, int tiles_max, double* __restrict__ partial) {
+    const int job = blockIdx.y;
+    const NdtJob& J = jobs[job];
+    if (J.phase == NDT_DONE) return;
+    const NdtSourceView src = sources[J.source];
+    const int base = blockIdx.x * kNdtThreads;
+    if (base >= src.n) return;
+    __shared__ NdtSweepShared sh;
+    if (threadIdx.x == 0) { ndt_pose_to_matrix(J.x_t, sh.T); ndt_angle_derivatives(J.x_t, &sh.ang); }
+    __syncthreads();
+    const NdtTargetView tg = targets[J.target];
+    double acc[kNdtSums];
+#pragma unroll
+    for (int k = 0; k < kNdtSums; ++k) acc[k] = 0.0;
+    const int i = base + threadIdx.x;
+    if (i < src.n) {
+        const float4 p = __ldg(&src.pts[i]);
+        const float x[3] = {p.x, p.y, p.z};
+        const float xt[3] = {sh.T[0] * p.x + sh.T[1] * p.y + sh.T[2] * p.z + sh.T[3],
+                             sh.T[4] * p.x + sh.T[5] * p.y + sh.T[6] * p.z + sh.T[7],
+                             sh.T[8] * p.x + sh.T[9] * p.y + sh.T[10] * p.z + sh.T[11]};
+        const int ncell = o.search7 ? 7 : 1;
+        for (int c = 0; c < ncell; ++c) {
+            // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
+            const int dx = (c == 1) - (c == 2), dy = (c == 3) - (c == 4), dz = (c == 5) - (c == 6);
+            const int li = ndt_lookup(tg, xt[0], xt[1], xt[2], dx, dy, dz);
+            if (li >= 0) ndt_point_cell(x, xt, &tg.leaves[li], sh.ang, o.d1, (float)o.d2, acc);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kNdtSums; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += shfl_xor_d(v, s);
+        if (lane == 0) sh.red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNdtSums) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kNdtThreads / 32; ++w) v += sh.red[w][threadIdx.x];
+        partial[((size_t)job * tiles_max + blockIdx.x) * kNdtSums + threadIdx.x] = v;
+    }
+}
+
+// ---- More-Thuente helpers ------------------------------------------------------------------------------------
+LILOC_DEV double ndt_psi(double a, double f_a, double f_0, double g_0, double mu) { return f_a - f_0 - mu * g_0 * a; }
+LILOC_DEV double ndt_dpsi(double g_a, double g_0, double mu) { return g_a - mu * g_0; }
+
+LILOC_DEV bool ndt_update_interval(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t, double g_t) {
+    if (f_t > f_l) { a_u = a_t; f_u = f_t; g_u = g_t; return false; }
+    else if (g_t * (a_l - a_t) > 0) { a_l = a_t; f_l = f_t; g_l = g_t; return false; }
+    else if (g_t * (a_l - a_t) < 0) { a_u = a_l; f_u = f_l; g_u = g_l; a_l = a_t; f_l = f_t; g_l = g_t; return false; }
+    return true;
+}
+
+LILOC_DEV double ndt_trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
+    if (f_t > f_l) {
+        const double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l, w = sqrt(z * z - g_t * g_l);
+        const double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+        const double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
+        return (fabs(a_c - a_l) < fabs(a_q - a_l)) ? a_c : 0.5 * (a_q + a_c);
+    } else if (g_t * g_l < 0) {
+        const double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l, w = sqrt(z * z - g_t * g_l);
+        const double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+        const double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+        return (fabs(a_c - a_t) >= fabs(a_s - a_t)) ? a_c : a_s;
+    } else if (fabs(g_t) <= fabs(g_l)) {
+        const double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l, w = sqrt(z * z - g_t * g_l);
+        const double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+        const double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+        const double a_n = (fabs(a_c - a_t) < fabs(a_s - a_t)) ? a_c : a_s;
+        return (a_t > a_l) ? fmin(a_t + 0.66 * (a_u - a_t), a_n) : fmax(a_t + 0.66 * (a_u - a_t), a_n);
+    }
+    const double z = 3 * (f_t - f_u) / (a_t - a_u) - g_t - g_u, w = sqrt(z * z - g_t * g_u);
+    return a_u + (a_t - a_u) * (w - g_u - z) / (g_t - g_u + 2 * w);
+}
+
+// JacobiSVD(H).solve(-g) for the symmetrised Hessian (upper triangle Hup[21])
+LILOC_DEV void ndt_newton_solve(const double* Hup, const double* g, double* dp) {
+    double A[6][6], U[6][6];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) { A[i][j] = Hup[k]; A[j][i] = Hup[k]; ++k; }
+    jacobi6_d(A, U);
+    double smax = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) smax = fmax(smax, fabs(A[i][i]));
+    const double thr = fmax(smax * 6.0 * 2.220446049250313e-16, 2.2250738585072014e-308);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dp[i] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        if (!(fabs(A[m][m]) > thr)) continue;
+        double proj = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) proj += U[i][m] * (-g[i]);
+        proj /= A[m][m];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dp[i] += U[i][m] * proj;
+    }
+}
+
+// One step of computeTransformation / computeStepLengthMT given the sums of the sweep at J.x_t.
+LILOC_DEV void ndt_job_step(NdtJob& J, const double* sums, const NdtOptsDev& o) {
+    const double mu = 1.e-4, nu = 0.9;
+    ++J.sweeps;
+    J.score = sums[0];
+    bool need_check = false;
+    double phi_t = 0, d_phi_t = 0, psi_t = 0, d_psi_t = 0;
+    if (J.phase == NDT_LS_FIRST || J.phase == NDT_LS_LOOP) {
+        phi_t = -J.score;
+        d_phi_t = 0.0;
+        for (int i = 0; i < 6; ++i) d_phi_t -= sums[1 + i] * J.dir[i];
+        psi_t = ndt_psi(J.a_t, phi_t, J.phi_0, J.d_phi_0, mu);
+        d_psi_t = ndt_dpsi(d_phi_t, J.d_phi_0, mu);
+        if (J.phase == NDT_LS_LOOP) {
+            if (J.open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
+                J.open_interval = 0;
+                J.f_l = J.f_l + J.phi_0 - mu * J.d_phi_0 * J.a_l; J.g_l = J.g_l + mu * J.d_phi_0;
+                J.f_u = J.f_u + J.phi_0 - mu * J.d_phi_0 * J.a_u; J.g_u = J.g_u + mu * J.d_phi_0;
+            }
+            if (J.open_interval) J.interval_converged = ndt_update_interval(J.a_l, J.f_l, J.g_l, J.a_u, J.f_u, J.g_u, J.a_t, psi_t, d_psi_t) ? 1 : 0;
+            else J.interval_converged = ndt_update_interval(J.a_l, J.f_l, J.g_l, J.a_u, J.f_u, J.g_u, J.a_t, phi_t, d_phi_t) ? 1 : 0;
+            J.step_iterations++;
+        } else {
+            J.step_iterations = 0;
+        }
+        need_check = true;
+    }
+    for (int guard = 0; guard < 64; ++guard) {
+        if (need_check) {
+            if (!J.interval_converged && J.step_iterations < 10 && !(psi_t <= 0 && d_phi_t <= -nu * J.d_phi_0)) {
+                if (J.open_interval) J.a_t = ndt_trial_value(J.a_l, J.f_l, J.g_l, J.a_u, J.f_u, J.g_u, J.a_t, psi_t, d_psi_t);
+                else J.a_t = ndt_trial_value(J.a_l, J.f_l, J.g_l, J.a_u, J.f_u, J.g_u, J.a_t, phi_t, d_phi_t);
+                J.a_t = fmin(J.a_t, o.step_max); J.a_t = fmax(J.a_t, o.step_min);
+                for (int i = 0; i < 6; ++i) J.x_t[i] = J.p[i] + J.dir[i] * J.a_t;
+                ndt_pose_to_matrix(J.x_t, J.Tfinal);
+                J.phase = NDT_LS_LOOP;
+                return;                                   // next sweep at the new trial point
+            }
+            need_check = false;
+            // line search finished: accept a_t
+            for (int i = 0; i < 6; ++i) J.p[i] += J.dir[i] * J.a_t;
+            const bool conv = J.nr_iterations > o.max_iterations || (J.nr_iterations && (fabs(J.a_t) < o.eps));
+            J.nr_iterations++;
+            if (conv) { J.converged = 1; J.phase = NDT_DONE; return; }
+        }
+        // Newton direction from the latest sums (they belong to the current p)
+        double dp[6];
+        ndt_newton_solve(sums + 7, sums + 1, dp);
+        double norm = 0.0;
+        for (int i = 0; i < 6; ++i) norm += dp[i] * dp[i];
+        norm = sqrt(norm);
+        if (norm == 0 || norm != norm) { J.converged = (norm == norm) ? 1 : 0; J.phase = NDT_DONE; return; }
+        for (int i = 0; i < 6; ++i) J.dir[i] = dp[i] / norm;
+        J.phi_0 = -J.score;
+        J.d_phi_0 = 0.0;
+        for (int i = 0; i < 6; ++i) J.d_phi_0 -= sums[1 + i] * J.dir[i];
+        if (J.d_phi_0 >= 0) {
+            if (J.d_phi_0 == 0) {                          // zero step: p unchanged, iteration counted
+                J.a_t = 0.0;
+                const bool conv = J.nr_iterations > o.max_iterations || (J.nr_iterations && (0.0 < o.eps));
+                J.nr_iterations++;
+                if (conv) { J.converged = 1; J.phase = NDT_DONE; return; }
+                continue;
+            }
+            J.d_phi_0 *= -1;
+            for (int i = 0; i < 6; ++i) J.dir[i] *= -1;
+        }
+        J.a_l = 0; J.a_u = 0;
+        J.f_l = ndt_psi(J.a_l, J.phi_0, J.phi_0, J.d_phi_0, mu); J.g_l = ndt_dpsi(J.d_phi_0, J.d_phi_0, mu);
+        J.f_u = ndt_psi(J.a_u, J.phi_0, J.phi_0, J.d_phi_0, mu); J.g_u = ndt_dpsi(J.d_phi_0, J.d_phi_0, mu);
+        J.interval_converged = ((o.step_max - o.step_min) < 0) ? 1 : 0;
+        J.open_interval = 1;
+        J.a_t = norm;
+        J.a_t = fmin(J.a_t, o.step_max); J.a_t = fmax(J.a_t, o.step_min);
+        for (int i = 0; i < 6; ++i) J.x_t[i] = J.p[i] + J.dir[i] * J.a_t;
+        ndt_pose_to_matrix(J.x_t, J.Tfinal);
+        J.phase = NDT_LS_FIRST;
+        return;
+    }
+    J.phase = NDT_DONE;                                   // unreachable in practice (guard)
+}
+
+// start (or restart, for the second of the reference's two back-to-back align calls) from a 3x4 guess
+LILOC_DEV void ndt_job_begin(NdtJob& J, const float* guess12) {
+    for (int i = 0; i < 12; ++i) J.Tfinal[i] = guess12[i];
+    ndt_matrix_to_pose(guess12, J.p);
+    for (int i = 0; i < 6; ++i) J.x_t[i] = J.p[i];
+    J.phase = NDT_AWAIT_FIRST;
+    J.nr_iterations = 0; J.converged = 0; J.sweeps = 0; J.step_iterations = 0; J.open_interval = 1; J.interval_converged = 0;
+}
+
+__global__ void k_ndt_begin(NdtJob* __restrict__ jobs, int n_jobs) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    NdtJob& J = jobs[j];
+    J.align_pass = 0; J.total_iterations = 0; J.total_sweeps = 0;
+    ndt_job_begin(J, J.guess);
+}
+
+// one block (32 threads) per job: reduce the tile partials in a fixed order, advance the state machine.
+__global__ void __launch_bounds__(32)
+k_ndt_update(NdtJob* __restrict__ jobs, const NdtSourceView* __restrict__ sources, NdtOptsDev o, int tiles_max,
+             const double* __restrict__ partial, int* __restrict__ n_active) {
+    const int job = blockIdx.x;
+    NdtJob& J = jobs[job];
+    if (J.phase == NDT_DONE) return;
+    __shared__ double sums[kNdtSums];
+    const int n_tiles = (sources[J.source].n + kNdtThreads - 1) / kNdtThreads;
+    if (threadIdx.x < kNdtSums) {
+        double v = 0.0;
+        const double* pj = partial + (size_t)job * tiles_max * kNdtSums + threadIdx.x;
+        for (int t = 0; t < n_tiles; ++t) v += pj[(size_t)t * kNdtSums];
+        sums[threadIdx.x] = v;
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        ndt_job_step(J, sums, o);
+        if (J.phase == NDT_DONE) {
+            J.total_iterations += J.nr_iterations; J.total_sweeps += J.sweeps;
+            if (J.align_pass + 1 < o.n_align) {          // registration->align() again from the previous result (:282-290)
+                const int pass = J.align_pass + 1;
+                float g[12];
+                for (int i = 0; i < 12; ++i) g[i] = J.Tfinal[i];
+                ndt_job_begin(J, g);
+                J.align_pass = pass;
+            }
+        }
+        if (J.phase != NDT_DONE) atomicAdd(n_active, 1);
+    }
+}
+
+}  // namespace liloc

@@ -206,3 +206,87 @@ def frame(kf_pts, kf_offs, poses6, map_leaf, scan_raw, scan_leaf, pose6, opts: S
     rc = lib.orc_frame(_p(pts), _p(offs), _p(poses), len(offs) - 1, map_leaf, _p(s), len(s), scan_leaf, _p(p),
                        C.byref(opts), C.byref(st), C.byref(res), C.byref(M), C.byref(Q), _p(ms))
     return p, res, rc, M.value, Q.value, ms
+
+
+# ---- NDT oracle (oracle/ndt_oracle.cpp) -----------------------------------------------------------------
+class NdtOpts(C.Structure):
+    _fields_ = [("step_size", C.c_double), ("outlier_ratio", C.c_double), ("trans_eps", C.c_double),
+                ("resolution", C.c_float), ("max_iterations", C.c_int), ("search", C.c_int), ("threads", C.c_int)]
+
+    def __init__(self, resolution=1.0, trans_eps=0.01, search=0, threads=1, step_size=0.1, outlier_ratio=0.55, max_iterations=35):
+        super().__init__(step_size, outlier_ratio, float(np.float32(trans_eps)), resolution, max_iterations, search, threads)
+
+
+class NdtResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("sweeps", C.c_int), ("score", C.c_double)]
+
+
+lib.orc_ndt_target_create.restype = C.c_void_p
+lib.orc_ndt_target_create.argtypes = [C.c_void_p, C.c_int, C.c_float]
+lib.orc_ndt_target_destroy.argtypes = [C.c_void_p]
+lib.orc_ndt_target_leaves.restype = C.c_int
+lib.orc_ndt_target_leaves.argtypes = [C.c_void_p]
+lib.orc_ndt_target_get.restype = C.c_int
+lib.orc_ndt_target_get.argtypes = [C.c_void_p] * 4 + [C.c_int]
+lib.orc_ndt_target_keys.restype = C.c_int
+lib.orc_ndt_target_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+lib.orc_ndt_pose_to_matrix.argtypes = [C.c_void_p, C.c_void_p]
+lib.orc_ndt_matrix_to_pose.argtypes = [C.c_void_p, C.c_void_p]
+lib.orc_ndt_derivatives.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(NdtOpts), C.c_void_p]
+lib.orc_ndt_align.restype = C.c_int
+lib.orc_ndt_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(NdtOpts), C.c_void_p, C.POINTER(NdtResult)]
+
+
+class NdtTarget:
+    def __init__(self, pts, resolution):
+        self._pts = _c(pts)
+        self._h = lib.orc_ndt_target_create(_p(self._pts), len(self._pts), resolution)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.orc_ndt_target_destroy(self._h)
+            self._h = None
+
+    def leaves(self):
+        n = lib.orc_ndt_target_leaves(self._h)
+        means, icovs, counts = np.zeros((n, 3)), np.zeros((n, 9), np.float32), np.zeros(n, np.int32)
+        lib.orc_ndt_target_get(self._h, _p(means), _p(icovs), _p(counts), n)
+        return means, icovs, counts
+
+    def keys(self):
+        n = lib.orc_ndt_target_leaves(self._h)
+        k = np.zeros(n, np.int32)
+        lib.orc_ndt_target_keys(self._h, _p(k), n)
+        return k
+
+
+def ndt_pose_to_matrix(p6):
+    p = np.ascontiguousarray(p6, np.float64).reshape(6)
+    T = np.zeros(12, np.float32)
+    lib.orc_ndt_pose_to_matrix(_p(p), _p(T))
+    return T.reshape(3, 4)
+
+
+def ndt_matrix_to_pose(T12):
+    T = np.ascontiguousarray(T12, np.float32).reshape(12)
+    p = np.zeros(6)
+    lib.orc_ndt_matrix_to_pose(_p(T), _p(p))
+    return p
+
+
+def ndt_derivatives(target: NdtTarget, src, p6, opts: NdtOpts):
+    s = _c(src)
+    p = np.ascontiguousarray(p6, np.float64).reshape(6)
+    out = np.zeros(28)
+    lib.orc_ndt_derivatives(target._h, _p(s), len(s), _p(p), C.byref(opts), _p(out))
+    return out
+
+
+def ndt_align(target: NdtTarget, src, guess12, opts: NdtOpts):
+    """guess12 / result: (3,4) float32 = top rows of the 4x4 Eigen::Matrix4f of registration->align(out, guess)."""
+    s = _c(src)
+    g = np.ascontiguousarray(guess12, np.float32).reshape(12)
+    out = np.zeros(12, np.float32)
+    res = NdtResult()
+    lib.orc_ndt_align(target._h, _p(s), len(s), _p(g), C.byref(opts), _p(out), C.byref(res))
+    return out.reshape(3, 4), res

@@ -1,0 +1,93 @@
+"""GPU parity tests of the relo-mode NDT path (C ABI liloc_ndt_*) against the oracle (oracle/ndt_oracle.cpp).
+Per-point terms follow the same float32 operation sequence on both sides; sums are double with a different
+(fixed) order, so derivatives agree to ~1e-12 relative and final poses within the north_star tolerance."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from test_ndt_oracle import guess_matrix, ndt_scene  # noqa: E402,F401
+
+
+def test_target_leaves_bit_exact(gpu_ctx, orc, ndt_scene):
+    sub, _, _ = ndt_scene
+    for res in (1.0, 0.8, 2.0):
+        n = gpu_ctx.ndt_target_put(1, sub, res)
+        means, icovs, counts, keys = gpu_ctx.ndt_target_get(1)
+        rm, ri, rc = orc.NdtTarget(sub, np.float32(res)).leaves()
+        assert n == len(rm) == len(means)
+        assert np.array_equal(counts, rc)
+        assert np.array_equal(means, rm)
+        assert np.array_equal(icovs, ri)
+
+
+def test_derivatives_match_oracle(gpu_ctx, orc, synth, ndt_scene):
+    from liloc_b200 import NdtOpts
+    sub, src, truth = ndt_scene
+    gpu_ctx.ndt_target_put(2, sub, 1.0)
+    gpu_ctx.ndt_source_put(2, src)
+    tg = orc.NdtTarget(sub, 1.0)
+    rng = np.random.default_rng(1)
+    for search in (0, 1):
+        for _ in range(4):
+            p = orc.ndt_matrix_to_pose(guess_matrix(synth, truth + np.r_[rng.uniform(-0.03, 0.03, 3), rng.uniform(-0.5, 0.5, 3)]))
+            got = gpu_ctx.ndt_derivatives(2, 2, p, NdtOpts(search=search))
+            ref = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=search, threads=8))
+            assert np.allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+def _pose_err(T, Tref):
+    dt = np.abs(T[:3, 3] - Tref[:3, 3]).max()
+    dR = np.abs(T[:3, :3] - Tref[:3, :3]).max()
+    return dt, dR
+
+
+@pytest.mark.parametrize("search", [0, 1])
+def test_align_matches_oracle(gpu_ctx, orc, synth, ndt_scene, search):
+    from liloc_b200 import NdtOpts
+    sub, src, truth = ndt_scene
+    gpu_ctx.ndt_target_put(3, sub, 1.0)
+    gpu_ctx.ndt_source_put(3, src)
+    tg = orc.NdtTarget(sub, 1.0)
+    rng = np.random.default_rng(5)
+    guesses = [guess_matrix(synth, truth + np.r_[rng.uniform(-0.02, 0.02, 3), rng.uniform(-0.4, 0.4, 3)]) for _ in range(12)]
+    guesses.append(guess_matrix(synth, truth + np.array([0, 0, 0, 500.0, 0, 0])))                 # no overlap at all
+    J = len(guesses)
+    T, score, iters, conv, sweeps = gpu_ctx.ndt_align_batch([3] * J, [3] * J, guesses, NdtOpts(search=search))
+    mism = []
+    for j in range(J):
+        Tr, rr = orc.ndt_align(tg, src, guesses[j], orc.NdtOpts(resolution=1.0, search=search, threads=8))
+        dt, dR = _pose_err(T[j], Tr)
+        assert dt <= 1e-4 and dR <= 1e-5, (j, dt, dR)          # 1e-4 m; rotation-matrix entries within 1e-5 (~1e-5 rad)
+        if (iters[j], conv[j], sweeps[j]) != (rr.iterations, rr.converged, rr.sweeps):
+            mism.append((j, iters[j], sweeps[j], rr.iterations, rr.sweeps))
+        assert abs(score[j] - rr.score) <= 1e-6 * max(1.0, abs(rr.score))
+    assert not mism, mism
+    assert np.abs(T[0, :3, 3] - truth[3:]).max() < 0.03
+
+
+def test_two_pass_align_and_batch_independence(gpu_ctx, orc, synth, ndt_scene):
+    """n_align = 2 (relocalisation init, :282-290) equals two chained single aligns; a batch equals its jobs run alone."""
+    from liloc_b200 import NdtOpts
+    sub, src, truth = ndt_scene
+    gpu_ctx.ndt_target_put(4, sub, 1.0)
+    gpu_ctx.ndt_target_put(5, sub[: len(sub) // 2], 1.0)
+    gpu_ctx.ndt_source_put(4, src)
+    gpu_ctx.ndt_source_put(5, src[::2])
+    g = [guess_matrix(synth, truth + np.array([0.01, 0, 0.03, 0.2, -0.1, 0.05])), guess_matrix(synth, truth + np.array([0, 0.01, -0.02, -0.15, 0.2, 0.0]))]
+    T2, s2, it2, c2, sw2 = gpu_ctx.ndt_align_batch([4, 5], [4, 5], g, NdtOpts(n_align=2))
+    for j, (t, s) in enumerate(((4, 4), (5, 5))):
+        Ta, _, ia, _, swa = gpu_ctx.ndt_align_batch([t], [s], [g[j]], NdtOpts())
+        Tb, sb, ib, _, swb = gpu_ctx.ndt_align_batch([t], [s], [Ta[0]], NdtOpts())
+        assert np.array_equal(Tb[0], T2[j]) and it2[j] == ia[0] + ib[0] and sw2[j] == swa[0] + swb[0]
+    tg = orc.NdtTarget(sub, 1.0)
+    Tr, _ = orc.ndt_align(tg, src, g[0], orc.NdtOpts(resolution=1.0, threads=8))
+    Tr2, _ = orc.ndt_align(tg, src, Tr, orc.NdtOpts(resolution=1.0, threads=8))
+    dt, dR = _pose_err(T2[0], Tr2)
+    assert dt <= 1e-4 and dR <= 1e-5
+
+
+def test_ndt_errors(gpu_ctx):
+    from liloc_b200 import LilocError
+    with pytest.raises(LilocError):
+        gpu_ctx.ndt_align_batch([999], [999], [np.eye(4, dtype=np.float32)])

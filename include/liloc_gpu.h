@@ -40,6 +40,13 @@ typedef struct { float x, y, z, intensity; } liloc_point;
 
 typedef struct liloc_ctx liloc_ctx;
 
+/* Feature classes.  LILOC_SURF is the reference's only class (the whole de-skewed scan, plane residuals,
+ * surfOptimization :981-1048).  LILOC_CORNER is the upstream LIO-SAM cornerOptimization the north_star names
+ * (line residuals); the reference dropped it (only remnants: laserCloudCornerTemp :947,950), so it is an
+ * optional superset: off by default, and every entry point without a class argument is surf-only. */
+#define LILOC_SURF   0
+#define LILOC_CORNER 1
+
 typedef struct {
     int device;             /* CUDA device ordinal */
     int max_scan_points;    /* N_SCAN * Horizon_SCAN, sizes scratch like allocateMemory() :228-230 */
@@ -52,8 +59,11 @@ typedef struct {
     int max_iters;          /* [20]  loop bound, src/mapOptmization.cpp:1190 */
     int stride;             /* [2]   every 2nd down-sampled point, :985 */
     int min_sel;            /* [50]  LMOptimization bail-out, :1080 */
-    int min_points;         /* [30]  gate is Q_all > min_points, :1187 */
-    int reserved[4];
+    int min_points;         /* [30]  gate is Q_all > min_points, :1187 (upstream surfFeatureMinValidNum 100) */
+    int enable_corner;      /* [0]   1 = also use the LILOC_CORNER class (upstream LIO-SAM: 30 iterations, stride 1) */
+    int min_points_corner;  /* [10]  upstream edgeFeatureMinValidNum: gate is Q_corner > min_points_corner */
+    int stride_corner;      /* [1] */
+    int reserved[1];
 } liloc_s2m_opts;
 
 typedef struct {
@@ -113,6 +123,28 @@ int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K
                 const liloc_point* scan, int n_scan, int scan_on_device, float scan_leaf,
                 float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res);
 
+/* The same with both feature classes (north_star superset; the reference frame is liloc_frame).  Arrays are
+ * indexed by class: [LILOC_SURF], [LILOC_CORNER].  The corner entries are read only when opts->enable_corner. */
+typedef struct {
+    const int* kf_ids; const float* kf_poses6; int K;
+    float map_leaf[2];                   /* surroundingKeyframeMapLeafSize | upstream mappingCornerLeafSize */
+    const liloc_point* scan[2]; int n_scan[2];
+    float scan_leaf[2];                  /* mappingSurfLeafSize | mappingCornerLeafSize */
+    int scan_on_device;
+} liloc_frame_in;
+int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res);
+typedef struct { int q_corner, map_points_corner, tiles_corner, tiles_surf, sort_redos; int reserved[3]; } liloc_s2m_extra;
+int liloc_last_s2m_extra(liloc_ctx* ctx, liloc_s2m_extra* out);
+
+/* Class-indexed variants of the step-wise entry points above (cls = LILOC_SURF | LILOC_CORNER). */
+int liloc_keyframe_put_features(liloc_ctx* ctx, int kf_id, const liloc_point* surf, int n_surf, const liloc_point* corner, int n_corner);
+int liloc_keyframe_size_class(liloc_ctx* ctx, int cls, int kf_id);
+int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const float* poses6, int K, float leaf, int* M_out, int* n_raw_out);
+int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts_map, int n, float leaf, int* M_out);
+int liloc_localmap_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, int* M_out);
+int liloc_scan_put_class(liloc_ctx* ctx, int cls, const liloc_point* pts_body, int n, int on_device, float leaf, int* Q_all_out);
+int liloc_scan_ds_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, int* Q_all_out);
+
 /* ---- relo-mode NDT registration: pcl::Registration interface of `registration` (:118) ----------------
  * Replaces ndt_omp's pclomp::NormalDistributionsTransform as LiLoc configures it (:175-199): a target is a
  * prior-session submap (setInputTarget, :273, anchorOptimize.hpp:394), a source is the full de-skewed scan
@@ -160,6 +192,9 @@ int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries_map, int nq, int* idx5
 /* surfOptimization at a fixed pose (:981-1048): per scan point i (multiples of stride) the flag
  * laserCloudOriSurfFlag[i] and coefficient coeffSelSurfVec[i]; arrays have Q_all entries. */
 int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag);
+int liloc_knn5_class(liloc_ctx* ctx, int cls, const liloc_point* queries_map, int nq, int* idx5, float* d2_5, int* found);
+/* surfOptimization (cls 0) / upstream cornerOptimization (cls 1) at a fixed pose, like liloc_surf_pass. */
+int liloc_feature_pass(liloc_ctx* ctx, int cls, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag);
 /* pcl::getTransformation as the device evaluates it: top 3x4 block, row-major. */
 int liloc_pose_to_T(liloc_ctx* ctx, const float* pose6, float* T12);
 
@@ -168,6 +203,11 @@ int liloc_pose_to_T(liloc_ctx* ctx, const float* pose6, float* T12);
 int liloc_debug_lm6(liloc_ctx* ctx, const float* A36, const float* b6, int n, float* x6, float* w6, float* P36, int* deg);
 /* Eigen colPivHouseholderQr().solve of n 5x3 systems A x = -1 (:1009); pts15 = n x 5 x 3 row-major. */
 int liloc_debug_plane(liloc_ctx* ctx, const float* pts15, int n, float* x3);
+
+/* cv::eigen of n symmetric 3x3 matrices as cornerOptimization uses it: w descending, eigenvectors as rows of V. */
+int liloc_debug_eigen3(liloc_ctx* ctx, const float* A9, int n, float* w3, float* V9);
+/* cornerOptimization's loop body after the kNN on explicit neighbours: pts15 = n x 5 x 3, sel3 = n x pointSel. */
+int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int n, liloc_point* coeff, int* keep);
 
 /* ---- timing: CUDA-event milliseconds of the phases of the last liloc_frame / call sequence ------ */
 typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;

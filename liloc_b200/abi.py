@@ -30,10 +30,28 @@ class _Config(C.Structure):
 class S2mOpts(C.Structure):
     """liloc_s2m_opts; defaults are the reference's constants (src/mapOptmization.cpp:1190,985,1080,1187)."""
     _fields_ = [("max_iters", C.c_int), ("stride", C.c_int), ("min_sel", C.c_int), ("min_points", C.c_int),
-                ("reserved", C.c_int * 4)]
+                ("enable_corner", C.c_int), ("min_points_corner", C.c_int), ("stride_corner", C.c_int),
+                ("reserved", C.c_int * 1)]
 
-    def __init__(self, max_iters: int = 20, stride: int = 2, min_sel: int = 50, min_points: int = 30):
-        super().__init__(max_iters, stride, min_sel, min_points)
+    def __init__(self, max_iters: int = 20, stride: int = 2, min_sel: int = 50, min_points: int = 30,
+                 enable_corner: int = 0, min_points_corner: int = 10, stride_corner: int = 1):
+        super().__init__(max_iters, stride, min_sel, min_points, enable_corner, min_points_corner, stride_corner)
+
+    @classmethod
+    def upstream(cls) -> "S2mOpts":
+        """Upstream LIO-SAM loop shape named by the north_star: corner + surf, stride 1, 30 iterations,
+        gate corner > 10 and surf > 100."""
+        return cls(max_iters=30, stride=1, min_sel=50, min_points=100, enable_corner=1, min_points_corner=10, stride_corner=1)
+
+
+class FrameIn(C.Structure):
+    _fields_ = [("kf_ids", C.c_void_p), ("kf_poses6", C.c_void_p), ("K", C.c_int), ("map_leaf", C.c_float * 2),
+                ("scan", C.c_void_p * 2), ("n_scan", C.c_int * 2), ("scan_leaf", C.c_float * 2), ("scan_on_device", C.c_int)]
+
+
+class S2mExtra(C.Structure):
+    _fields_ = [("q_corner", C.c_int), ("map_points_corner", C.c_int), ("tiles_corner", C.c_int), ("tiles_surf", C.c_int),
+                ("sort_redos", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class S2mResult(C.Structure):
@@ -129,6 +147,19 @@ def _load() -> C.CDLL:
         "liloc_stream": (C.c_void_p, [P]),
         "liloc_debug_lm6": (C.c_int, [P, P, P, C.c_int, P, P, P, P]),
         "liloc_debug_plane": (C.c_int, [P, P, C.c_int, P]),
+        "liloc_frame_features": (C.c_int, [P, C.POINTER(FrameIn), P, C.POINTER(S2mOpts), C.POINTER(S2mResult)]),
+        "liloc_last_s2m_extra": (C.c_int, [P, C.POINTER(S2mExtra)]),
+        "liloc_keyframe_put_features": (C.c_int, [P, C.c_int, P, C.c_int, P, C.c_int]),
+        "liloc_keyframe_size_class": (C.c_int, [P, C.c_int, C.c_int]),
+        "liloc_localmap_build_class": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, ip, ip]),
+        "liloc_localmap_set_class": (C.c_int, [P, C.c_int, P, C.c_int, C.c_float, ip]),
+        "liloc_localmap_get_class": (C.c_int, [P, C.c_int, P, C.c_int, ip]),
+        "liloc_scan_put_class": (C.c_int, [P, C.c_int, P, C.c_int, C.c_int, C.c_float, ip]),
+        "liloc_scan_ds_get_class": (C.c_int, [P, C.c_int, P, C.c_int, ip]),
+        "liloc_knn5_class": (C.c_int, [P, C.c_int, P, C.c_int, P, P, P]),
+        "liloc_feature_pass": (C.c_int, [P, C.c_int, P, C.c_int, P, P]),
+        "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
+        "liloc_debug_line": (C.c_int, [P, P, P, C.c_int, P, P]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -141,7 +172,10 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_keyframe_put_from_scan liloc_keyframe_size liloc_keyframe_clear liloc_localmap_build "
            "liloc_localmap_set liloc_localmap_get liloc_scan_put liloc_scan_put_dev liloc_scan_ds_get "
            "liloc_scan2map liloc_frame liloc_voxelgrid liloc_knn5 liloc_surf_pass liloc_pose_to_T "
-           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane").split()
+           "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
+           "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
+           "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -194,42 +228,46 @@ class Context:
         p = _cloud(pts)
         self._chk(lib.liloc_keyframe_put(self._h, kf_id, _ptr(p), len(p)))
 
+    def keyframe_put_features(self, kf_id: int, surf, corner) -> None:
+        a, b = _cloud(surf), _cloud(corner)
+        self._chk(lib.liloc_keyframe_put_features(self._h, kf_id, _ptr(a), len(a), _ptr(b), len(b)))
+
     def keyframe_put_from_scan(self, kf_id: int) -> None:
         self._chk(lib.liloc_keyframe_put_from_scan(self._h, kf_id))
 
-    def keyframe_size(self, kf_id: int) -> int:
-        return lib.liloc_keyframe_size(self._h, kf_id)
+    def keyframe_size(self, kf_id: int, cls: int = 0) -> int:
+        return lib.liloc_keyframe_size_class(self._h, cls, kf_id)
 
     def keyframe_clear(self) -> None:
         self._chk(lib.liloc_keyframe_clear(self._h))
 
     # ---- local map ----
-    def localmap_build(self, kf_ids, poses6, leaf: float) -> tuple[int, int]:
+    def localmap_build(self, kf_ids, poses6, leaf: float, cls: int = 0) -> tuple[int, int]:
         ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
         poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
         assert len(ids) == len(poses)
         M, n_raw = C.c_int(), C.c_int()
-        self._chk(lib.liloc_localmap_build(self._h, _ptr(ids), _ptr(poses), len(ids), leaf, C.byref(M), C.byref(n_raw)))
+        self._chk(lib.liloc_localmap_build_class(self._h, cls, _ptr(ids), _ptr(poses), len(ids), leaf, C.byref(M), C.byref(n_raw)))
         return M.value, n_raw.value
 
-    def localmap_set(self, pts_map, leaf: float) -> int:
+    def localmap_set(self, pts_map, leaf: float, cls: int = 0) -> int:
         p = _cloud(pts_map)
         M = C.c_int()
-        self._chk(lib.liloc_localmap_set(self._h, _ptr(p), len(p), leaf, C.byref(M)))
+        self._chk(lib.liloc_localmap_set_class(self._h, cls, _ptr(p), len(p), leaf, C.byref(M)))
         return M.value
 
-    def localmap_get(self) -> np.ndarray:
+    def localmap_get(self, cls: int = 0) -> np.ndarray:
         M = C.c_int()
-        self._chk(lib.liloc_localmap_get(self._h, None, 0, C.byref(M)))
+        self._chk(lib.liloc_localmap_get_class(self._h, cls, None, 0, C.byref(M)))
         out = np.empty((M.value, 4), np.float32)
-        self._chk(lib.liloc_localmap_get(self._h, _ptr(out), M.value, C.byref(M)))
+        self._chk(lib.liloc_localmap_get_class(self._h, cls, _ptr(out), M.value, C.byref(M)))
         return out
 
     # ---- scan ----
-    def scan_put(self, pts_body, leaf: float) -> int:
+    def scan_put(self, pts_body, leaf: float, cls: int = 0) -> int:
         p = _cloud(pts_body)
         Q = C.c_int()
-        self._chk(lib.liloc_scan_put(self._h, _ptr(p), len(p), leaf, C.byref(Q)))
+        self._chk(lib.liloc_scan_put_class(self._h, cls, _ptr(p), len(p), 0, leaf, C.byref(Q)))
         return Q.value
 
     def scan_put_dev(self, dev_ptr: int, n: int, leaf: float) -> int:
@@ -237,11 +275,11 @@ class Context:
         self._chk(lib.liloc_scan_put_dev(self._h, C.c_void_p(dev_ptr), n, leaf, C.byref(Q)))
         return Q.value
 
-    def scan_ds_get(self) -> np.ndarray:
+    def scan_ds_get(self, cls: int = 0) -> np.ndarray:
         Q = C.c_int()
-        self._chk(lib.liloc_scan_ds_get(self._h, None, 0, C.byref(Q)))
+        self._chk(lib.liloc_scan_ds_get_class(self._h, cls, None, 0, C.byref(Q)))
         out = np.empty((Q.value, 4), np.float32)
-        self._chk(lib.liloc_scan_ds_get(self._h, _ptr(out), Q.value, C.byref(Q)))
+        self._chk(lib.liloc_scan_ds_get_class(self._h, cls, _ptr(out), Q.value, C.byref(Q)))
         return out
 
     # ---- registration ----
@@ -268,6 +306,33 @@ class Context:
                                        _ptr(pose), C.byref(o), C.byref(res)))
         return pose, res, rc
 
+    def frame_features(self, kf_ids, poses6, map_leafs, scans, scan_leafs, pose6, opts: S2mOpts | None = None,
+                       scan_dev_ptrs=None, n_scans=None) -> tuple[np.ndarray, S2mResult, int]:
+        """liloc_frame_features: scans / leaf sizes are (surf, corner) pairs."""
+        ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
+        pose = np.array(pose6, dtype=np.float32).reshape(6).copy()
+        res = S2mResult()
+        o = opts or S2mOpts.upstream()
+        fi = FrameIn()
+        fi.kf_ids, fi.kf_poses6, fi.K = ids.ctypes.data, poses.ctypes.data, len(ids)
+        keep = []
+        for c in range(2):
+            fi.map_leaf[c], fi.scan_leaf[c] = float(map_leafs[c]), float(scan_leafs[c])
+            if scan_dev_ptrs is not None:
+                fi.scan[c], fi.n_scan[c] = int(scan_dev_ptrs[c]), int(n_scans[c])
+            else:
+                sc = _cloud(scans[c]); keep.append(sc)
+                fi.scan[c], fi.n_scan[c] = sc.ctypes.data if len(sc) else None, len(sc)
+        fi.scan_on_device = 1 if scan_dev_ptrs is not None else 0
+        rc = self._chk(lib.liloc_frame_features(self._h, C.byref(fi), _ptr(pose), C.byref(o), C.byref(res)))
+        return pose, res, rc
+
+    def last_s2m_extra(self) -> dict:
+        e = S2mExtra()
+        lib.liloc_last_s2m_extra(self._h, C.byref(e))
+        return {k: getattr(e, k) for k in ("q_corner", "map_points_corner", "tiles_corner", "tiles_surf", "sort_redos")}
+
     # ---- kernel-level ----
     def voxelgrid(self, pts, leaf: float) -> np.ndarray:
         p = _cloud(pts)
@@ -276,13 +341,33 @@ class Context:
         self._chk(lib.liloc_voxelgrid(self._h, _ptr(p), len(p), leaf, _ptr(out), len(p), C.byref(m)))
         return out[: m.value].copy()
 
-    def knn5(self, queries_map) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    def knn5(self, queries_map, cls: int = 0) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         q = _cloud(queries_map)
         idx = np.empty((len(q), 5), np.int32)
         d2 = np.empty((len(q), 5), np.float32)
         found = np.empty(len(q), np.int32)
-        self._chk(lib.liloc_knn5(self._h, _ptr(q), len(q), _ptr(idx), _ptr(d2), _ptr(found)))
+        self._chk(lib.liloc_knn5_class(self._h, cls, _ptr(q), len(q), _ptr(idx), _ptr(d2), _ptr(found)))
         return idx, d2, found
+
+    def feature_pass(self, cls: int, pose6, stride: int, q_all: int) -> tuple[np.ndarray, np.ndarray]:
+        pose = np.ascontiguousarray(pose6, dtype=np.float32).reshape(6)
+        coeff = np.zeros((q_all, 4), np.float32)
+        flag = np.zeros(q_all, np.uint8)
+        self._chk(lib.liloc_feature_pass(self._h, cls, _ptr(pose), stride, _ptr(coeff), _ptr(flag)))
+        return coeff, flag
+
+    def debug_eigen3(self, A):
+        A = np.ascontiguousarray(A, np.float32).reshape(-1, 9)
+        w, V = np.empty((len(A), 3), np.float32), np.empty((len(A), 9), np.float32)
+        self._chk(lib.liloc_debug_eigen3(self._h, _ptr(A), len(A), _ptr(w), _ptr(V)))
+        return w, V.reshape(-1, 3, 3)
+
+    def debug_line(self, pts, sel):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 15)
+        sel = np.ascontiguousarray(sel, np.float32).reshape(-1, 3)
+        coeff, keep = np.empty((len(pts), 4), np.float32), np.empty(len(pts), np.int32)
+        self._chk(lib.liloc_debug_line(self._h, _ptr(pts), _ptr(sel), len(pts), _ptr(coeff), _ptr(keep)))
+        return coeff, keep
 
     def surf_pass(self, pose6, stride: int, q_all: int) -> tuple[np.ndarray, np.ndarray]:
         pose = np.ascontiguousarray(pose6, dtype=np.float32).reshape(6)

@@ -1,10 +1,15 @@
 // liloc_b200/csrc/liloc_gpu.cu -- context, memory and the C ABI declared in include/liloc_gpu.h.
 //
-// One context = one GPU, one stream, one caller thread (mirrors `mtx`, src/mapOptmization.cpp:255).
+// One context = one GPU, one caller thread (mirrors `mtx`, src/mapOptmization.cpp:255).
 // Everything the path touches lives in HBM for the lifetime of the context: the keyframe arena
-// (body-frame float4 clouds), the concatenated local map, its down-sampled form, the search grid,
-// the down-sampled scan and the 6x6 state.  Per frame the host sends the raw scan and K keyframe
-// descriptors (80 bytes each) and reads back one result struct.
+// (body-frame float4 clouds), the concatenated local maps, their down-sampled form, the search grids,
+// the down-sampled scans and the 6x6 state.  Per frame the host sends the raw scan(s) and K keyframe
+// descriptors (64 bytes each) and reads back one result struct.
+//
+// A frame (liloc_frame / liloc_frame_features) is enqueued WITHOUT any host round trip: every size that is
+// only known on the device (M, Q_all, the search-grid geometry) is consumed on the device.  Up to three
+// streams run the independent branches (surf map | surf scan | corner map + corner scan) concurrently and
+// join before the registration kernel; the host synchronises once, at the end.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
@@ -47,12 +52,44 @@ struct VgInst {            // scratch of one VoxelGrid instance (the reference h
     int bits_used = 32;
 };
 
+constexpr int kClasses = 2;        // LILOC_SURF, LILOC_CORNER
+
+// One feature class: its local map, search grid and current scan.  Class 0 (surf) is the reference's only
+// class; class 1 (corner) is the upstream LIO-SAM superset the north_star names.
+struct FeatClass {
+    // local map
+    DevBuf<float4> raw;            // concatenated, map frame
+    DevBuf<float4> map;            // down-sampled (voxel order)
+    DevBuf<float4> cpts;           // the same points sorted by search cell
+    DevBuf<KfDesc> descs;
+    KfDesc* h_descs = nullptr;     // pinned
+    size_t h_descs_cap = 0;
+    int n_raw = 0;
+    int M = -1;                    // host copy, -1 unknown
+    bool have_map = false;
+    float map_leaf_last = 0.f;
+    // search grid (geometry on the device)
+    GridParams* d_gp = nullptr;
+    DevBuf<int> cell_counts, cell_start, grid_tiles;
+    // scan
+    DevBuf<float4> scan_raw;
+    DevBuf<float4> scan;           // down-sampled
+    int Q_all = -1;
+    int q_prev = -1;               // Q_all of the previous frame (sizes the registration launch; never affects results)
+    int n_scan_last = 0;
+    const float4* scan_src_last = nullptr;
+    float scan_leaf_last = 0.f;
+    bool have_scan = false;
+    VgInst vg_map, vg_scan;
+    int* d_M = nullptr;            // = vg_map.d_count
+    int* d_Q = nullptr;            // = vg_scan.d_count
+};
+
+struct HostClassInfo { VgParams map_vp, scan_vp; GridParams gp; int M, Q_all; };
 struct HostFrameInfo {     // pinned, written by async D2H
-    VgParams map_vp;
-    VgParams scan_vp;
-    int M;
-    int Q_all;
+    HostClassInfo c[kClasses];
     S2mResult res;
+    int scratch;
 };
 
 }  // namespace
@@ -60,58 +97,33 @@ struct HostFrameInfo {     // pinned, written by async D2H
 struct liloc_ctx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // surf map branch, registration, everything step-wise
+    cudaStream_t stream2 = nullptr;      // surf scan branch of a fused frame
+    cudaStream_t stream3 = nullptr;      // corner branch of a fused frame
+    cudaEvent_t ev_fork = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
     std::string err;
     long long launches = 0;
 
     // keyframe arena
     DevBuf<float4> arena;
     size_t arena_used = 0;
-    struct KfEntry { size_t off; int n; };
+    struct KfEntry { size_t off[kClasses]; int n[kClasses]; };
     std::unordered_map<int, KfEntry> kf;
 
-    // local map
-    DevBuf<float4> raw;            // concatenated, map frame
-    DevBuf<float4> map;            // down-sampled (voxel order)
-    int n_raw = 0;
-    int M = -1;                    // host copy, -1 unknown
-    bool have_map = false;
-    bool have_grid = false;
-    DevBuf<KfDesc> descs;
-    KfDesc* h_descs = nullptr;     // pinned
-    size_t h_descs_cap = 0;
-
-    // scan
-    DevBuf<float4> scan_raw;
-    DevBuf<float4> scan;           // down-sampled
-    int Q_all = -1;
-    int n_scan_last = 0;
-    const float4* scan_src_last = nullptr;
-    float scan_leaf_last = 0.f, map_leaf_last = 0.f;
-    long long sort_redos = 0;
-    bool have_scan = false;
-
-    // VoxelGrid instances: local map (main stream) and current scan (second stream, overlaps the map branch)
-    VgInst vg_map, vg_scan;
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int* d_M = nullptr;            // = vg_map.d_count
-    int* d_Q = nullptr;            // = vg_scan.d_count
-    DevBuf<int> tile_counts;       // search-grid scan scratch
-
-    // search grid
-    GridParams gp{};
-    DevBuf<int> cell_counts, cell_start, cell_cursor;
-    DevBuf<float4> cpts;
+    FeatClass fc[kClasses];
     int max_cells = 1 << 24;
+    long long sort_redos = 0;
+    bool corner_scan_current = false;    // the last scan upload carried corner features too
 
     // scan2map
     DevBuf<double> partial;
     float* d_pose = nullptr;       // 6
-    S2mState* d_state = nullptr;
+    S2mState* d_state[2] = {nullptr, nullptr};   // double-buffered: a frame that has to be redone must not see its own update
+    int state_cur = 0;
     S2mResult* d_result = nullptr;
     int s2m_max_blocks = 0;
     int s2m_nq_last = 0;
+    int s2m_nq_corner_last = 0;
 
     // NDT: cached targets (prior submaps), sources (scans), job state
     struct NdtTargetHost { DevBuf<int> table; DevBuf<NdtLeaf> leaves; NdtTargetView view; int n_leaves; float resolution; int slot; };
@@ -176,6 +188,7 @@ int ensure(liloc_ctx* ctx, DevBuf<T>& b, size_t n, bool keep = false) {
     CU(cudaMalloc(&np, cap * sizeof(T)));
     if (b.p) {
         if (ctx->stream2) CU(cudaStreamSynchronize(ctx->stream2));
+        if (ctx->stream3) CU(cudaStreamSynchronize(ctx->stream3));
         if (keep) CU(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaFree(b.p));
@@ -191,6 +204,8 @@ inline int blocks_for(const liloc_ctx* ctx, long long n, int per_block, int wave
     if (b < 1) b = 1;
     return (int)b;
 }
+
+inline bool bad_class(int cls) { return cls < 0 || cls >= kClasses; }
 
 __global__ void k_init_enc(unsigned* enc) {
     if (threadIdx.x < 3) enc[threadIdx.x] = 0xFFFFFFFFu;
@@ -215,6 +230,22 @@ __global__ void k_debug_plane(const float* pts, int n, float* x) {
     for (int r = 0; r < 5; ++r) for (int c = 0; c < 3; ++c) P[r][c] = pts[15 * i + 3 * r + c];
     plane_lsq_5x3(P, X);
     x[3 * i] = X[0]; x[3 * i + 1] = X[1]; x[3 * i + 2] = X[2];
+}
+__global__ void k_debug_eigen3(const float* A, int n, float* w, float* V) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    eigen3_jacobi(A + 9 * i, w + 3 * i, V + 9 * i);
+}
+// cornerOptimization's loop body on explicit neighbours: pts15 = 5 x 3 neighbours, sel = pointSel
+__global__ void k_debug_line(const float* pts, const float* sel3, int n, float4* coeff, int* keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float P[5][3];
+    for (int r = 0; r < 5; ++r) for (int c = 0; c < 3; ++c) P[r][c] = pts[15 * i + 3 * r + c];
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 sel = make_float4(sel3[3 * i], sel3[3 * i + 1], sel3[3 * i + 2], 0.f);
+    keep[i] = corner_residual(P, 0.f, sel, &c) ? 1 : 0;
+    coeff[i] = c;
 }
 
 // VoxelGrid of a device cloud on stream `st`.  The bounding box must already be in vi.d_enc when have_minmax.
@@ -249,6 +280,7 @@ int vg_run(liloc_ctx* ctx, VgInst& vi, cudaStream_t st, const float4* d_pts, int
     k_vg_keys<<<blocks_for(ctx, n, 256 * 4), 256, 0, st>>>(d_pts, n, vi.d_vp, vi.keys_a.p, vi.vals_a.p); KCHECK();
     size_t tb = vi.cub_tmp.cap;
     CU(cub::DeviceRadixSort::SortPairs(vi.cub_tmp.p, tb, vi.keys_a.p, vi.keys_b.p, vi.vals_a.p, vi.vals_b.p, n, 0, bits, st));
+    ctx->launches += 2 + (bits + 7) / 8;           // histogram + exclusive sum + one onesweep pass per 8 bits
     if (sort_only) return 0;
     k_run_count<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, n, vi.tile_counts.p); KCHECK();
     k_scan_tiles<<<1, 1024, 0, st>>>(vi.tile_counts.p, n_tiles, vi.d_count); KCHECK();
@@ -261,148 +293,153 @@ inline int next_bits_hint(int key_bits) {       // one bit of head-room, rounded
     return b > 32 ? 32 : b;
 }
 
-// Search-grid geometry from the local map's bounding box: cell edge 2^k >= 1 m, one cell of padding.
-GridParams grid_geometry(const float mn[3], const float mx[3], int max_cells) {
-    GridParams g{};
-    for (int k = 0; k < 24; ++k) {
-        const float inv = 1.0f / (float)(1 << k);
-        long long cells = 1;
-        for (int a = 0; a < 3; ++a) {
-            g.g0[a] = (int)floorf(mn[a] * inv) - 1;
-            const int g1 = (int)floorf(mx[a] * inv) + 1;
-            g.dim[a] = g1 - g.g0[a] + 1;
-            cells *= g.dim[a];
-        }
-        g.inv_cell = inv;
-        if (cells <= max_cells) { g.ncells = (int)cells; return g; }
-    }
-    g.ncells = -1;
-    return g;
-}
-
-int grid_build(liloc_ctx* ctx, int M, const float mn[3], const float mx[3]) {
+// Search structure over fc.map (replaces kdtreeSurfFromMap->setInputCloud, :1188), entirely on the device:
+// geometry from the bounding box in the VoxelGrid params, count -> exclusive scan -> scatter.
+// m_upper = host-side upper bound of the number of map points (sizes launches and buffers).
+int grid_enqueue(liloc_ctx* ctx, FeatClass& fc, cudaStream_t st, int m_upper) {
     int rc;
-    ctx->have_grid = false;
-    float lo[3] = {mn[0], mn[1], mn[2]}, hi[3] = {mx[0], mx[1], mx[2]};
-    if (M <= 0) { for (int a = 0; a < 3; ++a) { lo[a] = 0.f; hi[a] = 0.f; } }
-    ctx->gp = grid_geometry(lo, hi, ctx->max_cells);
-    if (ctx->gp.ncells < 0) return fail(ctx, LILOC_ERR_CAPACITY, "local map extent does not fit the search grid");
-    const int nc = ctx->gp.ncells;
-    if ((rc = ensure(ctx, ctx->cell_counts, (size_t)nc))) return rc;
-    if ((rc = ensure(ctx, ctx->cell_start, (size_t)nc + 1))) return rc;
-    if ((rc = ensure(ctx, ctx->cell_cursor, (size_t)nc))) return rc;
-    if ((rc = ensure(ctx, ctx->cpts, (size_t)(M > 0 ? M : 1)))) return rc;
-    const int n_tiles = (nc + kScanTile - 1) / kScanTile;
-    if ((rc = ensure(ctx, ctx->tile_counts, (size_t)n_tiles + 1))) return rc;
-    k_zero_int<<<blocks_for(ctx, nc, 256 * 4), 256, 0, ctx->stream>>>(ctx->cell_counts.p, nc); KCHECK();
-    if (M > 0) { k_grid_count<<<blocks_for(ctx, M, 256), 256, 0, ctx->stream>>>(ctx->map.p, M, ctx->gp, ctx->cell_counts.p); KCHECK(); }
-    k_scan_reduce<<<n_tiles, kScanThreads, 0, ctx->stream>>>(ctx->cell_counts.p, nc, ctx->tile_counts.p); KCHECK();
-    k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(ctx->tile_counts.p, n_tiles, ctx->tile_counts.p + n_tiles); KCHECK();
-    k_scan_down<<<n_tiles, kScanThreads, 0, ctx->stream>>>(ctx->cell_counts.p, nc, ctx->tile_counts.p, ctx->cell_start.p, ctx->cell_cursor.p); KCHECK();
-    if (M > 0) { k_grid_scatter<<<blocks_for(ctx, M, 256), 256, 0, ctx->stream>>>(ctx->map.p, M, ctx->gp, ctx->cell_cursor.p, ctx->cpts.p); KCHECK(); }
-    ctx->have_grid = true;
+    const int nc_max = ctx->max_cells;
+    if ((rc = ensure(ctx, fc.cell_counts, (size_t)nc_max))) return rc;
+    if ((rc = ensure(ctx, fc.cell_start, (size_t)nc_max + 1))) return rc;
+    if ((rc = ensure(ctx, fc.grid_tiles, (size_t)(nc_max / kScanTile) + 2))) return rc;
+    if ((rc = ensure(ctx, fc.cpts, (size_t)(m_upper > 0 ? m_upper : 1)))) return rc;
+    const int wide = ctx->num_sms * 4;
+    const int n_tiles_max = nc_max / kScanTile + 1;
+    k_grid_params<<<1, 32, 0, st>>>(fc.vg_map.d_vp->mn, fc.vg_map.d_vp->mx, fc.d_M, nc_max, fc.d_gp); KCHECK();
+    k_grid_zero<<<wide, 256, 0, st>>>(fc.d_gp, fc.cell_counts.p); KCHECK();
+    k_grid_count<<<blocks_for(ctx, m_upper, 256), 256, 0, st>>>(fc.map.p, fc.d_M, fc.d_gp, fc.cell_counts.p); KCHECK();
+    k_scan_reduce<<<wide, kScanThreads, 0, st>>>(fc.cell_counts.p, fc.d_gp, fc.grid_tiles.p); KCHECK();
+    k_scan_tiles_grid<<<1, 1024, 0, st>>>(fc.grid_tiles.p, fc.d_gp, fc.grid_tiles.p + n_tiles_max); KCHECK();
+    k_scan_down<<<wide, kScanThreads, 0, st>>>(fc.cell_counts.p, fc.d_gp, fc.grid_tiles.p, fc.cell_start.p, fc.cell_counts.p); KCHECK();
+    k_grid_scatter<<<blocks_for(ctx, m_upper, 256), 256, 0, st>>>(fc.map.p, fc.d_M, fc.d_gp, fc.cell_counts.p, fc.cpts.p); KCHECK();
     return 0;
 }
 
-GridView grid_view(const liloc_ctx* ctx) {
-    GridView g{ctx->cell_start.p, ctx->cpts.p, ctx->gp};
+GridView grid_view(const FeatClass& fc) {
+    GridView g{fc.cell_start.p, fc.cpts.p, fc.d_gp};
     return g;
 }
 
-void tick(liloc_ctx* ctx, int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], ctx->stream); }
+void tick(liloc_ctx* ctx, int i, cudaStream_t st) { if (ctx->timing) cudaEventRecord(ctx->ev[i], st); }
 
-// enqueue: keyframe descriptors -> transform + concat + bbox -> VoxelGrid; async D2H of {params, M}
-int localmap_enqueue(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf, int bits = 32) {
+// enqueue on `st`: keyframe descriptors -> transform + concat + bbox -> VoxelGrid -> search grid;
+// async D2H of {params, M, grid geometry}.  `timed`: record the phase events (main-stream surf branch only).
+int localmap_enqueue(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids, const float* poses6, int K, float leaf,
+                     int bits, bool timed) {
+    FeatClass& fc = ctx->fc[cls];
     if (K < 0 || (K > 0 && (!kf_ids || !poses6)) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap: bad arguments");
     int rc;
-    ctx->have_map = false; ctx->have_grid = false; ctx->M = -1;
-    if ((size_t)K > ctx->h_descs_cap) {
-        if (ctx->h_descs) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFreeHost(ctx->h_descs)); ctx->h_descs = nullptr; }
+    fc.have_map = false; fc.M = -1;
+    if ((size_t)K > fc.h_descs_cap) {
+        if (fc.h_descs) { CU(cudaFreeHost(fc.h_descs)); fc.h_descs = nullptr; }
         size_t cap = 256; while (cap < (size_t)K) cap *= 2;
-        CU(cudaMallocHost(&ctx->h_descs, cap * sizeof(KfDesc)));
-        ctx->h_descs_cap = cap;
-    } else if (ctx->h_descs) {
-        CU(cudaStreamSynchronize(ctx->stream));      // previous async copy out of the pinned staging must be done
+        CU(cudaMallocHost(&fc.h_descs, cap * sizeof(KfDesc)));
+        fc.h_descs_cap = cap;
     }
     long long total = 0;
     for (int k = 0; k < K; ++k) {
         auto it = ctx->kf.find(kf_ids[k]);
         if (it == ctx->kf.end()) return fail(ctx, LILOC_ERR_ARG, "localmap: unknown keyframe id %d", kf_ids[k]);
-        KfDesc& d = ctx->h_descs[k];
-        d.src_off = (long long)it->second.off; d.n = it->second.n; d.dst_off = (int)total;
+        KfDesc& d = fc.h_descs[k];
+        d.src_off = (long long)it->second.off[cls]; d.n = it->second.n[cls]; d.dst_off = (int)total;
         pose_to_T(poses6 + 6 * (size_t)k, d.T);
-        total += it->second.n;
+        total += it->second.n[cls];
         if (total > 0x7fffffffLL) return fail(ctx, LILOC_ERR_CAPACITY, "localmap: more than 2^31 points");
     }
-    ctx->n_raw = (int)total;
-    tick(ctx, 0);
+    fc.n_raw = (int)total;
+    if (timed) tick(ctx, 0, st);
     if (total > 0) {
-        if ((rc = ensure(ctx, ctx->descs, (size_t)K))) return rc;
-        if ((rc = ensure(ctx, ctx->raw, (size_t)total))) return rc;
-        CU(cudaMemcpyAsync(ctx->descs.p, ctx->h_descs, (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = ensure(ctx, fc.descs, (size_t)K))) return rc;
+        if ((rc = ensure(ctx, fc.raw, (size_t)total))) return rc;
+        CU(cudaMemcpyAsync(fc.descs.p, fc.h_descs, (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += (long long)K * (long long)sizeof(KfDesc);
-        k_init_enc<<<1, 32, 0, ctx->stream>>>(ctx->vg_map.d_enc); KCHECK();
-        k_assemble<<<blocks_for(ctx, total, kAsmTile), kMinMaxThreads, 0, ctx->stream>>>(ctx->arena.p, ctx->descs.p, K, (int)total, ctx->raw.p, ctx->vg_map.d_enc); KCHECK();
+        k_init_enc<<<1, 32, 0, st>>>(fc.vg_map.d_enc); KCHECK();
+        k_assemble<<<blocks_for(ctx, total, kAsmTile), kMinMaxThreads, 0, st>>>(ctx->arena.p, fc.descs.p, K, (int)total, fc.raw.p, fc.vg_map.d_enc); KCHECK();
     }
-    tick(ctx, 1);
-    ctx->map_leaf_last = leaf;
-    if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->raw.p, (int)total, leaf, true, ctx->map, bits))) return rc;
-    tick(ctx, 2);
-    if (total > 0) CU(cudaMemcpyAsync(&ctx->h_info->map_vp, ctx->vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->h_info->M, ctx->d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (timed) tick(ctx, 1, st);
+    fc.map_leaf_last = leaf;
+    if ((rc = vg_run(ctx, fc.vg_map, st, fc.raw.p, (int)total, leaf, true, fc.map, bits))) return rc;
+    if (timed) tick(ctx, 2, st);
+    if ((rc = grid_enqueue(ctx, fc, st, (int)total))) return rc;
+    if (timed) tick(ctx, 3, st);
+    HostClassInfo& hi = ctx->h_info->c[cls];
+    if (total > 0) CU(cudaMemcpyAsync(&hi.map_vp, fc.vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hi.M, fc.d_M, sizeof(int), cudaMemcpyDeviceToHost, st));
     ctx->stats.d2h_bytes += (long long)sizeof(VgParams) + 4;
-    ctx->have_map = true;
+    fc.have_map = true;
     return 0;
 }
 
-// after a stream sync: pick up M and the bounding box, build the search grid
-int localmap_finish(liloc_ctx* ctx) {
-    ctx->M = ctx->h_info->M;
-    return grid_build(ctx, ctx->M, ctx->h_info->map_vp.mn, ctx->h_info->map_vp.mx);
-}
-
-int scan_enqueue(liloc_ctx* ctx, const liloc_point* pts, int n, bool on_device, float leaf, cudaStream_t st = nullptr, int bits = 32) {
-    if (!st) st = ctx->stream;
+int scan_enqueue(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pts, int n, bool on_device, float leaf, int bits) {
+    FeatClass& fc = ctx->fc[cls];
     if (n < 0 || (n > 0 && !pts) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad arguments");
     int rc;
-    ctx->have_scan = false; ctx->Q_all = -1;
+    fc.have_scan = false; fc.Q_all = -1;
     const float4* src = reinterpret_cast<const float4*>(pts);
     if (!on_device && n > 0) {
-        if ((rc = ensure(ctx, ctx->scan_raw, (size_t)n))) return rc;
-        CU(cudaMemcpyAsync(ctx->scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+        if ((rc = ensure(ctx, fc.scan_raw, (size_t)n))) return rc;
+        CU(cudaMemcpyAsync(fc.scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += (long long)n * (long long)sizeof(float4);
-        src = ctx->scan_raw.p;
+        src = fc.scan_raw.p;
     }
-    ctx->scan_src_last = src; ctx->scan_leaf_last = leaf;
-    if ((rc = vg_run(ctx, ctx->vg_scan, st, src, n, leaf, false, ctx->scan, bits))) return rc;
-    if (n > 0) CU(cudaMemcpyAsync(&ctx->h_info->scan_vp, ctx->vg_scan.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&ctx->h_info->Q_all, ctx->d_Q, sizeof(int), cudaMemcpyDeviceToHost, st));
+    fc.scan_src_last = src; fc.scan_leaf_last = leaf;
+    if ((rc = vg_run(ctx, fc.vg_scan, st, src, n, leaf, false, fc.scan, bits))) return rc;
+    HostClassInfo& hi = ctx->h_info->c[cls];
+    if (n > 0) CU(cudaMemcpyAsync(&hi.scan_vp, fc.vg_scan.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hi.Q_all, fc.d_Q, sizeof(int), cudaMemcpyDeviceToHost, st));
     ctx->stats.d2h_bytes += 4 + (long long)sizeof(VgParams);
-    ctx->n_scan_last = n;
-    ctx->have_scan = true;
+    fc.n_scan_last = n;
+    fc.have_scan = true;
     return 0;
 }
 
-int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
-    if (!ctx->have_map || !ctx->have_grid) return fail(ctx, LILOC_ERR_STATE, "scan2map: no local map");
-    if (!ctx->have_scan || ctx->Q_all < 0) return fail(ctx, LILOC_ERR_STATE, "scan2map: no scan");
+const liloc_s2m_opts kDefaultOpts = {20, 2, 50, 30, 0, 10, 1, {0}};
+
+FeatView feat_view(const FeatClass& fc, int stride) {
+    FeatView v{};
+    v.scan = fc.scan.p; v.q_all = fc.d_Q; v.map = fc.map.p; v.map_count = fc.d_M;
+    v.grid = grid_view(fc); v.stride = stride < 1 ? 1 : stride;
+    return v;
+}
+
+int s2m_args(liloc_ctx* ctx, const liloc_s2m_opts* o, S2mArgs* a) {
+    const bool corner = o->enable_corner != 0;
+    for (int cls = 0; cls < (corner ? 2 : 1); ++cls) {
+        if (!ctx->fc[cls].have_map) return fail(ctx, LILOC_ERR_STATE, "scan2map: no %s local map", cls ? "corner" : "surf");
+        if (!ctx->fc[cls].have_scan) return fail(ctx, LILOC_ERR_STATE, "scan2map: no %s scan", cls ? "corner" : "surf");
+    }
     if (o->stride < 1 || o->max_iters < 1) return fail(ctx, LILOC_ERR_ARG, "scan2map: bad options");
+    *a = S2mArgs{};
+    a->f[0] = feat_view(ctx->fc[0], o->stride);
+    a->f[1] = feat_view(ctx->fc[1], o->stride_corner);
+    a->enable_corner = corner ? 1 : 0;
+    a->max_iters = o->max_iters; a->min_sel = o->min_sel; a->min_points = o->min_points; a->min_corner = o->min_points_corner;
+    return 0;
+}
+
+// Enqueue the registration kernel on the main stream.  Q_all is only known on the device here, so the launch is
+// sized from host-side upper bounds (the raw scan sizes); idle blocks only take part in the grid barrier.
+int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     int rc;
-    const int nq = (ctx->Q_all + o->stride - 1) / o->stride;
-    int blocks = (nq + kQPB - 1) / kQPB;
+    S2mArgs a;
+    if ((rc = s2m_args(ctx, o, &a))) return rc;
+    auto upper = [](const FeatClass& fc) {
+        if (fc.Q_all >= 0) return fc.Q_all;
+        const int guess = fc.q_prev > 0 ? fc.q_prev + fc.q_prev / 4 + kQPB : fc.n_scan_last;
+        return guess < fc.n_scan_last ? guess : fc.n_scan_last;
+    };
+    long long nq = (upper(ctx->fc[0]) + a.f[0].stride - 1) / a.f[0].stride;
+    if (a.enable_corner) nq += (upper(ctx->fc[1]) + a.f[1].stride - 1) / a.f[1].stride + kQPB;
+    long long blocks = (nq + kQPB - 1) / kQPB;
     if (blocks > ctx->s2m_max_blocks) blocks = ctx->s2m_max_blocks;
     if (blocks < 1) blocks = 1;
     if ((rc = ensure(ctx, ctx->partial, (size_t)2 * blocks * kNSums))) return rc;
     CU(cudaMemcpyAsync(ctx->d_pose, pose6, 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += 24;
-    ctx->s2m_nq_last = nq;
-    S2mArgs a{};
-    a.scan = ctx->scan.p; a.q_all = ctx->d_Q; a.map = ctx->map.p; a.map_count = ctx->d_M;
-    a.grid = grid_view(ctx);
-    a.stride = o->stride; a.max_iters = o->max_iters; a.min_sel = o->min_sel; a.min_points = o->min_points;
-    a.partial = ctx->partial.p; a.pose_io = ctx->d_pose; a.state = ctx->d_state; a.result = ctx->d_result;
+    a.partial = ctx->partial.p; a.pose_io = ctx->d_pose;
+    a.state = ctx->d_state[ctx->state_cur]; a.state_out = ctx->d_state[ctx->state_cur ^ 1]; a.result = ctx->d_result;
     void* args[] = {&a};
-    CU(cudaLaunchCooperativeKernel((void*)k_scan2map, dim3(blocks), dim3(kS2mThreads), args, 0, ctx->stream));
+    CU(cudaLaunchCooperativeKernel((void*)k_scan2map, dim3((unsigned)blocks), dim3(kS2mThreads), args, 0, ctx->stream));
     ++ctx->launches;
     CU(cudaMemcpyAsync(&ctx->h_info->res, ctx->d_result, sizeof(S2mResult), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += (long long)sizeof(S2mResult);
@@ -410,23 +447,33 @@ int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     return 0;
 }
 
-int s2m_collect(liloc_ctx* ctx, float* pose6, liloc_s2m_result* res) {
+// after the stream sync: commit the 6x6 state, hand out the result
+int s2m_collect(liloc_ctx* ctx, float* pose6, liloc_s2m_result* res, const liloc_s2m_opts* o) {
     const S2mResult& r = ctx->h_info->res;
     static_assert(sizeof(liloc_s2m_result) == 8 * sizeof(int) + 72 * sizeof(float), "result layout");
+    ctx->state_cur ^= 1;
     if (res) std::memcpy(res, &r, sizeof(liloc_s2m_result));
     if (!r.skipped) std::memcpy(pose6, r.pose, 6 * sizeof(float));
+    const int st0 = o->stride < 1 ? 1 : o->stride, st1 = o->stride_corner < 1 ? 1 : o->stride_corner;
+    ctx->s2m_nq_last = (r.q_all + st0 - 1) / st0;
+    ctx->s2m_nq_corner_last = o->enable_corner ? (r.extra[0] + st1 - 1) / st1 : 0;
     ctx->stats.s2m_iters += r.iters;
-    ctx->stats.alg_bytes_s2m += (double)r.iters * (96.0 * ctx->s2m_nq_last + 216.0);
+    ctx->stats.alg_bytes_s2m += (double)r.iters * (96.0 * (ctx->s2m_nq_last + ctx->s2m_nq_corner_last) + 216.0);
     return r.skipped ? LILOC_SKIPPED : LILOC_OK;
 }
 
-const liloc_s2m_opts kDefaultOpts = {20, 2, 50, 30, {0, 0, 0, 0}};
+// pick up the device-side counts after a synchronisation
+void class_collect(liloc_ctx* ctx, int cls, bool map, bool scan) {
+    FeatClass& fc = ctx->fc[cls];
+    if (map) fc.M = ctx->h_info->c[cls].M;
+    if (scan) { fc.Q_all = ctx->h_info->c[cls].Q_all; fc.q_prev = fc.Q_all; }
+}
 
 }  // namespace
 
 extern "C" {
 
-const char* liloc_version(void) { return "liloc_b200 0.1 (sm_100a)"; }
+const char* liloc_version(void) { return "liloc_b200 0.2 (sm_100a)"; }
 
 const char* liloc_last_error(const liloc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -449,22 +496,27 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
     CUB_(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB_(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUB_(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     CUB_(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CUB_(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    for (VgInst* vi : {&c->vg_map, &c->vg_scan}) {
-        CUB_(cudaMalloc(&vi->d_enc, 6 * sizeof(unsigned)));
-        CUB_(cudaMalloc(&vi->d_vp, sizeof(VgParams)));
-        CUB_(cudaMalloc(&vi->d_count, sizeof(int)));
+    CUB_(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
+    for (FeatClass& fc : c->fc) {
+        for (VgInst* vi : {&fc.vg_map, &fc.vg_scan}) {
+            CUB_(cudaMalloc(&vi->d_enc, 6 * sizeof(unsigned)));
+            CUB_(cudaMalloc(&vi->d_vp, sizeof(VgParams)));
+            CUB_(cudaMalloc(&vi->d_count, sizeof(int)));
+            CUB_(cudaMemset(vi->d_vp, 0, sizeof(VgParams)));
+            CUB_(cudaMemset(vi->d_count, 0, sizeof(int)));
+        }
+        fc.d_M = fc.vg_map.d_count;
+        fc.d_Q = fc.vg_scan.d_count;
+        CUB_(cudaMalloc(&fc.d_gp, sizeof(GridParams)));
+        CUB_(cudaMemset(fc.d_gp, 0, sizeof(GridParams)));
     }
-    c->d_M = c->vg_map.d_count;
-    c->d_Q = c->vg_scan.d_count;
     CUB_(cudaMalloc(&c->d_pose, 6 * sizeof(float)));
-    CUB_(cudaMalloc(&c->d_state, sizeof(S2mState)));
+    for (auto& s : c->d_state) { CUB_(cudaMalloc(&s, sizeof(S2mState))); CUB_(cudaMemset(s, 0, sizeof(S2mState))); }
     CUB_(cudaMalloc(&c->d_result, sizeof(S2mResult)));
-    CUB_(cudaMemset(c->d_state, 0, sizeof(S2mState)));
     CUB_(cudaMemset(c->d_result, 0, sizeof(S2mResult)));
-    CUB_(cudaMemset(c->d_M, 0, sizeof(int)));
-    CUB_(cudaMemset(c->d_Q, 0, sizeof(int)));
     CUB_(cudaMalloc(&c->d_ndt_active, sizeof(int)));
     CUB_(cudaMallocHost(&c->h_info, sizeof(HostFrameInfo)));
     std::memset(c->h_info, 0, sizeof(HostFrameInfo));
@@ -476,14 +528,17 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
 #undef CUB_
     const int scan_cap = cfg->max_scan_points > 0 ? cfg->max_scan_points : 16 * 1800;
     const int raw_cap = cfg->max_raw_points > 0 ? cfg->max_raw_points : (1 << 20);
+    FeatClass& s = c->fc[0];
     int rc;
-    if ((rc = ensure(c, c->scan_raw, (size_t)scan_cap)) || (rc = ensure(c, c->scan, (size_t)scan_cap)) ||
-        (rc = ensure(c, c->raw, (size_t)raw_cap)) || (rc = ensure(c, c->map, (size_t)raw_cap)) ||
-        (rc = ensure(c, c->vg_map.keys_a, (size_t)raw_cap)) || (rc = ensure(c, c->vg_map.keys_b, (size_t)raw_cap)) ||
-        (rc = ensure(c, c->vg_map.vals_a, (size_t)raw_cap)) || (rc = ensure(c, c->vg_map.vals_b, (size_t)raw_cap)) ||
-        (rc = ensure(c, c->vg_scan.keys_a, (size_t)scan_cap)) || (rc = ensure(c, c->vg_scan.keys_b, (size_t)scan_cap)) ||
-        (rc = ensure(c, c->vg_scan.vals_a, (size_t)scan_cap)) || (rc = ensure(c, c->vg_scan.vals_b, (size_t)scan_cap)) ||
-        (rc = ensure(c, c->arena, (size_t)raw_cap)) || (rc = ensure(c, c->cpts, (size_t)raw_cap)) ||
+    if ((rc = ensure(c, s.scan_raw, (size_t)scan_cap)) || (rc = ensure(c, s.scan, (size_t)scan_cap)) ||
+        (rc = ensure(c, s.raw, (size_t)raw_cap)) || (rc = ensure(c, s.map, (size_t)raw_cap)) ||
+        (rc = ensure(c, s.vg_map.keys_a, (size_t)raw_cap)) || (rc = ensure(c, s.vg_map.keys_b, (size_t)raw_cap)) ||
+        (rc = ensure(c, s.vg_map.vals_a, (size_t)raw_cap)) || (rc = ensure(c, s.vg_map.vals_b, (size_t)raw_cap)) ||
+        (rc = ensure(c, s.vg_scan.keys_a, (size_t)scan_cap)) || (rc = ensure(c, s.vg_scan.keys_b, (size_t)scan_cap)) ||
+        (rc = ensure(c, s.vg_scan.vals_a, (size_t)scan_cap)) || (rc = ensure(c, s.vg_scan.vals_b, (size_t)scan_cap)) ||
+        (rc = ensure(c, c->arena, (size_t)raw_cap)) || (rc = ensure(c, s.cpts, (size_t)raw_cap)) ||
+        (rc = ensure(c, s.cell_counts, (size_t)c->max_cells)) || (rc = ensure(c, s.cell_start, (size_t)c->max_cells + 1)) ||
+        (rc = ensure(c, s.grid_tiles, (size_t)(c->max_cells / kScanTile) + 2)) ||
         (rc = ensure(c, c->partial, (size_t)2 * c->s2m_max_blocks * kNSums)))
         return bail(rc);
     *out = c;
@@ -493,27 +548,29 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
 void liloc_destroy(liloc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (cudaStream_t st : {c->stream, c->stream2, c->stream3}) if (st) cudaStreamSynchronize(st);
     auto fr = [](void* p) { if (p) cudaFree(p); };
-    fr(c->arena.p); fr(c->raw.p); fr(c->map.p); fr(c->descs.p); fr(c->scan_raw.p); fr(c->scan.p);
-    for (VgInst* vi : {&c->vg_map, &c->vg_scan}) {
-        fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->cub_tmp.p); fr(vi->tile_counts.p);
-        fr(vi->d_enc); fr(vi->d_vp); fr(vi->d_count);
+    fr(c->arena.p);
+    for (FeatClass& fc : c->fc) {
+        fr(fc.raw.p); fr(fc.map.p); fr(fc.cpts.p); fr(fc.descs.p); fr(fc.scan_raw.p); fr(fc.scan.p);
+        fr(fc.cell_counts.p); fr(fc.cell_start.p); fr(fc.grid_tiles.p); fr(fc.d_gp);
+        if (fc.h_descs) cudaFreeHost(fc.h_descs);
+        for (VgInst* vi : {&fc.vg_map, &fc.vg_scan}) {
+            fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->cub_tmp.p); fr(vi->tile_counts.p);
+            fr(vi->d_enc); fr(vi->d_vp); fr(vi->d_count);
+        }
     }
-    fr(c->tile_counts.p);
-    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    fr(c->cell_counts.p); fr(c->cell_start.p); fr(c->cell_cursor.p); fr(c->cpts.p);
-    fr(c->partial.p); fr(c->d_pose); fr(c->d_state); fr(c->d_result);
+    if (c->ev_join2) cudaEventDestroy(c->ev_join2);
+    if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+    fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
     fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
-    if (c->h_descs) cudaFreeHost(c->h_descs);
     if (c->h_info) cudaFreeHost(c->h_info);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (cudaStream_t st : {c->stream2, c->stream3, c->stream}) if (st) cudaStreamDestroy(st);
     delete c;
 }
 
@@ -522,34 +579,55 @@ void liloc_destroy(liloc_ctx* c) {
     { cudaError_t e_ = cudaSetDevice((ctx)->device);                                   \
       if (e_ != cudaSuccess) return fail((ctx), LILOC_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); }
 
-int liloc_keyframe_put(liloc_ctx* ctx, int kf_id, const liloc_point* pts, int n) {
+// ---- keyframe store -----------------------------------------------------------------------------------
+int liloc_keyframe_put_features(liloc_ctx* ctx, int kf_id, const liloc_point* surf, int n_surf, const liloc_point* corner, int n_corner) {
     ENTER(ctx);
-    if (n < 0 || (n > 0 && !pts)) return fail(ctx, LILOC_ERR_ARG, "keyframe_put: bad arguments");
+    if (n_surf < 0 || n_corner < 0 || (n_surf > 0 && !surf) || (n_corner > 0 && !corner)) return fail(ctx, LILOC_ERR_ARG, "keyframe_put: bad arguments");
     int rc;
-    if ((rc = ensure(ctx, ctx->arena, ctx->arena_used + (size_t)n, true))) return rc;
-    if (n > 0) CU(cudaMemcpyAsync(ctx->arena.p + ctx->arena_used, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->kf[kf_id] = liloc_ctx::KfEntry{ctx->arena_used, n};
-    ctx->arena_used += (size_t)n;
+    if ((rc = ensure(ctx, ctx->arena, ctx->arena_used + (size_t)n_surf + (size_t)n_corner, true))) return rc;
+    liloc_ctx::KfEntry e{};
+    e.off[0] = ctx->arena_used; e.n[0] = n_surf;
+    e.off[1] = ctx->arena_used + (size_t)n_surf; e.n[1] = n_corner;
+    if (n_surf > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[0], surf, (size_t)n_surf * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_corner > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[1], corner, (size_t)n_corner * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));          // the caller may free its buffers on return
+    ctx->kf[kf_id] = e;
+    ctx->arena_used += (size_t)n_surf + (size_t)n_corner;
     return LILOC_OK;
+}
+
+int liloc_keyframe_put(liloc_ctx* ctx, int kf_id, const liloc_point* pts, int n) {
+    return liloc_keyframe_put_features(ctx, kf_id, pts, n, nullptr, 0);
 }
 
 int liloc_keyframe_put_from_scan(liloc_ctx* ctx, int kf_id) {
     ENTER(ctx);
-    if (!ctx->have_scan) return fail(ctx, LILOC_ERR_STATE, "keyframe_put_from_scan: no scan");
-    if (ctx->Q_all < 0) { CU(cudaStreamSynchronize(ctx->stream)); ctx->Q_all = ctx->h_info->Q_all; }
-    const int n = ctx->Q_all;
+    FeatClass& s = ctx->fc[0];
+    FeatClass& cr = ctx->fc[1];
+    if (!s.have_scan || s.Q_all < 0) return fail(ctx, LILOC_ERR_STATE, "keyframe_put_from_scan: no scan");
+    const bool corner = ctx->corner_scan_current && cr.have_scan && cr.Q_all >= 0;
+    const int n0 = s.Q_all, n1 = corner ? cr.Q_all : 0;
     int rc;
-    if ((rc = ensure(ctx, ctx->arena, ctx->arena_used + (size_t)n, true))) return rc;
-    if (n > 0) CU(cudaMemcpyAsync(ctx->arena.p + ctx->arena_used, ctx->scan.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->kf[kf_id] = liloc_ctx::KfEntry{ctx->arena_used, n};
-    ctx->arena_used += (size_t)n;
+    if ((rc = ensure(ctx, ctx->arena, ctx->arena_used + (size_t)n0 + (size_t)n1, true))) return rc;
+    liloc_ctx::KfEntry e{};
+    e.off[0] = ctx->arena_used; e.n[0] = n0; e.off[1] = ctx->arena_used + (size_t)n0; e.n[1] = n1;
+    if (n0 > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[0], s.scan.p, (size_t)n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n1 > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[1], cr.scan.p, (size_t)n1 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->kf[kf_id] = e;
+    ctx->arena_used += (size_t)n0 + (size_t)n1;
     return LILOC_OK;
 }
 
 int liloc_keyframe_size(liloc_ctx* ctx, int kf_id) {
     if (!ctx) return LILOC_ERR_ARG;
     auto it = ctx->kf.find(kf_id);
-    return it == ctx->kf.end() ? LILOC_ERR_ARG : it->second.n;
+    return it == ctx->kf.end() ? LILOC_ERR_ARG : it->second.n[0];
+}
+
+int liloc_keyframe_size_class(liloc_ctx* ctx, int cls, int kf_id) {
+    if (!ctx || bad_class(cls)) return LILOC_ERR_ARG;
+    auto it = ctx->kf.find(kf_id);
+    return it == ctx->kf.end() ? LILOC_ERR_ARG : it->second.n[cls];
 }
 
 int liloc_keyframe_clear(liloc_ctx* ctx) {
@@ -559,137 +637,169 @@ int liloc_keyframe_clear(liloc_ctx* ctx) {
     return LILOC_OK;
 }
 
-int liloc_localmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf, int* M_out, int* n_raw_out) {
+// ---- local map ----------------------------------------------------------------------------------------
+int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const float* poses6, int K, float leaf, int* M_out, int* n_raw_out) {
     ENTER(ctx);
+    if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "localmap_build: bad class %d", cls);
     int rc;
-    if ((rc = localmap_enqueue(ctx, kf_ids, poses6, K, leaf))) return rc;
+    if ((rc = localmap_enqueue(ctx, cls, ctx->stream, kf_ids, poses6, K, leaf, 32, false))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
-    if ((rc = localmap_finish(ctx))) return rc;
-    if (M_out) *M_out = ctx->M;
-    if (n_raw_out) *n_raw_out = ctx->n_raw;
+    class_collect(ctx, cls, true, false);
+    if (M_out) *M_out = ctx->fc[cls].M;
+    if (n_raw_out) *n_raw_out = ctx->fc[cls].n_raw;
+    return LILOC_OK;
+}
+
+int liloc_localmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf, int* M_out, int* n_raw_out) {
+    return liloc_localmap_build_class(ctx, LILOC_SURF, kf_ids, poses6, K, leaf, M_out, n_raw_out);
+}
+
+int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts, int n, float leaf, int* M_out) {
+    ENTER(ctx);
+    if (bad_class(cls) || n < 0 || (n > 0 && !pts) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap_set: bad arguments");
+    FeatClass& fc = ctx->fc[cls];
+    int rc;
+    fc.have_map = false; fc.M = -1;
+    if ((rc = ensure(ctx, fc.raw, (size_t)(n > 0 ? n : 1)))) return rc;
+    if (n > 0) CU(cudaMemcpyAsync(fc.raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    fc.n_raw = n;
+    if ((rc = vg_run(ctx, fc.vg_map, ctx->stream, fc.raw.p, n, leaf, false, fc.map, 32))) return rc;
+    if ((rc = grid_enqueue(ctx, fc, ctx->stream, n))) return rc;
+    HostClassInfo& hi = ctx->h_info->c[cls];
+    if (n > 0) CU(cudaMemcpyAsync(&hi.map_vp, fc.vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hi.M, fc.d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    fc.have_map = true;
+    class_collect(ctx, cls, true, false);
+    if (M_out) *M_out = fc.M;
     return LILOC_OK;
 }
 
 int liloc_localmap_set(liloc_ctx* ctx, const liloc_point* pts, int n, float leaf, int* M_out) {
-    ENTER(ctx);
-    if (n < 0 || (n > 0 && !pts) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap_set: bad arguments");
-    int rc;
-    ctx->have_map = false; ctx->have_grid = false; ctx->M = -1;
-    if ((rc = ensure(ctx, ctx->raw, (size_t)(n > 0 ? n : 1)))) return rc;
-    if (n > 0) CU(cudaMemcpyAsync(ctx->raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->n_raw = n;
-    if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->raw.p, n, leaf, false, ctx->map, 32))) return rc;
-    if (n > 0) CU(cudaMemcpyAsync(&ctx->h_info->map_vp, ctx->vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->h_info->M, ctx->d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->have_map = true;
-    if ((rc = localmap_finish(ctx))) return rc;
-    if (M_out) *M_out = ctx->M;
-    return LILOC_OK;
+    return liloc_localmap_set_class(ctx, LILOC_SURF, pts, n, leaf, M_out);
 }
 
-int liloc_localmap_get(liloc_ctx* ctx, liloc_point* out, int cap, int* M_out) {
+int liloc_localmap_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, int* M_out) {
     ENTER(ctx);
-    if (!ctx->have_map || ctx->M < 0) return fail(ctx, LILOC_ERR_STATE, "localmap_get: no local map");
-    if (M_out) *M_out = ctx->M;
+    if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "localmap_get: bad class %d", cls);
+    FeatClass& fc = ctx->fc[cls];
+    if (!fc.have_map || fc.M < 0) return fail(ctx, LILOC_ERR_STATE, "localmap_get: no local map");
+    if (M_out) *M_out = fc.M;
     if (out) {
-        if (cap < ctx->M) return fail(ctx, LILOC_ERR_CAPACITY, "localmap_get: cap %d < M %d", cap, ctx->M);
-        if (ctx->M > 0) CU(cudaMemcpyAsync(out, ctx->map.p, (size_t)ctx->M * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        if (cap < fc.M) return fail(ctx, LILOC_ERR_CAPACITY, "localmap_get: cap %d < M %d", cap, fc.M);
+        if (fc.M > 0) CU(cudaMemcpyAsync(out, fc.map.p, (size_t)fc.M * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return LILOC_OK;
 }
 
-int liloc_scan_put(liloc_ctx* ctx, const liloc_point* pts, int n, float leaf, int* Q_all_out) {
+int liloc_localmap_get(liloc_ctx* ctx, liloc_point* out, int cap, int* M_out) { return liloc_localmap_get_class(ctx, LILOC_SURF, out, cap, M_out); }
+
+// ---- current scan -------------------------------------------------------------------------------------
+static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n, bool on_device, float leaf, int* Q_all_out) {
     ENTER(ctx);
+    if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad class %d", cls);
     int rc;
-    if ((rc = scan_enqueue(ctx, pts, n, false, leaf))) return rc;
+    if ((rc = scan_enqueue(ctx, cls, ctx->stream, pts, n, on_device, leaf, 32))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->Q_all = ctx->h_info->Q_all;
-    if (Q_all_out) *Q_all_out = ctx->Q_all;
+    class_collect(ctx, cls, false, true);
+    if (cls == LILOC_SURF) ctx->corner_scan_current = false;      // a new frame starts with its surf scan
+    else ctx->corner_scan_current = true;
+    if (Q_all_out) *Q_all_out = ctx->fc[cls].Q_all;
     return LILOC_OK;
 }
 
-int liloc_scan_put_dev(liloc_ctx* ctx, const liloc_point* pts_dev, int n, float leaf, int* Q_all_out) {
-    ENTER(ctx);
-    int rc;
-    if ((rc = scan_enqueue(ctx, pts_dev, n, true, leaf))) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->Q_all = ctx->h_info->Q_all;
-    if (Q_all_out) *Q_all_out = ctx->Q_all;
-    return LILOC_OK;
+int liloc_scan_put(liloc_ctx* ctx, const liloc_point* pts, int n, float leaf, int* Q_all_out) { return scan_put_impl(ctx, LILOC_SURF, pts, n, false, leaf, Q_all_out); }
+int liloc_scan_put_dev(liloc_ctx* ctx, const liloc_point* pts_dev, int n, float leaf, int* Q_all_out) { return scan_put_impl(ctx, LILOC_SURF, pts_dev, n, true, leaf, Q_all_out); }
+int liloc_scan_put_class(liloc_ctx* ctx, int cls, const liloc_point* pts, int n, int on_device, float leaf, int* Q_all_out) {
+    return scan_put_impl(ctx, cls, pts, n, on_device != 0, leaf, Q_all_out);
 }
 
-int liloc_scan_ds_get(liloc_ctx* ctx, liloc_point* out, int cap, int* Q_all_out) {
+int liloc_scan_ds_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, int* Q_all_out) {
     ENTER(ctx);
-    if (!ctx->have_scan || ctx->Q_all < 0) return fail(ctx, LILOC_ERR_STATE, "scan_ds_get: no scan");
-    if (Q_all_out) *Q_all_out = ctx->Q_all;
+    if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "scan_ds_get: bad class %d", cls);
+    FeatClass& fc = ctx->fc[cls];
+    if (!fc.have_scan || fc.Q_all < 0) return fail(ctx, LILOC_ERR_STATE, "scan_ds_get: no scan");
+    if (Q_all_out) *Q_all_out = fc.Q_all;
     if (out) {
-        if (cap < ctx->Q_all) return fail(ctx, LILOC_ERR_CAPACITY, "scan_ds_get: cap %d < Q_all %d", cap, ctx->Q_all);
-        if (ctx->Q_all > 0) CU(cudaMemcpyAsync(out, ctx->scan.p, (size_t)ctx->Q_all * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        if (cap < fc.Q_all) return fail(ctx, LILOC_ERR_CAPACITY, "scan_ds_get: cap %d < Q_all %d", cap, fc.Q_all);
+        if (fc.Q_all > 0) CU(cudaMemcpyAsync(out, fc.scan.p, (size_t)fc.Q_all * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return LILOC_OK;
 }
 
+int liloc_scan_ds_get(liloc_ctx* ctx, liloc_point* out, int cap, int* Q_all_out) { return liloc_scan_ds_get_class(ctx, LILOC_SURF, out, cap, Q_all_out); }
+
+// ---- registration -------------------------------------------------------------------------------------
 int liloc_scan2map(liloc_ctx* ctx, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
     ENTER(ctx);
     if (!pose6) return fail(ctx, LILOC_ERR_ARG, "scan2map: null pose");
     const liloc_s2m_opts* o = opts ? opts : &kDefaultOpts;
     int rc;
-    tick(ctx, 4);
+    tick(ctx, 4, ctx->stream);
     if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
-    tick(ctx, 5);
+    tick(ctx, 5, ctx->stream);
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->timing) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->last_timing.s2m_ms = ms; }
-    return s2m_collect(ctx, pose6, res);
+    return s2m_collect(ctx, pose6, res, o);
 }
 
-int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K, float map_leaf,
-                const liloc_point* scan, int n_scan, int scan_on_device, float scan_leaf,
-                float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
+int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
     ENTER(ctx);
-    if (!pose6) return fail(ctx, LILOC_ERR_ARG, "frame: null pose");
+    if (!pose6 || !in) return fail(ctx, LILOC_ERR_ARG, "frame: null argument");
     const liloc_s2m_opts* o = opts ? opts : &kDefaultOpts;
+    const bool corner = o->enable_corner != 0;
+    FeatClass& fs = ctx->fc[0];
+    FeatClass& fcn = ctx->fc[1];
+    const bool dev = in->scan_on_device != 0;
     int rc;
-    // fork: the scan branch (H2D + VoxelGrid) runs on stream2 while the map branch runs on the main stream
-    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
-    if ((rc = scan_enqueue(ctx, scan, n_scan, scan_on_device != 0, scan_leaf, ctx->stream2, ctx->vg_scan.bits_hint))) return rc;
-    if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
-    CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
-    if ((rc = localmap_enqueue(ctx, kf_ids, kf_poses6, K, map_leaf, ctx->vg_map.bits_hint))) return rc;    // ev 0,1,2
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));                                              // join
-    tick(ctx, 3);
-    CU(cudaStreamSynchronize(ctx->stream));          // sync 1: M, bounding box, Q_all
-    // The sorts used the previous frame's key width; if this frame needed more bits, redo with the full 32.
-    if (ctx->n_raw > 0 && ctx->h_info->map_vp.key_bits > ctx->vg_map.bits_used) {
-        ++ctx->sort_redos;
-        if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->raw.p, ctx->n_raw, map_leaf, true, ctx->map, 32))) return rc;
-        CU(cudaMemcpyAsync(&ctx->h_info->M, ctx->d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+    bool force32 = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // fork: scan branch (H2D + VoxelGrid) on stream2, corner branch on stream3, surf map branch on the main stream
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
+        if ((rc = scan_enqueue(ctx, 0, ctx->stream2, in->scan[0], in->n_scan[0], dev, in->scan_leaf[0], force32 ? 32 : fs.vg_scan.bits_hint))) return rc;
+        if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
+        CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
+        if (corner) {
+            CU(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
+            if ((rc = localmap_enqueue(ctx, 1, ctx->stream3, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[1], force32 ? 32 : fcn.vg_map.bits_hint, false))) return rc;
+            if ((rc = scan_enqueue(ctx, 1, ctx->stream3, in->scan[1], in->n_scan[1], dev, in->scan_leaf[1], force32 ? 32 : fcn.vg_scan.bits_hint))) return rc;
+            CU(cudaEventRecord(ctx->ev_join3, ctx->stream3));
+        }
+        if ((rc = localmap_enqueue(ctx, 0, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[0], force32 ? 32 : fs.vg_map.bits_hint, true))) return rc;   // ev 0..3
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
+        if (corner) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join3, 0));
+        tick(ctx, 4, ctx->stream);
+        if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
+        tick(ctx, 5, ctx->stream);
+        CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation
+        // The sorts used the previous frame's key width; if this frame needed more bits the whole frame is redone
+        // with full 32-bit keys (the registration state is double-buffered, so the first attempt left no trace).
+        bool redo = false;
+        for (int cls = 0; cls < (corner ? 2 : 1); ++cls) {
+            FeatClass& fc = ctx->fc[cls];
+            const HostClassInfo& hi = ctx->h_info->c[cls];
+            if (fc.n_raw > 0 && hi.map_vp.key_bits > fc.vg_map.bits_used) redo = true;
+            if (in->n_scan[cls] > 0 && hi.scan_vp.key_bits > fc.vg_scan.bits_used) redo = true;
+            if (fc.n_raw > 0) fc.vg_map.bits_hint = next_bits_hint(hi.map_vp.key_bits);
+            if (in->n_scan[cls] > 0) fc.vg_scan.bits_hint = next_bits_hint(hi.scan_vp.key_bits);
+        }
+        if (!redo) break;
+        if (attempt == 1) return fail(ctx, LILOC_ERR_CUDA, "frame: radix-sort key width still too small after a 32-bit redo");
+        ++ctx->sort_redos; --ctx->stats.s2m_launches;
+        force32 = true;
     }
-    if (n_scan > 0 && ctx->h_info->scan_vp.key_bits > ctx->vg_scan.bits_used) {
-        ++ctx->sort_redos;
-        if ((rc = vg_run(ctx, ctx->vg_scan, ctx->stream, ctx->scan_src_last, n_scan, scan_leaf, true, ctx->scan, 32))) return rc;
-        CU(cudaMemcpyAsync(&ctx->h_info->Q_all, ctx->d_Q, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    if (ctx->n_raw > 0) ctx->vg_map.bits_hint = next_bits_hint(ctx->h_info->map_vp.key_bits);
-    if (n_scan > 0) ctx->vg_scan.bits_hint = next_bits_hint(ctx->h_info->scan_vp.key_bits);
-    ctx->Q_all = ctx->h_info->Q_all;
-    if ((rc = localmap_finish(ctx))) return rc;
-    tick(ctx, 4);
-    if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
-    tick(ctx, 5);
-    CU(cudaStreamSynchronize(ctx->stream));          // sync 2: result
+    for (int cls = 0; cls < (corner ? 2 : 1); ++cls) class_collect(ctx, cls, true, true);
+    ctx->corner_scan_current = corner;
     if (ctx->timing) {
         liloc_timing& t = ctx->last_timing;
         cudaEventElapsedTime(&t.assemble_ms, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&t.map_voxel_ms, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&t.grid_ms, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&t.scan_ms, ctx->ev[6], ctx->ev[7]);
-        cudaEventElapsedTime(&t.grid_ms, ctx->ev[3], ctx->ev[4]);
         cudaEventElapsedTime(&t.s2m_ms, ctx->ev[4], ctx->ev[5]);
         cudaEventElapsedTime(&t.total_ms, ctx->ev[0], ctx->ev[5]);
         liloc_stats& st = ctx->stats;
@@ -697,11 +807,36 @@ int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K
         st.grid_ms += t.grid_ms; st.s2m_ms += t.s2m_ms; st.total_ms += t.total_ms;
     }
     ++ctx->stats.frames;
-    ctx->stats.alg_bytes_map += 16.0 * ctx->n_raw + 16.0 * (ctx->M > 0 ? ctx->M : 0);
-    ctx->stats.alg_bytes_scan += 16.0 * ctx->n_scan_last + 16.0 * (ctx->Q_all > 0 ? ctx->Q_all : 0);
-    return s2m_collect(ctx, pose6, res);
+    for (int cls = 0; cls < (corner ? 2 : 1); ++cls) {
+        const FeatClass& fc = ctx->fc[cls];
+        ctx->stats.alg_bytes_map += 16.0 * fc.n_raw + 16.0 * (fc.M > 0 ? fc.M : 0);
+        ctx->stats.alg_bytes_scan += 16.0 * fc.n_scan_last + 16.0 * (fc.Q_all > 0 ? fc.Q_all : 0);
+    }
+    return s2m_collect(ctx, pose6, res, o);
 }
 
+int liloc_frame(liloc_ctx* ctx, const int* kf_ids, const float* kf_poses6, int K, float map_leaf,
+                const liloc_point* scan, int n_scan, int scan_on_device, float scan_leaf,
+                float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
+    liloc_frame_in in{};
+    in.kf_ids = kf_ids; in.kf_poses6 = kf_poses6; in.K = K;
+    in.map_leaf[0] = map_leaf; in.scan[0] = scan; in.n_scan[0] = n_scan; in.scan_leaf[0] = scan_leaf;
+    in.scan_on_device = scan_on_device;
+    liloc_s2m_opts o = opts ? *opts : kDefaultOpts;
+    o.enable_corner = 0;                             // this entry point is the reference's surf-only frame
+    return liloc_frame_features(ctx, &in, pose6, &o, res);
+}
+
+int liloc_last_s2m_extra(liloc_ctx* ctx, liloc_s2m_extra* out) {
+    if (!ctx || !out) return LILOC_ERR_ARG;
+    std::memset(out, 0, sizeof(*out));
+    const S2mResult& r = ctx->h_info->res;
+    out->q_corner = r.extra[0]; out->map_points_corner = r.extra[1]; out->tiles_corner = r.extra[2]; out->tiles_surf = r.extra[3];
+    out->sort_redos = (int)ctx->sort_redos;
+    return LILOC_OK;
+}
+
+// ---- kernel-level entry points ------------------------------------------------------------------------
 int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, liloc_point* out, int cap, int* m_out) {
     ENTER(ctx);
     if (n < 0 || (n > 0 && (!in || !out)) || !(leaf > 0.f) || !m_out) return fail(ctx, LILOC_ERR_ARG, "voxelgrid: bad arguments");
@@ -711,10 +846,11 @@ int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, li
     if (n > 0) CU(cudaMemcpyAsync(ctx->tmp_pts.p, in, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = ensure(ctx, ctx->tmp_i, 1))) return rc;
     {   // run on the scan instance's scratch but keep its result count (d_Q) untouched
-        int* keep = ctx->vg_scan.d_count;
-        ctx->vg_scan.d_count = ctx->tmp_i.p;
-        rc = vg_run(ctx, ctx->vg_scan, ctx->stream, ctx->tmp_pts.p, n, leaf, false, outb, 32);
-        ctx->vg_scan.d_count = keep;
+        VgInst& vi = ctx->fc[0].vg_scan;
+        int* keep = vi.d_count;
+        vi.d_count = ctx->tmp_i.p;
+        rc = vg_run(ctx, vi, ctx->stream, ctx->tmp_pts.p, n, leaf, false, outb, 32);
+        vi.d_count = keep;
         if (rc) return rc;
     }
     int m = 0;
@@ -727,17 +863,18 @@ int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, li
     return LILOC_OK;
 }
 
-int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries, int nq, int* idx5, float* d2_5, int* found) {
+int liloc_knn5_class(liloc_ctx* ctx, int cls, const liloc_point* queries, int nq, int* idx5, float* d2_5, int* found) {
     ENTER(ctx);
-    if (nq < 0 || (nq > 0 && (!queries || !idx5 || !d2_5 || !found))) return fail(ctx, LILOC_ERR_ARG, "knn5: bad arguments");
-    if (!ctx->have_grid) return fail(ctx, LILOC_ERR_STATE, "knn5: no local map");
+    if (bad_class(cls) || nq < 0 || (nq > 0 && (!queries || !idx5 || !d2_5 || !found))) return fail(ctx, LILOC_ERR_ARG, "knn5: bad arguments");
+    FeatClass& fc = ctx->fc[cls];
+    if (!fc.have_map) return fail(ctx, LILOC_ERR_STATE, "knn5: no local map");
     if (nq == 0) return LILOC_OK;
     int rc;
     if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)nq))) return rc;
     if ((rc = ensure(ctx, ctx->tmp_i, (size_t)nq * 6))) return rc;
     if ((rc = ensure(ctx, ctx->tmp_f, (size_t)nq * 5))) return rc;
     CU(cudaMemcpyAsync(ctx->tmp_pts.p, queries, (size_t)nq * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    k_knn5<<<blocks_for(ctx, (long long)nq * kKnnLanes, 256), 256, 0, ctx->stream>>>(ctx->tmp_pts.p, nq, grid_view(ctx), ctx->tmp_i.p, ctx->tmp_f.p, ctx->tmp_i.p + (size_t)nq * 5); KCHECK();
+    k_knn5<<<blocks_for(ctx, (long long)nq * kKnnLanes, 256), 256, 0, ctx->stream>>>(ctx->tmp_pts.p, nq, grid_view(fc), ctx->tmp_i.p, ctx->tmp_f.p, ctx->tmp_i.p + (size_t)nq * 5); KCHECK();
     CU(cudaMemcpyAsync(idx5, ctx->tmp_i.p, (size_t)nq * 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(found, ctx->tmp_i.p + (size_t)nq * 5, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(d2_5, ctx->tmp_f.p, (size_t)nq * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -745,12 +882,17 @@ int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries, int nq, int* idx5, fl
     return LILOC_OK;
 }
 
-int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag) {
+int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries, int nq, int* idx5, float* d2_5, int* found) {
+    return liloc_knn5_class(ctx, LILOC_SURF, queries, nq, idx5, d2_5, found);
+}
+
+int liloc_feature_pass(liloc_ctx* ctx, int cls, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag) {
     ENTER(ctx);
-    if (!pose6 || stride < 1 || !coeff || !flag) return fail(ctx, LILOC_ERR_ARG, "surf_pass: bad arguments");
-    if (!ctx->have_grid) return fail(ctx, LILOC_ERR_STATE, "surf_pass: no local map");
-    if (!ctx->have_scan || ctx->Q_all < 0) return fail(ctx, LILOC_ERR_STATE, "surf_pass: no scan");
-    const int Q = ctx->Q_all;
+    if (bad_class(cls) || !pose6 || stride < 1 || !coeff || !flag) return fail(ctx, LILOC_ERR_ARG, "feature_pass: bad arguments");
+    FeatClass& fc = ctx->fc[cls];
+    if (!fc.have_map) return fail(ctx, LILOC_ERR_STATE, "feature_pass: no local map");
+    if (!fc.have_scan || fc.Q_all < 0) return fail(ctx, LILOC_ERR_STATE, "feature_pass: no scan");
+    const int Q = fc.Q_all;
     if (Q == 0) return LILOC_OK;
     int rc;
     if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)Q))) return rc;
@@ -760,14 +902,18 @@ int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point*
     CU(cudaMemsetAsync(ctx->tmp_b.p, 0, (size_t)Q, ctx->stream));
     CU(cudaMemcpyAsync(ctx->tmp_f.p, pose6, 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     S2mArgs a{};
-    a.scan = ctx->scan.p; a.q_all = ctx->d_Q; a.map = ctx->map.p; a.map_count = ctx->d_M;
-    a.grid = grid_view(ctx); a.stride = stride;
+    a.f[cls] = feat_view(fc, stride);
+    a.enable_corner = cls;
     const int nq = (Q + stride - 1) / stride;
-    k_surf_pass<<<blocks_for(ctx, nq, kQPB), kS2mThreads, 0, ctx->stream>>>(a, ctx->tmp_f.p, ctx->tmp_pts.p, ctx->tmp_b.p); KCHECK();
+    k_feature_pass<<<blocks_for(ctx, nq, kQPB), kS2mThreads, 0, ctx->stream>>>(a, cls, ctx->tmp_f.p, ctx->tmp_pts.p, ctx->tmp_b.p); KCHECK();
     CU(cudaMemcpyAsync(coeff, ctx->tmp_pts.p, (size_t)Q * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(flag, ctx->tmp_b.p, (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LILOC_OK;
+}
+
+int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag) {
+    return liloc_feature_pass(ctx, LILOC_SURF, pose6, stride, coeff, flag);
 }
 
 int liloc_pose_to_T(liloc_ctx* ctx, const float* pose6, float* T12) {
@@ -808,6 +954,36 @@ int liloc_debug_plane(liloc_ctx* ctx, const float* pts15, int n, float* x3) {
     CU(cudaMemcpyAsync(ctx->tmp_f.p, pts15, (size_t)n * 15 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     k_debug_plane<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->tmp_f.p, n, ctx->tmp_f.p + 15 * (size_t)n); KCHECK();
     CU(cudaMemcpyAsync(x3, ctx->tmp_f.p + 15 * (size_t)n, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LILOC_OK;
+}
+
+int liloc_debug_eigen3(liloc_ctx* ctx, const float* A9, int n, float* w3, float* V9) {
+    ENTER(ctx);
+    if (n <= 0 || !A9 || !w3 || !V9) return fail(ctx, LILOC_ERR_ARG, "debug_eigen3: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_f, (size_t)n * 21))) return rc;
+    float* dA = ctx->tmp_f.p; float* dw = dA + 9 * (size_t)n; float* dV = dw + 3 * (size_t)n;
+    CU(cudaMemcpyAsync(dA, A9, (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_debug_eigen3<<<(n + 63) / 64, 64, 0, ctx->stream>>>(dA, n, dw, dV); KCHECK();
+    CU(cudaMemcpyAsync(w3, dw, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(V9, dV, (size_t)n * 9 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LILOC_OK;
+}
+
+int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int n, liloc_point* coeff, int* keep) {
+    ENTER(ctx);
+    if (n <= 0 || !pts15 || !sel3 || !coeff || !keep) return fail(ctx, LILOC_ERR_ARG, "debug_line: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_f, (size_t)n * 18))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_i, (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_f.p, pts15, (size_t)n * 15 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->tmp_f.p + 15 * (size_t)n, sel3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_debug_line<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->tmp_f.p, ctx->tmp_f.p + 15 * (size_t)n, n, ctx->tmp_pts.p, ctx->tmp_i.p); KCHECK();
+    CU(cudaMemcpyAsync(coeff, ctx->tmp_pts.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(keep, ctx->tmp_i.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LILOC_OK;
 }
@@ -862,9 +1038,9 @@ int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, 
     if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n))) return rc;
     CU(cudaMemcpyAsync(ctx->tmp_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     DevBuf<float4> none;
-    if ((rc = vg_run(ctx, ctx->vg_map, ctx->stream, ctx->tmp_pts.p, n, resolution, false, none, 32, true))) return rc;
+    if ((rc = vg_run(ctx, ctx->fc[0].vg_map, ctx->stream, ctx->tmp_pts.p, n, resolution, false, none, 32, true))) return rc;
     VgParams vp;
-    CU(cudaMemcpyAsync(&vp, ctx->vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&vp, ctx->fc[0].vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (vp.overflow) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_target_put: leaf size too small for the target extent (PCL overflow guard)");
     liloc_ctx::NdtTargetHost& T = ctx->ndt_targets[target_id];
@@ -877,7 +1053,7 @@ int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, 
     if ((rc = ensure(ctx, T.leaves, (size_t)(n / 6 + 1)))) return rc;
     k_fill_int<<<blocks_for(ctx, ncell, 256 * 4), 256, 0, ctx->stream>>>(T.table.p, ncell, -1); KCHECK();
     CU(cudaMemsetAsync(ctx->d_ndt_active, 0, sizeof(int), ctx->stream));
-    k_ndt_leaves<<<blocks_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->vg_map.keys_b.p, ctx->vg_map.vals_b.p, n, ctx->tmp_pts.p, T.leaves.p, T.table.p, ctx->d_ndt_active); KCHECK();
+    k_ndt_leaves<<<blocks_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->fc[0].vg_map.keys_b.p, ctx->fc[0].vg_map.vals_b.p, n, ctx->tmp_pts.p, T.leaves.p, T.table.p, ctx->d_ndt_active); KCHECK();
     int nl = 0;
     CU(cudaMemcpyAsync(&nl, ctx->d_ndt_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -947,7 +1123,7 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
     // worst case per align pass: first sweep + (max_iterations + 2) x (1 + 10) line-search sweeps
     const int max_sweeps = od.n_align * (1 + (od.max_iterations + 2) * 11);
     const int check_every = 4;
-    int* h_active = &ctx->h_info->Q_all;                   // pinned scratch int
+    int* h_active = &ctx->h_info->scratch;                   // pinned scratch int
     int done_sweeps = 0;
     while (done_sweeps < max_sweeps) {
         for (int k = 0; k < check_every; ++k) {

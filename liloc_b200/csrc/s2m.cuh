@@ -16,6 +16,10 @@
 //      solve of the 6x6, (iteration 0) Jacobi eigen-decomposition + degeneracy projector, pose update,
 //      convergence test.  Redundant evaluation is bit-identical in every block, so no second barrier.
 // No intermediate (point, coefficient) array ever reaches HBM.
+//
+// Two feature classes share the loop: class 0 = surf, the reference's only class (plane residuals); class 1 =
+// corner, the upstream LIO-SAM cornerOptimization the north_star names but the reference dropped (line
+// residuals).  Corner tiles run first, then surf tiles (combineOptimizationCoeffs order).
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"
@@ -41,20 +45,28 @@ struct S2mResult {                       // device mirror of liloc_s2m_result (s
     float matP[36];
     float AtA0[36];
     float pose[6];
+    int extra[8];                        // q_corner, map_points_corner, tiles_corner, tiles_surf, 0...
     float trace[32][16];                 // per iteration: n_sel, X[6], pose_after[6], AtB[0..2]
     int clk[32][8];                      // LILOC_S2M_PROFILE: SM-clock deltas of the iteration phases (block 0)
 };
 
-struct S2mArgs {
+struct FeatView {                        // one feature class
     const float4* scan;                  // down-sampled scan, body frame
     const int* q_all;                    // device count
     const float4* map;                   // down-sampled local map, original (voxel) order
     const int* map_count;
     GridView grid;
-    int stride, max_iters, min_sel, min_points;
+    int stride;
+};
+
+struct S2mArgs {
+    FeatView f[2];                       // 0 surf, 1 corner
+    int enable_corner;
+    int max_iters, min_sel, min_points, min_corner;
     double* partial;                     // [2][gridDim.x][kNSums]
     float* pose_io;                      // 6 floats: in = initial guess, out = result
-    S2mState* state;
+    const S2mState* state;               // members isDegenerate / matP before this call ...
+    S2mState* state_out;                 // ... and after it (double-buffered by the host, see liloc_frame_features)
     S2mResult* result;
 };
 
@@ -196,6 +208,111 @@ LILOC_DEV bool surf_residual(const float (&nb)[5][3], const float d2_4, const fl
     const float rng = sqrtf(sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z));
     const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / (double)rng);
     *coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+    return (double)s > 0.1;
+}
+
+// cv::eigen(sym 3x3) stand-in for cornerOptimization: the same cyclic Jacobi as eigen6_jacobi below (float32,
+// eigenvalues descending, eigenvectors as rows), indices compile-time so everything stays in registers.
+template <int P, int Q>
+__host__ __device__ __forceinline__ void jacobi_rotate3(float (&A)[3][3], float (&U)[3][3]) {
+    const float apq = A[P][Q];
+    if (apq == 0.f) return;
+    const float theta = (A[Q][Q] - A[P][P]) / (2.0f * apq);
+    const float t = (theta >= 0.f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+    const float c = 1.0f / sqrtf(t * t + 1.0f);
+    const float s = t * c;
+    const float h = t * apq;
+    A[P][P] -= h; A[Q][Q] += h; A[P][Q] = 0.f; A[Q][P] = 0.f;
+    constexpr int K = 3 - P - Q;         // the one remaining index
+    {
+        const float akp = A[K][P], akq = A[K][Q];
+        const float np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+        A[K][P] = np_; A[P][K] = np_; A[K][Q] = nq_; A[Q][K] = nq_;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float upk = U[P][k], uqk = U[Q][k];
+        U[P][k] = c * upk - s * uqk; U[Q][k] = s * upk + c * uqk;
+    }
+}
+
+__host__ __device__ inline void eigen3_jacobi(const float* A_in, float* w, float* V) {
+    float A[3][3], U[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { A[i][j] = A_in[i * 3 + j]; U[i][j] = (i == j) ? 1.f : 0.f; }
+    const float eps = 1.1920929e-07f;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        float off = 0.f, diag = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            diag += A[i][i] * A[i][i];
+#pragma unroll
+            for (int j = i + 1; j < 3; ++j) off += A[i][j] * A[i][j];
+        }
+        if (off <= (eps * eps) * diag || off == 0.f) break;
+        jacobi_rotate3<0, 1>(A, U); jacobi_rotate3<0, 2>(A, U); jacobi_rotate3<1, 2>(A, U);
+    }
+    float d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[i] = A[i][i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r += (d[j] > d[i] || (d[j] == d[i] && j < i)) ? 1 : 0;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            if (r == o) {
+                w[o] = d[i];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) V[o * 3 + k] = U[i][k];
+            }
+        }
+    }
+}
+
+// Loop body of upstream LIO-SAM cornerOptimization after the kNN (the reference has no
+// corner path).  Same operation sequence and type promotions as the oracle's corner_residual.
+LILOC_DEV bool corner_residual(const float (&nb)[5][3], const float d2_4, const float4 sel, float4* coeff) {
+    if (!(d2_4 < 1.0f)) return false;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { cx += nb[j][0]; cy += nb[j][1]; cz += nb[j][2]; }
+    cx /= 5.f; cy /= 5.f; cz /= 5.f;
+    float a11 = 0.f, a12 = 0.f, a13 = 0.f, a22 = 0.f, a23 = 0.f, a33 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float ax = nb[j][0] - cx, ay = nb[j][1] - cy, az = nb[j][2] - cz;
+        a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+        a22 += ay * ay; a23 += ay * az;
+        a33 += az * az;
+    }
+    a11 /= 5.f; a12 /= 5.f; a13 /= 5.f; a22 /= 5.f; a23 /= 5.f; a33 /= 5.f;
+    const float A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+    float w[3], V[9];
+    eigen3_jacobi(A, w, V);
+    if (!(w[0] > 3.f * w[1])) return false;
+    const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+    const float x1 = (float)((double)cx + 0.1 * (double)V[0]);
+    const float y1 = (float)((double)cy + 0.1 * (double)V[1]);
+    const float z1 = (float)((double)cz + 0.1 * (double)V[2]);
+    const float x2 = (float)((double)cx - 0.1 * (double)V[0]);
+    const float y2 = (float)((double)cy - 0.1 * (double)V[1]);
+    const float z2 = (float)((double)cz - 0.1 * (double)V[2]);
+    const float m11 = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+    const float m12 = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+    const float m13 = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+    const float a012 = sqrtf(m11 * m11 + m12 * m12 + m13 * m13);
+    const float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    const float la = ((y1 - y2) * m11 + (z1 - z2) * m12) / a012 / l12;
+    const float lb = -((x1 - x2) * m11 - (z1 - z2) * m13) / a012 / l12;
+    const float lc = -((x1 - x2) * m12 + (y1 - y2) * m13) / a012 / l12;
+    const float ld2 = a012 / l12;
+    const float s = (float)(1 - 0.9 * (double)fabsf(ld2));
+    *coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
     return (double)s > 0.1;
 }
 
@@ -401,6 +518,8 @@ __constant__ unsigned char c_sum_a[kNSums] = {0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3
 __constant__ unsigned char c_sum_c[kNSums] = {0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5, 6,6,6,6,6,6, 7};
 
 struct S2mShared {
+    FeatView fv[2];
+    GridParams gp[2];
     float T[12];
     float pose[6];
     float sc[6];
@@ -416,20 +535,21 @@ struct S2mShared {
     int n_sel;
 };
 
-// Residual rows for one tile of queries into shared memory (phases A and B).  A group of kKnnLanes lanes
-// owns one query: cooperative kNN, then lane 0 of the group does the plane fit and the Jacobian row.
-// Returns through coeff_out/flag_out as well when they are non-null (k_surf_pass).
-LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, const int nq,
+// Residual rows for one tile of queries of class `cls` into shared memory (phases A and B).  A group of
+// kKnnLanes lanes owns one query: cooperative kNN, then lane 0 of the group does the fit and the Jacobian row.
+// Returns through coeff_out/flag_out as well when they are non-null (k_feature_pass).
+LILOC_DEV void s2m_tile_rows(S2mShared& sh, const int cls, const int tile, const int nq,
                              float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
+    const FeatView& f = sh.fv[cls];
     const int s = threadIdx.x / kKnnLanes, sub = threadIdx.x % kKnnLanes;
     const int qk = tile * kQPB + s;
     const bool active = qk < nq;
     float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
-    if (active) { ori = __ldg(&a.scan[qk * a.stride]); sel = apply_T(sh.T, ori); }
+    if (active) { ori = __ldg(&f.scan[qk * f.stride]); sel = apply_T(sh.T, ori); }
 #ifdef LILOC_S2M_PROFILE
     if (threadIdx.x == 0) sh.dbg[0] = clock64();
 #endif
-    const Knn5 r = knn5_group<kKnnLanes>(a.grid, sel, sub, active);
+    const Knn5 r = knn5_group<kKnnLanes>(f.grid, sh.gp[cls], sel, sub, active);
 #ifdef LILOC_S2M_PROFILE
     if (threadIdx.x == 0) sh.dbg[1] = clock64();
 #endif
@@ -441,11 +561,12 @@ LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, co
             float nb[5][3];
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                const float4 p = __ldg(&a.map[r.i[j]]);
+                const float4 p = __ldg(&f.map[r.i[j]]);
                 nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
             }
             float4 c;
-            if (surf_residual(nb, r.d[4], ori, sel, &c)) { coeff = c; jacobian_row(sh.trig, ori, c, row); valid = 1.f; }
+            const bool keep = cls ? corner_residual(nb, r.d[4], sel, &c) : surf_residual(nb, r.d[4], ori, sel, &c);
+            if (keep) { coeff = c; jacobian_row(sh.trig, ori, c, row); valid = 1.f; }
         }
         if (valid == 0.f) {
 #pragma unroll
@@ -454,7 +575,7 @@ LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, co
 #pragma unroll
         for (int j = 0; j < 7; ++j) sh.row[s][j] = row[j];
         sh.row[s][7] = valid;
-        if (coeff_out && active) { coeff_out[qk * a.stride] = coeff; flag_out[qk * a.stride] = valid != 0.f ? 1 : 0; }
+        if (coeff_out && active) { coeff_out[qk * f.stride] = coeff; flag_out[qk * f.stride] = valid != 0.f ? 1 : 0; }
     }
 #ifdef LILOC_S2M_PROFILE
     if (threadIdx.x == 0) sh.dbg[2] = clock64();
@@ -463,6 +584,15 @@ LILOC_DEV void s2m_tile_rows(const S2mArgs& a, S2mShared& sh, const int tile, co
 #ifdef LILOC_S2M_PROFILE
     if (threadIdx.x == 0) sh.dbg[3] = clock64();
 #endif
+}
+
+// Stage the class views and the device-resident grid geometry in shared memory (once per kernel).
+LILOC_DEV void s2m_stage_views(const S2mArgs& a, S2mShared& sh) {
+    if (threadIdx.x == 0) {
+        sh.fv[0] = a.f[0]; sh.fv[1] = a.f[1];
+        sh.gp[0] = *a.f[0].grid.p;
+        if (a.enable_corner) sh.gp[1] = *a.f[1].grid.p;
+    }
 }
 
 // sin/cos of the three angles on six lanes in parallel, then T and the trig set by one thread.
@@ -486,18 +616,23 @@ LILOC_DEV void s2m_refresh_transform(S2mShared& sh) {
 __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S2mArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ S2mShared sh;
-    const int q_all = *a.q_all;
-    const int M = *a.map_count;
-    const int nq = (q_all + a.stride - 1) / a.stride;
-    const int n_tiles = (nq + kQPB - 1) / kQPB;
+    const int q_all = *a.f[0].q_all;
+    const int M = *a.f[0].map_count;
+    const int nq = (q_all + a.f[0].stride - 1) / a.f[0].stride;
+    const int q_corner = a.enable_corner ? *a.f[1].q_all : 0;
+    const int nq_c = a.enable_corner ? (q_corner + a.f[1].stride - 1) / a.f[1].stride : 0;
+    const int n_tiles_c = (nq_c + kQPB - 1) / kQPB;
+    const int n_tiles = n_tiles_c + (nq + kQPB - 1) / kQPB;
 
+    s2m_stage_views(a, sh);
     if (threadIdx.x < 6) sh.pose[threadIdx.x] = a.pose_io[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 68) sh.matP[threadIdx.x - 32] = a.state->matP[threadIdx.x - 32];
     if (threadIdx.x == 0) { sh.is_degenerate = a.state->is_degenerate; sh.done = 0; sh.n_sel = 0; }
     __syncthreads();
     s2m_refresh_transform(sh);
 
-    const bool skipped = !(q_all > a.min_points);             // :1187
+    // :1187; with corners the upstream gate (cornerDS > edgeFeatureMinValidNum && surfDS > surfFeatureMinValidNum)
+    const bool skipped = !(q_all > a.min_points) || (a.enable_corner && !(q_corner > a.min_corner));
     int iters = 0, converged = 0, too_few = 0;
 #ifdef LILOC_S2M_PROFILE
     long long clk[8];
@@ -510,7 +645,8 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
             S2M_CLK(0)
             double acc = 0.0;                               // threads < kNSums: running sum over this block's tiles
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                s2m_tile_rows(a, sh, tile, nq, nullptr, nullptr);
+                const int cls = tile < n_tiles_c ? 1 : 0;      // corner tiles first (combineOptimizationCoeffs order)
+                s2m_tile_rows(sh, cls, cls ? tile : tile - n_tiles_c, cls ? nq_c : nq, nullptr, nullptr);
                 if (threadIdx.x < kNSums) {                 // C
                     const int ia = c_sum_a[threadIdx.x], ic = c_sum_c[threadIdx.x];
 #pragma unroll 8
@@ -631,26 +767,30 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
         S2mResult* r = a.result;
         r->iters = iters; r->converged = converged; r->n_sel = sh.n_sel; r->is_degenerate = sh.is_degenerate;
         r->too_few = too_few; r->skipped = skipped ? 1 : 0; r->q_all = q_all; r->map_points = M;
+        r->extra[0] = q_corner; r->extra[1] = a.enable_corner ? *a.f[1].map_count : 0;
+        r->extra[2] = n_tiles_c; r->extra[3] = n_tiles - n_tiles_c;
         for (int i = 0; i < 36; ++i) r->matP[i] = sh.matP[i];
         for (int i = 0; i < 6; ++i) { r->pose[i] = sh.pose[i]; a.pose_io[i] = sh.pose[i]; }
-        a.state->is_degenerate = sh.is_degenerate;
-        for (int i = 0; i < 36; ++i) a.state->matP[i] = sh.matP[i];
+        a.state_out->is_degenerate = sh.is_degenerate;
+        for (int i = 0; i < 36; ++i) a.state_out->matP[i] = sh.matP[i];
     }
 }
 
-// surfOptimization at a fixed pose for the residual-level parity test (liloc_surf_pass): the same tile
-// function as the registration kernel, with the coefficients written out instead of reduced.
+// surfOptimization / cornerOptimization at a fixed pose for the residual-level parity tests (liloc_surf_pass,
+// liloc_feature_pass): the same tile function as the registration kernel, with the coefficients written out
+// instead of reduced.
 __global__ void __launch_bounds__(kS2mThreads)
-k_surf_pass(S2mArgs a, const float* __restrict__ pose6, float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
+k_feature_pass(S2mArgs a, int cls, const float* __restrict__ pose6, float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
     __shared__ S2mShared sh;
-    const int q_all = *a.q_all;
-    const int nq = (q_all + a.stride - 1) / a.stride;
-    const int n_tiles = (nq + kQPB - 1) / kQPB;
+    if (threadIdx.x == 0) { sh.fv[cls] = a.f[cls]; sh.gp[cls] = *a.f[cls].grid.p; }
     if (threadIdx.x < 6) sh.pose[threadIdx.x] = pose6[threadIdx.x];
     __syncthreads();
+    const int q_all = *sh.fv[cls].q_all;
+    const int nq = (q_all + sh.fv[cls].stride - 1) / sh.fv[cls].stride;
+    const int n_tiles = (nq + kQPB - 1) / kQPB;
     s2m_refresh_transform(sh);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        s2m_tile_rows(a, sh, tile, nq, coeff_out, flag_out);
+        s2m_tile_rows(sh, cls, tile, nq, coeff_out, flag_out);
         __syncthreads();
     }
 }

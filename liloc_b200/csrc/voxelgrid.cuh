@@ -194,8 +194,7 @@ k_run_count(const unsigned* __restrict__ skeys, int n, int* __restrict__ tile_co
 }
 
 // exclusive scan of the tile counts by one block; total -> *total_out
-__global__ void __launch_bounds__(1024)
-k_scan_tiles(int* __restrict__ tile_counts, int n_tiles, int* __restrict__ total_out) {
+LILOC_DEV void scan_tiles_body(int* __restrict__ tile_counts, int n_tiles, int* __restrict__ total_out) {
     __shared__ int s_w[32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -218,6 +217,10 @@ k_scan_tiles(int* __restrict__ tile_counts, int n_tiles, int* __restrict__ total
         __syncthreads();
     }
     if (threadIdx.x == 0) *total_out = s_carry;
+}
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(int* __restrict__ tile_counts, int n_tiles, int* __restrict__ total_out) {
+    scan_tiles_body(tile_counts, n_tiles, total_out);
 }
 
 // One centroid per run, written at the run's rank (ascending voxel index).  The tile's points are

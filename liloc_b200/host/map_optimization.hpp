@@ -87,7 +87,7 @@ public:
 
     Affine3f trans2Affine3f(const float t[6]) { return getTransformation(t[3], t[4], t[5], t[0], t[1], t[2]); }   // :404-406
 
-    liloc_s2m_opts s2m_opts{20, 2, 50, 30, {0, 0, 0, 0}};
+    liloc_s2m_opts s2m_opts{20, 2, 50, 30, 0, 10, 1, {0}};
     const std::vector<int>& lastSelection() const { return sel_ids_; }
 
 private:

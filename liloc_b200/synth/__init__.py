@@ -117,6 +117,25 @@ def scan(world: np.ndarray, pose6, sensor: Sensor, seed: int) -> np.ndarray:
     return out[:n].copy()
 
 
+def split_features(world: np.ndarray, pose6, scan_body: np.ndarray, tol: float = 0.12):
+    """Split a body-frame scan into (corner, surf) feature clouds the way an upstream LIO-SAM front end would
+    hand them to mapOptimization: a return is a *corner* feature when it lies within `tol` of a vertical edge
+    of the world (room corners, pillar edges), everything else is a *surf* feature.  (The reference has no
+    feature extraction -- SURVEY.md 0.2 D2 -- so this exists only for the north_star's corner superset.)"""
+    p = np.asarray(pose6, np.float64)
+    R = rot_zyx(p[0], p[1], p[2])
+    w = scan_body[:, :3].astype(np.float64) @ R.T + p[3:6]
+    best = np.full(len(w), np.inf)
+    for b in np.asarray(world, np.float64):
+        for ex in (b[0], b[3]):
+            for ey in (b[1], b[4]):
+                d = np.hypot(w[:, 0] - ex, w[:, 1] - ey)
+                d = np.where((w[:, 2] >= b[2] - tol) & (w[:, 2] <= b[5] + tol), d, np.inf)
+                best = np.minimum(best, d)
+    is_corner = best < tol
+    return np.ascontiguousarray(scan_body[is_corner]), np.ascontiguousarray(scan_body[~is_corner])
+
+
 def perturb(pose6, seed: int, dt=0.10, dr=0.02) -> np.ndarray:
     """Initial guess = ground truth + U(+-dt m, +-dr rad) per axis."""
     rng = np.random.default_rng(seed)

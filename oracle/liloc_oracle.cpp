@@ -501,6 +501,99 @@ int lm_step(const orc_point* ori, const orc_point* coef, int n_sel, int iter, in
     return ((double)deltaR < 0.05 && (double)deltaT < 0.05) ? 1 : 0;   // :1177
 }
 
+// ---------------------------------------------------------------------------------------------
+// Upstream LIO-SAM corner path.  NOT in the reference (it dropped feature extraction and
+// cornerOptimization; remnants: laserCloudCornerTemp src/mapOptmization.cpp:947,950 and the unused
+// msg/cloud_info.msg:28 field); the north_star names it, so it is restated from upstream LIO-SAM
+// (TixiaoShan/LIO-SAM mapOptmization.cpp cornerOptimization) as an optional
+// superset.  Parity for this class is GPU-vs-this-file only.
+
+// cv::eigen(sym 3x3): same cyclic Jacobi as eigen6_jacobi, eigenvalues descending, eigenvectors as rows.
+void eigen3_jacobi(const float A_in[9], float w[3], float V[9]) {
+    float A[3][3], U[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = A_in[i * 3 + j]; U[i][j] = (i == j) ? 1.f : 0.f; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        float off = 0.f, diag = 0.f;
+        for (int i = 0; i < 3; ++i) { diag += A[i][i] * A[i][i]; for (int j = i + 1; j < 3; ++j) off += A[i][j] * A[i][j]; }
+        if (off <= (FLT_EPSILON * FLT_EPSILON) * diag || off == 0.f) break;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            const float apq = A[p][q];
+            if (apq == 0.f) continue;
+            const float theta = (A[q][q] - A[p][p]) / (2.0f * apq);
+            const float t = (theta >= 0.f ? 1.0f : -1.0f) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0f));
+            const float c = 1.0f / std::sqrt(t * t + 1.0f);
+            const float s = t * c;
+            const float h = t * apq;
+            A[p][p] -= h; A[q][q] += h; A[p][q] = 0.f; A[q][p] = 0.f;
+            for (int k = 0; k < 3; ++k) {
+                if (k == p || k == q) continue;
+                const float akp = A[k][p], akq = A[k][q];
+                const float np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+                A[k][p] = np_; A[p][k] = np_; A[k][q] = nq_; A[q][k] = nq_;
+            }
+            for (int k = 0; k < 3; ++k) {
+                const float upk = U[p][k], uqk = U[q][k];
+                U[p][k] = c * upk - s * uqk; U[q][k] = s * upk + c * uqk;
+            }
+        }
+    }
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 2; ++i) {                         // selection sort, descending, stable on ties
+        int m = i;
+        for (int j = i + 1; j < 3; ++j) if (A[ord[j]][ord[j]] > A[ord[m]][ord[m]]) m = j;
+        const int t = ord[m]; for (int j = m; j > i; --j) ord[j] = ord[j - 1]; ord[i] = t;
+    }
+    for (int i = 0; i < 3; ++i) { w[i] = A[ord[i]][ord[i]]; for (int k = 0; k < 3; ++k) V[i * 3 + k] = U[ord[i]][k]; }
+}
+
+// Loop body of upstream cornerOptimization after the kNN: centroid and covariance of the 5 neighbours,
+// line test (largest eigenvalue > 3 x second), point-to-line distance and weight.  Type promotions as
+// upstream: `0.1 * v` and `1 - 0.9 * fabs(ld2)` are double expressions narrowed to float.
+bool line_residual(const float P[5][3], const orc_point& sel, orc_point* coeff) {
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int j = 0; j < 5; ++j) { cx += P[j][0]; cy += P[j][1]; cz += P[j][2]; }
+    cx /= 5.f; cy /= 5.f; cz /= 5.f;
+    float a11 = 0.f, a12 = 0.f, a13 = 0.f, a22 = 0.f, a23 = 0.f, a33 = 0.f;
+    for (int j = 0; j < 5; ++j) {
+        const float ax = P[j][0] - cx, ay = P[j][1] - cy, az = P[j][2] - cz;
+        a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+        a22 += ay * ay; a23 += ay * az;
+        a33 += az * az;
+    }
+    a11 /= 5.f; a12 /= 5.f; a13 /= 5.f; a22 /= 5.f; a23 /= 5.f; a33 /= 5.f;
+    const float A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+    float w[3], V[9];
+    eigen3_jacobi(A, w, V);
+    if (!(w[0] > 3.f * w[1])) return false;
+    const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+    const float x1 = (float)((double)cx + 0.1 * (double)V[0]);
+    const float y1 = (float)((double)cy + 0.1 * (double)V[1]);
+    const float z1 = (float)((double)cz + 0.1 * (double)V[2]);
+    const float x2 = (float)((double)cx - 0.1 * (double)V[0]);
+    const float y2 = (float)((double)cy - 0.1 * (double)V[1]);
+    const float z2 = (float)((double)cz - 0.1 * (double)V[2]);
+    const float m11 = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+    const float m12 = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+    const float m13 = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+    const float a012 = std::sqrt(m11 * m11 + m12 * m12 + m13 * m13);
+    const float l12 = std::sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    const float la = ((y1 - y2) * m11 + (z1 - z2) * m12) / a012 / l12;
+    const float lb = -((x1 - x2) * m11 - (z1 - z2) * m13) / a012 / l12;
+    const float lc = -((x1 - x2) * m12 + (y1 - y2) * m13) / a012 / l12;
+    const float ld2 = a012 / l12;
+    const float s = (float)(1 - 0.9 * (double)std::fabs(ld2));
+    coeff->x = s * la; coeff->y = s * lb; coeff->z = s * lc; coeff->w = s * ld2;
+    return (double)s > 0.1;
+}
+
+bool corner_residual(const orc_point* map, const int* idx5, const float* d2, const orc_point& sel, orc_point* coeff) {
+    if (idx5[4] < 0) return false;
+    if (!(d2[4] < 1.0f)) return false;
+    float P[5][3];
+    for (int j = 0; j < 5; ++j) { P[j][0] = map[idx5[j]].x; P[j][1] = map[idx5[j]].y; P[j][2] = map[idx5[j]].z; }
+    return line_residual(P, sel, coeff);
+}
+
 double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -666,6 +759,88 @@ int orc_frame(const orc_point* kf_points, const int64_t* kf_offsets, const float
     if (Q_out) *Q_out = Q_all;
     if (ms_out) { ms_out[0] = t1 - t0; ms_out[1] = t2 - t1; ms_out[2] = t3 - t2; ms_out[3] = t3 - t0; }
     return rc;
+}
+
+// ---- upstream LIO-SAM corner + surf superset (not in the reference; see the corner section above) -------
+void orc_eigen3(const float* A9, float* w3, float* V9) { eigen3_jacobi(A9, w3, V9); }
+
+int orc_line_residual(const float* pts15, const float* sel3, orc_point* coeff) {
+    float P[5][3];
+    for (int i = 0; i < 5; ++i) for (int j = 0; j < 3; ++j) P[i][j] = pts15[i * 3 + j];
+    orc_point sel{sel3[0], sel3[1], sel3[2], 0.f};
+    coeff->x = coeff->y = coeff->z = coeff->w = 0.f;
+    return line_residual(P, sel, coeff) ? 1 : 0;
+}
+
+// One pass of cornerOptimization at a fixed pose; same output convention as orc_surf_pass.
+int orc_corner_pass(const orc_point* map, int M, const orc_point* scan, int Q_all, int stride,
+                    const float* pose6, int knn, int threads, orc_point* ori_out, orc_point* coef_out, int* sel_index) {
+    float T[12]; pose_to_T(pose6, T);
+    KdTree tree; if (knn == 1) tree.build(map, M);
+    std::vector<uint8_t> flag((size_t)Q_all, 0);
+    std::vector<orc_point> coef((size_t)Q_all);
+    const int nq = (Q_all + stride - 1) / stride;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+    for (int k = 0; k < nq; ++k) {
+        const int i = k * stride;
+        const orc_point sel = apply_T(T, scan[i]);
+        int idx[5]; float d2[5];
+        if (knn == 1) tree.knn5(sel, idx, d2); else knn5_brute_one(map, M, sel, idx, d2);
+        orc_point c;
+        if (corner_residual(map, idx, d2, sel, &c)) { coef[i] = c; flag[i] = 1; }
+    }
+    int n = 0;
+    for (int i = 0; i < Q_all; ++i) if (flag[i]) { ori_out[n] = scan[i]; coef_out[n] = coef[i]; if (sel_index) sel_index[n] = i; ++n; }
+    return n;
+}
+
+// Upstream scan2MapOptimization: gate cornerDS > min_corner && surfDS > min_points; per iteration
+// cornerOptimization, surfOptimization, combineOptimizationCoeffs (corners first), LMOptimization.
+// o->stride applies to the surf loop (upstream 1), stride_corner to the corner loop (upstream 1).
+int orc_scan2map_features(const orc_point* map_s, int Ms, const orc_point* scan_s, int Qs,
+                          const orc_point* map_c, int Mc, const orc_point* scan_c, int Qc,
+                          int min_corner, int stride_corner, float* pose6,
+                          const orc_s2m_opts* o, orc_lm_state* st, orc_s2m_result* res) {
+    std::memset(res, 0, sizeof(*res));
+    if (!(Qc > min_corner && Qs > o->min_points)) { res->skipped = 1; return 1; }
+    KdTree tree_s, tree_c;
+    if (o->knn == 1) { tree_c.build(map_c, Mc); tree_s.build(map_s, Ms); }
+    std::vector<uint8_t> flag_s((size_t)Qs, 0), flag_c((size_t)Qc, 0);
+    std::vector<orc_point> coef_s((size_t)Qs), coef_c((size_t)Qc), ori, coef;
+    const int ss = o->stride > 0 ? o->stride : 1, sc = stride_corner > 0 ? stride_corner : 1;
+    const int nqs = (Qs + ss - 1) / ss, nqc = (Qc + sc - 1) / sc;
+    const int threads = o->threads > 0 ? o->threads : 1;
+    for (int iter = 0; iter < o->max_iters; ++iter) {
+        ori.clear(); coef.clear();
+        float T[12]; pose_to_T(pose6, T);
+#pragma omp parallel for num_threads(threads) schedule(static)
+        for (int k = 0; k < nqc; ++k) {
+            const int i = k * sc;
+            const orc_point sel = apply_T(T, scan_c[i]);
+            int idx[5]; float d2[5];
+            if (o->knn == 1) tree_c.knn5(sel, idx, d2); else knn5_brute_one(map_c, Mc, sel, idx, d2);
+            orc_point c;
+            if (corner_residual(map_c, idx, d2, sel, &c)) { coef_c[i] = c; flag_c[i] = 1; }
+        }
+#pragma omp parallel for num_threads(threads) schedule(static)
+        for (int k = 0; k < nqs; ++k) {
+            const int i = k * ss;
+            const orc_point sel = apply_T(T, scan_s[i]);
+            int idx[5]; float d2[5];
+            if (o->knn == 1) tree_s.knn5(sel, idx, d2); else knn5_brute_one(map_s, Ms, sel, idx, d2);
+            orc_point c;
+            if (surf_residual(map_s, idx, d2, scan_s[i], sel, &c)) { coef_s[i] = c; flag_s[i] = 1; }
+        }
+        for (int i = 0; i < Qc; ++i) if (flag_c[i]) { ori.push_back(scan_c[i]); coef.push_back(coef_c[i]); flag_c[i] = 0; }
+        for (int i = 0; i < Qs; ++i) if (flag_s[i]) { ori.push_back(scan_s[i]); coef.push_back(coef_s[i]); flag_s[i] = 0; }
+        res->iters = iter + 1;
+        res->n_sel = (int)ori.size();
+        const int r = lm_step(ori.data(), coef.data(), (int)ori.size(), iter, o->min_sel, pose6, st, nullptr, nullptr);
+        if (r == 1) { res->converged = 1; break; }
+        if (r == -1) { res->too_few = 1; break; }
+    }
+    res->is_degenerate = st->is_degenerate;
+    return 0;
 }
 
 }  // extern "C"

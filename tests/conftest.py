@@ -13,7 +13,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     # native pieces are built in-tree; (re)build what is stale so a fresh checkout can run the CPU suite
-    from liloc_b200 import _build
+    # (the recipe is loaded by path: importing the package dlopens libliloc_gpu.so, which may be stale or missing)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("liloc_b200_build", os.path.join(ROOT, "liloc_b200", "_build.py"))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
     _build.build_all()
 
 

@@ -61,6 +61,14 @@ def _load():
     L.orc_frame.restype = C.c_int
     L.orc_frame.argtypes = [P, P, P, C.c_int, C.c_float, P, C.c_int, C.c_float, P, C.POINTER(S2mOpts),
                             C.POINTER(LmState), C.POINTER(S2mResult), P, P, P]
+    L.orc_eigen3.argtypes = [P, P, P]
+    L.orc_line_residual.restype = C.c_int
+    L.orc_line_residual.argtypes = [P, P, P]
+    L.orc_corner_pass.restype = C.c_int
+    L.orc_corner_pass.argtypes = [P, C.c_int, P, C.c_int, C.c_int, P, C.c_int, C.c_int, P, P, P]
+    L.orc_scan2map_features.restype = C.c_int
+    L.orc_scan2map_features.argtypes = [P, C.c_int, P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_int, P,
+                                        C.POINTER(S2mOpts), C.POINTER(LmState), C.POINTER(S2mResult)]
     return L
 
 
@@ -179,6 +187,52 @@ def scan2map(map_pts, scan_ds, pose6, opts: S2mOpts | None = None, state: LmStat
     st = state if state is not None else LmState()
     res = S2mResult()
     rc = lib.orc_scan2map(_p(m), len(m), _p(s), len(s), _p(p), C.byref(o), C.byref(st), C.byref(res))
+    return p, res, rc, st
+
+
+# ---- upstream LIO-SAM corner superset (not in the reference; oracle/liloc_oracle.cpp "corner path") ----
+def eigen3(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(9)
+    w, V = np.empty(3, np.float32), np.empty(9, np.float32)
+    lib.orc_eigen3(_p(A), _p(w), _p(V))
+    return w, V.reshape(3, 3)
+
+
+def line_residual(pts5x3, sel3):
+    a = np.ascontiguousarray(pts5x3, np.float32).reshape(15)
+    q = np.ascontiguousarray(sel3, np.float32).reshape(3)
+    c = np.zeros(4, np.float32)
+    keep = lib.orc_line_residual(_p(a), _p(q), _p(c))
+    return c, keep
+
+
+def corner_pass(map_pts, scan_ds, pose6, stride=1, kdtree=False, threads=1):
+    """Returns (coeff[Q_all,4], flag[Q_all]) of cornerOptimization at a fixed pose."""
+    m, s = _c(map_pts), _c(scan_ds)
+    p = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    Q = len(s)
+    ori, coef, sel = np.empty((Q, 4), np.float32), np.empty((Q, 4), np.float32), np.empty(Q, np.int32)
+    n = lib.orc_corner_pass(_p(m), len(m), _p(s), Q, stride, _p(p), 1 if kdtree else 0, threads, _p(ori), _p(coef), _p(sel))
+    full, flag = np.zeros((Q, 4), np.float32), np.zeros(Q, np.uint8)
+    full[sel[:n]] = coef[:n]
+    flag[sel[:n]] = 1
+    return full, flag
+
+
+def upstream_opts(knn=1, threads=1) -> S2mOpts:
+    """Upstream LIO-SAM loop shape: 30 iterations, surf stride 1, gate surf > 100 (corner > 10 is an argument)."""
+    return S2mOpts(max_iters=30, stride=1, min_sel=50, min_points=100, knn=knn, threads=threads)
+
+
+def scan2map_features(map_s, scan_s, map_c, scan_c, pose6, opts: S2mOpts | None = None, state: LmState | None = None,
+                      min_corner=10, stride_corner=1):
+    ms, ss, mc, sc = _c(map_s), _c(scan_s), _c(map_c), _c(scan_c)
+    p = np.array(pose6, np.float32).reshape(6).copy()
+    o = opts or upstream_opts()
+    st = state if state is not None else LmState()
+    res = S2mResult()
+    rc = lib.orc_scan2map_features(_p(ms), len(ms), _p(ss), len(ss), _p(mc), len(mc), _p(sc), len(sc),
+                                   min_corner, stride_corner, _p(p), C.byref(o), C.byref(st), C.byref(res))
     return p, res, rc, st
 
 

@@ -6,14 +6,14 @@
 // the down-sampled scans and the 6x6 state.  Per frame the host sends the raw scan(s) and K keyframe
 // descriptors (64 bytes each) and reads back one result struct.
 //
-// A frame (liloc_frame / liloc_frame_features) is enqueued WITHOUT any host round trip: every size that is
-// only known on the device (M, Q_all, the search-grid geometry) is consumed on the device.  Up to three
-// streams run the independent branches (surf map | surf scan | corner map + corner scan) concurrently and
-// join before the registration kernel; the host synchronises once, at the end.
+// A frame (liloc_frame / liloc_frame_features) is THREE kernel launches and one host synchronisation: the
+// cooperative point-cloud pipeline (pipeline.cuh) once for the local maps (main stream) and once for the scans
+// (second stream, so the scan's H2D copy overlaps the map work), then the cooperative registration kernel
+// (s2m.cuh).  Every size that is only known on the device (M, Q_all, the search-grid geometry) is consumed on
+// the device.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdarg>
 #include <cstdio>
@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "voxelgrid.cuh"
 #include "knn_grid.cuh"
+#include "pipeline.cuh"
 #include "s2m.cuh"
 #include "ndt.cuh"
 
@@ -42,14 +43,12 @@ struct DevBuf {
 };
 
 struct VgInst {            // scratch of one VoxelGrid instance (the reference has three filters, :78-80)
-    DevBuf<unsigned> keys_a, keys_b, vals_a, vals_b;
-    DevBuf<unsigned char> cub_tmp;
+    DevBuf<unsigned> keys_a, keys_b, vals_a, vals_b;      // after the sort: keys_b / vals_b hold the sorted pairs
+    DevBuf<int> hist;              // 3 rotating block-histogram buffers of the radix sort
     DevBuf<int> tile_counts;
-    unsigned* d_enc = nullptr;     // 6 ordered-uint min/max
+    unsigned* d_enc = nullptr;     // 6 ordered-uint min/max (armed at creation, re-armed by the kernel)
     VgParams* d_vp = nullptr;
     int* d_count = nullptr;
-    int bits_hint = 32;            // radix-sort key bits expected for the next frame (verified after the fact)
-    int bits_used = 32;
 };
 
 constexpr int kClasses = 2;        // LILOC_SURF, LILOC_CORNER
@@ -89,6 +88,7 @@ struct HostClassInfo { VgParams map_vp, scan_vp; GridParams gp; int M, Q_all; };
 struct HostFrameInfo {     // pinned, written by async D2H
     HostClassInfo c[kClasses];
     S2mResult res;
+    unsigned long long marks[2 * kPipeMarks];
     int scratch;
 };
 
@@ -122,6 +122,8 @@ struct liloc_ctx {
     int state_cur = 0;
     S2mResult* d_result = nullptr;
     int s2m_max_blocks = 0;
+    int pipe_blocks = 0;                 // blocks of one point-cloud pipeline launch (one per SM: two launches co-reside)
+    unsigned long long* d_marks = nullptr;   // 2 x kPipeMarks phase timestamps (maps launch, scans launch)
     int s2m_nq_last = 0;
     int s2m_nq_corner_last = 0;
 
@@ -207,11 +209,6 @@ inline int blocks_for(const liloc_ctx* ctx, long long n, int per_block, int wave
 
 inline bool bad_class(int cls) { return cls < 0 || cls >= kClasses; }
 
-__global__ void k_init_enc(unsigned* enc) {
-    if (threadIdx.x < 3) enc[threadIdx.x] = 0xFFFFFFFFu;
-    else if (threadIdx.x < 6) enc[threadIdx.x] = 0u;
-}
-__global__ void k_set_int(int* p, int v) { *p = v; }
 __global__ void k_pose_to_T(const float* pose6, float* T) { if (threadIdx.x == 0) pose_to_T(pose6, T); }
 
 // device-side evaluation of the small dense algebra, one system per thread (kernel-level parity tests)
@@ -248,70 +245,50 @@ __global__ void k_debug_line(const float* pts, const float* sel3, int n, float4*
     coeff[i] = c;
 }
 
-// VoxelGrid of a device cloud on stream `st`.  The bounding box must already be in vi.d_enc when have_minmax.
-// `bits` = radix-sort key bits (32 = always safe; fewer = one 8-bit pass less, verified by the caller against
-// VgParams.key_bits after the fact).
-int vg_run(liloc_ctx* ctx, VgInst& vi, cudaStream_t st, const float4* d_pts, int n, float leaf, bool have_minmax,
-           DevBuf<float4>& out, int bits, bool sort_only = false) {
-    if (n <= 0) {
-        k_set_int<<<1, 1, 0, st>>>(vi.d_count, 0); KCHECK();
-        return 0;
-    }
+// ---- problems of the cooperative point-cloud pipeline (pipeline.cuh) ------------------------------------------
+// Scratch and output of one VoxelGrid over n points.
+int prob_voxelgrid(liloc_ctx* ctx, VgInst& vi, const float4* d_pts, int n, float leaf, DevBuf<float4>* out, VgProb* q) {
     int rc;
-    if (!sort_only && (rc = ensure(ctx, out, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, vi.keys_a, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, vi.keys_b, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, vi.vals_a, (size_t)n))) return rc;
-    if ((rc = ensure(ctx, vi.vals_b, (size_t)n))) return rc;
-    const int n_tiles = (n + kRunTile - 1) / kRunTile;
-    if ((rc = ensure(ctx, vi.tile_counts, (size_t)n_tiles + 1))) return rc;
-    if (bits < 1) bits = 1;
-    if (bits > 32) bits = 32;
-    vi.bits_used = bits;
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, vi.keys_a.p, vi.keys_b.p, vi.vals_a.p, vi.vals_b.p, n, 0, 32, st));
-    if ((rc = ensure(ctx, vi.cub_tmp, tmp_bytes))) return rc;
-
-    if (!have_minmax) {
-        k_init_enc<<<1, 32, 0, st>>>(vi.d_enc); KCHECK();
-        k_minmax<<<blocks_for(ctx, n, kMinMaxThreads * 4), kMinMaxThreads, 0, st>>>(d_pts, n, vi.d_enc); KCHECK();
-    }
-    k_vg_params<<<1, 1, 0, st>>>(vi.d_enc, leaf, n, vi.d_vp); KCHECK();
-    k_vg_keys<<<blocks_for(ctx, n, 256 * 4), 256, 0, st>>>(d_pts, n, vi.d_vp, vi.keys_a.p, vi.vals_a.p); KCHECK();
-    size_t tb = vi.cub_tmp.cap;
-    CU(cub::DeviceRadixSort::SortPairs(vi.cub_tmp.p, tb, vi.keys_a.p, vi.keys_b.p, vi.vals_a.p, vi.vals_b.p, n, 0, bits, st));
-    ctx->launches += 2 + (bits + 7) / 8;           // histogram + exclusive sum + one onesweep pass per 8 bits
-    if (sort_only) return 0;
-    k_run_count<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, n, vi.tile_counts.p); KCHECK();
-    k_scan_tiles<<<1, 1024, 0, st>>>(vi.tile_counts.p, n_tiles, vi.d_count); KCHECK();
-    k_run_centroids<<<n_tiles, kRunThreads, 0, st>>>(vi.keys_b.p, vi.vals_b.p, n, vi.tile_counts.p, d_pts, out.p); KCHECK();
+    const size_t cap = (size_t)(n > 0 ? n : 1);
+    if (out && (rc = ensure(ctx, *out, cap))) return rc;
+    if ((rc = ensure(ctx, vi.keys_a, cap))) return rc;
+    if ((rc = ensure(ctx, vi.keys_b, cap))) return rc;
+    if ((rc = ensure(ctx, vi.vals_a, cap))) return rc;
+    if ((rc = ensure(ctx, vi.vals_b, cap))) return rc;
+    if ((rc = ensure(ctx, vi.hist, (size_t)3 * kHistStride))) return rc;
+    if ((rc = ensure(ctx, vi.tile_counts, (size_t)(n / kRunTile) + 2))) return rc;
+    *q = VgProb{};
+    q->pts = d_pts; q->n = n; q->leaf = leaf;
+    q->keys[0] = vi.keys_a.p; q->keys[1] = vi.keys_b.p; q->vals[0] = vi.vals_a.p; q->vals[1] = vi.vals_b.p;
+    q->hist = vi.hist.p; q->tile_counts = vi.tile_counts.p; q->enc = vi.d_enc; q->vp = vi.d_vp;
+    q->out = out ? out->p : nullptr; q->count = vi.d_count;
+    q->sort_only = out ? 0 : 1;
     return 0;
 }
 
-inline int next_bits_hint(int key_bits) {       // one bit of head-room, rounded up to whole 8-bit radix passes
-    int b = ((key_bits + 1 + 7) / 8) * 8;
-    return b > 32 ? 32 : b;
-}
-
-// Search structure over fc.map (replaces kdtreeSurfFromMap->setInputCloud, :1188), entirely on the device:
-// geometry from the bounding box in the VoxelGrid params, count -> exclusive scan -> scatter.
-// m_upper = host-side upper bound of the number of map points (sizes launches and buffers).
-int grid_enqueue(liloc_ctx* ctx, FeatClass& fc, cudaStream_t st, int m_upper) {
+// Search structure over the class's down-sampled map (replaces kdtreeSurfFromMap->setInputCloud, :1188).
+int prob_add_grid(liloc_ctx* ctx, FeatClass& fc, int m_upper, VgProb* q) {
     int rc;
     const int nc_max = ctx->max_cells;
-    if ((rc = ensure(ctx, fc.cell_counts, (size_t)nc_max))) return rc;
+    if (!fc.cell_counts.p) {                          // the kernel keeps the counters zero outside the last grid
+        if ((rc = ensure(ctx, fc.cell_counts, (size_t)nc_max))) return rc;
+        CU(cudaMemsetAsync(fc.cell_counts.p, 0, fc.cell_counts.cap * sizeof(int), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     if ((rc = ensure(ctx, fc.cell_start, (size_t)nc_max + 1))) return rc;
     if ((rc = ensure(ctx, fc.grid_tiles, (size_t)(nc_max / kScanTile) + 2))) return rc;
     if ((rc = ensure(ctx, fc.cpts, (size_t)(m_upper > 0 ? m_upper : 1)))) return rc;
-    const int wide = ctx->num_sms * 4;
-    const int n_tiles_max = nc_max / kScanTile + 1;
-    k_grid_params<<<1, 32, 0, st>>>(fc.vg_map.d_vp->mn, fc.vg_map.d_vp->mx, fc.d_M, nc_max, fc.d_gp); KCHECK();
-    k_grid_zero<<<wide, 256, 0, st>>>(fc.d_gp, fc.cell_counts.p); KCHECK();
-    k_grid_count<<<blocks_for(ctx, m_upper, 256), 256, 0, st>>>(fc.map.p, fc.d_M, fc.d_gp, fc.cell_counts.p); KCHECK();
-    k_scan_reduce<<<wide, kScanThreads, 0, st>>>(fc.cell_counts.p, fc.d_gp, fc.grid_tiles.p); KCHECK();
-    k_scan_tiles_grid<<<1, 1024, 0, st>>>(fc.grid_tiles.p, fc.d_gp, fc.grid_tiles.p + n_tiles_max); KCHECK();
-    k_scan_down<<<wide, kScanThreads, 0, st>>>(fc.cell_counts.p, fc.d_gp, fc.grid_tiles.p, fc.cell_start.p, fc.cell_counts.p); KCHECK();
-    k_grid_scatter<<<blocks_for(ctx, m_upper, 256), 256, 0, st>>>(fc.map.p, fc.d_M, fc.d_gp, fc.cell_counts.p, fc.cpts.p); KCHECK();
+    q->build_grid = 1; q->max_cells = nc_max;
+    q->gp = fc.d_gp; q->cell_counts = fc.cell_counts.p; q->cell_start = fc.cell_start.p; q->grid_tiles = fc.grid_tiles.p; q->cpts = fc.cpts.p;
+    return 0;
+}
+
+int pipe_launch(liloc_ctx* ctx, cudaStream_t st, PipeArgs& a, unsigned long long* marks) {
+    if (a.n_prob <= 0) return 0;
+    a.marks = marks;
+    void* args[] = {&a};
+    CU(cudaLaunchCooperativeKernel((void*)k_voxel_pipeline, dim3((unsigned)ctx->pipe_blocks), dim3(kPipeThreads), args, 0, st));
+    ++ctx->launches;
     return 0;
 }
 
@@ -322,10 +299,9 @@ GridView grid_view(const FeatClass& fc) {
 
 void tick(liloc_ctx* ctx, int i, cudaStream_t st) { if (ctx->timing) cudaEventRecord(ctx->ev[i], st); }
 
-// enqueue on `st`: keyframe descriptors -> transform + concat + bbox -> VoxelGrid -> search grid;
-// async D2H of {params, M, grid geometry}.  `timed`: record the phase events (main-stream surf branch only).
-int localmap_enqueue(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids, const float* poses6, int K, float leaf,
-                     int bits, bool timed) {
+// Local-map problem of class `cls`: keyframe descriptors (H2D on `st`) -> transform + concat + bbox -> VoxelGrid ->
+// search grid.  Only fills *q; the caller launches the pipeline on the same stream.
+int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids, const float* poses6, int K, float leaf, VgProb* q) {
     FeatClass& fc = ctx->fc[cls];
     if (K < 0 || (K > 0 && (!kf_ids || !poses6)) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap: bad arguments");
     int rc;
@@ -347,30 +323,22 @@ int localmap_enqueue(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids
         if (total > 0x7fffffffLL) return fail(ctx, LILOC_ERR_CAPACITY, "localmap: more than 2^31 points");
     }
     fc.n_raw = (int)total;
-    if (timed) tick(ctx, 0, st);
-    if (total > 0) {
-        if ((rc = ensure(ctx, fc.descs, (size_t)K))) return rc;
-        if ((rc = ensure(ctx, fc.raw, (size_t)total))) return rc;
+    if ((rc = ensure(ctx, fc.descs, (size_t)(K > 0 ? K : 1)))) return rc;
+    if ((rc = ensure(ctx, fc.raw, (size_t)(total > 0 ? total : 1)))) return rc;
+    if (K > 0) {
         CU(cudaMemcpyAsync(fc.descs.p, fc.h_descs, (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += (long long)K * (long long)sizeof(KfDesc);
-        k_init_enc<<<1, 32, 0, st>>>(fc.vg_map.d_enc); KCHECK();
-        k_assemble<<<blocks_for(ctx, total, kAsmTile), kMinMaxThreads, 0, st>>>(ctx->arena.p, fc.descs.p, K, (int)total, fc.raw.p, fc.vg_map.d_enc); KCHECK();
     }
-    if (timed) tick(ctx, 1, st);
     fc.map_leaf_last = leaf;
-    if ((rc = vg_run(ctx, fc.vg_map, st, fc.raw.p, (int)total, leaf, true, fc.map, bits))) return rc;
-    if (timed) tick(ctx, 2, st);
-    if ((rc = grid_enqueue(ctx, fc, st, (int)total))) return rc;
-    if (timed) tick(ctx, 3, st);
-    HostClassInfo& hi = ctx->h_info->c[cls];
-    if (total > 0) CU(cudaMemcpyAsync(&hi.map_vp, fc.vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&hi.M, fc.d_M, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ctx->stats.d2h_bytes += (long long)sizeof(VgParams) + 4;
+    if ((rc = prob_voxelgrid(ctx, fc.vg_map, fc.raw.p, (int)total, leaf, &fc.map, q))) return rc;
+    q->arena = ctx->arena.p; q->descs = fc.descs.p; q->K = total > 0 ? K : 0; q->raw = fc.raw.p;
+    if ((rc = prob_add_grid(ctx, fc, (int)total, q))) return rc;
     fc.have_map = true;
     return 0;
 }
 
-int scan_enqueue(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pts, int n, bool on_device, float leaf, int bits) {
+// Scan problem of class `cls`: H2D on `st` (unless the scan is already on the device) -> VoxelGrid.
+int scan_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pts, int n, bool on_device, float leaf, VgProb* q) {
     FeatClass& fc = ctx->fc[cls];
     if (n < 0 || (n > 0 && !pts) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad arguments");
     int rc;
@@ -383,13 +351,18 @@ int scan_enqueue(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pt
         src = fc.scan_raw.p;
     }
     fc.scan_src_last = src; fc.scan_leaf_last = leaf;
-    if ((rc = vg_run(ctx, fc.vg_scan, st, src, n, leaf, false, fc.scan, bits))) return rc;
-    HostClassInfo& hi = ctx->h_info->c[cls];
-    if (n > 0) CU(cudaMemcpyAsync(&hi.scan_vp, fc.vg_scan.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&hi.Q_all, fc.d_Q, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ctx->stats.d2h_bytes += 4 + (long long)sizeof(VgParams);
+    if ((rc = prob_voxelgrid(ctx, fc.vg_scan, src, n, leaf, &fc.scan, q))) return rc;
     fc.n_scan_last = n;
     fc.have_scan = true;
+    return 0;
+}
+
+// async D2H of the device-side counts of a class (picked up by class_collect after a synchronisation)
+int class_fetch(liloc_ctx* ctx, int cls, cudaStream_t st, bool map, bool scan) {
+    FeatClass& fc = ctx->fc[cls];
+    HostClassInfo& hi = ctx->h_info->c[cls];
+    if (map) { CU(cudaMemcpyAsync(&hi.M, fc.d_M, sizeof(int), cudaMemcpyDeviceToHost, st)); ctx->stats.d2h_bytes += 4; }
+    if (scan) { CU(cudaMemcpyAsync(&hi.Q_all, fc.d_Q, sizeof(int), cudaMemcpyDeviceToHost, st)); ctx->stats.d2h_bytes += 4; }
     return 0;
 }
 
@@ -506,6 +479,8 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
             CUB_(cudaMalloc(&vi->d_vp, sizeof(VgParams)));
             CUB_(cudaMalloc(&vi->d_count, sizeof(int)));
             CUB_(cudaMemset(vi->d_vp, 0, sizeof(VgParams)));
+            { const unsigned arm[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+              CUB_(cudaMemcpy(vi->d_enc, arm, sizeof(arm), cudaMemcpyHostToDevice)); }
             CUB_(cudaMemset(vi->d_count, 0, sizeof(int)));
         }
         fc.d_M = fc.vg_map.d_count;
@@ -525,6 +500,11 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan2map, kS2mThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_scan2map cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->s2m_max_blocks = per_sm * c->num_sms;
+    CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_pipeline, kPipeThreads, 0));
+    if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_voxel_pipeline cannot be resident"); return bail(LILOC_ERR_CUDA); }
+    c->pipe_blocks = c->num_sms;
+    CUB_(cudaMalloc(&c->d_marks, 2 * kPipeMarks * sizeof(unsigned long long)));
+    CUB_(cudaMemset(c->d_marks, 0, 2 * kPipeMarks * sizeof(unsigned long long)));
 #undef CUB_
     const int scan_cap = cfg->max_scan_points > 0 ? cfg->max_scan_points : 16 * 1800;
     const int raw_cap = cfg->max_raw_points > 0 ? cfg->max_raw_points : (1 << 20);
@@ -537,8 +517,6 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
         (rc = ensure(c, s.vg_scan.keys_a, (size_t)scan_cap)) || (rc = ensure(c, s.vg_scan.keys_b, (size_t)scan_cap)) ||
         (rc = ensure(c, s.vg_scan.vals_a, (size_t)scan_cap)) || (rc = ensure(c, s.vg_scan.vals_b, (size_t)scan_cap)) ||
         (rc = ensure(c, c->arena, (size_t)raw_cap)) || (rc = ensure(c, s.cpts, (size_t)raw_cap)) ||
-        (rc = ensure(c, s.cell_counts, (size_t)c->max_cells)) || (rc = ensure(c, s.cell_start, (size_t)c->max_cells + 1)) ||
-        (rc = ensure(c, s.grid_tiles, (size_t)(c->max_cells / kScanTile) + 2)) ||
         (rc = ensure(c, c->partial, (size_t)2 * c->s2m_max_blocks * kNSums)))
         return bail(rc);
     *out = c;
@@ -556,13 +534,14 @@ void liloc_destroy(liloc_ctx* c) {
         fr(fc.cell_counts.p); fr(fc.cell_start.p); fr(fc.grid_tiles.p); fr(fc.d_gp);
         if (fc.h_descs) cudaFreeHost(fc.h_descs);
         for (VgInst* vi : {&fc.vg_map, &fc.vg_scan}) {
-            fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->cub_tmp.p); fr(vi->tile_counts.p);
+            fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->hist.p); fr(vi->tile_counts.p);
             fr(vi->d_enc); fr(vi->d_vp); fr(vi->d_count);
         }
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+    fr(c->d_marks);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
@@ -642,7 +621,11 @@ int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const
     ENTER(ctx);
     if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "localmap_build: bad class %d", cls);
     int rc;
-    if ((rc = localmap_enqueue(ctx, cls, ctx->stream, kf_ids, poses6, K, leaf, 32, false))) return rc;
+    PipeArgs pa{};
+    if ((rc = localmap_problem(ctx, cls, ctx->stream, kf_ids, poses6, K, leaf, &pa.prob[0]))) return rc;
+    pa.n_prob = 1;
+    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
+    if ((rc = class_fetch(ctx, cls, ctx->stream, true, false))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, true, false);
     if (M_out) *M_out = ctx->fc[cls].M;
@@ -663,11 +646,12 @@ int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts, in
     if ((rc = ensure(ctx, fc.raw, (size_t)(n > 0 ? n : 1)))) return rc;
     if (n > 0) CU(cudaMemcpyAsync(fc.raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     fc.n_raw = n;
-    if ((rc = vg_run(ctx, fc.vg_map, ctx->stream, fc.raw.p, n, leaf, false, fc.map, 32))) return rc;
-    if ((rc = grid_enqueue(ctx, fc, ctx->stream, n))) return rc;
-    HostClassInfo& hi = ctx->h_info->c[cls];
-    if (n > 0) CU(cudaMemcpyAsync(&hi.map_vp, fc.vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&hi.M, fc.d_M, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PipeArgs pa{};
+    if ((rc = prob_voxelgrid(ctx, fc.vg_map, fc.raw.p, n, leaf, &fc.map, &pa.prob[0]))) return rc;
+    if ((rc = prob_add_grid(ctx, fc, n, &pa.prob[0]))) return rc;
+    pa.n_prob = 1;
+    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
+    if ((rc = class_fetch(ctx, cls, ctx->stream, true, false))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     fc.have_map = true;
     class_collect(ctx, cls, true, false);
@@ -700,7 +684,11 @@ static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n,
     ENTER(ctx);
     if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad class %d", cls);
     int rc;
-    if ((rc = scan_enqueue(ctx, cls, ctx->stream, pts, n, on_device, leaf, 32))) return rc;
+    PipeArgs pa{};
+    if ((rc = scan_problem(ctx, cls, ctx->stream, pts, n, on_device, leaf, &pa.prob[0]))) return rc;
+    pa.n_prob = 1;
+    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
+    if ((rc = class_fetch(ctx, cls, ctx->stream, false, true))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, false, true);
     if (cls == LILOC_SURF) ctx->corner_scan_current = false;      // a new frame starts with its surf scan
@@ -750,55 +738,47 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     if (!pose6 || !in) return fail(ctx, LILOC_ERR_ARG, "frame: null argument");
     const liloc_s2m_opts* o = opts ? opts : &kDefaultOpts;
     const bool corner = o->enable_corner != 0;
-    FeatClass& fs = ctx->fc[0];
-    FeatClass& fcn = ctx->fc[1];
     const bool dev = in->scan_on_device != 0;
     int rc;
-    bool force32 = false;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        // fork: scan branch (H2D + VoxelGrid) on stream2, corner branch on stream3, surf map branch on the main stream
-        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
-        if ((rc = scan_enqueue(ctx, 0, ctx->stream2, in->scan[0], in->n_scan[0], dev, in->scan_leaf[0], force32 ? 32 : fs.vg_scan.bits_hint))) return rc;
-        if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
-        CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
-        if (corner) {
-            CU(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
-            if ((rc = localmap_enqueue(ctx, 1, ctx->stream3, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[1], force32 ? 32 : fcn.vg_map.bits_hint, false))) return rc;
-            if ((rc = scan_enqueue(ctx, 1, ctx->stream3, in->scan[1], in->n_scan[1], dev, in->scan_leaf[1], force32 ? 32 : fcn.vg_scan.bits_hint))) return rc;
-            CU(cudaEventRecord(ctx->ev_join3, ctx->stream3));
-        }
-        if ((rc = localmap_enqueue(ctx, 0, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[0], force32 ? 32 : fs.vg_map.bits_hint, true))) return rc;   // ev 0..3
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
-        if (corner) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join3, 0));
-        tick(ctx, 4, ctx->stream);
-        if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
-        tick(ctx, 5, ctx->stream);
-        CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation
-        // The sorts used the previous frame's key width; if this frame needed more bits the whole frame is redone
-        // with full 32-bit keys (the registration state is double-buffered, so the first attempt left no trace).
-        bool redo = false;
-        for (int cls = 0; cls < (corner ? 2 : 1); ++cls) {
-            FeatClass& fc = ctx->fc[cls];
-            const HostClassInfo& hi = ctx->h_info->c[cls];
-            if (fc.n_raw > 0 && hi.map_vp.key_bits > fc.vg_map.bits_used) redo = true;
-            if (in->n_scan[cls] > 0 && hi.scan_vp.key_bits > fc.vg_scan.bits_used) redo = true;
-            if (fc.n_raw > 0) fc.vg_map.bits_hint = next_bits_hint(hi.map_vp.key_bits);
-            if (in->n_scan[cls] > 0) fc.vg_scan.bits_hint = next_bits_hint(hi.scan_vp.key_bits);
-        }
-        if (!redo) break;
-        if (attempt == 1) return fail(ctx, LILOC_ERR_CUDA, "frame: radix-sort key width still too small after a 32-bit redo");
-        ++ctx->sort_redos; --ctx->stats.s2m_launches;
-        force32 = true;
+    const int ncls = corner ? 2 : 1;
+    // scans: H2D + VoxelGrid on stream2, so the copy overlaps the map pipeline on the main stream
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    PipeArgs ps{}, pm{};
+    for (int cls = 0; cls < ncls; ++cls)
+        if ((rc = scan_problem(ctx, cls, ctx->stream2, in->scan[cls], in->n_scan[cls], dev, in->scan_leaf[cls], &ps.prob[cls]))) return rc;
+    ps.n_prob = ncls;
+    if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
+    if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks + kPipeMarks : nullptr))) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
+    CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
+    // local maps: descriptors -> assemble -> VoxelGrid -> search grid, one launch for all classes
+    for (int cls = 0; cls < ncls; ++cls)
+        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[cls]))) return rc;
+    pm.n_prob = ncls;
+    tick(ctx, 0, ctx->stream);
+    if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks : nullptr))) return rc;
+    tick(ctx, 3, ctx->stream);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
+    tick(ctx, 4, ctx->stream);
+    if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
+    tick(ctx, 5, ctx->stream);
+    if (ctx->timing) CU(cudaMemcpyAsync(ctx->h_info->marks, ctx->d_marks, sizeof(ctx->h_info->marks), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation
+    {   // counts come back inside the result struct
+        const S2mResult& r = ctx->h_info->res;
+        ctx->h_info->c[0].M = r.map_points; ctx->h_info->c[0].Q_all = r.q_all;
+        ctx->h_info->c[1].M = r.extra[1];   ctx->h_info->c[1].Q_all = r.extra[0];
     }
     for (int cls = 0; cls < (corner ? 2 : 1); ++cls) class_collect(ctx, cls, true, true);
     ctx->corner_scan_current = corner;
     if (ctx->timing) {
         liloc_timing& t = ctx->last_timing;
-        cudaEventElapsedTime(&t.assemble_ms, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&t.map_voxel_ms, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&t.grid_ms, ctx->ev[2], ctx->ev[3]);
+        const unsigned long long* mk = ctx->h_info->marks;       // phase boundaries of the maps launch (ns)
+        auto span = [&](int i, int j) { return mk[j] > mk[i] ? (float)((double)(mk[j] - mk[i]) * 1e-6) : 0.f; };
+        t.assemble_ms = span(0, 1);                               // transform + concat + bounding box
+        t.map_voxel_ms = span(1, 5);                              // keys, radix sort, run count, centroids
+        t.grid_ms = span(5, 7);                                   // search-grid scan + scatter
         cudaEventElapsedTime(&t.scan_ms, ctx->ev[6], ctx->ev[7]);
         cudaEventElapsedTime(&t.s2m_ms, ctx->ev[4], ctx->ev[5]);
         cudaEventElapsedTime(&t.total_ms, ctx->ev[0], ctx->ev[5]);
@@ -847,11 +827,11 @@ int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, li
     if ((rc = ensure(ctx, ctx->tmp_i, 1))) return rc;
     {   // run on the scan instance's scratch but keep its result count (d_Q) untouched
         VgInst& vi = ctx->fc[0].vg_scan;
-        int* keep = vi.d_count;
-        vi.d_count = ctx->tmp_i.p;
-        rc = vg_run(ctx, vi, ctx->stream, ctx->tmp_pts.p, n, leaf, false, outb, 32);
-        vi.d_count = keep;
-        if (rc) return rc;
+        PipeArgs pa{};
+        if ((rc = prob_voxelgrid(ctx, vi, ctx->tmp_pts.p, n, leaf, &outb, &pa.prob[0]))) return rc;
+        pa.prob[0].count = ctx->tmp_i.p;
+        pa.n_prob = 1;
+        if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
     }
     int m = 0;
     CU(cudaMemcpyAsync(&m, ctx->tmp_i.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1037,8 +1017,12 @@ int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, 
     int rc;
     if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n))) return rc;
     CU(cudaMemcpyAsync(ctx->tmp_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf<float4> none;
-    if ((rc = vg_run(ctx, ctx->fc[0].vg_map, ctx->stream, ctx->tmp_pts.p, n, resolution, false, none, 32, true))) return rc;
+    {   // voxel keys + stable sort only: the sorted (key, source index) pairs land in keys_b / vals_b
+        PipeArgs pa{};
+        if ((rc = prob_voxelgrid(ctx, ctx->fc[0].vg_map, ctx->tmp_pts.p, n, resolution, nullptr, &pa.prob[0]))) return rc;
+        pa.n_prob = 1;
+        if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
+    }
     VgParams vp;
     CU(cudaMemcpyAsync(&vp, ctx->fc[0].vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,501 @@
+// liloc_b200/csrc/pipeline.cuh -- the whole point-cloud side of a frame as ONE persistent cooperative kernel.
+//
+// Replaces (reference, per frame): extractCloud's transform + concatenation (src/mapOptmization.cpp:936-961,
+// include/utility.h:388-407), the two pcl::VoxelGrid filters (:954-955, :972-973; semantics SURVEY.md A.1) and
+// kdtreeSurfFromMap->setInputCloud (:1188).  Up to four independent "problems" (surf map, surf scan, corner map,
+// corner scan) run through the same phases between grid barriers, so a frame costs one launch here plus one
+// launch of the registration kernel (s2m.cuh) instead of ~60 small launches:
+//
+//   P0  transform + concatenate the selected keyframes (map problems) and the bounding box of every cloud
+//   P1  VoxelGrid parameters; int32 voxel key per point; digit histogram of the first radix pass
+//   Sx  stable LSD radix sort of (key, source index), 8 bits per pass, ceil(key_bits / 8) passes: per-block
+//       digit offsets from the block histograms, warp-match ranking inside a tile, scatter; the histogram of the
+//       NEXT pass is accumulated while scattering, so a pass is a single phase
+//   R1  voxel-run heads per tile
+//   R2  one centroid per voxel run (float sums in ascending source index = the canonical order), written in
+//       ascending voxel index; the centroid's search-grid cell is counted in the same pass
+//   G1-G3  exclusive scan of the cell counts, then the points sorted by cell (the kNN search structure)
+//
+// Every size that only exists on the device (M, Q_all, search-grid geometry) stays there.  No library calls:
+// the radix sort is part of this kernel (the first version of this path used cub::DeviceRadixSort).
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "voxelgrid.cuh"
+#include "knn_grid.cuh"
+
+namespace liloc {
+
+namespace cg = cooperative_groups;
+
+constexpr int kPipeThreads = 256;
+constexpr int kSortBlocksMax = 148;                       // blocks that take part in the sort (one per SM)
+constexpr int kSortRounds = 4;
+constexpr int kSortTile = kPipeThreads * kSortRounds;     // 1024 items
+constexpr int kHistStride = kSortBlocksMax * 256;         // ints per histogram buffer (three rotate)
+constexpr int kMaxProbs = 4;
+
+struct VgProb {
+    const float4* pts;         // cloud to down-sample (== raw when assembling)
+    int n;                     // points (known on the host)
+    float leaf;
+    // optional: assemble pts from keyframes first
+    const float4* arena;
+    const KfDesc* descs;
+    int K;
+    float4* raw;
+    // scratch
+    unsigned* keys[2];
+    unsigned* vals[2];
+    int* hist;                 // 3 * kHistStride
+    int* tile_counts;          // ceil(n / kRunTile) + 1
+    unsigned* enc;             // 6 ordered-uint min / max; re-armed by the kernel for the next launch
+    VgParams* vp;              // out (diagnostics; the bounding box)
+    // output
+    float4* out;
+    int* count;
+    // optional: search grid over `out`
+    int build_grid;
+    int max_cells;
+    GridParams* gp;
+    int* cell_counts;          // all-zero outside [0, previous ncells) on entry; scatter cursor on exit
+    int* cell_start;
+    int* grid_tiles;
+    float4* cpts;
+    int sort_only;             // stop after the sort (NDT target build): sorted pairs are in keys[1] / vals[1]
+};
+
+constexpr int kPipeMarks = 16;
+struct PipeArgs {
+    VgProb prob[kMaxProbs];
+    int n_prob;
+    unsigned long long* marks;   // optional: %globaltimer (ns) at every phase boundary, written by block 0 (latency breakdown)
+};
+
+LILOC_DEV unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// VoxelGrid set-up from the ordered-uint bounding box.
+LILOC_DEV VgParams vg_params_compute(const unsigned* __restrict__ enc, float leaf, int n) {
+    VgParams p;
+    p.inv_leaf = 1.0f / leaf;
+    for (int a = 0; a < 3; ++a) { p.mn[a] = ord2f(enc[a]); p.mx[a] = ord2f(enc[3 + a]); }
+    if (n <= 0) { for (int a = 0; a < 3; ++a) { p.mn[a] = 0.f; p.mx[a] = 0.f; } }
+    const long long dx = (long long)((p.mx[0] - p.mn[0]) * p.inv_leaf) + 1;
+    const long long dy = (long long)((p.mx[1] - p.mn[1]) * p.inv_leaf) + 1;
+    const long long dz = (long long)((p.mx[2] - p.mn[2]) * p.inv_leaf) + 1;
+    p.overflow = (dx * dy * dz > 2147483647LL) ? 1 : 0;
+    int divb[3];
+    for (int a = 0; a < 3; ++a) {
+        p.minb[a] = (int)floorf(p.mn[a] * p.inv_leaf);
+        const int maxb = (int)floorf(p.mx[a] * p.inv_leaf);
+        divb[a] = maxb - p.minb[a] + 1;
+    }
+    p.mul[0] = 1; p.mul[1] = divb[0]; p.mul[2] = divb[0] * divb[1];
+    const long long max_key = p.overflow ? (long long)(n > 0 ? n - 1 : 0) : (long long)divb[0] * divb[1] * divb[2] - 1;
+    int bits = 1;
+    while (bits < 32 && (max_key >> bits) != 0) ++bits;
+    p.key_bits = bits;
+    return p;
+}
+
+// Search-grid geometry from a bounding box: cell edge 2^k >= 1 m, one cell of padding, at most max_cells cells.
+LILOC_DEV GridParams grid_params_compute(const float* mn, const float* mx, bool empty, int max_cells) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = empty ? 0.f : mn[a]; hi[a] = empty ? 0.f : mx[a]; }
+    GridParams g;
+    g.ncells = -1;
+    for (int k = 0; k < 24; ++k) {
+        const float inv = 1.0f / (float)(1 << k);
+        long long cells = 1;
+        for (int a = 0; a < 3; ++a) {
+            g.g0[a] = (int)floorf(lo[a] * inv) - 1;
+            const int g1 = (int)floorf(hi[a] * inv) + 1;
+            g.dim[a] = g1 - g.g0[a] + 1;
+            cells *= g.dim[a];
+        }
+        g.inv_cell = inv;
+        if (cells <= (long long)max_cells) { g.ncells = (int)cells; break; }
+    }
+    if (g.ncells < 0) { g.ncells = 1; g.dim[0] = g.dim[1] = g.dim[2] = 1; g.inv_cell = 0.f; g.g0[0] = g.g0[1] = g.g0[2] = 0; }
+    return g;
+}
+
+LILOC_DEV int voxel_key(const float4 p, const VgParams& vp, int i) {
+    if (vp.overflow) return i;
+    const int i0 = (int)(floorf(p.x * vp.inv_leaf) - (float)vp.minb[0]);
+    const int i1 = (int)(floorf(p.y * vp.inv_leaf) - (float)vp.minb[1]);
+    const int i2 = (int)(floorf(p.z * vp.inv_leaf) - (float)vp.minb[2]);
+    return i0 + i1 * vp.mul[1] + i2 * vp.mul[2];
+}
+
+LILOC_DEV int block_sum_256(int v) {                        // all 256 threads; returns the block total to every thread
+    __shared__ int s_w[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    return t;
+}
+
+struct SortGeom { int C, nb; };                            // items per sorting block (multiple of kSortTile), busy blocks
+LILOC_DEV SortGeom sort_geom(int n) {
+    SortGeom g;
+    const int gs = min((int)gridDim.x, kSortBlocksMax);
+    g.C = (((n + gs - 1) / gs + kSortTile - 1) / kSortTile) * kSortTile;
+    if (g.C < kSortTile) g.C = kSortTile;
+    g.nb = (n + g.C - 1) / g.C;
+    return g;
+}
+
+struct PipeSmemSort { int offs[256]; int wcnt[kPipeThreads / 32][256]; };
+struct PipeSmemRun { unsigned key[kRunTile]; float4 pt[kRunTile]; unsigned prev; };
+union PipeSmem { PipeSmemSort sort; PipeSmemRun run; int hist[256]; };
+
+// ---- P0 -------------------------------------------------------------------------------------------------------
+LILOC_DEV void pipe_bbox(const VgProb& q) {
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    if (q.K > 0) {
+        __shared__ int s_k0;
+        for (int tile = blockIdx.x; tile * kAsmTile < q.n; tile += gridDim.x) {
+            const int base = tile * kAsmTile;
+            __syncthreads();
+            if (threadIdx.x == 0) {               // last descriptor with dst_off <= base
+                int lo = 0, hi = q.K - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (q.descs[mid].dst_off <= base) lo = mid; else hi = mid - 1;
+                }
+                s_k0 = lo;
+            }
+            __syncthreads();
+            int k = s_k0;
+#pragma unroll
+            for (int j = 0; j < kAsmPerThread; ++j) {
+                const int i = base + j * kPipeThreads + threadIdx.x;
+                if (i < q.n) {
+                    while (k + 1 < q.K && q.descs[k + 1].dst_off <= i) ++k;
+                    const KfDesc* d = &q.descs[k];
+                    const float4 p = __ldg(&q.arena[d->src_off + (i - d->dst_off)]);
+                    const float4 o = apply_T(d->T, p);
+                    q.raw[i] = o;
+                    mn[0] = fminf(mn[0], o.x); mx[0] = fmaxf(mx[0], o.x);
+                    mn[1] = fminf(mn[1], o.y); mx[1] = fmaxf(mx[1], o.y);
+                    mn[2] = fminf(mn[2], o.z); mx[2] = fmaxf(mx[2], o.z);
+                }
+            }
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += gridDim.x * blockDim.x) {
+            const float4 p = __ldg(&q.pts[i]);
+            mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+            mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+            mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+        }
+    }
+    block_minmax_commit(mn, mx, q.enc);
+    // histogram buffers 1 and 2 must be zero when the first scatter pass accumulates into them
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kHistStride; i += gridDim.x * blockDim.x) q.hist[kHistStride + i] = 0;
+    if (q.build_grid) {                           // clear what the previous build left in the cell counters
+        const int prev = q.gp->ncells;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) q.cell_counts[i] = 0;
+    }
+}
+
+// ---- P1: keys + histogram of the first pass ----------------------------------------------------------------------
+LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSmem& sm) {
+    const SortGeom g = sort_geom(q.n);
+    if ((int)blockIdx.x >= g.nb) return;
+    unsigned* keys = q.keys[(npass + 1) & 1];                  // so that the last pass lands in buffer 1
+    sm.hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo = blockIdx.x * g.C, hi = min(q.n, lo + g.C);
+    for (int i = lo + threadIdx.x; i < hi; i += kPipeThreads) {
+        const unsigned key = (unsigned)voxel_key(__ldg(&q.pts[i]), vp, i);
+        keys[i] = key;
+        atomicAdd(&sm.hist[key & 255u], 1);
+    }
+    __syncthreads();
+    q.hist[blockIdx.x * 256 + threadIdx.x] = sm.hist[threadIdx.x];
+    __syncthreads();
+}
+
+// ---- one radix pass: offsets, stable in-tile ranking, scatter, next histogram --------------------------------------
+LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm) {
+    const SortGeom g = sort_geom(q.n);
+    if ((int)blockIdx.x >= g.nb) return;
+    const int src = (npass + 1 + pass) & 1, dst = src ^ 1;
+    const unsigned* __restrict__ skeys = q.keys[src];
+    const unsigned* __restrict__ svals = (pass == 0) ? nullptr : q.vals[src];      // pass 0: value = source index
+    unsigned* __restrict__ dkeys = q.keys[dst];
+    unsigned* __restrict__ dvals = q.vals[dst];
+    const int* __restrict__ hcur = q.hist + (pass % 3) * kHistStride;
+    int* __restrict__ hnext = (pass + 1 < npass) ? q.hist + ((pass + 1) % 3) * kHistStride : nullptr;
+    int* __restrict__ hzero = q.hist + ((pass + 2) % 3) * kHistStride;
+    const int shift = pass * 8;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // digit offsets of this block: all lower digits of every block + this digit of the blocks before
+    {
+        int pre = 0, tot = 0;
+        int b = 0;
+        for (; b + 4 <= g.nb; b += 4) {
+            const int v0 = hcur[(b + 0) * 256 + t], v1 = hcur[(b + 1) * 256 + t], v2 = hcur[(b + 2) * 256 + t], v3 = hcur[(b + 3) * 256 + t];
+            tot += v0 + v1 + v2 + v3;
+            pre += (b + 0 < (int)blockIdx.x ? v0 : 0) + (b + 1 < (int)blockIdx.x ? v1 : 0) + (b + 2 < (int)blockIdx.x ? v2 : 0) + (b + 3 < (int)blockIdx.x ? v3 : 0);
+        }
+        for (; b < g.nb; ++b) { const int v = hcur[b * 256 + t]; tot += v; if (b < (int)blockIdx.x) pre += v; }
+        int total;
+        const int excl = block_exclusive_scan_256(tot, &total);
+        sm.sort.offs[t] = excl + pre;
+#pragma unroll
+        for (int w = 0; w < kPipeThreads / 32; ++w) sm.sort.wcnt[w][t] = 0;
+    }
+    __syncthreads();
+    if (pass >= 1) hzero[blockIdx.x * 256 + t] = 0;            // free since the previous barrier; needed two passes on
+    const int lo = blockIdx.x * g.C, hi = min(q.n, lo + g.C);
+    for (int base = lo; base < hi; base += kSortTile) {
+        unsigned k[kSortRounds], v[kSortRounds];
+#pragma unroll
+        for (int r = 0; r < kSortRounds; ++r) {
+            const int i = base + r * kPipeThreads + t;
+            k[r] = 0u; v[r] = 0u;
+            if (i < hi) { k[r] = skeys[i]; v[r] = svals ? svals[i] : (unsigned)i; }
+        }
+#pragma unroll
+        for (int r = 0; r < kSortRounds; ++r) {
+            const int i = base + r * kPipeThreads + t;
+            const bool valid = i < hi;
+            const unsigned d = valid ? ((k[r] >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank == 0) sm.sort.wcnt[warp][d] = __popc(peers);
+            __syncthreads();
+            if (valid) {
+                int pos = sm.sort.offs[d] + rank;
+                for (int w = 0; w < warp; ++w) pos += sm.sort.wcnt[w][d];
+                dkeys[pos] = k[r];
+                dvals[pos] = v[r];
+                if (hnext) atomicAdd(&hnext[(pos / g.C) * 256 + ((k[r] >> (shift + 8)) & 255u)], 1);
+            }
+            __syncthreads();
+            int s = 0;
+#pragma unroll
+            for (int w = 0; w < kPipeThreads / 32; ++w) { s += sm.sort.wcnt[w][t]; sm.sort.wcnt[w][t] = 0; }
+            sm.sort.offs[t] += s;
+            __syncthreads();
+        }
+    }
+}
+
+// ---- R1: run heads per tile ---------------------------------------------------------------------------------------
+LILOC_DEV void pipe_run_count(const VgProb& q) {
+    const unsigned* __restrict__ skeys = q.keys[1];
+    const int n_tiles = (q.n + kRunTile - 1) / kRunTile;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int base = tile * kRunTile;
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < kRunPerThread; ++j) {
+            const int i = base + j * kPipeThreads + threadIdx.x;
+            if (i < q.n) c += (i == 0 || skeys[i] != skeys[i - 1]) ? 1 : 0;
+        }
+        const int total = block_sum_256(c);
+        if (threadIdx.x == 0) q.tile_counts[tile] = total;
+    }
+}
+
+// ---- R2: centroids (+ search-cell count) ----------------------------------------------------------------------------
+LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& sm) {
+    const unsigned* __restrict__ skeys = q.keys[1];
+    const unsigned* __restrict__ svals = q.vals[1];
+    const int n = q.n;
+    const int n_tiles = (n + kRunTile - 1) / kRunTile;
+    if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) *q.count = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int part = 0;
+        for (int u = threadIdx.x; u < tile; u += kPipeThreads) part += q.tile_counts[u];
+        const int tile_offset = block_sum_256(part);
+        const int base = tile * kRunTile;
+        const int cnt = min(kRunTile, n - base);
+#pragma unroll
+        for (int j = 0; j < kRunPerThread; ++j) {
+            const int l = j * kPipeThreads + threadIdx.x;
+            if (l < cnt) {
+                sm.run.key[l] = skeys[base + l];
+                sm.run.pt[l] = __ldg(&q.pts[svals[base + l]]);
+            }
+        }
+        if (threadIdx.x == 0) sm.run.prev = (base > 0) ? skeys[base - 1] : 0u;
+        __syncthreads();
+        const int l0 = threadIdx.x * kRunPerThread;
+        unsigned char head[kRunPerThread];
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < kRunPerThread; ++j) {
+            const int l = l0 + j;
+            bool h = false;
+            if (l < cnt) h = (l == 0) ? (base == 0 || sm.run.key[0] != sm.run.prev) : (sm.run.key[l] != sm.run.key[l - 1]);
+            head[j] = h ? 1 : 0;
+            c += head[j];
+        }
+        int total;
+        int rank = tile_offset + block_exclusive_scan_256(c, &total);
+        if (tile == n_tiles - 1 && threadIdx.x == 0) *q.count = tile_offset + total;
+#pragma unroll
+        for (int j = 0; j < kRunPerThread; ++j) {
+            if (!head[j]) continue;
+            const int l = l0 + j;
+            const unsigned key = sm.run.key[l];
+            float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+            int e = l;
+            do {
+                const float4 p = sm.run.pt[e];
+                sx += p.x; sy += p.y; sz += p.z; sw += p.w;
+                ++e;
+            } while (e < cnt && sm.run.key[e] == key);
+            int len = e - l;
+            if (e == cnt) {                              // run may continue in the next tile(s)
+                int gi = base + cnt;
+                while (gi < n && skeys[gi] == key) {
+                    const float4 p = __ldg(&q.pts[svals[gi]]);
+                    sx += p.x; sy += p.y; sz += p.z; sw += p.w;
+                    ++gi; ++len;
+                }
+            }
+            const float fc = (float)len;
+            const float4 o = make_float4(sx / fc, sy / fc, sz / fc, sw / fc);
+            q.out[rank] = o;
+            if (q.build_grid) {
+                const int cx = cell_coord(o.x, gp.inv_cell, gp.g0[0]);
+                const int cy = cell_coord(o.y, gp.inv_cell, gp.g0[1]);
+                const int cz = cell_coord(o.z, gp.inv_cell, gp.g0[2]);
+                atomicAdd(&q.cell_counts[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
+            }
+            ++rank;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- G1..G3: cell counts -> cell_start, points sorted by cell -----------------------------------------------------------
+LILOC_DEV void pipe_cells_reduce(const VgProb& q, const GridParams& gp) {
+    const int n = gp.ncells;
+    const int n_tiles = (n + kScanTile - 1) / kScanTile;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int base = tile * kScanTile;
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            const int i = base + j * kScanThreads + threadIdx.x;
+            if (i < n) c += q.cell_counts[i];
+        }
+        const int total = block_sum_256(c);
+        if (threadIdx.x == 0) q.grid_tiles[tile] = total;
+    }
+}
+
+LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp) {
+    const int n = gp.ncells;
+    const int n_tiles = (n + kScanTile - 1) / kScanTile;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int part = 0;
+        for (int u = threadIdx.x; u < tile; u += kPipeThreads) part += q.grid_tiles[u];
+        const int tile_offset = block_sum_256(part);
+        const int base = tile * kScanTile + threadIdx.x * kScanPerThread;
+        int v[kScanPerThread];
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? q.cell_counts[base + j] : 0; c += v[j]; }
+        int total;
+        int run = tile_offset + block_exclusive_scan_256(c, &total);
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            if (base + j < n) { q.cell_start[base + j] = run; q.cell_counts[base + j] = run; }
+            run += v[j];
+            if (base + j == n - 1) q.cell_start[n] = run;
+        }
+    }
+}
+
+LILOC_DEV void pipe_cells_scatter(const VgProb& q, const GridParams& gp) {
+    const int M = *q.count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float4 p = q.out[i];
+        const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
+        const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
+        const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
+        const int pos = atomicAdd(&q.cell_counts[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
+        q.cpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPipeThreads, 2) k_voxel_pipeline(const __grid_constant__ PipeArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) PipeSmem sm;
+    __shared__ VgParams s_vp[kMaxProbs];
+    __shared__ GridParams s_gp[kMaxProbs];
+    __shared__ int s_npass[kMaxProbs];
+    const int np = a.n_prob;
+    int mark = 0;
+#define PIPE_MARK() do { if (a.marks && blockIdx.x == 0 && threadIdx.x == 0 && mark < kPipeMarks) a.marks[mark] = global_ns(); ++mark; } while (0)
+    PIPE_MARK();                                                                          // 0 start
+    for (int p = 0; p < np; ++p) pipe_bbox(a.prob[p]);                                   // P0
+    grid.sync();
+    PIPE_MARK();                                                                          // 1 after assemble + bbox
+
+    if (threadIdx.x < np) {                                                               // P1
+        const VgProb& q = a.prob[threadIdx.x];
+        const VgParams vp = vg_params_compute(q.enc, q.leaf, q.n);
+        s_vp[threadIdx.x] = vp;
+        s_npass[threadIdx.x] = q.n > 0 ? (vp.key_bits + 7) / 8 : 0;
+        GridParams g{};
+        if (q.build_grid) g = grid_params_compute(vp.mn, vp.mx, q.n <= 0, q.max_cells);
+        s_gp[threadIdx.x] = g;
+        if (blockIdx.x == 0) { *q.vp = vp; if (q.build_grid) *q.gp = g; }
+    }
+    __syncthreads();
+    int max_pass = 0;
+    for (int p = 0; p < np; ++p) max_pass = max(max_pass, s_npass[p]);
+    for (int p = 0; p < np; ++p) if (a.prob[p].n > 0) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm);
+    grid.sync();
+    PIPE_MARK();                                                                          // 2 after keys
+
+    for (int pass = 0; pass < max_pass; ++pass) {                                         // radix passes
+        for (int p = 0; p < np; ++p) if (pass < s_npass[p]) pipe_sort_pass(a.prob[p], s_npass[p], pass, sm);
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 6 * np) {                                        // re-arm the bounding boxes
+        const int p = threadIdx.x / 6, w = threadIdx.x % 6;
+        a.prob[p].enc[w] = w < 3 ? 0xFFFFFFFFu : 0u;
+    }
+    PIPE_MARK();                                                                          // 3 after the sort
+    bool any_out = false, any_grid = false;
+    for (int p = 0; p < np; ++p) { any_out |= !a.prob[p].sort_only; any_grid |= a.prob[p].build_grid != 0; }
+    if (!any_out) return;
+
+    for (int p = 0; p < np; ++p) if (!a.prob[p].sort_only) pipe_run_count(a.prob[p]);     // R1
+    grid.sync();
+    PIPE_MARK();                                                                          // 4 after the run count
+    for (int p = 0; p < np; ++p) if (!a.prob[p].sort_only) pipe_centroids(a.prob[p], s_gp[p], sm);   // R2
+    if (!any_grid) { PIPE_MARK(); return; }                                               // 5 (block 0's own end)
+    grid.sync();
+    PIPE_MARK();                                                                          // 5 after the centroids
+    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_reduce(a.prob[p], s_gp[p]);    // G1
+    grid.sync();
+    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scan(a.prob[p], s_gp[p]);      // G2
+    grid.sync();
+    PIPE_MARK();                                                                          // 6 after the cell scan
+    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scatter(a.prob[p], s_gp[p]);   // G3
+    PIPE_MARK();                                                                          // 7 block 0's own end
+#undef PIPE_MARK
+}
+
+}  // namespace liloc

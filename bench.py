@@ -33,6 +33,9 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# --workload relo / jfgo / batch: BASELINE.json configs[3] / configs[4] (one scan vs K submaps) / configs[4] (offline batch
+# of (scan, submap, guess) triples) -- the relo-mode NDT registration, batched and sharded over the ranks.  The
+# default (lio, configs[1]) is what the driver runs; the others are run by hand and kept under profiles/.
 METRIC = "scan2map_registrations_per_s"
 UNIT = "registrations/s"
 YAML = "nclt.yaml"
@@ -267,6 +270,201 @@ def run_ours(args):
     m.close()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# relo-mode NDT workloads (BASELINE.json configs[3], configs[4])
+NDT_METRIC = "ndt_registrations_per_s"
+
+
+def make_ndt_workload(args):
+    """Targets (prior-session submaps: 10 consecutive un-down-sampled scans in the map frame, dataLoader.hpp:306-348),
+    sources (full de-skewed scans) and the (target, source, guess) item list.  Identical on every rank (seeded)."""
+    from liloc_b200 import synth, relo
+    import oracle_lib as orc            # only to transform clouds while building INPUTS
+    rng = np.random.default_rng(args.seed)
+    if args.workload == "relo":
+        world = synth.make_world(seed=args.seed)
+        traj = synth.trajectory_line(12, step=1.0, x0=-5)
+        sub = np.concatenate([orc.transform_cloud(synth.scan(world, traj[k], synth.VLP16, 30 + k), traj[k].astype(np.float32), threads=8) for k in range(10)])
+        src = synth.scan(world, traj[10], synth.VLP16, 77)
+        guesses = relo.hypothesis_grid(traj[10], 16, 16, 2.0, seed=args.seed)[: args.items or 256]
+        n = len(guesses)
+        return {"targets": {0: sub}, "sources": {0: src}, "tid": np.zeros(n, np.int64), "sid": np.zeros(n, np.int64), "guesses": guesses,
+                "n_align": 2, "round_robin": True,
+                "desc": f"configs[3]: relo NDT, {n} pose hypotheses (16 yaw x 16 xy) of one VLP-16 scan vs one prior submap, 2 x align each"}
+    n_sub = args.submaps
+    n_frames = n_sub * 10
+    seq = synth.make_sequence(synth.VLP16, n_frames, seed=args.seed, dt=0.1)
+    targets = {s: np.concatenate([orc.transform_cloud(seq.scans[10 * s + k], seq.truth[10 * s + k].astype(np.float32), threads=8) for k in range(10)])
+               for s in range(n_sub)}
+    if args.workload == "jfgo":
+        f = n_frames // 2 + 3
+        sources = {0: seq.scans[f]}
+        guesses, tid = [], []
+        for s in range(n_sub):                     # init = the submap's centre pose (its 5th keyframe) + noise
+            c = seq.truth[10 * s + 5].copy()
+            c[3:] += rng.normal(0, 0.2, 3); c[:3] += rng.normal(0, 0.01, 3)
+            guesses.append(relo.euler_to_matrix(*c)); tid.append(s)
+        return {"targets": targets, "sources": sources, "tid": np.array(tid), "sid": np.zeros(n_sub, np.int64), "guesses": np.stack(guesses),
+                "n_align": 1, "round_robin": True,
+                "desc": f"configs[4]a: JFGO scan-matching factors, one VLP-16 scan vs K={n_sub} prior submaps"}
+    n = args.items or 8000
+    fr = np.sort(rng.integers(0, n_frames, n))     # sorted by frame => by submap id: contiguous blocks reuse their grids
+    sources = {int(f): seq.scans[int(f)] for f in np.unique(fr)}
+    guesses = []
+    for f in fr:
+        c = seq.truth[f].copy()
+        c[3:] += rng.uniform(-0.3, 0.3, 3); c[:3] += rng.uniform(-0.02, 0.02, 3)
+        guesses.append(relo.euler_to_matrix(*c))
+    return {"targets": targets, "sources": sources, "tid": fr // 10, "sid": fr, "guesses": np.stack(guesses), "n_align": 1, "round_robin": False,
+            "desc": f"configs[4]b: offline batch of {n} (scan, submap, guess) triples over {n_sub} submaps / {len(sources)} scans"}
+
+
+def run_ndt(args):
+    import torch
+    import liloc_b200
+    from liloc_b200 import parallel, relo
+    rank, world, local = parallel.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- liloc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = make_ndt_workload(args)
+    n = len(w["guesses"])
+    mine = parallel.shard_round_robin(n, rank, world) if w["round_robin"] else np.arange(*parallel.shard_range(n, rank, world))
+    my_t = sorted(set(int(t) for t in w["tid"][mine])); my_s = sorted(set(int(x) for x in w["sid"][mine]))
+    opts = liloc_b200.NdtOpts(trans_eps=0.01, search=0, n_align=w["n_align"])
+    res = float(args.resolution)
+    ctx = liloc_b200.Context(device=local, max_scan_points=32 * 1800, max_raw_points=1 << 20)
+    pinned_t = {t: torch.from_numpy(np.ascontiguousarray(w["targets"][t])).pin_memory() for t in my_t}
+    pinned_s = {x: torch.from_numpy(np.ascontiguousarray(w["sources"][x])).pin_memory() for x in my_s}
+    h2d_t = sum(v.numel() * 4 for v in pinned_t.values()); h2d_s = sum(v.numel() * 4 for v in pinned_s.values())
+
+    def put_targets():
+        return [ctx.ndt_target_put(t, pinned_t[t].numpy(), res) for t in my_t]
+
+    def put_sources():
+        for x in my_s:
+            ctx.ndt_source_put(x, pinned_s[x].numpy())
+
+    def align():
+        return relo.align_sharded(ctx, w["tid"], w["sid"], w["guesses"], opts, dev, round_robin=w["round_robin"])
+
+    t0 = time.perf_counter(); leaves = put_targets(); torch.cuda.synchronize(); target_build_s = time.perf_counter() - t0
+    put_sources()
+    ctx.set_timing(True)
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ext = torch.cuda.ExternalStream(liloc_b200.lib.liloc_stream(ctx._h), device=dev)
+    for _ in range(args.warmup):
+        align()
+
+    def timed(e2e: bool):
+        parallel.barrier(); torch.cuda.synchronize()
+        ctx.ndt_stats(reset=True)
+        sampler = ClockSampler(local); sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tt, rows, loc = 0.0, None, None
+        ev0.record(ext)
+        for _ in range(args.steps):
+            l2_flush.fill_(1); torch.cuda.synchronize(); parallel.barrier()
+            t0 = time.perf_counter()
+            if e2e:                                  # what a relo frame pays: target grid + scan upload + align + results back
+                put_targets(); put_sources()
+            rows, loc = align()
+            torch.cuda.synchronize()
+            tt += time.perf_counter() - t0
+        ev1.record(ext); torch.cuda.synchronize(); parallel.barrier()
+        return tt, rows, loc, ctx.ndt_stats(), sampler.finish(), ev0.elapsed_time(ev1) * 1e-3
+
+    t_dev, rows, loc, st, clocks, ev_dev = timed(False)
+    t_e2e, rows2, _, st2, _, ev_e2e = timed(True)
+    assert np.array_equal(rows, rows2)               # same work, same answers
+    t_dev_max = parallel.max_over_ranks(t_dev, dev); t_e2e_max = parallel.max_over_ranks(t_e2e, dev)
+    sweep_ms = parallel.max_over_ranks(st["sweep_ms"], dev)
+    alg = parallel.sum_over_ranks(st["alg_bytes"], dev); launches = parallel.sum_over_ranks(st["sweep_launches"], dev)
+    job_sweeps = parallel.sum_over_ranks(st["job_sweeps"], dev)
+    if rank != 0:
+        ctx.close(); return
+    peak, peak_src = load_peaks()
+    value, e2e = n * args.steps / t_dev_max, n * args.steps / t_e2e_max
+    # roofline of k_ndt_sweep: algorithmic bytes of this rank's launches / their CUDA-event time
+    ach = st["alg_bytes"] / (st["sweep_ms"] * 1e-3) / 1e9 if st["sweep_ms"] > 0 else None
+    truth_hits = None
+    cpu = cpu_baseline_ndt(w, args) if (world == 1 and not args.no_cpu) else None
+    out = {
+        "metric": NDT_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_dev_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "items": n, "resolution": res, "search": "DIRECT1", "n_align": w["n_align"], "seed": args.seed,
+                   "sharding": ("round-robin" if w["round_robin"] else "contiguous blocks") + " over ranks, no data-path collective; one all-gather of 8 floats per item",
+                   "l2": "flushed (256 MiB fill) before every step", "timer": "host clock bracketed by device synchronisation, max over ranks; CUDA-event cross-check in device_s",
+                   "sizes": {"target_points": int(np.mean([len(v) for v in w["targets"].values()])), "source_points": int(np.mean([len(v) for v in w["sources"].values()])),
+                             "targets_rank0": len(my_t), "sources_rank0": len(my_s), "leaves": int(np.mean(leaves)) if leaves else 0,
+                             "sweeps_per_item": job_sweeps / max(n * args.steps, 1), "iterations_per_item": float(np.mean(rows[:, 7]))},
+                   "target_build_s_rank0": target_build_s},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": float(h2d_t + h2d_s + n * 72), "d2h_bytes_per_step": float(n * 152),
+                "note": "per step every rank re-uploads and rebuilds its target grids and re-uploads its scans (what a relo frame pays once per submap / scan)"},
+        "gpu_launches": int(launches),
+        "device_s": {"value_pass": ev_dev, "e2e_pass": ev_e2e},
+        "roofline": {"bound": "hbm", "kernel": "k_ndt_align, derivative-sweep phases (persistent cooperative kernel: one launch per batch)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                     "avg_sweep_phase_us": st["sweep_ms"] * 1e3 / max(st["sweep_phases"], 1), "sweep_phases_per_step": st["sweep_phases"] / args.steps,
+                     "sweep_share_of_step": sweep_ms * 1e-3 / t_dev_max,
+                     "alg_bytes_per_step_all_ranks": alg / args.steps,
+                     "note": "algorithmic bytes = sweeps x (16 P + 36 P c + 224) per job (SURVEY 8d); the leaf gather is served by L2, the per-point math is float with double accumulation"},
+        "cpu_baseline": cpu, "clocks": clocks, "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(out))
+    ctx.close()
+
+
+def cpu_baseline_ndt(w, args, max_items=None, budget_s=None):
+    """The reference's CPU path for the same items (oracle restatement of ndt_omp, OpenMP on all host cores), faithful
+    to its redundancy: setInputTarget rebuilds the voxel grid for every align call site (anchorOptimize.hpp:394)."""
+    import oracle_lib as orc
+    threads = orc.num_threads()
+    budget = budget_s if budget_s is not None else args.cpu_budget
+    n = len(w["guesses"])
+    pick = np.linspace(0, n - 1, min(n, max_items or 64)).astype(int)
+    o = orc.NdtOpts(resolution=float(args.resolution), trans_eps=0.01, search=0, threads=threads)
+    t0, done = time.perf_counter(), 0
+    for i in pick:
+        tg = orc.NdtTarget(w["targets"][int(w["tid"][i])], np.float32(args.resolution))        # setInputTarget
+        T = w["guesses"][i][:3]
+        for _ in range(w["n_align"]):
+            T, _ = orc.ndt_align(tg, w["sources"][int(w["sid"][i])], T, o)
+        done += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{done} of the {n} items, evenly spaced ({dt:.1f} s); each = voxel-grid build + {w['n_align']} x align"}
+
+
+def run_ndt_reference(args):
+    from liloc_b200 import parallel
+    rank, world, _ = parallel.env_world()
+    if rank != 0:
+        return
+    w = make_ndt_workload(args)
+    lat = []
+    per_step = max(1, args.ref_frames // 5)
+    for _ in range(args.warmup):
+        cpu_baseline_ndt(w, args, max_items=1, budget_s=1e9)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c = cpu_baseline_ndt(w, args, max_items=per_step, budget_s=1e9)
+        lat.append(c)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    print(json.dumps({
+        "impl": "reference", "metric": NDT_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "items_per_step": per_step, "resolution": float(args.resolution)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": lat[-1]["cores"], "kind": "port", "sample": f"{per_step} evenly spaced items per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "host": {"nproc": os.cpu_count()},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -279,10 +477,19 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=300, help="cpu_baseline: at most this many frames")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="cpu_baseline: seconds of CPU work")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", choices=["lio", "relo", "jfgo", "batch"], default="lio",
+                    help="lio = configs[1] (default, headline); relo = configs[3]; jfgo / batch = configs[4]")
+    ap.add_argument("--items", type=int, default=0, help="relo: hypotheses (256); batch: triples (8000)")
+    ap.add_argument("--submaps", type=int, default=64, help="jfgo / batch: prior submaps (10 keyframes each)")
+    ap.add_argument("--resolution", type=float, default=1.0, help="ndtResolution (lio_sam_default.yaml: 1.0)")
     args = ap.parse_args()
     if args.warmup < 3 and not os.environ.get("LILOC_BENCH_QUICK"):
         args.warmup = 3          # timing rule: at least 3 warm-up steps (LILOC_BENCH_QUICK=1 lifts it for profiler runs)
-    if args.impl == "reference":
+    if args.workload != "lio":
+        if args.seed == 2000:
+            args.seed = {"relo": 4000, "jfgo": 5000, "batch": 5001}[args.workload]
+        (run_ndt_reference if args.impl == "reference" else run_ndt)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -181,6 +181,17 @@ int liloc_ndt_target_get(liloc_ctx* ctx, int target_id, double* means, float* ic
 /* one derivative sweep at pose p6 = [tx,ty,tz,rx,ry,rz] (tests): out28 = score, gradient[6], Hessian upper[21] */
 int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const double* p6, const liloc_ndt_opts* opts, double* out28);
 
+/* Cumulative NDT counters since liloc_create / liloc_ndt_stats_reset.  A batch is ONE launch of the persistent
+ * kernel k_ndt_align; sweep_phases counts its lock-step derivative sweeps, sweep_ms their device time (%globaltimer
+ * around each sweep phase incl. its grid barrier, recorded only while timing is enabled); alg_bytes are the
+ * ALGORITHMIC bytes of SURVEY.md 8(d): per derivative sweep and job 16 P + 36 P c + 224 (P source points, c cells). */
+typedef struct {
+    long long batches, jobs, sweep_launches, sweep_phases, job_sweeps;
+    double sweep_ms, alg_bytes;
+} liloc_ndt_stats;
+int liloc_ndt_stats_get(const liloc_ctx* ctx, liloc_ndt_stats* out);
+int liloc_ndt_stats_reset(liloc_ctx* ctx);
+
 /* ---- kernel-level entry points (used by the parity tests; no reference caller) ------------------ */
 /* pcl::VoxelGrid<PointXYZI>::filter on a host cloud -> host cloud (cap >= n). */
 int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, liloc_point* out, int cap, int* m_out);
@@ -213,6 +224,12 @@ int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int 
 typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t);
 int liloc_set_timing(liloc_ctx* ctx, int enabled);
+/* Device-side latency breakdown of the last liloc_frame / liloc_frame_features made while timing is enabled:
+ * %globaltimer nanoseconds written by block 0 at the phase boundaries of the three launches --
+ * [0..15] local-map pipeline (start, assemble+bbox, keys, sort, run count, centroids, cell scan, end),
+ * [16..31] scan pipeline (same phases), [32] registration start, then per iteration i: [33+3i] tiles done,
+ * [34+3i] past the grid barrier, [35+3i] pose updated.  Returns the number of entries copied. */
+int liloc_last_marks(liloc_ctx* ctx, unsigned long long* out, int cap);
 /* Cumulative counters since liloc_create / liloc_stats_reset.  Phase times are CUDA-event milliseconds
  * summed over liloc_frame calls made while timing is enabled; alg_bytes_* are the ALGORITHMIC bytes of
  * assemble+map VoxelGrid 16 N_raw + 16 M, scan VoxelGrid 16 N_scan + 16 Q_all,

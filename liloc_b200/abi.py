@@ -92,6 +92,11 @@ class NdtOpts(C.Structure):
         super().__init__(step_size, outlier_ratio, float(np.float32(trans_eps)), max_iterations, search, n_align, 0)
 
 
+class NdtStats(C.Structure):
+    _fields_ = [(k, C.c_longlong) for k in ("batches", "jobs", "sweep_launches", "sweep_phases", "job_sweeps")] + \
+               [(k, C.c_double) for k in ("sweep_ms", "alg_bytes")]
+
+
 class NdtJob(C.Structure):
     _fields_ = [("target_id", C.c_int), ("source_id", C.c_int), ("guess", C.c_float * 16)]
 
@@ -99,6 +104,12 @@ class NdtJob(C.Structure):
 class NdtOut(C.Structure):
     _fields_ = [("T", C.c_float * 16), ("score", C.c_double), ("iterations", C.c_int), ("converged", C.c_int),
                 ("sweeps", C.c_int), ("n_source", C.c_int)]
+
+
+_NDT_JOB_DT = np.dtype([("target_id", np.int32), ("source_id", np.int32), ("guess", np.float32, 16)])
+_NDT_OUT_DT = np.dtype([("T", np.float32, 16), ("score", np.float64), ("iterations", np.int32), ("converged", np.int32),
+                        ("sweeps", np.int32), ("n_source", np.int32)], align=True)
+assert _NDT_JOB_DT.itemsize == C.sizeof(NdtJob) and _NDT_OUT_DT.itemsize == C.sizeof(NdtOut)
 
 
 def _load() -> C.CDLL:
@@ -159,6 +170,9 @@ def _load() -> C.CDLL:
         "liloc_knn5_class": (C.c_int, [P, C.c_int, P, C.c_int, P, P, P]),
         "liloc_feature_pass": (C.c_int, [P, C.c_int, P, C.c_int, P, P]),
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
+        "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
+        "liloc_ndt_stats_get": (C.c_int, [P, C.POINTER(NdtStats)]),
+        "liloc_ndt_stats_reset": (C.c_int, [P]),
         "liloc_debug_line": (C.c_int, [P, P, P, C.c_int, P, P]),
     }
     for name, (res, args) in sig.items():
@@ -175,7 +189,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -396,6 +410,13 @@ class Context:
             p = _cloud(pts_body)
             self._chk(lib.liloc_ndt_source_put(self._h, source_id, _ptr(p), len(p), 0))
 
+    def ndt_stats(self, reset: bool = False) -> dict:
+        st = NdtStats()
+        lib.liloc_ndt_stats_get(self._h, C.byref(st))
+        if reset:
+            lib.liloc_ndt_stats_reset(self._h)
+        return {k: getattr(st, k) for k, _ in NdtStats._fields_}
+
     def ndt_clear(self) -> None:
         self._chk(lib.liloc_ndt_clear(self._h))
 
@@ -403,18 +424,17 @@ class Context:
         """guesses: (J, 4, 4) or (J, 3, 4) float32 row-major.  Returns (T (J,4,4), score, iterations, converged, sweeps)."""
         g = np.asarray(guesses, np.float32)
         J = len(g)
-        jobs = (NdtJob * J)()
-        for j in range(J):
-            jobs[j].target_id, jobs[j].source_id = int(target_ids[j]), int(source_ids[j])
-            m = np.eye(4, dtype=np.float32)
-            m[: g[j].shape[0], :] = g[j]
-            jobs[j].guess[:] = m.reshape(16).tolist()
-        outs = (NdtOut * J)()
+        jobs = np.zeros(J, _NDT_JOB_DT)                      # same layout as liloc_ndt_job (checked at import)
+        jobs["target_id"] = np.asarray(target_ids, np.int32)
+        jobs["source_id"] = np.asarray(source_ids, np.int32)
+        m = np.tile(np.eye(4, dtype=np.float32), (J, 1, 1))
+        m[:, : g.shape[1], :] = g
+        jobs["guess"] = m.reshape(J, 16)
+        outs = np.zeros(J, _NDT_OUT_DT)
         o = opts or NdtOpts()
-        self._chk(lib.liloc_ndt_align_batch(self._h, jobs, J, C.byref(o), outs))
-        T = np.array([list(r.T) for r in outs], np.float32).reshape(J, 4, 4)
-        return (T, np.array([r.score for r in outs]), np.array([r.iterations for r in outs]),
-                np.array([r.converged for r in outs]), np.array([r.sweeps for r in outs]))
+        self._chk(lib.liloc_ndt_align_batch(self._h, C.cast(jobs.ctypes.data, C.POINTER(NdtJob)), J, C.byref(o),
+                                            C.cast(outs.ctypes.data, C.POINTER(NdtOut))))
+        return (outs["T"].reshape(J, 4, 4).copy(), outs["score"].copy(), outs["iterations"].copy(), outs["converged"].copy(), outs["sweeps"].copy())
 
     def ndt_target_get(self, target_id: int):
         n = lib.liloc_ndt_target_get(self._h, target_id, None, None, None, None, 0)
@@ -458,6 +478,12 @@ class Context:
     def last_trace(self, iters: int = 32) -> np.ndarray:
         out = np.zeros((32, 16), np.float32)
         n = lib.liloc_last_trace(self._h, _ptr(out), iters)
+        return out[:n]
+
+    def last_marks(self) -> np.ndarray:
+        """%globaltimer marks of the last timed frame (see include/liloc_gpu.h liloc_last_marks)."""
+        out = np.zeros(2 * 16 + 1 + 3 * 32, np.uint64)
+        n = lib.liloc_last_marks(self._h, _ptr(out), len(out))
         return out[:n]
 
     def last_clocks(self, iters: int = 32) -> np.ndarray:

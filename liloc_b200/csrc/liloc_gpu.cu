@@ -88,7 +88,7 @@ struct HostClassInfo { VgParams map_vp, scan_vp; GridParams gp; int M, Q_all; };
 struct HostFrameInfo {     // pinned, written by async D2H
     HostClassInfo c[kClasses];
     S2mResult res;
-    unsigned long long marks[2 * kPipeMarks];
+    unsigned long long marks[2 * kPipeMarks + kS2mMarks];
     int scratch;
 };
 
@@ -123,7 +123,7 @@ struct liloc_ctx {
     S2mResult* d_result = nullptr;
     int s2m_max_blocks = 0;
     int pipe_blocks = 0;                 // blocks of one point-cloud pipeline launch (one per SM: two launches co-reside)
-    unsigned long long* d_marks = nullptr;   // 2 x kPipeMarks phase timestamps (maps launch, scans launch)
+    unsigned long long* d_marks = nullptr;   // 2 x kPipeMarks phase timestamps (maps launch, scans launch) + kS2mMarks
     int s2m_nq_last = 0;
     int s2m_nq_corner_last = 0;
 
@@ -138,6 +138,11 @@ struct liloc_ctx {
     DevBuf<double> ndt_partial;
     int* d_ndt_active = nullptr;
     bool ndt_views_dirty = true;
+    liloc_ndt_stats ndt_stats{};
+    DevBuf<int> ndt_active;
+    int* d_ndt_counters = nullptr;       // 3 ints
+    unsigned long long* d_ndt_ns = nullptr;
+    int ndt_max_blocks = 0;
 
     // kernel-level test scratch
     DevBuf<float4> tmp_pts;
@@ -411,6 +416,7 @@ int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     ctx->stats.h2d_bytes += 24;
     a.partial = ctx->partial.p; a.pose_io = ctx->d_pose;
     a.state = ctx->d_state[ctx->state_cur]; a.state_out = ctx->d_state[ctx->state_cur ^ 1]; a.result = ctx->d_result;
+    a.marks = ctx->timing ? ctx->d_marks + 2 * kPipeMarks : nullptr;
     void* args[] = {&a};
     CU(cudaLaunchCooperativeKernel((void*)k_scan2map, dim3((unsigned)blocks), dim3(kS2mThreads), args, 0, ctx->stream));
     ++ctx->launches;
@@ -503,8 +509,13 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_pipeline, kPipeThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_voxel_pipeline cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->pipe_blocks = c->num_sms;
-    CUB_(cudaMalloc(&c->d_marks, 2 * kPipeMarks * sizeof(unsigned long long)));
-    CUB_(cudaMemset(c->d_marks, 0, 2 * kPipeMarks * sizeof(unsigned long long)));
+    CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ndt_align, kNdtThreads, 0));
+    if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_ndt_align cannot be resident"); return bail(LILOC_ERR_CUDA); }
+    c->ndt_max_blocks = per_sm * c->num_sms;
+    CUB_(cudaMalloc(&c->d_ndt_counters, 3 * sizeof(int)));
+    CUB_(cudaMalloc(&c->d_ndt_ns, sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_marks, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
+    CUB_(cudaMemset(c->d_marks, 0, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
 #undef CUB_
     const int scan_cap = cfg->max_scan_points > 0 ? cfg->max_scan_points : 16 * 1800;
     const int raw_cap = cfg->max_raw_points > 0 ? cfg->max_raw_points : (1 << 20);
@@ -547,6 +558,7 @@ void liloc_destroy(liloc_ctx* c) {
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
     fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
+    fr(c->ndt_active.p); fr(c->d_ndt_counters); fr(c->d_ndt_ns);
     if (c->h_info) cudaFreeHost(c->h_info);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {c->stream2, c->stream3, c->stream}) if (st) cudaStreamDestroy(st);
@@ -1098,31 +1110,47 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
         if (si->second.view.n > max_n) max_n = si->second.view.n;
     }
     const NdtOptsDev od = ndt_opts_dev(o, resolution);
-    const int tiles = (max_n + kNdtThreads - 1) / kNdtThreads;
+    const int tiles = (max_n + kNdtTile - 1) / kNdtTile;
     if ((rc = ensure(ctx, ctx->d_jobs, (size_t)n_jobs))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_partial, (size_t)n_jobs * tiles * kNdtSums))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_active, (size_t)2 * n_jobs))) return rc;
     CU(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
-    k_ndt_begin<<<(n_jobs + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_jobs.p, n_jobs); KCHECK();
+    CU(cudaMemsetAsync(ctx->d_ndt_ns, 0, sizeof(unsigned long long), ctx->stream));
+    NdtAlignArgs aa{};
+    aa.jobs = ctx->d_jobs.p; aa.n_jobs = n_jobs; aa.targets = ctx->d_tviews.p; aa.sources = ctx->d_sviews.p; aa.o = od;
+    aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.active = ctx->ndt_active.p; aa.counters = ctx->d_ndt_counters;
+    aa.sweep_ns = ctx->timing ? ctx->d_ndt_ns : nullptr;
     // worst case per align pass: first sweep + (max_iterations + 2) x (1 + 10) line-search sweeps
-    const int max_sweeps = od.n_align * (1 + (od.max_iterations + 2) * 11);
-    const int check_every = 4;
-    int* h_active = &ctx->h_info->scratch;                   // pinned scratch int
-    int done_sweeps = 0;
-    while (done_sweeps < max_sweeps) {
-        for (int k = 0; k < check_every; ++k) {
-            k_ndt_sweep<<<dim3(tiles, n_jobs), kNdtThreads, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_tviews.p, ctx->d_sviews.p, od, tiles, ctx->ndt_partial.p); KCHECK();
-            CU(cudaMemsetAsync(ctx->d_ndt_active, 0, sizeof(int), ctx->stream));
-            k_ndt_update<<<n_jobs, 32, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_sviews.p, od, tiles, ctx->ndt_partial.p, ctx->d_ndt_active); KCHECK();
-            ++done_sweeps;
-        }
-        CU(cudaMemcpyAsync(h_active, ctx->d_ndt_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (*h_active == 0) break;
+    aa.max_sweeps = od.n_align * (1 + (od.max_iterations + 2) * 11);
+    {
+        long long work = (long long)n_jobs * tiles;
+        long long blocks = work < ctx->ndt_max_blocks ? work : ctx->ndt_max_blocks;
+        if (blocks < 1) blocks = 1;
+        void* args[] = {&aa};
+        CU(cudaLaunchCooperativeKernel((void*)k_ndt_align, dim3((unsigned)blocks), dim3(kNdtThreads), args, 0, ctx->stream));
+        ++ctx->launches;
     }
+    int h_counters[3] = {0, 0, 0};
+    unsigned long long h_ns = 0;
+    CU(cudaMemcpyAsync(h_counters, ctx->d_ndt_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&h_ns, ctx->d_ndt_ns, sizeof(h_ns), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(hj.data(), ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
+    {
+        liloc_ndt_stats& ns = ctx->ndt_stats;
+        ns.batches += 1; ns.jobs += n_jobs; ns.sweep_launches += 1; ns.sweep_phases += h_counters[2];
+        ns.sweep_ms += (double)h_ns * 1e-6;
+        const int cells = od.search7 ? 7 : 1;
+        for (int j = 0; j < n_jobs; ++j) {
+            const double P = (double)ctx->ndt_sources[jobs[j].source_id].view.n;
+            ns.job_sweeps += hj[j].total_sweeps;
+            // per sweep and job, the scan once (16 P), a (mean, inverse covariance) gather per point and
+            // cell (36 P c) and 28 doubles out
+            ns.alg_bytes += (double)hj[j].total_sweeps * (16.0 * P + 36.0 * P * cells + 224.0);
+        }
+    }
     for (int j = 0; j < n_jobs; ++j) {
         liloc_ndt_out& r = outs[j];
         std::memcpy(r.T, hj[j].Tfinal, 12 * sizeof(float));
@@ -1164,11 +1192,11 @@ int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const do
     J.target = ti->second.slot; J.source = si->second.slot; J.phase = NDT_AWAIT_FIRST;
     for (int i = 0; i < 6; ++i) { J.p[i] = p6[i]; J.x_t[i] = p6[i]; }
     const NdtOptsDev od = ndt_opts_dev(o, ti->second.resolution);
-    const int n = si->second.view.n, tiles = (n + kNdtThreads - 1) / kNdtThreads;
+    const int n = si->second.view.n, tiles = (n + kNdtTile - 1) / kNdtTile;
     if ((rc = ensure(ctx, ctx->d_jobs, 1))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_partial, (size_t)tiles * kNdtSums))) return rc;
     CU(cudaMemcpyAsync(ctx->d_jobs.p, &J, sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
-    k_ndt_sweep<<<dim3(tiles, 1), kNdtThreads, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_tviews.p, ctx->d_sviews.p, od, tiles, ctx->ndt_partial.p); KCHECK();
+    k_ndt_sweep<<<tiles, kNdtThreads, 0, ctx->stream>>>(ctx->d_jobs.p, ctx->d_tviews.p, ctx->d_sviews.p, od, ctx->ndt_partial.p); KCHECK();
     std::vector<double> part((size_t)tiles * kNdtSums);
     CU(cudaMemcpyAsync(part.data(), ctx->ndt_partial.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1179,6 +1207,25 @@ int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const do
 }  // extern "C"
 
 extern "C" {
+
+int liloc_ndt_stats_get(const liloc_ctx* ctx, liloc_ndt_stats* out) {
+    if (!ctx || !out) return LILOC_ERR_ARG;
+    *out = ctx->ndt_stats;
+    return LILOC_OK;
+}
+
+int liloc_ndt_stats_reset(liloc_ctx* ctx) {
+    if (!ctx) return LILOC_ERR_ARG;
+    ctx->ndt_stats = liloc_ndt_stats{};
+    return LILOC_OK;
+}
+
+int liloc_last_marks(liloc_ctx* ctx, unsigned long long* out, int cap) {
+    if (!ctx || !out || cap < 0) return LILOC_ERR_ARG;
+    const int n = cap < 2 * kPipeMarks + kS2mMarks ? cap : 2 * kPipeMarks + kS2mMarks;
+    std::memcpy(out, ctx->h_info->marks, (size_t)n * sizeof(unsigned long long));
+    return n;
+}
 
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t) {
     if (!ctx || !t) return LILOC_ERR_ARG;

@@ -12,17 +12,20 @@
 // relocalisation (cfg 4) and the multi-submap JFGO matching (cfg 5) batch over.
 //
 // Kernels:  k_ndt_leaves   voxel runs -> Gaussian leaf records (sequential double sums in source order)
-//           k_ndt_sweep    one derivative sweep (score, gradient 6, Hessian 21) for every active job:
-//                          block = 256 points of one job, float per-point terms, double accumulation,
-//                          warp-shuffle + shared-memory reduction -> one partial per block
-//           k_ndt_update   per job: fixed-order reduction of the partials, then ONE step of the Newton /
-//                          More-Thuente state machine (all in double on the device; the host only polls
-//                          the number of unfinished jobs every few sweeps)
+//           k_ndt_align    the whole batch as one persistent cooperative kernel: derivative sweeps (score, gradient 6,
+//                          Hessian 21; a tile = 1024 points of one job, float per-point terms, double
+//                          accumulation, one shuffle + shared-memory reduction per tile), then per job a
+//                          fixed-order reduction of the tile partials and ONE step of the Newton / More-Thuente
+//                          state machine (double), then compaction of the unfinished-job list; no host polling
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "voxelgrid.cuh"
+#include "pipeline.cuh"
 
 namespace liloc {
+
+namespace cg = cooperative_groups;
 
 struct NdtLeaf { double mean[3]; float icov[9]; int n; int pad; };   // 64 bytes
 
@@ -54,6 +57,8 @@ struct NdtJob {
 };
 
 constexpr int kNdtThreads = 256;
+constexpr int kNdtPPT = 4;                            // source points per thread and tile
+constexpr int kNdtTile = kNdtThreads * kNdtPPT;       // 1024 source points per tile
 constexpr int kNdtSums = 28;      // score, gradient[6], Hessian upper triangle[21]
 
 // ---- small dense algebra in double, static indices only -------------------------------------------------
@@ -329,31 +334,28 @@ LILOC_DEV void ndt_point_cell(const float (&x)[3], const float (&xt)[3], const N
 
 struct NdtSweepShared { float T[12]; NdtAng ang; double red[kNdtThreads / 32][kNdtSums]; };
 
-// grid = (point tiles, jobs).  partial[(job * tiles_max + tile) * 28 + k]
-__global__ void __launch_bounds__(kNdtThreads)
-k_ndt_sweep(const NdtJob* __restrict__ jobs, const NdtTargetView* __restrict__ targets, const NdtSourceView* __restrict__ sources,
-            NdtOptsDev o, int tiles_max, double* __restrict__ partial) {
-    const int job = blockIdx.y;
-    const NdtJob& J = jobs[job];
-    if (J.phase == NDT_DONE) return;
-    const NdtSourceView src = sources[J.source];
-    const int base = blockIdx.x * kNdtThreads;
-    if (base >= src.n) return;
-    __shared__ NdtSweepShared sh;
+// One tile (kNdtTile source points, kNdtPPT per thread) of one derivative sweep of job J at J.x_t: float per-point
+// terms, double accumulation in registers over the thread's points, then ONE warp-shuffle + shared-memory
+// reduction per tile -> 28 doubles at `out`.  All threads of the block call this together.
+LILOC_DEV void ndt_sweep_tile(const NdtJob& J, const NdtTargetView& tg, const NdtSourceView& src, const NdtOptsDev& o,
+                              const int tile, NdtSweepShared& sh, double* __restrict__ out) {
+    __syncthreads();                                      // sh may still be read by the previous tile's tail
     if (threadIdx.x == 0) { ndt_pose_to_matrix(J.x_t, sh.T); ndt_angle_derivatives(J.x_t, &sh.ang); }
     __syncthreads();
-    const NdtTargetView tg = targets[J.target];
     double acc[kNdtSums];
 #pragma unroll
     for (int k = 0; k < kNdtSums; ++k) acc[k] = 0.0;
-    const int i = base + threadIdx.x;
-    if (i < src.n) {
+    const int base = tile * kNdtTile;
+    const int ncell = o.search7 ? 7 : 1;
+#pragma unroll 1
+    for (int r = 0; r < kNdtPPT; ++r) {
+        const int i = base + r * kNdtThreads + threadIdx.x;
+        if (i >= src.n) break;
         const float4 p = __ldg(&src.pts[i]);
         const float x[3] = {p.x, p.y, p.z};
         const float xt[3] = {sh.T[0] * p.x + sh.T[1] * p.y + sh.T[2] * p.z + sh.T[3],
                              sh.T[4] * p.x + sh.T[5] * p.y + sh.T[6] * p.z + sh.T[7],
                              sh.T[8] * p.x + sh.T[9] * p.y + sh.T[10] * p.z + sh.T[11]};
-        const int ncell = o.search7 ? 7 : 1;
         for (int c = 0; c < ncell; ++c) {
             // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
             const int dx = (c == 1) - (c == 2), dy = (c == 3) - (c == 4), dz = (c == 5) - (c == 6);
@@ -374,8 +376,17 @@ k_ndt_sweep(const NdtJob* __restrict__ jobs, const NdtTargetView* __restrict__ t
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kNdtThreads / 32; ++w) v += sh.red[w][threadIdx.x];
-        partial[((size_t)job * tiles_max + blockIdx.x) * kNdtSums + threadIdx.x] = v;
+        out[threadIdx.x] = v;
     }
+}
+
+// Stand-alone sweep of ONE job (liloc_ndt_derivatives, parity tests): grid = point tiles.
+__global__ void __launch_bounds__(kNdtThreads)
+k_ndt_sweep(const NdtJob* __restrict__ jobs, const NdtTargetView* __restrict__ targets, const NdtSourceView* __restrict__ sources,
+            NdtOptsDev o, double* __restrict__ partial) {
+    __shared__ NdtSweepShared sh;
+    const NdtJob& J = jobs[0];
+    ndt_sweep_tile(J, targets[J.target], sources[J.source], o, blockIdx.x, sh, partial + (size_t)blockIdx.x * kNdtSums);
 }
 
 // ---- More-Thuente helpers ------------------------------------------------------------------------------------
@@ -411,8 +422,40 @@ LILOC_DEV double ndt_trial_value(double a_l, double f_l, double g_l, double a_u,
     return a_u + (a_t - a_u) * (w - g_u - z) / (g_t - g_u + 2 * w);
 }
 
-// JacobiSVD(H).solve(-g) for the symmetrised Hessian (upper triangle Hup[21])
+// JacobiSVD(H).solve(-g) for the symmetrised Hessian (upper triangle Hup[21]).
+// Fast path: when H is well conditioned the minimum-norm solution IS H^-1 (-g), so it is computed by Gaussian
+// elimination with partial pivoting in double (pivot ratio > 1e-10; agrees with the SVD solution to ~1e-6 of the
+// tolerance the line search works at).  Otherwise the Jacobi eigen-decomposition gives the pseudo-inverse exactly
+// as JacobiSVD would: directions whose singular value is below 6 eps smax are dropped.
 LILOC_DEV void ndt_newton_solve(const double* Hup, const double* g, double* dp) {
+    {
+        double M[6][7];
+        int k = 0;
+        for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { M[i][j] = Hup[k]; M[j][i] = Hup[k]; ++k; }
+        for (int i = 0; i < 6; ++i) M[i][6] = -g[i];
+        double pmin = 1e300, pmax = 0.0;
+        bool ok = true;
+        for (int c = 0; c < 6 && ok; ++c) {
+            int pr = c; double best = fabs(M[c][c]);
+            for (int r = c + 1; r < 6; ++r) { const double v = fabs(M[r][c]); if (v > best) { best = v; pr = r; } }
+            if (!(best > 0.0) || best != best) { ok = false; break; }
+            if (pr != c) for (int j = c; j < 7; ++j) { const double t = M[c][j]; M[c][j] = M[pr][j]; M[pr][j] = t; }
+            pmin = fmin(pmin, best); pmax = fmax(pmax, best);
+            const double inv = 1.0 / M[c][c];
+            for (int r = c + 1; r < 6; ++r) {
+                const double f = M[r][c] * inv;
+                for (int j = c + 1; j < 7; ++j) M[r][j] -= f * M[c][j];
+            }
+        }
+        if (ok && pmin > 1e-10 * pmax) {
+            for (int i = 5; i >= 0; --i) {
+                double v = M[i][6];
+                for (int j = i + 1; j < 6; ++j) v -= M[i][j] * dp[j];
+                dp[i] = v / M[i][i];
+            }
+            return;
+        }
+    }
     double A[6][6], U[6][6];
     int k = 0;
 #pragma unroll
@@ -439,7 +482,7 @@ LILOC_DEV void ndt_newton_solve(const double* Hup, const double* g, double* dp) 
 }
 
 // One step of computeTransformation / computeStepLengthMT given the sums of the sweep at J.x_t.
-LILOC_DEV void ndt_job_step(NdtJob& J, const double* sums, const NdtOptsDev& o) {
+__device__ __noinline__ void ndt_job_step(NdtJob& J, const double* sums, const NdtOptsDev& o) {
     const double mu = 1.e-4, nu = 0.9;
     ++J.sweeps;
     J.score = sums[0];
@@ -529,44 +572,125 @@ LILOC_DEV void ndt_job_begin(NdtJob& J, const float* guess12) {
     J.nr_iterations = 0; J.converged = 0; J.sweeps = 0; J.step_iterations = 0; J.open_interval = 1; J.interval_converged = 0;
 }
 
-__global__ void k_ndt_begin(NdtJob* __restrict__ jobs, int n_jobs) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_jobs) return;
-    NdtJob& J = jobs[j];
-    J.align_pass = 0; J.total_iterations = 0; J.total_sweeps = 0;
-    ndt_job_begin(J, J.guess);
-}
+// ---- the whole batch of alignments as ONE persistent cooperative kernel ------------------------------------------------
+// Jobs advance in lock-step: a sweep phase (every (active job, point tile) pair is one work item, spread over all
+// blocks), a grid barrier, an update phase (one warp per active job: fixed-order reduction of the tile partials and
+// one step of the Newton / More-Thuente state machine), a barrier, and the compaction of the active-job list.  The
+// host launches once and reads the results back: no polling, no per-sweep launches.  (Letting the block that finishes
+// a job's last tile run that job's update was measured and is slower: the serial state machine stalls the block's
+// remaining tiles.)
+struct NdtAlignArgs {
+    NdtJob* jobs;
+    int n_jobs;
+    const NdtTargetView* targets;
+    const NdtSourceView* sources;
+    NdtOptsDev o;
+    int tiles_max;                 // ceil(max source size / kNdtTile)
+    double* partial;               // [n_jobs][tiles_max][kNdtSums]
+    int* active;                   // [2][n_jobs] double-buffered list of unfinished jobs
+    int* counters;                 // [0..1] list lengths, [2] sweep phases executed
+    unsigned long long* sweep_ns;  // accumulated wall time of the sweep phases (block 0), optional
+    int max_sweeps;
+};
 
-// one block (32 threads) per job: reduce the tile partials in a fixed order, advance the state machine.
-__global__ void __launch_bounds__(32)
-k_ndt_update(NdtJob* __restrict__ jobs, const NdtSourceView* __restrict__ sources, NdtOptsDev o, int tiles_max,
-             const double* __restrict__ partial, int* __restrict__ n_active) {
-    const int job = blockIdx.x;
-    NdtJob& J = jobs[job];
-    if (J.phase == NDT_DONE) return;
-    __shared__ double sums[kNdtSums];
-    const int n_tiles = (sources[J.source].n + kNdtThreads - 1) / kNdtThreads;
-    if (threadIdx.x < kNdtSums) {
-        double v = 0.0;
-        const double* pj = partial + (size_t)job * tiles_max * kNdtSums + threadIdx.x;
-        for (int t = 0; t < n_tiles; ++t) v += pj[(size_t)t * kNdtSums];
-        sums[threadIdx.x] = v;
+__global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ NdtSweepShared sh;
+    __shared__ int s_scan[kNdtThreads / 32];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    for (int j = gtid; j < a.n_jobs; j += gsize) {
+        NdtJob& J = a.jobs[j];
+        J.align_pass = 0; J.total_iterations = 0; J.total_sweeps = 0;
+        ndt_job_begin(J, J.guess);
+        a.active[j] = j;
     }
-    __syncwarp();
-    if (threadIdx.x == 0) {
-        ndt_job_step(J, sums, o);
-        if (J.phase == NDT_DONE) {
-            J.total_iterations += J.nr_iterations; J.total_sweeps += J.sweeps;
-            if (J.align_pass + 1 < o.n_align) {          // registration->align() again from the previous result (:282-290)
-                const int pass = J.align_pass + 1;
-                float g[12];
-                for (int i = 0; i < 12; ++i) g[i] = J.Tfinal[i];
-                ndt_job_begin(J, g);
-                J.align_pass = pass;
+    if (gtid == 0) { a.counters[0] = a.n_jobs; a.counters[1] = 0; a.counters[2] = 0; }
+    grid.sync();
+    unsigned long long sweep_ns = 0;
+    int cur = 0;
+    for (int it = 0; it < a.max_sweeps; ++it) {
+        const int n_active = *((volatile int*)&a.counters[cur]);
+        if (n_active == 0) break;
+        const int* act = a.active + (size_t)cur * a.n_jobs;
+        // ---- sweep ----
+        unsigned long long t0 = 0;
+        if (a.sweep_ns && gtid == 0) t0 = global_ns();
+        const long long n_work = (long long)n_active * a.tiles_max;
+        for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int job = act[w / a.tiles_max], tile = (int)(w % a.tiles_max);
+            const NdtJob& J = a.jobs[job];
+            const NdtSourceView src = a.sources[J.source];
+            if (tile * kNdtTile >= src.n) continue;
+            ndt_sweep_tile(J, a.targets[J.target], src, a.o, tile, sh, a.partial + ((size_t)job * a.tiles_max + tile) * kNdtSums);
+        }
+        grid.sync();
+        if (a.sweep_ns && gtid == 0) sweep_ns += global_ns() - t0;
+        // ---- update: one warp per active job (all jobs in parallel; the state machine itself is serial) ----
+        const int lane = threadIdx.x & 31;
+        const int gwarp = gtid >> 5, nwarps = gsize >> 5;
+        // spread the jobs over the SMs first: warp k of the grid -> block k % gridDim.x
+        for (int k = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; k < n_active; k += nwarps) {
+            const int job = act[k];
+            NdtJob& J = a.jobs[job];
+            const int n_tiles = (a.sources[J.source].n + kNdtTile - 1) / kNdtTile;
+            double v = 0.0;
+            if (lane < kNdtSums) {
+                const double* pj = a.partial + (size_t)job * a.tiles_max * kNdtSums + lane;
+                int t = 0;
+                for (; t + 4 <= n_tiles; t += 4) {
+                    const double v0 = __ldcg(&pj[(size_t)(t + 0) * kNdtSums]), v1 = __ldcg(&pj[(size_t)(t + 1) * kNdtSums]);
+                    const double v2 = __ldcg(&pj[(size_t)(t + 2) * kNdtSums]), v3 = __ldcg(&pj[(size_t)(t + 3) * kNdtSums]);
+                    v += v0; v += v1; v += v2; v += v3;
+                }
+                for (; t < n_tiles; ++t) v += __ldcg(&pj[(size_t)t * kNdtSums]);
+            }
+            double sums[kNdtSums];
+#pragma unroll
+            for (int q = 0; q < kNdtSums; ++q) {
+                int lo = __double2loint(v), hi = __double2hiint(v);
+                lo = __shfl_sync(0xffffffffu, lo, q); hi = __shfl_sync(0xffffffffu, hi, q);
+                sums[q] = __hiloint2double(hi, lo);
+            }
+            if (lane == 0) {
+                ndt_job_step(J, sums, a.o);
+                if (J.phase == NDT_DONE) {
+                    J.total_iterations += J.nr_iterations; J.total_sweeps += J.sweeps;
+                    if (J.align_pass + 1 < a.o.n_align) {     // registration->align() again from the previous result (:282-290)
+                        const int pass = J.align_pass + 1;
+                        float g[12];
+                        for (int i = 0; i < 12; ++i) g[i] = J.Tfinal[i];
+                        ndt_job_begin(J, g);
+                        J.align_pass = pass;
+                    }
+                }
             }
         }
-        if (J.phase != NDT_DONE) atomicAdd(n_active, 1);
+        (void)gwarp;
+        grid.sync();
+        // ---- compaction of the active list (block 0; order preserved so the run is deterministic) ----
+        if (blockIdx.x == 0) {
+            int* nxt = a.active + (size_t)(cur ^ 1) * a.n_jobs;
+            int carry = 0;
+            for (int base = 0; base < n_active; base += kNdtThreads) {
+                const int k = base + threadIdx.x;
+                const int job = k < n_active ? act[k] : -1;
+                const bool keep = job >= 0 && ((volatile NdtJob*)a.jobs)[job].phase != NDT_DONE;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) s_scan[threadIdx.x >> 5] = __popc(bal);
+                __syncthreads();
+                int wbase = 0, tot = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < kNdtThreads / 32; ++w2) { if (w2 < (int)(threadIdx.x >> 5)) wbase += s_scan[w2]; tot += s_scan[w2]; }
+                if (keep) nxt[carry + wbase + __popc(bal & ((1u << lane) - 1u))] = job;
+                carry += tot;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) { a.counters[cur ^ 1] = carry; a.counters[2] = it + 1; }
+        }
+        grid.sync();
+        cur ^= 1;
     }
+    if (a.sweep_ns && gtid == 0) *a.sweep_ns += sweep_ns;
 }
 
 }  // namespace liloc

@@ -68,7 +68,16 @@ struct S2mArgs {
     const S2mState* state;               // members isDegenerate / matP before this call ...
     S2mState* state_out;                 // ... and after it (double-buffered by the host, see liloc_frame_features)
     S2mResult* result;
+    unsigned long long* marks;           // optional latency breakdown: %globaltimer at [0] start and, per iteration i,
+                                         // [1+3i] tiles done, [2+3i] past the grid barrier, [3+3i] pose updated (block 0)
 };
+constexpr int kS2mMarks = 1 + 3 * 32;
+
+LILOC_DEV unsigned long long s2m_global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- 5x3 least squares  A x = -1  (Eigen::colPivHouseholderQr().solve, src/mapOptmization.cpp:1009) --
 // Same operation sequence as oracle plane_lsq_5x3.  Register-only: every array index is static.
@@ -633,6 +642,8 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
 
     // :1187; with corners the upstream gate (cornerDS > edgeFeatureMinValidNum && surfDS > surfFeatureMinValidNum)
     const bool skipped = !(q_all > a.min_points) || (a.enable_corner && !(q_corner > a.min_corner));
+    const bool marking = a.marks != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (marking) a.marks[0] = s2m_global_ns();
     int iters = 0, converged = 0, too_few = 0;
 #ifdef LILOC_S2M_PROFILE
     long long clk[8];
@@ -655,10 +666,12 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
                 __syncthreads();
             }
             S2M_CLK(1)
+            if (marking && iter < 32) a.marks[1 + 3 * iter] = s2m_global_ns();
             double* part = a.partial + (size_t)(iter & 1) * gridDim.x * kNSums;
             if (threadIdx.x < kNSums) part[(size_t)blockIdx.x * kNSums + threadIdx.x] = acc;
             grid.sync();
             S2M_CLK(2)
+            if (marking && iter < 32) a.marks[2 + 3 * iter] = s2m_global_ns();
             // D: fixed-order reduction of the block partials, identical in every block.  Thread (j, c) sums
             // blocks j, j + kRedGroups, ... of column c (coalesced 224-byte rows, loads batched ahead of
             // the dependent adds), then column c adds its kRedGroups group sums in order.
@@ -749,6 +762,7 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
             S2M_CLK(4)
             if (sh.done == 0) s2m_refresh_transform(sh);
             S2M_CLK(5)
+            if (marking && iter < 32) a.marks[3 + 3 * iter] = s2m_global_ns();
 #ifdef LILOC_S2M_PROFILE
             if (blockIdx.x == 0 && threadIdx.x == 0 && iter < 32)
             {

@@ -83,6 +83,25 @@ def gather_results(local_rows: np.ndarray, n_items: int, device=None) -> np.ndar
     return out
 
 
+def gather_padded(local_rows: np.ndarray, per: int, device=None) -> np.ndarray:
+    """All-gather of per-rank blocks padded to `per` rows -> (world, per, 8) on every rank."""
+    rank, world, _ = env_world()
+    local_rows = np.ascontiguousarray(local_rows, np.float32).reshape(-1, RESULT_WIDTH)
+    if world == 1:
+        out = np.zeros((1, per, RESULT_WIDTH), np.float32)
+        out[0, : len(local_rows)] = local_rows
+        return out
+    import torch
+    import torch.distributed as dist
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
+    send = torch.zeros((per, RESULT_WIDTH), dtype=torch.float32, device=dev)
+    send[: len(local_rows)] = torch.from_numpy(local_rows).to(dev)
+    recv = torch.empty((world * per, RESULT_WIDTH), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    return recv.cpu().numpy().reshape(world, per, RESULT_WIDTH)
+
+
 def max_over_ranks(value: float, device=None) -> float:
     rank, world, _ = env_world()
     if world == 1:

@@ -62,3 +62,65 @@ def test_two_rank_gather_gloo(tmp_path):
     for rank, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {rank} ok" in o
+
+
+def test_relo_guess_helpers():
+    from liloc_b200 import relo
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        p = np.r_[rng.uniform(-1.2, 1.2, 2), rng.uniform(-3.1, 3.1), rng.uniform(-50, 50, 3)]
+        T = relo.euler_to_matrix(*p)
+        assert T.dtype == np.float32 and np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-6)
+        assert np.allclose(relo.matrix_to_pose6(T), p, atol=2e-6 * 50)
+    g = relo.hypothesis_grid([0.01, -0.02, 0.3, 5.0, -2.0, 1.8], 16, 16, 2.0, seed=3)
+    assert g.shape == (256, 4, 4)
+    assert np.allclose(g[0], relo.euler_to_matrix(0.01, -0.02, 0.3, 5.0, -2.0, 1.8))          # first hypothesis = the given pose
+    d = np.hypot(g[:, 0, 3] - 5.0, g[:, 1, 3] + 2.0)
+    assert d.max() <= 2.0 + 1e-5 and np.allclose(g[:, 2, 3], 1.8)
+    yaws = np.array([relo.matrix_to_pose6(t)[2] for t in g[::16]])
+    assert len(np.unique(np.round(yaws, 4))) == 16
+
+
+RELO_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, ROOT_DIR)
+    from liloc_b200 import parallel, relo
+    rank, world, _ = parallel.init("gloo")
+
+    class FakeCtx:            # stands in for the device context: the result of an item is a function of the item alone
+        def ndt_align_batch(self, tids, sids, guesses, opts):
+            J = len(guesses)
+            T = np.array(guesses, np.float32).copy()
+            T[:, 0, 3] += np.asarray(tids, np.float32) + 0.5 * np.asarray(sids, np.float32)
+            return T, np.arange(J) * 0.0 + T[:, 1, 3], (np.asarray(tids) % 7).astype(np.int64), np.ones(J, np.int64), np.full(J, 9)
+
+    n = 37
+    tids, sids = np.arange(n) % 5, np.arange(n) % 3
+    guesses = np.stack([relo.euler_to_matrix(0, 0, 0.01 * i, float(i), 2.0 * i, 1.0) for i in range(n)])
+    for rr in (False, True):
+        rows, loc = relo.align_sharded(FakeCtx(), tids, sids, guesses, None, None, round_robin=rr)
+        assert rows.shape == (n, 8)
+        want_x = np.arange(n) + tids + 0.5 * sids
+        assert np.allclose(rows[:, 3], want_x) and np.allclose(rows[:, 4], 2.0 * np.arange(n)) and np.array_equal(rows[:, 7], tids % 7)
+        mine = loc["items"]
+        assert len(mine) in (n // world, n // world + 1)
+        assert (mine[1] - mine[0] == world) if rr else (mine[1] - mine[0] == 1)
+    print("rank", rank, "ok")
+""")
+
+
+def test_relo_items_shard_and_gather_gloo(tmp_path):
+    script = tmp_path / "relo_worker.py"
+    script.write_text(RELO_WORKER.replace('ROOT_DIR', repr(ROOT)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for rank, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {rank} ok" in o

@@ -140,6 +140,7 @@ struct liloc_ctx {
     bool ndt_views_dirty = true;
     liloc_ndt_stats ndt_stats{};
     DevBuf<int> ndt_active;
+    DevBuf<NdtPoseCache> ndt_pose;
     int* d_ndt_counters = nullptr;       // 3 ints
     unsigned long long* d_ndt_ns = nullptr;
     int ndt_max_blocks = 0;
@@ -558,7 +559,7 @@ void liloc_destroy(liloc_ctx* c) {
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
     fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
-    fr(c->ndt_active.p); fr(c->d_ndt_counters); fr(c->d_ndt_ns);
+    fr(c->ndt_active.p); fr(c->ndt_pose.p); fr(c->d_ndt_counters); fr(c->d_ndt_ns);
     if (c->h_info) cudaFreeHost(c->h_info);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {c->stream2, c->stream3, c->stream}) if (st) cudaStreamDestroy(st);
@@ -1114,12 +1115,13 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
     if ((rc = ensure(ctx, ctx->d_jobs, (size_t)n_jobs))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_partial, (size_t)n_jobs * tiles * kNdtSums))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_active, (size_t)2 * n_jobs))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_pose, (size_t)n_jobs))) return rc;
     CU(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
     CU(cudaMemsetAsync(ctx->d_ndt_ns, 0, sizeof(unsigned long long), ctx->stream));
     NdtAlignArgs aa{};
     aa.jobs = ctx->d_jobs.p; aa.n_jobs = n_jobs; aa.targets = ctx->d_tviews.p; aa.sources = ctx->d_sviews.p; aa.o = od;
-    aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.active = ctx->ndt_active.p; aa.counters = ctx->d_ndt_counters;
+    aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.pose = ctx->ndt_pose.p; aa.active = ctx->ndt_active.p; aa.counters = ctx->d_ndt_counters;
     aa.sweep_ns = ctx->timing ? ctx->d_ndt_ns : nullptr;
     // worst case per align pass: first sweep + (max_iterations + 2) x (1 + 10) line-search sweeps
     aa.max_sweeps = od.n_align * (1 + (od.max_iterations + 2) * 11);

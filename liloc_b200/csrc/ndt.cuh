@@ -332,15 +332,25 @@ LILOC_DEV void ndt_point_cell(const float (&x)[3], const float (&xt)[3], const N
         }
 }
 
-struct NdtSweepShared { float T[12]; NdtAng ang; double red[kNdtThreads / 32][kNdtSums]; };
+// What a sweep needs of a job's trial pose x_t: the 3x4 transform and the angle-derivative tables.  Evaluated once
+// per job and round by the thread that moves x_t (double sin/cos: ~thousands of cycles), not once per tile.
+struct NdtPoseCache { float T[12]; NdtAng ang; };
+constexpr int kNdtPoseFloats = sizeof(NdtPoseCache) / sizeof(float);
+LILOC_DEV void ndt_pose_cache_fill(const double* x_t, NdtPoseCache* pc) { ndt_pose_to_matrix(x_t, pc->T); ndt_angle_derivatives(x_t, &pc->ang); }
+
+struct NdtSweepShared { NdtPoseCache pc; double red[kNdtThreads / 32][kNdtSums]; };
 
 // One tile (kNdtTile source points, kNdtPPT per thread) of one derivative sweep of job J at J.x_t: float per-point
 // terms, double accumulation in registers over the thread's points, then ONE warp-shuffle + shared-memory
 // reduction per tile -> 28 doubles at `out`.  All threads of the block call this together.
-LILOC_DEV void ndt_sweep_tile(const NdtJob& J, const NdtTargetView& tg, const NdtSourceView& src, const NdtOptsDev& o,
+template <bool kPoseInGlobal>
+LILOC_DEV void ndt_sweep_tile(const NdtPoseCache* __restrict__ pc, const NdtTargetView& tg, const NdtSourceView& src, const NdtOptsDev& o,
                               const int tile, NdtSweepShared& sh, double* __restrict__ out) {
     __syncthreads();                                      // sh may still be read by the previous tile's tail
-    if (threadIdx.x == 0) { ndt_pose_to_matrix(J.x_t, sh.T); ndt_angle_derivatives(J.x_t, &sh.ang); }
+    if (threadIdx.x < kNdtPoseFloats) {                   // written by another block in the previous round: read through L2
+        const float* src_f = reinterpret_cast<const float*>(pc) + threadIdx.x;
+        reinterpret_cast<float*>(&sh.pc)[threadIdx.x] = kPoseInGlobal ? __ldcg(src_f) : *src_f;
+    }
     __syncthreads();
     double acc[kNdtSums];
 #pragma unroll
@@ -353,14 +363,15 @@ LILOC_DEV void ndt_sweep_tile(const NdtJob& J, const NdtTargetView& tg, const Nd
         if (i >= src.n) break;
         const float4 p = __ldg(&src.pts[i]);
         const float x[3] = {p.x, p.y, p.z};
-        const float xt[3] = {sh.T[0] * p.x + sh.T[1] * p.y + sh.T[2] * p.z + sh.T[3],
-                             sh.T[4] * p.x + sh.T[5] * p.y + sh.T[6] * p.z + sh.T[7],
-                             sh.T[8] * p.x + sh.T[9] * p.y + sh.T[10] * p.z + sh.T[11]};
+        const float* T = sh.pc.T;
+        const float xt[3] = {T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3],
+                             T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
+                             T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11]};
         for (int c = 0; c < ncell; ++c) {
             // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
             const int dx = (c == 1) - (c == 2), dy = (c == 3) - (c == 4), dz = (c == 5) - (c == 6);
             const int li = ndt_lookup(tg, xt[0], xt[1], xt[2], dx, dy, dz);
-            if (li >= 0) ndt_point_cell(x, xt, &tg.leaves[li], sh.ang, o.d1, (float)o.d2, acc);
+            if (li >= 0) ndt_point_cell(x, xt, &tg.leaves[li], sh.pc.ang, o.d1, (float)o.d2, acc);
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -385,8 +396,11 @@ __global__ void __launch_bounds__(kNdtThreads)
 k_ndt_sweep(const NdtJob* __restrict__ jobs, const NdtTargetView* __restrict__ targets, const NdtSourceView* __restrict__ sources,
             NdtOptsDev o, double* __restrict__ partial) {
     __shared__ NdtSweepShared sh;
+    __shared__ NdtPoseCache s_pc;
     const NdtJob& J = jobs[0];
-    ndt_sweep_tile(J, targets[J.target], sources[J.source], o, blockIdx.x, sh, partial + (size_t)blockIdx.x * kNdtSums);
+    if (threadIdx.x == 0) ndt_pose_cache_fill(J.x_t, &s_pc);
+    __syncthreads();
+    ndt_sweep_tile<false>(&s_pc, targets[J.target], sources[J.source], o, blockIdx.x, sh, partial + (size_t)blockIdx.x * kNdtSums);
 }
 
 // ---- More-Thuente helpers ------------------------------------------------------------------------------------
@@ -587,6 +601,7 @@ struct NdtAlignArgs {
     NdtOptsDev o;
     int tiles_max;                 // ceil(max source size / kNdtTile)
     double* partial;               // [n_jobs][tiles_max][kNdtSums]
+    NdtPoseCache* pose;            // [n_jobs] transform + angle tables of every job's current trial pose
     int* active;                   // [2][n_jobs] double-buffered list of unfinished jobs
     int* counters;                 // [0..1] list lengths, [2] sweep phases executed
     unsigned long long* sweep_ns;  // accumulated wall time of the sweep phases (block 0), optional
@@ -602,6 +617,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
         NdtJob& J = a.jobs[j];
         J.align_pass = 0; J.total_iterations = 0; J.total_sweeps = 0;
         ndt_job_begin(J, J.guess);
+        ndt_pose_cache_fill(J.x_t, &a.pose[j]);
         a.active[j] = j;
     }
     if (gtid == 0) { a.counters[0] = a.n_jobs; a.counters[1] = 0; a.counters[2] = 0; }
@@ -621,7 +637,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
             const NdtJob& J = a.jobs[job];
             const NdtSourceView src = a.sources[J.source];
             if (tile * kNdtTile >= src.n) continue;
-            ndt_sweep_tile(J, a.targets[J.target], src, a.o, tile, sh, a.partial + ((size_t)job * a.tiles_max + tile) * kNdtSums);
+            ndt_sweep_tile<true>(&a.pose[job], a.targets[J.target], src, a.o, tile, sh, a.partial + ((size_t)job * a.tiles_max + tile) * kNdtSums);
         }
         grid.sync();
         if (a.sweep_ns && gtid == 0) sweep_ns += global_ns() - t0;
@@ -663,6 +679,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
                         J.align_pass = pass;
                     }
                 }
+                if (J.phase != NDT_DONE) ndt_pose_cache_fill(J.x_t, &a.pose[job]);
             }
         }
         (void)gwarp;

@@ -122,7 +122,8 @@ struct liloc_ctx {
     int state_cur = 0;
     S2mResult* d_result = nullptr;
     int s2m_max_blocks = 0;
-    int pipe_blocks = 0;                 // blocks of one point-cloud pipeline launch (one per SM: two launches co-reside)
+    int pipe_blocks = 0;                 // blocks of a narrow point-cloud pipeline launch (one per SM)
+    int pipe_blocks_wide = 0;            // blocks of a wide one (two per SM when three fit, so wide + narrow co-reside)
     unsigned long long* d_marks = nullptr;   // 2 x kPipeMarks phase timestamps (maps launch, scans launch) + kS2mMarks
     int s2m_nq_last = 0;
     int s2m_nq_corner_last = 0;
@@ -289,11 +290,14 @@ int prob_add_grid(liloc_ctx* ctx, FeatClass& fc, int m_upper, VgProb* q) {
     return 0;
 }
 
-int pipe_launch(liloc_ctx* ctx, cudaStream_t st, PipeArgs& a, unsigned long long* marks) {
+// `wide`: two blocks per SM (the local maps: streaming phases over 10^5..10^6 points); otherwise one block per SM
+// (the scans), so that a wide and a narrow launch are co-resident (3 blocks of 80 registers x 256 threads per SM).
+int pipe_launch(liloc_ctx* ctx, cudaStream_t st, PipeArgs& a, unsigned long long* marks, bool wide = false) {
     if (a.n_prob <= 0) return 0;
     a.marks = marks;
     void* args[] = {&a};
-    CU(cudaLaunchCooperativeKernel((void*)k_voxel_pipeline, dim3((unsigned)ctx->pipe_blocks), dim3(kPipeThreads), args, 0, st));
+    const int blocks = wide ? ctx->pipe_blocks_wide : ctx->pipe_blocks;
+    CU(cudaLaunchCooperativeKernel((void*)k_voxel_pipeline, dim3((unsigned)blocks), dim3(kPipeThreads), args, 0, st));
     ++ctx->launches;
     return 0;
 }
@@ -510,6 +514,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_pipeline, kPipeThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_voxel_pipeline cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->pipe_blocks = c->num_sms;
+    c->pipe_blocks_wide = per_sm >= 3 ? 2 * c->num_sms : c->num_sms;
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ndt_align, kNdtThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_ndt_align cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->ndt_max_blocks = per_sm * c->num_sms;
@@ -770,7 +775,10 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[cls]))) return rc;
     pm.n_prob = ncls;
     tick(ctx, 0, ctx->stream);
-    if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks : nullptr))) return rc;
+    // measured (profiles/): two blocks per SM pay off for the streaming phases only above ~1.5 M raw points; below
+    // that the sort (148 blocks) and the gathers are faster with one block per SM
+    const bool wide = (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
+    if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks : nullptr, wide))) return rc;
     tick(ctx, 3, ctx->stream);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
     tick(ctx, 4, ctx->stream);

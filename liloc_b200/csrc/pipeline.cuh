@@ -145,17 +145,24 @@ LILOC_DEV int block_sum_256(int v) {                        // all 256 threads; 
     return t;
 }
 
-struct SortGeom { int C, nb; };                            // items per sorting block (multiple of kSortTile), busy blocks
+struct SortGeom { int C, nb; };                            // items per sorting block (multiple of 256), busy blocks
 LILOC_DEV SortGeom sort_geom(int n) {
     SortGeom g;
     const int gs = min((int)gridDim.x, kSortBlocksMax);
+    // whole 1024-item tiles per block: finer chunks put more blocks to work but every block reads every busy
+    // block's histogram row (O(nb^2) L2 traffic), which measured slower (profiles/frame_latency_r01.md)
     g.C = (((n + gs - 1) / gs + kSortTile - 1) / kSortTile) * kSortTile;
     if (g.C < kSortTile) g.C = kSortTile;
     g.nb = (n + g.C - 1) / g.C;
     return g;
 }
 
-struct PipeSmemSort { int offs[256]; int wcnt[kPipeThreads / 32][256]; };
+constexpr int kSortUnits = kSortRounds * (kPipeThreads / 32);      // (round, warp) pairs of a tile, in item order
+struct PipeSmemSort {
+    int offs[256];                                 // next free slot of every digit for this block
+    unsigned short cnt[kSortUnits][256];           // items of digit d in unit u (zero between tiles)
+    unsigned short pre[kSortUnits][256];           // exclusive prefix of cnt over the units
+};
 struct PipeSmemRun { unsigned key[kRunTile]; float4 pt[kRunTile]; unsigned prev; };
 union PipeSmem { PipeSmemSort sort; PipeSmemRun run; int hist[256]; };
 
@@ -245,52 +252,73 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
     {
         int pre = 0, tot = 0;
         int b = 0;
-        for (; b + 4 <= g.nb; b += 4) {
-            const int v0 = hcur[(b + 0) * 256 + t], v1 = hcur[(b + 1) * 256 + t], v2 = hcur[(b + 2) * 256 + t], v3 = hcur[(b + 3) * 256 + t];
-            tot += v0 + v1 + v2 + v3;
-            pre += (b + 0 < (int)blockIdx.x ? v0 : 0) + (b + 1 < (int)blockIdx.x ? v1 : 0) + (b + 2 < (int)blockIdx.x ? v2 : 0) + (b + 3 < (int)blockIdx.x ? v3 : 0);
+#pragma unroll 1
+        for (; b + 16 <= g.nb; b += 16) {                       // 16 independent loads in flight per thread
+            int v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = hcur[(b + u) * 256 + t];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { tot += v[u]; pre += (b + u < (int)blockIdx.x) ? v[u] : 0; }
         }
         for (; b < g.nb; ++b) { const int v = hcur[b * 256 + t]; tot += v; if (b < (int)blockIdx.x) pre += v; }
         int total;
         const int excl = block_exclusive_scan_256(tot, &total);
         sm.sort.offs[t] = excl + pre;
 #pragma unroll
-        for (int w = 0; w < kPipeThreads / 32; ++w) sm.sort.wcnt[w][t] = 0;
+        for (int u = 0; u < kSortUnits; ++u) sm.sort.cnt[u][t] = 0;
     }
     __syncthreads();
     if (pass >= 1) hzero[blockIdx.x * 256 + t] = 0;            // free since the previous barrier; needed two passes on
     const int lo = blockIdx.x * g.C, hi = min(q.n, lo + g.C);
+    int carry = 0;                                              // items of digit t in the tiles already scattered
     for (int base = lo; base < hi; base += kSortTile) {
+        const int rounds = min(kSortRounds, (hi - base + kPipeThreads - 1) / kPipeThreads);
         unsigned k[kSortRounds], v[kSortRounds];
+        int rank[kSortRounds];
 #pragma unroll
         for (int r = 0; r < kSortRounds; ++r) {
             const int i = base + r * kPipeThreads + t;
             k[r] = 0u; v[r] = 0u;
             if (i < hi) { k[r] = skeys[i]; v[r] = svals ? svals[i] : (unsigned)i; }
         }
+        // 1. stable rank inside every (round, warp) unit by warp match; the unit leader publishes the unit's count
 #pragma unroll
         for (int r = 0; r < kSortRounds; ++r) {
             const int i = base + r * kPipeThreads + t;
             const bool valid = i < hi;
             const unsigned d = valid ? ((k[r] >> shift) & 255u) : 256u;
             const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            if (valid && rank == 0) sm.sort.wcnt[warp][d] = __popc(peers);
-            __syncthreads();
-            if (valid) {
-                int pos = sm.sort.offs[d] + rank;
-                for (int w = 0; w < warp; ++w) pos += sm.sort.wcnt[w][d];
+            rank[r] = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank[r] == 0) sm.sort.cnt[r * (kPipeThreads / 32) + warp][d] = (unsigned short)__popc(peers);
+        }
+        __syncthreads();
+        // 2. per digit: exclusive prefix over the units (item order), counters cleared for the next tile
+        {
+            sm.sort.offs[t] += carry;
+            int run = 0;
+            const int units = rounds * (kPipeThreads / 32);
+            for (int u = 0; u < units; ++u) {
+                const int c = sm.sort.cnt[u][t];
+                sm.sort.pre[u][t] = (unsigned short)run;
+                sm.sort.cnt[u][t] = 0;
+                run += c;
+            }
+            carry = run;
+        }
+        __syncthreads();
+        // 3. scatter; the histogram of the next pass is accumulated at the destination block's row
+#pragma unroll
+        for (int r = 0; r < kSortRounds; ++r) {
+            const int i = base + r * kPipeThreads + t;
+            if (i < hi) {
+                const unsigned d = (k[r] >> shift) & 255u;
+                const int pos = sm.sort.offs[d] + sm.sort.pre[r * (kPipeThreads / 32) + warp][d] + rank[r];
                 dkeys[pos] = k[r];
                 dvals[pos] = v[r];
                 if (hnext) atomicAdd(&hnext[(pos / g.C) * 256 + ((k[r] >> (shift + 8)) & 255u)], 1);
             }
-            __syncthreads();
-            int s = 0;
-#pragma unroll
-            for (int w = 0; w < kPipeThreads / 32; ++w) { s += sm.sort.wcnt[w][t]; sm.sort.wcnt[w][t] = 0; }
-            sm.sort.offs[t] += s;
-            __syncthreads();
         }
+        __syncthreads();
     }
 }
 

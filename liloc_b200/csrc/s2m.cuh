@@ -33,7 +33,9 @@ constexpr int kS2mThreads = 256;
 constexpr int kS2mWarps = kS2mThreads / 32;
 constexpr int kQPB = kS2mThreads / kKnnLanes;   // queries per tile: one group of kKnnLanes lanes per query
 constexpr int kNSums = 28;               // 21 (upper J^T J) + 6 (J^T r) + 1 (count)
-constexpr int kRedGroups = kS2mThreads / kNSums;   // 18 groups of 28 threads for the cross-block reduction
+constexpr int kRedGroups = kS2mThreads / kNSums;   // 9 groups of 28 threads for the cross-block reduction
+constexpr int kSumsPerWarp = (kNSums + kS2mWarps - 1) / kS2mWarps;      // 4: warp w reduces sums 4w .. 4w+3 of a tile
+static_assert(kQPB == 32, "the tile sums map one query row to one lane");
 
 struct S2mState {                        // members isDegenerate / matP (src/mapOptmization.cpp:90-91)
     int is_degenerate;
@@ -654,21 +656,44 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
     if (!skipped) {
         for (int iter = 0; iter < a.max_iters; ++iter) {
             S2M_CLK(0)
-            double acc = 0.0;                               // threads < kNSums: running sum over this block's tiles
+            // C: lane = query row of the tile, warp w owns sums 4w .. 4w+3.  Products of two floats are exact in double;
+            // the 32 rows are added by a fixed xor-shuffle tree (5 levels instead of a 32-long chain of dependent
+            // FP64 adds, which cost ~290 cycles each on this part and used to be the longest piece of the tile).
+            double acc[kSumsPerWarp];                        // lane 0 of every warp: running sums over this block's tiles
+#pragma unroll
+            for (int u = 0; u < kSumsPerWarp; ++u) acc[u] = 0.0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int cls = tile < n_tiles_c ? 1 : 0;      // corner tiles first (combineOptimizationCoeffs order)
                 s2m_tile_rows(sh, cls, cls ? tile : tile - n_tiles_c, cls ? nq_c : nq, nullptr, nullptr);
-                if (threadIdx.x < kNSums) {                 // C
-                    const int ia = c_sum_a[threadIdx.x], ic = c_sum_c[threadIdx.x];
-#pragma unroll 8
-                    for (int s = 0; s < kQPB; ++s) acc += (double)sh.row[s][ia] * (double)sh.row[s][ic];
+                {
+                    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                    double v[kSumsPerWarp];
+#pragma unroll
+                    for (int u = 0; u < kSumsPerWarp; ++u) {
+                        const int k = warp * kSumsPerWarp + u;
+                        v[u] = 0.0;
+                        if (k < kNSums) v[u] = (double)sh.row[lane][c_sum_a[k]] * (double)sh.row[lane][c_sum_c[k]];
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < kSumsPerWarp; ++u) v[u] += shfl_xor_d(v[u], o);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSumsPerWarp; ++u) acc[u] += v[u];
                 }
                 __syncthreads();
             }
             S2M_CLK(1)
             if (marking && iter < 32) a.marks[1 + 3 * iter] = s2m_global_ns();
             double* part = a.partial + (size_t)(iter & 1) * gridDim.x * kNSums;
-            if (threadIdx.x < kNSums) part[(size_t)blockIdx.x * kNSums + threadIdx.x] = acc;
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int u = 0; u < kSumsPerWarp; ++u) {
+                    const int k = (threadIdx.x >> 5) * kSumsPerWarp + u;
+                    if (k < kNSums) part[(size_t)blockIdx.x * kNSums + k] = acc[u];
+                }
+            }
             grid.sync();
             S2M_CLK(2)
             if (marking && iter < 32) a.marks[2 + 3 * iter] = s2m_global_ns();
@@ -678,24 +703,24 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
             if (threadIdx.x < kRedGroups * kNSums) {
                 const int c = threadIdx.x % kNSums, j = threadIdx.x / kNSums;
                 const int nb = (int)gridDim.x;
-                double sacc = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains: FP64 add latency is long
                 int b = j;
                 for (; b + 3 * kRedGroups < nb; b += 4 * kRedGroups) {
                     const double v0 = __ldcg(&part[(size_t)b * kNSums + c]);
                     const double v1 = __ldcg(&part[(size_t)(b + kRedGroups) * kNSums + c]);
                     const double v2 = __ldcg(&part[(size_t)(b + 2 * kRedGroups) * kNSums + c]);
                     const double v3 = __ldcg(&part[(size_t)(b + 3 * kRedGroups) * kNSums + c]);
-                    sacc += v0; sacc += v1; sacc += v2; sacc += v3;
+                    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
                 }
-                for (; b < nb; b += kRedGroups) sacc += __ldcg(&part[(size_t)b * kNSums + c]);
-                sh.red[j][c] = sacc;
+                for (; b < nb; b += kRedGroups) s0 += __ldcg(&part[(size_t)b * kNSums + c]);
+                sh.red[j][c] = (s0 + s1) + (s2 + s3);
             }
             __syncthreads();
             if (threadIdx.x < kNSums) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int j = 0; j < kRedGroups; ++j) sacc += sh.red[j][threadIdx.x];
-                sh.sums[threadIdx.x] = sacc;
+                const double* r = &sh.red[0][threadIdx.x];
+                static_assert(kRedGroups == 9, "fixed reduction tree below");
+                sh.sums[threadIdx.x] = (((r[0 * kNSums] + r[1 * kNSums]) + (r[2 * kNSums] + r[3 * kNSums])) +
+                                        ((r[4 * kNSums] + r[5 * kNSums]) + (r[6 * kNSums] + r[7 * kNSums]))) + r[8 * kNSums];
             }
             __syncthreads();
             S2M_CLK(3)

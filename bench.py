@@ -52,20 +52,53 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line), sampled every 20 ms
+    through NVML (nvidia_ml_py); falls back to `nvidia-smi -lms` if NVML is unavailable."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.proc = index, [], threading.Event(), None
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.mx, self.reasons, self.proc = [], [], set(), None
+
+    def _sample_nvml(self, nv, h):
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for name, bit in self.BAD.items():
+            if r & bit:
+                self.reasons.add(name)
 
     def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.replace(",", "").isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            while True:
+                self._sample_nvml(nv, h)
+                if self.stop_flag.wait(0.02):
+                    self._sample_nvml(nv, h)
+                    return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                r = [c.strip() for c in line.split(",")]
+                try:
+                    self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+                except Exception:
+                    pass
                 if self.stop_flag.is_set():
                     break
         except Exception:
@@ -73,19 +106,11 @@ class ClockSampler(threading.Thread):
 
     def finish(self) -> dict:
         self.stop_flag.set()
+        self.join(timeout=2.0)
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def make_workload(n_frames: int, seed: int, n_total: int | None = None):
@@ -231,20 +256,32 @@ def run_ours(args):
     value = frames_all / t_dev_max
     e2e = frames_all / t_e2e_max
     peak, peak_src = load_peaks()
-    # roofline of the dominant kernel by share of the frame: decided from the measured phase times
-    phases = {k: st_dev[k] for k in ("assemble_ms", "map_voxel_ms", "scan_ms", "grid_ms", "s2m_ms")}
+    # Roofline of the dominant kernel.  A frame is three launches: k_voxel_pipeline (local maps), k_voxel_pipeline (scan,
+    # concurrent on a second stream) and k_scan2map; the local-map launch is the longest (profiles/launches_r01*.txt:
+    # k_voxel_pipeline ~70 % of the device time).  Its duration comes from the %globaltimer marks block 0 writes at the
+    # phase boundaries of that launch on its own stream (liloc_last_marks), summed by the library over the timed region;
+    # its algorithmic bytes are 16 N_raw + 16 M per launch.
+    map_ms = st_dev["assemble_ms"] + st_dev["map_voxel_ms"] + st_dev["grid_ms"]
+    n_fr = max(st_dev["frames"], 1)
+    map_gbs = st_dev["alg_bytes_map"] / (map_ms * 1e-3) / 1e9 if map_ms > 0 else None
     s2m_gbs = st_dev["alg_bytes_s2m"] / (st_dev["s2m_ms"] * 1e-3) / 1e9 if st_dev["s2m_ms"] > 0 else None
-    map_gbs = st_dev["alg_bytes_map"] / ((st_dev["assemble_ms"] + st_dev["map_voxel_ms"]) * 1e-3) / 1e9 if st_dev["map_voxel_ms"] > 0 else None
     scan_gbs = st_dev["alg_bytes_scan"] / (st_dev["scan_ms"] * 1e-3) / 1e9 if st_dev["scan_ms"] > 0 else None
-    dominant = max(phases, key=phases.get)
-    roof = {"bound": "hbm", "kernel": "k_scan2map (persistent cooperative, one launch per frame)", "achieved": s2m_gbs, "peak": peak, "unit": "GB/s",
-            "frac": (s2m_gbs / peak) if s2m_gbs else None, "traffic": None, "peak_source": peak_src,
-            "avg_launch_us": st_dev["s2m_ms"] * 1e3 / max(st_dev["s2m_launches"], 1),
-            "avg_iters_per_launch": st_dev["s2m_iters"] / max(st_dev["s2m_launches"], 1),
-            "note": "latency-bound: <= 20 dependent Gauss-Newton iterations over an L2-resident working set (SURVEY 8d)",
-            "phase_share": {k: v / max(st_dev["total_ms"], 1e-9) for k, v in phases.items()}, "dominant_phase": dominant,
-            "map_assemble_voxel": {"achieved": map_gbs, "frac": (map_gbs / peak) if map_gbs else None},
-            "scan_voxel": {"achieved": scan_gbs, "frac": (scan_gbs / peak) if scan_gbs else None}}
+    traffic = None
+    try:            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))["k_voxel_pipeline_local_map"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "k_voxel_pipeline, local-map launch (assemble + VoxelGrid + search grid; persistent cooperative, one launch per frame)",
+            "achieved": map_gbs, "peak": peak, "unit": "GB/s", "frac": (map_gbs / peak) if map_gbs else None, "traffic": traffic,
+            "peak_source": peak_src, "avg_launch_us": map_ms * 1e3 / n_fr, "alg_bytes_per_launch": st_dev["alg_bytes_map"] / n_fr,
+            "note": "latency-bound, not bandwidth-bound: ~10 dependent phases separated by grid barriers over an L2-resident working set "
+                    "(SURVEY 8d); phase-by-phase latency in profiles/frame_latency_r01.md",
+            "per_frame_us": {"local_map_launch": map_ms * 1e3 / n_fr, "scan_launch(concurrent)": st_dev["scan_ms"] * 1e3 / n_fr,
+                             "scan2map_launch": st_dev["s2m_ms"] * 1e3 / n_fr, "frame_device_total": st_dev["total_ms"] * 1e3 / n_fr},
+            "k_scan2map": {"achieved": s2m_gbs, "frac": (s2m_gbs / peak) if s2m_gbs else None,
+                           "avg_launch_us": st_dev["s2m_ms"] * 1e3 / max(st_dev["s2m_launches"], 1),
+                           "avg_iters_per_launch": st_dev["s2m_iters"] / max(st_dev["s2m_launches"], 1)},
+            "k_voxel_pipeline_scan": {"achieved": scan_gbs, "frac": (scan_gbs / peak) if scan_gbs else None}}
     cpu = cpu_baseline_sample(seq, args.cpu_frames, args.cpu_budget) if (world == 1 and not args.no_cpu) else None
     its = [r.iters for r in reps if r.processed and r.iters > 0]
     out = {
@@ -367,8 +404,8 @@ def run_ndt(args):
         for _ in range(args.steps):
             l2_flush.fill_(1); torch.cuda.synchronize(); parallel.barrier()
             t0 = time.perf_counter()
-            if e2e:                                  # what a relo frame pays: target grid + scan upload + align + results back
-                put_targets(); put_sources()
+            if e2e:                                  # per step: the scans go up from pinned host memory, results come back;
+                put_sources()                        # the prior-session submap grids stay resident (loaded once per session)
             rows, loc = align()
             torch.cuda.synchronize()
             tt += time.perf_counter() - t0
@@ -401,8 +438,11 @@ def run_ndt(args):
                              "targets_rank0": len(my_t), "sources_rank0": len(my_s), "leaves": int(np.mean(leaves)) if leaves else 0,
                              "sweeps_per_item": job_sweeps / max(n * args.steps, 1), "iterations_per_item": float(np.mean(rows[:, 7]))},
                    "target_build_s_rank0": target_build_s},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": float(h2d_t + h2d_s + n * 72), "d2h_bytes_per_step": float(n * 152),
-                "note": "per step every rank re-uploads and rebuilds its target grids and re-uploads its scans (what a relo frame pays once per submap / scan)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": float(h2d_s + n * 72), "d2h_bytes_per_step": float(n * 152),
+                "note": "per step every rank uploads its scans and the guesses and reads the results back; the prior-session submap grids "
+                        "are resident (built once per session: target_build_s_rank0, h2d_bytes_targets_rank0) -- the CPU reference rebuilds "
+                        "the grid in every setInputTarget (anchorOptimize.hpp:394)",
+                "h2d_bytes_targets_rank0": float(h2d_t)},
         "gpu_launches": int(launches),
         "device_s": {"value_pass": ev_dev, "e2e_pass": ev_e2e},
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align, derivative-sweep phases (persistent cooperative kernel: one launch per batch)", "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -2,6 +2,7 @@
 
   python profiles/summarize.py launches gpurun_out/launches_r01.csv  > profiles/launches_r01.txt
   python profiles/summarize.py raw      gpurun_out/top_r01.ncu-rep   > profiles/top_r01.txt
+  python profiles/summarize.py traffic  gpurun_out/frame_r01b.ncu-rep        (JSON: DRAM bytes per launch and kernel)
 """
 import collections
 import csv
@@ -47,5 +48,24 @@ def raw(path):
                 print(f"    {w:62s} {row[hdr.index(w)]:>16s} {units[hdr.index(w)]}")
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per captured launch (ncu prints per-row units in the second row only,
+    so this re-queries with --print-units base)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for row in rows[2:]:
+        g = lambda k: float(row[hdr.index(k)].replace(",", "")) * UNIT.get(units[hdr.index(k)], 1.0)
+        res.append({"kernel": re.sub(r"\(.*", "", row[hdr.index("Kernel Name")]), "grid": int(float(row[hdr.index("launch__grid_size")])),
+                    "duration_us": g("gpu__time_duration.sum") / (1e3 if units[hdr.index("gpu__time_duration.sum")] in ("ns", "nsecond") else 1.0),
+                    "dram_read_bytes": g("dram__bytes_read.sum"), "dram_write_bytes": g("dram__bytes_write.sum")})
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2])

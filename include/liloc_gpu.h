@@ -173,6 +173,12 @@ typedef struct {
     int n_source;
 } liloc_ndt_out;
 int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts_map, int n, float resolution, int* n_leaves_out);
+/* generateSubMaps (include/dataManager/dataLoader.hpp:306-348) for one submap on the device: the K prior-session
+ * keyframes (stored with liloc_keyframe_put) are transformed by their prior poses and concatenated -- the reference
+ * keeps the submap un-down-sampled (:332-336) -- and become NDT target `target_id`.  Nothing crosses PCIe. */
+int liloc_ndt_target_put_keyframes(liloc_ctx* ctx, int target_id, const int* kf_ids, const float* poses6, int K, float resolution,
+                                   int* n_leaves_out, int* n_points_out);
+int liloc_ndt_target_size(liloc_ctx* ctx, int target_id);      /* points of the target cloud, or <0 if unknown id */
 int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts_body, int n, int on_device);
 int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs);
 int liloc_ndt_clear(liloc_ctx* ctx);

@@ -171,6 +171,8 @@ def _load() -> C.CDLL:
         "liloc_feature_pass": (C.c_int, [P, C.c_int, P, C.c_int, P, P]),
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
         "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
+        "liloc_ndt_target_put_keyframes": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, ip, ip]),
+        "liloc_ndt_target_size": (C.c_int, [P, C.c_int]),
         "liloc_ndt_stats_get": (C.c_int, [P, C.POINTER(NdtStats)]),
         "liloc_ndt_stats_reset": (C.c_int, [P]),
         "liloc_debug_line": (C.c_int, [P, P, P, C.c_int, P, P]),
@@ -189,7 +191,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -402,6 +404,13 @@ class Context:
         n = C.c_int()
         self._chk(lib.liloc_ndt_target_put(self._h, target_id, _ptr(p), len(p), resolution, C.byref(n)))
         return n.value
+
+    def ndt_target_put_keyframes(self, target_id: int, kf_ids, poses6, resolution: float) -> tuple[int, int]:
+        ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
+        nl, npts = C.c_int(), C.c_int()
+        self._chk(lib.liloc_ndt_target_put_keyframes(self._h, target_id, _ptr(ids), _ptr(poses), len(ids), resolution, C.byref(nl), C.byref(npts)))
+        return nl.value, npts.value
 
     def ndt_source_put(self, source_id: int, pts_body=None, dev_ptr: int | None = None, n: int | None = None) -> None:
         if dev_ptr is not None:

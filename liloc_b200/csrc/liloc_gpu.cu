@@ -129,7 +129,8 @@ struct liloc_ctx {
     int s2m_nq_corner_last = 0;
 
     // NDT: cached targets (prior submaps), sources (scans), job state
-    struct NdtTargetHost { DevBuf<int> table; DevBuf<NdtLeaf> leaves; NdtTargetView view; int n_leaves; float resolution; int slot; };
+    struct NdtTargetHost { DevBuf<int> table; DevBuf<NdtLeaf> leaves; NdtTargetView view; int n_leaves; float resolution; int slot; int n_points; };
+    DevBuf<KfDesc> ndt_descs;
     struct NdtSourceHost { DevBuf<float4> own; NdtSourceView view; int slot; };
     std::unordered_map<int, NdtTargetHost> ndt_targets;
     std::unordered_map<int, NdtSourceHost> ndt_sources;
@@ -564,6 +565,7 @@ void liloc_destroy(liloc_ctx* c) {
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
     fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
+    fr(c->ndt_descs.p);
     fr(c->ndt_active.p); fr(c->ndt_pose.p); fr(c->d_ndt_counters); fr(c->d_ndt_ns);
     if (c->h_info) cudaFreeHost(c->h_info);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -1032,15 +1034,14 @@ int ndt_sync_views(liloc_ctx* ctx) {
 
 extern "C" {
 
-int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, int n, float resolution, int* n_leaves_out) {
-    ENTER(ctx);
-    if (n <= 0 || !pts || !(resolution > 0.f)) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put: bad arguments");
+// Voxel-Gaussian grid of the n points at ctx->tmp_pts (already on the device, or assembled there by the pipeline when
+// kf != nullptr): voxel keys + stable sort (k_voxel_pipeline, sort_only), one leaf per voxel run, dense cell table.
+static int ndt_target_build(liloc_ctx* ctx, int target_id, int n, float resolution, const VgProb* assemble, int* n_leaves_out) {
     int rc;
-    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n))) return rc;
-    CU(cudaMemcpyAsync(ctx->tmp_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    {   // voxel keys + stable sort only: the sorted (key, source index) pairs land in keys_b / vals_b
+    {
         PipeArgs pa{};
         if ((rc = prob_voxelgrid(ctx, ctx->fc[0].vg_map, ctx->tmp_pts.p, n, resolution, nullptr, &pa.prob[0]))) return rc;
+        if (assemble) { pa.prob[0].arena = assemble->arena; pa.prob[0].descs = assemble->descs; pa.prob[0].K = assemble->K; pa.prob[0].raw = ctx->tmp_pts.p; }
         pa.n_prob = 1;
         if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
     }
@@ -1062,12 +1063,56 @@ int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, 
     int nl = 0;
     CU(cudaMemcpyAsync(&nl, ctx->d_ndt_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    T.n_leaves = nl; T.resolution = resolution;
+    T.n_leaves = nl; T.resolution = resolution; T.n_points = n;
     T.view.table = T.table.p; T.view.leaves = T.leaves.p; T.view.inv_leaf = vp.inv_leaf;
     for (int a = 0; a < 3; ++a) { T.view.minb[a] = vp.minb[a]; T.view.divb[a] = divb[a]; T.view.maxb[a] = vp.minb[a] + divb[a] - 1; }
     ctx->ndt_views_dirty = true;
     if (n_leaves_out) *n_leaves_out = nl;
     return LILOC_OK;
+}
+
+int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, int n, float resolution, int* n_leaves_out) {
+    ENTER(ctx);
+    if (n <= 0 || !pts || !(resolution > 0.f)) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    return ndt_target_build(ctx, target_id, n, resolution, nullptr, n_leaves_out);
+}
+
+// generateSubMaps (include/dataManager/dataLoader.hpp:306-348) for one submap, on the device: the K prior keyframes
+// (already in the arena, liloc_keyframe_put) are transformed by their prior poses and concatenated -- the submap the
+// reference keeps un-down-sampled (:332-336) -- and its voxel-Gaussian grid is built.  Nothing crosses PCIe.
+int liloc_ndt_target_put_keyframes(liloc_ctx* ctx, int target_id, const int* kf_ids, const float* poses6, int K, float resolution,
+                                   int* n_leaves_out, int* n_points_out) {
+    ENTER(ctx);
+    if (K <= 0 || !kf_ids || !poses6 || !(resolution > 0.f)) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put_keyframes: bad arguments");
+    int rc;
+    std::vector<KfDesc> h((size_t)K);
+    long long total = 0;
+    for (int k = 0; k < K; ++k) {
+        auto it = ctx->kf.find(kf_ids[k]);
+        if (it == ctx->kf.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put_keyframes: unknown keyframe id %d", kf_ids[k]);
+        h[k].src_off = (long long)it->second.off[0]; h[k].n = it->second.n[0]; h[k].dst_off = (int)total;
+        pose_to_T(poses6 + 6 * (size_t)k, h[k].T);
+        total += it->second.n[0];
+        if (total > 0x7fffffffLL) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_target_put_keyframes: more than 2^31 points");
+    }
+    if (total <= 0) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put_keyframes: empty submap");
+    if ((rc = ensure(ctx, ctx->ndt_descs, (size_t)K))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)total))) return rc;
+    CU(cudaMemcpyAsync(ctx->ndt_descs.p, h.data(), (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));          // the staging vector dies at return
+    VgProb asmb{};
+    asmb.arena = ctx->arena.p; asmb.descs = ctx->ndt_descs.p; asmb.K = K;
+    if (n_points_out) *n_points_out = (int)total;
+    return ndt_target_build(ctx, target_id, (int)total, resolution, &asmb, n_leaves_out);
+}
+
+int liloc_ndt_target_size(liloc_ctx* ctx, int target_id) {
+    if (!ctx) return LILOC_ERR_ARG;
+    auto it = ctx->ndt_targets.find(target_id);
+    return it == ctx->ndt_targets.end() ? LILOC_ERR_ARG : it->second.n_points;
 }
 
 int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts, int n, int on_device) {

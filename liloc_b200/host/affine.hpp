@@ -55,6 +55,29 @@ inline void getTranslationAndEulerAngles(const Affine3f& t, float& x, float& y, 
     yaw = std::atan2(t.m[1][0], t.m[0][0]);
 }
 
+// eulerToRotation (include/math_tools.h:229-237): Rz(yaw) * Ry(pitch) * Rx(roll) as the product of three float rotation
+// matrices (Eigen::AngleAxisf::toRotationMatrix: cosf / sinf of each angle), with the translation in the last column:
+// the init_guess of the NDT call sites (src/mapOptmization.cpp:276-280, anchorOptimize.hpp:397-401).  Row-major 4x4.
+inline void eulerToMatrix4(float roll, float pitch, float yaw, float x, float y, float z, float* T16) {
+    const float cr = std::cos(roll), sr = std::sin(roll), cp = std::cos(pitch), sp = std::sin(pitch), cy = std::cos(yaw), sy = std::sin(yaw);
+    const float Rz[3][3] = {{cy, -sy, 0}, {sy, cy, 0}, {0, 0, 1}}, Ry[3][3] = {{cp, 0, sp}, {0, 1, 0}, {-sp, 0, cp}}, Rx[3][3] = {{1, 0, 0}, {0, cr, -sr}, {0, sr, cr}};
+    float M[3][3], R[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i][j] = Rz[i][0] * Ry[0][j] + Rz[i][1] * Ry[1][j] + Rz[i][2] * Ry[2][j];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i][j] = M[i][0] * Rx[0][j] + M[i][1] * Rx[1][j] + M[i][2] * Rx[2][j];
+    const float t[3] = {x, y, z};
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T16[4 * i + j] = R[i][j]; T16[4 * i + 3] = t[i]; }
+    T16[12] = T16[13] = T16[14] = 0.f; T16[15] = 1.f;
+}
+
+// RotMtoEuler<float> (include/math_tools.h:92-111) on the rotation block of a row-major 4x4, plus the translation.
+inline void matrix4ToEuler(const float* T16, float& roll, float& pitch, float& yaw, float& x, float& y, float& z) {
+    const float r00 = T16[0], r10 = T16[4], r20 = T16[8], r21 = T16[9], r22 = T16[10], r11 = T16[5], r12 = T16[6];
+    const float sy = std::sqrt(r00 * r00 + r10 * r10);
+    if (!(sy < 1e-6)) { roll = std::atan2(r21, r22); pitch = std::atan2(-r20, sy); yaw = std::atan2(r10, r00); }
+    else { roll = std::atan2(-r12, r11); pitch = std::atan2(-r20, sy); yaw = 0.f; }
+    x = T16[3]; y = T16[7]; z = T16[11];
+}
+
 // tf::Quaternion::setRPY / slerp and tf::Matrix3x3::getRPY, double precision, as used by transformUpdate
 struct Quat { double x, y, z, w; };
 inline Quat quatFromRPY(double roll, double pitch, double yaw) {

@@ -27,6 +27,8 @@ struct liloc_host_report {               // mirror of liloc_host::FrameReport
     float guess[6];
     int is_degenerate, iters, converged, n_sel, q_all, map_points, n_raw, n_selected_keyframes, keyframe_id;
     double reg_ms;
+    int relo_initialized, relo_submap, relo_iterations, relo_converged;
+    float relo_pose[6];
 };
 
 static thread_local std::string g_err;
@@ -46,6 +48,8 @@ static void to_report(const liloc_host::FrameReport& r, liloc_host_report* o) {
     o->is_degenerate = r.is_degenerate; o->iters = r.iters; o->converged = r.converged; o->n_sel = r.n_sel;
     o->q_all = r.q_all; o->map_points = r.map_points; o->n_raw = r.n_raw; o->n_selected_keyframes = r.n_selected_keyframes;
     o->keyframe_id = r.keyframe_id; o->reg_ms = r.reg_ms;
+    o->relo_initialized = r.relo_initialized; o->relo_submap = r.relo_submap; o->relo_iterations = r.relo_iterations; o->relo_converged = r.relo_converged;
+    std::memcpy(o->relo_pose, r.relo_pose, sizeof(o->relo_pose));
 }
 
 static liloc_host::CloudInfo to_info(const liloc_host_cloud_info& m) {
@@ -72,6 +76,25 @@ int liloc_host_run(void* h, const liloc_host_cloud_info* msgs, int F, liloc_host
         const int rc = liloc_host_handle(h, msgs + i, outs ? outs + i : nullptr);
         if (rc < 0) return rc;
     }
+    return 0;
+}
+
+// relo mode: prior session = n key poses (rows [roll, pitch, yaw, x, y, z, time]) + their key clouds (body frame)
+int liloc_host_load_prior(void* h, const double* keyposes7, int n, const liloc_point* clouds, const long long* offsets) {
+    auto* m = static_cast<mapOptimization*>(h);
+    std::vector<liloc_host::PointTypePose> kp((size_t)(n > 0 ? n : 0));
+    for (int i = 0; i < n; ++i) {
+        const double* r = keyposes7 + 7 * i;
+        kp[i] = liloc_host::PointTypePose{(float)r[3], (float)r[4], (float)r[5], (float)i, (float)r[0], (float)r[1], (float)r[2], r[6]};
+    }
+    return m->loadPriorSession(kp.data(), n, clouds, offsets) ? (int)m->prior().SubMapCenteriod.size() : -1;
+}
+void liloc_host_initialpose(void* h, float x, float y, float yaw) { static_cast<mapOptimization*>(h)->initialposeHandler(x, y, yaw); }
+int liloc_host_submap_info(void* h, int s, float* centroid3, int* first, int* count, int* points) {
+    const auto& p = static_cast<mapOptimization*>(h)->prior();
+    if (s < 0 || s >= (int)p.SubMapCenteriod.size()) return -1;
+    centroid3[0] = p.SubMapCenteriod[s].x; centroid3[1] = p.SubMapCenteriod[s].y; centroid3[2] = p.SubMapCenteriod[s].z;
+    *first = p.submap_first[s]; *count = p.submap_count[s]; *points = p.submap_points[s];
     return 0;
 }
 

@@ -78,7 +78,8 @@ void mapOptimization::reset() {
     timeLastProcessing_ = -1; lastImuPreTransAvailable_ = false;
     lastImuTransformation_ = Affine3f::Identity(); lastImuPreTransformation_ = Affine3f::Identity();
     sel_ids_.clear(); sel_poses_.clear(); have_selection_ = false;
-    if (ctx_) liloc_keyframe_clear(ctx_);
+    prior_ = PriorSession{};
+    if (ctx_) { liloc_keyframe_clear(ctx_); liloc_ndt_clear(ctx_); }
 }
 
 mapOptimization::~mapOptimization() { if (ctx_) liloc_destroy(ctx_); }
@@ -88,6 +89,10 @@ FrameReport mapOptimization::laserCloudInfoHandler(const CloudInfo& msgIn) {
     timeLaserInfoCur = msgIn.stamp;
     cloudInfo = msgIn;                                                         // :252-253
     if (timeLaserInfoCur - timeLastProcessing_ < timeInterval) return rep_;    // :257
+    if (mode == ModeType::RELO && !poseInitialized) {                          // :261-305
+        if (!systemInitialized) return rep_;                                   // "Wait for Initialized Pose ..."
+        if (!relocalizeInit()) { rep_.status = LILOC_ERR_STATE; return rep_; }
+    }
     const double t0 = now_ms();
     have_selection_ = false;
     updateInitialGuess();                  // :309
@@ -98,6 +103,7 @@ FrameReport mapOptimization::laserCloudInfoHandler(const CloudInfo& msgIn) {
     rep_.reg_ms = now_ms() - t0;           // :317-318
     reg_time.push_back(rep_.reg_ms);
     if (mode == ModeType::LIO) saveLIOKeyFramesAndFactor();                    // :327-330
+    else saveRELOKeyFramesAndFactor();                                         // :331-334
     rep_.processed = 1;
     std::memcpy(rep_.pose, transformTobeMapped, sizeof(rep_.pose));
     rep_.is_degenerate = isDegenerate ? 1 : 0;                                 // publishOdometry :1573
@@ -279,6 +285,116 @@ void mapOptimization::saveLIOKeyFramesAndFactor() {
     PointType p3{transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5], (float)id};   // :1423-1427
     PointTypePose p6{p3.x, p3.y, p3.z, p3.intensity, transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2], timeLaserInfoCur};
     if (liloc_keyframe_put_from_scan(ctx_, id) < 0) { error_ = liloc_last_error(ctx_); return; }       // :1453-1457
+    cloudKeyPoses3D.push_back(p3);
+    cloudKeyPoses6D.push_back(p6);
+    rep_.keyframe_id = id;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// relo mode
+// ---------------------------------------------------------------------------------------------------------
+bool mapOptimization::loadPriorSession(const PointTypePose* keyPoses, int n, const liloc_point* clouds, const long long* offsets) {
+    if (!ctx_) { error_ = "no device context"; return false; }
+    if (n <= 0 || !keyPoses || !clouds || !offsets) { error_ = "loadPriorSession: bad arguments"; return false; }
+    prior_ = PriorSession{};
+    prior_.KeyPoses6D.assign(keyPoses, keyPoses + n);
+    for (int i = 0; i < n; ++i) {                                               // loadKeyCloud (dataLoader.hpp:283-304)
+        const long long cnt = offsets[i + 1] - offsets[i];
+        if (liloc_keyframe_put(ctx_, kPriorKeyframeBase + i, clouds + offsets[i], (int)cnt) < 0) { error_ = liloc_last_error(ctx_); return false; }
+    }
+    // generateSubMaps (dataLoader.hpp:306-348): every submap_size key clouds, transformed by their key poses and
+    // concatenated (NOT down-sampled: the filtered copy is overwritten, :332-336); centroid = mean key position
+    float x = 0.f, y = 0.f, z = 0.f;
+    int count = 0, first = 0;
+    std::vector<int> ids; std::vector<float> poses;
+    for (int i = 0; i < n; ++i) {
+        ++count;
+        const PointTypePose& p = prior_.KeyPoses6D[i];
+        ids.push_back(kPriorKeyframeBase + i);
+        const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+        poses.insert(poses.end(), pose6, pose6 + 6);
+        x += p.x; y += p.y; z += p.z;
+        if (count % prior_.submap_size == 0 || i == n - 1) {
+            const int sid = (int)prior_.SubMapCenteriod.size();
+            int leaves = 0, pts = 0;
+            if (liloc_ndt_target_put_keyframes(ctx_, sid, ids.data(), poses.data(), count, ndtResolution, &leaves, &pts) < 0) {
+                error_ = liloc_last_error(ctx_); return false;
+            }
+            prior_.SubMapCenteriod.push_back(PointType{x / (float)count, y / (float)count, z / (float)count, (float)sid});
+            prior_.submap_first.push_back(first); prior_.submap_count.push_back(count); prior_.submap_points.push_back(pts);
+            first = i + 1; count = 0; x = y = z = 0.f; ids.clear(); poses.clear();
+        }
+    }
+    return true;
+}
+
+void mapOptimization::initialposeHandler(float x, float y, float yaw) {        // :755-769: only x, y and yaw are taken
+    transformTobeMappedInit[0] = 0.f; transformTobeMappedInit[1] = 0.f; transformTobeMappedInit[2] = yaw;
+    transformTobeMappedInit[3] = x;   transformTobeMappedInit[4] = y;   transformTobeMappedInit[5] = 0.f;
+    systemInitialized = true;
+}
+
+int mapOptimization::searchNearestSubMap(float x, float y, float z) const {
+    int best = -1; float bd = 0.f;
+    const PointType q{x, y, z, 0.f};
+    for (int i = 0; i < (int)prior_.SubMapCenteriod.size(); ++i) {
+        const float d = sqDist(q, prior_.SubMapCenteriod[i]);
+        if (best < 0 || d < bd) { bd = d; best = i; }
+    }
+    return best;
+}
+
+// registration->setInputTarget(submap) / setInputSource(laserCloudSurfLast) / align x n_align / getFinalTransformation
+int mapOptimization::ndtAlign(int submap, const float guess6[6], int n_align, float out6[6], int* iterations, int* converged) {
+    int rc = liloc_ndt_source_put(ctx_, /*source_id=*/0, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device);
+    if (rc < 0) return rc;
+    liloc_ndt_opts o{};
+    o.step_size = 0.1; o.outlier_ratio = 0.55; o.trans_eps = ndtEpsilon; o.max_iterations = 35;          // pclomp defaults + :178
+    o.search = regMethod == "DIRECT7" ? LILOC_NDT_DIRECT7 : LILOC_NDT_DIRECT1;                           // :181-190
+    o.n_align = n_align;
+    liloc_ndt_job job{};
+    job.target_id = submap; job.source_id = 0;
+    eulerToMatrix4(guess6[0], guess6[1], guess6[2], guess6[3], guess6[4], guess6[5], job.guess);         // :276-280
+    liloc_ndt_out out{};
+    rc = liloc_ndt_align_batch(ctx_, &job, 1, &o, &out);
+    if (rc < 0) return rc;
+    matrix4ToEuler(out.T, out6[0], out6[1], out6[2], out6[3], out6[4], out6[5]);                         // :288-289
+    if (iterations) *iterations = out.iterations;
+    if (converged) *converged = out.converged;
+    return 0;
+}
+
+bool mapOptimization::relocalizeInit() {
+    if (!ctx_) { error_ = "no device context"; return false; }
+    if (prior_.SubMapCenteriod.empty()) { error_ = "relo mode: no prior session loaded"; return false; }
+    const int submap = searchNearestSubMap(transformTobeMappedInit[3], transformTobeMappedInit[4], transformTobeMappedInit[5]);   // :267-270
+    float out6[6];
+    int it = 0, conv = 0;
+    if (ndtAlign(submap, transformTobeMappedInit, /*n_align=*/2, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); return false; }   // :273-287
+    std::memcpy(transformTobeMappedInit, out6, sizeof(out6));                   // :291-296
+    systemInitialized = true; poseInitialized = true;                          // :298-299
+    rep_.relo_initialized = 1; rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
+    std::memcpy(rep_.relo_pose, out6, sizeof(out6));
+    return true;
+}
+
+void mapOptimization::saveRELOKeyFramesAndFactor() {
+    if (rep_.status < 0) return;
+    // optimize->addOdomFactors() -> addScanMatchingFactor() (anchorOptimize.hpp:382-407): one align of the full scan
+    // against the submap nearest to the current pose, started from the current pose.  The reference feeds the result
+    // into its ISAM2 graph (out of scope here); it is reported in the frame report instead.
+    if (!prior_.SubMapCenteriod.empty() && !rep_.relo_initialized) {
+        const int submap = searchNearestSubMap(transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
+        float out6[6]; int it = 0, conv = 0;
+        if (ndtAlign(submap, transformTobeMapped, 1, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); rep_.status = LILOC_ERR_CUDA; return; }
+        rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
+        std::memcpy(rep_.relo_pose, out6, sizeof(out6));
+    }
+    // every processed frame becomes a keyframe (the saveFrame() gate is commented out, :1338-1339)
+    const int id = (int)cloudKeyPoses3D.size();
+    PointType p3{transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5], (float)id};
+    PointTypePose p6{p3.x, p3.y, p3.z, p3.intensity, transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2], timeLaserInfoCur};
+    if (liloc_keyframe_put_from_scan(ctx_, id) < 0) { error_ = liloc_last_error(ctx_); return; }       // :1381-1385
     cloudKeyPoses3D.push_back(p3);
     cloudKeyPoses6D.push_back(p6);
     rep_.keyframe_id = id;

@@ -43,6 +43,21 @@ struct FrameReport {                             // what the reference would pub
     int q_all = 0, map_points = 0, n_raw = 0, n_selected_keyframes = 0;
     int keyframe_id = -1;                        // id if this frame became a keyframe
     double reg_ms = 0.0;                         // reg_time (:307-318): init guess + map + downsample + scan2map
+    // relo mode
+    int relo_initialized = 0;                    // this frame ran the relocalisation init (:261-305)
+    int relo_submap = -1;                        // prior submap the scan was matched against (searchNearestSubMapAndVertex)
+    int relo_iterations = 0, relo_converged = 0;
+    float relo_pose[6] = {0, 0, 0, 0, 0, 0};     // NDT result as [roll, pitch, yaw, x, y, z] (the scan-matching factor's poseTo)
+};
+
+// What mapOptimization keeps of the prior session (dataManager::Session, include/dataManager/dataLoader.hpp:128-391):
+// key poses and the submaps cut every `submap_size` keyframes.  The key clouds and the submap grids live on the device.
+struct PriorSession {
+    std::vector<PointTypePose> KeyPoses6D;       // prior key poses (g2o vertices)
+    std::vector<PointType> SubMapCenteriod;      // mean key position of each submap (:321-325)
+    std::vector<int> submap_first, submap_count; // keyframe range of each submap
+    std::vector<int> submap_points;              // points of each submap cloud
+    int submap_size = 10;
 };
 
 class mapOptimization : public ParamServer {
@@ -85,6 +100,18 @@ public:
     bool saveFrame();                          // :1245-1264
     void saveLIOKeyFramesAndFactor();          // :1391-1461
 
+    // ---- relo mode: relocalisation against a prior session (the NDT side of :171-206, :261-305, :755-769 and of
+    //      AnchorOptimization::addScanMatchingFactor, anchorOptimize.hpp:382-421).  The GTSAM graphs are out of scope
+    //      (SURVEY.md 2, rows 12-13): the registration result is reported, not fused.
+    // Prior key clouds (body frame, concatenated; offsets has n + 1 entries) + key poses -> device keyframes + submaps.
+    bool loadPriorSession(const PointTypePose* keyPoses, int n, const liloc_point* clouds, const long long* offsets);
+    void initialposeHandler(float x, float y, float yaw);                       // :755-769
+    int searchNearestSubMap(float x, float y, float z) const;                   // dataLoader.hpp:350-357 (1-NN on the centroids)
+    bool relocalizeInit();                                                      // :261-305
+    void saveRELOKeyFramesAndFactor();                                          // :1336-1389 (+ anchorOptimize.hpp:382-407)
+    const PriorSession& prior() const { return prior_; }
+    static constexpr int kPriorKeyframeBase = 1 << 24;                          // device keyframe ids of the prior session
+
     Affine3f trans2Affine3f(const float t[6]) { return getTransformation(t[3], t[4], t[5], t[0], t[1], t[2]); }   // :404-406
 
     liloc_s2m_opts s2m_opts{20, 2, 50, 30, 0, 10, 1, {0}};
@@ -103,6 +130,8 @@ private:
     std::vector<float> sel_poses_;
     bool have_selection_ = false;
     FrameReport rep_;
+    PriorSession prior_;
+    int ndtAlign(int submap, const float guess6[6], int n_align, float out6[6], int* iterations, int* converged);
 };
 
 // pcl::VoxelGrid on a handful of key positions (extractNearby :916-917); host-side because it is part of

@@ -25,7 +25,9 @@ class Report(C.Structure):
     _fields_ = [("processed", C.c_int), ("status", C.c_int), ("pose", C.c_float * 6), ("guess", C.c_float * 6),
                 ("is_degenerate", C.c_int), ("iters", C.c_int), ("converged", C.c_int), ("n_sel", C.c_int),
                 ("q_all", C.c_int), ("map_points", C.c_int), ("n_raw", C.c_int), ("n_selected_keyframes", C.c_int),
-                ("keyframe_id", C.c_int), ("reg_ms", C.c_double)]
+                ("keyframe_id", C.c_int), ("reg_ms", C.c_double),
+                ("relo_initialized", C.c_int), ("relo_submap", C.c_int), ("relo_iterations", C.c_int), ("relo_converged", C.c_int),
+                ("relo_pose", C.c_float * 6)]
 
 
 def _load():
@@ -45,6 +47,11 @@ def _load():
     L.liloc_host_run.restype = C.c_int
     L.liloc_host_run.argtypes = [P, C.POINTER(CloudInfo), C.c_int, C.POINTER(Report)]
     L.liloc_host_reset.argtypes = [P]
+    L.liloc_host_load_prior.restype = C.c_int
+    L.liloc_host_load_prior.argtypes = [P, P, C.c_int, P, P]
+    L.liloc_host_initialpose.argtypes = [P, C.c_float, C.c_float, C.c_float]
+    L.liloc_host_submap_info.restype = C.c_int
+    L.liloc_host_submap_info.argtypes = [P, C.c_int, P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.liloc_host_set_s2m_opts.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
     L.liloc_host_num_keyframes.restype = C.c_int
     L.liloc_host_num_keyframes.argtypes = [P]
@@ -145,6 +152,30 @@ class MapOptimization:
         if rc < 0:
             raise RuntimeError(f"liloc_host_run failed ({rc}): " + (lib().liloc_host_error(self._h) or b"").decode())
         return reps
+
+    # ---- relo mode ----
+    def load_prior_session(self, keyposes7, clouds) -> int:
+        """Prior session: key poses (n, 7) [roll, pitch, yaw, x, y, z, time] + their key clouds (body frame).
+        Returns the number of submaps (dataLoader.hpp generateSubMaps, every 10 keyframes)."""
+        kp = np.ascontiguousarray(keyposes7, np.float64).reshape(-1, 7)
+        flat = np.ascontiguousarray(np.concatenate(clouds), np.float32)
+        offs = np.zeros(len(clouds) + 1, np.int64)
+        offs[1:] = np.cumsum([len(c) for c in clouds])
+        n = lib().liloc_host_load_prior(self._h, kp.ctypes.data, len(kp), flat.ctypes.data, offs.ctypes.data)
+        if n < 0:
+            raise RuntimeError("loadPriorSession: " + (lib().liloc_host_error(self._h) or b"").decode())
+        return n
+
+    def initialpose(self, x: float, y: float, yaw: float):
+        """/initialpose (src/mapOptmization.cpp:755-769)."""
+        lib().liloc_host_initialpose(self._h, float(x), float(y), float(yaw))
+
+    def submap_info(self, s: int) -> dict:
+        c = np.zeros(3, np.float32)
+        first, count, pts = C.c_int(), C.c_int(), C.c_int()
+        if lib().liloc_host_submap_info(self._h, s, c.ctypes.data, C.byref(first), C.byref(count), C.byref(pts)) != 0:
+            raise IndexError(s)
+        return {"centroid": c, "first": first.value, "count": count.value, "points": pts.value}
 
     def num_keyframes(self) -> int:
         return lib().liloc_host_num_keyframes(self._h)

@@ -41,6 +41,12 @@ UNIT = "registrations/s"
 YAML = "nclt.yaml"
 
 
+def host_threads(orc) -> int:
+    """All host cores for the CPU arms.  torchrun exports OMP_NUM_THREADS=1 for its workers; the oracle takes its thread
+    count as an argument (an OpenMP num_threads clause), so the launcher's default does not throttle the reference."""
+    return max(int(orc.num_threads()), int(os.cpu_count() or 1))
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -128,7 +134,7 @@ def run_reference(args):
         return
     import oracle_lib as orc
     import ref_pipeline as rp
-    threads = orc.num_threads()
+    threads = host_threads(orc)
     per_step = args.ref_frames
     total = (args.warmup + args.steps) * per_step
     seq = make_workload(max(total, 2), args.seed, n_total=args.frames)   # head of the same 1000-frame sequence
@@ -163,7 +169,7 @@ def cpu_baseline_sample(seq, n_sample: int, budget_s: float):
     """Oracle timed on the box's host cores over the head of the same sequence (rank 0, N = 1)."""
     import oracle_lib as orc
     import ref_pipeline as rp
-    threads = orc.num_threads()
+    threads = host_threads(orc)
     lio = rp.RefLio(rp.Params(YAML), threads=threads)
     warm = min(10, max(len(seq.scans) // 4, 1))
     for f in range(warm):
@@ -461,7 +467,7 @@ def cpu_baseline_ndt(w, args, max_items=None, budget_s=None):
     """The reference's CPU path for the same items (oracle restatement of ndt_omp, OpenMP on all host cores), faithful
     to its redundancy: setInputTarget rebuilds the voxel grid for every align call site (anchorOptimize.hpp:394)."""
     import oracle_lib as orc
-    threads = orc.num_threads()
+    threads = host_threads(orc)
     budget = budget_s if budget_s is not None else args.cpu_budget
     n = len(w["guesses"])
     pick = np.linspace(0, n - 1, min(n, max_items or 64)).astype(int)

@@ -455,6 +455,8 @@ def run_ndt(args):
                      "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
                      "avg_sweep_phase_us": st["sweep_ms"] * 1e3 / max(st["sweep_phases"], 1), "sweep_phases_per_step": st["sweep_phases"] / args.steps,
                      "sweep_share_of_step": sweep_ms * 1e-3 / t_dev_max,
+                     "per_round_us": {"sweep": st["sweep_ms"] * 1e3 / max(st["sweep_phases"], 1), "update": st["update_ms"] * 1e3 / max(st["sweep_phases"], 1),
+                                      "compaction": st["compact_ms"] * 1e3 / max(st["sweep_phases"], 1)},
                      "alg_bytes_per_step_all_ranks": alg / args.steps,
                      "note": "algorithmic bytes = sweeps x (16 P + 36 P c + 224) per job (SURVEY 8d); the leaf gather is served by L2, the per-point math is float with double accumulation"},
         "cpu_baseline": cpu, "clocks": clocks, "host": {"nproc": os.cpu_count()},

@@ -194,6 +194,7 @@ int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const do
 typedef struct {
     long long batches, jobs, sweep_launches, sweep_phases, job_sweeps;
     double sweep_ms, alg_bytes;
+    double update_ms, compact_ms;   /* device time of the per-job state-machine phases and of the active-list compaction */
 } liloc_ndt_stats;
 int liloc_ndt_stats_get(const liloc_ctx* ctx, liloc_ndt_stats* out);
 int liloc_ndt_stats_reset(liloc_ctx* ctx);

@@ -94,7 +94,7 @@ class NdtOpts(C.Structure):
 
 class NdtStats(C.Structure):
     _fields_ = [(k, C.c_longlong) for k in ("batches", "jobs", "sweep_launches", "sweep_phases", "job_sweeps")] + \
-               [(k, C.c_double) for k in ("sweep_ms", "alg_bytes")]
+               [(k, C.c_double) for k in ("sweep_ms", "alg_bytes", "update_ms", "compact_ms")]
 
 
 class NdtJob(C.Structure):

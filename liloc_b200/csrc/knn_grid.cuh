@@ -13,7 +13,7 @@
 // are found and the query is rejected -- the same decision the reference takes.
 //
 // Layout in HBM: map points sorted by cell (x fastest) as float4 {x, y, z, bitcast(original index)};
-// cell_start[ncells + 1] exclusive offsets.  The three x-adjacent cells of a (y, z) row are one
+// cell_start[ncells + 1] exclusive offsets (built by the G phases of pipeline.cuh).  The three x-adjacent cells of a (y, z) row are one
 // contiguous range, so a query reads 9 ranges with coalesced 16-byte loads, one lane per point.
 #pragma once
 #include "common.cuh"
@@ -28,7 +28,7 @@ struct GridParams {
     int ncells;
 };
 
-// The geometry is derived ON THE DEVICE from the local map's bounding box (k_grid_params), so building the
+// The geometry is derived ON THE DEVICE from the local map's bounding box (pipeline.cuh, grid_params_compute), so building the
 // search structure needs no host round trip; consumers read it through this pointer.
 struct GridView {
     const int* __restrict__ cell_start;
@@ -38,142 +38,9 @@ struct GridView {
 
 LILOC_DEV int cell_coord(float v, float inv_cell, int g0) { return (int)floorf(v * inv_cell) - g0; }
 
-__global__ void __launch_bounds__(256) k_zero_int(int* __restrict__ a, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = 0;
-}
-
-// Search-grid geometry from the bounding box of the cloud the map was down-sampled from (a superset of the
-// centroids' box): cell edge 2^k >= 1 m, one cell of padding, at most max_cells cells.  One thread; also
-// zeroes nothing -- the counters are cleared by k_grid_zero once ncells is known.
-__global__ void k_grid_params(const float* __restrict__ mn, const float* __restrict__ mx, const int* __restrict__ M,
-                              int max_cells, GridParams* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float lo[3], hi[3];
-    const bool empty = *M <= 0;
-    for (int a = 0; a < 3; ++a) { lo[a] = empty ? 0.f : mn[a]; hi[a] = empty ? 0.f : mx[a]; }
-    GridParams g;
-    g.ncells = -1;
-    for (int k = 0; k < 24; ++k) {
-        const float inv = 1.0f / (float)(1 << k);
-        long long cells = 1;
-        for (int a = 0; a < 3; ++a) {
-            g.g0[a] = (int)floorf(lo[a] * inv) - 1;
-            const int g1 = (int)floorf(hi[a] * inv) + 1;
-            g.dim[a] = g1 - g.g0[a] + 1;
-            cells *= g.dim[a];
-        }
-        g.inv_cell = inv;
-        if (cells <= (long long)max_cells) { g.ncells = (int)cells; break; }
-    }
-    if (g.ncells < 0) { g.ncells = 1; g.dim[0] = g.dim[1] = g.dim[2] = 1; g.inv_cell = 0.f; g.g0[0] = g.g0[1] = g.g0[2] = 0; }   // unreachable for finite input
-    *out = g;
-}
-
-__global__ void __launch_bounds__(256) k_grid_zero(const GridParams* __restrict__ gp, int* __restrict__ counts) {
-    const int n = gp->ncells;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) counts[i] = 0;
-}
-
-__global__ void __launch_bounds__(256)
-k_grid_count(const float4* __restrict__ map, const int* __restrict__ M_dev, const GridParams* __restrict__ gpp, int* __restrict__ counts) {
-    const GridParams gp = *gpp;
-    const int M = *M_dev;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
-        const float4 p = __ldg(&map[i]);
-        const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
-        const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
-        const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
-        atomicAdd(&counts[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
-    }
-}
-
-// cursor[] starts as a copy of cell_start[]; order inside a cell is arbitrary, which is harmless
-// because the query uses the (d2, index) total order.
-__global__ void __launch_bounds__(256)
-k_grid_scatter(const float4* __restrict__ map, const int* __restrict__ M_dev, const GridParams* __restrict__ gpp,
-               int* __restrict__ cursor, float4* __restrict__ cpts) {
-    const GridParams gp = *gpp;
-    const int M = *M_dev;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
-        const float4 p = __ldg(&map[i]);
-        const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
-        const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
-        const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
-        const int pos = atomicAdd(&cursor[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
-        cpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-    }
-}
-
-// ---- multi-tile exclusive scan of the cell counts (-> cell_start); n = gp->ncells lives on the device,
-// so the kernels run on a fixed launch grid and loop over tiles -------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
-constexpr int kScanTile = kScanThreads * kScanPerThread;
-
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_reduce(const int* __restrict__ in, const GridParams* __restrict__ gp, int* __restrict__ tile_sums) {
-    __shared__ int s_w[kScanThreads / 32];
-    const int n = gp->ncells;
-    const int n_tiles = (n + kScanTile - 1) / kScanTile;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int base = tile * kScanTile;
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            const int i = base + j * kScanThreads + threadIdx.x;
-            if (i < n) c += in[i];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-#pragma unroll
-            for (int w = 0; w < kScanThreads / 32; ++w) t += s_w[w];
-            tile_sums[tile] = t;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_scan_tiles_grid(int* __restrict__ tile_counts, const GridParams* __restrict__ gp, int* __restrict__ total_out) {
-    scan_tiles_body(tile_counts, (gp->ncells + kScanTile - 1) / kScanTile, total_out);
-}
-
-// out[i] = exclusive prefix, out[n] = grand total; `cursor` (which may alias `in`) receives the same values
-// (the scatter cursor).
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_down(const int* in, const GridParams* __restrict__ gp, const int* __restrict__ tile_offsets,
-            int* __restrict__ out, int* cursor) {
-    __shared__ int s_w[kScanThreads / 32];
-    const int n = gp->ncells;
-    const int n_tiles = (n + kScanTile - 1) / kScanTile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int base = tile * kScanTile + threadIdx.x * kScanPerThread;
-        int v[kScanPerThread];
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? in[base + j] : 0; c += v[j]; }
-        int inc = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        __syncthreads();
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        int run = tile_offsets[tile] + inc - c;
-#pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) run += s_w[w];
-#pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            if (base + j < n) { out[base + j] = run; cursor[base + j] = run; }
-            run += v[j];
-            if (base + j == n - 1) { out[n] = run; }
-        }
-    }
-}
+constexpr int kScanTile = kScanThreads * kScanPerThread;     // cells per block and step of the cell-count scan (pipeline.cuh)
 
 // ---- exact 5-NN, one warp per query ---------------------------------------------------------------
 struct Knn5 { float d[5]; int i[5]; };     // ascending (d2, index); i == INT_MAX marks "none"

@@ -520,7 +520,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_ndt_align cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->ndt_max_blocks = per_sm * c->num_sms;
     CUB_(cudaMalloc(&c->d_ndt_counters, 3 * sizeof(int)));
-    CUB_(cudaMalloc(&c->d_ndt_ns, sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_ndt_ns, 3 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_marks, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_marks, 0, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
 #undef CUB_
@@ -1171,7 +1171,7 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
     if ((rc = ensure(ctx, ctx->ndt_pose, (size_t)n_jobs))) return rc;
     CU(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
-    CU(cudaMemsetAsync(ctx->d_ndt_ns, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ndt_ns, 0, 3 * sizeof(unsigned long long), ctx->stream));
     NdtAlignArgs aa{};
     aa.jobs = ctx->d_jobs.p; aa.n_jobs = n_jobs; aa.targets = ctx->d_tviews.p; aa.sources = ctx->d_sviews.p; aa.o = od;
     aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.pose = ctx->ndt_pose.p; aa.active = ctx->ndt_active.p; aa.counters = ctx->d_ndt_counters;
@@ -1187,16 +1187,16 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
         ++ctx->launches;
     }
     int h_counters[3] = {0, 0, 0};
-    unsigned long long h_ns = 0;
+    unsigned long long h_ns[3] = {0, 0, 0};
     CU(cudaMemcpyAsync(h_counters, ctx->d_ndt_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&h_ns, ctx->d_ndt_ns, sizeof(h_ns), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h_ns, ctx->d_ndt_ns, sizeof(h_ns), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(hj.data(), ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
     {
         liloc_ndt_stats& ns = ctx->ndt_stats;
         ns.batches += 1; ns.jobs += n_jobs; ns.sweep_launches += 1; ns.sweep_phases += h_counters[2];
-        ns.sweep_ms += (double)h_ns * 1e-6;
+        ns.sweep_ms += (double)h_ns[0] * 1e-6; ns.update_ms += (double)h_ns[1] * 1e-6; ns.compact_ms += (double)h_ns[2] * 1e-6;
         const int cells = od.search7 ? 7 : 1;
         for (int j = 0; j < n_jobs; ++j) {
             const double P = (double)ctx->ndt_sources[jobs[j].source_id].view.n;

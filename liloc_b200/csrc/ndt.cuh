@@ -604,7 +604,7 @@ struct NdtAlignArgs {
     NdtPoseCache* pose;            // [n_jobs] transform + angle tables of every job's current trial pose
     int* active;                   // [2][n_jobs] double-buffered list of unfinished jobs
     int* counters;                 // [0..1] list lengths, [2] sweep phases executed
-    unsigned long long* sweep_ns;  // accumulated wall time of the sweep phases (block 0), optional
+    unsigned long long* sweep_ns;  // [0] accumulated time of the sweep phases, [1] update phases, [2] compaction phases (block 0; optional)
     int max_sweeps;
 };
 
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
     }
     if (gtid == 0) { a.counters[0] = a.n_jobs; a.counters[1] = 0; a.counters[2] = 0; }
     grid.sync();
-    unsigned long long sweep_ns = 0;
+    unsigned long long sweep_ns = 0, update_ns = 0, compact_ns = 0;
     int cur = 0;
     for (int it = 0; it < a.max_sweeps; ++it) {
         const int n_active = *((volatile int*)&a.counters[cur]);
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
             ndt_sweep_tile<true>(&a.pose[job], a.targets[J.target], src, a.o, tile, sh, a.partial + ((size_t)job * a.tiles_max + tile) * kNdtSums);
         }
         grid.sync();
-        if (a.sweep_ns && gtid == 0) sweep_ns += global_ns() - t0;
+        if (a.sweep_ns && gtid == 0) { const unsigned long long t1 = global_ns(); sweep_ns += t1 - t0; t0 = t1; }
         // ---- update: one warp per active job (all jobs in parallel; the state machine itself is serial) ----
         const int lane = threadIdx.x & 31;
         const int gwarp = gtid >> 5, nwarps = gsize >> 5;
@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
         }
         (void)gwarp;
         grid.sync();
+        if (a.sweep_ns && gtid == 0) { const unsigned long long t1 = global_ns(); update_ns += t1 - t0; t0 = t1; }
         // ---- compaction of the active list (block 0; order preserved so the run is deterministic) ----
         if (blockIdx.x == 0) {
             int* nxt = a.active + (size_t)(cur ^ 1) * a.n_jobs;
@@ -705,9 +706,10 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
             if (threadIdx.x == 0) { a.counters[cur ^ 1] = carry; a.counters[2] = it + 1; }
         }
         grid.sync();
+        if (a.sweep_ns && gtid == 0) compact_ns += global_ns() - t0;
         cur ^= 1;
     }
-    if (a.sweep_ns && gtid == 0) *a.sweep_ns += sweep_ns;
+    if (a.sweep_ns && gtid == 0) { a.sweep_ns[0] += sweep_ns; a.sweep_ns[1] += update_ns; a.sweep_ns[2] += compact_ns; }
 }
 
 }  // namespace liloc

@@ -51,7 +51,11 @@ typedef struct {
     int device;             /* CUDA device ordinal */
     int max_scan_points;    /* N_SCAN * Horizon_SCAN, sizes scratch like allocateMemory() :228-230 */
     int max_raw_points;     /* initial capacity of the concatenated local map (grows on demand) */
-    int reserved[5];
+    int map_cache;          /* [0] 1 = keep the local map + search grid of the previous frame when the selected keyframes,
+                               their poses and the leaf size are bit-identical (the result is a pure function of those
+                               inputs, so outputs do not change; the reference recomputes every frame).  See also
+                               liloc_set_map_cache. */
+    int reserved[4];
 } liloc_config;
 
 /* scan2MapOptimization knobs.  Reference values in brackets. */
@@ -230,6 +234,8 @@ int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int 
 /* ---- timing: CUDA-event milliseconds of the phases of the last liloc_frame / call sequence ------ */
 typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t);
+/* Local-map memoisation (liloc_config.map_cache) on / off at run time; returns the number of frames that reused the map. */
+long long liloc_set_map_cache(liloc_ctx* ctx, int enabled);
 int liloc_set_timing(liloc_ctx* ctx, int enabled);
 /* Device-side latency breakdown of the last liloc_frame / liloc_frame_features made while timing is enabled:
  * %globaltimer nanoseconds written by block 0 at the phase boundaries of the three launches --

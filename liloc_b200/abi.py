@@ -23,8 +23,8 @@ class LilocError(RuntimeError):
 
 
 class _Config(C.Structure):
-    _fields_ = [("device", C.c_int), ("max_scan_points", C.c_int), ("max_raw_points", C.c_int),
-                ("reserved", C.c_int * 5)]
+    _fields_ = [("device", C.c_int), ("max_scan_points", C.c_int), ("max_raw_points", C.c_int), ("map_cache", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 class S2mOpts(C.Structure):
@@ -171,6 +171,7 @@ def _load() -> C.CDLL:
         "liloc_feature_pass": (C.c_int, [P, C.c_int, P, C.c_int, P, P]),
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
         "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
+        "liloc_set_map_cache": (C.c_longlong, [P, C.c_int]),
         "liloc_ndt_target_put_keyframes": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, ip, ip]),
         "liloc_ndt_target_size": (C.c_int, [P, C.c_int]),
         "liloc_ndt_stats_get": (C.c_int, [P, C.POINTER(NdtStats)]),
@@ -191,7 +192,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -208,8 +209,8 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
 class Context:
     """One liloc_ctx (one GPU, one stream).  Mirrors the calls mapOptimization makes per frame."""
 
-    def __init__(self, device: int = 0, max_scan_points: int = 32 * 1800, max_raw_points: int = 1 << 20):
-        cfg = _Config(device, max_scan_points, max_raw_points)
+    def __init__(self, device: int = 0, max_scan_points: int = 32 * 1800, max_raw_points: int = 1 << 20, map_cache: bool = False):
+        cfg = _Config(device, max_scan_points, max_raw_points, int(map_cache))
         h = C.c_void_p()
         rc = lib.liloc_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -488,6 +489,10 @@ class Context:
         out = np.zeros((32, 16), np.float32)
         n = lib.liloc_last_trace(self._h, _ptr(out), iters)
         return out[:n]
+
+    def set_map_cache(self, on: bool) -> int:
+        """Local-map memoisation on / off; returns the number of frames that have reused their map so far."""
+        return int(lib.liloc_set_map_cache(self._h, int(on)))
 
     def last_marks(self) -> np.ndarray:
         """%globaltimer marks of the last timed frame (see include/liloc_gpu.h liloc_last_marks)."""

@@ -113,6 +113,9 @@ struct liloc_ctx {
     FeatClass fc[kClasses];
     int max_cells = 1 << 24;
     long long sort_redos = 0;
+    bool map_cache = false;              // liloc_config.map_cache
+    long long map_cache_hits = 0;
+    struct MapKey { std::vector<int> ids; std::vector<float> poses; float leaf = 0.f; bool valid = false; } map_key[kClasses];
     bool corner_scan_current = false;    // the last scan upload carried corner features too
 
     // scan2map
@@ -317,6 +320,7 @@ int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids
     if (K < 0 || (K > 0 && (!kf_ids || !poses6)) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap: bad arguments");
     int rc;
     fc.have_map = false; fc.M = -1;
+    ctx->map_key[cls].valid = false;
     if ((size_t)K > fc.h_descs_cap) {
         if (fc.h_descs) { CU(cudaFreeHost(fc.h_descs)); fc.h_descs = nullptr; }
         size_t cap = 256; while (cap < (size_t)K) cap *= 2;
@@ -476,6 +480,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     liloc_ctx* c = new liloc_ctx();
     c->device = cfg->device;
     c->num_sms = prop.multiProcessorCount;
+    c->map_cache = cfg->map_cache != 0;
     ctx = c;
     auto bail = [&](int rc) { g_create_error = c->err; liloc_destroy(c); return rc; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
@@ -590,6 +595,7 @@ int liloc_keyframe_put_features(liloc_ctx* ctx, int kf_id, const liloc_point* su
     if (n_surf > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[0], surf, (size_t)n_surf * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     if (n_corner > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[1], corner, (size_t)n_corner * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));          // the caller may free its buffers on return
+    if (ctx->kf.count(kf_id)) for (auto& k : ctx->map_key) k.valid = false;      // an id re-used for new data
     ctx->kf[kf_id] = e;
     ctx->arena_used += (size_t)n_surf + (size_t)n_corner;
     return LILOC_OK;
@@ -612,6 +618,7 @@ int liloc_keyframe_put_from_scan(liloc_ctx* ctx, int kf_id) {
     e.off[0] = ctx->arena_used; e.n[0] = n0; e.off[1] = ctx->arena_used + (size_t)n0; e.n[1] = n1;
     if (n0 > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[0], s.scan.p, (size_t)n0 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     if (n1 > 0) CU(cudaMemcpyAsync(ctx->arena.p + e.off[1], cr.scan.p, (size_t)n1 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->kf.count(kf_id)) for (auto& k : ctx->map_key) k.valid = false;
     ctx->kf[kf_id] = e;
     ctx->arena_used += (size_t)n0 + (size_t)n1;
     return LILOC_OK;
@@ -633,6 +640,7 @@ int liloc_keyframe_clear(liloc_ctx* ctx) {
     ENTER(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->kf.clear(); ctx->arena_used = 0;
+    for (auto& k : ctx->map_key) k.valid = false;
     return LILOC_OK;
 }
 
@@ -663,6 +671,7 @@ int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts, in
     FeatClass& fc = ctx->fc[cls];
     int rc;
     fc.have_map = false; fc.M = -1;
+    ctx->map_key[cls].valid = false;
     if ((rc = ensure(ctx, fc.raw, (size_t)(n > 0 ? n : 1)))) return rc;
     if (n > 0) CU(cudaMemcpyAsync(fc.raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     fc.n_raw = n;
@@ -772,14 +781,27 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks + kPipeMarks : nullptr))) return rc;
     if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
     CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
-    // local maps: descriptors -> assemble -> VoxelGrid -> search grid, one launch for all classes
-    for (int cls = 0; cls < ncls; ++cls)
-        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[cls]))) return rc;
-    pm.n_prob = ncls;
+    // local maps: descriptors -> assemble -> VoxelGrid -> search grid, one launch for all classes.  With map_cache a
+    // class whose (ids, poses, leaf) are bit-identical to the map it already holds is left as it is.
+    for (int cls = 0; cls < ncls; ++cls) {
+        liloc_ctx::MapKey& key = ctx->map_key[cls];
+        const size_t K = (size_t)(in->K > 0 ? in->K : 0);
+        const bool hit = ctx->map_cache && key.valid && ctx->fc[cls].have_map && key.leaf == in->map_leaf[cls] && key.ids.size() == K &&
+                         (K == 0 || (std::memcmp(key.ids.data(), in->kf_ids, K * sizeof(int)) == 0 &&
+                                     std::memcmp(key.poses.data(), in->kf_poses6, K * 6 * sizeof(float)) == 0));
+        if (hit) { ++ctx->map_cache_hits; continue; }
+        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[pm.n_prob]))) return rc;
+        ++pm.n_prob;
+        if (ctx->map_cache) {
+            key.ids.assign(in->kf_ids, in->kf_ids + K); key.poses.assign(in->kf_poses6, in->kf_poses6 + 6 * K);
+            key.leaf = in->map_leaf[cls]; key.valid = true;
+        }
+    }
     tick(ctx, 0, ctx->stream);
     // measured (profiles/): two blocks per SM pay off for the streaming phases only above ~1.5 M raw points; below
     // that the sort (148 blocks) and the gathers are faster with one block per SM
     const bool wide = (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
+    const bool map_launched = pm.n_prob > 0;
     if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks : nullptr, wide))) return rc;
     tick(ctx, 3, ctx->stream);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
@@ -798,7 +820,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     if (ctx->timing) {
         liloc_timing& t = ctx->last_timing;
         const unsigned long long* mk = ctx->h_info->marks;       // phase boundaries of the maps launch (ns)
-        auto span = [&](int i, int j) { return mk[j] > mk[i] ? (float)((double)(mk[j] - mk[i]) * 1e-6) : 0.f; };
+        auto span = [&](int i, int j) { return (map_launched && mk[j] > mk[i]) ? (float)((double)(mk[j] - mk[i]) * 1e-6) : 0.f; };
         t.assemble_ms = span(0, 1);                               // transform + concat + bounding box
         t.map_voxel_ms = span(1, 5);                              // keys, radix sort, run count, centroids
         t.grid_ms = span(5, 7);                                   // search-grid scan + scatter
@@ -812,7 +834,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     ++ctx->stats.frames;
     for (int cls = 0; cls < (corner ? 2 : 1); ++cls) {
         const FeatClass& fc = ctx->fc[cls];
-        ctx->stats.alg_bytes_map += 16.0 * fc.n_raw + 16.0 * (fc.M > 0 ? fc.M : 0);
+        if (map_launched) ctx->stats.alg_bytes_map += 16.0 * fc.n_raw + 16.0 * (fc.M > 0 ? fc.M : 0);
         ctx->stats.alg_bytes_scan += 16.0 * fc.n_scan_last + 16.0 * (fc.Q_all > 0 ? fc.Q_all : 0);
     }
     return s2m_collect(ctx, pose6, res, o);
@@ -1280,6 +1302,13 @@ int liloc_last_marks(liloc_ctx* ctx, unsigned long long* out, int cap) {
     const int n = cap < 2 * kPipeMarks + kS2mMarks ? cap : 2 * kPipeMarks + kS2mMarks;
     std::memcpy(out, ctx->h_info->marks, (size_t)n * sizeof(unsigned long long));
     return n;
+}
+
+long long liloc_set_map_cache(liloc_ctx* ctx, int enabled) {
+    if (!ctx) return LILOC_ERR_ARG;
+    ctx->map_cache = enabled != 0;
+    if (!ctx->map_cache) for (auto& k : ctx->map_key) k.valid = false;
+    return ctx->map_cache_hits;
 }
 
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t) {

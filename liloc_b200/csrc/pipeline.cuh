@@ -224,10 +224,20 @@ LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSme
     sm.hist[threadIdx.x] = 0;
     __syncthreads();
     const int lo = blockIdx.x * g.C, hi = min(q.n, lo + g.C);
-    for (int i = lo + threadIdx.x; i < hi; i += kPipeThreads) {
-        const unsigned key = (unsigned)voxel_key(__ldg(&q.pts[i]), vp, i);
-        keys[i] = key;
-        atomicAdd(&sm.hist[key & 255u], 1);
+#pragma unroll 1
+    for (int i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * kPipeThreads) {      // four point loads in flight per thread
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * kPipeThreads; if (i < hi) p[u] = __ldg(&q.pts[i]); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kPipeThreads;
+            if (i < hi) {
+                const unsigned key = (unsigned)voxel_key(p[u], vp, i);
+                keys[i] = key;
+                atomicAdd(&sm.hist[key & 255u], 1);
+            }
+        }
     }
     __syncthreads();
     q.hist[blockIdx.x * 256 + threadIdx.x] = sm.hist[threadIdx.x];
@@ -251,16 +261,14 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
     // digit offsets of this block: all lower digits of every block + this digit of the blocks before
     {
         int pre = 0, tot = 0;
-        int b = 0;
 #pragma unroll 1
-        for (; b + 16 <= g.nb; b += 16) {                       // 16 independent loads in flight per thread
-            int v[16];
+        for (int b = 0; b < g.nb; b += 16) {                    // 16 independent (predicated) loads in flight per thread:
+            int v[16];                                          // a scalar tail loop would pay one L2 latency per row
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = hcur[(b + u) * 256 + t];
+            for (int u = 0; u < 16; ++u) v[u] = (b + u < g.nb) ? hcur[(b + u) * 256 + t] : 0;
 #pragma unroll
             for (int u = 0; u < 16; ++u) { tot += v[u]; pre += (b + u < (int)blockIdx.x) ? v[u] : 0; }
         }
-        for (; b < g.nb; ++b) { const int v = hcur[b * 256 + t]; tot += v; if (b < (int)blockIdx.x) pre += v; }
         int total;
         const int excl = block_exclusive_scan_256(tot, &total);
         sm.sort.offs[t] = excl + pre;
@@ -348,7 +356,13 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) *q.count = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int part = 0;
-        for (int u = threadIdx.x; u < tile; u += kPipeThreads) part += q.tile_counts[u];
+#pragma unroll 1
+        for (int u0 = threadIdx.x; u0 < tile; u0 += 4 * kPipeThreads) {
+            int v[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[w] = (u0 + w * kPipeThreads < tile) ? q.tile_counts[u0 + w * kPipeThreads] : 0;
+            part += (v[0] + v[1]) + (v[2] + v[3]);
+        }
         const int tile_offset = block_sum_256(part);
         const int base = tile * kRunTile;
         const int cnt = min(kRunTile, n - base);
@@ -434,7 +448,13 @@ LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp) {
     const int n_tiles = (n + kScanTile - 1) / kScanTile;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int part = 0;
-        for (int u = threadIdx.x; u < tile; u += kPipeThreads) part += q.grid_tiles[u];
+#pragma unroll 1
+        for (int u0 = threadIdx.x; u0 < tile; u0 += 4 * kPipeThreads) {
+            int v[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[w] = (u0 + w * kPipeThreads < tile) ? q.grid_tiles[u0 + w * kPipeThreads] : 0;
+            part += (v[0] + v[1]) + (v[2] + v[3]);
+        }
         const int tile_offset = block_sum_256(part);
         const int base = tile * kScanTile + threadIdx.x * kScanPerThread;
         int v[kScanPerThread];

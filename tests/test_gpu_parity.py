@@ -282,6 +282,36 @@ def test_frame_sequence_matches_oracle(gpu_ctx, orc, synth):
     assert gpu_ctx.kernel_launches() > 0
 
 
+def test_map_cache_is_output_identical(gpu_ctx, orc, synth):
+    """liloc_config.map_cache: frames whose keyframe selection, poses and leaf are unchanged reuse the local map and
+    its search grid; every output (pose bits, counters, the map itself) must equal the uncached run."""
+    world = synth.make_world(seed=23)
+    traj = synth.trajectory_line(9, step=0.3, x0=-2)
+    sensor, scan_leaf, map_leaf = synth.VLP16, 0.4, 0.5
+    kfs = [orc.voxelgrid(synth.scan(world, traj[k], sensor, 2300 + k), scan_leaf) for k in range(4)]
+    scans = [synth.scan(world, traj[k], sensor, 2300 + k) for k in range(4, 9)]
+
+    def run(cache):
+        gpu_ctx.keyframe_clear()
+        gpu_ctx.set_map_cache(False)
+        hits0 = gpu_ctx.set_map_cache(cache)
+        for k, c in enumerate(kfs):
+            gpu_ctx.keyframe_put(k, c)
+        ids, poses = [0, 1, 2, 3], traj[:4].astype(np.float32)
+        out = []
+        for j, raw in enumerate(scans):
+            if j == 3:                                   # selection changes once: the cached map must be dropped
+                ids, poses = [1, 2, 3], traj[1:4].astype(np.float32)
+            pose, res, rc = gpu_ctx.frame(ids, poses, map_leaf, raw, scan_leaf, synth.perturb(traj[4 + j], 70 + j, dt=0.05, dr=0.01))
+            out.append((pose.tobytes(), res.iters, res.n_sel, res.converged, res.map_points, res.q_all, gpu_ctx.localmap_get().tobytes()))
+        return out, gpu_ctx.set_map_cache(False) - hits0
+
+    ref, h0 = run(False)
+    got, h1 = run(True)
+    assert h0 == 0 and h1 == 3                           # frames 1, 2 (same selection) and 4 (same as frame 3)
+    assert got == ref
+
+
 def test_errors_are_codes_not_exceptions_from_c(gpu_ctx):
     from liloc_b200 import LilocError
     with pytest.raises(LilocError) as e:

@@ -698,21 +698,23 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
             S2M_CLK(2)
             if (marking && iter < 32) a.marks[2 + 3 * iter] = s2m_global_ns();
             // D: fixed-order reduction of the block partials, identical in every block.  Thread (j, c) sums
-            // blocks j, j + kRedGroups, ... of column c (coalesced 224-byte rows, loads batched ahead of
-            // the dependent adds), then column c adds its kRedGroups group sums in order.
+            // blocks j, j + kRedGroups, ... of column c (coalesced 224-byte rows; an L2 round trip is ~0.5 us here, so
+            // all of a thread's loads are issued before the first add), then column c adds its kRedGroups group sums.
             if (threadIdx.x < kRedGroups * kNSums) {
                 const int c = threadIdx.x % kNSums, j = threadIdx.x / kNSums;
-                const int nb = (int)gridDim.x;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains: FP64 add latency is long
-                int b = j;
-                for (; b + 3 * kRedGroups < nb; b += 4 * kRedGroups) {
-                    const double v0 = __ldcg(&part[(size_t)b * kNSums + c]);
-                    const double v1 = __ldcg(&part[(size_t)(b + kRedGroups) * kNSums + c]);
-                    const double v2 = __ldcg(&part[(size_t)(b + 2 * kRedGroups) * kNSums + c]);
-                    const double v3 = __ldcg(&part[(size_t)(b + 3 * kRedGroups) * kNSums + c]);
-                    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+                const int nb = min((int)gridDim.x, n_tiles);         // blocks beyond the tile count wrote zeros: skip them
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four independent chains
+#pragma unroll 1
+                for (int b = j; b < nb; b += 16 * kRedGroups) {     // 16 (predicated) L2 loads in flight per thread
+                    double v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int bb = b + u * kRedGroups;
+                        v[u] = bb < nb ? __ldcg(&part[(size_t)bb * kNSums + c]) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4) { s0 += v[u]; s1 += v[u + 1]; s2 += v[u + 2]; s3 += v[u + 3]; }
                 }
-                for (; b < nb; b += kRedGroups) s0 += __ldcg(&part[(size_t)b * kNSums + c]);
                 sh.red[j][c] = (s0 + s1) + (s2 + s3);
             }
             __syncthreads();

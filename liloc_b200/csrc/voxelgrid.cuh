@@ -56,6 +56,7 @@ LILOC_DEV void block_minmax_commit(float mn[3], float mx[3], unsigned* __restric
             atomicMax(&enc[3 + a], f2ord(hi));
         }
     }
+    __syncthreads();                          // the staging arrays are reused by the next call (next problem of the phase)
 }
 
 constexpr int kAsmPerThread = 4;

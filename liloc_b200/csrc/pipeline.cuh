@@ -228,7 +228,7 @@ LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSme
     for (int i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * kPipeThreads) {      // four point loads in flight per thread
         float4 p[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int i = i0 + u * kPipeThreads; if (i < hi) p[u] = __ldg(&q.pts[i]); }
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * kPipeThreads; if (i < hi) p[u] = q.pts[i]; }     // plain load: a map cloud was written by phase P0 of this launch
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kPipeThreads;
@@ -371,7 +371,7 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
             const int l = j * kPipeThreads + threadIdx.x;
             if (l < cnt) {
                 sm.run.key[l] = skeys[base + l];
-                sm.run.pt[l] = __ldg(&q.pts[svals[base + l]]);
+                sm.run.pt[l] = q.pts[svals[base + l]];
             }
         }
         if (threadIdx.x == 0) sm.run.prev = (base > 0) ? skeys[base - 1] : 0u;
@@ -406,7 +406,7 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
             if (e == cnt) {                              // run may continue in the next tile(s)
                 int gi = base + cnt;
                 while (gi < n && skeys[gi] == key) {
-                    const float4 p = __ldg(&q.pts[svals[gi]]);
+                    const float4 p = q.pts[svals[gi]];
                     sx += p.x; sy += p.y; sz += p.z; sw += p.w;
                     ++gi; ++len;
                 }

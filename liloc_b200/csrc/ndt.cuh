@@ -338,11 +338,16 @@ struct NdtPoseCache { float T[12]; NdtAng ang; };
 constexpr int kNdtPoseFloats = sizeof(NdtPoseCache) / sizeof(float);
 LILOC_DEV void ndt_pose_cache_fill(const double* x_t, NdtPoseCache* pc) { ndt_pose_to_matrix(x_t, pc->T); ndt_angle_derivatives(x_t, &pc->ang); }
 
-struct NdtSweepShared { NdtPoseCache pc; double red[kNdtThreads / 32][kNdtSums]; };
+constexpr int kNdtWarpCap = 256;          // per-warp ring of gathered (point, leaf) hits: < 32 left over + 32 * 7 new per round
+struct NdtSweepShared {
+    NdtPoseCache pc;
+    double red[kNdtThreads / 32][kNdtSums];
+    int2 hits[kNdtThreads / 32][kNdtWarpCap];      // {source point index, leaf index}
+};
 
-// One tile (kNdtTile source points, kNdtPPT per thread) of one derivative sweep of job J at J.x_t: float per-point
-// terms, double accumulation in registers over the thread's points, then ONE warp-shuffle + shared-memory
-// reduction per tile -> 28 doubles at `out`.  All threads of the block call this together.
+// One tile (kNdtTile source points) of one derivative sweep of a job at its trial pose: cell look-ups, warp-level
+// compaction of the (point, leaf) hits, float per-hit terms with double accumulation in registers, then ONE
+// warp-shuffle + shared-memory reduction per tile -> 28 doubles at `out`.  All threads of the block call this together.
 template <bool kPoseInGlobal>
 LILOC_DEV void ndt_sweep_tile(const NdtPoseCache* __restrict__ pc, const NdtTargetView& tg, const NdtSourceView& src, const NdtOptsDev& o,
                               const int tile, NdtSweepShared& sh, double* __restrict__ out) {
@@ -357,30 +362,97 @@ LILOC_DEV void ndt_sweep_tile(const NdtPoseCache* __restrict__ pc, const NdtTarg
     for (int k = 0; k < kNdtSums; ++k) acc[k] = 0.0;
     const int base = tile * kNdtTile;
     const int ncell = o.search7 ? 7 : 1;
-#pragma unroll 1
-    for (int r = 0; r < kNdtPPT; ++r) {
-        const int i = base + r * kNdtThreads + threadIdx.x;
-        if (i >= src.n) break;
-        const float4 p = __ldg(&src.pts[i]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* T = sh.pc.T;
+    // Only about half of the points fall into a voxel that holds a Gaussian; evaluated in place, half of every warp
+    // idles through the ~800 instructions of ndt_point_cell (ncu: 17 of 32 lanes active on average).  Each warp
+    // therefore gathers its (point, leaf) hits into a small ring in shared memory with ballots -- no block barrier --
+    // and evaluates them 32 at a time with every lane busy.
+    int2* ring = sh.hits[warp];
+    int head = 0, count = 0;                              // warp-uniform
+    auto evaluate = [&](const int2 h) {
+        const float4 p = __ldg(&src.pts[h.x]);
         const float x[3] = {p.x, p.y, p.z};
-        const float* T = sh.pc.T;
         const float xt[3] = {T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3],
                              T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
                              T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11]};
-        for (int c = 0; c < ncell; ++c) {
-            // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
-            const int dx = (c == 1) - (c == 2), dy = (c == 3) - (c == 4), dz = (c == 5) - (c == 6);
-            const int li = ndt_lookup(tg, xt[0], xt[1], xt[2], dx, dy, dz);
-            if (li >= 0) ndt_point_cell(x, xt, &tg.leaves[li], sh.pc.ang, o.d1, (float)o.d2, acc);
+        ndt_point_cell(x, xt, &tg.leaves[h.y], sh.pc.ang, o.d1, (float)o.d2, acc);
+    };
+    if (ncell == 1) {
+        // DIRECT1: the four cell look-ups of a thread (dependent L2 gathers) are issued together, then gathered
+        int li[kNdtPPT];
+#pragma unroll
+        for (int r = 0; r < kNdtPPT; ++r) {
+            const int i = base + r * kNdtThreads + threadIdx.x;
+            li[r] = -1;
+            if (i < src.n) {
+                const float4 p = __ldg(&src.pts[i]);
+                li[r] = ndt_lookup(tg, T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3], T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
+                                   T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11], 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kNdtPPT; ++r) {
+            const unsigned m = __ballot_sync(0xffffffffu, li[r] >= 0);
+            if (li[r] >= 0) ring[count + __popc(m & ((1u << lane) - 1u))] = make_int2(base + r * kNdtThreads + threadIdx.x, li[r]);
+            count += __popc(m);
+        }
+        __syncwarp();
+        while (count >= 32) { evaluate(ring[head + lane]); head += 32; count -= 32; }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < kNdtPPT; ++r) {
+            const int i = base + r * kNdtThreads + threadIdx.x;
+            const bool valid = i < src.n;
+            float xt0 = 0.f, xt1 = 0.f, xt2 = 0.f;
+            if (valid) {
+                const float4 p = __ldg(&src.pts[i]);
+                xt0 = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
+                xt1 = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
+                xt2 = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
+            }
+            for (int c = 0; c < 7; ++c) {
+                // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
+                const int dx = (c == 1) - (c == 2), dy = (c == 3) - (c == 4), dz = (c == 5) - (c == 6);
+                const int li = valid ? ndt_lookup(tg, xt0, xt1, xt2, dx, dy, dz) : -1;
+                const unsigned m = __ballot_sync(0xffffffffu, li >= 0);
+                if (li >= 0) ring[(head + count + __popc(m & ((1u << lane) - 1u))) % kNdtWarpCap] = make_int2(i, li);
+                count += __popc(m);
+            }
+            __syncwarp();
+            while (count >= 32) {
+                evaluate(ring[(head + lane) % kNdtWarpCap]);
+                head = (head + 32) % kNdtWarpCap; count -= 32;
+            }
+            __syncwarp();
         }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < count) evaluate(ring[(head + lane) % kNdtWarpCap]);
+    // Warp reduction of the 28 sums as a reduce-scatter butterfly: at every level a lane keeps one half of its values
+    // and sends the other half to its partner (62 shuffles and 31 adds instead of 280 and 140 for 28 separate trees);
+    // afterwards lane k holds the warp total of sum k.
+    {
+        double v16[16];
+        const bool b16 = (lane & 16) != 0;
 #pragma unroll
-    for (int k = 0; k < kNdtSums; ++k) {
-        double v = acc[k];
+        for (int j = 0; j < 16; ++j) {
+            const double lo = acc[j], hi = (j + 16 < kNdtSums) ? acc[j + 16] : 0.0;
+            v16[j] = (b16 ? hi : lo) + shfl_xor_d(b16 ? lo : hi, 16);
+        }
+        double v8[8];
+        const bool b8 = (lane & 8) != 0;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += shfl_xor_d(v, s);
-        if (lane == 0) sh.red[warp][k] = v;
+        for (int j = 0; j < 8; ++j) v8[j] = (b8 ? v16[j + 8] : v16[j]) + shfl_xor_d(b8 ? v16[j] : v16[j + 8], 8);
+        double v4[4];
+        const bool b4 = (lane & 4) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v4[j] = (b4 ? v8[j + 4] : v8[j]) + shfl_xor_d(b4 ? v8[j] : v8[j + 4], 4);
+        const bool b2 = (lane & 2) != 0, b1 = (lane & 1) != 0;
+        double v2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) v2[j] = (b2 ? v4[j + 2] : v4[j]) + shfl_xor_d(b2 ? v4[j] : v4[j + 2], 2);
+        const double v1 = (b1 ? v2[1] : v2[0]) + shfl_xor_d(b1 ? v2[0] : v2[1], 1);
+        if (lane < kNdtSums) sh.red[warp][lane] = v1;
     }
     __syncthreads();
     if (threadIdx.x < kNdtSums) {

@@ -515,30 +515,52 @@ LILOC_DEV double ndt_trial_value(double a_l, double f_l, double g_l, double a_u,
 // as JacobiSVD would: directions whose singular value is below 6 eps smax are dropped.
 LILOC_DEV void ndt_newton_solve(const double* Hup, const double* g, double* dp) {
     {
+        // every index below is a compile-time constant (full unrolling, row swaps as selects) so that the 6x7 system
+        // can stay in registers instead of being indexed in local memory
         double M[6][7];
-        int k = 0;
-        for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { M[i][j] = Hup[k]; M[j][i] = Hup[k]; ++k; }
+        {
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = i; j < 6; ++j) { M[i][j] = Hup[k]; M[j][i] = Hup[k]; ++k; }
+        }
+#pragma unroll
         for (int i = 0; i < 6; ++i) M[i][6] = -g[i];
         double pmin = 1e300, pmax = 0.0;
         bool ok = true;
-        for (int c = 0; c < 6 && ok; ++c) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
             int pr = c; double best = fabs(M[c][c]);
+#pragma unroll
             for (int r = c + 1; r < 6; ++r) { const double v = fabs(M[r][c]); if (v > best) { best = v; pr = r; } }
-            if (!(best > 0.0) || best != best) { ok = false; break; }
-            if (pr != c) for (int j = c; j < 7; ++j) { const double t = M[c][j]; M[c][j] = M[pr][j]; M[pr][j] = t; }
+            if (!(best > 0.0) || best != best) ok = false;
+#pragma unroll
+            for (int r = c + 1; r < 6; ++r) {
+                const bool sw = pr == r;
+#pragma unroll
+                for (int j = c; j < 7; ++j) { const double a0 = M[c][j], a1 = M[r][j]; M[c][j] = sw ? a1 : a0; M[r][j] = sw ? a0 : a1; }
+            }
             pmin = fmin(pmin, best); pmax = fmax(pmax, best);
             const double inv = 1.0 / M[c][c];
+#pragma unroll
             for (int r = c + 1; r < 6; ++r) {
                 const double f = M[r][c] * inv;
+#pragma unroll
                 for (int j = c + 1; j < 7; ++j) M[r][j] -= f * M[c][j];
             }
         }
         if (ok && pmin > 1e-10 * pmax) {
+            double x[6];
+#pragma unroll
             for (int i = 5; i >= 0; --i) {
                 double v = M[i][6];
-                for (int j = i + 1; j < 6; ++j) v -= M[i][j] * dp[j];
-                dp[i] = v / M[i][i];
+#pragma unroll
+                for (int j = i + 1; j < 6; ++j) v -= M[i][j] * x[j];
+                x[i] = v / M[i][i];
             }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dp[i] = x[i];
             return;
         }
     }
@@ -740,18 +762,22 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
                 sums[q] = __hiloint2double(hi, lo);
             }
             if (lane == 0) {
-                ndt_job_step(J, sums, a.o);
-                if (J.phase == NDT_DONE) {
-                    J.total_iterations += J.nr_iterations; J.total_sweeps += J.sweeps;
-                    if (J.align_pass + 1 < a.o.n_align) {     // registration->align() again from the previous result (:282-290)
-                        const int pass = J.align_pass + 1;
+                // The state machine touches dozens of fields in dependent order: run it on a local copy (one batch of
+                // loads, one of stores) instead of paying an L2 round trip per field.
+                NdtJob L = J;
+                ndt_job_step(L, sums, a.o);
+                if (L.phase == NDT_DONE) {
+                    L.total_iterations += L.nr_iterations; L.total_sweeps += L.sweeps;
+                    if (L.align_pass + 1 < a.o.n_align) {     // registration->align() again from the previous result (:282-290)
+                        const int pass = L.align_pass + 1;
                         float g[12];
-                        for (int i = 0; i < 12; ++i) g[i] = J.Tfinal[i];
-                        ndt_job_begin(J, g);
-                        J.align_pass = pass;
+                        for (int i = 0; i < 12; ++i) g[i] = L.Tfinal[i];
+                        ndt_job_begin(L, g);
+                        L.align_pass = pass;
                     }
                 }
-                if (J.phase != NDT_DONE) ndt_pose_cache_fill(J.x_t, &a.pose[job]);
+                if (L.phase != NDT_DONE) ndt_pose_cache_fill(L.x_t, &a.pose[job]);
+                J = L;
             }
         }
         (void)gwarp;

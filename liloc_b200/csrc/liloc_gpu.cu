@@ -17,6 +17,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -113,6 +114,7 @@ struct liloc_ctx {
     FeatClass fc[kClasses];
     int max_cells = 1 << 24;
     long long sort_redos = 0;
+    bool wide_maps = true;               // local-map launch with two blocks per SM (LILOC_PIPE_NARROW=1 in the environment: one)
     bool map_cache = false;              // liloc_config.map_cache
     long long map_cache_hits = 0;
     struct MapKey { std::vector<int> ids; std::vector<float> poses; float leaf = 0.f; bool valid = false; } map_key[kClasses];
@@ -127,6 +129,7 @@ struct liloc_ctx {
     int s2m_max_blocks = 0;
     int pipe_blocks = 0;                 // blocks of a narrow point-cloud pipeline launch (one per SM)
     int pipe_blocks_wide = 0;            // blocks of a wide one (two per SM when three fit, so wide + narrow co-reside)
+    int* d_sm_scratch = nullptr;             // 2 x kSmScratch ints, zero between launches (pipeline.cuh)
     unsigned long long* d_marks = nullptr;   // 2 x kPipeMarks phase timestamps (maps launch, scans launch) + kS2mMarks
     int s2m_nq_last = 0;
     int s2m_nq_corner_last = 0;
@@ -294,11 +297,13 @@ int prob_add_grid(liloc_ctx* ctx, FeatClass& fc, int m_upper, VgProb* q) {
     return 0;
 }
 
-// `wide`: two blocks per SM (the local maps: streaming phases over 10^5..10^6 points); otherwise one block per SM
-// (the scans), so that a wide and a narrow launch are co-resident (3 blocks of 80 registers x 256 threads per SM).
+// `wide`: two blocks per SM (local maps above ~1.5 M raw points, whose streaming phases want the extra loads in flight;
+// the concurrent scan launch then waits for a free slot); otherwise one block per SM, so that the map and the scan
+// launch are co-resident (2 blocks of 96 registers x 256 threads per SM).
 int pipe_launch(liloc_ctx* ctx, cudaStream_t st, PipeArgs& a, unsigned long long* marks, bool wide = false) {
     if (a.n_prob <= 0) return 0;
     a.marks = marks;
+    a.sm_scratch = ctx->d_sm_scratch + (st == ctx->stream2 ? kSmScratch : 0);     // the two launches of a frame overlap
     void* args[] = {&a};
     const int blocks = wide ? ctx->pipe_blocks_wide : ctx->pipe_blocks;
     CU(cudaLaunchCooperativeKernel((void*)k_voxel_pipeline, dim3((unsigned)blocks), dim3(kPipeThreads), args, 0, st));
@@ -481,6 +486,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     c->device = cfg->device;
     c->num_sms = prop.multiProcessorCount;
     c->map_cache = cfg->map_cache != 0;
+    { const char* e = getenv("LILOC_PIPE_NARROW"); c->wide_maps = !(e && e[0] == '1'); }
     ctx = c;
     auto bail = [&](int rc) { g_create_error = c->err; liloc_destroy(c); return rc; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
@@ -520,12 +526,14 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_pipeline, kPipeThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_voxel_pipeline cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->pipe_blocks = c->num_sms;
-    c->pipe_blocks_wide = per_sm >= 3 ? 2 * c->num_sms : c->num_sms;
+    c->pipe_blocks_wide = per_sm >= 3 ? 2 * c->num_sms : c->num_sms;      // wide (2 per SM) + narrow (1 per SM) must co-reside
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ndt_align, kNdtThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_ndt_align cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->ndt_max_blocks = per_sm * c->num_sms;
     CUB_(cudaMalloc(&c->d_ndt_counters, 3 * sizeof(int)));
     CUB_(cudaMalloc(&c->d_ndt_ns, 3 * sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_sm_scratch, 2 * kSmScratch * sizeof(int)));
+    CUB_(cudaMemset(c->d_sm_scratch, 0, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMalloc(&c->d_marks, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_marks, 0, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
 #undef CUB_
@@ -564,7 +572,7 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
-    fr(c->d_marks);
+    fr(c->d_marks); fr(c->d_sm_scratch);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
@@ -798,9 +806,9 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         }
     }
     tick(ctx, 0, ctx->stream);
-    // measured (profiles/): two blocks per SM pay off for the streaming phases only above ~1.5 M raw points; below
-    // that the sort (148 blocks) and the gathers are faster with one block per SM
-    const bool wide = (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
+    // measured (profiles/frame_latency_r01.md): two blocks per SM pay off for the streaming phases above ~1.5 M raw
+    // points (Mid-360 map: 394 -> 332 us); below that one block per SM is as fast or faster (centroid gathers)
+    const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
     const bool map_launched = pm.n_prob > 0;
     if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks : nullptr, wide))) return rc;
     tick(ctx, 3, ctx->stream);

@@ -70,7 +70,9 @@ struct PipeArgs {
     VgProb prob[kMaxProbs];
     int n_prob;
     unsigned long long* marks;   // optional: %globaltimer (ns) at every phase boundary, written by block 0 (latency breakdown)
+    int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters + the sort-block counter
 };
+constexpr int kSmScratch = 513;
 
 LILOC_DEV unsigned long long global_ns() {
     unsigned long long t;
@@ -145,10 +147,13 @@ LILOC_DEV int block_sum_256(int v) {                        // all 256 threads; 
     return t;
 }
 
-struct SortGeom { int C, nb; };                            // items per sorting block (multiple of 256), busy blocks
-LILOC_DEV SortGeom sort_geom(int n) {
+// The sort runs on at most one block per SM (more blocks only add histogram rows for every block to read).  With two
+// blocks per SM resident, WHICH blocks sort is decided at run time: the first block to arrive on an SM takes a sort
+// index (s_sort_idx), the others get -1; s_nsort = number of sorting blocks.
+struct SortGeom { int C, nb; };                            // items per sorting block (whole tiles), busy sort blocks
+LILOC_DEV SortGeom sort_geom(int n, int nsort) {
     SortGeom g;
-    const int gs = min((int)gridDim.x, kSortBlocksMax);
+    const int gs = max(1, min(nsort, kSortBlocksMax));
     // whole 1024-item tiles per block: finer chunks put more blocks to work but every block reads every busy
     // block's histogram row (O(nb^2) L2 traffic), which measured slower (profiles/frame_latency_r01.md)
     g.C = (((n + gs - 1) / gs + kSortTile - 1) / kSortTile) * kSortTile;
@@ -183,15 +188,29 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
                 s_k0 = lo;
             }
             __syncthreads();
+            // addresses first, then all loads of the thread in flight, then the transforms
             int k = s_k0;
+            const KfDesc* d[kAsmPerThread];
+            float4 p[kAsmPerThread];
 #pragma unroll
             for (int j = 0; j < kAsmPerThread; ++j) {
                 const int i = base + j * kPipeThreads + threadIdx.x;
+                d[j] = nullptr;
                 if (i < q.n) {
                     while (k + 1 < q.K && q.descs[k + 1].dst_off <= i) ++k;
-                    const KfDesc* d = &q.descs[k];
-                    const float4 p = __ldg(&q.arena[d->src_off + (i - d->dst_off)]);
-                    const float4 o = apply_T(d->T, p);
+                    d[j] = &q.descs[k];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kAsmPerThread; ++j) {
+                const int i = base + j * kPipeThreads + threadIdx.x;
+                if (d[j]) p[j] = __ldg(&q.arena[d[j]->src_off + (i - d[j]->dst_off)]);
+            }
+#pragma unroll
+            for (int j = 0; j < kAsmPerThread; ++j) {
+                const int i = base + j * kPipeThreads + threadIdx.x;
+                if (d[j]) {
+                    const float4 o = apply_T(d[j]->T, p[j]);
                     q.raw[i] = o;
                     mn[0] = fminf(mn[0], o.x); mx[0] = fmaxf(mx[0], o.x);
                     mn[1] = fminf(mn[1], o.y); mx[1] = fmaxf(mx[1], o.y);
@@ -217,13 +236,13 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
 }
 
 // ---- P1: keys + histogram of the first pass ----------------------------------------------------------------------
-LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSmem& sm) {
-    const SortGeom g = sort_geom(q.n);
-    if ((int)blockIdx.x >= g.nb) return;
+LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSmem& sm, const int sidx, const int nsort) {
+    const SortGeom g = sort_geom(q.n, nsort);
+    if (sidx < 0 || sidx >= g.nb) return;
     unsigned* keys = q.keys[(npass + 1) & 1];                  // so that the last pass lands in buffer 1
     sm.hist[threadIdx.x] = 0;
     __syncthreads();
-    const int lo = blockIdx.x * g.C, hi = min(q.n, lo + g.C);
+    const int lo = sidx * g.C, hi = min(q.n, lo + g.C);
 #pragma unroll 1
     for (int i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * kPipeThreads) {      // four point loads in flight per thread
         float4 p[4];
@@ -240,14 +259,14 @@ LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSme
         }
     }
     __syncthreads();
-    q.hist[blockIdx.x * 256 + threadIdx.x] = sm.hist[threadIdx.x];
+    q.hist[sidx * 256 + threadIdx.x] = sm.hist[threadIdx.x];
     __syncthreads();
 }
 
 // ---- one radix pass: offsets, stable in-tile ranking, scatter, next histogram --------------------------------------
-LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm) {
-    const SortGeom g = sort_geom(q.n);
-    if ((int)blockIdx.x >= g.nb) return;
+LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm, const int sidx, const int nsort) {
+    const SortGeom g = sort_geom(q.n, nsort);
+    if (sidx < 0 || sidx >= g.nb) return;
     const int src = (npass + 1 + pass) & 1, dst = src ^ 1;
     const unsigned* __restrict__ skeys = q.keys[src];
     const unsigned* __restrict__ svals = (pass == 0) ? nullptr : q.vals[src];      // pass 0: value = source index
@@ -267,7 +286,7 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
 #pragma unroll
             for (int u = 0; u < 16; ++u) v[u] = (b + u < g.nb) ? hcur[(b + u) * 256 + t] : 0;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) { tot += v[u]; pre += (b + u < (int)blockIdx.x) ? v[u] : 0; }
+            for (int u = 0; u < 16; ++u) { tot += v[u]; pre += (b + u < sidx) ? v[u] : 0; }
         }
         int total;
         const int excl = block_exclusive_scan_256(tot, &total);
@@ -276,8 +295,8 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
         for (int u = 0; u < kSortUnits; ++u) sm.sort.cnt[u][t] = 0;
     }
     __syncthreads();
-    if (pass >= 1) hzero[blockIdx.x * 256 + t] = 0;            // free since the previous barrier; needed two passes on
-    const int lo = blockIdx.x * g.C, hi = min(q.n, lo + g.C);
+    if (pass >= 1) hzero[sidx * 256 + t] = 0;                  // free since the previous barrier; needed two passes on
+    const int lo = sidx * g.C, hi = min(q.n, lo + g.C);
     int carry = 0;                                              // items of digit t in the tiles already scattered
     for (int base = lo; base < hi; base += kSortTile) {
         const int rounds = min(kSortRounds, (hi - base + kPipeThreads - 1) / kPipeThreads);
@@ -397,11 +416,23 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
             const unsigned key = sm.run.key[l];
             float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
             int e = l;
-            do {
-                const float4 p = sm.run.pt[e];
-                sx += p.x; sy += p.y; sz += p.z; sw += p.w;
-                ++e;
-            } while (e < cnt && sm.run.key[e] == key);
+            // four elements per trip: the keys and points of a trip are loaded together, so a long run (a voxel seen by
+            // many keyframes) costs the four dependent float adds per element, not a shared-memory latency per element
+            bool more = true;
+            while (more) {
+                float4 pp[4]; bool same[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ee = min(e + u, cnt - 1);
+                    same[u] = (e + u < cnt) && sm.run.key[ee] == key;
+                    pp[u] = sm.run.pt[ee];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (more && same[u]) { sx += pp[u].x; sy += pp[u].y; sz += pp[u].z; sw += pp[u].w; ++e; }
+                    else more = false;
+                }
+            }
             int len = e - l;
             if (e == cnt) {                              // run may continue in the next tile(s)
                 int gi = base + cnt;
@@ -485,13 +516,22 @@ LILOC_DEV void pipe_cells_scatter(const VgProb& q, const GridParams& gp) {
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPipeThreads, 2) k_voxel_pipeline(const __grid_constant__ PipeArgs a) {
+__global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid_constant__ PipeArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) PipeSmem sm;
     __shared__ VgParams s_vp[kMaxProbs];
     __shared__ GridParams s_gp[kMaxProbs];
     __shared__ int s_npass[kMaxProbs];
     const int np = a.n_prob;
+    __shared__ int s_sort_idx, s_nsort;
+    if (threadIdx.x == 0) {                      // the first block to arrive on an SM becomes that SM's sorting block
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int slot = atomicAdd(&a.sm_scratch[smid & 511u], 1);
+        int idx = -1;
+        if (slot == 0) { idx = atomicAdd(&a.sm_scratch[512], 1); if (idx >= kSortBlocksMax) idx = -1; }
+        s_sort_idx = idx;
+    }
     int mark = 0;
 #define PIPE_MARK() do { if (a.marks && blockIdx.x == 0 && threadIdx.x == 0 && mark < kPipeMarks) a.marks[mark] = global_ns(); ++mark; } while (0)
     PIPE_MARK();                                                                          // 0 start
@@ -499,6 +539,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_voxel_pipeline(const __grid
     grid.sync();
     PIPE_MARK();                                                                          // 1 after assemble + bbox
 
+    if (threadIdx.x == 0) s_nsort = min(__ldcg(&a.sm_scratch[512]), kSortBlocksMax);
     if (threadIdx.x < np) {                                                               // P1
         const VgProb& q = a.prob[threadIdx.x];
         const VgParams vp = vg_params_compute(q.enc, q.leaf, q.n);
@@ -512,12 +553,14 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_voxel_pipeline(const __grid
     __syncthreads();
     int max_pass = 0;
     for (int p = 0; p < np; ++p) max_pass = max(max_pass, s_npass[p]);
-    for (int p = 0; p < np; ++p) if (a.prob[p].n > 0) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm);
+    const int sidx = s_sort_idx, nsort = s_nsort;
+    for (int p = 0; p < np; ++p) if (a.prob[p].n > 0) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm, sidx, nsort);
     grid.sync();
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < kSmScratch; i += kPipeThreads) a.sm_scratch[i] = 0;   // re-armed for the next launch
     PIPE_MARK();                                                                          // 2 after keys
 
     for (int pass = 0; pass < max_pass; ++pass) {                                         // radix passes
-        for (int p = 0; p < np; ++p) if (pass < s_npass[p]) pipe_sort_pass(a.prob[p], s_npass[p], pass, sm);
+        for (int p = 0; p < np; ++p) if (pass < s_npass[p]) pipe_sort_pass(a.prob[p], s_npass[p], pass, sm, sidx, nsort);
         grid.sync();
     }
     if (blockIdx.x == 0 && threadIdx.x < 6 * np) {                                        // re-arm the bounding boxes

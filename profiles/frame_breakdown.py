@@ -62,6 +62,20 @@ def main():
         ex = {"n_scan": len(raw), "q_all": res.q_all, "map_points": res.map_points, "n_raw": int(sum(len(c) for c in kfs)), "iters": res.iters}
     out = {k: float(np.median([r[k] for r in rows])) / 1e3 for k in rows[0]}
     out["wall_us(p50 host clock per frame call)"] = float(np.median(wall[20:]))
+    if os.environ.get("CPU", "1") != "0":
+        # the reference's CPU path on the same frame (oracle restatement, OpenMP on all host cores; faithful redundancy:
+        # re-concatenation, single-threaded VoxelGrid, search tree rebuilt) -- the north_star's p50 latency comparison
+        threads = max(orc.num_threads(), os.cpu_count() or 1)
+        pts = np.concatenate(kfs); offs = np.zeros(n_kf + 1, np.int64); offs[1:] = np.cumsum([len(c) for c in kfs])
+        cpu_ms = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            rp, rres, rrc, M, Q, ms = orc.frame(pts, offs, poses, map_leaf, raw, scan_leaf, guess, orc.S2mOpts(knn=1, threads=threads))
+            cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        assert (rres.iters, rres.n_sel) == (res.iters, res.n_sel) and np.abs(rp - pose).max() < 1e-4
+        out["cpu_reference_ms(p50, %d threads)" % threads] = float(np.median(cpu_ms)) * 1e3      # printed in us like the rest
+        out["cpu_reference.assemble+mapDS"] = float(ms[0]) * 1e3; out["cpu_reference.scanDS"] = float(ms[1]) * 1e3; out["cpu_reference.scan2map"] = float(ms[2]) * 1e3
+        out["p50 latency ratio CPU reference / GPU frame call"] = float(np.median(cpu_ms)) * 1e3 / out["wall_us(p50 host clock per frame call)"]
     print(f"# frame latency breakdown, {name}, {ex}, median of {reps} frames, microseconds")
     for k, v in out.items():
         print(f"{k:45s} {v:9.2f}")

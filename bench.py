@@ -336,12 +336,11 @@ def make_ndt_workload(args):
     """Targets (prior-session submaps: 10 consecutive un-down-sampled scans in the map frame, dataLoader.hpp:306-348),
     sources (full de-skewed scans) and the (target, source, guess) item list.  Identical on every rank (seeded)."""
     from liloc_b200 import synth, relo
-    import oracle_lib as orc            # only to transform clouds while building INPUTS
     rng = np.random.default_rng(args.seed)
     if args.workload == "relo":
         world = synth.make_world(seed=args.seed)
         traj = synth.trajectory_line(12, step=1.0, x0=-5)
-        sub = np.concatenate([orc.transform_cloud(synth.scan(world, traj[k], synth.VLP16, 30 + k), traj[k].astype(np.float32), threads=8) for k in range(10)])
+        sub = np.concatenate([synth.transform_cloud(synth.scan(world, traj[k], synth.VLP16, 30 + k), traj[k]) for k in range(10)])
         src = synth.scan(world, traj[10], synth.VLP16, 77)
         guesses = relo.hypothesis_grid(traj[10], 16, 16, 2.0, seed=args.seed)[: args.items or 256]
         n = len(guesses)
@@ -351,7 +350,7 @@ def make_ndt_workload(args):
     n_sub = args.submaps
     n_frames = n_sub * 10
     seq = synth.make_sequence(synth.VLP16, n_frames, seed=args.seed, dt=0.1)
-    targets = {s: np.concatenate([orc.transform_cloud(seq.scans[10 * s + k], seq.truth[10 * s + k].astype(np.float32), threads=8) for k in range(10)])
+    targets = {s: np.concatenate([synth.transform_cloud(seq.scans[10 * s + k], seq.truth[10 * s + k]) for k in range(10)])
                for s in range(n_sub)}
     if args.workload == "jfgo":
         f = n_frames // 2 + 3

@@ -136,6 +136,17 @@ def split_features(world: np.ndarray, pose6, scan_body: np.ndarray, tol: float =
     return np.ascontiguousarray(scan_body[is_corner]), np.ascontiguousarray(scan_body[~is_corner])
 
 
+def transform_cloud(pts: np.ndarray, pose6) -> np.ndarray:
+    """Body-frame cloud -> map frame by the pose [roll, pitch, yaw, x, y, z] (float32 result; used to build synthetic
+    prior-session submaps, i.e. inputs -- the product's own transform runs on the device)."""
+    p = np.asarray(pose6, np.float64)
+    R = rot_zyx(p[0], p[1], p[2]).astype(np.float32)
+    out = np.empty_like(pts, dtype=np.float32)
+    out[:, :3] = pts[:, :3].astype(np.float32) @ R.T + p[3:6].astype(np.float32)
+    out[:, 3] = pts[:, 3]
+    return out
+
+
 def perturb(pose6, seed: int, dt=0.10, dr=0.02) -> np.ndarray:
     """Initial guess = ground truth + U(+-dt m, +-dr rad) per axis."""
     rng = np.random.default_rng(seed)

@@ -1,4 +1,7 @@
-"""Device-side latency breakdown of one lio frame (run on the GPU box):  python profiles/frame_breakdown.py [vlp16|hdl32|mid360]
+"""Device-side latency breakdown of one lio frame (run on the GPU box):  python tests/tools/frame_breakdown.py [vlp16|hdl32|mid360]
+
+(Lives under tests/ because it also times the CPU oracle on the same frame; nothing outside tests/, smoke() and
+bench.py's CPU legs may touch oracle/.)
 
 Prints the median duration of every phase of the three launches of a frame (local-map pipeline, scan pipeline,
 registration) from the %globaltimer marks block 0 writes at the phase boundaries (liloc_last_marks), next to the
@@ -10,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 

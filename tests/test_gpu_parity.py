@@ -85,6 +85,35 @@ def test_voxelgrid_edge_cases(gpu_ctx, orc):
     assert np.array_equal(gpu_ctx.voxelgrid(pts, 0.5), orc.voxelgrid(pts, 0.5))
 
 
+@pytest.mark.parametrize("n", [255, 256, 257, 1023, 1024, 1025, 148 * 1024 - 1, 148 * 1024, 148 * 1024 + 1, 300001])
+def test_voxelgrid_sort_tile_boundaries(gpu_ctx, orc, n):
+    """Sizes around the tile / chunk boundaries of the in-kernel radix sort (256-thread rounds, 1024-item tiles,
+    148 sorting blocks)."""
+    rng = np.random.default_rng(n)
+    pts = (rng.normal(size=(n, 4)) * np.array([25, 14, 2, 50])).astype(np.float32)
+    assert np.array_equal(gpu_ctx.voxelgrid(pts, 0.4), orc.voxelgrid(pts, 0.4))
+
+
+def test_voxelgrid_sort_key_widths_and_long_runs(gpu_ctx, orc):
+    rng = np.random.default_rng(77)
+    # 1..4 radix passes: the key width is decided on the device from the bounding box
+    for extent, leaf in ((3.0, 0.5), (40.0, 0.4), (400.0, 0.4), (900.0, 0.1)):
+        pts = rng.uniform(-extent, extent, (40000, 4)).astype(np.float32)
+        pts[:, 2] *= 0.05
+        got, ref = gpu_ctx.voxelgrid(pts, leaf), orc.voxelgrid(pts, leaf)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (extent, leaf)
+    # one voxel holding 300 k points (a run across ~300 tiles and every sorting block) next to sparse ones
+    pts = np.concatenate([rng.uniform(0.01, 0.19, (300000, 4)), rng.uniform(-30, 30, (5000, 4))]).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    assert np.array_equal(gpu_ctx.voxelgrid(pts, 0.2), orc.voxelgrid(pts, 0.2))
+    # a skewed digit distribution: everything on one line along x (only the low key bits vary), then along z
+    for axis in (0, 2):
+        pts = np.zeros((60000, 4), np.float32)
+        pts[:, axis] = rng.uniform(-200, 200, 60000)
+        pts[:, 3] = np.arange(60000)
+        assert np.array_equal(gpu_ctx.voxelgrid(pts, 0.3), orc.voxelgrid(pts, 0.3))
+
+
 def test_localmap_build_bit_exact(gpu_ctx, orc, scene_hdl):
     s = scene_hdl
     gpu_ctx.keyframe_clear()

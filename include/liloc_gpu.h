@@ -191,6 +191,17 @@ int liloc_ndt_target_get(liloc_ctx* ctx, int target_id, double* means, float* ic
 /* one derivative sweep at pose p6 = [tx,ty,tz,rx,ry,rz] (tests): out28 = score, gradient[6], Hessian upper[21] */
 int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const double* p6, const liloc_ndt_opts* opts, double* out28);
 
+/* ---- ICP fitness score: AnchorOptimization::getICPFitnessScore (include/egoOptimization/anchorOptimize.hpp:465-481) ----
+ * Mean SQUARED distance from every point of cloud 1 to its nearest neighbour in cloud 2 (pcl::registration::
+ * CorrespondenceEstimation::determineCorrespondences with its default, unbounded, maximum distance), summed sequentially
+ * in source order in float like the reference.  Each cloud is first transformed by its pose6 (transformPointCloud,
+ * :425, :439; NULL = identity).  The `_resident` form takes cloud 1 from the keyframe store and cloud 2 from an NDT
+ * source -- what addScanMatchingFactor compares (:427-442): a prior vertex' key cloud against the current scan --
+ * so nothing crosses PCIe. */
+int liloc_icp_fitness(liloc_ctx* ctx, const liloc_point* cloud1, int n1, const float* pose6_1,
+                      const liloc_point* cloud2, int n2, const float* pose6_2, float* score_out);
+int liloc_icp_fitness_resident(liloc_ctx* ctx, int kf_id, const float* pose6_kf, int ndt_source_id, const float* pose6_src, float* score_out);
+
 /* Cumulative NDT counters since liloc_create / liloc_ndt_stats_reset.  A batch is ONE launch of the persistent
  * kernel k_ndt_align; sweep_phases counts its lock-step derivative sweeps, sweep_ms their device time (%globaltimer
  * around each sweep phase incl. its grid barrier, recorded only while timing is enabled); alg_bytes are the

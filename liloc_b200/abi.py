@@ -172,6 +172,8 @@ def _load() -> C.CDLL:
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
         "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
         "liloc_set_map_cache": (C.c_longlong, [P, C.c_int]),
+        "liloc_icp_fitness": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P, fp]),
+        "liloc_icp_fitness_resident": (C.c_int, [P, C.c_int, P, C.c_int, P, fp]),
         "liloc_ndt_target_put_keyframes": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, ip, ip]),
         "liloc_ndt_target_size": (C.c_int, [P, C.c_int]),
         "liloc_ndt_stats_get": (C.c_int, [P, C.POINTER(NdtStats)]),
@@ -192,7 +194,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -419,6 +421,22 @@ class Context:
         else:
             p = _cloud(pts_body)
             self._chk(lib.liloc_ndt_source_put(self._h, source_id, _ptr(p), len(p), 0))
+
+    def icp_fitness(self, cloud1, pose6_1, cloud2, pose6_2) -> float:
+        a, b = _cloud(cloud1), _cloud(cloud2)
+        p1 = None if pose6_1 is None else np.ascontiguousarray(pose6_1, np.float32).reshape(6)
+        p2 = None if pose6_2 is None else np.ascontiguousarray(pose6_2, np.float32).reshape(6)
+        out = C.c_float()
+        self._chk(lib.liloc_icp_fitness(self._h, _ptr(a), len(a), None if p1 is None else _ptr(p1), _ptr(b), len(b),
+                                        None if p2 is None else _ptr(p2), C.byref(out)))
+        return out.value
+
+    def icp_fitness_resident(self, kf_id: int, pose6_kf, source_id: int, pose6_src) -> float:
+        p1 = np.ascontiguousarray(pose6_kf, np.float32).reshape(6)
+        p2 = np.ascontiguousarray(pose6_src, np.float32).reshape(6)
+        out = C.c_float()
+        self._chk(lib.liloc_icp_fitness_resident(self._h, kf_id, _ptr(p1), source_id, _ptr(p2), C.byref(out)))
+        return out.value
 
     def ndt_stats(self, reset: bool = False) -> dict:
         st = NdtStats()

@@ -151,4 +151,80 @@ k_knn5(const float4* __restrict__ queries, int nq, GridView g, int* __restrict__
     }
 }
 
+// ---- exact UNBOUNDED 1-NN (pcl::registration::CorrespondenceEstimation, max distance = infinity) -------------------
+// Replaces the kd-tree query of AnchorOptimization::getICPFitnessScore (include/egoOptimization/anchorOptimize.hpp:465-481).
+// A group of kKnnLanes lanes owns one query and searches cubic shells of cells around the query's cell, ring by ring.
+// After rings 0..r every unseen point lies in a cell at Chebyshev distance >= r + 1, i.e. farther than r cell edges from
+// the query, so the search stops as soon as best <= (r * edge)^2 (or the shells have left the grid).  Distance as
+// FLANN's L2_Simple: ((dx^2) + (dy^2)) + (dz^2) in float.
+__global__ void __launch_bounds__(256)
+k_nn1_dist2(const float4* __restrict__ queries, int nq, const float* __restrict__ T12, GridView g, float* __restrict__ d2_out) {
+    const GridParams gp = *g.p;
+    __shared__ float sT[12];
+    if (threadIdx.x < 12) sT[threadIdx.x] = T12[threadIdx.x];
+    __syncthreads();
+    const int sub = threadIdx.x % kKnnLanes;
+    const int groups_per_grid = (gridDim.x * blockDim.x) / kKnnLanes;
+    const int nq_pad = ((nq + groups_per_grid - 1) / groups_per_grid) * groups_per_grid;     // keep warps converged
+    const float edge = 1.0f / gp.inv_cell;
+    for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kKnnLanes; qi < nq_pad; qi += groups_per_grid) {
+        const bool active = qi < nq;
+        const float4 q = active ? apply_T(sT, __ldg(&queries[qi])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int cx = cell_coord(q.x, gp.inv_cell, gp.g0[0]);
+        const int cy = cell_coord(q.y, gp.inv_cell, gp.g0[1]);
+        const int cz = cell_coord(q.z, gp.inv_cell, gp.g0[2]);
+        // the last ring that still touches the grid
+        int rmax = max(max(max(cx, gp.dim[0] - 1 - cx), max(cy, gp.dim[1] - 1 - cy)), max(cz, gp.dim[2] - 1 - cz));
+        if (!active) rmax = -1;
+        float best = 3.4e38f;
+        for (int r = 0;; ++r) {
+            // group-uniform loop control: every lane of the warp takes part in the shuffles below
+            const bool mine = active && r <= rmax && !(r >= 1 && best <= ((float)(r - 1) * edge) * ((float)(r - 1) * edge));
+            if (__ballot_sync(0xffffffffu, mine) == 0u) break;
+            if (mine) {
+                for (int dz = -r; dz <= r; ++dz) {
+                    const int zz = cz + dz;
+                    if (zz < 0 || zz >= gp.dim[2]) continue;
+                    for (int dy = -r; dy <= r; ++dy) {
+                        const int yy = cy + dy;
+                        if (yy < 0 || yy >= gp.dim[1]) continue;
+                        const bool face = (dz == -r || dz == r || dy == -r || dy == r);
+                        const int base = (zz * gp.dim[1] + yy) * gp.dim[0];
+                        // on a face of the shell the whole x-range belongs to ring r; elsewhere only its two end cells
+                        for (int part = 0; part < (face ? 1 : 2); ++part) {
+                            int x0, x1;
+                            if (face) { x0 = cx - r; x1 = cx + r; }
+                            else { x0 = x1 = (part == 0 ? cx - r : cx + r); if (r == 0 && part == 1) continue; }
+                            x0 = max(x0, 0); x1 = min(x1, gp.dim[0] - 1);
+                            if (x0 > x1) continue;
+                            const int js = __ldg(&g.cell_start[base + x0]), je = __ldg(&g.cell_start[base + x1 + 1]);
+                            for (int j = js + sub; j < je; j += kKnnLanes) best = fminf(best, dist2(q, __ldg(&g.cpts[j])));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = kKnnLanes / 2; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        if (active && sub == 0) d2_out[qi] = best;
+    }
+}
+
+// fitness_score += corr.distance, sequentially in source order in float, then / n (anchorOptimize.hpp:473-478):
+// one thread, eight loads in flight.
+__global__ void k_seq_mean(const float* __restrict__ v, int n, float* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    float s = 0.f;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = v[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += w[u];
+    }
+    for (; i < n; ++i) s += v[i];
+    *out = s / (float)n;
+}
+
 }  // namespace liloc

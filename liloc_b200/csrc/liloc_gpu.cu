@@ -112,6 +112,8 @@ struct liloc_ctx {
     std::unordered_map<int, KfEntry> kf;
 
     FeatClass fc[kClasses];
+    FeatClass aux;                       // scratch class of liloc_icp_fitness (its own cloud + search grid)
+    DevBuf<float> aux_d2;
     int max_cells = 1 << 24;
     long long sort_redos = 0;
     bool wide_maps = true;               // local-map launch with two blocks per SM (LILOC_PIPE_NARROW=1 in the environment: one)
@@ -496,7 +498,8 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
-    for (FeatClass& fc : c->fc) {
+    for (FeatClass* fcp : {&c->fc[0], &c->fc[1], &c->aux}) {
+        FeatClass& fc = *fcp;
         for (VgInst* vi : {&fc.vg_map, &fc.vg_scan}) {
             CUB_(cudaMalloc(&vi->d_enc, 6 * sizeof(unsigned)));
             CUB_(cudaMalloc(&vi->d_vp, sizeof(VgParams)));
@@ -560,7 +563,9 @@ void liloc_destroy(liloc_ctx* c) {
     for (cudaStream_t st : {c->stream, c->stream2, c->stream3}) if (st) cudaStreamSynchronize(st);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(c->arena.p);
-    for (FeatClass& fc : c->fc) {
+    fr(c->aux_d2.p);
+    for (FeatClass* fcp : {&c->fc[0], &c->fc[1], &c->aux}) {
+        FeatClass& fc = *fcp;
         fr(fc.raw.p); fr(fc.map.p); fr(fc.cpts.p); fr(fc.descs.p); fr(fc.scan_raw.p); fr(fc.scan.p);
         fr(fc.cell_counts.p); fr(fc.cell_start.p); fr(fc.grid_tiles.p); fr(fc.d_gp);
         if (fc.h_descs) cudaFreeHost(fc.h_descs);
@@ -1019,6 +1024,70 @@ int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int 
     CU(cudaMemcpyAsync(keep, ctx->tmp_i.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LILOC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// ICP fitness score
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+// cloud 1 (n1 points, transform T1) against cloud 2 (n2 points, transform T2); both already on the device
+int icp_fitness_dev(liloc_ctx* ctx, const float4* d1, int n1, const float* pose6_1, const float4* d2, int n2, const float* pose6_2, float* score_out) {
+    if (n1 <= 0 || n2 <= 0) return fail(ctx, LILOC_ERR_ARG, "icp_fitness: empty cloud");
+    static const float kIdentity6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int rc;
+    FeatClass& ax = ctx->aux;
+    KfDesc desc{};
+    desc.src_off = 0; desc.n = n2; desc.dst_off = 0;
+    pose_to_T(pose6_2 ? pose6_2 : kIdentity6, desc.T);
+    float T1[12];
+    pose_to_T(pose6_1 ? pose6_1 : kIdentity6, T1);
+    if ((rc = ensure(ctx, ax.descs, 1))) return rc;
+    if ((rc = ensure(ctx, ax.raw, (size_t)n2))) return rc;
+    if ((rc = ensure(ctx, ctx->aux_d2, (size_t)n1 + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_f, 32))) return rc;
+    CU(cudaMemcpyAsync(ax.descs.p, &desc, sizeof(KfDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->tmp_f.p, T1, sizeof(T1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));          // desc / T1 are stack variables
+    PipeArgs pa{};
+    VgProb& q = pa.prob[0];
+    if ((rc = prob_voxelgrid(ctx, ax.vg_map, ax.raw.p, n2, 1.0f, &ax.raw, &q))) return rc;       // leaf unused: grid_only
+    q.arena = d2; q.descs = ax.descs.p; q.K = 1; q.raw = ax.raw.p; q.grid_only = 1; q.sort_only = 0;
+    if ((rc = prob_add_grid(ctx, ax, n2, &q))) return rc;
+    pa.n_prob = 1;
+    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
+    k_nn1_dist2<<<blocks_for(ctx, (long long)n1 * kKnnLanes, 256), 256, 0, ctx->stream>>>(d1, n1, ctx->tmp_f.p, grid_view(ax), ctx->aux_d2.p); KCHECK();
+    k_seq_mean<<<1, 32, 0, ctx->stream>>>(ctx->aux_d2.p, n1, ctx->aux_d2.p + n1); KCHECK();
+    CU(cudaMemcpyAsync(score_out, ctx->aux_d2.p + n1, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LILOC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int liloc_icp_fitness(liloc_ctx* ctx, const liloc_point* cloud1, int n1, const float* pose6_1,
+                      const liloc_point* cloud2, int n2, const float* pose6_2, float* score_out) {
+    ENTER(ctx);
+    if (n1 <= 0 || n2 <= 0 || !cloud1 || !cloud2 || !score_out) return fail(ctx, LILOC_ERR_ARG, "icp_fitness: bad arguments");
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)n1 + (size_t)n2))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_pts.p, cloud1, (size_t)n1 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->tmp_pts.p + n1, cloud2, (size_t)n2 * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    return icp_fitness_dev(ctx, ctx->tmp_pts.p, n1, pose6_1, ctx->tmp_pts.p + n1, n2, pose6_2, score_out);
+}
+
+int liloc_icp_fitness_resident(liloc_ctx* ctx, int kf_id, const float* pose6_kf, int ndt_source_id, const float* pose6_src, float* score_out) {
+    ENTER(ctx);
+    if (!score_out) return fail(ctx, LILOC_ERR_ARG, "icp_fitness: null argument");
+    auto ki = ctx->kf.find(kf_id);
+    auto si = ctx->ndt_sources.find(ndt_source_id);
+    if (ki == ctx->kf.end()) return fail(ctx, LILOC_ERR_ARG, "icp_fitness: unknown keyframe id %d", kf_id);
+    if (si == ctx->ndt_sources.end()) return fail(ctx, LILOC_ERR_ARG, "icp_fitness: unknown source id %d", ndt_source_id);
+    return icp_fitness_dev(ctx, ctx->arena.p + ki->second.off[0], ki->second.n[0], pose6_kf, si->second.view.pts, si->second.view.n, pose6_src, score_out);
 }
 
 }  // extern "C"

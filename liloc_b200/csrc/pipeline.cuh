@@ -63,6 +63,7 @@ struct VgProb {
     int* grid_tiles;
     float4* cpts;
     int sort_only;             // stop after the sort (NDT target build): sorted pairs are in keys[1] / vals[1]
+    int grid_only;             // no down-sampling: the search grid is built over the (assembled) cloud itself; out == pts
 };
 
 constexpr int kPipeMarks = 16;
@@ -457,6 +458,18 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
     }
 }
 
+// grid_only problems: the cloud itself is the search set -- count its points per cell, publish the count
+LILOC_DEV void pipe_cells_count_direct(const VgProb& q, const GridParams& gp) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = q.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += gridDim.x * blockDim.x) {
+        const float4 p = q.out[i];
+        const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
+        const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
+        const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
+        atomicAdd(&q.cell_counts[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
+    }
+}
+
 // ---- G1..G3: cell counts -> cell_start, points sorted by cell -----------------------------------------------------------
 LILOC_DEV void pipe_cells_reduce(const VgProb& q, const GridParams& gp) {
     const int n = gp.ncells;
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
         const VgProb& q = a.prob[threadIdx.x];
         const VgParams vp = vg_params_compute(q.enc, q.leaf, q.n);
         s_vp[threadIdx.x] = vp;
-        s_npass[threadIdx.x] = q.n > 0 ? (vp.key_bits + 7) / 8 : 0;
+        s_npass[threadIdx.x] = (q.n > 0 && !q.grid_only) ? (vp.key_bits + 7) / 8 : 0;
         GridParams g{};
         if (q.build_grid) g = grid_params_compute(vp.mn, vp.mx, q.n <= 0, q.max_cells);
         s_gp[threadIdx.x] = g;
@@ -554,7 +567,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     int max_pass = 0;
     for (int p = 0; p < np; ++p) max_pass = max(max_pass, s_npass[p]);
     const int sidx = s_sort_idx, nsort = s_nsort;
-    for (int p = 0; p < np; ++p) if (a.prob[p].n > 0) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm, sidx, nsort);
+    for (int p = 0; p < np; ++p) if (a.prob[p].n > 0 && !a.prob[p].grid_only) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm, sidx, nsort);
     grid.sync();
     if (blockIdx.x == 0) for (int i = threadIdx.x; i < kSmScratch; i += kPipeThreads) a.sm_scratch[i] = 0;   // re-armed for the next launch
     PIPE_MARK();                                                                          // 2 after keys
@@ -572,10 +585,13 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     for (int p = 0; p < np; ++p) { any_out |= !a.prob[p].sort_only; any_grid |= a.prob[p].build_grid != 0; }
     if (!any_out) return;
 
-    for (int p = 0; p < np; ++p) if (!a.prob[p].sort_only) pipe_run_count(a.prob[p]);     // R1
+    for (int p = 0; p < np; ++p) {                                                        // R1
+        if (a.prob[p].grid_only) pipe_cells_count_direct(a.prob[p], s_gp[p]);
+        else if (!a.prob[p].sort_only) pipe_run_count(a.prob[p]);
+    }
     grid.sync();
     PIPE_MARK();                                                                          // 4 after the run count
-    for (int p = 0; p < np; ++p) if (!a.prob[p].sort_only) pipe_centroids(a.prob[p], s_gp[p], sm);   // R2
+    for (int p = 0; p < np; ++p) if (!a.prob[p].sort_only && !a.prob[p].grid_only) pipe_centroids(a.prob[p], s_gp[p], sm);   // R2
     if (!any_grid) { PIPE_MARK(); return; }                                               // 5 (block 0's own end)
     grid.sync();
     PIPE_MARK();                                                                          // 5 after the centroids

@@ -29,6 +29,8 @@ struct liloc_host_report {               // mirror of liloc_host::FrameReport
     double reg_ms;
     int relo_initialized, relo_submap, relo_iterations, relo_converged;
     float relo_pose[6];
+    int relo_n_vertices, relo_vertex[3];
+    float relo_fitness[3];
 };
 
 static thread_local std::string g_err;
@@ -50,6 +52,8 @@ static void to_report(const liloc_host::FrameReport& r, liloc_host_report* o) {
     o->keyframe_id = r.keyframe_id; o->reg_ms = r.reg_ms;
     o->relo_initialized = r.relo_initialized; o->relo_submap = r.relo_submap; o->relo_iterations = r.relo_iterations; o->relo_converged = r.relo_converged;
     std::memcpy(o->relo_pose, r.relo_pose, sizeof(o->relo_pose));
+    o->relo_n_vertices = r.relo_n_vertices;
+    std::memcpy(o->relo_vertex, r.relo_vertex, sizeof(o->relo_vertex)); std::memcpy(o->relo_fitness, r.relo_fitness, sizeof(o->relo_fitness));
 }
 
 static liloc_host::CloudInfo to_info(const liloc_host_cloud_info& m) {

@@ -344,6 +344,23 @@ int mapOptimization::searchNearestSubMap(float x, float y, float z) const {
     return best;
 }
 
+// kdtreeSearchVertex_->radiusSearch(pose, 5.0) over the submap's vertices, ascending distance, first three
+// (dataLoader.hpp:366-389; the extra skip rule there only concerns vertices added by addNewPrior, which is out of scope)
+std::vector<int> mapOptimization::searchVertexes(int submap, float x, float y, float z) const {
+    std::vector<std::pair<float, int>> hits;
+    const PointType q{x, y, z, 0.f};
+    for (int k = 0; k < prior_.submap_count[submap]; ++k) {
+        const int id = prior_.submap_first[submap] + k;
+        const PointTypePose& p = prior_.KeyPoses6D[id];
+        const float d = sqDist(q, PointType{p.x, p.y, p.z, 0.f});
+        if (d < 25.0f) hits.push_back({d, id});
+    }
+    std::sort(hits.begin(), hits.end());
+    std::vector<int> out;
+    for (const auto& h : hits) { if ((int)out.size() == 3) break; out.push_back(h.second); }
+    return out;
+}
+
 // registration->setInputTarget(submap) / setInputSource(laserCloudSurfLast) / align x n_align / getFinalTransformation
 int mapOptimization::ndtAlign(int submap, const float guess6[6], int n_align, float out6[6], int* iterations, int* converged) {
     int rc = liloc_ndt_source_put(ctx_, /*source_id=*/0, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device);
@@ -385,10 +402,26 @@ void mapOptimization::saveRELOKeyFramesAndFactor() {
     // into its ISAM2 graph (out of scope here); it is reported in the frame report instead.
     if (!prior_.SubMapCenteriod.empty() && !rep_.relo_initialized) {
         const int submap = searchNearestSubMap(transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
-        float out6[6]; int it = 0, conv = 0;
-        if (ndtAlign(submap, transformTobeMapped, 1, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); rep_.status = LILOC_ERR_CUDA; return; }
-        rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
-        std::memcpy(rep_.relo_pose, out6, sizeof(out6));
+        const std::vector<int> vertexes = searchVertexes(submap, transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
+        rep_.relo_n_vertices = (int)vertexes.size();
+        if (vertexes.size() > 1) {                 // `usingVertexes_->size() <= 1` => addNewPrior() instead of matching (:387-390)
+            float out6[6]; int it = 0, conv = 0;
+            if (ndtAlign(submap, transformTobeMapped, 1, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); rep_.status = LILOC_ERR_CUDA; return; }
+            rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
+            std::memcpy(rep_.relo_pose, out6, sizeof(out6));
+            // per prior vertex: getICPFitnessScore(its key cloud at its prior pose, the scan at the matched pose), capped
+            // at 2 (:427-446).  Both clouds are already on the device.
+            for (size_t v = 0; v < vertexes.size(); ++v) {
+                const PointTypePose& p = prior_.KeyPoses6D[vertexes[v]];
+                const float pose_i[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+                float score = 0.f;
+                if (liloc_icp_fitness_resident(ctx_, kPriorKeyframeBase + vertexes[v], pose_i, /*ndt source*/ 0, out6, &score) < 0) {
+                    error_ = liloc_last_error(ctx_); rep_.status = LILOC_ERR_CUDA; return;
+                }
+                if (score > 2) score = 2;
+                rep_.relo_vertex[v] = vertexes[v]; rep_.relo_fitness[v] = score;
+            }
+        }
     }
     // every processed frame becomes a keyframe (the saveFrame() gate is commented out, :1338-1339)
     const int id = (int)cloudKeyPoses3D.size();

@@ -48,6 +48,9 @@ struct FrameReport {                             // what the reference would pub
     int relo_submap = -1;                        // prior submap the scan was matched against (searchNearestSubMapAndVertex)
     int relo_iterations = 0, relo_converged = 0;
     float relo_pose[6] = {0, 0, 0, 0, 0, 0};     // NDT result as [roll, pitch, yaw, x, y, z] (the scan-matching factor's poseTo)
+    int relo_n_vertices = 0;                     // prior vertices within 5 m of the pose (usingVertexes_, at most 3)
+    int relo_vertex[3] = {-1, -1, -1};           // their prior keyframe ids
+    float relo_fitness[3] = {0, 0, 0};           // getICPFitnessScore of each vertex' key cloud against the matched scan, capped at 2
 };
 
 // What mapOptimization keeps of the prior session (dataManager::Session, include/dataManager/dataLoader.hpp:128-391):
@@ -107,6 +110,7 @@ public:
     bool loadPriorSession(const PointTypePose* keyPoses, int n, const liloc_point* clouds, const long long* offsets);
     void initialposeHandler(float x, float y, float yaw);                       // :755-769
     int searchNearestSubMap(float x, float y, float z) const;                   // dataLoader.hpp:350-357 (1-NN on the centroids)
+    std::vector<int> searchVertexes(int submap, float x, float y, float z) const;   // dataLoader.hpp:366-389 (radius 5 m, at most 3)
     bool relocalizeInit();                                                      // :261-305
     void saveRELOKeyFramesAndFactor();                                          // :1336-1389 (+ anchorOptimize.hpp:382-407)
     const PriorSession& prior() const { return prior_; }

@@ -843,4 +843,28 @@ int orc_scan2map_features(const orc_point* map_s, int Ms, const orc_point* scan_
     return 0;
 }
 
+// AnchorOptimization::getICPFitnessScore (include/egoOptimization/anchorOptimize.hpp:465-481) on the two clouds the
+// caller built with transformPointCloud (:425, :439): pcl CorrespondenceEstimation::determineCorrespondences with the
+// default (unbounded) max distance = exact 1-NN of every cloud-1 point in cloud 2, Correspondence::distance = SQUARED
+// distance; `fitness_score += corr.distance` sequentially in float, divided by the number of correspondences.
+float orc_icp_fitness(const orc_point* c1, int n1, const float* pose6_1, const orc_point* c2, int n2, const float* pose6_2,
+                      int knn, int threads) {
+    std::vector<orc_point> a((size_t)n1), b((size_t)n2);
+    float T1[12], T2[12];
+    pose_to_T(pose6_1, T1); pose_to_T(pose6_2, T2);
+    for (int i = 0; i < n1; ++i) a[i] = apply_T(T1, c1[i]);
+    for (int i = 0; i < n2; ++i) b[i] = apply_T(T2, c2[i]);
+    KdTree tree; if (knn == 1) tree.build(b.data(), n2);
+    std::vector<float> d((size_t)n1);
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+    for (int i = 0; i < n1; ++i) {
+        int idx[5]; float d2[5];
+        if (knn == 1) tree.knn5(a[i], idx, d2); else knn5_brute_one(b.data(), n2, a[i], idx, d2);
+        d[i] = d2[0];
+    }
+    float s = 0.f;
+    for (int i = 0; i < n1; ++i) s += d[i];
+    return s / (float)n1;
+}
+
 }  // extern "C"

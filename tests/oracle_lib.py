@@ -61,6 +61,8 @@ def _load():
     L.orc_frame.restype = C.c_int
     L.orc_frame.argtypes = [P, P, P, C.c_int, C.c_float, P, C.c_int, C.c_float, P, C.POINTER(S2mOpts),
                             C.POINTER(LmState), C.POINTER(S2mResult), P, P, P]
+    L.orc_icp_fitness.restype = C.c_float
+    L.orc_icp_fitness.argtypes = [P, C.c_int, P, P, C.c_int, P, C.c_int, C.c_int]
     L.orc_eigen3.argtypes = [P, P, P]
     L.orc_line_residual.restype = C.c_int
     L.orc_line_residual.argtypes = [P, P, P]
@@ -234,6 +236,14 @@ def scan2map_features(map_s, scan_s, map_c, scan_c, pose6, opts: S2mOpts | None 
     rc = lib.orc_scan2map_features(_p(ms), len(ms), _p(ss), len(ss), _p(mc), len(mc), _p(sc), len(sc),
                                    min_corner, stride_corner, _p(p), C.byref(o), C.byref(st), C.byref(res))
     return p, res, rc, st
+
+
+def icp_fitness(cloud1, pose6_1, cloud2, pose6_2, kdtree=True, threads=1) -> float:
+    """getICPFitnessScore (anchorOptimize.hpp:465-481): mean squared 1-NN distance of cloud 1 (transformed) in cloud 2."""
+    a, b = _c(cloud1), _c(cloud2)
+    p1 = np.ascontiguousarray(pose6_1, np.float32).reshape(6)
+    p2 = np.ascontiguousarray(pose6_2, np.float32).reshape(6)
+    return float(lib.orc_icp_fitness(_p(a), len(a), _p(p1), _p(b), len(b), _p(p2), 1 if kdtree else 0, threads))
 
 
 def localmap_build(kf_clouds, poses6, leaf, threads=1):

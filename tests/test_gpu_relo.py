@@ -105,4 +105,36 @@ def test_relo_mode_through_host_class(orc, synth):
             assert np.abs(synth.rot_zyx(*[float(v) for v in got[:3]]) - Tm[:, :3]).max() <= (1e-5 if same_path else 1e-3)
             n_same += same_path
             assert np.abs(got[3:5] - cur[f][3:5]).max() < 0.2       # NDT at 1 m resolution with eps 0.01: decimetre-level
+            # prior vertices within 5 m (at most 3, nearest first) and their ICP fitness against the matched scan
+            d2 = ((prior_traj[lo:lo + 10, 3:].astype(np.float32) - pose[3:]) ** 2).sum(1)
+            near = [lo + int(k) for k in np.argsort(d2, kind="stable") if d2[k] < 25.0][:3]
+            assert rep.relo_n_vertices == len(near) and list(rep.relo_vertex)[: len(near)] == near
+            for v, vid in enumerate(near):
+                want = orc.icp_fitness(prior_clouds[vid], prior_traj[vid].astype(np.float32), scans[f], got, threads=8)
+                assert rep.relo_fitness[v] == np.float32(min(want, 2.0)), (f, v, rep.relo_fitness[v], want)
         assert n_same >= 3
+
+
+def test_icp_fitness_bit_exact(gpu_ctx, orc, synth):
+    """liloc_icp_fitness (getICPFitnessScore, anchorOptimize.hpp:465-481): unbounded exact 1-NN on the search grid, squared
+    distances summed sequentially in float -> the same bits as the oracle."""
+    rng = np.random.default_rng(41)
+    world = synth.make_world(seed=41)
+    traj = synth.trajectory_line(4, x0=-2)
+    a = synth.scan(world, traj[0], synth.VLP16, 4100)
+    b = synth.scan(world, traj[2], synth.VLP16, 4102)
+    cases = [(a, traj[0], b, traj[2]),                                     # two overlapping scans, 2 m apart
+             (a[::7], traj[0], b, traj[2] + np.array([0, 0, 0.3, 5.0, -3.0, 0.5])),      # misaligned: larger distances, more rings
+             (a[:500], traj[0] + np.array([0, 0, 0, 200.0, 0, 0]), b[::3], traj[2]),   # no overlap at all: far outside the grid
+             ((rng.normal(size=(300, 4)) * 30).astype(np.float32), np.zeros(6), (rng.normal(size=(7, 4)) * 30).astype(np.float32), np.zeros(6))]
+    for c1, p1, c2, p2 in cases:
+        got = gpu_ctx.icp_fitness(c1, p1, c2, p2)
+        ref = orc.icp_fitness(c1, np.asarray(p1, np.float32), c2, np.asarray(p2, np.float32), kdtree=True, threads=8)
+        assert got == ref, (got, ref)
+    assert gpu_ctx.icp_fitness(a, traj[0], a, traj[0]) == 0.0
+    # resident form: cloud 1 from the keyframe store, cloud 2 from an NDT source
+    gpu_ctx.keyframe_clear(); gpu_ctx.ndt_clear()
+    gpu_ctx.keyframe_put(5, a)
+    gpu_ctx.ndt_source_put(0, b)
+    got = gpu_ctx.icp_fitness_resident(5, traj[0], 0, traj[2])
+    assert got == orc.icp_fitness(a, traj[0].astype(np.float32), b, traj[2].astype(np.float32), threads=8)

@@ -235,3 +235,22 @@ def test_scan2map_degenerate_scene_sets_flag(orc, synth):
     P = np.array(st.matP, np.float32).reshape(6, 6)
     assert np.linalg.matrix_rank(P.astype(np.float64), tol=1e-3) < 6
     assert abs(pose[5] - traj[4][5]) < 0.02            # z is still observable
+
+
+def test_icp_fitness_matches_ckdtree(orc):
+    """getICPFitnessScore restatement (anchorOptimize.hpp:465-481) against scipy: unbounded exact 1-NN, mean squared distance."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(31)
+    a = (rng.normal(size=(2000, 4)) * [12, 9, 1.5, 1]).astype(np.float32)
+    b = (rng.normal(size=(2500, 4)) * [12, 9, 1.5, 1]).astype(np.float32)
+    b[:50, :3] += 300.0                                   # far clutter: must not matter
+    p1 = np.array([0.02, -0.01, 0.4, 1.5, -2.0, 0.2], np.float32)
+    p2 = np.array([0.0, 0.01, -0.1, 0.3, 0.1, 0.0], np.float32)
+    at, bt = orc.transform_cloud(a, p1), orc.transform_cloud(b, p2)
+    d, _ = cKDTree(bt[:, :3].astype(np.float64)).query(at[:, :3].astype(np.float64))
+    want = float((d ** 2).mean())
+    for kd in (True, False):
+        got = orc.icp_fitness(a, p1, b, p2, kdtree=kd, threads=4)
+        assert abs(got - want) <= 2e-5 * want
+    assert orc.icp_fitness(a, p1, b, p2, kdtree=True) == orc.icp_fitness(a, p1, b, p2, kdtree=False)
+    assert orc.icp_fitness(a, p1, a, p1) == 0.0

@@ -191,6 +191,11 @@ int liloc_ndt_target_get(liloc_ctx* ctx, int target_id, double* means, float* ic
 /* one derivative sweep at pose p6 = [tx,ty,tz,rx,ry,rz] (tests): out28 = score, gradient[6], Hessian upper[21] */
 int liloc_ndt_derivatives(liloc_ctx* ctx, int target_id, int source_id, const double* p6, const liloc_ndt_opts* opts, double* out28);
 
+/* ---- global map of the visualisation thread: publishGlobalMap (src/mapOptmization.cpp:698-753) ----------------------------
+ * transformPointCloud of the K selected keyframes (:744-746) + VoxelGrid(globalMapVisualizationLeafSize) (:749-750) in
+ * buffers of their own (the frame's local map is not touched).  out may be NULL (count only); cap in points. */
+int liloc_globalmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf, liloc_point* out, int cap, int* M_out);
+
 /* ---- ICP fitness score: AnchorOptimization::getICPFitnessScore (include/egoOptimization/anchorOptimize.hpp:465-481) ----
  * Mean SQUARED distance from every point of cloud 1 to its nearest neighbour in cloud 2 (pcl::registration::
  * CorrespondenceEstimation::determineCorrespondences with its default, unbounded, maximum distance), summed sequentially

@@ -172,6 +172,7 @@ def _load() -> C.CDLL:
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
         "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
         "liloc_set_map_cache": (C.c_longlong, [P, C.c_int]),
+        "liloc_globalmap_build": (C.c_int, [P, P, P, C.c_int, C.c_float, P, C.c_int, ip]),
         "liloc_icp_fitness": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P, fp]),
         "liloc_icp_fitness_resident": (C.c_int, [P, C.c_int, P, C.c_int, P, fp]),
         "liloc_ndt_target_put_keyframes": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, ip, ip]),
@@ -194,7 +195,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -421,6 +422,15 @@ class Context:
         else:
             p = _cloud(pts_body)
             self._chk(lib.liloc_ndt_source_put(self._h, source_id, _ptr(p), len(p), 0))
+
+    def globalmap_build(self, kf_ids, poses6, leaf: float) -> np.ndarray:
+        ids = np.ascontiguousarray(kf_ids, dtype=np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(-1, 6)
+        M = C.c_int()
+        self._chk(lib.liloc_globalmap_build(self._h, _ptr(ids), _ptr(poses), len(ids), leaf, None, 0, C.byref(M)))
+        out = np.empty((max(M.value, 1), 4), np.float32)
+        self._chk(lib.liloc_globalmap_build(self._h, _ptr(ids), _ptr(poses), len(ids), leaf, _ptr(out), len(out), C.byref(M)))
+        return out[: M.value].copy()
 
     def icp_fitness(self, cloud1, pose6_1, cloud2, pose6_2) -> float:
         a, b = _cloud(cloud1), _cloud(cloud2)

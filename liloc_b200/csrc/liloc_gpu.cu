@@ -1029,6 +1029,50 @@ int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int 
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------
+// Global-map down-sample of the visualisation thread
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int liloc_globalmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6, int K, float leaf, liloc_point* out, int cap, int* M_out) {
+    ENTER(ctx);
+    if (K < 0 || (K > 0 && (!kf_ids || !poses6)) || !(leaf > 0.f) || !M_out) return fail(ctx, LILOC_ERR_ARG, "globalmap_build: bad arguments");
+    FeatClass& ax = ctx->aux;                        // its own buffers: the frame's local map stays untouched
+    int rc;
+    std::vector<KfDesc> h((size_t)(K > 0 ? K : 1));
+    long long total = 0;
+    for (int k = 0; k < K; ++k) {
+        auto it = ctx->kf.find(kf_ids[k]);
+        if (it == ctx->kf.end()) return fail(ctx, LILOC_ERR_ARG, "globalmap_build: unknown keyframe id %d", kf_ids[k]);
+        h[k].src_off = (long long)it->second.off[0]; h[k].n = it->second.n[0]; h[k].dst_off = (int)total;
+        pose_to_T(poses6 + 6 * (size_t)k, h[k].T);
+        total += it->second.n[0];
+        if (total > 0x7fffffffLL) return fail(ctx, LILOC_ERR_CAPACITY, "globalmap_build: more than 2^31 points");
+    }
+    if ((rc = ensure(ctx, ax.descs, (size_t)(K > 0 ? K : 1)))) return rc;
+    if ((rc = ensure(ctx, ax.raw, (size_t)(total > 0 ? total : 1)))) return rc;
+    if (K > 0) CU(cudaMemcpyAsync(ax.descs.p, h.data(), (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));          // the staging vector dies at return
+    PipeArgs pa{};
+    VgProb& q = pa.prob[0];
+    if ((rc = prob_voxelgrid(ctx, ax.vg_map, ax.raw.p, (int)total, leaf, &ax.map, &q))) return rc;
+    q.arena = ctx->arena.p; q.descs = ax.descs.p; q.K = total > 0 ? K : 0; q.raw = ax.raw.p;
+    pa.n_prob = 1;
+    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr, total > 1500000))) return rc;
+    int m = 0;
+    CU(cudaMemcpyAsync(&m, ax.vg_map.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *M_out = m;
+    if (out) {
+        if (m > cap) return fail(ctx, LILOC_ERR_CAPACITY, "globalmap_build: cap %d < M %d", cap, m);
+        if (m > 0) CU(cudaMemcpyAsync(out, ax.map.p, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return LILOC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
 // ICP fitness score
 // ---------------------------------------------------------------------------------------------------------
 namespace {

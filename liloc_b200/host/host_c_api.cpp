@@ -102,6 +102,14 @@ int liloc_host_submap_info(void* h, int s, float* centroid3, int* first, int* co
     return 0;
 }
 
+// publishGlobalMap (:698-753): returns the number of points (copied into out when cap suffices), or <0
+int liloc_host_global_map(void* h, liloc_point* out, int cap) {
+    std::vector<liloc_point> g;
+    if (!static_cast<mapOptimization*>(h)->publishGlobalMap(g)) return -1;
+    if (out && (int)g.size() <= cap && !g.empty()) std::memcpy(out, g.data(), g.size() * sizeof(liloc_point));
+    return (int)g.size();
+}
+
 void liloc_host_reset(void* h) { static_cast<mapOptimization*>(h)->reset(); }
 
 void liloc_host_set_s2m_opts(void* h, int max_iters, int stride, int min_sel, int min_points) {

@@ -290,6 +290,39 @@ void mapOptimization::saveLIOKeyFramesAndFactor() {
     rep_.keyframe_id = id;
 }
 
+bool mapOptimization::publishGlobalMap(std::vector<liloc_point>& globalMapKeyFramesDS) {
+    globalMapKeyFramesDS.clear();
+    if (cloudKeyPoses3D.empty()) return true;                                   // :714-715
+    if (!ctx_) { error_ = "no device context"; return false; }
+    const PointType& last = cloudKeyPoses3D.back();
+    const float r2 = globalMapVisualizationSearchRadius * globalMapVisualizationSearchRadius;
+    std::vector<std::pair<float, int>> hits;                                    // radiusSearch (:729), ascending distance
+    for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) { const float d = sqDist(last, cloudKeyPoses3D[i]); if (d < r2) hits.push_back({d, i}); }
+    std::sort(hits.begin(), hits.end());
+    std::vector<PointType> globalMapKeyPoses;
+    for (const auto& h : hits) globalMapKeyPoses.push_back(cloudKeyPoses3D[h.second]);
+    std::vector<PointType> ds = voxelGridSmall(globalMapKeyPoses, globalMapVisualizationPoseDensity);   // :735-738
+    std::vector<int> ids; std::vector<float> poses;
+    for (auto& pt : ds) {                                                        // nearestKSearch(pt, 1) (:739-742)
+        int best = 0; float bd = sqDist(pt, cloudKeyPoses3D[0]);
+        for (int i = 1; i < (int)cloudKeyPoses3D.size(); ++i) { const float d = sqDist(pt, cloudKeyPoses3D[i]); if (d < bd) { bd = d; best = i; } }
+        pt.intensity = cloudKeyPoses3D[best].intensity;
+        if (pointDistance(pt, last) > globalMapVisualizationSearchRadius) continue;               // :745-746
+        const int k = (int)pt.intensity;
+        const PointTypePose& p = cloudKeyPoses6D[k];
+        ids.push_back(k);
+        const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+        poses.insert(poses.end(), pose6, pose6 + 6);
+    }
+    int M = 0;
+    if (liloc_globalmap_build(ctx_, ids.data(), poses.data(), (int)ids.size(), globalMapVisualizationLeafSize, nullptr, 0, &M) < 0) { error_ = liloc_last_error(ctx_); return false; }
+    globalMapKeyFramesDS.resize((size_t)M);
+    if (M > 0 && liloc_globalmap_build(ctx_, ids.data(), poses.data(), (int)ids.size(), globalMapVisualizationLeafSize, globalMapKeyFramesDS.data(), M, &M) < 0) {
+        error_ = liloc_last_error(ctx_); return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // relo mode
 // ---------------------------------------------------------------------------------------------------------

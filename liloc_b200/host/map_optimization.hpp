@@ -102,6 +102,9 @@ public:
     float constraintTransformation(float value, float limit);          // :1236-1243
     bool saveFrame();                          // :1245-1264
     void saveLIOKeyFramesAndFactor();          // :1391-1461
+    // the cloud publishGlobalMap (:698-753, 1 Hz visualisation thread) would publish: key poses within
+    // globalMapVisualizationSearchRadius thinned at ...PoseDensity, their clouds transformed + down-sampled at ...LeafSize
+    bool publishGlobalMap(std::vector<liloc_point>& globalMapKeyFramesDS);
 
     // ---- relo mode: relocalisation against a prior session (the NDT side of :171-206, :261-305, :755-769 and of
     //      AnchorOptimization::addScanMatchingFactor, anchorOptimize.hpp:382-421).  The GTSAM graphs are out of scope

@@ -47,6 +47,8 @@ def _load():
     L.liloc_host_run.restype = C.c_int
     L.liloc_host_run.argtypes = [P, C.POINTER(CloudInfo), C.c_int, C.POINTER(Report)]
     L.liloc_host_reset.argtypes = [P]
+    L.liloc_host_global_map.restype = C.c_int
+    L.liloc_host_global_map.argtypes = [P, P, C.c_int]
     L.liloc_host_load_prior.restype = C.c_int
     L.liloc_host_load_prior.argtypes = [P, P, C.c_int, P, P]
     L.liloc_host_initialpose.argtypes = [P, C.c_float, C.c_float, C.c_float]
@@ -176,6 +178,15 @@ class MapOptimization:
         if lib().liloc_host_submap_info(self._h, s, c.ctypes.data, C.byref(first), C.byref(count), C.byref(pts)) != 0:
             raise IndexError(s)
         return {"centroid": c, "first": first.value, "count": count.value, "points": pts.value}
+
+    def global_map(self) -> np.ndarray:
+        """The cloud publishGlobalMap (:698-753) would publish."""
+        n = lib().liloc_host_global_map(self._h, None, 0)
+        if n < 0:
+            raise RuntimeError("publishGlobalMap: " + (lib().liloc_host_error(self._h) or b"").decode())
+        out = np.empty((max(n, 1), 4), np.float32)
+        lib().liloc_host_global_map(self._h, out.ctypes.data, len(out))
+        return out[:n]
 
     def num_keyframes(self) -> int:
         return lib().liloc_host_num_keyframes(self._h)

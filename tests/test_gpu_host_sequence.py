@@ -41,6 +41,16 @@ def test_lio_sequence_through_host_class(orc, synth):
                 n_kf += 1
         assert n_checked == len(seq.scans) - 1 and 5 < n_kf <= len(seq.scans)
         assert m.num_keyframes() == n_kf
+        # publishGlobalMap (:698-753): every key pose is within the 1000 m radius; thinning at 10 m keeps a subset
+        gm = m.global_map()
+        kp = m.keyposes()
+        pos = np.c_[kp[:, 3:6], np.arange(len(kp))].astype(np.float32)
+        last = pos[-1]
+        order = np.lexsort((np.arange(len(pos)), ((last[:3] - pos[:, :3]) ** 2).sum(1)))
+        ds = orc.voxelgrid(pos[order], np.float32(m.param("globalMapVisualizationPoseDensity")))
+        ids = [int(np.argmin(((c[:3] - pos[:, :3]) ** 2).sum(1))) for c in ds]
+        want = orc.localmap_build([kf_clouds[i] for i in ids], kp[ids][:, :6].astype(np.float32), np.float32(m.param("globalMapVisualizationLeafSize")), threads=8)
+        assert len(ids) >= 2 and gm.shape == want.shape and np.array_equal(gm, want)
 
 
 def test_time_interval_gate_drops_frames(synth):

@@ -143,6 +143,8 @@ int liloc_last_s2m_extra(liloc_ctx* ctx, liloc_s2m_extra* out);
 /* Class-indexed variants of the step-wise entry points above (cls = LILOC_SURF | LILOC_CORNER). */
 int liloc_keyframe_put_features(liloc_ctx* ctx, int kf_id, const liloc_point* surf, int n_surf, const liloc_point* corner, int n_corner);
 int liloc_keyframe_size_class(liloc_ctx* ctx, int cls, int kf_id);
+/* host copy of a stored keyframe cloud (the save_map / save_session services write them as PCDs/<k>.pcd, :495-517, :602-611) */
+int liloc_keyframe_get(liloc_ctx* ctx, int cls, int kf_id, liloc_point* out, int cap, int* n_out);
 int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const float* poses6, int K, float leaf, int* M_out, int* n_raw_out);
 int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts_map, int n, float leaf, int* M_out);
 int liloc_localmap_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, int* M_out);

@@ -172,6 +172,7 @@ def _load() -> C.CDLL:
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
         "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
         "liloc_set_map_cache": (C.c_longlong, [P, C.c_int]),
+        "liloc_keyframe_get": (C.c_int, [P, C.c_int, C.c_int, P, C.c_int, ip]),
         "liloc_globalmap_build": (C.c_int, [P, P, P, C.c_int, C.c_float, P, C.c_int, ip]),
         "liloc_icp_fitness": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P, fp]),
         "liloc_icp_fitness_resident": (C.c_int, [P, C.c_int, P, C.c_int, P, fp]),
@@ -195,7 +196,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -257,6 +258,13 @@ class Context:
 
     def keyframe_size(self, kf_id: int, cls: int = 0) -> int:
         return lib.liloc_keyframe_size_class(self._h, cls, kf_id)
+
+    def keyframe_get(self, kf_id: int, cls: int = 0) -> np.ndarray:
+        n = C.c_int()
+        self._chk(lib.liloc_keyframe_get(self._h, cls, kf_id, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        self._chk(lib.liloc_keyframe_get(self._h, cls, kf_id, _ptr(out), len(out), C.byref(n)))
+        return out[: n.value]
 
     def keyframe_clear(self) -> None:
         self._chk(lib.liloc_keyframe_clear(self._h))

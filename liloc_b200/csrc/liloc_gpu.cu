@@ -649,6 +649,21 @@ int liloc_keyframe_size_class(liloc_ctx* ctx, int cls, int kf_id) {
     return it == ctx->kf.end() ? LILOC_ERR_ARG : it->second.n[cls];
 }
 
+int liloc_keyframe_get(liloc_ctx* ctx, int cls, int kf_id, liloc_point* out, int cap, int* n_out) {
+    ENTER(ctx);
+    if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "keyframe_get: bad class %d", cls);
+    auto it = ctx->kf.find(kf_id);
+    if (it == ctx->kf.end()) return fail(ctx, LILOC_ERR_ARG, "keyframe_get: unknown keyframe id %d", kf_id);
+    const int n = it->second.n[cls];
+    if (n_out) *n_out = n;
+    if (out) {
+        if (cap < n) return fail(ctx, LILOC_ERR_CAPACITY, "keyframe_get: cap %d < n %d", cap, n);
+        if (n > 0) CU(cudaMemcpyAsync(out, ctx->arena.p + it->second.off[cls], (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return LILOC_OK;
+}
+
 int liloc_keyframe_clear(liloc_ctx* ctx) {
     ENTER(ctx);
     CU(cudaStreamSynchronize(ctx->stream));

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "map_optimization.hpp"
+#include "session_io.hpp"
 
 using liloc_host::mapOptimization;
 
@@ -93,6 +94,36 @@ int liloc_host_load_prior(void* h, const double* keyposes7, int n, const liloc_p
     }
     return m->loadPriorSession(kp.data(), n, clouds, offsets) ? (int)m->prior().SubMapCenteriod.size() : -1;
 }
+int liloc_host_load_prior_dir(void* h, const char* dir) {
+    auto* m = static_cast<mapOptimization*>(h);
+    return m->loadPriorSessionDir(dir ? dir : "") ? (int)m->prior().SubMapCenteriod.size() : -1;
+}
+int liloc_host_save_session(void* h, const char* dir) { return static_cast<mapOptimization*>(h)->saveSession(dir ? dir : "") ? 0 : -1; }
+
+// session file format, host only (no device context needed): parse a PCD / a g2o; used by the CPU tests
+int liloc_host_load_pcd(const char* path, liloc_point* out, int cap, char* err, int err_cap) {
+    std::vector<liloc_point> pts; std::string e;
+    if (!liloc_host::loadPCD(path, pts, e)) { if (err && err_cap > 0) { std::strncpy(err, e.c_str(), err_cap - 1); err[err_cap - 1] = 0; } return -1; }
+    if (out && (int)pts.size() <= cap && !pts.empty()) std::memcpy(out, pts.data(), pts.size() * sizeof(liloc_point));
+    return (int)pts.size();
+}
+int liloc_host_save_pcd(const char* path, const liloc_point* pts, int n) { std::string e; return liloc_host::savePCDBinary(path, pts, n, e) ? 0 : -1; }
+int liloc_host_load_g2o(const char* path, double* keyposes7, int cap) {
+    std::vector<liloc_host::PointTypePose> kp; std::string e;
+    if (!liloc_host::loadSessionGraph(path, kp, e)) return -1;
+    for (int i = 0; i < (int)kp.size() && i < cap; ++i) {
+        double* o = keyposes7 + 7 * i;
+        o[0] = kp[i].roll; o[1] = kp[i].pitch; o[2] = kp[i].yaw; o[3] = kp[i].x; o[4] = kp[i].y; o[5] = kp[i].z; o[6] = kp[i].intensity;
+    }
+    return (int)kp.size();
+}
+int liloc_host_save_g2o(const char* path, const double* keyposes7, int n) {
+    std::vector<liloc_host::PointTypePose> kp((size_t)(n > 0 ? n : 0));
+    for (int i = 0; i < n; ++i) { const double* r = keyposes7 + 7 * i; kp[i] = liloc_host::PointTypePose{(float)r[3], (float)r[4], (float)r[5], (float)i, (float)r[0], (float)r[1], (float)r[2], r[6]}; }
+    std::string e;
+    return liloc_host::saveSessionGraph(path, kp, e) ? 0 : -1;
+}
+
 void liloc_host_initialpose(void* h, float x, float y, float yaw) { static_cast<mapOptimization*>(h)->initialposeHandler(x, y, yaw); }
 int liloc_host_submap_info(void* h, int s, float* centroid3, int* first, int* count, int* points) {
     const auto& p = static_cast<mapOptimization*>(h)->prior();

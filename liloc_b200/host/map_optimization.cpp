@@ -1,11 +1,13 @@
 // liloc_b200/host/map_optimization.cpp -- see map_optimization.hpp.
 #include "map_optimization.hpp"
+#include "session_io.hpp"
 
 #include <algorithm>
 #include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <filesystem>
 
 namespace liloc_host {
 
@@ -359,6 +361,37 @@ bool mapOptimization::loadPriorSession(const PointTypePose* keyPoses, int n, con
         }
     }
     return true;
+}
+
+bool mapOptimization::loadPriorSessionDir(const std::string& dir) {
+    std::vector<PointTypePose> kp;
+    std::vector<std::vector<liloc_point>> clouds;
+    if (!loadSessionGraph(dir + "/singlesession_posegraph.g2o", kp, error_)) return false;
+    if (!loadKeyClouds(dir + "/PCDs", clouds, error_)) return false;
+    if (clouds.size() != kp.size()) { error_ = "session " + dir + ": " + std::to_string(kp.size()) + " vertices but " + std::to_string(clouds.size()) + " key clouds"; return false; }
+    std::vector<liloc_point> flat;
+    std::vector<long long> offs(1, 0);
+    for (const auto& c : clouds) { flat.insert(flat.end(), c.begin(), c.end()); offs.push_back((long long)flat.size()); }
+    return loadPriorSession(kp.data(), (int)kp.size(), flat.data(), offs.data());
+}
+
+bool mapOptimization::saveSession(const std::string& dir) {
+    if (!ctx_) { error_ = "no device context"; return false; }
+    std::error_code ec;
+    std::filesystem::create_directories(dir + "/PCDs", ec);
+    if (ec) { error_ = "cannot create " + dir + "/PCDs: " + ec.message(); return false; }
+    if (!saveSessionGraph(dir + "/singlesession_posegraph.g2o", cloudKeyPoses6D, error_)) return false;
+    std::vector<liloc_point> buf;
+    for (int k = 0; k < (int)cloudKeyPoses6D.size(); ++k) {
+        int n = 0;
+        if (liloc_keyframe_get(ctx_, LILOC_SURF, k, nullptr, 0, &n) < 0) { error_ = liloc_last_error(ctx_); return false; }
+        buf.resize((size_t)(n > 0 ? n : 1));
+        if (liloc_keyframe_get(ctx_, LILOC_SURF, k, buf.data(), n, &n) < 0) { error_ = liloc_last_error(ctx_); return false; }
+        if (!savePCDBinary(dir + "/PCDs/" + std::to_string(k) + ".pcd", buf.data(), n, error_)) return false;
+    }
+    std::vector<liloc_point> gm;                      // globalMap.pcd (:612-621)
+    if (!publishGlobalMap(gm)) return false;
+    return savePCDBinary(dir + "/globalMap.pcd", gm.data(), (int)gm.size(), error_);
 }
 
 void mapOptimization::initialposeHandler(float x, float y, float yaw) {        // :755-769: only x, y and yaw are taken

@@ -111,6 +111,11 @@ public:
     //      (SURVEY.md 2, rows 12-13): the registration result is reported, not fused.
     // Prior key clouds (body frame, concatenated; offsets has n + 1 entries) + key poses -> device keyframes + submaps.
     bool loadPriorSession(const PointTypePose* keyPoses, int n, const liloc_point* clouds, const long long* offsets);
+    // The same from a session directory in the reference's on-disk format (singlesession_posegraph.g2o + PCDs/<k>.pcd,
+    // dataLoader.hpp:207-304), and the writer of that format for the current session (save_session / save_map,
+    // :420-635: pose graph + one PCD per keyframe; nothing is deleted, unlike the reference's `rm -r`).
+    bool loadPriorSessionDir(const std::string& session_dir);
+    bool saveSession(const std::string& session_dir);
     void initialposeHandler(float x, float y, float yaw);                       // :755-769
     int searchNearestSubMap(float x, float y, float z) const;                   // dataLoader.hpp:350-357 (1-NN on the centroids)
     std::vector<int> searchVertexes(int submap, float x, float y, float z) const;   // dataLoader.hpp:366-389 (radius 5 m, at most 3)

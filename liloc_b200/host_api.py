@@ -52,6 +52,18 @@ def _load():
     L.liloc_host_load_prior.restype = C.c_int
     L.liloc_host_load_prior.argtypes = [P, P, C.c_int, P, P]
     L.liloc_host_initialpose.argtypes = [P, C.c_float, C.c_float, C.c_float]
+    L.liloc_host_load_prior_dir.restype = C.c_int
+    L.liloc_host_load_prior_dir.argtypes = [P, C.c_char_p]
+    L.liloc_host_save_session.restype = C.c_int
+    L.liloc_host_save_session.argtypes = [P, C.c_char_p]
+    L.liloc_host_load_pcd.restype = C.c_int
+    L.liloc_host_load_pcd.argtypes = [C.c_char_p, P, C.c_int, C.c_char_p, C.c_int]
+    L.liloc_host_save_pcd.restype = C.c_int
+    L.liloc_host_save_pcd.argtypes = [C.c_char_p, P, C.c_int]
+    L.liloc_host_load_g2o.restype = C.c_int
+    L.liloc_host_load_g2o.argtypes = [C.c_char_p, P, C.c_int]
+    L.liloc_host_save_g2o.restype = C.c_int
+    L.liloc_host_save_g2o.argtypes = [C.c_char_p, P, C.c_int]
     L.liloc_host_submap_info.restype = C.c_int
     L.liloc_host_submap_info.argtypes = [P, C.c_int, P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.liloc_host_set_s2m_opts.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -87,6 +99,39 @@ def lib():
     if _lib is None:
         _lib = _load()
     return _lib
+
+
+def load_pcd(path: str) -> np.ndarray:
+    """pcl::io::loadPCDFile<PointXYZI> as the host reads session files (liloc_b200/host/session_io.cpp)."""
+    err = C.create_string_buffer(512)
+    n = lib().liloc_host_load_pcd(path.encode(), None, 0, err, 512)
+    if n < 0:
+        raise IOError(err.value.decode())
+    out = np.empty((max(n, 1), 4), np.float32)
+    lib().liloc_host_load_pcd(path.encode(), out.ctypes.data, len(out), err, 512)
+    return out[:n]
+
+
+def save_pcd(path: str, pts) -> None:
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+    if lib().liloc_host_save_pcd(path.encode(), p.ctypes.data, len(p)) != 0:
+        raise IOError(path)
+
+
+def load_g2o(path: str) -> np.ndarray:
+    """Key poses (n, 7) [roll, pitch, yaw, x, y, z, node id] of a singlesession_posegraph.g2o."""
+    n = lib().liloc_host_load_g2o(path.encode(), None, 0)
+    if n < 0:
+        raise IOError(path)
+    out = np.zeros((n, 7), np.float64)
+    lib().liloc_host_load_g2o(path.encode(), out.ctypes.data, n)
+    return out
+
+
+def save_g2o(path: str, keyposes7) -> None:
+    kp = np.ascontiguousarray(keyposes7, np.float64).reshape(-1, 7)
+    if lib().liloc_host_save_g2o(path.encode(), kp.ctypes.data, len(kp)) != 0:
+        raise IOError(path)
 
 
 def yaml_param(yaml: str, key: str) -> float:
@@ -167,6 +212,16 @@ class MapOptimization:
         if n < 0:
             raise RuntimeError("loadPriorSession: " + (lib().liloc_host_error(self._h) or b"").decode())
         return n
+
+    def load_prior_session_dir(self, session_dir: str) -> int:
+        n = lib().liloc_host_load_prior_dir(self._h, session_dir.encode())
+        if n < 0:
+            raise RuntimeError("loadPriorSessionDir: " + (lib().liloc_host_error(self._h) or b"").decode())
+        return n
+
+    def save_session(self, session_dir: str) -> None:
+        if lib().liloc_host_save_session(self._h, session_dir.encode()) != 0:
+            raise RuntimeError("saveSession: " + (lib().liloc_host_error(self._h) or b"").decode())
 
     def initialpose(self, x: float, y: float, yaw: float):
         """/initialpose (src/mapOptmization.cpp:755-769)."""

@@ -138,3 +138,40 @@ def test_icp_fitness_bit_exact(gpu_ctx, orc, synth):
     gpu_ctx.ndt_source_put(0, b)
     got = gpu_ctx.icp_fitness_resident(5, traj[0], 0, traj[2])
     assert got == orc.icp_fitness(a, traj[0].astype(np.float32), b, traj[2].astype(np.float32), threads=8)
+
+
+def test_session_round_trip_lio_save_then_relocalise(tmp_path, orc, synth):
+    """A lio session saved in the reference's on-disk format (g2o + PCDs/<k>.pcd, src/mapOptmization.cpp:420-635) is loaded
+    as the prior session of a relo run (dataLoader.hpp:207-348) and the first scan of a new session relocalises on it."""
+    from liloc_b200 import host_api
+    seq = synth.make_sequence(synth.VLP16, 40, seed=6, world_size=(60.0, 40.0), n_pillars=14, loop_radius=(20.0, 11.0), dt=0.21)
+    sdir = str(tmp_path / "session")
+    with host_api.MapOptimization("lio_sam_default.yaml", "lio", device=0) as m:
+        reps = m.run(host_api.make_infos(seq.scans, seq.odom, seq.stamps))
+        n_kf = m.num_keyframes()
+        kp = m.keyposes()
+        m.save_session(sdir)
+        kf_ids = [r.keyframe_id for r in reps if r.keyframe_id >= 0]
+        frames_of_kf = [f for f, r in enumerate(reps) if r.keyframe_id >= 0]
+    assert n_kf > 10 and sorted(os.listdir(os.path.join(sdir, "PCDs")), key=lambda s: int(s[:-4])) == [f"{k}.pcd" for k in range(n_kf)]
+    # the files hold exactly what the session held
+    back = host_api.load_g2o(os.path.join(sdir, "singlesession_posegraph.g2o"))
+    dang = (back[:, :3] - kp[:, :3] + np.pi) % (2 * np.pi) - np.pi                  # yaw may come back as -pi instead of +pi
+    assert len(back) == n_kf and np.abs(back[:, 3:6] - kp[:, 3:6]).max() < 5e-6 and np.abs(dang).max() < 5e-6
+    k = kf_ids[3]
+    assert np.array_equal(host_api.load_pcd(os.path.join(sdir, "PCDs", f"{k}.pcd")), orc.voxelgrid(seq.scans[frames_of_kf[3]], 0.2))
+    assert len(host_api.load_pcd(os.path.join(sdir, "globalMap.pcd"))) > 1000
+    # new session in relo mode against the saved one: scan of frame 12, /initialpose 0.4 m / 0.04 rad off its lio pose
+    f = 12
+    truth = np.array(reps[f].pose, np.float32)
+    with host_api.MapOptimization("lio_sam_default.yaml", "relo", device=0) as r:
+        assert r.load_prior_session_dir(sdir) == (n_kf + 9) // 10
+        r.initialpose(truth[3] + 0.3, truth[4] - 0.25, truth[2] + 0.04)
+        info = host_api.make_infos([seq.scans[f]], seq.odom[f:f + 1], np.array([900.0]))
+        rep = r.handle(info[0])
+        assert rep.processed == 1 and rep.relo_initialized == 1 and rep.relo_converged == 1
+        got = np.array(rep.relo_pose, np.float32)
+        assert np.abs(got[3:5] - truth[3:5]).max() < 0.1 and abs(got[2] - truth[2]) < 0.01
+
+
+import os  # noqa: E402

@@ -1,0 +1,95 @@
+"""CPU tests of the session file format (liloc_b200/host/session_io.cpp): the PCD and g2o files the reference writes in
+save_map / save_session (src/mapOptmization.cpp:420-635) and reads in dataManager::Session (dataLoader.hpp:207-304).
+PCL and GTSAM are not available here, so the files are produced byte by byte the way those libraries lay them out."""
+import os
+
+import numpy as np
+import pytest
+
+
+def _pcd_header(fields, sizes, types, counts, n, data):
+    return ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS %s\nSIZE %s\nTYPE %s\nCOUNT %s\nWIDTH %d\nHEIGHT 1\n"
+            "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n" % (" ".join(fields), " ".join(map(str, sizes)), " ".join(types), " ".join(map(str, counts)), n, n, data)).encode()
+
+
+def test_pcd_binary_xyzi_as_pcl_writes_it(tmp_path):
+    from liloc_b200 import host_api
+    rng = np.random.default_rng(1)
+    pts = rng.normal(size=(777, 4)).astype(np.float32) * 30
+    p = tmp_path / "0.pcd"
+    p.write_bytes(_pcd_header(["x", "y", "z", "intensity"], [4] * 4, ["F"] * 4, [1] * 4, len(pts), "binary") + pts.tobytes())
+    assert np.array_equal(host_api.load_pcd(str(p)), pts)
+    # our writer produces the same bytes, and reads back
+    q = tmp_path / "1.pcd"
+    host_api.save_pcd(str(q), pts)
+    assert q.read_bytes() == p.read_bytes()
+    assert np.array_equal(host_api.load_pcd(str(q)), pts)
+
+
+def test_pcd_padding_extra_fields_and_field_order(tmp_path):
+    from liloc_b200 import host_api
+    rng = np.random.default_rng(2)
+    n = 100
+    pts = rng.normal(size=(n, 4)).astype(np.float32)
+    # old PCL layouts keep the struct padding as "_" fields: x y z _ intensity _(x3)  = the 32-byte in-memory PointXYZI
+    rec = np.zeros((n, 8), np.float32)
+    rec[:, 0:3] = pts[:, :3]; rec[:, 3] = 1.0; rec[:, 4] = pts[:, 3]
+    p = tmp_path / "pad.pcd"
+    p.write_bytes(_pcd_header(["x", "y", "z", "_", "intensity", "_"], [4, 4, 4, 4, 4, 4], ["F"] * 6, [1, 1, 1, 1, 1, 3], n, "binary") + rec.tobytes())
+    assert np.array_equal(host_api.load_pcd(str(p)), pts)
+    # other field order + an integer ring field + a double time field (Velodyne-style clouds)
+    dt = np.dtype([("intensity", "<f4"), ("ring", "<u2"), ("z", "<f4"), ("time", "<f8"), ("y", "<f4"), ("x", "<f4")])
+    r2 = np.zeros(n, dt)
+    r2["x"], r2["y"], r2["z"], r2["intensity"], r2["ring"], r2["time"] = pts[:, 0], pts[:, 1], pts[:, 2], pts[:, 3], 7, 1.5
+    p2 = tmp_path / "order.pcd"
+    p2.write_bytes(_pcd_header(["intensity", "ring", "z", "time", "y", "x"], [4, 2, 4, 8, 4, 4], ["F", "U", "F", "F", "F", "F"], [1] * 6, n, "binary") + r2.tobytes())
+    assert np.array_equal(host_api.load_pcd(str(p2)), pts)
+    # xyz only -> intensity 0
+    p3 = tmp_path / "xyz.pcd"
+    p3.write_bytes(_pcd_header(["x", "y", "z"], [4] * 3, ["F"] * 3, [1] * 3, n, "binary") + np.ascontiguousarray(pts[:, :3]).tobytes())
+    got = host_api.load_pcd(str(p3))
+    assert np.array_equal(got[:, :3], pts[:, :3]) and not got[:, 3].any()
+
+
+def test_pcd_ascii_and_errors(tmp_path):
+    from liloc_b200 import host_api
+    pts = np.array([[1.5, -2.25, 3.0, 10.0], [0.0, 0.125, -7.5, 255.0]], np.float32)
+    p = tmp_path / "a.pcd"
+    p.write_bytes(_pcd_header(["x", "y", "z", "intensity"], [4] * 4, ["F"] * 4, [1] * 4, 2, "ascii") + b"1.5 -2.25 3 10\n0 0.125 -7.5 255\n")
+    assert np.array_equal(host_api.load_pcd(str(p)), pts)
+    with pytest.raises(IOError):
+        host_api.load_pcd(str(tmp_path / "missing.pcd"))
+    bad = tmp_path / "short.pcd"
+    bad.write_bytes(_pcd_header(["x", "y", "z", "intensity"], [4] * 4, ["F"] * 4, [1] * 4, 10, "binary") + b"\0" * 40)
+    with pytest.raises(IOError, match="truncated"):
+        host_api.load_pcd(str(bad))
+    comp = tmp_path / "comp.pcd"
+    comp.write_bytes(_pcd_header(["x", "y", "z", "intensity"], [4] * 4, ["F"] * 4, [1] * 4, 1, "binary_compressed") + b"\0" * 16)
+    with pytest.raises(IOError, match="not supported"):
+        host_api.load_pcd(str(comp))
+
+
+def test_g2o_vertices_round_trip(tmp_path):
+    from liloc_b200 import host_api
+    # a file in the reference's own format (README example line, dataLoader.hpp:60) with edges mixed in and ids out of order
+    txt = ("VERTEX_SE3:QUAT 1 1.000000 2.000000 0.500000 0.000000 0.000000 0.382683 0.923880\n"
+           "VERTEX_SE3:QUAT 0 0.000000 0.000000 0.000000 0.000000 0.000000 0.000000 1.000000\n"
+           "EDGE_SE3:QUAT 0 1 1.000000 2.000000 0.500000 0.000000 0.000000 0.382683 0.923880\n"
+           "VERTEX_SE3:QUAT 99 -61.332581 -9.253125 0.131973 -0.004256 -0.005810 -0.625732 0.780005\n")
+    p = tmp_path / "g.g2o"
+    p.write_text(txt)
+    kp = host_api.load_g2o(str(p))
+    assert kp.shape == (3, 7) and list(kp[:, 6]) == [0, 1, 99]                    # ascending node id, id in `intensity`
+    assert np.allclose(kp[1, :6], [0, 0, np.pi / 4, 1, 2, 0.5], atol=1e-5)
+    q = np.array([-0.004256, -0.005810, -0.625732, 0.780005]); q /= np.linalg.norm(q)
+    yaw = np.arctan2(2 * (q[0] * q[1] + q[3] * q[2]), 1 - 2 * (q[1] ** 2 + q[2] ** 2))
+    assert abs(kp[2, 2] - yaw) < 1e-6 and np.allclose(kp[2, 3:6], [-61.332581, -9.253125, 0.131973], atol=1e-5)
+    # writer -> reader: poses survive the 6-decimal text format
+    rng = np.random.default_rng(3)
+    poses = np.c_[rng.uniform(-0.3, 0.3, (20, 2)), rng.uniform(-3, 3, 20), rng.uniform(-50, 50, (20, 3)), np.zeros(20)]
+    out = tmp_path / "w.g2o"
+    host_api.save_g2o(str(out), poses)
+    lines = out.read_text().splitlines()
+    assert sum(l.startswith("VERTEX_SE3:QUAT") for l in lines) == 20 and sum(l.startswith("EDGE_SE3:QUAT") for l in lines) == 19
+    back = host_api.load_g2o(str(out))
+    assert np.abs(back[:, :3] - poses[:, :3]).max() < 5e-6 and np.abs(back[:, 3:6] - poses[:, 3:6]).max() < 5e-6   # float32 + 6 decimals

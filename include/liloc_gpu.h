@@ -114,6 +114,33 @@ int liloc_scan_put(liloc_ctx* ctx, const liloc_point* pts_body, int n, float lea
 int liloc_scan_put_dev(liloc_ctx* ctx, const liloc_point* pts_body_dev, int n, float leaf, int* Q_all_out);
 int liloc_scan_ds_get(liloc_ctx* ctx, liloc_point* out, int cap, int* Q_all_out);  /* laserCloudSurfLastDS */
 
+/* ---- de-skew: imageProjection::projectPointCloud src/imageProjection.cpp:645-673 ------
+ * The step before the path: the raw sweep is uploaded once; the range / ring / stride filters (:654-668), the
+ * IMU-interpolated rotation of every surviving point (deskewPoint :615-643, findRotation :573-597) and the
+ * compaction into fullCloud (push_back order) run on the device.  The de-skewed cloud (`cloud_deskewed`) stays there:
+ * pass LILOC_SCAN_DESKEWED as scan_on_device / on_device to liloc_frame, liloc_frame_features, liloc_scan_put_class or
+ * liloc_ndt_source_put to consume it without a host round trip (its size is read from device memory).
+ * The IMU arrays are what imuDeskewInfo (:441-496) fills on the host: imu_pointer_cur + 1 valid entries (<= 2000). */
+typedef struct { int ring; float time; } liloc_ring_time;      /* PointXYZIRT::ring / ::time (src/imageProjection.cpp:5-16) */
+typedef struct {
+    double time_scan_cur;                                      /* timeScanCur (:414) */
+    const double* imu_time; const double* imu_rot_x; const double* imu_rot_y; const double* imu_rot_z;
+    int imu_pointer_cur;                                       /* after the decrement of :490 */
+    int deskew_flag;                                           /* -1: no time channel (:400-410) */
+    int imu_available;                                         /* cloudInfo.imuAvailable (:495) */
+    float lidar_min_range, lidar_max_range;                    /* [1.0, 1000.0] include/utility.h:257-258 */
+    int n_scan, downsample_rate, point_filter_num;             /* N_SCAN, [1], [3] include/utility.h:254-255 */
+    int reserved[2];
+} liloc_deskew_params;
+#define LILOC_SCAN_HOST 0
+#define LILOC_SCAN_DEVICE 1
+#define LILOC_SCAN_DESKEWED 2
+/* n_out may be NULL: then nothing is synchronised and the count stays on the device. */
+int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* ring_time, int n,
+                 const liloc_deskew_params* params, int* n_out);
+int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out);   /* fullCloud, for publishClouds (:675-679) */
+int liloc_last_deskew_ms(liloc_ctx* ctx, float* ms);                             /* device time of the last de-skew launch (liloc_set_timing) */
+
 /* ---- registration: scan2MapOptimization :1183-1201 (everything except transformUpdate :1202) -----
  * pose6: in = initial guess (updateInitialGuess :831-900), out = optimised transformTobeMapped.
  * All iterations run on the device without a host round trip.  isDegenerate / matP persist in the

@@ -83,6 +83,19 @@ def stats_of(ctx_handle) -> dict:
     return st.as_dict()
 
 
+class DeskewParams(C.Structure):
+    """liloc_deskew_params: what imuDeskewInfo / cachePointCloud leave for projectPointCloud (src/imageProjection.cpp)."""
+    _fields_ = [("time_scan_cur", C.c_double),
+                ("imu_time", C.c_void_p), ("imu_rot_x", C.c_void_p), ("imu_rot_y", C.c_void_p), ("imu_rot_z", C.c_void_p),
+                ("imu_pointer_cur", C.c_int), ("deskew_flag", C.c_int), ("imu_available", C.c_int),
+                ("lidar_min_range", C.c_float), ("lidar_max_range", C.c_float),
+                ("n_scan", C.c_int), ("downsample_rate", C.c_int), ("point_filter_num", C.c_int), ("reserved", C.c_int * 2)]
+
+
+RING_TIME = np.dtype([("ring", np.int32), ("time", np.float32)])
+SCAN_HOST, SCAN_DEVICE, SCAN_DESKEWED = 0, 1, 2
+
+
 class NdtOpts(C.Structure):
     """liloc_ndt_opts; defaults = ndt_omp defaults + LiLoc's yaml (ndtEpsilon 0.01, regMethod DIRECT1)."""
     _fields_ = [("step_size", C.c_double), ("outlier_ratio", C.c_double), ("trans_eps", C.c_double),
@@ -128,6 +141,9 @@ def _load() -> C.CDLL:
         "liloc_keyframe_put": (C.c_int, [P, C.c_int, P, C.c_int]),
         "liloc_keyframe_put_from_scan": (C.c_int, [P, C.c_int]),
         "liloc_keyframe_size": (C.c_int, [P, C.c_int]),
+        "liloc_deskew": (C.c_int, [P, P, P, C.c_int, C.POINTER(DeskewParams), ip]),
+        "liloc_deskewed_get": (C.c_int, [P, P, C.c_int, ip]),
+        "liloc_last_deskew_ms": (C.c_int, [P, fp]),
         "liloc_keyframe_clear": (C.c_int, [P]),
         "liloc_localmap_build": (C.c_int, [P, P, P, C.c_int, C.c_float, ip, ip]),
         "liloc_localmap_set": (C.c_int, [P, P, C.c_int, C.c_float, ip]),
@@ -196,7 +212,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -303,6 +319,51 @@ class Context:
         self._chk(lib.liloc_scan_put_dev(self._h, C.c_void_p(dev_ptr), n, leaf, C.byref(Q)))
         return Q.value
 
+    # ---- de-skew (imageProjection::projectPointCloud) ----
+    def deskew(self, pts, ring, time, imu_time=None, imu_rot=None, time_scan_cur: float = 0.0, deskew_flag: int = 1,
+               imu_available: bool = True, min_range: float = 1.0, max_range: float = 1000.0, n_scan: int = 16,
+               downsample_rate: int = 1, point_filter_num: int = 3, sync: bool = True) -> int | None:
+        """liloc_deskew.  imu_time: (m,) float64, imu_rot: (m, 3) float64 integrated angles (imuRotX/Y/Z); the last valid
+        index is m - 1.  Returns the size of the de-skewed cloud (None with sync=False: it stays on the device)."""
+        p = _cloud(pts)
+        rt = np.empty(len(p), RING_TIME)
+        rt["ring"], rt["time"] = np.asarray(ring, np.int32), np.asarray(time, np.float32)
+        dp = DeskewParams()
+        dp.time_scan_cur = float(time_scan_cur)
+        keep = []
+        if imu_time is not None and len(imu_time):
+            t = np.ascontiguousarray(imu_time, np.float64)
+            r = [np.ascontiguousarray(np.asarray(imu_rot, np.float64)[:, k]) for k in range(3)]
+            keep = [t, *r]
+            dp.imu_time, dp.imu_rot_x, dp.imu_rot_y, dp.imu_rot_z = (a.ctypes.data for a in keep)
+            dp.imu_pointer_cur = len(t) - 1
+        else:
+            dp.imu_pointer_cur = -1
+            imu_available = False
+        dp.deskew_flag, dp.imu_available = int(deskew_flag), int(bool(imu_available))
+        dp.lidar_min_range, dp.lidar_max_range = float(min_range), float(max_range)
+        dp.n_scan, dp.downsample_rate, dp.point_filter_num = int(n_scan), int(downsample_rate), int(point_filter_num)
+        n = C.c_int()
+        self._chk(lib.liloc_deskew(self._h, _ptr(p), _ptr(rt), len(p), C.byref(dp), C.byref(n) if sync else None))
+        return n.value if sync else None
+
+    def deskewed_get(self) -> np.ndarray:
+        n = C.c_int()
+        self._chk(lib.liloc_deskewed_get(self._h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        self._chk(lib.liloc_deskewed_get(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def last_deskew_ms(self) -> float:
+        ms = C.c_float()
+        self._chk(lib.liloc_last_deskew_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def scan_put_deskewed(self, leaf: float) -> int:
+        Q = C.c_int()
+        self._chk(lib.liloc_scan_put_class(self._h, 0, None, 0, SCAN_DESKEWED, leaf, C.byref(Q)))
+        return Q.value
+
     def scan_ds_get(self, cls: int = 0) -> np.ndarray:
         Q = C.c_int()
         self._chk(lib.liloc_scan_ds_get_class(self._h, cls, None, 0, C.byref(Q)))
@@ -325,7 +386,9 @@ class Context:
         pose = np.array(pose6, dtype=np.float32).reshape(6).copy()
         res = S2mResult()
         o = opts or S2mOpts()
-        if scan_dev_ptr is not None:
+        if scan is None and scan_dev_ptr is None:           # the de-skewed sweep the context holds
+            sp, n, on_dev = None, 0, SCAN_DESKEWED
+        elif scan_dev_ptr is not None:
             sp, n, on_dev = C.c_void_p(scan_dev_ptr), int(n_scan), 1
         else:
             s = _cloud(scan)
@@ -425,7 +488,9 @@ class Context:
         return nl.value, npts.value
 
     def ndt_source_put(self, source_id: int, pts_body=None, dev_ptr: int | None = None, n: int | None = None) -> None:
-        if dev_ptr is not None:
+        if pts_body is None and dev_ptr is None:            # the de-skewed sweep the context holds
+            self._chk(lib.liloc_ndt_source_put(self._h, source_id, None, 0, SCAN_DESKEWED))
+        elif dev_ptr is not None:
             self._chk(lib.liloc_ndt_source_put(self._h, source_id, C.c_void_p(dev_ptr), int(n), 1))
         else:
             p = _cloud(pts_body)

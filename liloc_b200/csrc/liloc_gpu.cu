@@ -30,6 +30,7 @@
 #include "pipeline.cuh"
 #include "s2m.cuh"
 #include "ndt.cuh"
+#include "deskew.cuh"
 
 using namespace liloc;
 
@@ -91,6 +92,7 @@ struct HostFrameInfo {     // pinned, written by async D2H
     S2mResult res;
     unsigned long long marks[2 * kPipeMarks + kS2mMarks];
     int scratch;
+    int dk_n;
 };
 
 }  // namespace
@@ -154,6 +156,21 @@ struct liloc_ctx {
     int* d_ndt_counters = nullptr;       // 3 ints
     unsigned long long* d_ndt_ns = nullptr;
     int ndt_max_blocks = 0;
+
+    // de-skew (imageProjection): raw sweep in, de-skewed cloud out into fc[0].scan_raw
+    DevBuf<float4> dk_pts;
+    DevBuf<int2> dk_rt;
+    DevBuf<int> dk_tiles;
+    double* d_dk_imu = nullptr;          // 4 x kImuMax
+    double* h_dk_imu = nullptr;          // pinned staging of the same, two slots
+    int dk_slot = 0;
+    cudaEvent_t ev_dk_slot[2]{};
+    int* d_dk_n = nullptr;               // points of the de-skewed cloud
+    int dk_n_upper = -1;                 // raw points of the last sweep (-1: no de-skewed cloud)
+    int dk_n = -1;                       // host copy of *d_dk_n, -1 while unknown
+    cudaEvent_t ev_deskew = nullptr;
+    cudaEvent_t ev_dk[2]{};              // timing
+    float dk_ms = 0.f;
 
     // kernel-level test scratch
     DevBuf<float4> tmp_pts;
@@ -359,21 +376,35 @@ int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids
     return 0;
 }
 
-// Scan problem of class `cls`: H2D on `st` (unless the scan is already on the device) -> VoxelGrid.
-int scan_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pts, int n, bool on_device, float leaf, VgProb* q) {
+// Scan problem of class `cls`: H2D on `st` (LILOC_SCAN_HOST), a caller-owned device cloud (LILOC_SCAN_DEVICE) or the
+// de-skewed sweep this context holds (LILOC_SCAN_DESKEWED: its size is read from device memory) -> VoxelGrid.
+int scan_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pts, int n, int mode, float leaf, VgProb* q) {
     FeatClass& fc = ctx->fc[cls];
+    const int* n_dev = nullptr;
+    if (mode == LILOC_SCAN_DESKEWED) {
+        if (cls != LILOC_SURF) return fail(ctx, LILOC_ERR_ARG, "scan_put: the de-skewed sweep is the surf-class scan");
+        if (ctx->dk_n_upper < 0) return fail(ctx, LILOC_ERR_STATE, "scan_put: no de-skewed sweep (call liloc_deskew first)");
+        pts = reinterpret_cast<const liloc_point*>(fc.scan_raw.p);
+        n = ctx->dk_n >= 0 ? ctx->dk_n : ctx->dk_n_upper;
+        if (ctx->dk_n < 0) n_dev = ctx->d_dk_n;
+        CU(cudaStreamWaitEvent(st, ctx->ev_deskew, 0));
+    } else if (mode != LILOC_SCAN_HOST && mode != LILOC_SCAN_DEVICE) {
+        return fail(ctx, LILOC_ERR_ARG, "scan_put: bad scan_on_device %d", mode);
+    }
     if (n < 0 || (n > 0 && !pts) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad arguments");
     int rc;
     fc.have_scan = false; fc.Q_all = -1;
     const float4* src = reinterpret_cast<const float4*>(pts);
-    if (!on_device && n > 0) {
+    if (mode == LILOC_SCAN_HOST && n > 0) {
         if ((rc = ensure(ctx, fc.scan_raw, (size_t)n))) return rc;
         CU(cudaMemcpyAsync(fc.scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += (long long)n * (long long)sizeof(float4);
         src = fc.scan_raw.p;
+        if (cls == LILOC_SURF) ctx->dk_n_upper = -1;          // the de-skewed sweep lived in this buffer
     }
     fc.scan_src_last = src; fc.scan_leaf_last = leaf;
     if ((rc = prob_voxelgrid(ctx, fc.vg_scan, src, n, leaf, &fc.scan, q))) return rc;
+    q->n_dev = n_dev;
     fc.n_scan_last = n;
     fc.have_scan = true;
     return 0;
@@ -537,6 +568,13 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaMalloc(&c->d_ndt_ns, 3 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_sm_scratch, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMemset(c->d_sm_scratch, 0, 2 * kSmScratch * sizeof(int)));
+    CUB_(cudaMalloc(&c->d_dk_imu, 4 * kImuMax * sizeof(double)));
+    CUB_(cudaMallocHost(&c->h_dk_imu, 2 * 4 * kImuMax * sizeof(double)));
+    for (auto& e : c->ev_dk_slot) CUB_(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUB_(cudaMalloc(&c->d_dk_n, sizeof(int)));
+    CUB_(cudaMemset(c->d_dk_n, 0, sizeof(int)));
+    CUB_(cudaEventCreateWithFlags(&c->ev_deskew, cudaEventDisableTiming));
+    for (auto& e : c->ev_dk) CUB_(cudaEventCreate(&e));
     CUB_(cudaMalloc(&c->d_marks, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_marks, 0, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
 #undef CUB_
@@ -578,6 +616,11 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
     fr(c->d_marks); fr(c->d_sm_scratch);
+    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu); fr(c->d_dk_n);
+    if (c->h_dk_imu) cudaFreeHost(c->h_dk_imu);
+    if (c->ev_deskew) cudaEventDestroy(c->ev_deskew);
+    for (auto& e : c->ev_dk) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_dk_slot) if (e) cudaEventDestroy(e);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
@@ -737,7 +780,7 @@ int liloc_localmap_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap,
 int liloc_localmap_get(liloc_ctx* ctx, liloc_point* out, int cap, int* M_out) { return liloc_localmap_get_class(ctx, LILOC_SURF, out, cap, M_out); }
 
 // ---- current scan -------------------------------------------------------------------------------------
-static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n, bool on_device, float leaf, int* Q_all_out) {
+static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n, int on_device, float leaf, int* Q_all_out) {
     ENTER(ctx);
     if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "scan_put: bad class %d", cls);
     int rc;
@@ -748,16 +791,17 @@ static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n,
     if ((rc = class_fetch(ctx, cls, ctx->stream, false, true))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, false, true);
+    if (on_device == LILOC_SCAN_DESKEWED) { ctx->dk_n = ctx->h_info->dk_n; ctx->fc[cls].n_scan_last = ctx->dk_n; }
     if (cls == LILOC_SURF) ctx->corner_scan_current = false;      // a new frame starts with its surf scan
     else ctx->corner_scan_current = true;
     if (Q_all_out) *Q_all_out = ctx->fc[cls].Q_all;
     return LILOC_OK;
 }
 
-int liloc_scan_put(liloc_ctx* ctx, const liloc_point* pts, int n, float leaf, int* Q_all_out) { return scan_put_impl(ctx, LILOC_SURF, pts, n, false, leaf, Q_all_out); }
-int liloc_scan_put_dev(liloc_ctx* ctx, const liloc_point* pts_dev, int n, float leaf, int* Q_all_out) { return scan_put_impl(ctx, LILOC_SURF, pts_dev, n, true, leaf, Q_all_out); }
+int liloc_scan_put(liloc_ctx* ctx, const liloc_point* pts, int n, float leaf, int* Q_all_out) { return scan_put_impl(ctx, LILOC_SURF, pts, n, LILOC_SCAN_HOST, leaf, Q_all_out); }
+int liloc_scan_put_dev(liloc_ctx* ctx, const liloc_point* pts_dev, int n, float leaf, int* Q_all_out) { return scan_put_impl(ctx, LILOC_SURF, pts_dev, n, LILOC_SCAN_DEVICE, leaf, Q_all_out); }
 int liloc_scan_put_class(liloc_ctx* ctx, int cls, const liloc_point* pts, int n, int on_device, float leaf, int* Q_all_out) {
-    return scan_put_impl(ctx, cls, pts, n, on_device != 0, leaf, Q_all_out);
+    return scan_put_impl(ctx, cls, pts, n, on_device, leaf, Q_all_out);
 }
 
 int liloc_scan_ds_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, int* Q_all_out) {
@@ -775,6 +819,103 @@ int liloc_scan_ds_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, 
 }
 
 int liloc_scan_ds_get(liloc_ctx* ctx, liloc_point* out, int cap, int* Q_all_out) { return liloc_scan_ds_get_class(ctx, LILOC_SURF, out, cap, Q_all_out); }
+
+// ---- de-skew (imageProjection::projectPointCloud, src/imageProjection.cpp:645-673) ---------------------------------
+// Runs on stream2 (the scan branch of a fused frame): H2D of the raw sweep and of the IMU arrays, one cooperative
+// launch, the count back into pinned memory.  Nothing is synchronised unless the caller asks for the count.
+int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* ring_time, int n, const liloc_deskew_params* p, int* n_out) {
+    ENTER(ctx);
+    if (n < 0 || (n > 0 && (!pts || !ring_time)) || !p) return fail(ctx, LILOC_ERR_ARG, "deskew: bad arguments");
+    if (p->downsample_rate < 1 || p->point_filter_num < 1) return fail(ctx, LILOC_ERR_ARG, "deskew: downsample_rate and point_filter_num must be >= 1");
+    const bool deskew = p->deskew_flag != -1 && p->imu_available != 0;
+    if (deskew && (p->imu_pointer_cur < 0 || p->imu_pointer_cur >= kImuMax || !p->imu_time || !p->imu_rot_x || !p->imu_rot_y || !p->imu_rot_z))
+        return fail(ctx, LILOC_ERR_ARG, "deskew: bad IMU arrays (imu_pointer_cur %d, queue length %d)", p->imu_pointer_cur, kImuMax);
+    int rc;
+    cudaStream_t st = ctx->stream2;
+    FeatClass& fc = ctx->fc[LILOC_SURF];
+    const size_t cap = (size_t)(n > 0 ? n : 1);
+    if ((rc = ensure(ctx, ctx->dk_pts, cap)) || (rc = ensure(ctx, ctx->dk_rt, cap)) || (rc = ensure(ctx, fc.scan_raw, cap)) ||
+        (rc = ensure(ctx, ctx->dk_tiles, cap / kDeskewThreads + 2))) return rc;
+    // the previous sweep's consumers (main stream) must be done with scan_raw before it is overwritten
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+    if (n > 0) {
+        CU(cudaMemcpyAsync(ctx->dk_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->dk_rt.p, ring_time, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += (long long)n * 24;
+    }
+    if (deskew) {
+        const int m = p->imu_pointer_cur + 1;
+        const int slot = ctx->dk_slot; ctx->dk_slot ^= 1;          // two pinned staging slots, each guarded by an event
+        CU(cudaEventSynchronize(ctx->ev_dk_slot[slot]));
+        double* stage = ctx->h_dk_imu + (size_t)slot * 4 * kImuMax;
+        const double* src[4] = {p->imu_time, p->imu_rot_x, p->imu_rot_y, p->imu_rot_z};
+        for (int k = 0; k < 4; ++k) std::memcpy(stage + (size_t)k * m, src[k], (size_t)m * sizeof(double));
+        for (int k = 0; k < 4; ++k)
+            CU(cudaMemcpyAsync(ctx->d_dk_imu + (size_t)k * kImuMax, stage + (size_t)k * m, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(ctx->ev_dk_slot[slot], st));
+        ctx->stats.h2d_bytes += (long long)m * 32;
+    }
+    DeskewArgs a{};
+    a.pts = ctx->dk_pts.p; a.rt = ctx->dk_rt.p; a.n = n;
+    a.imu = ctx->d_dk_imu; a.imu_last = p->imu_pointer_cur; a.t_cur = p->time_scan_cur; a.deskew = deskew ? 1 : 0;
+    a.rmin = p->lidar_min_range; a.rmax = p->lidar_max_range;
+    a.n_scan = p->n_scan; a.ds_rate = p->downsample_rate; a.pf_num = p->point_filter_num;
+    a.tile_count = ctx->dk_tiles.p; a.out = fc.scan_raw.p; a.n_out = ctx->d_dk_n;
+    const int n_tiles = (n + kDeskewThreads - 1) / kDeskewThreads;
+    const int blocks = n_tiles < 1 ? 1 : (n_tiles < ctx->num_sms ? n_tiles : ctx->num_sms);
+    void* args[] = {&a};
+    if (ctx->timing) cudaEventRecord(ctx->ev_dk[0], st);
+    CU(cudaLaunchCooperativeKernel((void*)k_deskew, dim3((unsigned)blocks), dim3(kDeskewThreads), args, 0, st));
+    ++ctx->launches;
+    if (ctx->timing) cudaEventRecord(ctx->ev_dk[1], st);
+    CU(cudaMemcpyAsync(&ctx->h_info->dk_n, ctx->d_dk_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ctx->stats.d2h_bytes += 4;
+    CU(cudaEventRecord(ctx->ev_deskew, st));
+    ctx->dk_n_upper = n; ctx->dk_n = -1;
+    fc.have_scan = false; fc.Q_all = -1;
+    if (n_out) {
+        CU(cudaStreamSynchronize(st));
+        ctx->dk_n = ctx->h_info->dk_n;
+        *n_out = ctx->dk_n;
+        if (ctx->timing) cudaEventElapsedTime(&ctx->dk_ms, ctx->ev_dk[0], ctx->ev_dk[1]);
+    }
+    return LILOC_OK;
+}
+
+static int deskew_count(liloc_ctx* ctx) {          // host copy of the de-skewed cloud's size (synchronises when still unknown)
+    if (ctx->dk_n_upper < 0) return fail(ctx, LILOC_ERR_STATE, "no de-skewed sweep (call liloc_deskew first)");
+    if (ctx->dk_n < 0) {
+        CU(cudaStreamSynchronize(ctx->stream2));
+        ctx->dk_n = ctx->h_info->dk_n;
+    }
+    return 0;
+}
+
+int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out) {
+    ENTER(ctx);
+    int rc;
+    if ((rc = deskew_count(ctx))) return rc;
+    if (n_out) *n_out = ctx->dk_n;
+    if (out) {
+        if (cap < ctx->dk_n) return fail(ctx, LILOC_ERR_CAPACITY, "deskewed_get: cap %d < n %d", cap, ctx->dk_n);
+        if (ctx->dk_n > 0) CU(cudaMemcpyAsync(out, ctx->fc[LILOC_SURF].scan_raw.p, (size_t)ctx->dk_n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream2));
+        CU(cudaStreamSynchronize(ctx->stream2));
+        ctx->stats.d2h_bytes += (long long)ctx->dk_n * 16;
+    }
+    return LILOC_OK;
+}
+
+int liloc_last_deskew_ms(liloc_ctx* ctx, float* ms) {
+    ENTER(ctx);
+    if (!ms) return fail(ctx, LILOC_ERR_ARG, "last_deskew_ms: null");
+    if (ctx->timing && ctx->dk_n_upper >= 0) {
+        CU(cudaStreamSynchronize(ctx->stream2));
+        cudaEventElapsedTime(&ctx->dk_ms, ctx->ev_dk[0], ctx->ev_dk[1]);
+    }
+    *ms = ctx->dk_ms;
+    return LILOC_OK;
+}
 
 // ---- registration -------------------------------------------------------------------------------------
 int liloc_scan2map(liloc_ctx* ctx, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
@@ -795,7 +936,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     if (!pose6 || !in) return fail(ctx, LILOC_ERR_ARG, "frame: null argument");
     const liloc_s2m_opts* o = opts ? opts : &kDefaultOpts;
     const bool corner = o->enable_corner != 0;
-    const bool dev = in->scan_on_device != 0;
+    const int dev = in->scan_on_device;
     int rc;
     const int ncls = corner ? 2 : 1;
     // scans: H2D + VoxelGrid on stream2, so the copy overlaps the map pipeline on the main stream
@@ -803,7 +944,8 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     PipeArgs ps{}, pm{};
     for (int cls = 0; cls < ncls; ++cls)
-        if ((rc = scan_problem(ctx, cls, ctx->stream2, in->scan[cls], in->n_scan[cls], dev, in->scan_leaf[cls], &ps.prob[cls]))) return rc;
+        if ((rc = scan_problem(ctx, cls, ctx->stream2, in->scan[cls], in->n_scan[cls],
+                               (dev == LILOC_SCAN_DESKEWED && cls != LILOC_SURF) ? LILOC_SCAN_HOST : dev, in->scan_leaf[cls], &ps.prob[cls]))) return rc;
     ps.n_prob = ncls;
     if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
     if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks + kPipeMarks : nullptr))) return rc;
@@ -844,6 +986,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         ctx->h_info->c[1].M = r.extra[1];   ctx->h_info->c[1].Q_all = r.extra[0];
     }
     for (int cls = 0; cls < (corner ? 2 : 1); ++cls) class_collect(ctx, cls, true, true);
+    if (dev == LILOC_SCAN_DESKEWED) { ctx->dk_n = ctx->h_info->dk_n; ctx->fc[LILOC_SURF].n_scan_last = ctx->dk_n; }
     ctx->corner_scan_current = corner;
     if (ctx->timing) {
         liloc_timing& t = ctx->last_timing;
@@ -1275,6 +1418,13 @@ int liloc_ndt_target_size(liloc_ctx* ctx, int target_id) {
 
 int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts, int n, int on_device) {
     ENTER(ctx);
+    if (on_device == LILOC_SCAN_DESKEWED) {          // the de-skewed sweep this context holds (setInputSource(laserCloudSurfLast), :274)
+        int rc;
+        if ((rc = deskew_count(ctx))) return rc;
+        pts = reinterpret_cast<const liloc_point*>(ctx->fc[LILOC_SURF].scan_raw.p);
+        n = ctx->dk_n;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_deskew, 0));
+    }
     if (n <= 0 || !pts) return fail(ctx, LILOC_ERR_ARG, "ndt_source_put: bad arguments");
     liloc_ctx::NdtSourceHost& S = ctx->ndt_sources[source_id];
     if (on_device) {

@@ -37,7 +37,8 @@ constexpr int kMaxProbs = 4;
 
 struct VgProb {
     const float4* pts;         // cloud to down-sample (== raw when assembling)
-    int n;                     // points (known on the host)
+    int n;                     // points (known on the host), or their upper bound when n_dev is set
+    const int* n_dev;          // optional: the count lives on the device (written by an earlier launch: the de-skewed scan)
     float leaf;
     // optional: assemble pts from keyframes first
     const float4* arena;
@@ -74,6 +75,8 @@ struct PipeArgs {
     int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters + the sort-block counter
 };
 constexpr int kSmScratch = 513;
+
+LILOC_DEV int prob_n(const VgProb& q) { return q.n_dev ? min(__ldg(q.n_dev), q.n) : q.n; }
 
 LILOC_DEV unsigned long long global_ns() {
     unsigned long long t;
@@ -177,7 +180,7 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
     if (q.K > 0) {
         __shared__ int s_k0;
-        for (int tile = blockIdx.x; tile * kAsmTile < q.n; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile * kAsmTile < prob_n(q); tile += gridDim.x) {
             const int base = tile * kAsmTile;
             __syncthreads();
             if (threadIdx.x == 0) {               // last descriptor with dst_off <= base
@@ -197,7 +200,7 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
             for (int j = 0; j < kAsmPerThread; ++j) {
                 const int i = base + j * kPipeThreads + threadIdx.x;
                 d[j] = nullptr;
-                if (i < q.n) {
+                if (i < prob_n(q)) {
                     while (k + 1 < q.K && q.descs[k + 1].dst_off <= i) ++k;
                     d[j] = &q.descs[k];
                 }
@@ -220,7 +223,7 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
             }
         }
     } else {
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += gridDim.x * blockDim.x) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prob_n(q); i += gridDim.x * blockDim.x) {
             const float4 p = __ldg(&q.pts[i]);
             mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
             mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
@@ -238,12 +241,12 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
 
 // ---- P1: keys + histogram of the first pass ----------------------------------------------------------------------
 LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSmem& sm, const int sidx, const int nsort) {
-    const SortGeom g = sort_geom(q.n, nsort);
+    const SortGeom g = sort_geom(prob_n(q), nsort);
     if (sidx < 0 || sidx >= g.nb) return;
     unsigned* keys = q.keys[(npass + 1) & 1];                  // so that the last pass lands in buffer 1
     sm.hist[threadIdx.x] = 0;
     __syncthreads();
-    const int lo = sidx * g.C, hi = min(q.n, lo + g.C);
+    const int lo = sidx * g.C, hi = min(prob_n(q), lo + g.C);
 #pragma unroll 1
     for (int i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * kPipeThreads) {      // four point loads in flight per thread
         float4 p[4];
@@ -266,7 +269,7 @@ LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSme
 
 // ---- one radix pass: offsets, stable in-tile ranking, scatter, next histogram --------------------------------------
 LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm, const int sidx, const int nsort) {
-    const SortGeom g = sort_geom(q.n, nsort);
+    const SortGeom g = sort_geom(prob_n(q), nsort);
     if (sidx < 0 || sidx >= g.nb) return;
     const int src = (npass + 1 + pass) & 1, dst = src ^ 1;
     const unsigned* __restrict__ skeys = q.keys[src];
@@ -297,7 +300,7 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
     }
     __syncthreads();
     if (pass >= 1) hzero[sidx * 256 + t] = 0;                  // free since the previous barrier; needed two passes on
-    const int lo = sidx * g.C, hi = min(q.n, lo + g.C);
+    const int lo = sidx * g.C, hi = min(prob_n(q), lo + g.C);
     int carry = 0;                                              // items of digit t in the tiles already scattered
     for (int base = lo; base < hi; base += kSortTile) {
         const int rounds = min(kSortRounds, (hi - base + kPipeThreads - 1) / kPipeThreads);
@@ -353,14 +356,14 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
 // ---- R1: run heads per tile ---------------------------------------------------------------------------------------
 LILOC_DEV void pipe_run_count(const VgProb& q) {
     const unsigned* __restrict__ skeys = q.keys[1];
-    const int n_tiles = (q.n + kRunTile - 1) / kRunTile;
+    const int n_tiles = (prob_n(q) + kRunTile - 1) / kRunTile;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * kRunTile;
         int c = 0;
 #pragma unroll
         for (int j = 0; j < kRunPerThread; ++j) {
             const int i = base + j * kPipeThreads + threadIdx.x;
-            if (i < q.n) c += (i == 0 || skeys[i] != skeys[i - 1]) ? 1 : 0;
+            if (i < prob_n(q)) c += (i == 0 || skeys[i] != skeys[i - 1]) ? 1 : 0;
         }
         const int total = block_sum_256(c);
         if (threadIdx.x == 0) q.tile_counts[tile] = total;
@@ -371,7 +374,7 @@ LILOC_DEV void pipe_run_count(const VgProb& q) {
 LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& sm) {
     const unsigned* __restrict__ skeys = q.keys[1];
     const unsigned* __restrict__ svals = q.vals[1];
-    const int n = q.n;
+    const int n = prob_n(q);
     const int n_tiles = (n + kRunTile - 1) / kRunTile;
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) *q.count = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -460,8 +463,8 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
 
 // grid_only problems: the cloud itself is the search set -- count its points per cell, publish the count
 LILOC_DEV void pipe_cells_count_direct(const VgProb& q, const GridParams& gp) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = q.n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += gridDim.x * blockDim.x) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = prob_n(q);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prob_n(q); i += gridDim.x * blockDim.x) {
         const float4 p = q.out[i];
         const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
         const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
@@ -555,11 +558,11 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     if (threadIdx.x == 0) s_nsort = min(__ldcg(&a.sm_scratch[512]), kSortBlocksMax);
     if (threadIdx.x < np) {                                                               // P1
         const VgProb& q = a.prob[threadIdx.x];
-        const VgParams vp = vg_params_compute(q.enc, q.leaf, q.n);
+        const VgParams vp = vg_params_compute(q.enc, q.leaf, prob_n(q));
         s_vp[threadIdx.x] = vp;
-        s_npass[threadIdx.x] = (q.n > 0 && !q.grid_only) ? (vp.key_bits + 7) / 8 : 0;
+        s_npass[threadIdx.x] = (prob_n(q) > 0 && !q.grid_only) ? (vp.key_bits + 7) / 8 : 0;
         GridParams g{};
-        if (q.build_grid) g = grid_params_compute(vp.mn, vp.mx, q.n <= 0, q.max_cells);
+        if (q.build_grid) g = grid_params_compute(vp.mn, vp.mx, prob_n(q) <= 0, q.max_cells);
         s_gp[threadIdx.x] = g;
         if (blockIdx.x == 0) { *q.vp = vp; if (q.build_grid) *q.gp = g; }
     }
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     int max_pass = 0;
     for (int p = 0; p < np; ++p) max_pass = max(max_pass, s_npass[p]);
     const int sidx = s_sort_idx, nsort = s_nsort;
-    for (int p = 0; p < np; ++p) if (a.prob[p].n > 0 && !a.prob[p].grid_only) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm, sidx, nsort);
+    for (int p = 0; p < np; ++p) if (prob_n(a.prob[p]) > 0 && !a.prob[p].grid_only) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm, sidx, nsort);
     grid.sync();
     if (blockIdx.x == 0) for (int i = threadIdx.x; i < kSmScratch; i += kPipeThreads) a.sm_scratch[i] = 0;   // re-armed for the next launch
     PIPE_MARK();                                                                          // 2 after keys

@@ -212,9 +212,8 @@ void mapOptimization::downsampleCurrentScan() {
     // device call issued by scan2MapOptimization(); without, it runs here because the first keyframe needs it.
     if (!have_selection_) {
         int q = 0;
-        const int rc = cloudInfo.cloud_on_device
-            ? liloc_scan_put_dev(ctx_, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, mappingSurfLeafSize, &q)
-            : liloc_scan_put(ctx_, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, mappingSurfLeafSize, &q);
+        // cloud_on_device: LILOC_SCAN_HOST, LILOC_SCAN_DEVICE or LILOC_SCAN_DESKEWED (the sweep ImageProjection left on the device)
+        const int rc = liloc_scan_put_class(ctx_, LILOC_SURF, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device, mappingSurfLeafSize, &q);
         if (rc < 0) { error_ = liloc_last_error(ctx_); rep_.status = rc; return; }
         laserCloudSurfLastDSNum = q;
         rep_.q_all = q;

@@ -147,6 +147,60 @@ def transform_cloud(pts: np.ndarray, pose6) -> np.ndarray:
     return out
 
 
+def raw_sweep(scan_body: np.ndarray, sensor: Sensor, gyro=(0.05, -0.03, 0.4), imu_rate: float = 500.0, sweep_s: float = 0.1,
+              time_scan_cur: float = 1000.0, seed: int = 0, outliers: float = 0.02) -> dict:
+    """A raw (skewed) sweep as the LiDAR driver would publish it, built from a motion-free body-frame scan: every point
+    gets a ring (elevation bin) and a relative time (azimuth fraction of the sweep; points are ordered by time), and
+    is rotated by the inverse of the motion the sensor made since the start of the sweep under the body rate `gyro`
+    (rad/s).  A few points are made invalid (ring out of range, range below the minimum) so that the filters of
+    projectPointCloud have something to drop.  Also returns the IMU samples covering the sweep.  Inputs only: the
+    de-skew itself runs on the device."""
+    rng = np.random.default_rng(seed)
+    p = np.asarray(scan_body, np.float64)
+    az = np.arctan2(p[:, 1], p[:, 0])
+    t = (az + np.pi) / (2 * np.pi) * sweep_s
+    order = np.argsort(t, kind="stable")
+    p, t = p[order], t[order]
+    el = np.degrees(np.arctan2(p[:, 2], np.hypot(p[:, 0], p[:, 1])))
+    ring = np.clip(np.round((el - sensor.el_min_deg) / max(sensor.el_max_deg - sensor.el_min_deg, 1e-9) * (sensor.n_rings - 1)), 0,
+                   sensor.n_rings - 1).astype(np.int32)
+    w = np.asarray(gyro, np.float64)
+    n_imu = int(np.ceil((sweep_s + 0.03) * imu_rate)) + 1
+    stamps = time_scan_cur - 0.008 + np.arange(n_imu) / imu_rate
+    gyro_s = np.tile(w, (n_imu, 1)) + rng.normal(0, 1e-3, (n_imu, 3))
+    # the motion the reference assumes: integrated angles -> Rz Ry Rx; raw = R(t)^-1 R(0) p
+    ang0 = w * 0.008
+    R0 = rot_zyx(*ang0)
+    raw = np.empty((len(p), 4), np.float32)
+    ang = ang0[None, :] + w[None, :] * t[:, None]
+    for i in range(len(p)):
+        raw[i, :3] = rot_zyx(*ang[i]).T @ (R0 @ p[i, :3])
+    raw[:, 3] = p[:, 3]
+    bad = rng.random(len(p)) < outliers
+    ring = np.where(bad & (rng.random(len(p)) < 0.5), sensor.n_rings + 3, ring).astype(np.int32)
+    near = bad & (ring < sensor.n_rings)
+    raw[near, :3] *= (0.3 / np.maximum(np.linalg.norm(raw[near, :3], axis=1), 1e-6))[:, None].astype(np.float32)
+    return {"pts": raw, "ring": ring, "time": t.astype(np.float32), "imu_stamps": stamps, "imu_gyro": gyro_s,
+            "time_scan_cur": time_scan_cur, "time_scan_end": time_scan_cur + float(t[-1]) if len(t) else time_scan_cur,
+            "truth": p.astype(np.float32)}
+
+
+def imu_integrate(stamps, gyro, time_scan_end: float, queue_length: int = 2000):
+    """imuDeskewInfo (src/imageProjection.cpp:441-496) for an already-trimmed IMU queue: integrated angles per sample
+    (double, sequential).  Returns (imu_time (m,), imu_rot (m, 3)); imuPointerCur = m - 1."""
+    tt, rr = [], []
+    for i in range(len(stamps)):
+        t = float(stamps[i])
+        if t > time_scan_end + 0.01 or len(tt) >= queue_length:
+            break
+        if not tt:
+            tt.append(t); rr.append((0.0, 0.0, 0.0)); continue
+        dt = t - tt[-1]
+        rr.append(tuple(rr[-1][k] + float(gyro[i][k]) * dt for k in range(3)))
+        tt.append(t)
+    return np.asarray(tt, np.float64), np.asarray(rr, np.float64).reshape(-1, 3)
+
+
 def perturb(pose6, seed: int, dt=0.10, dr=0.02) -> np.ndarray:
     """Initial guess = ground truth + U(+-dt m, +-dr rad) per axis."""
     rng = np.random.default_rng(seed)

@@ -71,8 +71,23 @@ def _load():
     L.orc_scan2map_features.restype = C.c_int
     L.orc_scan2map_features.argtypes = [P, C.c_int, P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_int, P,
                                         C.POINTER(S2mOpts), C.POINTER(LmState), C.POINTER(S2mResult)]
+    L.orc_imu_integrate.restype = C.c_int
+    L.orc_imu_integrate.argtypes = [P, P, C.c_int, C.c_double, C.c_int, P, P, P, P]
+    L.orc_deskew.restype = C.c_int
+    L.orc_deskew.argtypes = [P, P, C.c_int, C.POINTER(DeskewParams), P]
+    L.orc_orientation_times.argtypes = [P, C.c_int, P]
     return L
 
+
+class DeskewParams(C.Structure):
+    _fields_ = [("time_scan_cur", C.c_double),
+                ("imu_time", C.c_void_p), ("imu_rot_x", C.c_void_p), ("imu_rot_y", C.c_void_p), ("imu_rot_z", C.c_void_p),
+                ("imu_pointer_cur", C.c_int), ("deskew_flag", C.c_int), ("imu_available", C.c_int),
+                ("lidar_min_range", C.c_float), ("lidar_max_range", C.c_float),
+                ("n_scan", C.c_int), ("downsample_rate", C.c_int), ("point_filter_num", C.c_int)]
+
+
+RING_TIME = np.dtype([("ring", np.int32), ("time", np.float32)])
 
 lib = _load()
 
@@ -244,6 +259,50 @@ def icp_fitness(cloud1, pose6_1, cloud2, pose6_2, kdtree=True, threads=1) -> flo
     p1 = np.ascontiguousarray(pose6_1, np.float32).reshape(6)
     p2 = np.ascontiguousarray(pose6_2, np.float32).reshape(6)
     return float(lib.orc_icp_fitness(_p(a), len(a), _p(p1), _p(b), len(b), _p(p2), 1 if kdtree else 0, threads))
+
+
+def imu_integrate(stamps, gyro, time_scan_end, cap=2000):
+    """imuDeskewInfo (src/imageProjection.cpp:441-496) -> (imu_time (m,), imu_rot (m, 3)); m - 1 = imuPointerCur."""
+    st = np.ascontiguousarray(stamps, np.float64)
+    g = np.ascontiguousarray(gyro, np.float64).reshape(-1, 3)
+    t = np.zeros(cap, np.float64); r = [np.zeros(cap, np.float64) for _ in range(3)]
+    last = lib.orc_imu_integrate(_p(st), _p(g), len(st), float(time_scan_end), cap, _p(t), _p(r[0]), _p(r[1]), _p(r[2]))
+    m = last + 1
+    return t[:m].copy(), np.stack([a[:m] for a in r], axis=1)
+
+
+def deskew(pts, ring, time, imu_time=None, imu_rot=None, time_scan_cur=0.0, deskew_flag=1, imu_available=True,
+           min_range=1.0, max_range=1000.0, n_scan=16, downsample_rate=1, point_filter_num=3) -> np.ndarray:
+    """projectPointCloud + deskewPoint (src/imageProjection.cpp:615-673) -> fullCloud."""
+    p = _c(pts)
+    rt = np.empty(len(p), RING_TIME)
+    rt["ring"], rt["time"] = np.asarray(ring, np.int32), np.asarray(time, np.float32)
+    dp = DeskewParams()
+    dp.time_scan_cur = float(time_scan_cur)
+    keep = []
+    if imu_time is not None and len(imu_time):
+        t = np.ascontiguousarray(imu_time, np.float64)
+        r = [np.ascontiguousarray(np.asarray(imu_rot, np.float64)[:, k]) for k in range(3)]
+        keep = [t, *r]
+        dp.imu_time, dp.imu_rot_x, dp.imu_rot_y, dp.imu_rot_z = (a.ctypes.data for a in keep)
+        dp.imu_pointer_cur = len(t) - 1
+    else:
+        dp.imu_pointer_cur = -1
+        imu_available = False
+    dp.deskew_flag, dp.imu_available = int(deskew_flag), int(bool(imu_available))
+    dp.lidar_min_range, dp.lidar_max_range = float(min_range), float(max_range)
+    dp.n_scan, dp.downsample_rate, dp.point_filter_num = int(n_scan), int(downsample_rate), int(point_filter_num)
+    out = np.empty((max(len(p), 1), 4), np.float32)
+    m = lib.orc_deskew(_p(p), _p(rt), len(p), C.byref(dp), _p(out))
+    return out[:m].copy()
+
+
+def orientation_times(pts) -> np.ndarray:
+    """relative time of every point of a cloud without ring / time channels (src/imageProjection.cpp:279-326)"""
+    p = _c(pts)
+    out = np.zeros(len(p), np.float32)
+    lib.orc_orientation_times(_p(p), len(p), _p(out))
+    return out
 
 
 def localmap_build(kf_clouds, poses6, leaf, threads=1):

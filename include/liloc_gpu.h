@@ -139,6 +139,7 @@ typedef struct {
 int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* ring_time, int n,
                  const liloc_deskew_params* params, int* n_out);
 int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out);   /* fullCloud, for publishClouds (:675-679) */
+int liloc_last_deskew_marks(liloc_ctx* ctx, unsigned long long* out3);            /* ns: block 0 at start / after the barrier / end */
 int liloc_last_deskew_ms(liloc_ctx* ctx, float* ms);                             /* device time of the last de-skew launch (liloc_set_timing) */
 
 /* ---- registration: scan2MapOptimization :1183-1201 (everything except transformUpdate :1202) -----
@@ -187,12 +188,13 @@ int liloc_scan_ds_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, 
  * built once per id and cached (the reference rebuilds it on every setInputTarget). */
 #define LILOC_NDT_DIRECT1 0
 #define LILOC_NDT_DIRECT7 1
+#define LILOC_NDT_KDTREE 2     /* pclomp::KDTREE: every leaf whose centroid is closer than `resolution` to the transformed point */
 typedef struct {
     double step_size;       /* [0.1]  pclomp default */
     double outlier_ratio;   /* [0.55] pclomp default */
     double trans_eps;       /* ndtEpsilon (:178) */
     int max_iterations;     /* [35]   pclomp default */
-    int search;             /* LILOC_NDT_DIRECT1 | LILOC_NDT_DIRECT7  (regMethod, :181-190) */
+    int search;             /* LILOC_NDT_DIRECT1 | LILOC_NDT_DIRECT7 | LILOC_NDT_KDTREE  (regMethod, :181-199) */
     int n_align;            /* [1]; 2 for the relocalisation init */
     int reserved;
 } liloc_ndt_opts;

@@ -83,6 +83,12 @@ def stats_of(ctx_handle) -> dict:
     return st.as_dict()
 
 
+def last_deskew_ms_of(ctx_handle) -> float:
+    ms = C.c_float()
+    lib.liloc_last_deskew_ms(C.c_void_p(ctx_handle), C.byref(ms))
+    return ms.value
+
+
 class DeskewParams(C.Structure):
     """liloc_deskew_params: what imuDeskewInfo / cachePointCloud leave for projectPointCloud (src/imageProjection.cpp)."""
     _fields_ = [("time_scan_cur", C.c_double),
@@ -144,6 +150,7 @@ def _load() -> C.CDLL:
         "liloc_deskew": (C.c_int, [P, P, P, C.c_int, C.POINTER(DeskewParams), ip]),
         "liloc_deskewed_get": (C.c_int, [P, P, C.c_int, ip]),
         "liloc_last_deskew_ms": (C.c_int, [P, fp]),
+        "liloc_last_deskew_marks": (C.c_int, [P, P]),
         "liloc_keyframe_clear": (C.c_int, [P]),
         "liloc_localmap_build": (C.c_int, [P, P, P, C.c_int, C.c_float, ip, ip]),
         "liloc_localmap_set": (C.c_int, [P, P, C.c_int, C.c_float, ip]),
@@ -212,7 +219,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -238,9 +245,17 @@ class Context:
         self._h = h
         self.device = device
 
+    @classmethod
+    def borrow(cls, handle: int, device: int = 0) -> "Context":
+        """A view on a liloc_ctx owned by someone else (the host class): close() does not destroy it."""
+        self = cls.__new__(cls)
+        self._h, self.device, self._borrowed = C.c_void_p(handle), device, True
+        return self
+
     def close(self) -> None:
         if getattr(self, "_h", None):
-            lib.liloc_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib.liloc_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -358,6 +373,11 @@ class Context:
         ms = C.c_float()
         self._chk(lib.liloc_last_deskew_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_deskew_marks(self) -> np.ndarray:
+        out = np.zeros(3, np.uint64)
+        self._chk(lib.liloc_last_deskew_marks(self._h, _ptr(out)))
+        return out
 
     def scan_put_deskewed(self, leaf: float) -> int:
         Q = C.c_int()

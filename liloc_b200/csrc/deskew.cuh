@@ -38,9 +38,16 @@ struct DeskewArgs {
     int* tile_count;             // ceil(n / 256)
     float4* out;
     int* n_out;
+    unsigned long long* marks;   // optional: %globaltimer (ns) of block 0 at start / after the barrier / at its end
 };
 
 struct Aff3 { float l[3][3]; float t[3]; };
+
+LILOC_DEV unsigned long long deskew_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 LILOC_DEV float sum3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
 
@@ -81,12 +88,24 @@ LILOC_DEV Aff3 aff_mul(const Aff3& a, const Aff3& b) {                   // Eige
     return r;
 }
 
-// findRotation (:573-597).  s_time: imuTime staged in shared memory; rot: the three angle arrays in global memory.
-LILOC_DEV void find_rotation(const double* s_time, const double* __restrict__ imu, int last, double pointTime, float* rx, float* ry, float* rz) {
+// findRotation (:573-597).  s_time: imuTime staged in shared memory; the three angle arrays are read from global memory.
+// The reference walks the samples from the front until the first one later than the point; when the stamps are
+// non-decreasing (`sorted`: the normal case) that index is found by bisection instead, with the same result.
+LILOC_DEV void find_rotation(const double* s_time, const double* __restrict__ imu, int last, bool sorted, double pointTime,
+                             float* rx, float* ry, float* rz) {
     int front = 0;
-    while (front < last) {
-        if (pointTime < s_time[front]) break;
-        ++front;
+    if (sorted) {
+        int lo = 0, hi = last;                      // first index in [0, last) with pointTime < time, else last
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (pointTime < s_time[mid]) hi = mid; else lo = mid + 1;
+        }
+        front = lo;
+    } else {
+        while (front < last) {
+            if (pointTime < s_time[front]) break;
+            ++front;
+        }
     }
     const double* RX = imu + kImuMax; const double* RY = imu + 2 * kImuMax; const double* RZ = imu + 3 * kImuMax;
     if (pointTime > s_time[front] || front == 0) {
@@ -123,7 +142,15 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
     const int tpb = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;         // contiguous tiles per block
     const int t0 = min(n_tiles, (int)blockIdx.x * tpb), t1 = min(n_tiles, t0 + tpb);
 
-    if (a.deskew) for (int k = threadIdx.x; k <= a.imu_last; k += kDeskewThreads) s_time[k] = __ldg(a.imu + k);
+    if (a.marks && blockIdx.x == 0 && threadIdx.x == 0) a.marks[0] = deskew_ns();
+    bool sorted = true;
+    if (a.deskew) {
+        for (int k = threadIdx.x; k <= a.imu_last; k += kDeskewThreads) {
+            const double tk = __ldg(a.imu + k);
+            s_time[k] = tk;
+            if (k < a.imu_last && !(tk <= __ldg(a.imu + k + 1))) sorted = false;
+        }
+    }
 
     // ---- A: tile counts ----
     for (int t = t0; t < t1; ++t) {
@@ -133,7 +160,9 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
         const int c = __syncthreads_count(keep);
         if (threadIdx.x == 0) a.tile_count[t] = c;
     }
+    sorted = __syncthreads_and(sorted) != 0;
     grid.sync();
+    if (a.marks && blockIdx.x == 0 && threadIdx.x == 0) a.marks[1] = deskew_ns();
 
     // ---- B: offsets, the sweep's first surviving point, transform + store ----
     int before = 0, total = 0, first_tile = INT_MAX;
@@ -156,7 +185,10 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
     for (int w = 0; w < 8; ++w) { before += s_red[0][w]; total += s_red[1][w]; first_tile = min(first_tile, s_w[w]); }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.n_out = total;
-    if (t0 >= t1 || total == 0) return;
+    if (t0 >= t1 || total == 0) {
+        if (a.marks && blockIdx.x == 0 && threadIdx.x == 0) a.marks[2] = deskew_ns();
+        return;
+    }
 
     if (a.deskew) {
         // first survivor of the first non-empty tile: warp 0 scans that tile with ballots
@@ -171,7 +203,7 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
             }
             if (lane == 0) {
                 float rx, ry, rz;
-                find_rotation(s_time, a.imu, a.imu_last, a.t_cur + (double)__int_as_float(__ldg(a.rt + first).y), &rx, &ry, &rz);
+                find_rotation(s_time, a.imu, a.imu_last, sorted, a.t_cur + (double)__int_as_float(__ldg(a.rt + first).y), &rx, &ry, &rz);
                 s_start_inv = aff_inverse(aff_from_rpy(rx, ry, rz));
             }
         }
@@ -195,7 +227,7 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
             float4 o = p;
             if (a.deskew) {
                 float rx, ry, rz;
-                find_rotation(s_time, a.imu, a.imu_last, a.t_cur + (double)__int_as_float(rt.y), &rx, &ry, &rz);
+                find_rotation(s_time, a.imu, a.imu_last, sorted, a.t_cur + (double)__int_as_float(rt.y), &rx, &ry, &rz);
                 const Aff3 bt = aff_mul(s_start_inv, aff_from_rpy(rx, ry, rz));
                 o.x = bt.l[0][0] * p.x + bt.l[0][1] * p.y + bt.l[0][2] * p.z + bt.t[0];
                 o.y = bt.l[1][0] * p.x + bt.l[1][1] * p.y + bt.l[1][2] * p.z + bt.t[1];
@@ -206,6 +238,7 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
         base += tile_total;
         __syncthreads();
     }
+    if (a.marks && blockIdx.x == 0 && threadIdx.x == 0) a.marks[2] = deskew_ns();
 }
 
 }  // namespace liloc

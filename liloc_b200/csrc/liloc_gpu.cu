@@ -166,6 +166,8 @@ struct liloc_ctx {
     int dk_slot = 0;
     cudaEvent_t ev_dk_slot[2]{};
     int* d_dk_n = nullptr;               // points of the de-skewed cloud
+    unsigned long long* d_dk_marks = nullptr;   // 3 phase timestamps of the last launch (timing)
+    int dk_blocks_per_sm = 1;
     int dk_n_upper = -1;                 // raw points of the last sweep (-1: no de-skewed cloud)
     int dk_n = -1;                       // host copy of *d_dk_n, -1 while unknown
     cudaEvent_t ev_deskew = nullptr;
@@ -564,6 +566,9 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ndt_align, kNdtThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_ndt_align cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->ndt_max_blocks = per_sm * c->num_sms;
+    CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deskew, kDeskewThreads, 0));
+    if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_deskew cannot be resident"); return bail(LILOC_ERR_CUDA); }
+    c->dk_blocks_per_sm = per_sm >= 2 ? 2 : 1;
     CUB_(cudaMalloc(&c->d_ndt_counters, 3 * sizeof(int)));
     CUB_(cudaMalloc(&c->d_ndt_ns, 3 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_sm_scratch, 2 * kSmScratch * sizeof(int)));
@@ -572,6 +577,8 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaMallocHost(&c->h_dk_imu, 2 * 4 * kImuMax * sizeof(double)));
     for (auto& e : c->ev_dk_slot) CUB_(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB_(cudaMalloc(&c->d_dk_n, sizeof(int)));
+    CUB_(cudaMalloc(&c->d_dk_marks, 3 * sizeof(unsigned long long)));
+    CUB_(cudaMemset(c->d_dk_marks, 0, 3 * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_dk_n, 0, sizeof(int)));
     CUB_(cudaEventCreateWithFlags(&c->ev_deskew, cudaEventDisableTiming));
     for (auto& e : c->ev_dk) CUB_(cudaEventCreate(&e));
@@ -616,7 +623,7 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
     fr(c->d_marks); fr(c->d_sm_scratch);
-    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu); fr(c->d_dk_n);
+    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu); fr(c->d_dk_n); fr(c->d_dk_marks);
     if (c->h_dk_imu) cudaFreeHost(c->h_dk_imu);
     if (c->ev_deskew) cudaEventDestroy(c->ev_deskew);
     for (auto& e : c->ev_dk) if (e) cudaEventDestroy(e);
@@ -863,7 +870,9 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     a.n_scan = p->n_scan; a.ds_rate = p->downsample_rate; a.pf_num = p->point_filter_num;
     a.tile_count = ctx->dk_tiles.p; a.out = fc.scan_raw.p; a.n_out = ctx->d_dk_n;
     const int n_tiles = (n + kDeskewThreads - 1) / kDeskewThreads;
-    const int blocks = n_tiles < 1 ? 1 : (n_tiles < ctx->num_sms ? n_tiles : ctx->num_sms);
+    const int max_blocks = ctx->num_sms * ctx->dk_blocks_per_sm;
+    const int blocks = n_tiles < 1 ? 1 : (n_tiles < max_blocks ? n_tiles : max_blocks);
+    a.marks = ctx->timing ? ctx->d_dk_marks : nullptr;
     void* args[] = {&a};
     if (ctx->timing) cudaEventRecord(ctx->ev_dk[0], st);
     CU(cudaLaunchCooperativeKernel((void*)k_deskew, dim3((unsigned)blocks), dim3(kDeskewThreads), args, 0, st));
@@ -903,6 +912,15 @@ int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out) {
         CU(cudaStreamSynchronize(ctx->stream2));
         ctx->stats.d2h_bytes += (long long)ctx->dk_n * 16;
     }
+    return LILOC_OK;
+}
+
+// phase timestamps (ns, %globaltimer) of block 0 in the last de-skew launch: start, after the barrier, end
+int liloc_last_deskew_marks(liloc_ctx* ctx, unsigned long long* out3) {
+    ENTER(ctx);
+    if (!out3) return fail(ctx, LILOC_ERR_ARG, "last_deskew_marks: null");
+    CU(cudaStreamSynchronize(ctx->stream2));
+    CU(cudaMemcpy(out3, ctx->d_dk_marks, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return LILOC_OK;
 }
 
@@ -1306,7 +1324,9 @@ NdtOptsDev ndt_opts_dev(const liloc_ndt_opts* o, float resolution) {
     d.d1 = -log(c1 + c2) - d3;
     d.d2 = -2.0 * log((-log(c1 * exp(-0.5) + c2) - d3) / d.d1);
     d.step_max = o->step_size; d.step_min = o->trans_eps / 2.0; d.eps = o->trans_eps;
-    d.max_iterations = o->max_iterations; d.search7 = o->search == LILOC_NDT_DIRECT7 ? 1 : 0;
+    d.max_iterations = o->max_iterations;
+    d.search = o->search == LILOC_NDT_DIRECT7 ? 1 : (o->search == LILOC_NDT_KDTREE ? 2 : 0);
+    d.radius2 = resolution * resolution;
     d.n_align = o->n_align > 0 ? o->n_align : 1;
     return d;
 }
@@ -1505,7 +1525,7 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
         liloc_ndt_stats& ns = ctx->ndt_stats;
         ns.batches += 1; ns.jobs += n_jobs; ns.sweep_launches += 1; ns.sweep_phases += h_counters[2];
         ns.sweep_ms += (double)h_ns[0] * 1e-6; ns.update_ms += (double)h_ns[1] * 1e-6; ns.compact_ms += (double)h_ns[2] * 1e-6;
-        const int cells = od.search7 ? 7 : 1;
+        const int cells = od.search == 2 ? 27 : (od.search == 1 ? 7 : 1);
         for (int j = 0; j < n_jobs; ++j) {
             const double P = (double)ctx->ndt_sources[jobs[j].source_id].view.n;
             ns.job_sweeps += hj[j].total_sweeps;

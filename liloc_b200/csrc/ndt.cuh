@@ -41,7 +41,8 @@ struct NdtSourceView { const float4* pts; int n; };
 struct NdtOptsDev {
     double d1, d2;             // gauss_d1_, gauss_d2_
     double step_max, step_min, eps;
-    int max_iterations, search7, n_align;
+    int max_iterations, search, n_align;      // search: 0 DIRECT1, 1 DIRECT7, 2 KDTREE
+    float radius2;                            // KDTREE: resolution^2 (float, like pcl's radius * radius)
 };
 
 enum { NDT_AWAIT_FIRST = 0, NDT_LS_FIRST = 1, NDT_LS_LOOP = 2, NDT_DONE = 3 };
@@ -361,7 +362,7 @@ LILOC_DEV void ndt_sweep_tile(const NdtPoseCache* __restrict__ pc, const NdtTarg
 #pragma unroll
     for (int k = 0; k < kNdtSums; ++k) acc[k] = 0.0;
     const int base = tile * kNdtTile;
-    const int ncell = o.search7 ? 7 : 1;
+    const int ncell = o.search == 2 ? 27 : (o.search == 1 ? 7 : 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* T = sh.pc.T;
     // Only about half of the points fall into a voxel that holds a Gaussian; evaluated in place, half of every warp
@@ -411,20 +412,31 @@ LILOC_DEV void ndt_sweep_tile(const NdtPoseCache* __restrict__ pc, const NdtTarg
                 xt1 = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
                 xt2 = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
             }
-            for (int c = 0; c < 7; ++c) {
-                // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
-                const int dx = (c == 1) - (c == 2), dy = (c == 3) - (c == 4), dz = (c == 5) - (c == 6);
-                const int li = valid ? ndt_lookup(tg, xt0, xt1, xt2, dx, dy, dz) : -1;
+            for (int c = 0; c < ncell; ++c) {
+                int dx, dy, dz;
+                if (ncell == 7) {       // DIRECT7 displacement order: centre, +x, -x, +y, -y, +z, -z
+                    dx = (c == 1) - (c == 2); dy = (c == 3) - (c == 4); dz = (c == 5) - (c == 6);
+                } else {                // KDTREE: radiusSearch(x_trans, resolution) over the leaf centroids.  A centroid closer
+                    dx = c % 3 - 1; dy = (c / 3) % 3 - 1; dz = c / 9 - 1;       // than one voxel edge lies in the 3x3x3 block around the point's voxel
+                }
+                int li = valid ? ndt_lookup(tg, xt0, xt1, xt2, dx, dy, dz) : -1;
+                if (ncell == 27 && li >= 0) {
+                    const NdtLeaf* L = &tg.leaves[li];
+                    const float ex = (float)__ldg(&L->mean[0]) - xt0, ey = (float)__ldg(&L->mean[1]) - xt1, ez = (float)__ldg(&L->mean[2]) - xt2;
+                    if (!(ex * ex + ey * ey + ez * ez < o.radius2)) li = -1;     // FLANN radius search: squared distance < radius^2
+                }
                 const unsigned m = __ballot_sync(0xffffffffu, li >= 0);
                 if (li >= 0) ring[(head + count + __popc(m & ((1u << lane) - 1u))) % kNdtWarpCap] = make_int2(i, li);
                 count += __popc(m);
+                if (c % 7 == 6 || c == ncell - 1) {     // drain: at most 31 left over + 7 x 32 new entries fit the ring
+                    __syncwarp();
+                    while (count >= 32) {
+                        evaluate(ring[(head + lane) % kNdtWarpCap]);
+                        head = (head + 32) % kNdtWarpCap; count -= 32;
+                    }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
-            while (count >= 32) {
-                evaluate(ring[(head + lane) % kNdtWarpCap]);
-                head = (head + 32) % kNdtWarpCap; count -= 32;
-            }
-            __syncwarp();
         }
     }
     if (lane < count) evaluate(ring[(head + lane) % kNdtWarpCap]);

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 
+#include "image_projection.hpp"
 #include "map_optimization.hpp"
 #include "session_io.hpp"
 
@@ -229,6 +230,66 @@ int liloc_host_debug_voxelgrid_small(const float* in4, int n, float leaf, float*
     const auto o = liloc_host::voxelGridSmall(v, leaf);
     std::memcpy(out4, o.data(), sizeof(float) * 4 * o.size());
     return (int)o.size();
+}
+
+// ---- ImageProjection (src/imageProjection.cpp): the node in front of mapOptimization, sharing its device context ----
+void* liloc_host_ip_create(const char* yaml_path, void* map_optimization) {
+    auto* m = static_cast<mapOptimization*>(map_optimization);
+    auto* ip = new (std::nothrow) liloc_host::ImageProjection(yaml_path ? yaml_path : "", m ? m->context() : nullptr);
+    if (!ip) { g_err = "out of memory"; return nullptr; }
+    if (!ip->ok()) { g_err = ip->error(); delete ip; return nullptr; }
+    return ip;
+}
+void liloc_host_ip_destroy(void* ip) { delete static_cast<liloc_host::ImageProjection*>(ip); }
+const char* liloc_host_ip_error(void* ip) { return ip ? static_cast<liloc_host::ImageProjection*>(ip)->error().c_str() : g_err.c_str(); }
+// msg11 = stamp, angular_velocity xyz, linear_acceleration xyz, orientation xyzw
+void liloc_host_ip_imu(void* ip, const double* msg11) {
+    liloc_host::ImuMsg m{};
+    m.stamp = msg11[0];
+    for (int i = 0; i < 3; ++i) { m.angular_velocity[i] = msg11[1 + i]; m.linear_acceleration[i] = msg11[4 + i]; }
+    for (int i = 0; i < 4; ++i) m.orientation[i] = msg11[7 + i];
+    static_cast<liloc_host::ImageProjection*>(ip)->imuHandler(m);
+}
+// msg9 = stamp, position xyz, orientation xyzw, pose.covariance[0]
+void liloc_host_ip_odom(void* ip, const double* msg9) {
+    liloc_host::OdomMsg m{};
+    m.stamp = msg9[0];
+    for (int i = 0; i < 3; ++i) m.position[i] = msg9[1 + i];
+    for (int i = 0; i < 4; ++i) m.orientation[i] = msg9[4 + i];
+    m.covariance0 = msg9[8];
+    static_cast<liloc_host::ImageProjection*>(ip)->odometryHandler(m);
+}
+static void from_info(const liloc_host::CloudInfo& c, liloc_host_cloud_info* m) {
+    m->stamp = c.stamp; m->imuAvailable = c.imuAvailable; m->odomAvailable = c.odomAvailable;
+    m->imuRollInit = c.imuRollInit; m->imuPitchInit = c.imuPitchInit; m->imuYawInit = c.imuYawInit;
+    m->initialGuessX = c.initialGuessX; m->initialGuessY = c.initialGuessY; m->initialGuessZ = c.initialGuessZ;
+    m->initialGuessRoll = c.initialGuessRoll; m->initialGuessPitch = c.initialGuessPitch; m->initialGuessYaw = c.initialGuessYaw;
+    m->cloud_deskewed = c.cloud_deskewed; m->cloud_size = c.cloud_size; m->cloud_on_device = c.cloud_on_device;
+}
+// cloudHandler: 1 = a cloud_info was produced (the reference publishes it), 0 = nothing yet (queue filling / waiting for IMU), <0 error
+int liloc_host_ip_cloud(void* ip, double stamp, const liloc_point* pts, const liloc_ring_time* ring_time, int n, int has_time, liloc_host_cloud_info* out) {
+    auto* p = static_cast<liloc_host::ImageProjection*>(ip);
+    liloc_host::CloudInfo ci;
+    const bool produced = p->cloudHandler(stamp, pts, ring_time, n, has_time != 0, &ci);
+    if (!p->ok()) return LILOC_ERR_STATE;
+    if (produced && out) from_info(ci, out);
+    return produced ? 1 : 0;
+}
+struct liloc_host_livox_point { float x, y, z; unsigned char reflectivity, tag, line; unsigned offset_time; };
+int liloc_host_ip_cloud_livox(void* ip, double stamp, const liloc_host_livox_point* pts, int n, liloc_host_cloud_info* out) {
+    static_assert(sizeof(liloc_host_livox_point) == sizeof(liloc_host::LivoxPoint), "layout");
+    auto* p = static_cast<liloc_host::ImageProjection*>(ip);
+    liloc_host::CloudInfo ci;
+    const bool produced = p->cloudHandlerLivox(stamp, reinterpret_cast<const liloc_host::LivoxPoint*>(pts), n, &ci);
+    if (!p->ok()) return LILOC_ERR_STATE;
+    if (produced && out) from_info(ci, out);
+    return produced ? 1 : 0;
+}
+void liloc_host_ip_times(void* ip, double* timeScanCur, double* timeScanEnd, int* deskewFlag) {
+    auto* p = static_cast<liloc_host::ImageProjection*>(ip);
+    if (timeScanCur) *timeScanCur = p->timeScanCur;
+    if (timeScanEnd) *timeScanEnd = p->timeScanEnd;
+    if (deskewFlag) *deskewFlag = p->deskewFlag;
 }
 
 }  // extern "C"

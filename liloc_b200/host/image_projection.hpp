@@ -8,6 +8,7 @@
 #pragma once
 #include <deque>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/liloc_gpu.h"
@@ -69,6 +70,7 @@ public:
 private:
     struct Sweep { double stamp; std::vector<liloc_point> pts; std::vector<liloc_ring_time> rt; bool has_time; };
     std::deque<Sweep> cloudQueue;
+    std::deque<std::pair<double, std::vector<LivoxPoint>>> cloudQueueLivox;
     Sweep current_;
     liloc_ctx* ctx_;
     std::string error_;
@@ -80,6 +82,7 @@ private:
 
     void resetParameters();                                                   // :143-158
     bool cachePointCloud(Sweep&& msg);                                        // :270-423
+    bool cachePointCloudLivox(double stamp, const LivoxPoint* pts, int n);    // :208-268
     bool deskewInfo();                                                        // :425-439
     void imuDeskewInfo();                                                     // :441-496
     void odomDeskewInfo();                                                    // :498-571

@@ -432,7 +432,7 @@ int mapOptimization::ndtAlign(int submap, const float guess6[6], int n_align, fl
     if (rc < 0) return rc;
     liloc_ndt_opts o{};
     o.step_size = 0.1; o.outlier_ratio = 0.55; o.trans_eps = ndtEpsilon; o.max_iterations = 35;          // pclomp defaults + :178
-    o.search = regMethod == "DIRECT7" ? LILOC_NDT_DIRECT7 : LILOC_NDT_DIRECT1;                           // :181-190
+    o.search = regMethod == "DIRECT7" ? LILOC_NDT_DIRECT7 : (regMethod == "KDTREE" ? LILOC_NDT_KDTREE : LILOC_NDT_DIRECT1);   // :181-199
     o.n_align = n_align;
     liloc_ndt_job job{};
     job.target_id = submap; job.source_id = 0;

@@ -88,6 +88,18 @@ def _load():
     L.liloc_host_debug_transform_update.argtypes = [P, C.POINTER(CloudInfo)]
     L.liloc_host_debug_voxelgrid_small.restype = C.c_int
     L.liloc_host_debug_voxelgrid_small.argtypes = [P, C.c_int, C.c_float, P]
+    L.liloc_host_ip_create.restype = P
+    L.liloc_host_ip_create.argtypes = [C.c_char_p, P]
+    L.liloc_host_ip_destroy.argtypes = [P]
+    L.liloc_host_ip_error.restype = C.c_char_p
+    L.liloc_host_ip_error.argtypes = [P]
+    L.liloc_host_ip_imu.argtypes = [P, P]
+    L.liloc_host_ip_odom.argtypes = [P, P]
+    L.liloc_host_ip_cloud.restype = C.c_int
+    L.liloc_host_ip_cloud.argtypes = [P, C.c_double, P, P, C.c_int, C.c_int, C.POINTER(CloudInfo)]
+    L.liloc_host_ip_cloud_livox.restype = C.c_int
+    L.liloc_host_ip_cloud_livox.argtypes = [P, C.c_double, P, C.c_int, C.POINTER(CloudInfo)]
+    L.liloc_host_ip_times.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     return L
 
 
@@ -289,6 +301,70 @@ class MapOptimization:
 
     def ctx_handle(self) -> int:
         return lib().liloc_host_ctx(self._h)
+
+
+LIVOX_POINT = np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), ("reflectivity", np.uint8), ("tag", np.uint8),
+                        ("line", np.uint8), ("_pad", np.uint8), ("offset_time", np.uint32)])
+RING_TIME = np.dtype([("ring", np.int32), ("time", np.float32)])
+
+
+class ImageProjection:
+    """Handle on one host `ImageProjection` (src/imageProjection.cpp:63) that shares the device context of a
+    MapOptimization: the CloudInfo it produces refers to the de-skewed sweep left on the device."""
+
+    def __init__(self, yaml: str, map_optimization: MapOptimization):
+        L = lib()
+        self._mo = map_optimization
+        self._h = L.liloc_host_ip_create(config_path(yaml).encode(), map_optimization._h)
+        if not self._h:
+            raise RuntimeError("ImageProjection: " + (L.liloc_host_ip_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().liloc_host_ip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def imu(self, stamp, gyro, acc=(0.0, 0.0, 9.8), quat=(0.0, 0.0, 0.0, 1.0)) -> None:
+        m = np.array([stamp, *gyro, *acc, *quat], np.float64)
+        lib().liloc_host_ip_imu(self._h, m.ctypes.data)
+
+    def odom(self, stamp, position, quat=(0.0, 0.0, 0.0, 1.0), covariance0=0.0) -> None:
+        m = np.array([stamp, *position, *quat, covariance0], np.float64)
+        lib().liloc_host_ip_odom(self._h, m.ctypes.data)
+
+    def _ret(self, rc, info):
+        if rc < 0:
+            raise RuntimeError("ImageProjection: " + (lib().liloc_host_ip_error(self._h) or b"").decode())
+        return info if rc == 1 else None
+
+    def cloud(self, stamp, pts, ring=None, time=None, has_time=True):
+        """cloudHandler: returns the CloudInfo the reference would publish, or None (queue filling / waiting for IMU)."""
+        p = np.ascontiguousarray(pts, np.float32)
+        rt = None
+        if ring is not None:
+            rt = np.empty(len(p), RING_TIME)
+            rt["ring"], rt["time"] = np.asarray(ring, np.int32), np.asarray(time, np.float32)
+        info = CloudInfo()
+        rc = lib().liloc_host_ip_cloud(self._h, float(stamp), p.ctypes.data, rt.ctypes.data if rt is not None else None, len(p),
+                                       1 if has_time else 0, C.byref(info))
+        return self._ret(rc, info)
+
+    def cloud_livox(self, stamp, points):
+        p = np.ascontiguousarray(points, LIVOX_POINT)
+        info = CloudInfo()
+        rc = lib().liloc_host_ip_cloud_livox(self._h, float(stamp), p.ctypes.data, len(p), C.byref(info))
+        return self._ret(rc, info)
+
+    def times(self):
+        a, b, f = C.c_double(), C.c_double(), C.c_int()
+        lib().liloc_host_ip_times(self._h, C.byref(a), C.byref(b), C.byref(f))
+        return a.value, b.value, f.value
 
 
 def make_infos(scans, odom_poses6, stamps, device_ptrs=None):

@@ -173,15 +173,15 @@ def raw_sweep(scan_body: np.ndarray, sensor: Sensor, gyro=(0.05, -0.03, 0.4), im
     R0 = rot_zyx(*ang0)
     raw = np.empty((len(p), 4), np.float32)
     ang = ang0[None, :] + w[None, :] * t[:, None]
-    for i in range(len(p)):
-        raw[i, :3] = rot_zyx(*ang[i]).T @ (R0 @ p[i, :3])
+    Rt = np.moveaxis(rot_zyx(ang[:, 0], ang[:, 1], ang[:, 2]), -1, 0)        # (n, 3, 3)
+    raw[:, :3] = np.einsum("nji,nj->ni", Rt, p[:, :3] @ R0.T)               # R(t)^T (R0 p)
     raw[:, 3] = p[:, 3]
     bad = rng.random(len(p)) < outliers
     ring = np.where(bad & (rng.random(len(p)) < 0.5), sensor.n_rings + 3, ring).astype(np.int32)
     near = bad & (ring < sensor.n_rings)
     raw[near, :3] *= (0.3 / np.maximum(np.linalg.norm(raw[near, :3], axis=1), 1e-6))[:, None].astype(np.float32)
     return {"pts": raw, "ring": ring, "time": t.astype(np.float32), "imu_stamps": stamps, "imu_gyro": gyro_s,
-            "time_scan_cur": time_scan_cur, "time_scan_end": time_scan_cur + float(t[-1]) if len(t) else time_scan_cur,
+            "time_scan_cur": time_scan_cur, "time_scan_end": time_scan_cur + float(np.float32(t[-1])) if len(t) else time_scan_cur,
             "truth": p.astype(np.float32)}
 
 

@@ -89,6 +89,7 @@ struct NdtLeaf { double mean[3]; float icov[9]; int n; int key; };
 
 struct NdtTarget {
     float inv_leaf;
+    float resolution = 0.f;
     int minb[3], maxb[3], divb[3];
     std::vector<int> table;          // dense cell -> leaf index, -1 = no usable leaf
     std::vector<NdtLeaf> leaves;
@@ -98,6 +99,7 @@ struct NdtTarget {
         ok = false; leaves.clear(); table.clear();
         if (n <= 0) return;
         inv_leaf = 1.0f / resolution;
+        this->resolution = resolution;
         float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         for (int i = 0; i < n; ++i) {
             const float v[3] = {pts[i].x, pts[i].y, pts[i].z};
@@ -285,7 +287,7 @@ inline bool point_cell_terms(const float x[3], const float xt[3], const NdtLeaf&
 
 struct Sums { double v[28]; };
 
-Sums derivative_sweep(const NdtTarget& tg, const orc_point* src, int n, const double* p, const NdtConsts& K, int search7, int threads) {
+Sums derivative_sweep(const NdtTarget& tg, const orc_point* src, int n, const double* p, const NdtConsts& K, int search, int threads) {
     float T[12]; pose_to_matrix(p, T);
     AngDeriv A; angle_derivatives(p, &A);
     const double d1 = K.d1; const float d2 = (float)K.d2;
@@ -297,10 +299,21 @@ Sums derivative_sweep(const NdtTarget& tg, const orc_point* src, int n, const do
         const float x[3] = {src[i].x, src[i].y, src[i].z};
         const float xt[3] = {T[0] * x[0] + T[1] * x[1] + T[2] * x[2] + T[3], T[4] * x[0] + T[5] * x[1] + T[6] * x[2] + T[7],
                              T[8] * x[0] + T[9] * x[1] + T[10] * x[2] + T[11]};
-        const int ncell = search7 ? 7 : 1;
+        // search: 0 DIRECT1 (the point's voxel), 1 DIRECT7 (+ the six face neighbours), 2 KDTREE (radiusSearch over the leaf
+        // centroids with radius = resolution: squared float distance < radius^2, FLANN RadiusResultSet; such a centroid can
+        // only belong to one of the 27 voxels around the point's voxel).  ndt_omp sums the neighbours in FLANN's distance
+        // order; here in voxel order -- the sums are double, the difference is in their last bits.
+        const int ncell = search == 2 ? 27 : (search == 1 ? 7 : 1);
+        const float radius2 = tg.resolution * tg.resolution;
         for (int c = 0; c < ncell; ++c) {
-            const int li = tg.lookup(xt[0], xt[1], xt[2], kDisp7[c][0], kDisp7[c][1], kDisp7[c][2]);
+            const int dx = ncell == 27 ? c % 3 - 1 : kDisp7[c][0], dy = ncell == 27 ? (c / 3) % 3 - 1 : kDisp7[c][1], dz = ncell == 27 ? c / 9 - 1 : kDisp7[c][2];
+            const int li = tg.lookup(xt[0], xt[1], xt[2], dx, dy, dz);
             if (li < 0) continue;
+            if (ncell == 27) {
+                const auto& L = tg.leaves[(size_t)li];
+                const float ex = (float)L.mean[0] - xt[0], ey = (float)L.mean[1] - xt[1], ez = (float)L.mean[2] - xt[2];
+                if (!(ex * ex + ey * ey + ez * ez < radius2)) continue;
+            }
             float t[28];
             point_cell_terms(x, xt, tg.leaves[(size_t)li], A, d1, d2, t);
             for (int k = 0; k < 28; ++k) s.v[k] += (double)t[k];
@@ -374,7 +387,7 @@ typedef struct {
     double trans_eps;        // (double) ndtEpsilon, a float parameter in the reference (include/utility.h:285)
     float resolution;        // ndtResolution
     int max_iterations;      // 35
-    int search;              // 0 DIRECT1, 1 DIRECT7
+    int search;              // 0 DIRECT1, 1 DIRECT7, 2 KDTREE
     int threads;
 } orc_ndt_opts;
 

@@ -131,3 +131,111 @@ def test_ndt_source_from_the_deskewed_sweep(gpu_ctx, orc, synth, scene_small):
     out_d = gpu_ctx.ndt_align_batch([0], [1], T[None], NdtOpts())
     assert np.array_equal(out_h[0], out_d[0]) and out_h[2][0] == out_d[2][0] and out_h[4][0] == out_d[4][0]
     gpu_ctx.ndt_clear()
+
+
+def _quat_from_rpy(r, p, y):        # tf::Quaternion::setRPY
+    cr, sr, cp, sp, cy, sy = np.cos(r / 2), np.sin(r / 2), np.cos(p / 2), np.sin(p / 2), np.cos(y / 2), np.sin(y / 2)
+    return (sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy)
+
+
+def test_image_projection_node_in_front_of_map_optimization(orc, synth):
+    """The two host classes in one process: ImageProjection (IMU / odometry queues, gyro integration on the host,
+    de-skew on the device) hands mapOptimization a CloudInfo whose cloud never left the device; the frames must equal,
+    bit for bit, the frames of a second mapOptimization fed the oracle's de-skewed cloud from host memory."""
+    from liloc_b200 import host_api
+    from liloc_b200.abi import Context
+    yaml = "lio_sam_default.yaml"
+    F = 9
+    seq = synth.make_sequence(synth.VLP16, F, seed=6, world_size=(60.0, 40.0), n_pillars=10, loop_radius=(20.0, 11.0), dt=0.21)
+    with host_api.MapOptimization(yaml, "lio", device=0) as m_raw, host_api.MapOptimization(yaml, "lio", device=0) as m_ref:
+        ip = host_api.ImageProjection(yaml, m_raw)
+        ctx = Context.borrow(m_raw.ctx_handle())
+        R = np.array([0.9994142, 0.03275957, 0.00990251, -0.03266505, 0.99942062, -0.00956125, -0.01021, 0.00923218, 0.99990526]).reshape(3, 3)
+        sweeps, produced = [], 0
+        for f in range(F):
+            sw = synth.raw_sweep(seq.scans[f], seq.sensor, gyro=(0.05, -0.02, 0.3 + 0.05 * f), time_scan_cur=float(seq.stamps[f]), seed=100 + f)
+            sweeps.append(sw)
+            for st, g in zip(sw["imu_stamps"], sw["imu_gyro"]):
+                ip.imu(st, g)
+            r, p, y, x, yy, z = [float(v) for v in seq.odom[f]]
+            ip.odom(seq.stamps[f] - 0.005, (x, yy, z), _quat_from_rpy(r, p, y))
+            ip.odom(seq.stamps[f], (x, yy, z), _quat_from_rpy(r, p, y))
+            info = ip.cloud(seq.stamps[f], sw["pts"], sw["ring"], sw["time"], has_time=True)
+            if f < 2:
+                assert info is None                      # cachePointCloud holds two sweeps back (:271-273)
+                continue
+            k = f - 2                                    # the sweep that was processed
+            s = sweeps[k]
+            assert info is not None and info.cloud_on_device == 2 and info.stamp == seq.stamps[k]
+            assert info.imuAvailable == 1 and info.odomAvailable == 1
+            assert abs(info.initialGuessX - seq.odom[k][3]) < 1e-6 and abs(info.initialGuessYaw - seq.odom[k][2]) < 1e-6
+            t_cur, t_end, flag = ip.times()
+            assert (t_cur, flag) == (seq.stamps[k], 1) and t_end == s["time_scan_end"]
+            # the oracle's view of the same sweep: extrinsic rotation of the gyro (imuConverter), integration, de-skew
+            g_rot = np.array([[R[i, 0] * g[0] + R[i, 1] * g[1] + R[i, 2] * g[2] for i in range(3)] for g in s["imu_gyro"]])
+            it, ir = orc.imu_integrate(s["imu_stamps"], g_rot, s["time_scan_end"])
+            ref = orc.deskew(s["pts"], s["ring"], s["time"], it, ir, s["time_scan_cur"], n_scan=16, point_filter_num=1, min_range=2.0, max_range=100.0)
+            got = ctx.deskewed_get()
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+            rep_raw = m_raw.handle(info)
+            info_h = host_api.CloudInfo.from_buffer_copy(info)
+            info_h.cloud_deskewed, info_h.cloud_size, info_h.cloud_on_device = ref.ctypes.data, len(ref), 0
+            rep_ref = m_ref.handle(info_h)
+            assert rep_raw.processed == rep_ref.processed == 1 and rep_raw.status == rep_ref.status == 0
+            assert list(rep_raw.pose) == list(rep_ref.pose) and list(rep_raw.guess) == list(rep_ref.guess)
+            assert (rep_raw.q_all, rep_raw.map_points, rep_raw.iters, rep_raw.n_sel, rep_raw.keyframe_id) == \
+                   (rep_ref.q_all, rep_ref.map_points, rep_ref.iters, rep_ref.n_sel, rep_ref.keyframe_id)
+            produced += 1
+        assert produced == F - 2 and m_raw.num_keyframes() == m_ref.num_keyframes() >= 3
+        # a sweep whose IMU data has not arrived yet is not published ("Waiting for IMU data ...", :429-432)
+        sw = synth.raw_sweep(seq.scans[0], seq.sensor, time_scan_cur=float(seq.stamps[-1]) + 5.0, seed=7)
+        assert ip.cloud(float(seq.stamps[-1]) + 5.0, sw["pts"], sw["ring"], sw["time"]) is not None     # sweep F-2: its IMU data is there
+        assert ip.cloud(float(seq.stamps[-1]) + 5.2, sw["pts"], sw["ring"], sw["time"]) is not None     # sweep F-1
+        assert ip.cloud(float(seq.stamps[-1]) + 5.4, sw["pts"], sw["ring"], sw["time"]) is None         # the sweep at +5.0: no IMU data
+        ctx.close(); ip.close()
+
+
+def test_livox_custom_msg_path(orc, synth):
+    """cloudHandlerLivox (:194-268): tag / line / IsNear filters, time in ms, sort by time, then the common path."""
+    from liloc_b200 import host_api
+    from liloc_b200.abi import Context
+    yaml = "lio_sam_mid360.yaml"
+    world = synth.make_world(seed=8)
+    rng = np.random.default_rng(8)
+    with host_api.MapOptimization(yaml, "lio", device=0) as m:
+        ip = host_api.ImageProjection(yaml, m)
+        ctx = Context.borrow(m.ctx_handle())
+        msgs = []
+        for f in range(3):
+            sc = synth.scan(world, np.array([0, 0, 0.1 * f, -5.0 + f, 2.0, 1.8], np.float32), synth.MID360, seed=80 + f)
+            lp = np.zeros(len(sc), host_api.LIVOX_POINT)
+            lp["x"], lp["y"], lp["z"] = sc[:, 0], sc[:, 1], sc[:, 2]
+            lp["line"] = rng.integers(0, 10, len(sc))                      # N_SCAN 8: lines 8, 9 are dropped
+            lp["tag"] = rng.choice([0x00, 0x10, 0x20, 0x30, 0x01], len(sc))
+            lp["offset_time"] = rng.permutation(len(sc)).astype(np.uint32) * 4000    # ns, unsorted
+            lp["x"][5] = lp["x"][4]                                          # IsNear with the previous point
+            stamp = 50.0 + 0.1 * f
+            msgs.append((stamp, lp))
+            for k in range(40):
+                ip.imu(stamp - 0.008 + k * 0.005, (0.01, 0.02, 0.2))
+            info = ip.cloud_livox(stamp, lp)
+            assert (info is None) == (f < 2)
+        stamp, lp = msgs[0]
+        keep = np.ones(len(lp), bool); keep[0] = False
+        keep &= (lp["line"] < 8) & (((lp["tag"] & 0x30) == 0x10) | ((lp["tag"] & 0x30) == 0x00))
+        near = np.zeros(len(lp), bool)
+        for c in "xyz":
+            near[1:] |= np.abs(lp[c][1:] - lp[c][:-1]) < 1e-7
+        keep &= ~near
+        tms = (0.0 + lp["offset_time"].astype(np.float64) * 1e-6).astype(np.float32)[keep]
+        order = np.argsort(tms, kind="stable")
+        pts = np.stack([lp["x"][keep], lp["y"][keep], lp["z"][keep], np.zeros(keep.sum(), np.float32)], axis=1)[order]
+        ring, tms = lp["line"][keep][order].astype(np.int32), tms[order]
+        t_cur, t_end, flag = ip.times()
+        assert t_cur == stamp and flag == 1 and t_end == stamp + float(tms[-1]) / 1000.0
+        st = np.array([stamp - 0.008 + k * 0.005 for k in range(40)] + [msgs[1][0] - 0.008 + k * 0.005 for k in range(40)] + [msgs[2][0] - 0.008 + k * 0.005 for k in range(40)])
+        it, ir = orc.imu_integrate(st, np.tile((0.01, 0.02, 0.2), (len(st), 1)), t_end)
+        ref = orc.deskew(pts, ring, tms, it, ir, stamp, n_scan=8, point_filter_num=1, min_range=1.0, max_range=100.0)
+        got = ctx.deskewed_get()
+        assert len(ref) > 1000 and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        ctx.close(); ip.close()

@@ -28,7 +28,7 @@ def test_derivatives_match_oracle(gpu_ctx, orc, synth, ndt_scene):
     gpu_ctx.ndt_source_put(2, src)
     tg = orc.NdtTarget(sub, 1.0)
     rng = np.random.default_rng(1)
-    for search in (0, 1):
+    for search in (0, 1, 2):             # DIRECT1, DIRECT7, KDTREE
         for _ in range(4):
             p = orc.ndt_matrix_to_pose(guess_matrix(synth, truth + np.r_[rng.uniform(-0.03, 0.03, 3), rng.uniform(-0.5, 0.5, 3)]))
             got = gpu_ctx.ndt_derivatives(2, 2, p, NdtOpts(search=search))
@@ -42,7 +42,7 @@ def _pose_err(T, Tref):
     return dt, dR
 
 
-@pytest.mark.parametrize("search", [0, 1])
+@pytest.mark.parametrize("search", [0, 1, 2])
 def test_align_matches_oracle(gpu_ctx, orc, synth, ndt_scene, search):
     from liloc_b200 import NdtOpts
     sub, src, truth = ndt_scene

@@ -125,7 +125,7 @@ def test_pose_matrix_round_trip(orc):
         assert np.allclose(R, Rx @ Ry @ Rz, atol=1e-6)                            # p = [t, eulerAngles(0,1,2)]: R = Rx Ry Rz
 
 
-@pytest.mark.parametrize("search", [0, 1])
+@pytest.mark.parametrize("search", [0, 1, 2])
 def test_align_recovers_truth(orc, synth, ndt_scene, search):
     sub, src, truth = ndt_scene
     tg = orc.NdtTarget(sub, 1.0)
@@ -146,3 +146,32 @@ def test_align_without_overlap_terminates(orc, synth, ndt_scene):
     T, res = orc.ndt_align(tg, src, guess_matrix(synth, g), orc.NdtOpts(resolution=1.0, threads=4))
     assert res.sweeps == 1 and res.iterations == 0              # zero gradient -> delta_p_norm == 0 -> return (computeTransformation)
     assert np.allclose(T, guess_matrix(synth, g))
+
+
+def test_kdtree_neighbourhood_matches_scipy_radius_search(orc, synth, ndt_scene):
+    """regMethod KDTREE (src/mapOptmization.cpp:195-199): the neighbourhood of a transformed point is every leaf whose
+    centroid is closer than `resolution` -- pinned against scipy's ball query over the oracle's own leaf centroids."""
+    from scipy.spatial import cKDTree
+    sub, src, truth = ndt_scene
+    src = src[::2]
+    tg = orc.NdtTarget(sub, 1.0)
+    means, icovs, counts = tg.leaves()
+    p = orc.ndt_matrix_to_pose(guess_matrix(synth, truth + np.array([0.004, -0.003, 0.01, 0.05, -0.04, 0.02])))
+    got = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=2, threads=4))
+    T0 = orc.ndt_pose_to_matrix(p)
+    xt = (src[:, :3] @ T0[:, :3].T + T0[:, 3]).astype(np.float32)
+    tree = cKDTree(means.astype(np.float32).astype(np.float64))
+    nb = tree.query_ball_point(xt.astype(np.float64), r=1.0)
+    c1, c2 = 10 * (1 - 0.55), 0.55 / 1.0 ** 3
+    d3 = -np.log(c2); d1 = -np.log(c1 + c2) - d3; d2 = -2 * np.log((-np.log(c1 * np.exp(-0.5) + c2) - d3) / d1)
+    score, pairs = 0.0, 0
+    for i, ids in enumerate(nb):
+        for l in ids:
+            d = xt[i].astype(np.float64) - means[l]
+            score += -d1 * np.exp(-0.5 * d2 * d @ icovs[l].reshape(3, 3).astype(np.float64) @ d)
+            pairs += 1
+    assert pairs > 2 * len(src)                                     # several Gaussians per point, unlike DIRECT1
+    assert abs(got[0] - score) < 1e-4 * abs(score)
+    s1 = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=0, threads=4))[0]
+    s7 = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=1, threads=4))[0]
+    assert got[0] > s7 > s1 > 0                                     # more neighbours, more score (-d1 > 0)

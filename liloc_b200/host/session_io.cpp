@@ -33,6 +33,31 @@ float read_scalar(const unsigned char* p, const PcdField& f) {
     }
 }
 
+// liblzf's lzf_decompress (the codec behind PCL's binary_compressed): control byte < 32 = literal run of ctrl + 1
+// bytes; otherwise a back reference of length (ctrl >> 5) + 2 (+ one extension byte when the 3-bit field is 7) at
+// distance ((ctrl & 31) << 8 | next byte) + 1.  Returns false on a malformed stream or a size mismatch.
+bool lzf_decompress(const unsigned char* in, size_t in_len, unsigned char* out, size_t out_len) {
+    size_t ip = 0, op = 0;
+    while (ip < in_len) {
+        unsigned ctrl = in[ip++];
+        if (ctrl < 32) {
+            ++ctrl;
+            if (ip + ctrl > in_len || op + ctrl > out_len) return false;
+            std::memcpy(out + op, in + ip, ctrl);
+            ip += ctrl; op += ctrl;
+        } else {
+            size_t len = ctrl >> 5;
+            if (len == 7) { if (ip >= in_len) return false; len += in[ip++]; }
+            if (ip >= in_len) return false;
+            const size_t dist = ((size_t)(ctrl & 31u) << 8 | in[ip++]) + 1;
+            len += 2;
+            if (dist > op || op + len > out_len) return false;
+            for (size_t k = 0; k < len; ++k, ++op) out[op] = out[op - dist];     // may overlap: byte by byte
+        }
+    }
+    return op == out_len;
+}
+
 // gtsam::Rot3(Quaternion(w, x, y, z)).roll() / pitch() / yaw()  (R = Rz(yaw) Ry(pitch) Rx(roll))
 void quat_to_rpy(double qx, double qy, double qz, double qw, float& roll, float& pitch, float& yaw) {
     const double n = std::sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
@@ -116,8 +141,28 @@ bool loadPCD(const std::string& path, std::vector<liloc_point>& out, std::string
             }
             out[p] = liloc_point{v[0], v[1], v[2], v[3]};
         }
+    } else if (data == "binary_compressed") {
+        // pcl::PCDWriter::writeBinaryCompressed: uint32 compressed size, uint32 uncompressed size, LZF stream; the
+        // uncompressed block is field-major (all x, then all y, ...), each field SIZE * COUNT bytes per point.
+        unsigned sizes[2];
+        f.read(reinterpret_cast<char*>(sizes), 8);
+        if (f.gcount() != 8) { err = path + ": truncated binary_compressed header"; return false; }
+        const size_t csize = sizes[0], usize = sizes[1];
+        if (usize != (size_t)points * rec) { err = path + ": binary_compressed size does not match POINTS x record size"; return false; }
+        std::vector<unsigned char> cbuf(csize), buf(usize);
+        f.read(reinterpret_cast<char*>(cbuf.data()), (std::streamsize)csize);
+        if ((size_t)f.gcount() != csize) { err = path + ": truncated binary_compressed data"; return false; }
+        if (!lzf_decompress(cbuf.data(), csize, buf.data(), usize)) { err = path + ": corrupt LZF stream"; return false; }
+        std::vector<size_t> col(fields.size());
+        size_t acc = 0;
+        for (size_t k = 0; k < fields.size(); ++k) { col[k] = acc; acc += (size_t)fields[k].size * fields[k].count * (size_t)points; }
+        auto at = [&](int k, long long p) { return read_scalar(buf.data() + col[k] + (size_t)p * fields[k].size * fields[k].count, fields[k]); };
+        for (long long p = 0; p < points; ++p) {
+            out[p].x = at(ix, p); out[p].y = at(iy, p); out[p].z = at(iz, p);
+            out[p].intensity = ii >= 0 ? at(ii, p) : 0.f;
+        }
     } else {
-        err = path + ": DATA " + data + " is not supported (ascii and binary are; the reference writes binary)";
+        err = path + ": DATA " + data + " is not supported (ascii, binary and binary_compressed are; the reference writes binary)";
         return false;
     }
     return true;

@@ -5,7 +5,8 @@
 //     singlesession_posegraph.g2o     VERTEX_SE3:QUAT id x y z qx qy qz qw   /   EDGE_SE3:QUAT i j x y z qx qy qz qw
 //     PCDs/<k>.pcd                    key cloud k, body frame (pcl::io::savePCDFileBinary of pcl::PointXYZI)
 //     globalMap.pcd                   (visualisation only; not needed by the path)
-// The reference reads these with PCL and GTSAM; here: a PCD reader for the `ascii` and `binary` encodings with
+// The reference reads these with PCL and GTSAM; here: a PCD reader for the `ascii`, `binary` and `binary_compressed`
+// (LZF, field-major) encodings with
 // x / y / z / intensity float fields in any order (padding and extra fields are skipped), a g2o vertex parser, and
 // the matching writers.
 #pragma once

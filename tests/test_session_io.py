@@ -64,7 +64,7 @@ def test_pcd_ascii_and_errors(tmp_path):
     with pytest.raises(IOError, match="truncated"):
         host_api.load_pcd(str(bad))
     comp = tmp_path / "comp.pcd"
-    comp.write_bytes(_pcd_header(["x", "y", "z", "intensity"], [4] * 4, ["F"] * 4, [1] * 4, 1, "binary_compressed") + b"\0" * 16)
+    comp.write_bytes(_pcd_header(["x", "y", "z", "intensity"], [4] * 4, ["F"] * 4, [1] * 4, 1, "binary_zstd") + b"\0" * 16)
     with pytest.raises(IOError, match="not supported"):
         host_api.load_pcd(str(comp))
 
@@ -93,3 +93,65 @@ def test_g2o_vertices_round_trip(tmp_path):
     assert sum(l.startswith("VERTEX_SE3:QUAT") for l in lines) == 20 and sum(l.startswith("EDGE_SE3:QUAT") for l in lines) == 19
     back = host_api.load_g2o(str(out))
     assert np.abs(back[:, :3] - poses[:, :3]).max() < 5e-6 and np.abs(back[:, 3:6] - poses[:, 3:6]).max() < 5e-6   # float32 + 6 decimals
+
+
+def _lzf_compress(data: bytes) -> bytes:
+    """A small LZF encoder (liblzf stream format): greedy matches of 3..264 bytes within the last 8192 bytes, found through
+    a dictionary of 3-byte prefixes; everything else as literal runs of at most 32 bytes."""
+    out, lit, last, i, n = bytearray(), bytearray(), {}, 0, len(data)
+
+    def flush():
+        for a in range(0, len(lit), 32):
+            run = lit[a:a + 32]
+            out.append(len(run) - 1); out.extend(run)
+        lit.clear()
+    while i < n:
+        key = data[i:i + 3]
+        j = last.get(key, -1) if len(key) == 3 else -1
+        if len(key) == 3:
+            last[key] = i
+        if j >= 0 and i - j <= 8192:
+            ln = 3
+            while i + ln < n and ln < 264 and data[j + ln] == data[i + ln]:
+                ln += 1
+            flush()
+            dist, l2 = i - j - 1, ln - 2
+            if l2 < 7:
+                out.append((l2 << 5) | (dist >> 8))
+            else:
+                out.append((7 << 5) | (dist >> 8)); out.append(l2 - 7)
+            out.append(dist & 0xFF)
+            i += ln
+        else:
+            lit.append(data[i]); i += 1
+    flush()
+    return bytes(out)
+
+
+def test_pcd_binary_compressed(tmp_path):
+    """pcl::io::savePCDFileBinaryCompressed: sizes + LZF stream over the field-major block."""
+    import struct
+    from liloc_b200 import host_api
+    rng = np.random.default_rng(3)
+    n = 1500
+    pts = np.round(rng.normal(size=(n, 4)) * 20, 1).astype(np.float32)      # few distinct values: real back references
+    pts[200:900, 2] = 1.25; pts[:, 3] = 7.0                                    # long runs (overlapping copies)
+    ring = rng.integers(0, 16, n).astype(np.uint16)
+    block = pts[:, 0].tobytes() + pts[:, 1].tobytes() + pts[:, 2].tobytes() + pts[:, 3].tobytes() + ring.tobytes()
+    comp = _lzf_compress(block)
+    assert len(comp) < 0.8 * len(block)
+    p = tmp_path / "c.pcd"
+    p.write_bytes(_pcd_header(["x", "y", "z", "intensity", "ring"], [4, 4, 4, 4, 2], ["F", "F", "F", "F", "U"], [1] * 5, n, "binary_compressed")
+                  + struct.pack("<II", len(comp), len(block)) + comp)
+    assert np.array_equal(host_api.load_pcd(str(p)), pts)
+    # literal-only stream (what an encoder emits for incompressible data)
+    lit = b"".join(bytes([len(block[a:a + 32]) - 1]) + block[a:a + 32] for a in range(0, len(block), 32))
+    p.write_bytes(_pcd_header(["x", "y", "z", "intensity", "ring"], [4, 4, 4, 4, 2], ["F", "F", "F", "F", "U"], [1] * 5, n, "binary_compressed")
+                  + struct.pack("<II", len(lit), len(block)) + lit)
+    assert np.array_equal(host_api.load_pcd(str(p)), pts)
+    # corrupt streams are rejected, not read out of bounds
+    for bad in (comp[:-3], b"\xe0\xff\xff" + comp, comp + b"\x05abc"):
+        p.write_bytes(_pcd_header(["x", "y", "z", "intensity", "ring"], [4, 4, 4, 4, 2], ["F", "F", "F", "F", "U"], [1] * 5, n, "binary_compressed")
+                      + struct.pack("<II", len(bad), len(block)) + bad)
+        with pytest.raises(Exception):
+            host_api.load_pcd(str(p))

@@ -29,7 +29,8 @@ struct DeskewArgs {
     const float4* pts;           // x, y, z, intensity
     const int2* rt;              // ring, time (float bits)
     int n;
-    const double* imu;           // 4 x kImuMax: time | rotX | rotY | rotZ
+    const double* imu;           // 4 x imu_stride: time | rotX | rotY | rotZ
+    int imu_stride;
     int imu_last;                // imuPointerCur
     double t_cur;                // timeScanCur
     int deskew;                  // deskewFlag != -1 && imuAvailable
@@ -91,7 +92,7 @@ LILOC_DEV Aff3 aff_mul(const Aff3& a, const Aff3& b) {                   // Eige
 // findRotation (:573-597).  s_time: imuTime staged in shared memory; the three angle arrays are read from global memory.
 // The reference walks the samples from the front until the first one later than the point; when the stamps are
 // non-decreasing (`sorted`: the normal case) that index is found by bisection instead, with the same result.
-LILOC_DEV void find_rotation(const double* s_time, const double* __restrict__ imu, int last, bool sorted, double pointTime,
+LILOC_DEV void find_rotation(const double* s_time, const double* __restrict__ imu, int stride, int last, bool sorted, double pointTime,
                              float* rx, float* ry, float* rz) {
     int front = 0;
     if (sorted) {
@@ -107,7 +108,7 @@ LILOC_DEV void find_rotation(const double* s_time, const double* __restrict__ im
             ++front;
         }
     }
-    const double* RX = imu + kImuMax; const double* RY = imu + 2 * kImuMax; const double* RZ = imu + 3 * kImuMax;
+    const double* RX = imu + stride; const double* RY = imu + 2 * stride; const double* RZ = imu + 3 * stride;
     if (pointTime > s_time[front] || front == 0) {
         *rx = (float)__ldg(RX + front); *ry = (float)__ldg(RY + front); *rz = (float)__ldg(RZ + front);
     } else {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
             }
             if (lane == 0) {
                 float rx, ry, rz;
-                find_rotation(s_time, a.imu, a.imu_last, sorted, a.t_cur + (double)__int_as_float(__ldg(a.rt + first).y), &rx, &ry, &rz);
+                find_rotation(s_time, a.imu, a.imu_stride, a.imu_last, sorted, a.t_cur + (double)__int_as_float(__ldg(a.rt + first).y), &rx, &ry, &rz);
                 s_start_inv = aff_inverse(aff_from_rpy(rx, ry, rz));
             }
         }
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
             float4 o = p;
             if (a.deskew) {
                 float rx, ry, rz;
-                find_rotation(s_time, a.imu, a.imu_last, sorted, a.t_cur + (double)__int_as_float(rt.y), &rx, &ry, &rz);
+                find_rotation(s_time, a.imu, a.imu_stride, a.imu_last, sorted, a.t_cur + (double)__int_as_float(rt.y), &rx, &ry, &rz);
                 const Aff3 bt = aff_mul(s_start_inv, aff_from_rpy(rx, ry, rz));
                 o.x = bt.l[0][0] * p.x + bt.l[0][1] * p.y + bt.l[0][2] * p.z + bt.t[0];
                 o.y = bt.l[1][0] * p.x + bt.l[1][1] * p.y + bt.l[1][2] * p.z + bt.t[1];

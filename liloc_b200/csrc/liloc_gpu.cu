@@ -858,14 +858,13 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
         double* stage = ctx->h_dk_imu + (size_t)slot * 4 * kImuMax;
         const double* src[4] = {p->imu_time, p->imu_rot_x, p->imu_rot_y, p->imu_rot_z};
         for (int k = 0; k < 4; ++k) std::memcpy(stage + (size_t)k * m, src[k], (size_t)m * sizeof(double));
-        for (int k = 0; k < 4; ++k)
-            CU(cudaMemcpyAsync(ctx->d_dk_imu + (size_t)k * kImuMax, stage + (size_t)k * m, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_dk_imu, stage, (size_t)4 * m * sizeof(double), cudaMemcpyHostToDevice, st));      // one copy: 4 arrays of m
         CU(cudaEventRecord(ctx->ev_dk_slot[slot], st));
         ctx->stats.h2d_bytes += (long long)m * 32;
     }
     DeskewArgs a{};
     a.pts = ctx->dk_pts.p; a.rt = ctx->dk_rt.p; a.n = n;
-    a.imu = ctx->d_dk_imu; a.imu_last = p->imu_pointer_cur; a.t_cur = p->time_scan_cur; a.deskew = deskew ? 1 : 0;
+    a.imu = ctx->d_dk_imu; a.imu_stride = p->imu_pointer_cur + 1; a.imu_last = p->imu_pointer_cur; a.t_cur = p->time_scan_cur; a.deskew = deskew ? 1 : 0;
     a.rmin = p->lidar_min_range; a.rmax = p->lidar_max_range;
     a.n_scan = p->n_scan; a.ds_rate = p->downsample_rate; a.pf_num = p->point_filter_num;
     a.tile_count = ctx->dk_tiles.p; a.out = fc.scan_raw.p; a.n_out = ctx->d_dk_n;

@@ -153,7 +153,7 @@ def run_reference(args):
     n = args.steps * per_step
     value = n / dt
     sample = f"frames {args.warmup * per_step}..{f - 1} of the sequence ({per_step} frames per step), map built by the preceding frames"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "p50_frame_ms": float(np.percentile(lat, 50)), "p95_frame_ms": float(np.percentile(lat, 95)),
@@ -395,7 +395,7 @@ def run_ours(args):
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         "host": {"nproc": os.cpu_count()},
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     m.close()
 
 
@@ -546,7 +546,7 @@ def run_ndt(args):
                      "note": "algorithmic bytes = sweeps x (16 P + 36 P c + 224) per job (SURVEY 8d); the leaf gather is served by L2, the per-point math is float with double accumulation"},
         "cpu_baseline": cpu, "clocks": clocks, "host": {"nproc": os.cpu_count()},
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     ctx.close()
 
 
@@ -589,7 +589,7 @@ def run_ndt_reference(args):
         lat.append(c)
     dt = time.perf_counter() - t0
     value = args.steps * per_step / dt
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": NDT_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
         "config": {"workload": w["desc"], "items_per_step": per_step, "resolution": float(args.resolution)},
@@ -598,7 +598,24 @@ def run_ndt_reference(args):
     }))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The one JSON line of the run, on the process's original stdout."""
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def main():
+    # stdout carries exactly one line, the JSON result: anything libraries print there (NCCL's version banner under
+    # torchrun, for one) is sent to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -39,6 +39,7 @@ struct DeskewArgs {
     int* tile_count;             // ceil(n / 256)
     float4* out;
     int* n_out;
+    int* n_out_host;             // the same count into mapped host memory (no copy behind the launch)
     unsigned long long* marks;   // optional: %globaltimer (ns) of block 0 at start / after the barrier / at its end
 };
 
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kDeskewThreads, 2) k_deskew(const __grid_const
 #pragma unroll
     for (int w = 0; w < 8; ++w) { before += s_red[0][w]; total += s_red[1][w]; first_tile = min(first_tile, s_w[w]); }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.n_out = total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.n_out = total; *a.n_out_host = total; }
     if (t0 >= t1 || total == 0) {
         if (a.marks && blockIdx.x == 0 && threadIdx.x == 0) a.marks[2] = deskew_ns();
         return;

@@ -130,6 +130,9 @@ struct liloc_ctx {
     S2mState* d_state[2] = {nullptr, nullptr};   // double-buffered: a frame that has to be redone must not see its own update
     int state_cur = 0;
     S2mResult* d_result = nullptr;
+    S2mResult* d_result_host = nullptr;          // device alias of h_info->res (mapped pinned memory)
+    unsigned long long* d_marks_host = nullptr;  // device alias of h_info->marks
+    int* d_dk_n_host = nullptr;                  // device alias of h_info->dk_n
     int s2m_max_blocks = 0;
     int pipe_blocks = 0;                 // blocks of a narrow point-cloud pipeline launch (one per SM)
     int pipe_blocks_wide = 0;            // blocks of a wide one (two per SM when three fit, so wide + narrow co-reside)
@@ -341,7 +344,8 @@ void tick(liloc_ctx* ctx, int i, cudaStream_t st) { if (ctx->timing) cudaEventRe
 
 // Local-map problem of class `cls`: keyframe descriptors (H2D on `st`) -> transform + concat + bbox -> VoxelGrid ->
 // search grid.  Only fills *q; the caller launches the pipeline on the same stream.
-int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids, const float* poses6, int K, float leaf, VgProb* q) {
+int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids, const float* poses6, int K, float leaf, VgProb* q,
+                     PipeArgs* pa = nullptr) {
     FeatClass& fc = ctx->fc[cls];
     if (K < 0 || (K > 0 && (!kf_ids || !poses6)) || !(leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "localmap: bad arguments");
     int rc;
@@ -366,13 +370,20 @@ int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids
     fc.n_raw = (int)total;
     if ((rc = ensure(ctx, fc.descs, (size_t)(K > 0 ? K : 1)))) return rc;
     if ((rc = ensure(ctx, fc.raw, (size_t)(total > 0 ? total : 1)))) return rc;
+    int inline1 = 0;
     if (K > 0) {
-        CU(cudaMemcpyAsync(fc.descs.p, fc.h_descs, (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, st));
+        if (pa && pa->n_inline + K <= kInlineDescs) {          // descriptors as kernel parameters (pipeline.cuh)
+            std::memcpy(pa->inline_descs + pa->n_inline, fc.h_descs, (size_t)K * sizeof(KfDesc));
+            inline1 = pa->n_inline + 1;
+            pa->n_inline += K;
+        } else {
+            CU(cudaMemcpyAsync(fc.descs.p, fc.h_descs, (size_t)K * sizeof(KfDesc), cudaMemcpyHostToDevice, st));
+        }
         ctx->stats.h2d_bytes += (long long)K * (long long)sizeof(KfDesc);
     }
     fc.map_leaf_last = leaf;
     if ((rc = prob_voxelgrid(ctx, fc.vg_map, fc.raw.p, (int)total, leaf, &fc.map, q))) return rc;
-    q->arena = ctx->arena.p; q->descs = fc.descs.p; q->K = total > 0 ? K : 0; q->raw = fc.raw.p;
+    q->arena = ctx->arena.p; q->descs = fc.descs.p; q->inline1 = inline1; q->K = total > 0 ? K : 0; q->raw = fc.raw.p;
     if ((rc = prob_add_grid(ctx, fc, (int)total, q))) return rc;
     fc.have_map = true;
     return 0;
@@ -462,16 +473,17 @@ int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     if (blocks > ctx->s2m_max_blocks) blocks = ctx->s2m_max_blocks;
     if (blocks < 1) blocks = 1;
     if ((rc = ensure(ctx, ctx->partial, (size_t)2 * blocks * kNSums))) return rc;
-    CU(cudaMemcpyAsync(ctx->d_pose, pose6, 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // the initial guess is a kernel parameter: a 24-byte H2D copy between the map launch and this one would put a
+    // copy-engine hop (several microseconds) on the frame's critical path
+    for (int i = 0; i < 6; ++i) a.pose_in[i] = pose6[i];
     ctx->stats.h2d_bytes += 24;
     a.partial = ctx->partial.p; a.pose_io = ctx->d_pose;
-    a.state = ctx->d_state[ctx->state_cur]; a.state_out = ctx->d_state[ctx->state_cur ^ 1]; a.result = ctx->d_result;
-    a.marks = ctx->timing ? ctx->d_marks + 2 * kPipeMarks : nullptr;
+    a.state = ctx->d_state[ctx->state_cur]; a.state_out = ctx->d_state[ctx->state_cur ^ 1]; a.result = ctx->d_result_host;
+    a.marks = ctx->timing ? ctx->d_marks_host + 2 * kPipeMarks : nullptr;
     void* args[] = {&a};
     CU(cudaLaunchCooperativeKernel((void*)k_scan2map, dim3((unsigned)blocks), dim3(kS2mThreads), args, 0, ctx->stream));
     ++ctx->launches;
-    CU(cudaMemcpyAsync(&ctx->h_info->res, ctx->d_result, sizeof(S2mResult), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += (long long)sizeof(S2mResult);
+    ctx->stats.d2h_bytes += (long long)sizeof(S2mResult);        // written by the kernel into mapped host memory
     ++ctx->stats.s2m_launches;
     return 0;
 }
@@ -552,8 +564,17 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaMalloc(&c->d_result, sizeof(S2mResult)));
     CUB_(cudaMemset(c->d_result, 0, sizeof(S2mResult)));
     CUB_(cudaMalloc(&c->d_ndt_active, sizeof(int)));
-    CUB_(cudaMallocHost(&c->h_info, sizeof(HostFrameInfo)));
+    // pinned AND mapped: the registration kernel and the phase marks write their results straight into host memory
+    // (posted PCIe writes), so no device-to-host copy sits between the last kernel of a frame and the host's wake-up
+    CUB_(cudaHostAlloc(&c->h_info, sizeof(HostFrameInfo), cudaHostAllocMapped));
     std::memset(c->h_info, 0, sizeof(HostFrameInfo));
+    {
+        HostFrameInfo* dev_alias = nullptr;
+        CUB_(cudaHostGetDevicePointer(&dev_alias, c->h_info, 0));
+        c->d_result_host = &dev_alias->res;
+        c->d_marks_host = dev_alias->marks;
+        c->d_dk_n_host = &dev_alias->dk_n;
+    }
     for (auto& e : c->ev) CUB_(cudaEventCreate(&e));
     int per_sm = 0;
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan2map, kS2mThreads, 0));
@@ -728,7 +749,7 @@ int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const
     if (bad_class(cls)) return fail(ctx, LILOC_ERR_ARG, "localmap_build: bad class %d", cls);
     int rc;
     PipeArgs pa{};
-    if ((rc = localmap_problem(ctx, cls, ctx->stream, kf_ids, poses6, K, leaf, &pa.prob[0]))) return rc;
+    if ((rc = localmap_problem(ctx, cls, ctx->stream, kf_ids, poses6, K, leaf, &pa.prob[0], &pa))) return rc;
     pa.n_prob = 1;
     if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr))) return rc;
     if ((rc = class_fetch(ctx, cls, ctx->stream, true, false))) return rc;
@@ -867,7 +888,7 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     a.imu = ctx->d_dk_imu; a.imu_stride = p->imu_pointer_cur + 1; a.imu_last = p->imu_pointer_cur; a.t_cur = p->time_scan_cur; a.deskew = deskew ? 1 : 0;
     a.rmin = p->lidar_min_range; a.rmax = p->lidar_max_range;
     a.n_scan = p->n_scan; a.ds_rate = p->downsample_rate; a.pf_num = p->point_filter_num;
-    a.tile_count = ctx->dk_tiles.p; a.out = fc.scan_raw.p; a.n_out = ctx->d_dk_n;
+    a.tile_count = ctx->dk_tiles.p; a.out = fc.scan_raw.p; a.n_out = ctx->d_dk_n; a.n_out_host = ctx->d_dk_n_host;
     const int n_tiles = (n + kDeskewThreads - 1) / kDeskewThreads;
     const int max_blocks = ctx->num_sms * ctx->dk_blocks_per_sm;
     const int blocks = n_tiles < 1 ? 1 : (n_tiles < max_blocks ? n_tiles : max_blocks);
@@ -877,8 +898,7 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     CU(cudaLaunchCooperativeKernel((void*)k_deskew, dim3((unsigned)blocks), dim3(kDeskewThreads), args, 0, st));
     ++ctx->launches;
     if (ctx->timing) cudaEventRecord(ctx->ev_dk[1], st);
-    CU(cudaMemcpyAsync(&ctx->h_info->dk_n, ctx->d_dk_n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ctx->stats.d2h_bytes += 4;
+    ctx->stats.d2h_bytes += 4;                                   // the count, written by the kernel into mapped host memory
     CU(cudaEventRecord(ctx->ev_deskew, st));
     ctx->dk_n_upper = n; ctx->dk_n = -1;
     fc.have_scan = false; fc.Q_all = -1;
@@ -965,7 +985,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
                                (dev == LILOC_SCAN_DESKEWED && cls != LILOC_SURF) ? LILOC_SCAN_HOST : dev, in->scan_leaf[cls], &ps.prob[cls]))) return rc;
     ps.n_prob = ncls;
     if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
-    if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks + kPipeMarks : nullptr))) return rc;
+    if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks_host + kPipeMarks : nullptr))) return rc;
     if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
     CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
     // local maps: descriptors -> assemble -> VoxelGrid -> search grid, one launch for all classes.  With map_cache a
@@ -977,7 +997,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
                          (K == 0 || (std::memcmp(key.ids.data(), in->kf_ids, K * sizeof(int)) == 0 &&
                                      std::memcmp(key.poses.data(), in->kf_poses6, K * 6 * sizeof(float)) == 0));
         if (hit) { ++ctx->map_cache_hits; continue; }
-        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[pm.n_prob]))) return rc;
+        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[pm.n_prob], &pm))) return rc;
         ++pm.n_prob;
         if (ctx->map_cache) {
             key.ids.assign(in->kf_ids, in->kf_ids + K); key.poses.assign(in->kf_poses6, in->kf_poses6 + 6 * K);
@@ -989,13 +1009,12 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     // points (Mid-360 map: 394 -> 332 us); below that one block per SM is as fast or faster (centroid gathers)
     const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
     const bool map_launched = pm.n_prob > 0;
-    if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks : nullptr, wide))) return rc;
+    if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks_host : nullptr, wide))) return rc;
     tick(ctx, 3, ctx->stream);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
     tick(ctx, 4, ctx->stream);
     if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
     tick(ctx, 5, ctx->stream);
-    if (ctx->timing) CU(cudaMemcpyAsync(ctx->h_info->marks, ctx->d_marks, sizeof(ctx->h_info->marks), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation
     {   // counts come back inside the result struct
         const S2mResult& r = ctx->h_info->res;

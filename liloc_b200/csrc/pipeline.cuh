@@ -43,6 +43,7 @@ struct VgProb {
     // optional: assemble pts from keyframes first
     const float4* arena;
     const KfDesc* descs;
+    int inline1;               // 1 + index of this problem's first descriptor in PipeArgs::inline_descs (0: read `descs`)
     int K;
     float4* raw;
     // scratch
@@ -68,9 +69,14 @@ struct VgProb {
 };
 
 constexpr int kPipeMarks = 16;
+constexpr int kInlineDescs = 40;      // keyframe descriptors that travel with the launch (40 x 64 B of kernel parameters)
 struct PipeArgs {
     VgProb prob[kMaxProbs];
     int n_prob;
+    // Small local maps (the usual case: 15-30 keyframes) carry their descriptors as kernel parameters: a host-to-device
+    // copy in front of the launch would put a copy-engine hop of several microseconds at the start of every frame.
+    int n_inline;
+    KfDesc inline_descs[kInlineDescs];
     unsigned long long* marks;   // optional: %globaltimer (ns) at every phase boundary, written by block 0 (latency breakdown)
     int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters + the sort-block counter
 };
@@ -176,7 +182,8 @@ struct PipeSmemRun { unsigned key[kRunTile]; float4 pt[kRunTile]; unsigned prev;
 union PipeSmem { PipeSmemSort sort; PipeSmemRun run; int hist[256]; };
 
 // ---- P0 -------------------------------------------------------------------------------------------------------
-LILOC_DEV void pipe_bbox(const VgProb& q) {
+LILOC_DEV void pipe_bbox(const PipeArgs& a, const VgProb& q) {
+    const KfDesc* __restrict__ descs = q.inline1 ? &a.inline_descs[q.inline1 - 1] : q.descs;
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
     if (q.K > 0) {
         __shared__ int s_k0;
@@ -187,7 +194,7 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
                 int lo = 0, hi = q.K - 1;
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (q.descs[mid].dst_off <= base) lo = mid; else hi = mid - 1;
+                    if (descs[mid].dst_off <= base) lo = mid; else hi = mid - 1;
                 }
                 s_k0 = lo;
             }
@@ -201,8 +208,8 @@ LILOC_DEV void pipe_bbox(const VgProb& q) {
                 const int i = base + j * kPipeThreads + threadIdx.x;
                 d[j] = nullptr;
                 if (i < prob_n(q)) {
-                    while (k + 1 < q.K && q.descs[k + 1].dst_off <= i) ++k;
-                    d[j] = &q.descs[k];
+                    while (k + 1 < q.K && descs[k + 1].dst_off <= i) ++k;
+                    d[j] = &descs[k];
                 }
             }
 #pragma unroll
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     int mark = 0;
 #define PIPE_MARK() do { if (a.marks && blockIdx.x == 0 && threadIdx.x == 0 && mark < kPipeMarks) a.marks[mark] = global_ns(); ++mark; } while (0)
     PIPE_MARK();                                                                          // 0 start
-    for (int p = 0; p < np; ++p) pipe_bbox(a.prob[p]);                                   // P0
+    for (int p = 0; p < np; ++p) pipe_bbox(a, a.prob[p]);                                   // P0
     grid.sync();
     PIPE_MARK();                                                                          // 1 after assemble + bbox
 

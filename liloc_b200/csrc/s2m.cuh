@@ -66,7 +66,8 @@ struct S2mArgs {
     int enable_corner;
     int max_iters, min_sel, min_points, min_corner;
     double* partial;                     // [2][gridDim.x][kNSums]
-    float* pose_io;                      // 6 floats: in = initial guess, out = result
+    float pose_in[6];                    // initial guess (travels with the launch: no copy in front of the kernel)
+    float* pose_io;                      // 6 floats: out = result (also in S2mResult::pose)
     const S2mState* state;               // members isDegenerate / matP before this call ...
     S2mState* state_out;                 // ... and after it (double-buffered by the host, see liloc_frame_features)
     S2mResult* result;
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
     const int n_tiles = n_tiles_c + (nq + kQPB - 1) / kQPB;
 
     s2m_stage_views(a, sh);
-    if (threadIdx.x < 6) sh.pose[threadIdx.x] = a.pose_io[threadIdx.x];
+    if (threadIdx.x < 6) sh.pose[threadIdx.x] = a.pose_in[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 68) sh.matP[threadIdx.x - 32] = a.state->matP[threadIdx.x - 32];
     if (threadIdx.x == 0) { sh.is_degenerate = a.state->is_degenerate; sh.done = 0; sh.n_sel = 0; }
     __syncthreads();

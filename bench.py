@@ -358,7 +358,10 @@ def run_ours(args):
         pass
     roof = {"bound": "hbm", "kernel": "k_voxel_pipeline, local-map launch (assemble + VoxelGrid + search grid; persistent cooperative, one launch per frame)",
             "achieved": map_gbs, "peak": peak, "unit": "GB/s", "frac": (map_gbs / peak) if map_gbs else None, "traffic": traffic,
-            "peak_source": peak_src, "avg_launch_us": map_ms * 1e3 / n_fr, "alg_bytes_per_launch": st_dev["alg_bytes_map"] / n_fr,
+            "peak_source": peak_src, "avg_launch_us": map_ms * 1e3 / n_fr,
+            "timing_source": "%globaltimer marks written by block 0 of every launch into mapped host memory, live inside the timed region; "
+                             "no CUDA events inside a frame (one between two launches costs ~2.5 us of device time); the timed region "
+                             "as a whole is bracketed by CUDA events on the library's stream (device_s)", "alg_bytes_per_launch": st_dev["alg_bytes_map"] / n_fr,
             "note": "latency-bound, not bandwidth-bound: ~10 dependent phases separated by grid barriers over an L2-resident working set "
                     "(SURVEY 8d); phase-by-phase latency in profiles/frame_latency_r01.md",
             "per_frame_us": {"local_map_launch": map_ms * 1e3 / n_fr, "scan_launch(concurrent)": st_dev["scan_ms"] * 1e3 / n_fr,

@@ -288,7 +288,9 @@ int liloc_set_timing(liloc_ctx* ctx, int enabled);
  * %globaltimer nanoseconds written by block 0 at the phase boundaries of the three launches --
  * [0..15] local-map pipeline (start, assemble+bbox, keys, sort, run count, centroids, cell scan, end),
  * [16..31] scan pipeline (same phases), [32] registration start, then per iteration i: [33+3i] tiles done,
- * [34+3i] past the grid barrier, [35+3i] pose updated.  Returns the number of entries copied. */
+ * [34+3i] past the grid barrier, [35+3i] pose updated, [129] end of the registration kernel.  The kernels write them
+ * straight into mapped host memory; liloc_last_timing is derived from them (no CUDA events inside a frame).
+ * Returns the number of entries copied. */
 int liloc_last_marks(liloc_ctx* ctx, unsigned long long* out, int cap);
 /* Cumulative counters since liloc_create / liloc_stats_reset.  Phase times are CUDA-event milliseconds
  * summed over liloc_frame calls made while timing is enabled; alg_bytes_* are the ALGORITHMIC bytes of

@@ -617,7 +617,7 @@ class Context:
 
     def last_marks(self) -> np.ndarray:
         """%globaltimer marks of the last timed frame (see include/liloc_gpu.h liloc_last_marks)."""
-        out = np.zeros(2 * 16 + 1 + 3 * 32, np.uint64)
+        out = np.zeros(2 * 16 + 2 + 3 * 32, np.uint64)           # [130] = end of the registration kernel
         n = lib.liloc_last_marks(self._h, _ptr(out), len(out))
         return out[:n]
 

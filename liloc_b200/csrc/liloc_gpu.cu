@@ -93,6 +93,7 @@ struct HostFrameInfo {     // pinned, written by async D2H
     unsigned long long marks[2 * kPipeMarks + kS2mMarks];
     int scratch;
     int dk_n;
+    unsigned long long dk_marks[3];      // de-skew launch: block 0 at start / after the barrier / end
 };
 
 }  // namespace
@@ -169,12 +170,11 @@ struct liloc_ctx {
     int dk_slot = 0;
     cudaEvent_t ev_dk_slot[2]{};
     int* d_dk_n = nullptr;               // points of the de-skewed cloud
-    unsigned long long* d_dk_marks = nullptr;   // 3 phase timestamps of the last launch (timing)
+    unsigned long long* d_dk_marks = nullptr;   // device alias of h_info->dk_marks (timing)
     int dk_blocks_per_sm = 1;
     int dk_n_upper = -1;                 // raw points of the last sweep (-1: no de-skewed cloud)
     int dk_n = -1;                       // host copy of *d_dk_n, -1 while unknown
     cudaEvent_t ev_deskew = nullptr;
-    cudaEvent_t ev_dk[2]{};              // timing
     float dk_ms = 0.f;
 
     // kernel-level test scratch
@@ -574,6 +574,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
         c->d_result_host = &dev_alias->res;
         c->d_marks_host = dev_alias->marks;
         c->d_dk_n_host = &dev_alias->dk_n;
+        c->d_dk_marks = dev_alias->dk_marks;
     }
     for (auto& e : c->ev) CUB_(cudaEventCreate(&e));
     int per_sm = 0;
@@ -598,11 +599,8 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaMallocHost(&c->h_dk_imu, 2 * 4 * kImuMax * sizeof(double)));
     for (auto& e : c->ev_dk_slot) CUB_(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB_(cudaMalloc(&c->d_dk_n, sizeof(int)));
-    CUB_(cudaMalloc(&c->d_dk_marks, 3 * sizeof(unsigned long long)));
-    CUB_(cudaMemset(c->d_dk_marks, 0, 3 * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_dk_n, 0, sizeof(int)));
     CUB_(cudaEventCreateWithFlags(&c->ev_deskew, cudaEventDisableTiming));
-    for (auto& e : c->ev_dk) CUB_(cudaEventCreate(&e));
     CUB_(cudaMalloc(&c->d_marks, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_marks, 0, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
 #undef CUB_
@@ -644,10 +642,9 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
     fr(c->d_marks); fr(c->d_sm_scratch);
-    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu); fr(c->d_dk_n); fr(c->d_dk_marks);
+    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu); fr(c->d_dk_n);
     if (c->h_dk_imu) cudaFreeHost(c->h_dk_imu);
     if (c->ev_deskew) cudaEventDestroy(c->ev_deskew);
-    for (auto& e : c->ev_dk) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_dk_slot) if (e) cudaEventDestroy(e);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
@@ -894,10 +891,8 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     const int blocks = n_tiles < 1 ? 1 : (n_tiles < max_blocks ? n_tiles : max_blocks);
     a.marks = ctx->timing ? ctx->d_dk_marks : nullptr;
     void* args[] = {&a};
-    if (ctx->timing) cudaEventRecord(ctx->ev_dk[0], st);
     CU(cudaLaunchCooperativeKernel((void*)k_deskew, dim3((unsigned)blocks), dim3(kDeskewThreads), args, 0, st));
     ++ctx->launches;
-    if (ctx->timing) cudaEventRecord(ctx->ev_dk[1], st);
     ctx->stats.d2h_bytes += 4;                                   // the count, written by the kernel into mapped host memory
     CU(cudaEventRecord(ctx->ev_deskew, st));
     ctx->dk_n_upper = n; ctx->dk_n = -1;
@@ -906,7 +901,6 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
         CU(cudaStreamSynchronize(st));
         ctx->dk_n = ctx->h_info->dk_n;
         *n_out = ctx->dk_n;
-        if (ctx->timing) cudaEventElapsedTime(&ctx->dk_ms, ctx->ev_dk[0], ctx->ev_dk[1]);
     }
     return LILOC_OK;
 }
@@ -939,16 +933,17 @@ int liloc_last_deskew_marks(liloc_ctx* ctx, unsigned long long* out3) {
     ENTER(ctx);
     if (!out3) return fail(ctx, LILOC_ERR_ARG, "last_deskew_marks: null");
     CU(cudaStreamSynchronize(ctx->stream2));
-    CU(cudaMemcpy(out3, ctx->d_dk_marks, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    std::memcpy(out3, ctx->h_info->dk_marks, 3 * sizeof(unsigned long long));
     return LILOC_OK;
 }
 
 int liloc_last_deskew_ms(liloc_ctx* ctx, float* ms) {
     ENTER(ctx);
     if (!ms) return fail(ctx, LILOC_ERR_ARG, "last_deskew_ms: null");
-    if (ctx->timing && ctx->dk_n_upper >= 0) {
+    if (ctx->timing && ctx->dk_n_upper >= 0) {                   // in-kernel duration (block 0, %globaltimer)
         CU(cudaStreamSynchronize(ctx->stream2));
-        cudaEventElapsedTime(&ctx->dk_ms, ctx->ev_dk[0], ctx->ev_dk[1]);
+        const unsigned long long* mk = ctx->h_info->dk_marks;
+        ctx->dk_ms = mk[2] > mk[0] ? (float)((double)(mk[2] - mk[0]) * 1e-6) : 0.f;
     }
     *ms = ctx->dk_ms;
     return LILOC_OK;
@@ -984,9 +979,10 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         if ((rc = scan_problem(ctx, cls, ctx->stream2, in->scan[cls], in->n_scan[cls],
                                (dev == LILOC_SCAN_DESKEWED && cls != LILOC_SURF) ? LILOC_SCAN_HOST : dev, in->scan_leaf[cls], &ps.prob[cls]))) return rc;
     ps.n_prob = ncls;
-    if (ctx->timing) cudaEventRecord(ctx->ev[6], ctx->stream2);
+    // No CUDA events inside a frame, not even with timing on: an event record between two launches costs ~2.5 us of
+    // device time each (measured: 151 -> 145 us per frame without the two around the join).  The phase durations come
+    // from the %globaltimer marks block 0 of every launch writes into mapped host memory.
     if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks_host + kPipeMarks : nullptr))) return rc;
-    if (ctx->timing) cudaEventRecord(ctx->ev[7], ctx->stream2);
     CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
     // local maps: descriptors -> assemble -> VoxelGrid -> search grid, one launch for all classes.  With map_cache a
     // class whose (ids, poses, leaf) are bit-identical to the map it already holds is left as it is.
@@ -1004,17 +1000,13 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
             key.leaf = in->map_leaf[cls]; key.valid = true;
         }
     }
-    tick(ctx, 0, ctx->stream);
     // measured (profiles/frame_latency_r01.md): two blocks per SM pay off for the streaming phases above ~1.5 M raw
     // points (Mid-360 map: 394 -> 332 us); below that one block per SM is as fast or faster (centroid gathers)
     const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
     const bool map_launched = pm.n_prob > 0;
     if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks_host : nullptr, wide))) return rc;
-    tick(ctx, 3, ctx->stream);
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
-    tick(ctx, 4, ctx->stream);
     if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
-    tick(ctx, 5, ctx->stream);
     CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation
     {   // counts come back inside the result struct
         const S2mResult& r = ctx->h_info->res;
@@ -1031,9 +1023,13 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         t.assemble_ms = span(0, 1);                               // transform + concat + bounding box
         t.map_voxel_ms = span(1, 5);                              // keys, radix sort, run count, centroids
         t.grid_ms = span(5, 7);                                   // search-grid scan + scatter
-        cudaEventElapsedTime(&t.scan_ms, ctx->ev[6], ctx->ev[7]);
-        cudaEventElapsedTime(&t.s2m_ms, ctx->ev[4], ctx->ev[5]);
-        cudaEventElapsedTime(&t.total_ms, ctx->ev[0], ctx->ev[5]);
+        const unsigned long long* ms_ = mk + kPipeMarks;         // scans launch: [0] start .. [5] block 0's end (no search grid)
+        const unsigned long long* mr = mk + 2 * kPipeMarks;      // registration: [0] start .. [kS2mMarks - 1] end
+        auto dur = [](unsigned long long a0, unsigned long long a1) { return a1 > a0 ? (float)((double)(a1 - a0) * 1e-6) : 0.f; };
+        t.scan_ms = dur(ms_[0], ms_[5]);
+        t.s2m_ms = dur(mr[0], mr[kS2mMarks - 1]);
+        const unsigned long long first = map_launched ? (mk[0] < ms_[0] ? mk[0] : ms_[0]) : ms_[0];
+        t.total_ms = dur(first, mr[kS2mMarks - 1]);              // first kernel's first instruction .. last kernel's last
         liloc_stats& st = ctx->stats;
         st.assemble_ms += t.assemble_ms; st.map_voxel_ms += t.map_voxel_ms; st.scan_ms += t.scan_ms;
         st.grid_ms += t.grid_ms; st.s2m_ms += t.s2m_ms; st.total_ms += t.total_ms;

@@ -74,7 +74,7 @@ struct S2mArgs {
     unsigned long long* marks;           // optional latency breakdown: %globaltimer at [0] start and, per iteration i,
                                          // [1+3i] tiles done, [2+3i] past the grid barrier, [3+3i] pose updated (block 0)
 };
-constexpr int kS2mMarks = 1 + 3 * 32;
+constexpr int kS2mMarks = 2 + 3 * 32;      // start, three per iteration, [kS2mMarks - 1] = end of block 0
 
 LILOC_DEV unsigned long long s2m_global_ns() {
     unsigned long long t;
@@ -815,6 +815,7 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
         for (int i = 0; i < 6; ++i) { r->pose[i] = sh.pose[i]; a.pose_io[i] = sh.pose[i]; }
         a.state_out->is_degenerate = sh.is_degenerate;
         for (int i = 0; i < 36; ++i) a.state_out->matP[i] = sh.matP[i];
+        if (a.marks) a.marks[kS2mMarks - 1] = s2m_global_ns();
     }
 }
 

@@ -1,5 +1,4 @@
-"""Device time of the de-skew launch (k_deskew): CUDA events around the launch and block 0's %globaltimer marks
-(start -> after the grid barrier -> end).  Usage: python tests/tools/deskew_timing.py [vlp16|hdl32|mid360]"""
+"""Device time of the de-skew launch (k_deskew): block 0's %globaltimer marks (start -> after the grid barrier -> end).  Usage: python tests/tools/deskew_timing.py [vlp16|hdl32|mid360]"""
 import os
 import sys
 
@@ -27,7 +26,7 @@ def main():
                 mk = ctx.last_deskew_marks().astype(np.int64)
                 if it >= 10:
                     ev.append(ctx.last_deskew_ms() * 1e3); a.append((mk[1] - mk[0]) * 1e-3); b.append((mk[2] - mk[1]) * 1e-3)
-            print(f"{name} n_raw={len(sw['pts'])} point_filter_num={pf} n_out={n} imu={len(t)}: events p50 {np.median(ev):.1f} us | "
+            print(f"{name} n_raw={len(sw['pts'])} point_filter_num={pf} n_out={n} imu={len(t)}: in-kernel total p50 {np.median(ev):.1f} us | "
                   f"marks: counts+barrier {np.median(a):.1f} us, offsets+transform {np.median(b):.1f} us")
 
 

@@ -59,7 +59,7 @@ def main():
                 "s2m.reduce+solve(avg/iter)": np.mean([g[3 + 3 * i] - g[2 + 3 * i] for i in range(it)]),
                 "s2m.total": g[3 * it] - g[0], "s2m.iters": it * 1000,
                 "frame.device(map start -> s2m end)": g[3 * it] - m[0],
-                "event.scan_ms": tm["scan_ms"] * 1e6, "event.s2m_ms": tm["s2m_ms"] * 1e6, "event.total_ms": tm["total_ms"] * 1e6,
+                "timing.scan_ms": tm["scan_ms"] * 1e6, "timing.s2m_ms": tm["s2m_ms"] * 1e6, "timing.total_ms": tm["total_ms"] * 1e6,
             }
             rows.append(row)
         ex = {"n_scan": len(raw), "q_all": res.q_all, "map_points": res.map_points, "n_raw": int(sum(len(c) for c in kfs)), "iters": res.iters}

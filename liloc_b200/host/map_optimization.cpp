@@ -80,6 +80,7 @@ void mapOptimization::reset() {
     timeLastProcessing_ = -1; lastImuPreTransAvailable_ = false;
     lastImuTransformation_ = Affine3f::Identity(); lastImuPreTransformation_ = Affine3f::Identity();
     sel_ids_.clear(); sel_poses_.clear(); have_selection_ = false;
+    nearby_ds_.clear(); nearby_n_ = 0;
     prior_ = PriorSession{};
     if (ctx_) { liloc_keyframe_clear(ctx_); liloc_ndt_clear(ctx_); }
 }
@@ -165,23 +166,40 @@ void mapOptimization::extractSurroundingKeyFrames() {
 
 void mapOptimization::extractNearby() {
     const PointType& last = cloudKeyPoses3D.back();
-    // radiusSearch(last, R): d2 < R^2, ascending distance (:908-914)
-    const float r2 = surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius;
-    std::vector<std::pair<float, int>> hits;
-    for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
-        const float d = sqDist(last, cloudKeyPoses3D[i]);
-        if (d < r2) hits.push_back({d, i});
+    // The radius search, its VoxelGrid thinning and the 1-NN index recovery (:908-922) depend only on the key poses, which
+    // change when a keyframe is added (~40 % of the frames): their result is kept until then.  Only the "last 5 s" tail
+    // (:924-931) depends on the frame's stamp.
+    const PointType& first = cloudKeyPoses3D.front();
+    const bool cached = nearby_n_ == cloudKeyPoses3D.size() && nearby_last_.x == last.x && nearby_last_.y == last.y && nearby_last_.z == last.z &&
+                        nearby_first_.x == first.x && nearby_first_.y == first.y && nearby_first_.z == first.z;
+    if (!cached) {
+        // radiusSearch(last, R): d2 < R^2, ascending distance (:908-914)
+        const float r2 = surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius;
+        std::vector<std::pair<float, int>> hits;
+        hits.reserve(cloudKeyPoses3D.size());
+        for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
+            const float d = sqDist(last, cloudKeyPoses3D[i]);
+            if (d < r2) hits.push_back({d, i});
+        }
+        std::sort(hits.begin(), hits.end());
+        std::vector<PointType> surroundingKeyPoses;
+        surroundingKeyPoses.reserve(hits.size());
+        for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
+        nearby_ds_ = voxelGridSmall(surroundingKeyPoses, surroundingKeyframeDensity);                    // :916-917
+        for (auto& pt : nearby_ds_) {          // nearestKSearch(pt, 1): recover the keyframe index (:918-922)
+            // exact scan; a pose is only measured when its x offset alone does not already rule it out
+            int best = 0; float bd = sqDist(pt, cloudKeyPoses3D[0]);
+            for (int i = 1; i < (int)cloudKeyPoses3D.size(); ++i) {
+                const float ex = pt.x - cloudKeyPoses3D[i].x;
+                if (ex * ex >= bd) continue;
+                const float d = sqDist(pt, cloudKeyPoses3D[i]);
+                if (d < bd) { bd = d; best = i; }
+            }
+            pt.intensity = cloudKeyPoses3D[best].intensity;
+        }
+        nearby_n_ = cloudKeyPoses3D.size(); nearby_last_ = last; nearby_first_ = first;
     }
-    std::sort(hits.begin(), hits.end());
-    std::vector<PointType> surroundingKeyPoses;
-    surroundingKeyPoses.reserve(hits.size());
-    for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
-    std::vector<PointType> surroundingKeyPosesDS = voxelGridSmall(surroundingKeyPoses, surroundingKeyframeDensity);   // :916-917
-    for (auto& pt : surroundingKeyPosesDS) {   // nearestKSearch(pt, 1): recover the keyframe index (:918-922)
-        int best = 0; float bd = sqDist(pt, cloudKeyPoses3D[0]);
-        for (int i = 1; i < (int)cloudKeyPoses3D.size(); ++i) { const float d = sqDist(pt, cloudKeyPoses3D[i]); if (d < bd) { bd = d; best = i; } }
-        pt.intensity = cloudKeyPoses3D[best].intensity;
-    }
+    std::vector<PointType> surroundingKeyPosesDS = nearby_ds_;
     for (int i = (int)cloudKeyPoses3D.size() - 1; i >= 0; --i) {               // :924-931 (duplicates possible)
         if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 5.0) surroundingKeyPosesDS.push_back(cloudKeyPoses3D[i]);
         else break;

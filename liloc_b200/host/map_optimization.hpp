@@ -141,6 +141,10 @@ private:
     std::vector<int> sel_ids_;
     std::vector<float> sel_poses_;
     bool have_selection_ = false;
+    // extractNearby's pose-only part, valid while the key poses are unchanged
+    std::vector<PointType> nearby_ds_;
+    size_t nearby_n_ = 0;
+    PointType nearby_last_{0, 0, 0, 0}, nearby_first_{0, 0, 0, 0};
     FrameReport rep_;
     PriorSession prior_;
     int ndtAlign(int submap, const float guess6[6], int n_align, float out6[6], int* iterations, int* converged);

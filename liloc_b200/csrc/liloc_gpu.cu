@@ -47,7 +47,7 @@ struct DevBuf {
 struct VgInst {            // scratch of one VoxelGrid instance (the reference has three filters, :78-80)
     DevBuf<unsigned> keys_a, keys_b, vals_a, vals_b;      // after the sort: keys_b / vals_b hold the sorted pairs
     DevBuf<int> hist;              // 3 rotating block-histogram buffers of the radix sort
-    DevBuf<int> tile_counts;
+    DevBuf<unsigned long long> tile_state;   // look-back words of the centroid phase (pipeline.cuh)
     unsigned* d_enc = nullptr;     // 6 ordered-uint min/max (armed at creation, re-armed by the kernel)
     VgParams* d_vp = nullptr;
     int* d_count = nullptr;
@@ -71,7 +71,8 @@ struct FeatClass {
     float map_leaf_last = 0.f;
     // search grid (geometry on the device)
     GridParams* d_gp = nullptr;
-    DevBuf<int> cell_counts, cell_start, grid_tiles;
+    DevBuf<int> cell_counts, cell_start;
+    DevBuf<unsigned long long> grid_state;   // look-back words of the cell-count scan
     // scan
     DevBuf<float4> scan_raw;
     DevBuf<float4> scan;           // down-sampled
@@ -107,6 +108,7 @@ struct liloc_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
     std::string err;
     long long launches = 0;
+    unsigned pipe_epoch = 0;             // launch counter of the point-cloud pipeline (tags its look-back words)
 
     // keyframe arena
     DevBuf<float4> arena;
@@ -237,6 +239,20 @@ int ensure(liloc_ctx* ctx, DevBuf<T>& b, size_t n, bool keep = false) {
     return 0;
 }
 
+// look-back words (pipeline.cuh) are tagged with the launch counter, which starts at 1: a fresh buffer must not hold a
+// stale tag by accident, so it is cleared once when it is (re)allocated
+template <typename T>
+int ensure_zeroed(liloc_ctx* ctx, DevBuf<T>& b, size_t n) {
+    const size_t before = b.cap;
+    int rc = ensure(ctx, b, n);
+    if (rc) return rc;
+    if (b.cap != before) {
+        CU(cudaMemsetAsync(b.p, 0, b.cap * sizeof(T), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
 inline int blocks_for(const liloc_ctx* ctx, long long n, int per_block, int waves = 8) {
     long long b = (n + per_block - 1) / per_block;
     const long long cap = (long long)ctx->num_sms * waves;
@@ -294,11 +310,11 @@ int prob_voxelgrid(liloc_ctx* ctx, VgInst& vi, const float4* d_pts, int n, float
     if ((rc = ensure(ctx, vi.vals_a, cap))) return rc;
     if ((rc = ensure(ctx, vi.vals_b, cap))) return rc;
     if ((rc = ensure(ctx, vi.hist, (size_t)3 * kHistStride))) return rc;
-    if ((rc = ensure(ctx, vi.tile_counts, (size_t)(n / kRunTile) + 2))) return rc;
+    if ((rc = ensure_zeroed(ctx, vi.tile_state, (size_t)(n / kRunTile) + 2))) return rc;
     *q = VgProb{};
     q->pts = d_pts; q->n = n; q->leaf = leaf;
     q->keys[0] = vi.keys_a.p; q->keys[1] = vi.keys_b.p; q->vals[0] = vi.vals_a.p; q->vals[1] = vi.vals_b.p;
-    q->hist = vi.hist.p; q->tile_counts = vi.tile_counts.p; q->enc = vi.d_enc; q->vp = vi.d_vp;
+    q->hist = vi.hist.p; q->tile_state = vi.tile_state.p; q->enc = vi.d_enc; q->vp = vi.d_vp;
     q->out = out ? out->p : nullptr; q->count = vi.d_count;
     q->sort_only = out ? 0 : 1;
     return 0;
@@ -314,10 +330,10 @@ int prob_add_grid(liloc_ctx* ctx, FeatClass& fc, int m_upper, VgProb* q) {
         CU(cudaStreamSynchronize(ctx->stream));
     }
     if ((rc = ensure(ctx, fc.cell_start, (size_t)nc_max + 1))) return rc;
-    if ((rc = ensure(ctx, fc.grid_tiles, (size_t)(nc_max / kScanTile) + 2))) return rc;
+    if ((rc = ensure_zeroed(ctx, fc.grid_state, (size_t)(nc_max / kScanTile) + 2))) return rc;
     if ((rc = ensure(ctx, fc.cpts, (size_t)(m_upper > 0 ? m_upper : 1)))) return rc;
     q->build_grid = 1; q->max_cells = nc_max;
-    q->gp = fc.d_gp; q->cell_counts = fc.cell_counts.p; q->cell_start = fc.cell_start.p; q->grid_tiles = fc.grid_tiles.p; q->cpts = fc.cpts.p;
+    q->gp = fc.d_gp; q->cell_counts = fc.cell_counts.p; q->cell_start = fc.cell_start.p; q->grid_state = fc.grid_state.p; q->cpts = fc.cpts.p;
     return 0;
 }
 
@@ -327,6 +343,7 @@ int prob_add_grid(liloc_ctx* ctx, FeatClass& fc, int m_upper, VgProb* q) {
 int pipe_launch(liloc_ctx* ctx, cudaStream_t st, PipeArgs& a, unsigned long long* marks, bool wide = false) {
     if (a.n_prob <= 0) return 0;
     a.marks = marks;
+    a.epoch = ++ctx->pipe_epoch;
     a.sm_scratch = ctx->d_sm_scratch + (st == ctx->stream2 ? kSmScratch : 0);     // the two launches of a frame overlap
     void* args[] = {&a};
     const int blocks = wide ? ctx->pipe_blocks_wide : ctx->pipe_blocks;
@@ -631,10 +648,10 @@ void liloc_destroy(liloc_ctx* c) {
     for (FeatClass* fcp : {&c->fc[0], &c->fc[1], &c->aux}) {
         FeatClass& fc = *fcp;
         fr(fc.raw.p); fr(fc.map.p); fr(fc.cpts.p); fr(fc.descs.p); fr(fc.scan_raw.p); fr(fc.scan.p);
-        fr(fc.cell_counts.p); fr(fc.cell_start.p); fr(fc.grid_tiles.p); fr(fc.d_gp);
+        fr(fc.cell_counts.p); fr(fc.cell_start.p); fr(fc.grid_state.p); fr(fc.d_gp);
         if (fc.h_descs) cudaFreeHost(fc.h_descs);
         for (VgInst* vi : {&fc.vg_map, &fc.vg_scan}) {
-            fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->hist.p); fr(vi->tile_counts.p);
+            fr(vi->keys_a.p); fr(vi->keys_b.p); fr(vi->vals_a.p); fr(vi->vals_b.p); fr(vi->hist.p); fr(vi->tile_state.p);
             fr(vi->d_enc); fr(vi->d_vp); fr(vi->d_count);
         }
     }

@@ -11,10 +11,12 @@
 //   Sx  stable LSD radix sort of (key, source index), 8 bits per pass, ceil(key_bits / 8) passes: per-block
 //       digit offsets from the block histograms, warp-match ranking inside a tile, scatter; the histogram of the
 //       NEXT pass is accumulated while scattering, so a pass is a single phase
-//   R1  voxel-run heads per tile
 //   R2  one centroid per voxel run (float sums in ascending source index = the canonical order), written in
-//       ascending voxel index; the centroid's search-grid cell is counted in the same pass
-//   G1-G3  exclusive scan of the cell counts, then the points sorted by cell (the kNN search structure)
+//       ascending voxel index; the output offset of a tile is the number of run heads in all earlier tiles, obtained
+//       by a decoupled look-back over per-tile words (no separate counting phase, no barrier); the centroid's
+//       search-grid cell is counted in the same pass
+//   G2, G3  exclusive scan of the cell counts (one pass, the same look-back), then the points sorted by cell (the kNN
+//       search structure)
 //
 // Every size that only exists on the device (M, Q_all, search-grid geometry) stays there.  No library calls:
 // the radix sort is part of this kernel (the first version of this path used cub::DeviceRadixSort).
@@ -50,7 +52,7 @@ struct VgProb {
     unsigned* keys[2];
     unsigned* vals[2];
     int* hist;                 // 3 * kHistStride
-    int* tile_counts;          // ceil(n / kRunTile) + 1
+    unsigned long long* tile_state;   // ceil(n / kRunTile) + 1 look-back words (epoch << 32 | run heads of the tile)
     unsigned* enc;             // 6 ordered-uint min / max; re-armed by the kernel for the next launch
     VgParams* vp;              // out (diagnostics; the bounding box)
     // output
@@ -62,7 +64,7 @@ struct VgProb {
     GridParams* gp;
     int* cell_counts;          // all-zero outside [0, previous ncells) on entry; scatter cursor on exit
     int* cell_start;
-    int* grid_tiles;
+    unsigned long long* grid_state;   // look-back words of the cell-count scan
     float4* cpts;
     int sort_only;             // stop after the sort (NDT target build): sorted pairs are in keys[1] / vals[1]
     int grid_only;             // no down-sampling: the search grid is built over the (assembled) cloud itself; out == pts
@@ -76,6 +78,7 @@ struct PipeArgs {
     // Small local maps (the usual case: 15-30 keyframes) carry their descriptors as kernel parameters: a host-to-device
     // copy in front of the launch would put a copy-engine hop of several microseconds at the start of every frame.
     int n_inline;
+    unsigned epoch;              // launch counter: tags the look-back words, so they never need clearing
     KfDesc inline_descs[kInlineDescs];
     unsigned long long* marks;   // optional: %globaltimer (ns) at every phase boundary, written by block 0 (latency breakdown)
     int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters + the sort-block counter
@@ -155,6 +158,24 @@ LILOC_DEV int block_sum_256(int v) {                        // all 256 threads; 
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s_w[w];
     return t;
+}
+
+// Decoupled look-back over per-tile totals (phases R2 and G2).  A tile publishes (epoch, total) as one 64-bit word, then
+// sums the totals of every earlier tile, spinning on the words that are not there yet.  Tiles are handed out round-robin
+// in ascending order and a block publishes before it waits, so with all blocks resident (cooperative launch) every
+// wait ends: the earliest unpublished tile always belongs to a block that is not waiting on anything later.  This
+// replaces a separate counting phase and its grid barrier (~4.5 us per launch at 220 k points).  The spin is bounded:
+// a bug shows up as a wrong result in the parity tests, not as a hung GPU.
+LILOC_DEV int pipe_lookback(unsigned long long* state, int tile, int total, unsigned epoch) {
+    if (threadIdx.x == 0) atomicExch(&state[tile], ((unsigned long long)epoch << 32) | (unsigned)total);
+    int part = 0;
+    for (int u = threadIdx.x; u < tile; u += kPipeThreads) {
+        unsigned long long w;
+        int spins = 0;
+        do { w = *((volatile unsigned long long*)&state[u]); } while ((unsigned)(w >> 32) != epoch && ++spins < (1 << 22));
+        part += (int)(unsigned)(w & 0xffffffffull);
+    }
+    return block_sum_256(part);
 }
 
 // The sort runs on at most one block per SM (more blocks only add histogram rows for every block to read).  With two
@@ -360,40 +381,14 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
     }
 }
 
-// ---- R1: run heads per tile ---------------------------------------------------------------------------------------
-LILOC_DEV void pipe_run_count(const VgProb& q) {
-    const unsigned* __restrict__ skeys = q.keys[1];
-    const int n_tiles = (prob_n(q) + kRunTile - 1) / kRunTile;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int base = tile * kRunTile;
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kRunPerThread; ++j) {
-            const int i = base + j * kPipeThreads + threadIdx.x;
-            if (i < prob_n(q)) c += (i == 0 || skeys[i] != skeys[i - 1]) ? 1 : 0;
-        }
-        const int total = block_sum_256(c);
-        if (threadIdx.x == 0) q.tile_counts[tile] = total;
-    }
-}
-
 // ---- R2: centroids (+ search-cell count) ----------------------------------------------------------------------------
-LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& sm) {
+LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& sm, const unsigned epoch) {
     const unsigned* __restrict__ skeys = q.keys[1];
     const unsigned* __restrict__ svals = q.vals[1];
     const int n = prob_n(q);
     const int n_tiles = (n + kRunTile - 1) / kRunTile;
     if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) *q.count = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int part = 0;
-#pragma unroll 1
-        for (int u0 = threadIdx.x; u0 < tile; u0 += 4 * kPipeThreads) {
-            int v[4];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) v[w] = (u0 + w * kPipeThreads < tile) ? q.tile_counts[u0 + w * kPipeThreads] : 0;
-            part += (v[0] + v[1]) + (v[2] + v[3]);
-        }
-        const int tile_offset = block_sum_256(part);
         const int base = tile * kRunTile;
         const int cnt = min(kRunTile, n - base);
 #pragma unroll
@@ -418,7 +413,9 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
             c += head[j];
         }
         int total;
-        int rank = tile_offset + block_exclusive_scan_256(c, &total);
+        const int local_rank = block_exclusive_scan_256(c, &total);
+        const int tile_offset = pipe_lookback(q.tile_state, tile, total, epoch);      // run heads in all earlier tiles
+        int rank = tile_offset + local_rank;
         if (tile == n_tiles - 1 && threadIdx.x == 0) *q.count = tile_offset + total;
 #pragma unroll
         for (int j = 0; j < kRunPerThread; ++j) {
@@ -480,43 +477,19 @@ LILOC_DEV void pipe_cells_count_direct(const VgProb& q, const GridParams& gp) {
     }
 }
 
-// ---- G1..G3: cell counts -> cell_start, points sorted by cell -----------------------------------------------------------
-LILOC_DEV void pipe_cells_reduce(const VgProb& q, const GridParams& gp) {
+// ---- G2, G3: cell counts -> cell_start (one pass, look-back across tiles), points sorted by cell -----------------------------------------------------------
+LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsigned epoch) {
     const int n = gp.ncells;
     const int n_tiles = (n + kScanTile - 1) / kScanTile;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int base = tile * kScanTile;
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            const int i = base + j * kScanThreads + threadIdx.x;
-            if (i < n) c += q.cell_counts[i];
-        }
-        const int total = block_sum_256(c);
-        if (threadIdx.x == 0) q.grid_tiles[tile] = total;
-    }
-}
-
-LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp) {
-    const int n = gp.ncells;
-    const int n_tiles = (n + kScanTile - 1) / kScanTile;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int part = 0;
-#pragma unroll 1
-        for (int u0 = threadIdx.x; u0 < tile; u0 += 4 * kPipeThreads) {
-            int v[4];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) v[w] = (u0 + w * kPipeThreads < tile) ? q.grid_tiles[u0 + w * kPipeThreads] : 0;
-            part += (v[0] + v[1]) + (v[2] + v[3]);
-        }
-        const int tile_offset = block_sum_256(part);
         const int base = tile * kScanTile + threadIdx.x * kScanPerThread;
         int v[kScanPerThread];
         int c = 0;
 #pragma unroll
         for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? q.cell_counts[base + j] : 0; c += v[j]; }
         int total;
-        int run = tile_offset + block_exclusive_scan_256(c, &total);
+        const int local = block_exclusive_scan_256(c, &total);
+        int run = pipe_lookback(q.grid_state, tile, total, epoch) + local;
 #pragma unroll
         for (int j = 0; j < kScanPerThread; ++j) {
             if (base + j < n) { q.cell_start[base + j] = run; q.cell_counts[base + j] = run; }
@@ -595,19 +568,15 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     for (int p = 0; p < np; ++p) { any_out |= !a.prob[p].sort_only; any_grid |= a.prob[p].build_grid != 0; }
     if (!any_out) return;
 
-    for (int p = 0; p < np; ++p) {                                                        // R1
+    PIPE_MARK();                                                                          // 4 (kept for the layout of the marks)
+    for (int p = 0; p < np; ++p) {                                                        // R2 (R1, a counting phase, is folded into it)
         if (a.prob[p].grid_only) pipe_cells_count_direct(a.prob[p], s_gp[p]);
-        else if (!a.prob[p].sort_only) pipe_run_count(a.prob[p]);
+        else if (!a.prob[p].sort_only) pipe_centroids(a.prob[p], s_gp[p], sm, a.epoch);
     }
-    grid.sync();
-    PIPE_MARK();                                                                          // 4 after the run count
-    for (int p = 0; p < np; ++p) if (!a.prob[p].sort_only && !a.prob[p].grid_only) pipe_centroids(a.prob[p], s_gp[p], sm);   // R2
     if (!any_grid) { PIPE_MARK(); return; }                                               // 5 (block 0's own end)
     grid.sync();
     PIPE_MARK();                                                                          // 5 after the centroids
-    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_reduce(a.prob[p], s_gp[p]);    // G1
-    grid.sync();
-    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scan(a.prob[p], s_gp[p]);      // G2
+    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scan(a.prob[p], s_gp[p], a.epoch);   // G2
     grid.sync();
     PIPE_MARK();                                                                          // 6 after the cell scan
     for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scatter(a.prob[p], s_gp[p]);   // G3

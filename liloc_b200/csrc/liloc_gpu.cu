@@ -113,7 +113,10 @@ struct liloc_ctx {
     // keyframe arena
     DevBuf<float4> arena;
     size_t arena_used = 0;
-    struct KfEntry { size_t off[kClasses]; int n[kClasses]; };
+    struct KfEntry {
+        size_t off[kClasses]; int n[kClasses];
+        float pose6[6]; float T[12]; bool have_T;     // the last pose this keyframe was placed with and its 3x4 transform (six double sin / cos per pose)
+    };
     std::unordered_map<int, KfEntry> kf;
 
     FeatClass fc[kClasses];
@@ -380,7 +383,13 @@ int localmap_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const int* kf_ids
         if (it == ctx->kf.end()) return fail(ctx, LILOC_ERR_ARG, "localmap: unknown keyframe id %d", kf_ids[k]);
         KfDesc& d = fc.h_descs[k];
         d.src_off = (long long)it->second.off[cls]; d.n = it->second.n[cls]; d.dst_off = (int)total;
-        pose_to_T(poses6 + 6 * (size_t)k, d.T);
+        liloc_ctx::KfEntry& e = it->second;
+        if (!e.have_T || std::memcmp(e.pose6, poses6 + 6 * (size_t)k, sizeof(e.pose6)) != 0) {      // key poses rarely move
+            std::memcpy(e.pose6, poses6 + 6 * (size_t)k, sizeof(e.pose6));
+            pose_to_T(e.pose6, e.T);
+            e.have_T = true;
+        }
+        std::memcpy(d.T, e.T, sizeof(d.T));
         total += it->second.n[cls];
         if (total > 0x7fffffffLL) return fail(ctx, LILOC_ERR_CAPACITY, "localmap: more than 2^31 points");
     }
@@ -999,8 +1008,6 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     // No CUDA events inside a frame, not even with timing on: an event record between two launches costs ~2.5 us of
     // device time each (measured: 151 -> 145 us per frame without the two around the join).  The phase durations come
     // from the %globaltimer marks block 0 of every launch writes into mapped host memory.
-    if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks_host + kPipeMarks : nullptr))) return rc;
-    CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
     // local maps: descriptors -> assemble -> VoxelGrid -> search grid, one launch for all classes.  With map_cache a
     // class whose (ids, poses, leaf) are bit-identical to the map it already holds is left as it is.
     for (int cls = 0; cls < ncls; ++cls) {
@@ -1022,6 +1029,11 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
     const bool map_launched = pm.n_prob > 0;
     if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks_host : nullptr, wide))) return rc;
+    // The scan launch is issued AFTER the map launch: its upload was enqueued first (above) and takes longer than the host
+    // needs to get here, while the map launch -- the longer branch when the scan is already on the device -- would
+    // otherwise start a launch-call later.
+    if ((rc = pipe_launch(ctx, ctx->stream2, ps, ctx->timing ? ctx->d_marks_host + kPipeMarks : nullptr))) return rc;
+    CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
     if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation

@@ -18,6 +18,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -95,6 +96,7 @@ struct HostFrameInfo {     // pinned, written by async D2H
     int scratch;
     int dk_n;
     unsigned long long dk_marks[3];      // de-skew launch: block 0 at start / after the barrier / end
+    unsigned done_seq;                   // written last by the registration kernel: sequence number of the finished frame
 };
 
 }  // namespace
@@ -139,6 +141,9 @@ struct liloc_ctx {
     S2mResult* d_result_host = nullptr;          // device alias of h_info->res (mapped pinned memory)
     unsigned long long* d_marks_host = nullptr;  // device alias of h_info->marks
     int* d_dk_n_host = nullptr;                  // device alias of h_info->dk_n
+    unsigned* d_done_host = nullptr;             // device alias of h_info->done_seq
+    unsigned frame_seq = 0;                      // sequence number of the last enqueued registration
+    bool poll_result = true;                     // wait for a frame by polling done_seq (LILOC_NO_POLL=1: cudaStreamSynchronize)
     int s2m_max_blocks = 0;
     int pipe_blocks = 0;                 // blocks of a narrow point-cloud pipeline launch (one per SM)
     int pipe_blocks_wide = 0;            // blocks of a wide one (two per SM when three fit, so wide + narrow co-reside)
@@ -506,6 +511,7 @@ int s2m_enqueue(liloc_ctx* ctx, const float* pose6, const liloc_s2m_opts* o) {
     a.partial = ctx->partial.p; a.pose_io = ctx->d_pose;
     a.state = ctx->d_state[ctx->state_cur]; a.state_out = ctx->d_state[ctx->state_cur ^ 1]; a.result = ctx->d_result_host;
     a.marks = ctx->timing ? ctx->d_marks_host + 2 * kPipeMarks : nullptr;
+    a.done_flag = ctx->d_done_host; a.done_value = ++ctx->frame_seq;
     void* args[] = {&a};
     CU(cudaLaunchCooperativeKernel((void*)k_scan2map, dim3((unsigned)blocks), dim3(kS2mThreads), args, 0, ctx->stream));
     ++ctx->launches;
@@ -560,6 +566,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->map_cache = cfg->map_cache != 0;
     { const char* e = getenv("LILOC_PIPE_NARROW"); c->wide_maps = !(e && e[0] == '1'); }
+    { const char* e = getenv("LILOC_NO_POLL"); c->poll_result = !(e && e[0] == '1'); }
     ctx = c;
     auto bail = [&](int rc) { g_create_error = c->err; liloc_destroy(c); return rc; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
@@ -600,6 +607,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
         c->d_result_host = &dev_alias->res;
         c->d_marks_host = dev_alias->marks;
         c->d_dk_n_host = &dev_alias->dk_n;
+        c->d_done_host = &dev_alias->done_seq;
         c->d_dk_marks = dev_alias->dk_marks;
     }
     for (auto& e : c->ev) CUB_(cudaEventCreate(&e));
@@ -989,6 +997,25 @@ int liloc_scan2map(liloc_ctx* ctx, float* pose6, const liloc_s2m_opts* opts, lil
     return s2m_collect(ctx, pose6, res, o);
 }
 
+// Wait for the registration kernel enqueued last.  The kernel writes its result into mapped host memory and then the
+// frame's sequence number; polling that word returns a few microseconds before cudaStreamSynchronize would (which waits
+// for the kernel to retire).  Everything enqueued afterwards is stream-ordered behind the kernel anyway.  If the word
+// does not arrive (a faulted kernel never writes it) the stream is synchronised and the error surfaces there.
+static int frame_wait(liloc_ctx* ctx) {
+    if (ctx->poll_result) {
+        const volatile unsigned* flag = &ctx->h_info->done_seq;
+        const unsigned want = ctx->frame_seq;
+        const auto t0 = std::chrono::steady_clock::now();
+        int spins = 0;
+        while (*flag != want) {
+            if ((++spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
+        }
+        if (*flag == want) return 0;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
     ENTER(ctx);
     if (!pose6 || !in) return fail(ctx, LILOC_ERR_ARG, "frame: null argument");
@@ -1036,7 +1063,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
     if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));          // the frame's only host synchronisation
+    if ((rc = frame_wait(ctx))) return rc;           // the frame's only host synchronisation
     {   // counts come back inside the result struct
         const S2mResult& r = ctx->h_info->res;
         ctx->h_info->c[0].M = r.map_points; ctx->h_info->c[0].Q_all = r.q_all;

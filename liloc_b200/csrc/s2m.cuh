@@ -67,6 +67,8 @@ struct S2mArgs {
     int max_iters, min_sel, min_points, min_corner;
     double* partial;                     // [2][gridDim.x][kNSums]
     float pose_in[6];                    // initial guess (travels with the launch: no copy in front of the kernel)
+    unsigned* done_flag;                 // optional (mapped host memory): receives done_value after everything else is written
+    unsigned done_value;
     float* pose_io;                      // 6 floats: out = result (also in S2mResult::pose)
     const S2mState* state;               // members isDegenerate / matP before this call ...
     S2mState* state_out;                 // ... and after it (double-buffered by the host, see liloc_frame_features)
@@ -816,6 +818,10 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
         a.state_out->is_degenerate = sh.is_degenerate;
         for (int i = 0; i < 36; ++i) a.state_out->matP[i] = sh.matP[i];
         if (a.marks) a.marks[kS2mMarks - 1] = s2m_global_ns();
+        if (a.done_flag) {                   // the host polls this word instead of waiting for the kernel to retire
+            __threadfence_system();
+            *(volatile unsigned*)a.done_flag = a.done_value;
+        }
     }
 }
 

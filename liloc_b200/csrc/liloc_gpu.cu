@@ -97,6 +97,7 @@ struct HostFrameInfo {     // pinned, written by async D2H
     int dk_n;
     unsigned long long dk_marks[3];      // de-skew launch: block 0 at start / after the barrier / end
     unsigned done_seq;                   // written last by the registration kernel: sequence number of the finished frame
+    int pipe_error;                      // set by the point-cloud pipeline when a look-back wait gave up
 };
 
 }  // namespace
@@ -110,6 +111,7 @@ struct liloc_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
     std::string err;
     long long launches = 0;
+    bool pipe_failed = false;            // a pipeline launch reported a look-back time-out since the last check
     unsigned pipe_epoch = 0;             // launch counter of the point-cloud pipeline (tags its look-back words)
 
     // keyframe arena
@@ -142,6 +144,7 @@ struct liloc_ctx {
     unsigned long long* d_marks_host = nullptr;  // device alias of h_info->marks
     int* d_dk_n_host = nullptr;                  // device alias of h_info->dk_n
     unsigned* d_done_host = nullptr;             // device alias of h_info->done_seq
+    int* d_pipe_error_host = nullptr;            // device alias of h_info->pipe_error
     unsigned frame_seq = 0;                      // sequence number of the last enqueued registration
     bool poll_result = true;                     // wait for a frame by polling done_seq (LILOC_NO_POLL=1: cudaStreamSynchronize)
     int s2m_max_blocks = 0;
@@ -352,6 +355,7 @@ int pipe_launch(liloc_ctx* ctx, cudaStream_t st, PipeArgs& a, unsigned long long
     if (a.n_prob <= 0) return 0;
     a.marks = marks;
     a.epoch = ++ctx->pipe_epoch;
+    a.error_flag = ctx->d_pipe_error_host;
     a.sm_scratch = ctx->d_sm_scratch + (st == ctx->stream2 ? kSmScratch : 0);     // the two launches of a frame overlap
     void* args[] = {&a};
     const int blocks = wide ? ctx->pipe_blocks_wide : ctx->pipe_blocks;
@@ -538,6 +542,11 @@ int s2m_collect(liloc_ctx* ctx, float* pose6, liloc_s2m_result* res, const liloc
 // pick up the device-side counts after a synchronisation
 void class_collect(liloc_ctx* ctx, int cls, bool map, bool scan) {
     FeatClass& fc = ctx->fc[cls];
+    if (ctx->h_info->pipe_error) {           // sticky until read: surfaces through liloc_last_error of the next failing call
+        ctx->h_info->pipe_error = 0;
+        ctx->err = "point-cloud pipeline: a look-back wait gave up (results of this call are not valid)";
+        ctx->pipe_failed = true;
+    }
     if (map) fc.M = ctx->h_info->c[cls].M;
     if (scan) { fc.Q_all = ctx->h_info->c[cls].Q_all; fc.q_prev = fc.Q_all; }
 }
@@ -608,6 +617,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
         c->d_marks_host = dev_alias->marks;
         c->d_dk_n_host = &dev_alias->dk_n;
         c->d_done_host = &dev_alias->done_seq;
+        c->d_pipe_error_host = &dev_alias->pipe_error;
         c->d_dk_marks = dev_alias->dk_marks;
     }
     for (auto& e : c->ev) CUB_(cudaEventCreate(&e));
@@ -786,6 +796,7 @@ int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const
     if ((rc = class_fetch(ctx, cls, ctx->stream, true, false))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, true, false);
+    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
     if (M_out) *M_out = ctx->fc[cls].M;
     if (n_raw_out) *n_raw_out = ctx->fc[cls].n_raw;
     return LILOC_OK;
@@ -814,6 +825,7 @@ int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts, in
     CU(cudaStreamSynchronize(ctx->stream));
     fc.have_map = true;
     class_collect(ctx, cls, true, false);
+    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
     if (M_out) *M_out = fc.M;
     return LILOC_OK;
 }
@@ -850,6 +862,7 @@ static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n,
     if ((rc = class_fetch(ctx, cls, ctx->stream, false, true))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, false, true);
+    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
     if (on_device == LILOC_SCAN_DESKEWED) { ctx->dk_n = ctx->h_info->dk_n; ctx->fc[cls].n_scan_last = ctx->dk_n; }
     if (cls == LILOC_SURF) ctx->corner_scan_current = false;      // a new frame starts with its surf scan
     else ctx->corner_scan_current = true;
@@ -1096,6 +1109,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         if (map_launched) ctx->stats.alg_bytes_map += 16.0 * fc.n_raw + 16.0 * (fc.M > 0 ? fc.M : 0);
         ctx->stats.alg_bytes_scan += 16.0 * fc.n_scan_last + 16.0 * (fc.Q_all > 0 ? fc.Q_all : 0);
     }
+    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
     return s2m_collect(ctx, pose6, res, o);
 }
 

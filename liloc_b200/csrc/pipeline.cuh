@@ -82,6 +82,7 @@ struct PipeArgs {
     KfDesc inline_descs[kInlineDescs];
     unsigned long long* marks;   // optional: %globaltimer (ns) at every phase boundary, written by block 0 (latency breakdown)
     int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters + the sort-block counter
+    int* error_flag;             // mapped host word: set when a look-back wait gives up (the host then reports an error)
 };
 constexpr int kSmScratch = 513;
 
@@ -169,13 +170,14 @@ LILOC_DEV int block_sum_256(int v) {                        // all 256 threads; 
 LILOC_DEV void pipe_publish(unsigned long long* state, int tile, int total, unsigned epoch) {
     if (threadIdx.x == 0) atomicExch(&state[tile], ((unsigned long long)epoch << 32) | (unsigned)total);
 }
-LILOC_DEV int pipe_lookback(unsigned long long* state, int tile, int total, unsigned epoch, bool publish = true) {
+LILOC_DEV int pipe_lookback(unsigned long long* state, int tile, int total, unsigned epoch, int* error_flag, bool publish = true) {
     if (publish) pipe_publish(state, tile, total, epoch);
     int part = 0;
     for (int u = threadIdx.x; u < tile; u += kPipeThreads) {
         unsigned long long w;
         int spins = 0;
         do { w = *((volatile unsigned long long*)&state[u]); } while ((unsigned)(w >> 32) != epoch && ++spins < (1 << 22));
+        if ((unsigned)(w >> 32) != epoch && error_flag) *(volatile int*)error_flag = 1;      // gave up: the result is not valid
         part += (int)(unsigned)(w & 0xffffffffull);
     }
     return block_sum_256(part);
@@ -385,7 +387,7 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
 }
 
 // ---- R2: centroids (+ search-cell count) ----------------------------------------------------------------------------
-LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& sm, const unsigned epoch) {
+LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& sm, const unsigned epoch, int* error_flag) {
     const unsigned* __restrict__ skeys = q.keys[1];
     const unsigned* __restrict__ svals = q.vals[1];
     const int n = prob_n(q);
@@ -433,7 +435,7 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
         }
         int total;
         const int local_rank = block_exclusive_scan_256(c, &total);
-        const int tile_offset = pipe_lookback(q.tile_state, tile, total, epoch, !ahead);      // run heads in all earlier tiles
+        const int tile_offset = pipe_lookback(q.tile_state, tile, total, epoch, error_flag, !ahead);      // run heads in all earlier tiles
         int rank = tile_offset + local_rank;
         if (tile == n_tiles - 1 && threadIdx.x == 0) *q.count = tile_offset + total;
 #pragma unroll
@@ -497,7 +499,7 @@ LILOC_DEV void pipe_cells_count_direct(const VgProb& q, const GridParams& gp) {
 }
 
 // ---- G2, G3: cell counts -> cell_start (one pass, look-back across tiles), points sorted by cell -----------------------------------------------------------
-LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsigned epoch) {
+LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsigned epoch, int* error_flag) {
     const int n = gp.ncells;
     const int n_tiles = (n + kScanTile - 1) / kScanTile;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -508,7 +510,7 @@ LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsi
         for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? q.cell_counts[base + j] : 0; c += v[j]; }
         int total;
         const int local = block_exclusive_scan_256(c, &total);
-        int run = pipe_lookback(q.grid_state, tile, total, epoch) + local;
+        int run = pipe_lookback(q.grid_state, tile, total, epoch, error_flag) + local;
 #pragma unroll
         for (int j = 0; j < kScanPerThread; ++j) {
             if (base + j < n) { q.cell_start[base + j] = run; q.cell_counts[base + j] = run; }
@@ -590,12 +592,12 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     PIPE_MARK();                                                                          // 4 (kept for the layout of the marks)
     for (int p = 0; p < np; ++p) {                                                        // R2 (R1, a counting phase, is folded into it)
         if (a.prob[p].grid_only) pipe_cells_count_direct(a.prob[p], s_gp[p]);
-        else if (!a.prob[p].sort_only) pipe_centroids(a.prob[p], s_gp[p], sm, a.epoch);
+        else if (!a.prob[p].sort_only) pipe_centroids(a.prob[p], s_gp[p], sm, a.epoch, a.error_flag);
     }
     if (!any_grid) { PIPE_MARK(); return; }                                               // 5 (block 0's own end)
     grid.sync();
     PIPE_MARK();                                                                          // 5 after the centroids
-    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scan(a.prob[p], s_gp[p], a.epoch);   // G2
+    for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scan(a.prob[p], s_gp[p], a.epoch, a.error_flag);   // G2
     grid.sync();
     PIPE_MARK();                                                                          // 6 after the cell scan
     for (int p = 0; p < np; ++p) if (a.prob[p].build_grid) pipe_cells_scatter(a.prob[p], s_gp[p]);   // G3

@@ -635,7 +635,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deskew, kDeskewThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_deskew cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->dk_blocks_per_sm = per_sm >= 2 ? 2 : 1;
-    CUB_(cudaMalloc(&c->d_ndt_counters, 3 * sizeof(int)));
+    CUB_(cudaMalloc(&c->d_ndt_counters, 4 * sizeof(int)));
     CUB_(cudaMalloc(&c->d_ndt_ns, 3 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_sm_scratch, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMemset(c->d_sm_scratch, 0, 2 * kSmScratch * sizeof(int)));
@@ -1572,6 +1572,7 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
         else if (resolution != ti->second.resolution) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: all targets of one batch must share the resolution");
         std::memset(&hj[j], 0, sizeof(NdtJob));
         hj[j].target = ti->second.slot; hj[j].source = si->second.slot;
+        hj[j].n_tiles = (si->second.view.n + kNdtTile - 1) / kNdtTile;
         std::memcpy(hj[j].guess, jobs[j].guess, 12 * sizeof(float));     // top 3 rows of the row-major 4x4
         if (si->second.view.n > max_n) max_n = si->second.view.n;
     }

@@ -55,6 +55,7 @@ struct NdtJob {
     float Tfinal[12];
     float guess[12];
     int total_iterations, total_sweeps;
+    int n_tiles, pad_;            // ceil(source points / kNdtTile), set by the host
 };
 
 constexpr int kNdtThreads = 256;
@@ -127,11 +128,15 @@ __host__ __device__ inline void jacobi6_d(double (&A)[6][6], double (&U)[6][6]) 
 }
 
 // ---- pose algebra at the 4x4 boundary (same operation order as the oracle) ------------------------------
+__host__ __device__ inline void ndt_matrix_from_sincos(const double* p, float ca, float sa, float cb, float sb, float cc, float sc, float* T);
 __host__ __device__ inline void ndt_pose_to_matrix(const double* p, float* T) {
     const float a = (float)p[3], b = (float)p[4], c = (float)p[5];
     const float ca = (float)cos((double)a), sa = (float)sin((double)a);
     const float cb = (float)cos((double)b), sb = (float)sin((double)b);
     const float cc = (float)cos((double)c), sc = (float)sin((double)c);
+    ndt_matrix_from_sincos(p, ca, sa, cb, sb, cc, sc, T);
+}
+__host__ __device__ inline void ndt_matrix_from_sincos(const double* p, float ca, float sa, float cb, float sb, float cc, float sc, float* T) {
     const float Rx[9] = {1, 0, 0, 0, ca, -sa, 0, sa, ca}, Ry[9] = {cb, 0, sb, 0, 1, 0, -sb, 0, cb}, Rz[9] = {cc, -sc, 0, sc, cc, 0, 0, 0, 1};
     float M[9], R[9];
 #pragma unroll
@@ -163,11 +168,15 @@ __host__ __device__ inline void ndt_matrix_to_pose(const float* T, double* p) {
 
 struct NdtAng { float j[8][3]; float h[15][3]; };
 
+__host__ __device__ inline void ndt_angles_from_sincos(double cx, double sx, double cy, double sy, double cz, double sz, NdtAng* A);
 __host__ __device__ inline void ndt_angle_derivatives(const double* p, NdtAng* A) {
     double cx, cy, cz, sx, sy, sz;
     if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
     if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
     if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
+    ndt_angles_from_sincos(cx, sx, cy, sy, cz, sz, A);
+}
+__host__ __device__ inline void ndt_angles_from_sincos(double cx, double sx, double cy, double sy, double cz, double sz, NdtAng* A) {
     const double J[8][3] = {
         {-sx * sz + cx * sy * cz, -sx * cz - cx * sy * sz, -cx * cy}, {cx * sz + sx * sy * cz, cx * cz - sx * sy * sz, -sx * cy},
         {-sy * cz, sy * sz, cy}, {sx * cy * cz, -sx * cy * sz, sx * sy}, {-cx * cy * cz, cx * cy * sz, -cx * sy},
@@ -344,6 +353,32 @@ LILOC_DEV void ndt_point_cell(const float (&x)[3], const float (&xt)[3], const N
 struct NdtPoseCache { float T[12]; NdtAng ang; };
 constexpr int kNdtPoseFloats = sizeof(NdtPoseCache) / sizeof(float);
 LILOC_DEV void ndt_pose_cache_fill(const double* x_t, NdtPoseCache* pc) { ndt_pose_to_matrix(x_t, pc->T); ndt_angle_derivatives(x_t, &pc->ang); }
+
+// The same by a whole warp: the twelve double sin / cos evaluations (six for the float transform, six for the
+// angle-derivative tables) are what the serial version spends its time on; lanes 0..5 do one angle each -- lanes 0..2 the
+// float-rounded angles of ndt_pose_to_matrix, lanes 3..5 the double angles of ndt_angle_derivatives with its small-angle
+// rule -- and lane 0 assembles the tables from the shuffled results.  Same values as ndt_pose_cache_fill.
+LILOC_DEV void ndt_pose_cache_fill_warp(const double* x_t_lane0, bool go, NdtPoseCache* pc) {
+    const int lane = threadIdx.x & 31;
+    double x[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = __shfl_sync(0xffffffffu, go ? x_t_lane0[i] : 0.0, 0);
+    double c = 1.0, s = 0.0;
+    if (lane < 3) {
+        const double ang = (double)(float)(lane == 0 ? x[3] : lane == 1 ? x[4] : x[5]);
+        c = cos(ang); s = sin(ang);
+    } else if (lane < 6) {
+        const double ang = lane == 3 ? x[3] : lane == 4 ? x[4] : x[5];
+        if (!(fabs(ang) < 10e-5)) { c = cos(ang); s = sin(ang); }
+    }
+    double cs[6], sn[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { cs[i] = __shfl_sync(0xffffffffu, c, i); sn[i] = __shfl_sync(0xffffffffu, s, i); }
+    if (lane == 0 && go) {
+        ndt_matrix_from_sincos(x, (float)cs[0], (float)sn[0], (float)cs[1], (float)sn[1], (float)cs[2], (float)sn[2], pc->T);
+        ndt_angles_from_sincos(cs[3], sn[3], cs[4], sn[4], cs[5], sn[5], &pc->ang);
+    }
+}
 
 constexpr int kNdtWarpCap = 256;          // per-warp ring of gathered (point, leaf) hits: < 32 left over + 32 * 7 new per round
 struct NdtSweepShared {
@@ -732,10 +767,11 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
         ndt_pose_cache_fill(J.x_t, &a.pose[j]);
         a.active[j] = j;
     }
-    if (gtid == 0) { a.counters[0] = a.n_jobs; a.counters[1] = 0; a.counters[2] = 0; }
+    if (gtid == 0) { a.counters[0] = a.n_jobs; a.counters[1] = 0; a.counters[2] = 0; a.counters[3] = 0; }
     grid.sync();
     unsigned long long sweep_ns = 0, update_ns = 0, compact_ns = 0;
     int cur = 0;
+    int fin_seen = 0;                                       // finished jobs at the last compaction
     for (int it = 0; it < a.max_sweeps; ++it) {
         const int n_active = *((volatile int*)&a.counters[cur]);
         if (n_active == 0) break;
@@ -760,7 +796,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
         for (int k = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; k < n_active; k += nwarps) {
             const int job = act[k];
             NdtJob& J = a.jobs[job];
-            const int n_tiles = (a.sources[J.source].n + kNdtTile - 1) / kNdtTile;
+            const int n_tiles = J.n_tiles;
             double v = 0.0;
             if (lane < kNdtSums) {
                 const double* pj = a.partial + (size_t)job * a.tiles_max * kNdtSums + lane;
@@ -781,6 +817,8 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
                 lo = __shfl_sync(0xffffffffu, lo, q); hi = __shfl_sync(0xffffffffu, hi, q);
                 sums[q] = __hiloint2double(hi, lo);
             }
+            double xt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            bool go = false;
             if (lane == 0) {
                 // The state machine touches dozens of fields in dependent order: run it on a local copy (one batch of
                 // loads, one of stores) instead of paying an L2 round trip per field.
@@ -796,12 +834,23 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
                         L.align_pass = pass;
                     }
                 }
-                if (L.phase != NDT_DONE) ndt_pose_cache_fill(L.x_t, &a.pose[job]);
+                go = L.phase != NDT_DONE;
+                if (!go) atomicAdd(&a.counters[3], 1);         // the job leaves the active list: a compaction is due
+#pragma unroll
+                for (int i = 0; i < 6; ++i) xt[i] = L.x_t[i];
                 J = L;
             }
+            __syncwarp();
+            ndt_pose_cache_fill_warp(xt, go, &a.pose[job]);   // the next sweep's transform and angle tables, six lanes for the sin / cos
         }
+        if (gtid == 0) a.counters[2] = it + 1;
         grid.sync();
         if (a.sweep_ns && gtid == 0) { const unsigned long long t1 = global_ns(); update_ns += t1 - t0; t0 = t1; }
+        // Nothing to compact while no job has finished (most rounds): the list, its length and `cur` stay as they are and
+        // the round ends here -- one barrier and ~3 us less.
+        const int fin = *((volatile int*)&a.counters[3]);
+        if (fin == fin_seen) continue;
+        fin_seen = fin;
         // ---- compaction of the active list (block 0).  The order is preserved: neighbouring work items then stay
         // neighbouring jobs (same submap, same scan -> shared L2 lines).  Appending with an atomic cursor from the update
         // phase saves this phase and its barrier (~3 us per round) but scrambles the list: measured 7 % slower on the

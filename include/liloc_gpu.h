@@ -130,14 +130,20 @@ typedef struct {
     int imu_available;                                         /* cloudInfo.imuAvailable (:495) */
     float lidar_min_range, lidar_max_range;                    /* [1.0, 1000.0] include/utility.h:257-258 */
     int n_scan, downsample_rate, point_filter_num;             /* N_SCAN, [1], [3] include/utility.h:254-255 */
-    int reserved[2];
+    int reserved[2];                                           /* [0]: 0, or LILOC_DESKEW_AHEAD */
 } liloc_deskew_params;
 #define LILOC_SCAN_HOST 0
 #define LILOC_SCAN_DEVICE 1
 #define LILOC_SCAN_DESKEWED 2
+/* params->reserved[0] = LILOC_DESKEW_AHEAD: the sweep is de-skewed into a second slot and stays STAGED while
+ * LILOC_SCAN_DESKEWED keeps referring to the current sweep; liloc_deskew_advance() makes the staged sweep current.
+ * Lets the next sweep upload and de-skew (on a stream of its own) while the current frame runs -- the reference's
+ * imageProjection node is two sweeps ahead of mapOptimization too (cloudQueue, :271-276). */
+#define LILOC_DESKEW_AHEAD 1
 /* n_out may be NULL: then nothing is synchronised and the count stays on the device. */
 int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* ring_time, int n,
                  const liloc_deskew_params* params, int* n_out);
+int liloc_deskew_advance(liloc_ctx* ctx);
 int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out);   /* fullCloud, for publishClouds (:675-679) */
 int liloc_last_deskew_marks(liloc_ctx* ctx, unsigned long long* out3);            /* ns: block 0 at start / after the barrier / end */
 int liloc_last_deskew_ms(liloc_ctx* ctx, float* ms);                             /* device time of the last de-skew launch (liloc_set_timing) */

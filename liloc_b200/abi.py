@@ -100,6 +100,7 @@ class DeskewParams(C.Structure):
 
 RING_TIME = np.dtype([("ring", np.int32), ("time", np.float32)])
 SCAN_HOST, SCAN_DEVICE, SCAN_DESKEWED = 0, 1, 2
+DESKEW_AHEAD = 1
 
 
 class NdtOpts(C.Structure):
@@ -149,6 +150,7 @@ def _load() -> C.CDLL:
         "liloc_keyframe_size": (C.c_int, [P, C.c_int]),
         "liloc_deskew": (C.c_int, [P, P, P, C.c_int, C.POINTER(DeskewParams), ip]),
         "liloc_deskewed_get": (C.c_int, [P, P, C.c_int, ip]),
+        "liloc_deskew_advance": (C.c_int, [P]),
         "liloc_last_deskew_ms": (C.c_int, [P, fp]),
         "liloc_last_deskew_marks": (C.c_int, [P, P]),
         "liloc_keyframe_clear": (C.c_int, [P]),
@@ -219,7 +221,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance").split()
 
 
 def _cloud(a) -> np.ndarray:
@@ -337,7 +339,7 @@ class Context:
     # ---- de-skew (imageProjection::projectPointCloud) ----
     def deskew(self, pts, ring, time, imu_time=None, imu_rot=None, time_scan_cur: float = 0.0, deskew_flag: int = 1,
                imu_available: bool = True, min_range: float = 1.0, max_range: float = 1000.0, n_scan: int = 16,
-               downsample_rate: int = 1, point_filter_num: int = 3, sync: bool = True) -> int | None:
+               downsample_rate: int = 1, point_filter_num: int = 3, sync: bool = True, ahead: bool = False) -> int | None:
         """liloc_deskew.  imu_time: (m,) float64, imu_rot: (m, 3) float64 integrated angles (imuRotX/Y/Z); the last valid
         index is m - 1.  Returns the size of the de-skewed cloud (None with sync=False: it stays on the device)."""
         p = _cloud(pts)
@@ -358,9 +360,14 @@ class Context:
         dp.deskew_flag, dp.imu_available = int(deskew_flag), int(bool(imu_available))
         dp.lidar_min_range, dp.lidar_max_range = float(min_range), float(max_range)
         dp.n_scan, dp.downsample_rate, dp.point_filter_num = int(n_scan), int(downsample_rate), int(point_filter_num)
+        dp.reserved[0] = DESKEW_AHEAD if ahead else 0
         n = C.c_int()
         self._chk(lib.liloc_deskew(self._h, _ptr(p), _ptr(rt), len(p), C.byref(dp), C.byref(n) if sync else None))
         return n.value if sync else None
+
+    def deskew_advance(self) -> None:
+        """The sweep staged with ahead=True becomes the current one."""
+        self._chk(lib.liloc_deskew_advance(self._h))
 
     def deskewed_get(self) -> np.ndarray:
         n = C.c_int()

@@ -94,7 +94,7 @@ struct HostFrameInfo {     // pinned, written by async D2H
     S2mResult res;
     unsigned long long marks[2 * kPipeMarks + kS2mMarks];
     int scratch;
-    int dk_n;
+    int dk_n[2];                         // de-skewed points of the two sweep slots
     unsigned long long dk_marks[3];      // de-skew launch: block 0 at start / after the barrier / end
     unsigned done_seq;                   // written last by the registration kernel: sequence number of the finished frame
     int pipe_error;                      // set by the point-cloud pipeline when a look-back wait gave up
@@ -142,7 +142,6 @@ struct liloc_ctx {
     S2mResult* d_result = nullptr;
     S2mResult* d_result_host = nullptr;          // device alias of h_info->res (mapped pinned memory)
     unsigned long long* d_marks_host = nullptr;  // device alias of h_info->marks
-    int* d_dk_n_host = nullptr;                  // device alias of h_info->dk_n
     unsigned* d_done_host = nullptr;             // device alias of h_info->done_seq
     int* d_pipe_error_host = nullptr;            // device alias of h_info->pipe_error
     unsigned frame_seq = 0;                      // sequence number of the last enqueued registration
@@ -174,7 +173,18 @@ struct liloc_ctx {
     unsigned long long* d_ndt_ns = nullptr;
     int ndt_max_blocks = 0;
 
-    // de-skew (imageProjection): raw sweep in, de-skewed cloud out into fc[0].scan_raw
+    // de-skew (imageProjection): raw sweep in, de-skewed cloud out.  Two output slots: the current sweep (what
+    // LILOC_SCAN_DESKEWED refers to) and one staged ahead of it (LILOC_DESKEW_AHEAD), so that the next sweep can be uploaded
+    // and de-skewed on stream3 while the current frame runs.
+    struct DkSweep {
+        DevBuf<float4> out;
+        int* d_n = nullptr;              // device count
+        int* d_n_host = nullptr;         // device alias of h_info->dk_n[slot]
+        int n_upper = -1;                // raw points of the sweep (-1: empty slot)
+        int n = -1;                      // host copy of the count, -1 while unknown
+        cudaEvent_t ev_done = nullptr;   // recorded behind the de-skew launch
+    } dk[2];
+    int dk_cur = -1, dk_staged = -1;
     DevBuf<float4> dk_pts;
     DevBuf<int2> dk_rt;
     DevBuf<int> dk_tiles;
@@ -182,12 +192,9 @@ struct liloc_ctx {
     double* h_dk_imu = nullptr;          // pinned staging of the same, two slots
     int dk_slot = 0;
     cudaEvent_t ev_dk_slot[2]{};
-    int* d_dk_n = nullptr;               // points of the de-skewed cloud
+    cudaEvent_t ev_dk_fork2 = nullptr;
     unsigned long long* d_dk_marks = nullptr;   // device alias of h_info->dk_marks (timing)
     int dk_blocks_per_sm = 1;
-    int dk_n_upper = -1;                 // raw points of the last sweep (-1: no de-skewed cloud)
-    int dk_n = -1;                       // host copy of *d_dk_n, -1 while unknown
-    cudaEvent_t ev_deskew = nullptr;
     float dk_ms = 0.f;
 
     // kernel-level test scratch
@@ -431,11 +438,12 @@ int scan_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pt
     const int* n_dev = nullptr;
     if (mode == LILOC_SCAN_DESKEWED) {
         if (cls != LILOC_SURF) return fail(ctx, LILOC_ERR_ARG, "scan_put: the de-skewed sweep is the surf-class scan");
-        if (ctx->dk_n_upper < 0) return fail(ctx, LILOC_ERR_STATE, "scan_put: no de-skewed sweep (call liloc_deskew first)");
-        pts = reinterpret_cast<const liloc_point*>(fc.scan_raw.p);
-        n = ctx->dk_n >= 0 ? ctx->dk_n : ctx->dk_n_upper;
-        if (ctx->dk_n < 0) n_dev = ctx->d_dk_n;
-        CU(cudaStreamWaitEvent(st, ctx->ev_deskew, 0));
+        if (ctx->dk_cur < 0) return fail(ctx, LILOC_ERR_STATE, "scan_put: no de-skewed sweep (call liloc_deskew first)");
+        liloc_ctx::DkSweep& S = ctx->dk[ctx->dk_cur];
+        pts = reinterpret_cast<const liloc_point*>(S.out.p);
+        n = S.n >= 0 ? S.n : S.n_upper;
+        if (S.n < 0) n_dev = S.d_n;
+        CU(cudaStreamWaitEvent(st, S.ev_done, 0));
     } else if (mode != LILOC_SCAN_HOST && mode != LILOC_SCAN_DEVICE) {
         return fail(ctx, LILOC_ERR_ARG, "scan_put: bad scan_on_device %d", mode);
     }
@@ -448,7 +456,6 @@ int scan_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pt
         CU(cudaMemcpyAsync(fc.scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += (long long)n * (long long)sizeof(float4);
         src = fc.scan_raw.p;
-        if (cls == LILOC_SURF) ctx->dk_n_upper = -1;          // the de-skewed sweep lived in this buffer
     }
     fc.scan_src_last = src; fc.scan_leaf_last = leaf;
     if ((rc = prob_voxelgrid(ctx, fc.vg_scan, src, n, leaf, &fc.scan, q))) return rc;
@@ -615,7 +622,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
         CUB_(cudaHostGetDevicePointer(&dev_alias, c->h_info, 0));
         c->d_result_host = &dev_alias->res;
         c->d_marks_host = dev_alias->marks;
-        c->d_dk_n_host = &dev_alias->dk_n;
+        for (int k = 0; k < 2; ++k) c->dk[k].d_n_host = &dev_alias->dk_n[k];
         c->d_done_host = &dev_alias->done_seq;
         c->d_pipe_error_host = &dev_alias->pipe_error;
         c->d_dk_marks = dev_alias->dk_marks;
@@ -642,9 +649,12 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaMalloc(&c->d_dk_imu, 4 * kImuMax * sizeof(double)));
     CUB_(cudaMallocHost(&c->h_dk_imu, 2 * 4 * kImuMax * sizeof(double)));
     for (auto& e : c->ev_dk_slot) CUB_(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUB_(cudaMalloc(&c->d_dk_n, sizeof(int)));
-    CUB_(cudaMemset(c->d_dk_n, 0, sizeof(int)));
-    CUB_(cudaEventCreateWithFlags(&c->ev_deskew, cudaEventDisableTiming));
+    for (auto& S : c->dk) {
+        CUB_(cudaMalloc(&S.d_n, sizeof(int)));
+        CUB_(cudaMemset(S.d_n, 0, sizeof(int)));
+        CUB_(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    }
+    CUB_(cudaEventCreateWithFlags(&c->ev_dk_fork2, cudaEventDisableTiming));
     CUB_(cudaMalloc(&c->d_marks, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
     CUB_(cudaMemset(c->d_marks, 0, (2 * kPipeMarks + kS2mMarks) * sizeof(unsigned long long)));
 #undef CUB_
@@ -686,9 +696,10 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
     fr(c->d_marks); fr(c->d_sm_scratch);
-    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu); fr(c->d_dk_n);
+    fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu);
+    for (auto& S : c->dk) { fr(S.out.p); fr(S.d_n); if (S.ev_done) cudaEventDestroy(S.ev_done); }
+    if (c->ev_dk_fork2) cudaEventDestroy(c->ev_dk_fork2);
     if (c->h_dk_imu) cudaFreeHost(c->h_dk_imu);
-    if (c->ev_deskew) cudaEventDestroy(c->ev_deskew);
     for (auto& e : c->ev_dk_slot) if (e) cudaEventDestroy(e);
     fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
@@ -863,7 +874,7 @@ static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n,
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, false, true);
     if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
-    if (on_device == LILOC_SCAN_DESKEWED) { ctx->dk_n = ctx->h_info->dk_n; ctx->fc[cls].n_scan_last = ctx->dk_n; }
+    if (on_device == LILOC_SCAN_DESKEWED) { liloc_ctx::DkSweep& S = ctx->dk[ctx->dk_cur]; S.n = ctx->h_info->dk_n[ctx->dk_cur]; ctx->fc[cls].n_scan_last = S.n; }
     if (cls == LILOC_SURF) ctx->corner_scan_current = false;      // a new frame starts with its surf scan
     else ctx->corner_scan_current = true;
     if (Q_all_out) *Q_all_out = ctx->fc[cls].Q_all;
@@ -893,8 +904,10 @@ int liloc_scan_ds_get_class(liloc_ctx* ctx, int cls, liloc_point* out, int cap, 
 int liloc_scan_ds_get(liloc_ctx* ctx, liloc_point* out, int cap, int* Q_all_out) { return liloc_scan_ds_get_class(ctx, LILOC_SURF, out, cap, Q_all_out); }
 
 // ---- de-skew (imageProjection::projectPointCloud, src/imageProjection.cpp:645-673) ---------------------------------
-// Runs on stream2 (the scan branch of a fused frame): H2D of the raw sweep and of the IMU arrays, one cooperative
-// launch, the count back into pinned memory.  Nothing is synchronised unless the caller asks for the count.
+// Runs on stream3, a stream of its own: H2D of the raw sweep and of the IMU arrays, one cooperative launch, the count
+// into mapped host memory.  Nothing is synchronised unless the caller asks for the count.  The result goes into the sweep
+// slot that is not the current one and becomes the current sweep at once -- or, with LILOC_DESKEW_AHEAD, stays staged
+// until liloc_deskew_advance: the next sweep is then uploaded and de-skewed while the current frame runs.
 int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* ring_time, int n, const liloc_deskew_params* p, int* n_out) {
     ENTER(ctx);
     if (n < 0 || (n > 0 && (!pts || !ring_time)) || !p) return fail(ctx, LILOC_ERR_ARG, "deskew: bad arguments");
@@ -902,15 +915,19 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     const bool deskew = p->deskew_flag != -1 && p->imu_available != 0;
     if (deskew && (p->imu_pointer_cur < 0 || p->imu_pointer_cur >= kImuMax || !p->imu_time || !p->imu_rot_x || !p->imu_rot_y || !p->imu_rot_z))
         return fail(ctx, LILOC_ERR_ARG, "deskew: bad IMU arrays (imu_pointer_cur %d, queue length %d)", p->imu_pointer_cur, kImuMax);
+    const bool ahead = p->reserved[0] == LILOC_DESKEW_AHEAD;
     int rc;
-    cudaStream_t st = ctx->stream2;
-    FeatClass& fc = ctx->fc[LILOC_SURF];
+    cudaStream_t st = ctx->stream3;
+    const int slot = ctx->dk_cur < 0 ? 0 : (ctx->dk_cur ^ 1);             // never the current sweep's slot
+    liloc_ctx::DkSweep& S = ctx->dk[slot];
     const size_t cap = (size_t)(n > 0 ? n : 1);
-    if ((rc = ensure(ctx, ctx->dk_pts, cap)) || (rc = ensure(ctx, ctx->dk_rt, cap)) || (rc = ensure(ctx, fc.scan_raw, cap)) ||
+    if ((rc = ensure(ctx, ctx->dk_pts, cap)) || (rc = ensure(ctx, ctx->dk_rt, cap)) || (rc = ensure(ctx, S.out, cap)) ||
         (rc = ensure(ctx, ctx->dk_tiles, cap / kDeskewThreads + 2))) return rc;
-    // the previous sweep's consumers (main stream) must be done with scan_raw before it is overwritten
+    // whatever was enqueued so far on the frame's streams may still read this slot (a sweep two de-skews back)
     CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CU(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+    CU(cudaEventRecord(ctx->ev_dk_fork2, ctx->stream2));
+    CU(cudaStreamWaitEvent(st, ctx->ev_dk_fork2, 0));
     if (n > 0) {
         CU(cudaMemcpyAsync(ctx->dk_pts.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->dk_rt.p, ring_time, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, st));
@@ -918,13 +935,13 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     }
     if (deskew) {
         const int m = p->imu_pointer_cur + 1;
-        const int slot = ctx->dk_slot; ctx->dk_slot ^= 1;          // two pinned staging slots, each guarded by an event
-        CU(cudaEventSynchronize(ctx->ev_dk_slot[slot]));
-        double* stage = ctx->h_dk_imu + (size_t)slot * 4 * kImuMax;
+        const int stg = ctx->dk_slot; ctx->dk_slot ^= 1;           // two pinned staging slots, each guarded by an event
+        CU(cudaEventSynchronize(ctx->ev_dk_slot[stg]));
+        double* stage = ctx->h_dk_imu + (size_t)stg * 4 * kImuMax;
         const double* src[4] = {p->imu_time, p->imu_rot_x, p->imu_rot_y, p->imu_rot_z};
         for (int k = 0; k < 4; ++k) std::memcpy(stage + (size_t)k * m, src[k], (size_t)m * sizeof(double));
         CU(cudaMemcpyAsync(ctx->d_dk_imu, stage, (size_t)4 * m * sizeof(double), cudaMemcpyHostToDevice, st));      // one copy: 4 arrays of m
-        CU(cudaEventRecord(ctx->ev_dk_slot[slot], st));
+        CU(cudaEventRecord(ctx->ev_dk_slot[stg], st));
         ctx->stats.h2d_bytes += (long long)m * 32;
     }
     DeskewArgs a{};
@@ -932,31 +949,47 @@ int liloc_deskew(liloc_ctx* ctx, const liloc_point* pts, const liloc_ring_time* 
     a.imu = ctx->d_dk_imu; a.imu_stride = p->imu_pointer_cur + 1; a.imu_last = p->imu_pointer_cur; a.t_cur = p->time_scan_cur; a.deskew = deskew ? 1 : 0;
     a.rmin = p->lidar_min_range; a.rmax = p->lidar_max_range;
     a.n_scan = p->n_scan; a.ds_rate = p->downsample_rate; a.pf_num = p->point_filter_num;
-    a.tile_count = ctx->dk_tiles.p; a.out = fc.scan_raw.p; a.n_out = ctx->d_dk_n; a.n_out_host = ctx->d_dk_n_host;
+    a.tile_count = ctx->dk_tiles.p; a.out = S.out.p; a.n_out = S.d_n; a.n_out_host = S.d_n_host;
     const int n_tiles = (n + kDeskewThreads - 1) / kDeskewThreads;
-    const int max_blocks = ctx->num_sms * ctx->dk_blocks_per_sm;
+    // a sweep staged ahead shares the GPU with the current frame's launches: one block per SM leaves them room
+    const int max_blocks = ctx->num_sms * (ahead ? 1 : ctx->dk_blocks_per_sm);
     const int blocks = n_tiles < 1 ? 1 : (n_tiles < max_blocks ? n_tiles : max_blocks);
     a.marks = ctx->timing ? ctx->d_dk_marks : nullptr;
     void* args[] = {&a};
     CU(cudaLaunchCooperativeKernel((void*)k_deskew, dim3((unsigned)blocks), dim3(kDeskewThreads), args, 0, st));
     ++ctx->launches;
     ctx->stats.d2h_bytes += 4;                                   // the count, written by the kernel into mapped host memory
-    CU(cudaEventRecord(ctx->ev_deskew, st));
-    ctx->dk_n_upper = n; ctx->dk_n = -1;
-    fc.have_scan = false; fc.Q_all = -1;
+    CU(cudaEventRecord(S.ev_done, st));
+    S.n_upper = n; S.n = -1;
+    if (ahead) {
+        ctx->dk_staged = slot;
+    } else {
+        ctx->dk_cur = slot; ctx->dk_staged = -1;
+        ctx->fc[LILOC_SURF].have_scan = false; ctx->fc[LILOC_SURF].Q_all = -1;
+    }
     if (n_out) {
         CU(cudaStreamSynchronize(st));
-        ctx->dk_n = ctx->h_info->dk_n;
-        *n_out = ctx->dk_n;
+        S.n = ctx->h_info->dk_n[slot];
+        *n_out = S.n;
     }
     return LILOC_OK;
 }
 
-static int deskew_count(liloc_ctx* ctx) {          // host copy of the de-skewed cloud's size (synchronises when still unknown)
-    if (ctx->dk_n_upper < 0) return fail(ctx, LILOC_ERR_STATE, "no de-skewed sweep (call liloc_deskew first)");
-    if (ctx->dk_n < 0) {
-        CU(cudaStreamSynchronize(ctx->stream2));
-        ctx->dk_n = ctx->h_info->dk_n;
+// The sweep staged by a LILOC_DESKEW_AHEAD call becomes the current one.
+int liloc_deskew_advance(liloc_ctx* ctx) {
+    ENTER(ctx);
+    if (ctx->dk_staged < 0) return fail(ctx, LILOC_ERR_STATE, "deskew_advance: no sweep staged ahead");
+    ctx->dk_cur = ctx->dk_staged; ctx->dk_staged = -1;
+    ctx->fc[LILOC_SURF].have_scan = false; ctx->fc[LILOC_SURF].Q_all = -1;
+    return LILOC_OK;
+}
+
+static int deskew_count(liloc_ctx* ctx) {          // host copy of the current sweep's size (synchronises when still unknown)
+    if (ctx->dk_cur < 0) return fail(ctx, LILOC_ERR_STATE, "no de-skewed sweep (call liloc_deskew first)");
+    liloc_ctx::DkSweep& S = ctx->dk[ctx->dk_cur];
+    if (S.n < 0) {
+        CU(cudaEventSynchronize(S.ev_done));
+        S.n = ctx->h_info->dk_n[ctx->dk_cur];
     }
     return 0;
 }
@@ -965,12 +998,13 @@ int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out) {
     ENTER(ctx);
     int rc;
     if ((rc = deskew_count(ctx))) return rc;
-    if (n_out) *n_out = ctx->dk_n;
+    const liloc_ctx::DkSweep& S = ctx->dk[ctx->dk_cur];
+    if (n_out) *n_out = S.n;
     if (out) {
-        if (cap < ctx->dk_n) return fail(ctx, LILOC_ERR_CAPACITY, "deskewed_get: cap %d < n %d", cap, ctx->dk_n);
-        if (ctx->dk_n > 0) CU(cudaMemcpyAsync(out, ctx->fc[LILOC_SURF].scan_raw.p, (size_t)ctx->dk_n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream2));
-        CU(cudaStreamSynchronize(ctx->stream2));
-        ctx->stats.d2h_bytes += (long long)ctx->dk_n * 16;
+        if (cap < S.n) return fail(ctx, LILOC_ERR_CAPACITY, "deskewed_get: cap %d < n %d", cap, S.n);
+        CU(cudaEventSynchronize(S.ev_done));
+        if (S.n > 0) CU(cudaMemcpy(out, S.out.p, (size_t)S.n * sizeof(float4), cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += (long long)S.n * 16;
     }
     return LILOC_OK;
 }
@@ -979,7 +1013,7 @@ int liloc_deskewed_get(liloc_ctx* ctx, liloc_point* out, int cap, int* n_out) {
 int liloc_last_deskew_marks(liloc_ctx* ctx, unsigned long long* out3) {
     ENTER(ctx);
     if (!out3) return fail(ctx, LILOC_ERR_ARG, "last_deskew_marks: null");
-    CU(cudaStreamSynchronize(ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->stream3));
     std::memcpy(out3, ctx->h_info->dk_marks, 3 * sizeof(unsigned long long));
     return LILOC_OK;
 }
@@ -987,8 +1021,8 @@ int liloc_last_deskew_marks(liloc_ctx* ctx, unsigned long long* out3) {
 int liloc_last_deskew_ms(liloc_ctx* ctx, float* ms) {
     ENTER(ctx);
     if (!ms) return fail(ctx, LILOC_ERR_ARG, "last_deskew_ms: null");
-    if (ctx->timing && ctx->dk_n_upper >= 0) {                   // in-kernel duration (block 0, %globaltimer)
-        CU(cudaStreamSynchronize(ctx->stream2));
+    if (ctx->timing && (ctx->dk_cur >= 0 || ctx->dk_staged >= 0)) {      // in-kernel duration (block 0, %globaltimer)
+        CU(cudaStreamSynchronize(ctx->stream3));
         const unsigned long long* mk = ctx->h_info->dk_marks;
         ctx->dk_ms = mk[2] > mk[0] ? (float)((double)(mk[2] - mk[0]) * 1e-6) : 0.f;
     }
@@ -1083,7 +1117,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         ctx->h_info->c[1].M = r.extra[1];   ctx->h_info->c[1].Q_all = r.extra[0];
     }
     for (int cls = 0; cls < (corner ? 2 : 1); ++cls) class_collect(ctx, cls, true, true);
-    if (dev == LILOC_SCAN_DESKEWED) { ctx->dk_n = ctx->h_info->dk_n; ctx->fc[LILOC_SURF].n_scan_last = ctx->dk_n; }
+    if (dev == LILOC_SCAN_DESKEWED) { liloc_ctx::DkSweep& S = ctx->dk[ctx->dk_cur]; S.n = ctx->h_info->dk_n[ctx->dk_cur]; ctx->fc[LILOC_SURF].n_scan_last = S.n; }
     ctx->corner_scan_current = corner;
     if (ctx->timing) {
         liloc_timing& t = ctx->last_timing;
@@ -1525,9 +1559,9 @@ int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts, 
     if (on_device == LILOC_SCAN_DESKEWED) {          // the de-skewed sweep this context holds (setInputSource(laserCloudSurfLast), :274)
         int rc;
         if ((rc = deskew_count(ctx))) return rc;
-        pts = reinterpret_cast<const liloc_point*>(ctx->fc[LILOC_SURF].scan_raw.p);
-        n = ctx->dk_n;
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_deskew, 0));
+        pts = reinterpret_cast<const liloc_point*>(ctx->dk[ctx->dk_cur].out.p);
+        n = ctx->dk[ctx->dk_cur].n;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->dk[ctx->dk_cur].ev_done, 0));
     }
     if (n <= 0 || !pts) return fail(ctx, LILOC_ERR_ARG, "ndt_source_put: bad arguments");
     liloc_ctx::NdtSourceHost& S = ctx->ndt_sources[source_id];

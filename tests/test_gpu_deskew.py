@@ -239,3 +239,41 @@ def test_livox_custom_msg_path(orc, synth):
         got = ctx.deskewed_get()
         assert len(ref) > 1000 and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
         ctx.close(); ip.close()
+
+
+def test_sweep_staged_ahead_of_the_current_frame(gpu_ctx, orc, synth, scene_small):
+    """LILOC_DESKEW_AHEAD: the next sweep is uploaded and de-skewed (on a stream of its own) while LILOC_SCAN_DESKEWED still
+    refers to the current one; liloc_deskew_advance swaps.  Frames pipelined this way equal the sequential ones."""
+    s = scene_small
+    gpu_ctx.keyframe_clear()
+    for k, c in enumerate(s.kf_clouds):
+        gpu_ctx.keyframe_put(k, c)
+    ids = list(range(len(s.kf_clouds)))
+    sweeps = []
+    for f in range(4):
+        sw = synth.raw_sweep(s.scan_raw, s.sensor, gyro=(0.05 * f, 0.02, 0.3 - 0.2 * f), seed=40 + f)
+        t, r = orc.imu_integrate(sw["imu_stamps"], sw["imu_gyro"], sw["time_scan_end"])
+        sweeps.append((sw, t, r))
+    kw = dict(n_scan=16, point_filter_num=1, min_range=1.0)
+
+    def dk(i, **extra):
+        sw, t, r = sweeps[i]
+        return gpu_ctx.deskew(sw["pts"], sw["ring"], sw["time"], t, r, sw["time_scan_cur"], sync=False, **kw, **extra)
+    seq = []
+    for i in range(4):                                   # sequential: de-skew, then the frame
+        dk(i)
+        seq.append(gpu_ctx.frame(ids, s.kf_poses, s.map_leaf, None, s.scan_leaf, s.guess))
+    with pytest.raises(Exception):
+        gpu_ctx.deskew_advance()                         # nothing staged
+    dk(0)
+    for i in range(4):                                   # pipelined: sweep i + 1 is staged while frame i runs
+        if i + 1 < 4:
+            dk(i + 1, ahead=True)
+        pose, res, rc = gpu_ctx.frame(ids, s.kf_poses, s.map_leaf, None, s.scan_leaf, s.guess)
+        assert rc == 0 and np.array_equal(pose, seq[i][0]) and (res.iters, res.n_sel, res.q_all) == (seq[i][1].iters, seq[i][1].n_sel, seq[i][1].q_all), i
+        sw, t, r = sweeps[i]
+        ref = orc.deskew(sw["pts"], sw["ring"], sw["time"], t, r, sw["time_scan_cur"], **kw)
+        assert np.array_equal(gpu_ctx.deskewed_get().view(np.uint32), ref.view(np.uint32))      # still the current sweep
+        if i + 1 < 4:
+            gpu_ctx.deskew_advance()
+    assert len({tuple(p[0]) for p in seq}) > 1           # the four sweeps really differ

@@ -59,7 +59,7 @@ LILOC_DEV void top5_insert(Knn5& t, float d, int i) {
 
 // Exact 5-NN by a group of L lanes (L = 1, 2, 4, 8 ...; groups are aligned inside a warp, and ALL 32 lanes of
 // the warp must call this together -- lanes without a query pass active = false).  Lane `sub` of the group
-// scans every L-th point of the 9 cell rows with its own sorted top-5 in registers; the L lists are then
+// scans every L-th candidate of the 9 cell rows (taken as one sequence) with its own sorted top-5 in registers; the L lists are then
 // merged with five rounds of (d2, index) arg-min over xor-shuffles.  On return every lane of the group
 // holds the same result.  Far fewer instructions than one warp per query: the map is a surface, so a
 // 27-cell neighbourhood holds only ~100-250 candidates.
@@ -80,25 +80,36 @@ LILOC_DEV Knn5 knn5_group(const GridView& g, const GridParams& gp, const float4 
             re[r] = __ldg(&g.cell_start[base + x1 + 1]);
         }
     }
+    // The nine rows as ONE candidate sequence: candidate k of the query lives at cpts[k + delta[r]] for the row r with
+    // pre[r] <= k < pre[r + 1].  A lane takes candidates sub, sub + L, ... and issues nine loads per pass whatever row they
+    // fall in, so a query with ~70 candidates is done in one or two memory latencies; scanning row by row took as many
+    // passes as the longest row needs (3-4) with most loads of a pass idle.  The result does not depend on the order in
+    // which candidates are seen: the top-5 is kept in the total order (d2, index).
+    int pre[10], delta[9];
+    pre[0] = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) { pre[r + 1] = pre[r] + (re[r] - rs[r]); delta[r] = rs[r] - pre[r]; }
+    const int total = pre[9];
     Knn5 t;
 #pragma unroll
     for (int k = 0; k < 5; ++k) { t.d[k] = 3.4e38f; t.i[k] = 0x7fffffff; }
-    // Row-parallel scan: every pass issues one load per row (up to 9 independent 16-byte loads in
-    // flight per lane) before any distance is evaluated, so a pass costs one memory latency, not nine.
-    for (int k = sub;; k += L) {
+    for (int k0 = sub; k0 < total; k0 += 9 * L) {
         float4 p[9];
-        bool any = false;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            const int j = rs[r] + k;
-            if (j < re[r]) { p[r] = __ldg(&g.cpts[j]); any = true; }
+        for (int u = 0; u < 9; ++u) {
+            const int k = k0 + u * L;
+            if (k < total) {
+                int off = delta[0];
+#pragma unroll
+                for (int r = 1; r < 9; ++r) if (k >= pre[r]) off = delta[r];
+                p[u] = __ldg(&g.cpts[k + off]);
+            }
         }
-        if (!any) break;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            if (rs[r] + k < re[r]) {
-                const float d = dist2(q, p[r]);
-                if (d < 1.0f) top5_insert(t, d, __float_as_int(p[r].w));
+        for (int u = 0; u < 9; ++u) {
+            if (k0 + u * L < total) {
+                const float d = dist2(q, p[u]);
+                if (d < 1.0f) top5_insert(t, d, __float_as_int(p[u].w));
             }
         }
     }

@@ -277,3 +277,26 @@ def test_sweep_staged_ahead_of_the_current_frame(gpu_ctx, orc, synth, scene_smal
         if i + 1 < 4:
             gpu_ctx.deskew_advance()
     assert len({tuple(p[0]) for p in seq}) > 1           # the four sweeps really differ
+
+
+def test_large_sweep_several_tiles_per_block(gpu_ctx, orc):
+    """A 128-beam sweep (262 144 returns): more 256-point tiles than resident blocks, so every block walks several tiles
+    and the tile offsets cross block boundaries."""
+    rng = np.random.default_rng(61)
+    n = 262144
+    pts = (rng.normal(size=(n, 4)) * np.array([30.0, 30.0, 3.0, 40.0])).astype(np.float32)
+    ring = rng.integers(-2, 132, n).astype(np.int32)
+    tm = np.sort(rng.uniform(0.0, 0.1, n)).astype(np.float32)
+    imu_t = 700.0 - 0.004 + np.arange(60) * 0.002
+    imu_r = np.cumsum(rng.normal(0, 2e-3, (60, 3)), axis=0); imu_r[0] = 0
+    for pf, ds in ((1, 1), (3, 2)):
+        kw = dict(n_scan=128, downsample_rate=ds, point_filter_num=pf, min_range=2.0, max_range=90.0)
+        ref = orc.deskew(pts, ring, tm, imu_t, imu_r, 700.0, **kw)
+        n_out = gpu_ctx.deskew(pts, ring, tm, imu_t, imu_r, 700.0, **kw)
+        got = gpu_ctx.deskewed_get()
+        assert n_out == len(ref) and 1000 < len(ref) < n
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # and staged ahead (one block per SM: twice as many tiles per block)
+    gpu_ctx.deskew(pts, ring, tm, imu_t, imu_r, 700.0, ahead=True, sync=False, **kw)
+    gpu_ctx.deskew_advance()
+    assert np.array_equal(gpu_ctx.deskewed_get().view(np.uint32), ref.view(np.uint32))

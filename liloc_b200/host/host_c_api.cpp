@@ -285,6 +285,18 @@ int liloc_host_ip_cloud_livox(void* ip, double stamp, const liloc_host_livox_poi
     if (produced && out) from_info(ci, out);
     return produced ? 1 : 0;
 }
+// the inputs of the last published sweep's de-skew call: imu4 = time | rotX | rotY | rotZ (each imuPointerCur + 1 long, cap
+// entries of room per array), the sweep's points and ring / time as handed to liloc_deskew.  Returns the number of points.
+int liloc_host_ip_last_sweep(void* ip, double* imu4, int imu_cap, int* imuPointerCur, liloc_point* pts, liloc_ring_time* rt, int cap) {
+    auto* p = static_cast<liloc_host::ImageProjection*>(ip);
+    const int last = p->lastImuPointerCur(), m = last >= 0 ? last + 1 : 0;
+    if (imuPointerCur) *imuPointerCur = last;
+    if (imu4 && m <= imu_cap) for (int a = 0; a < 4; ++a) for (int k = 0; k < m; ++k) imu4[(size_t)a * imu_cap + k] = p->lastImu()[(size_t)a * m + k];
+    const int n = (int)p->lastSweepPoints().size();
+    if (pts && rt && n <= cap) { std::memcpy(pts, p->lastSweepPoints().data(), (size_t)n * sizeof(liloc_point)); std::memcpy(rt, p->lastSweepRingTime().data(), (size_t)n * sizeof(liloc_ring_time)); }
+    return n;
+}
+
 void liloc_host_ip_times(void* ip, double* timeScanCur, double* timeScanEnd, int* deskewFlag) {
     auto* p = static_cast<liloc_host::ImageProjection*>(ip);
     if (timeScanCur) *timeScanCur = p->timeScanCur;

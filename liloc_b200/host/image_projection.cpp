@@ -46,7 +46,6 @@ void rpyOf(const double q[4], double& roll, double& pitch, double& yaw) {   // t
 
 ImageProjection::ImageProjection(const std::string& yaml_path, liloc_ctx* ctx) : ParamServer(yaml_path), ctx_(ctx) {
     if (!param_error.empty()) error_ = param_error;
-    else if (!ctx_) error_ = "ImageProjection: no device context";
     // include/utility.h:275-278 (identity when the yaml has no extrinsics)
     double extRPY[3][3];
     for (int i = 0; i < 3; ++i)
@@ -278,9 +277,16 @@ bool ImageProjection::projectPointCloud() {
     p.imu_available = cloudInfo.imuAvailable;
     p.lidar_min_range = lidarMinRange; p.lidar_max_range = lidarMaxRange;
     p.n_scan = N_SCAN; p.downsample_rate = downsampleRate; p.point_filter_num = point_filter_num;
+    // keep what this sweep's device call receives (diagnostics; the CPU tests of the host logic read it)
+    const int m = imuPointerCur >= 0 ? imuPointerCur + 1 : 0;
+    last_imu_pointer_ = imuPointerCur;
+    last_imu_.resize((size_t)4 * m);
+    for (int k = 0; k < m; ++k) { last_imu_[k] = imuTime[k]; last_imu_[m + k] = imuRotX[k]; last_imu_[2 * m + k] = imuRotY[k]; last_imu_[3 * m + k] = imuRotZ[k]; }
+    last_pts_ = current_.pts; last_rt_ = current_.rt;
+    last_size_ = -1;
+    if (!ctx_) return true;                                                   // host logic only
     const int rc = liloc_deskew(ctx_, current_.pts.data(), current_.rt.data(), (int)current_.pts.size(), &p, nullptr);
     if (rc < 0) { error_ = liloc_last_error(ctx_); return false; }
-    last_size_ = -1;
     return true;
 }
 

@@ -35,7 +35,9 @@ const int queueLength = 2000;                      // :61
 
 class ImageProjection : public ParamServer {
 public:
-    // `ctx`: the device context the de-skewed cloud is left in (mapOptimization::context() when both run in one process)
+    // `ctx`: the device context the de-skewed cloud is left in (mapOptimization::context() when both run in one process).
+    // ctx == nullptr: host logic only (CPU tests) -- everything but the device call of projectPointCloud runs, and the
+    // inputs that call would have received stay readable (lastSweep*).
     ImageProjection(const std::string& yaml_path, liloc_ctx* ctx);
 
     void imuHandler(const ImuMsg& imuMsg);                                   // :162-173 (imuConverter, include/utility.h:306-336)
@@ -50,6 +52,11 @@ public:
     bool ok() const { return error_.empty(); }
     const std::string& error() const { return error_; }
     int lastCloudSize() const { return last_size_; }                          // fullCloud->size() of the last published sweep, -1 unknown
+    // what projectPointCloud handed (or would have handed) to liloc_deskew for the last published sweep
+    const std::vector<double>& lastImu() const { return last_imu_; }         // 4 x (lastImuPointerCur() + 1): time | rotX | rotY | rotZ
+    int lastImuPointerCur() const { return last_imu_pointer_; }
+    const std::vector<liloc_point>& lastSweepPoints() const { return last_pts_; }
+    const std::vector<liloc_ring_time>& lastSweepRingTime() const { return last_rt_; }
 
     // the sensor-specific time fields mapped onto PointXYZIRT::time (:332-379)
     static float ousterTime(unsigned t_ns) { return t_ns * 1e-9f; }
@@ -75,6 +82,10 @@ private:
     liloc_ctx* ctx_;
     std::string error_;
     int last_size_ = -1;
+    std::vector<double> last_imu_;
+    int last_imu_pointer_ = -1;
+    std::vector<liloc_point> last_pts_;
+    std::vector<liloc_ring_time> last_rt_;
     double extRot_[3][3], extQRPY_[4];                                        // include/utility.h:275-278
     // cachePointCloudLivox's function statics (:209-211)
     bool livox_first_scan_ = true;

@@ -100,6 +100,8 @@ def _load():
     L.liloc_host_ip_cloud_livox.restype = C.c_int
     L.liloc_host_ip_cloud_livox.argtypes = [P, C.c_double, P, C.c_int, C.POINTER(CloudInfo)]
     L.liloc_host_ip_times.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.liloc_host_ip_last_sweep.restype = C.c_int
+    L.liloc_host_ip_last_sweep.argtypes = [P, P, C.c_int, C.POINTER(C.c_int), P, P, C.c_int]
     return L
 
 
@@ -312,10 +314,11 @@ class ImageProjection:
     """Handle on one host `ImageProjection` (src/imageProjection.cpp:63) that shares the device context of a
     MapOptimization: the CloudInfo it produces refers to the de-skewed sweep left on the device."""
 
-    def __init__(self, yaml: str, map_optimization: MapOptimization):
+    def __init__(self, yaml: str, map_optimization: MapOptimization | None):
+        """map_optimization = None: host logic only (no device; projectPointCloud's device call is skipped)."""
         L = lib()
         self._mo = map_optimization
-        self._h = L.liloc_host_ip_create(config_path(yaml).encode(), map_optimization._h)
+        self._h = L.liloc_host_ip_create(config_path(yaml).encode(), map_optimization._h if map_optimization is not None else None)
         if not self._h:
             raise RuntimeError("ImageProjection: " + (L.liloc_host_ip_error(None) or b"").decode())
 
@@ -360,6 +363,17 @@ class ImageProjection:
         info = CloudInfo()
         rc = lib().liloc_host_ip_cloud_livox(self._h, float(stamp), p.ctypes.data, len(p), C.byref(info))
         return self._ret(rc, info)
+
+    def last_sweep(self):
+        """(imu_time (m,), imu_rot (m, 3), pts (n, 4), ring (n,), time (n,)) of the last published sweep's de-skew call."""
+        cap = 2000
+        imu = np.zeros((4, cap), np.float64)
+        last = C.c_int()
+        n = lib().liloc_host_ip_last_sweep(self._h, imu.ctypes.data, cap, C.byref(last), None, None, 0)
+        pts = np.zeros((n, 4), np.float32); rt = np.zeros(n, RING_TIME)
+        lib().liloc_host_ip_last_sweep(self._h, imu.ctypes.data, cap, C.byref(last), pts.ctypes.data, rt.ctypes.data, n)
+        m = last.value + 1 if last.value >= 0 else 0
+        return imu[0, :m].copy(), imu[1:, :m].T.copy(), pts, rt["ring"].copy(), rt["time"].copy()
 
     def times(self):
         a, b, f = C.c_double(), C.c_double(), C.c_int()

@@ -284,7 +284,8 @@ int liloc_debug_eigen3(liloc_ctx* ctx, const float* A9, int n, float* w3, float*
 /* cornerOptimization's loop body after the kNN on explicit neighbours: pts15 = n x 5 x 3, sel3 = n x pointSel. */
 int liloc_debug_line(liloc_ctx* ctx, const float* pts15, const float* sel3, int n, liloc_point* coeff, int* keep);
 
-/* ---- timing: CUDA-event milliseconds of the phases of the last liloc_frame / call sequence ------ */
+/* ---- timing: milliseconds of the phases of the last liloc_frame (from the in-kernel %globaltimer marks below;
+ *      the step-wise liloc_scan2map uses CUDA events) ------------------------------------------------------ */
 typedef struct { float assemble_ms, map_voxel_ms, grid_ms, scan_ms, s2m_ms, total_ms; } liloc_timing;
 int liloc_last_timing(liloc_ctx* ctx, liloc_timing* t);
 /* Local-map memoisation (liloc_config.map_cache) on / off at run time; returns the number of frames that reused the map. */
@@ -292,13 +293,13 @@ long long liloc_set_map_cache(liloc_ctx* ctx, int enabled);
 int liloc_set_timing(liloc_ctx* ctx, int enabled);
 /* Device-side latency breakdown of the last liloc_frame / liloc_frame_features made while timing is enabled:
  * %globaltimer nanoseconds written by block 0 at the phase boundaries of the three launches --
- * [0..15] local-map pipeline (start, assemble+bbox, keys, sort, run count, centroids, cell scan, end),
+ * [0..15] local-map pipeline (start, assemble+bbox, keys, sort, (unused), centroids, cell scan, end),
  * [16..31] scan pipeline (same phases), [32] registration start, then per iteration i: [33+3i] tiles done,
  * [34+3i] past the grid barrier, [35+3i] pose updated, [129] end of the registration kernel.  The kernels write them
  * straight into mapped host memory; liloc_last_timing is derived from them (no CUDA events inside a frame).
  * Returns the number of entries copied. */
 int liloc_last_marks(liloc_ctx* ctx, unsigned long long* out, int cap);
-/* Cumulative counters since liloc_create / liloc_stats_reset.  Phase times are CUDA-event milliseconds
+/* Cumulative counters since liloc_create / liloc_stats_reset.  Phase times are the liloc_timing milliseconds
  * summed over liloc_frame calls made while timing is enabled; alg_bytes_* are the ALGORITHMIC bytes of
  * assemble+map VoxelGrid 16 N_raw + 16 M, scan VoxelGrid 16 N_scan + 16 Q_all,
  * scan2map I (96 Q + 216) with Q = ceil(Q_all / stride) and I the iterations actually executed. */

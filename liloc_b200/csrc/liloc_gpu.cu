@@ -139,7 +139,6 @@ struct liloc_ctx {
     float* d_pose = nullptr;       // 6
     S2mState* d_state[2] = {nullptr, nullptr};   // double-buffered: a frame that has to be redone must not see its own update
     int state_cur = 0;
-    S2mResult* d_result = nullptr;
     S2mResult* d_result_host = nullptr;          // device alias of h_info->res (mapped pinned memory)
     unsigned long long* d_marks_host = nullptr;  // device alias of h_info->marks
     unsigned* d_done_host = nullptr;             // device alias of h_info->done_seq
@@ -610,8 +609,6 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     }
     CUB_(cudaMalloc(&c->d_pose, 6 * sizeof(float)));
     for (auto& s : c->d_state) { CUB_(cudaMalloc(&s, sizeof(S2mState))); CUB_(cudaMemset(s, 0, sizeof(S2mState))); }
-    CUB_(cudaMalloc(&c->d_result, sizeof(S2mResult)));
-    CUB_(cudaMemset(c->d_result, 0, sizeof(S2mResult)));
     CUB_(cudaMalloc(&c->d_ndt_active, sizeof(int)));
     // pinned AND mapped: the registration kernel and the phase marks write their results straight into host memory
     // (posted PCIe writes), so no device-to-host copy sits between the last kernel of a frame and the host's wake-up
@@ -701,7 +698,7 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_dk_fork2) cudaEventDestroy(c->ev_dk_fork2);
     if (c->h_dk_imu) cudaFreeHost(c->h_dk_imu);
     for (auto& e : c->ev_dk_slot) if (e) cudaEventDestroy(e);
-    fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]); fr(c->d_result);
+    fr(c->partial.p); fr(c->d_pose); fr(c->d_state[0]); fr(c->d_state[1]);
     fr(c->tmp_pts.p); fr(c->tmp_i.p); fr(c->tmp_f.p); fr(c->tmp_b.p);
     for (auto& kv : c->ndt_targets) { fr(kv.second.table.p); fr(kv.second.leaves.p); }
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);

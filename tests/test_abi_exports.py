@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -42,11 +44,38 @@ def test_library_is_sm100a_only():
     assert archs == {"sm_100a"}, archs
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """Every ctypes mirror in liloc_b200/abi.py against sizeof / offsetof of the real header, compiled here with gcc (C, not C++:
+    the header is the C ABI)."""
+    import shutil
+    import subprocess
     from liloc_b200 import abi
     assert ctypes.sizeof(abi.S2mOpts) == 8 * 4
     assert ctypes.sizeof(abi.S2mResult) == 8 * 4 + 72 * 4
     assert ctypes.sizeof(abi._Config) == 8 * 4
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    mirrors = {"liloc_s2m_opts": abi.S2mOpts, "liloc_s2m_result": abi.S2mResult, "liloc_config": abi._Config, "liloc_frame_in": abi.FrameIn,
+               "liloc_s2m_extra": abi.S2mExtra, "liloc_timing": abi.Timing, "liloc_stats": abi.Stats, "liloc_ndt_opts": abi.NdtOpts,
+               "liloc_ndt_stats": abi.NdtStats, "liloc_ndt_job": abi.NdtJob, "liloc_ndt_out": abi.NdtOut, "liloc_deskew_params": abi.DeskewParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "liloc_gpu.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("liloc_point %zu\\n", sizeof(liloc_point));', '  printf("liloc_ring_time %zu\\n", sizeof(liloc_ring_time));', '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr            # also proves the header is plain C
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+    assert int(got["liloc_point"]) == 16 and int(got["liloc_ring_time"]) == abi.RING_TIME.itemsize == 8
 
 
 def test_product_does_not_reference_the_oracle():

@@ -1,0 +1,53 @@
+"""CPU tests of bench.py's contract: the reference arm (the one arm that runs without a GPU) prints exactly one JSON line on
+stdout with the keys the driver reads, for the lio workload and for an NDT workload; the product arm refuses to run
+without a CUDA device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+        "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(*args, timeout=600):
+    env = dict(os.environ, LILOC_BENCH_QUICK="1")
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def _one_json_line(stdout):
+    lines = [l for l in stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines                      # nothing but the result on stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_lio_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-frames", "3", "--frames", "40")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = _one_json_line(r.stdout)
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "scan2map_registrations_per_s" and d["unit"] == "registrations/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_ndt_line():
+    r = _run("--impl", "reference", "--workload", "relo", "--items", "4", "--steps", "1", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = _one_json_line(r.stdout)
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+
+
+def test_product_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    r = _run("--steps", "1", "--warmup", "1", "--frames", "5", "--no-cpu")
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout) or "CUDA" in r.stderr

@@ -51,3 +51,15 @@ def test_product_arm_has_no_cpu_fallback():
     r = _run("--steps", "1", "--warmup", "1", "--frames", "5", "--no-cpu")
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout) or "CUDA" in r.stderr
+
+
+def test_reference_arm_under_torchrun_only_rank0_works():
+    """Launched the way the driver launches N > 1: rank 0 alone runs and prints the line, the other rank exits 0 silently."""
+    env = dict(os.environ, LILOC_BENCH_QUICK="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--ref-frames", "3", "--frames", "40"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = _one_json_line(r.stdout)
+    assert d["impl"] == "reference" and d["value"] > 0

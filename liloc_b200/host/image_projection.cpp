@@ -42,6 +42,36 @@ void rpyOf(const double q[4], double& roll, double& pitch, double& yaw) {   // t
     quatToRPY(Quat{q[0], q[1], q[2], q[3]}, roll, pitch, yaw);
 }
 
+// Relative time of every return of a cloud that has no time channel, from its azimuth (src/imageProjection.cpp:279-326).
+// The sensor turns clockwise, so -atan2(y, x) grows along the sweep; it is unwrapped against the first return's azimuth
+// until the sweep has passed the half turn and against the last return's afterwards.  A sweep lasts 0.1 s.  Types as in
+// the reference: the azimuth of a return is a float, the two reference angles and every comparison are double.
+void azimuthTimes(const std::vector<liloc_point>& cloud, std::vector<liloc_ring_time>& out) {
+    auto azimuth = [](const liloc_point& p) -> float { return -std::atan2(p.y, p.x); };
+    const double two_pi = 2 * M_PI;
+    const double first = azimuth(cloud.front());
+    double last = azimuth(cloud.back()) + two_pi;
+    if (last - first > 3 * M_PI) last -= two_pi;
+    else if (last - first < M_PI) last += two_pi;
+    const double span = last - first;
+    bool past_half = false;
+    for (size_t i = 0; i < cloud.size(); ++i) {
+        float a = azimuth(cloud[i]);
+        if (past_half) {
+            a += two_pi;
+            if (a < last - M_PI * 3 / 2) a += two_pi;
+            else if (a > last + M_PI / 2) a -= two_pi;
+        } else {
+            if (a < first - M_PI / 2) a += two_pi;
+            else if (a > first + M_PI * 3 / 2) a -= two_pi;
+            past_half = a - first > M_PI;
+        }
+        const float fraction = (a - first) / span;
+        out[i].ring = 0;                                                  // PointXYZIRT::ring stays value-initialised
+        out[i].time = 0.1 * fraction;
+    }
+}
+
 }  // namespace
 
 ImageProjection::ImageProjection(const std::string& yaml_path, liloc_ctx* ctx) : ParamServer(yaml_path), ctx_(ctx) {
@@ -150,30 +180,8 @@ bool ImageProjection::cachePointCloud(Sweep&& msg) {
     if (cloudQueue.size() <= 2) return false;
     current_ = std::move(cloudQueue.front());
     cloudQueue.pop_front();
-    const int n = (int)current_.pts.size();
     if (!have_ring_time_channel) {                                        // :279-326: time from the azimuth, ring unknown (0)
-        bool halfPassed = false;
-        const std::vector<liloc_point>& P = current_.pts;
-        const double startOrientation = -std::atan2(P[0].y, P[0].x);
-        double endOrientation = -std::atan2(P[n - 1].y, P[n - 1].x) + 2 * M_PI;
-        if (endOrientation - startOrientation > 3 * M_PI) endOrientation -= 2 * M_PI;
-        else if (endOrientation - startOrientation < M_PI) endOrientation += 2 * M_PI;
-        const double orientationDiff = endOrientation - startOrientation;
-        for (int i = 0; i < n; ++i) {
-            float ori = -std::atan2(P[i].y, P[i].x);
-            if (!halfPassed) {
-                if (ori < startOrientation - M_PI / 2) ori += 2 * M_PI;
-                else if (ori > startOrientation + M_PI * 3 / 2) ori -= 2 * M_PI;
-                if (ori - startOrientation > M_PI) halfPassed = true;
-            } else {
-                ori += 2 * M_PI;
-                if (ori < endOrientation - M_PI * 3 / 2) ori += 2 * M_PI;
-                else if (ori > endOrientation + M_PI / 2) ori -= 2 * M_PI;
-            }
-            const float relTime = (ori - startOrientation) / orientationDiff;
-            current_.rt[i].ring = 0;                                      // PointXYZIRT::ring stays value-initialised
-            current_.rt[i].time = 0.1 * relTime;
-        }
+        azimuthTimes(current_.pts, current_.rt);
         deskewFlag = 1;
     } else if (deskewFlag == 0) {                                         // :400-410
         deskewFlag = current_.has_time ? 1 : -1;

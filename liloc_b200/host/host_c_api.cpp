@@ -211,6 +211,7 @@ int liloc_host_debug_extract_nearby(void* h, double stamp, int* ids, int cap) {
     m->extractSurroundingKeyFrames();
     return liloc_host_last_selection(h, ids, cap);
 }
+void liloc_host_debug_nearby_plain(void* h, int on) { static_cast<mapOptimization*>(h)->nearby_plain_only = on != 0; }
 void liloc_host_debug_set_pose(void* h, const float* pose6) { std::memcpy(static_cast<mapOptimization*>(h)->transformTobeMapped, pose6, 24); }
 void liloc_host_debug_get_pose(void* h, float* pose6) { std::memcpy(pose6, static_cast<mapOptimization*>(h)->transformTobeMapped, 24); }
 void liloc_host_debug_update_initial_guess(void* h, const liloc_host_cloud_info* msg) {

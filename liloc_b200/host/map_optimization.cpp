@@ -80,7 +80,7 @@ void mapOptimization::reset() {
     timeLastProcessing_ = -1; lastImuPreTransAvailable_ = false;
     lastImuTransformation_ = Affine3f::Identity(); lastImuPreTransformation_ = Affine3f::Identity();
     sel_ids_.clear(); sel_poses_.clear(); have_selection_ = false;
-    nearby_ds_.clear(); nearby_n_ = 0;
+    nearby_ds_.clear(); nearby_n_ = 0; by_x_.clear(); by_x_n_ = 0;
     prior_ = PriorSession{};
     if (ctx_) { liloc_keyframe_clear(ctx_); liloc_ndt_clear(ctx_); }
 }
@@ -164,6 +164,102 @@ void mapOptimization::extractSurroundingKeyFrames() {
     extractNearby();
 }
 
+// extractNearby's pose-only part, the way the reference does it step by step: radiusSearch (ascending distance) ->
+// VoxelGrid -> nearestKSearch(1) per centroid.  Used when the fast version below declines.
+void mapOptimization::extractNearbyPlain(const PointType& last) {
+    const float r2 = surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius;
+    std::vector<std::pair<float, int>> hits;                                           // :908-914
+    hits.reserve(cloudKeyPoses3D.size());
+    for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
+        const float d = sqDist(last, cloudKeyPoses3D[i]);
+        if (d < r2) hits.push_back({d, i});
+    }
+    std::sort(hits.begin(), hits.end());
+    std::vector<PointType> surroundingKeyPoses;
+    surroundingKeyPoses.reserve(hits.size());
+    for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
+    nearby_ds_ = voxelGridSmall(surroundingKeyPoses, surroundingKeyframeDensity);      // :916-917
+    for (auto& pt : nearby_ds_) {                                                      // :918-922
+        int best = 0; float bd = sqDist(pt, cloudKeyPoses3D[0]);
+        for (int i = 1; i < (int)cloudKeyPoses3D.size(); ++i) { const float d = sqDist(pt, cloudKeyPoses3D[i]); if (d < bd) { bd = d; best = i; } }
+        pt.intensity = cloudKeyPoses3D[best].intensity;
+    }
+}
+
+// The same result with one sort and windowed 1-NN searches (the plain version is ~30 us at a few hundred key poses, on
+// every frame that follows a new keyframe).  (1) The VoxelGrid sums a voxel's poses in the order of its input, which is
+// ascending (distance, index): sorting the hits once by (voxel, distance, index) gives the same groups in the same
+// order.  (2) The nearest key pose of a centroid is searched in a list of the key poses sorted by x, outwards from the
+// centroid's x until the x offset alone exceeds the best distance; ties go to the lowest index like a front-to-back scan.
+bool mapOptimization::extractNearbyFast(const PointType& last) {
+    const int N = (int)cloudKeyPoses3D.size();
+    // x-sorted index, extended by the poses added since the last call (rebuilt when the list shrank)
+    if (by_x_n_ > (size_t)N) { by_x_.clear(); by_x_n_ = 0; }
+    for (int i = (int)by_x_n_; i < N; ++i) {
+        const std::pair<float, int> e{cloudKeyPoses3D[i].x, i};
+        by_x_.insert(std::upper_bound(by_x_.begin(), by_x_.end(), e), e);
+    }
+    by_x_n_ = (size_t)N;
+    const float r2 = surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius;
+    using Hit = HitScratch;
+    std::vector<Hit>& hits = hit_scratch_;
+    hits.clear();
+    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    for (int i = 0; i < N; ++i) {
+        const PointType& p = cloudKeyPoses3D[i];
+        const float d = sqDist(last, p);
+        if (!(d < r2)) continue;
+        if (hits.empty()) { mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z; }
+        else {
+            mn[0] = std::min(mn[0], p.x); mx[0] = std::max(mx[0], p.x);
+            mn[1] = std::min(mn[1], p.y); mx[1] = std::max(mx[1], p.y);
+            mn[2] = std::min(mn[2], p.z); mx[2] = std::max(mx[2], p.z);
+        }
+        hits.push_back(Hit{0, d, i});
+    }
+    nearby_ds_.clear();
+    if (hits.empty()) return true;
+    // pcl::VoxelGrid parameters, as in voxelGridSmall
+    const float inv = 1.0f / surroundingKeyframeDensity;
+    const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+    if (dx * dy * dz > (long long)INT_MAX) return false;                   // PCL's "leaf size too small" path: plain version
+    int minb[3], divb[3];
+    for (int a = 0; a < 3; ++a) { minb[a] = (int)std::floor(mn[a] * inv); divb[a] = (int)std::floor(mx[a] * inv) - minb[a] + 1; }
+    for (Hit& h : hits) {
+        const PointType& p = cloudKeyPoses3D[h.i];
+        const int i0 = (int)(std::floor(p.x * inv) - (float)minb[0]);
+        const int i1 = (int)(std::floor(p.y * inv) - (float)minb[1]);
+        const int i2 = (int)(std::floor(p.z * inv) - (float)minb[2]);
+        h.key = i0 + i1 * divb[0] + i2 * divb[0] * divb[1];
+    }
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) {
+        if (a.key != b.key) return a.key < b.key;
+        if (a.d != b.d) return a.d < b.d;
+        return a.i < b.i;
+    });
+    for (size_t g0 = 0; g0 < hits.size();) {
+        size_t g1 = g0; float sx = 0, sy = 0, sz = 0, sw = 0;
+        for (; g1 < hits.size() && hits[g1].key == hits[g0].key; ++g1) { const PointType& p = cloudKeyPoses3D[hits[g1].i]; sx += p.x; sy += p.y; sz += p.z; sw += p.intensity; }
+        const float c = (float)(g1 - g0);
+        PointType pt{sx / c, sy / c, sz / c, sw / c};
+        // nearest key pose: outwards from the centroid's x in the x-sorted list
+        int best = -1; float bd = 3.4e38f;
+        auto consider = [&](int i) { const float d = sqDist(pt, cloudKeyPoses3D[i]); if (d < bd || (d == bd && i < best)) { bd = d; best = i; } };
+        const size_t pos = (size_t)(std::lower_bound(by_x_.begin(), by_x_.end(), std::pair<float, int>{pt.x, -1}) - by_x_.begin());
+        size_t r = pos; long long l = (long long)pos - 1;
+        while (r < by_x_.size() || l >= 0) {
+            bool moved = false;
+            if (r < by_x_.size()) { const float ex = by_x_[r].first - pt.x; if (ex * ex <= bd) { consider(by_x_[r].second); ++r; moved = true; } else r = by_x_.size(); }
+            if (l >= 0) { const float ex = pt.x - by_x_[(size_t)l].first; if (ex * ex <= bd) { consider(by_x_[(size_t)l].second); --l; moved = true; } else l = -1; }
+            if (!moved) break;
+        }
+        pt.intensity = cloudKeyPoses3D[best].intensity;
+        nearby_ds_.push_back(pt);
+        g0 = g1;
+    }
+    return true;
+}
+
 void mapOptimization::extractNearby() {
     const PointType& last = cloudKeyPoses3D.back();
     // The radius search, its VoxelGrid thinning and the 1-NN index recovery (:908-922) depend only on the key poses, which
@@ -172,31 +268,8 @@ void mapOptimization::extractNearby() {
     const PointType& first = cloudKeyPoses3D.front();
     const bool cached = nearby_n_ == cloudKeyPoses3D.size() && nearby_last_.x == last.x && nearby_last_.y == last.y && nearby_last_.z == last.z &&
                         nearby_first_.x == first.x && nearby_first_.y == first.y && nearby_first_.z == first.z;
-    if (!cached) {
-        // radiusSearch(last, R): d2 < R^2, ascending distance (:908-914)
-        const float r2 = surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius;
-        std::vector<std::pair<float, int>> hits;
-        hits.reserve(cloudKeyPoses3D.size());
-        for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
-            const float d = sqDist(last, cloudKeyPoses3D[i]);
-            if (d < r2) hits.push_back({d, i});
-        }
-        std::sort(hits.begin(), hits.end());
-        std::vector<PointType> surroundingKeyPoses;
-        surroundingKeyPoses.reserve(hits.size());
-        for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
-        nearby_ds_ = voxelGridSmall(surroundingKeyPoses, surroundingKeyframeDensity);                    // :916-917
-        for (auto& pt : nearby_ds_) {          // nearestKSearch(pt, 1): recover the keyframe index (:918-922)
-            // exact scan; a pose is only measured when its x offset alone does not already rule it out
-            int best = 0; float bd = sqDist(pt, cloudKeyPoses3D[0]);
-            for (int i = 1; i < (int)cloudKeyPoses3D.size(); ++i) {
-                const float ex = pt.x - cloudKeyPoses3D[i].x;
-                if (ex * ex >= bd) continue;
-                const float d = sqDist(pt, cloudKeyPoses3D[i]);
-                if (d < bd) { bd = d; best = i; }
-            }
-            pt.intensity = cloudKeyPoses3D[best].intensity;
-        }
+    if (!cached || nearby_plain_only) {
+        if (nearby_plain_only || !extractNearbyFast(last)) extractNearbyPlain(last);
         nearby_n_ = cloudKeyPoses3D.size(); nearby_last_ = last; nearby_first_ = first;
     }
     std::vector<PointType> surroundingKeyPosesDS = nearby_ds_;

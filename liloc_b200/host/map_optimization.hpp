@@ -11,6 +11,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/liloc_gpu.h"
@@ -95,6 +96,8 @@ public:
     void updateInitialGuess();                 // :831-900
     void extractSurroundingKeyFrames();        // :963-968
     void extractNearby();                      // :902-934
+    void extractNearbyPlain(const PointType& last);   // its pose-only part, step by step like the reference
+    bool extractNearbyFast(const PointType& last);    // the same result with one sort and windowed 1-NN searches
     void extractCloud(const std::vector<PointType>& cloudToExtract);   // :936-961
     void downsampleCurrentScan();              // :970-975
     void scan2MapOptimization();               // :1183-1207
@@ -127,6 +130,7 @@ public:
     Affine3f trans2Affine3f(const float t[6]) { return getTransformation(t[3], t[4], t[5], t[0], t[1], t[2]); }   // :404-406
 
     liloc_s2m_opts s2m_opts{20, 2, 50, 30, 0, 10, 1, {0}};
+    bool nearby_plain_only = false;             // tests: always take extractNearbyPlain (and never the cached result)
     const std::vector<int>& lastSelection() const { return sel_ids_; }
 
 private:
@@ -145,6 +149,10 @@ private:
     std::vector<PointType> nearby_ds_;
     size_t nearby_n_ = 0;
     PointType nearby_last_{0, 0, 0, 0}, nearby_first_{0, 0, 0, 0};
+    std::vector<std::pair<float, int>> by_x_;    // key poses sorted by (x, index), extended as poses are added
+    size_t by_x_n_ = 0;
+    struct HitScratch { int key; float d; int i; };
+    std::vector<HitScratch> hit_scratch_;
     FrameReport rep_;
     PriorSession prior_;
     int ndtAlign(int submap, const float guess6[6], int n_align, float out6[6], int* iterations, int* converged);

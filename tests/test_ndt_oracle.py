@@ -175,3 +175,42 @@ def test_kdtree_neighbourhood_matches_scipy_radius_search(orc, synth, ndt_scene)
     s1 = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=0, threads=4))[0]
     s7 = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=1, threads=4))[0]
     assert got[0] > s7 > s1 > 0                                     # more neighbours, more score (-d1 > 0)
+
+
+def test_newton_direction_is_the_minimum_norm_solution(orc):
+    """JacobiSVD(H).solve(-g) (computeTransformation): H^-1 (-g) when H is regular, the pseudo-inverse solution when a
+    direction is unobservable (planar scenes: zero rows / columns) -- against numpy."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        A = rng.normal(size=(6, 6)); H = A @ A.T + 0.1 * np.eye(6); g = rng.normal(size=6)
+        assert np.allclose(orc.ndt_newton(H, g), np.linalg.solve(H, -g), rtol=1e-9, atol=1e-12)
+    for _ in range(20):                                             # rank 4: two unobservable directions
+        B = rng.normal(size=(6, 4)); H = B @ B.T; g = B @ rng.normal(size=4)
+        want = np.linalg.pinv(H, rcond=1e-12) @ -g
+        got = orc.ndt_newton(H, g)
+        assert np.allclose(got, want, rtol=1e-6, atol=1e-9), (got, want)
+    # indefinite Hessians (far from the optimum) are solved as they are, like the SVD does
+    H = np.diag([3.0, -2.0, 1.0, 5.0, -0.5, 4.0]); g = np.arange(1.0, 7.0)
+    assert np.allclose(orc.ndt_newton(H, g), -g / np.diag(H))
+
+
+def test_more_thuente_trial_values(orc):
+    """trialValueSelectionMT (More & Thuente 1994, section 4): case 1 picks the cubic minimiser when it is closer to a_l
+    than the quadratic one, else their mean; the cubic / quadratic / secant minimisers are checked on polynomials whose
+    minimisers are known in closed form."""
+    # case 1 (f_t > f_l): interpolate f(a) = (a - 1)^2 through a_l = 0 and a_t = 3 -> both minimisers are a = 1
+    f = lambda a: (a - 1.0) ** 2
+    df = lambda a: 2.0 * (a - 1.0)
+    a = orc.ndt_trial_value(0.0, f(0.0), df(0.0), 5.0, f(5.0), df(5.0), 3.0, f(3.0), df(3.0))
+    assert abs(a - 1.0) < 1e-12
+    # case 1 with a genuine cubic f(a) = a^3 - 3a (local minimum at a = 1): a_l = 0, a_t = 2
+    f = lambda a: a ** 3 - 3 * a
+    df = lambda a: 3 * a * a - 3
+    a_c = 1.0                                                       # cubic through (0, 2) with both slopes reproduces f
+    a_q = 0.0 - 0.5 * (0.0 - 2.0) * df(0.0) / (df(0.0) - (f(0.0) - f(2.0)) / (0.0 - 2.0))
+    want = a_c if abs(a_c - 0.0) < abs(a_q - 0.0) else 0.5 * (a_q + a_c)
+    assert abs(orc.ndt_trial_value(0.0, f(0.0), df(0.0), 4.0, f(4.0), df(4.0), 2.0, f(2.0), df(2.0)) - want) < 1e-12
+    # case 2 (f_t <= f_l, slopes of opposite sign): cubic vs secant minimiser, the one farther from a_t ... on a parabola both are exact
+    f = lambda a: (a - 2.0) ** 2
+    df = lambda a: 2.0 * (a - 2.0)
+    assert abs(orc.ndt_trial_value(0.0, f(0.0), df(0.0), 9.0, f(9.0), df(9.0), 3.0, f(3.0), df(3.0)) - 2.0) < 1e-12

@@ -190,3 +190,39 @@ def test_golden_fixture_from_the_numpy_restatement():
     # the integration of the fixture's IMU samples is reproduced too (imuDeskewInfo)
     dt = np.diff(g["imu_time"])
     assert np.all(dt > 0) and np.all(g["imu_rot"][0] == 0)
+
+
+def test_zero_motion_is_the_identity_bit_for_bit():
+    """All integrated angles zero: getTransformation is the exact identity, its cofactor inverse and the product too, and
+    1*x + 0*y + 0*z + 0 reproduces every coordinate exactly."""
+    sw = _sweep(seed=9)
+    t, r = orc.imu_integrate(sw["imu_stamps"], np.zeros_like(sw["imu_gyro"]), sw["time_scan_end"])
+    assert np.all(r == 0)
+    out = orc.deskew(sw["pts"], sw["ring"], sw["time"], t, r, sw["time_scan_cur"], point_filter_num=2)
+    assert np.array_equal(out, sw["pts"][_keep_mask(sw, 1.0, 1000.0, 16, 1, 2)])
+
+
+def test_filter_parameters_property():
+    """hypothesis: for any ranges / strides the survivors are exactly the numpy mask, in order (deskew switched off)."""
+    from hypothesis import given, settings, strategies as st
+    sw = _sweep(seed=10)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.floats(0.0, 30.0), st.floats(5.0, 120.0), st.integers(1, 40), st.integers(1, 5), st.integers(1, 9))
+    def check(minr, maxr, n_scan, ds, pf):
+        out = orc.deskew(sw["pts"], sw["ring"], sw["time"], deskew_flag=-1, min_range=minr, max_range=maxr, n_scan=n_scan,
+                         downsample_rate=ds, point_filter_num=pf)
+        m = _keep_mask(sw, np.float32(minr), np.float32(maxr), n_scan, ds, pf)
+        assert np.array_equal(out, sw["pts"][m])
+    check()
+
+
+def test_rigid_motion_preserves_ranges():
+    """de-skewing is a rotation about the sensor origin (findPosition is zero): ranges are preserved to float accuracy"""
+    sw = _sweep(seed=11, gyro=(0.4, 0.3, -1.0))
+    t, r = orc.imu_integrate(sw["imu_stamps"], sw["imu_gyro"], sw["time_scan_end"])
+    out = orc.deskew(sw["pts"], sw["ring"], sw["time"], t, r, sw["time_scan_cur"], min_range=0.0, point_filter_num=1)
+    keep = _keep_mask(sw, 0.0, 1000.0, 16, 1, 1)
+    r_in = np.linalg.norm(sw["pts"][keep, :3].astype(np.float64), axis=1)
+    r_out = np.linalg.norm(out[:, :3].astype(np.float64), axis=1)
+    assert np.abs(r_in - r_out).max() < 2e-5 * max(1.0, r_in.max())

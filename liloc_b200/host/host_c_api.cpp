@@ -219,6 +219,11 @@ void liloc_host_debug_update_initial_guess(void* h, const liloc_host_cloud_info*
     m->cloudInfo = to_info(*msg); m->timeLaserInfoCur = msg->stamp;
     m->updateInitialGuess();
 }
+// init_guess exactly as the class builds it for registration->align (eulerToRotation, src/mapOptmization.cpp:276-280): tests feed the
+// oracle the same 16 floats
+void liloc_host_debug_euler_to_matrix(const float* pose6, float* T16) {
+    liloc_host::eulerToMatrix4(pose6[0], pose6[1], pose6[2], pose6[3], pose6[4], pose6[5], T16);
+}
 int liloc_host_debug_save_frame(void* h) { return static_cast<mapOptimization*>(h)->saveFrame() ? 1 : 0; }
 void liloc_host_debug_transform_update(void* h, const liloc_host_cloud_info* msg) {
     auto* m = static_cast<mapOptimization*>(h);

@@ -84,6 +84,7 @@ def _load():
     L.liloc_host_debug_set_pose.argtypes = [P, P]
     L.liloc_host_debug_get_pose.argtypes = [P, P]
     L.liloc_host_debug_update_initial_guess.argtypes = [P, C.POINTER(CloudInfo)]
+    L.liloc_host_debug_euler_to_matrix.argtypes = [P, P]
     L.liloc_host_debug_save_frame.restype = C.c_int
     L.liloc_host_debug_save_frame.argtypes = [P]
     L.liloc_host_debug_transform_update.argtypes = [P, C.POINTER(CloudInfo)]
@@ -107,6 +108,15 @@ def _load():
 
 
 _lib = None
+
+
+def euler_to_matrix(pose6) -> np.ndarray:
+    """init_guess of the NDT call sites exactly as the host class builds it (eulerToRotation in float32,
+    src/mapOptmization.cpp:276-280): (4, 4) float32.  Parity tests hand the oracle these very bits."""
+    p = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    T = np.zeros(16, np.float32)
+    lib().liloc_host_debug_euler_to_matrix(p.ctypes.data, T.ctypes.data)
+    return T.reshape(4, 4)
 
 
 def lib():

@@ -22,8 +22,9 @@
 //     evaluated in double and rounded to float, accumulation of score / gradient / Hessian in double;
 //   * the Hessian is evaluated in every derivative sweep (ndt_omp recomputes it after the line search with
 //     a double-precision twin of the same formula);
-//   * the Newton step solves the symmetrised 6x6 Hessian with a Jacobi eigen-decomposition pseudo-inverse
-//     (== JacobiSVD::solve for a symmetric matrix);
+//   * ONE summation order for the 28 sums of a sweep, independent of thread count (see derivative_sweep);
+//   * the Newton step solves the symmetrised 6x6 Hessian: Gaussian elimination with partial pivoting when it is well
+//     conditioned, Jacobi eigen-decomposition pseudo-inverse (== JacobiSVD::solve for a symmetric matrix) otherwise;
 //   * voxel covariance eigen-decomposition: cyclic Jacobi in double; 3x3 inverse by cofactors.
 
 #include <algorithm>
@@ -287,24 +288,100 @@ inline bool point_cell_terms(const float x[3], const float xt[3], const NdtLeaf&
 
 struct Sums { double v[28]; };
 
+// CANONICAL SUMMATION ORDER of the 28 sums of a derivative sweep (shared with the device, liloc_b200/csrc/ndt.cuh
+// ndt_sweep_tile + the job update).  ndt_omp itself sums per OpenMP thread and then over threads, so its result
+// depends on the thread count in the last bits -- and the More-Thuente line search branches on such bits.  Both
+// sides of the parity tests therefore use ONE fixed order, independent of thread count / grid size:
+//   * the source cloud is cut into tiles of 1024 consecutive points; a tile is 8 "warps"; warp w owns the points
+//     base + r * 256 + w * 32 + lane   (r = 0..3 rounds, lane = 0..31);
+//   * a warp's (point, cell) hits -- cells that hold a Gaussian (and, for KDTREE, pass the radius test) -- are
+//     enumerated in (round, cell, lane) order and dealt round-robin to 32 accumulators: hit number s goes to
+//     accumulator s % 32, each accumulator adds its hits' float terms in that order in double, starting from 0;
+//   * the 32 accumulators are combined by a butterfly: a[l] += a[l + s] for l < s, s = 16, 8, 4, 2, 1;
+//   * the 8 warp totals are added in warp order to 0.0, the tile totals in tile order to 0.0.
+constexpr int kTile = 1024, kWarps = 8, kLanes = 32, kRounds = 4;
+
+void sweep_tile(const NdtTarget& tg, const orc_point* src, int n, int tile, const float* T, const AngDeriv& A, double d1, float d2,
+                int search, double* out28) {
+    const int ncell = search == 2 ? 27 : (search == 1 ? 7 : 1);
+    const float radius2 = tg.resolution * tg.resolution;
+    const int base = tile * kTile;
+    double tile_tot[28];
+    for (int k = 0; k < 28; ++k) tile_tot[k] = 0.0;
+    for (int w = 0; w < kWarps; ++w) {
+        double acc[kLanes][28];
+        for (int l = 0; l < kLanes; ++l) for (int k = 0; k < 28; ++k) acc[l][k] = 0.0;
+        long long seq = 0;
+        for (int r = 0; r < kRounds; ++r) {
+            float xs[kLanes][3], xts[kLanes][3];
+            bool valid[kLanes];
+            for (int l = 0; l < kLanes; ++l) {
+                const int i = base + r * (kWarps * kLanes) + w * kLanes + l;
+                valid[l] = i < n;
+                if (!valid[l]) continue;
+                const float x[3] = {src[i].x, src[i].y, src[i].z};
+                for (int a = 0; a < 3; ++a) xs[l][a] = x[a];
+                xts[l][0] = T[0] * x[0] + T[1] * x[1] + T[2] * x[2] + T[3];
+                xts[l][1] = T[4] * x[0] + T[5] * x[1] + T[6] * x[2] + T[7];
+                xts[l][2] = T[8] * x[0] + T[9] * x[1] + T[10] * x[2] + T[11];
+            }
+            // search: 0 DIRECT1 (the point's voxel), 1 DIRECT7 (+ the six face neighbours), 2 KDTREE (radiusSearch over the
+            // leaf centroids with radius = resolution: squared float distance < radius^2, FLANN RadiusResultSet; such a
+            // centroid can only belong to one of the 27 voxels around the point's voxel).  ndt_omp sums the neighbours in
+            // FLANN's distance order; here in voxel order (canonical).
+            for (int c = 0; c < ncell; ++c) {
+                const int dx = ncell == 27 ? c % 3 - 1 : kDisp7[c][0], dy = ncell == 27 ? (c / 3) % 3 - 1 : kDisp7[c][1], dz = ncell == 27 ? c / 9 - 1 : kDisp7[c][2];
+                for (int l = 0; l < kLanes; ++l) {
+                    if (!valid[l]) continue;
+                    const float* xt = xts[l];
+                    const int li = tg.lookup(xt[0], xt[1], xt[2], dx, dy, dz);
+                    if (li < 0) continue;
+                    const NdtLeaf& L = tg.leaves[(size_t)li];
+                    if (ncell == 27) {
+                        const float ex = (float)L.mean[0] - xt[0], ey = (float)L.mean[1] - xt[1], ez = (float)L.mean[2] - xt[2];
+                        if (!(ex * ex + ey * ey + ez * ez < radius2)) continue;
+                    }
+                    float t[28];
+                    const bool used = point_cell_terms(xs[l], xt, L, A, d1, d2, t);
+                    double* a = acc[seq % kLanes];
+                    ++seq;                                  // a rejected pair (d2 * e outside [0, 1]) still takes its slot
+                    if (used) for (int k = 0; k < 28; ++k) a[k] += (double)t[k];
+                }
+            }
+        }
+        for (int s = kLanes / 2; s >= 1; s >>= 1)
+            for (int l = 0; l < s; ++l) for (int k = 0; k < 28; ++k) acc[l][k] = acc[l][k] + acc[l + s][k];
+        for (int k = 0; k < 28; ++k) tile_tot[k] += acc[0][k];
+    }
+    for (int k = 0; k < 28; ++k) out28[k] = tile_tot[k];
+}
+
 Sums derivative_sweep(const NdtTarget& tg, const orc_point* src, int n, const double* p, const NdtConsts& K, int search, int threads) {
     float T[12]; pose_to_matrix(p, T);
     AngDeriv A; angle_derivatives(p, &A);
     const double d1 = K.d1; const float d2 = (float)K.d2;
-    // per-point contributions summed in ascending point order (ndt_omp: "invariant against the summing up order")
-    std::vector<Sums> per((size_t)std::max(n, 1));
-#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+    const int n_tiles = (n + kTile - 1) / kTile;
+    std::vector<Sums> per((size_t)std::max(n_tiles, 1));
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 1)
+    for (int t = 0; t < n_tiles; ++t) sweep_tile(tg, src, n, t, T, A, d1, d2, search, per[(size_t)t].v);
+    Sums tot; for (int k = 0; k < 28; ++k) tot.v[k] = 0.0;
+    for (int t = 0; t < n_tiles; ++t) for (int k = 0; k < 28; ++k) tot.v[k] += per[(size_t)t].v[k];
+    return tot;
+}
+
+// Plain per-point summation in ascending point order (what a single-threaded ndt_omp does): kept as the cross-check
+// of the canonical order above (tests/test_ndt_oracle.py: the two agree to ~1e-13 relative).
+Sums derivative_sweep_sequential(const NdtTarget& tg, const orc_point* src, int n, const double* p, const NdtConsts& K, int search) {
+    float T[12]; pose_to_matrix(p, T);
+    AngDeriv A; angle_derivatives(p, &A);
+    const double d1 = K.d1; const float d2 = (float)K.d2;
+    const int ncell = search == 2 ? 27 : (search == 1 ? 7 : 1);
+    const float radius2 = tg.resolution * tg.resolution;
+    Sums tot; for (int k = 0; k < 28; ++k) tot.v[k] = 0.0;
     for (int i = 0; i < n; ++i) {
-        Sums s; for (int k = 0; k < 28; ++k) s.v[k] = 0.0;
         const float x[3] = {src[i].x, src[i].y, src[i].z};
         const float xt[3] = {T[0] * x[0] + T[1] * x[1] + T[2] * x[2] + T[3], T[4] * x[0] + T[5] * x[1] + T[6] * x[2] + T[7],
                              T[8] * x[0] + T[9] * x[1] + T[10] * x[2] + T[11]};
-        // search: 0 DIRECT1 (the point's voxel), 1 DIRECT7 (+ the six face neighbours), 2 KDTREE (radiusSearch over the leaf
-        // centroids with radius = resolution: squared float distance < radius^2, FLANN RadiusResultSet; such a centroid can
-        // only belong to one of the 27 voxels around the point's voxel).  ndt_omp sums the neighbours in FLANN's distance
-        // order; here in voxel order -- the sums are double, the difference is in their last bits.
-        const int ncell = search == 2 ? 27 : (search == 1 ? 7 : 1);
-        const float radius2 = tg.resolution * tg.resolution;
         for (int c = 0; c < ncell; ++c) {
             const int dx = ncell == 27 ? c % 3 - 1 : kDisp7[c][0], dy = ncell == 27 ? (c / 3) % 3 - 1 : kDisp7[c][1], dz = ncell == 27 ? c / 9 - 1 : kDisp7[c][2];
             const int li = tg.lookup(xt[0], xt[1], xt[2], dx, dy, dz);
@@ -315,18 +392,16 @@ Sums derivative_sweep(const NdtTarget& tg, const orc_point* src, int n, const do
                 if (!(ex * ex + ey * ey + ez * ez < radius2)) continue;
             }
             float t[28];
-            point_cell_terms(x, xt, tg.leaves[(size_t)li], A, d1, d2, t);
-            for (int k = 0; k < 28; ++k) s.v[k] += (double)t[k];
+            if (point_cell_terms(x, xt, tg.leaves[(size_t)li], A, d1, d2, t)) for (int k = 0; k < 28; ++k) tot.v[k] += (double)t[k];
         }
-        per[(size_t)i] = s;
     }
-    Sums tot; for (int k = 0; k < 28; ++k) tot.v[k] = 0.0;
-    for (int i = 0; i < n; ++i) for (int k = 0; k < 28; ++k) tot.v[k] += per[(size_t)i].v[k];
     return tot;
 }
 
-// Newton direction: pseudo-inverse solve of the symmetric 6x6 (JacobiSVD(H).solve(-g))
-void newton_solve(const double* Hup /*21*/, const double* g, double* dp) {
+// Newton direction: JacobiSVD(H).solve(-g) of the symmetrised 6x6 Hessian.
+// newton_solve_pinv: the pseudo-inverse through a Jacobi eigen-decomposition (== JacobiSVD::solve for a symmetric matrix:
+// directions whose singular value is below 6 eps smax are dropped).
+void newton_solve_pinv(const double* Hup /*21*/, const double* g, double* dp) {
     double H[36], w[6], V[36];
     int k = 0;
     for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { H[i * 6 + j] = Hup[k]; H[j * 6 + i] = Hup[k]; ++k; }
@@ -342,6 +417,45 @@ void newton_solve(const double* Hup /*21*/, const double* g, double* dp) {
         proj /= w[m];
         for (int i = 0; i < 6; ++i) dp[i] += V[i * 6 + m] * proj;
     }
+}
+
+// CANONICAL Newton solve (shared with the device, ndt.cuh ndt_newton_solve): when H is well conditioned the
+// minimum-norm solution IS H^-1 (-g); it is then computed by Gaussian elimination with partial pivoting in double
+// (first row of maximal |pivot|; accepted when min |pivot| > 1e-10 max |pivot|), which costs a fraction of the Jacobi
+// sweeps; otherwise the pseudo-inverse above.  The two agree to ~1e-12 relative where the fast path applies
+// (tests/test_ndt_oracle.py::test_newton_paths_agree); the choice only fixes WHICH last bits both sides share.
+void newton_solve(const double* Hup /*21*/, const double* g, double* dp) {
+    double M[6][7];
+    {
+        int k = 0;
+        for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { M[i][j] = Hup[k]; M[j][i] = Hup[k]; ++k; }
+    }
+    for (int i = 0; i < 6; ++i) M[i][6] = -g[i];
+    double pmin = 1e300, pmax = 0.0;
+    bool ok = true;
+    for (int c = 0; c < 6; ++c) {
+        int pr = c; double best = std::fabs(M[c][c]);
+        for (int r = c + 1; r < 6; ++r) { const double v = std::fabs(M[r][c]); if (v > best) { best = v; pr = r; } }
+        if (!(best > 0.0) || best != best) ok = false;
+        if (pr != c) for (int j = c; j < 7; ++j) std::swap(M[c][j], M[pr][j]);
+        pmin = std::min(pmin, best); pmax = std::max(pmax, best);
+        const double inv = 1.0 / M[c][c];
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = M[r][c] * inv;
+            for (int j = c + 1; j < 7; ++j) M[r][j] -= f * M[c][j];
+        }
+    }
+    if (ok && pmin > 1e-10 * pmax) {
+        double x[6];
+        for (int i = 5; i >= 0; --i) {
+            double v = M[i][6];
+            for (int j = i + 1; j < 6; ++j) v -= M[i][j] * x[j];
+            x[i] = v / M[i][i];
+        }
+        for (int i = 0; i < 6; ++i) dp[i] = x[i];
+        return;
+    }
+    newton_solve_pinv(Hup, g, dp);
 }
 
 // ---- More-Thuente helpers (computeStepLengthMT and friends) --------------------------------------------
@@ -429,6 +543,7 @@ void orc_ndt_matrix_to_pose(const float* T12, double* p6) { matrix_to_pose(T12, 
 // the Newton direction of computeTransformation (JacobiSVD(H).solve(-g)) and the cubic / quadratic trial value of the
 // More-Thuente step (trialValueSelectionMT), exposed for the known-answer tests
 void orc_ndt_newton(const double* Hup21, const double* g6, double* dp6) { newton_solve(Hup21, g6, dp6); }
+void orc_ndt_newton_pinv(const double* Hup21, const double* g6, double* dp6) { newton_solve_pinv(Hup21, g6, dp6); }
 double orc_ndt_trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
     return trial_value_mt(a_l, f_l, g_l, a_u, f_u, g_u, a_t, f_t, g_t);
 }
@@ -437,6 +552,13 @@ double orc_ndt_trial_value(double a_l, double f_l, double g_l, double a_u, doubl
 void orc_ndt_derivatives(void* tp, const orc_point* src, int n, const double* p6, const orc_ndt_opts* o, double* out28) {
     const NdtConsts K = gauss_consts(o->resolution, o->outlier_ratio);
     const Sums s = derivative_sweep(*static_cast<NdtTarget*>(tp), src, n, p6, K, o->search, o->threads);
+    std::memcpy(out28, s.v, sizeof(s.v));
+}
+
+// the same sums in plain ascending point order (cross-check of the canonical order)
+void orc_ndt_derivatives_sequential(void* tp, const orc_point* src, int n, const double* p6, const orc_ndt_opts* o, double* out28) {
+    const NdtConsts K = gauss_consts(o->resolution, o->outlier_ratio);
+    const Sums s = derivative_sweep_sequential(*static_cast<NdtTarget*>(tp), src, n, p6, K, o->search);
     std::memcpy(out28, s.v, sizeof(s.v));
 }
 

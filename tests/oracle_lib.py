@@ -357,6 +357,8 @@ lib.orc_ndt_pose_to_matrix.argtypes = [C.c_void_p, C.c_void_p]
 lib.orc_ndt_matrix_to_pose.argtypes = [C.c_void_p, C.c_void_p]
 lib.orc_ndt_derivatives.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(NdtOpts), C.c_void_p]
 lib.orc_ndt_newton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.orc_ndt_newton_pinv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.orc_ndt_derivatives_sequential.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(NdtOpts), C.c_void_p]
 lib.orc_ndt_trial_value.restype = C.c_double
 lib.orc_ndt_trial_value.argtypes = [C.c_double] * 9
 lib.orc_ndt_align.restype = C.c_int
@@ -408,6 +410,15 @@ def ndt_derivatives(target: NdtTarget, src, p6, opts: NdtOpts):
     return out
 
 
+def ndt_derivatives_sequential(target: NdtTarget, src, p6, opts: NdtOpts):
+    """The same 28 sums in plain ascending point order (cross-check of the canonical tile order)."""
+    s = _c(src)
+    p = np.ascontiguousarray(p6, np.float64).reshape(6)
+    out = np.empty(28, np.float64)
+    lib.orc_ndt_derivatives_sequential(target._h, _p(s), len(s), _p(p), C.byref(opts), _p(out))
+    return out
+
+
 def ndt_align(target: NdtTarget, src, guess12, opts: NdtOpts):
     """guess12 / result: (3,4) float32 = top rows of the 4x4 Eigen::Matrix4f of registration->align(out, guess)."""
     s = _c(src)
@@ -424,6 +435,15 @@ def ndt_newton(H, g):
     up = np.ascontiguousarray([H[i, j] for i in range(6) for j in range(i, 6)], np.float64)
     dp = np.zeros(6, np.float64)
     lib.orc_ndt_newton(_p(up), _p(g), _p(dp))
+    return dp
+
+
+def ndt_newton_pinv(H, g):
+    """The pure pseudo-inverse solve (Jacobi eigen-decomposition), the fallback branch of ndt_newton."""
+    H = np.asarray(H, np.float64); g = np.ascontiguousarray(g, np.float64)
+    up = np.ascontiguousarray([H[i, j] for i in range(6) for j in range(i, 6)], np.float64)
+    dp = np.zeros(6, np.float64)
+    lib.orc_ndt_newton_pinv(_p(up), _p(g), _p(dp))
     return dp
 
 

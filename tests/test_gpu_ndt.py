@@ -1,6 +1,8 @@
 """GPU parity tests of the relo-mode NDT path (C ABI liloc_ndt_*) against the oracle (oracle/ndt_oracle.cpp).
-Per-point terms follow the same float32 operation sequence on both sides; sums are double with a different
-(fixed) order, so derivatives agree to ~1e-12 relative and final poses within the north_star tolerance."""
+Per-point terms follow the same float32 operation sequence on both sides and the 28 double sums are added in ONE
+canonical order on both sides (oracle/ndt_oracle.cpp derivative_sweep <-> ndt.cuh ndt_sweep_tile), so the sums are
+bit-identical, the Newton / More-Thuente iteration takes the same path (iterations and sweeps exact) and final
+poses agree far inside the north_star tolerance (1e-4 m, 1e-5 rad)."""
 import numpy as np
 import pytest
 
@@ -28,12 +30,16 @@ def test_derivatives_match_oracle(gpu_ctx, orc, synth, ndt_scene):
     gpu_ctx.ndt_source_put(2, src)
     tg = orc.NdtTarget(sub, 1.0)
     rng = np.random.default_rng(1)
+    exact = total = 0
     for search in (0, 1, 2):             # DIRECT1, DIRECT7, KDTREE
         for _ in range(4):
             p = orc.ndt_matrix_to_pose(guess_matrix(synth, truth + np.r_[rng.uniform(-0.03, 0.03, 3), rng.uniform(-0.5, 0.5, 3)]))
             got = gpu_ctx.ndt_derivatives(2, 2, p, NdtOpts(search=search))
             ref = orc.ndt_derivatives(tg, src, p, orc.NdtOpts(resolution=1.0, search=search, threads=8))
-            assert np.allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+            # same float terms, same summation order: identical up to the (float-rounded) transcendental functions
+            assert np.allclose(got, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max()), np.abs(got - ref).max()
+            exact += int(np.array_equal(got, ref)); total += 1
+    assert exact >= total - 1, (exact, total)
 
 
 def _pose_err(T, Tref):
@@ -85,6 +91,61 @@ def test_two_pass_align_and_batch_independence(gpu_ctx, orc, synth, ndt_scene):
     Tr2, _ = orc.ndt_align(tg, src, Tr, orc.NdtOpts(resolution=1.0, threads=8))
     dt, dR = _pose_err(T2[0], Tr2)
     assert dt <= 1e-4 and dR <= 1e-5
+
+
+def _bench_workload(name):
+    import types
+    import bench
+    return bench.make_ndt_workload(types.SimpleNamespace(seed={"relo": 4000, "jfgo": 5000}[name], workload=name, items=0, submaps=64))
+
+
+def _check_workload_against_oracle(gpu_ctx, orc, w, res=1.0):
+    """Every job of a bench workload: iterations / sweeps / convergence exact, pose inside the north_star tolerance."""
+    from liloc_b200 import NdtOpts
+    gpu_ctx.ndt_clear()
+    for t, pts in w["targets"].items():
+        gpu_ctx.ndt_target_put(int(t), pts, res)
+    for s_, pts in w["sources"].items():
+        gpu_ctx.ndt_source_put(int(s_), pts)
+    T, score, iters, conv, sweeps = gpu_ctx.ndt_align_batch(w["tid"], w["sid"], w["guesses"], NdtOpts(trans_eps=0.01, search=0, n_align=w["n_align"]))
+    o = orc.NdtOpts(resolution=res, trans_eps=0.01, search=0, threads=8)
+    tgs = {}
+    bad, worst_t, worst_r, n_max_iter, n_far = [], 0.0, 0.0, 0, 0
+    for j in range(len(w["guesses"])):
+        t = int(w["tid"][j])
+        if t not in tgs:
+            tgs[t] = orc.NdtTarget(w["targets"][t], np.float32(res))
+        Tr, it, sw = w["guesses"][j][:3], 0, 0
+        for _ in range(w["n_align"]):
+            Tr, rr = orc.ndt_align(tgs[t], w["sources"][int(w["sid"][j])], Tr, o)
+            it += rr.iterations; sw += rr.sweeps
+        dt, dR = _pose_err(T[j], Tr)
+        worst_t, worst_r = max(worst_t, dt), max(worst_r, dR)
+        n_max_iter += int(rr.iterations >= 36)
+        n_far += int(np.abs(Tr[:3, 3] - w["guesses"][j][:3, 3]).max() > 0.5)
+        if (iters[j], sweeps[j], conv[j]) != (it, sw, rr.converged) or dt > 1e-4 or dR > 1e-5:
+            bad.append((j, iters[j], sweeps[j], it, sw, dt, dR))
+        assert abs(score[j] - rr.score) <= 1e-9 * max(1.0, abs(rr.score)), (j, score[j], rr.score)
+    assert not bad, bad[:8]
+    return worst_t, worst_r, n_max_iter, n_far
+
+
+def test_bench_relo_workload_matches_oracle(gpu_ctx, orc):
+    """BASELINE configs[3] exactly as `bench.py --workload relo` runs it: 256 hypotheses (16 yaw offsets over the full circle
+    x 16 positions), 2 x align each (src/mapOptmization.cpp:282-290) -- EVERY job against the oracle, including the
+    hypotheses half a turn off, the ones that run into max_iterations and the sign-flipped directions."""
+    w = _bench_workload("relo")
+    assert len(w["guesses"]) == 256 and w["n_align"] == 2
+    worst_t, worst_r, n_max_iter, n_far = _check_workload_against_oracle(gpu_ctx, orc, w)
+    assert n_far > 20                          # the far hypotheses really move (or wander) a long way
+
+
+def test_bench_jfgo_workload_matches_oracle(gpu_ctx, orc):
+    """BASELINE configs[4]a as `bench.py --workload jfgo` runs it: one scan against K = 64 prior submaps
+    (anchorOptimize.hpp:394-407) -- every job against the oracle (most submaps do not overlap the scan at all)."""
+    w = _bench_workload("jfgo")
+    assert len(w["guesses"]) == 64
+    _check_workload_against_oracle(gpu_ctx, orc, w)
 
 
 def test_ndt_errors(gpu_ctx):

@@ -8,9 +8,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _guess_matrix(synth, pose6):
-    T = np.zeros((3, 4), np.float32)
-    T[:, :3] = synth.rot_zyx(*[float(v) for v in pose6[:3]]); T[:, 3] = pose6[3:]
-    return T
+    """The init_guess bits the host class hands to align (float32 eulerToRotation, :276-280): the More-Thuente path is only
+    reproducible from the very same starting matrix."""
+    from liloc_b200 import host_api
+    return host_api.euler_to_matrix(pose6)[:3].copy()
 
 
 def _rot_err(synth, a6, b6):
@@ -84,7 +85,6 @@ def test_relo_mode_through_host_class(orc, synth):
         assert np.abs(got[3:] - cur[0][3:]).max() < 0.05 and abs(got[2] - cur[0][2]) < 5e-3      # relocalised onto the truth
         assert rep.keyframe_id == 0                                                              # every relo frame is a keyframe
         # following frames: scan2map against the current session's keyframes + scan matching against the prior submap
-        n_same = 0
         for f in range(1, len(cur)):
             rep = m.handle(infos[f])
             assert rep.processed == 1 and rep.status == 0 and rep.keyframe_id == f and rep.iters > 0
@@ -95,15 +95,11 @@ def test_relo_mode_through_host_class(orc, synth):
             sub = np.concatenate([orc.transform_cloud(prior_clouds[k], prior_traj[k].astype(np.float32), threads=8) for k in range(lo, lo + 10)])
             Tm, rr = orc.ndt_align(orc.NdtTarget(sub, res), scans[f], _guess_matrix(synth, pose), o)
             got = np.array(rep.relo_pose, np.float32)
-            # Started this close to the optimum, More-Thuente's branch tests compare function values that differ only in
-            # their last bits, so two summation orders (the oracle's OpenMP partition, the device's tile tree -- and
-            # ndt_omp itself across thread counts) can take a different number of steps.  Same path => north_star
-            # tolerance; different path => both stopped by the same |step| < ndtEpsilon (0.01) rule, centimetre-level.
-            assert rep.relo_converged == rr.converged and abs(rep.relo_iterations - rr.iterations) <= 4
-            same_path = rep.relo_iterations == rr.iterations
-            assert np.abs(got[3:] - Tm[:, 3]).max() <= (1e-4 if same_path else 1e-2)
-            assert np.abs(synth.rot_zyx(*[float(v) for v in got[:3]]) - Tm[:, :3]).max() <= (1e-5 if same_path else 1e-3)
-            n_same += same_path
+            # one canonical summation order on both sides (ndt.cuh ndt_sweep_tile <-> oracle derivative_sweep): the
+            # More-Thuente iteration takes the same path, so the north_star tolerance holds for every frame
+            assert rep.relo_converged == rr.converged and rep.relo_iterations == rr.iterations
+            assert np.abs(got[3:] - Tm[:, 3]).max() <= 1e-4
+            assert np.abs(synth.rot_zyx(*[float(v) for v in got[:3]]) - Tm[:, :3]).max() <= 1e-5
             assert np.abs(got[3:5] - cur[f][3:5]).max() < 0.2       # NDT at 1 m resolution with eps 0.01: decimetre-level
             # prior vertices within 5 m (at most 3, nearest first) and their ICP fitness against the matched scan
             d2 = ((prior_traj[lo:lo + 10, 3:].astype(np.float32) - pose[3:]) ** 2).sum(1)
@@ -112,7 +108,6 @@ def test_relo_mode_through_host_class(orc, synth):
             for v, vid in enumerate(near):
                 want = orc.icp_fitness(prior_clouds[vid], prior_traj[vid].astype(np.float32), scans[f], got, threads=8)
                 assert rep.relo_fitness[v] == np.float32(min(want, 2.0)), (f, v, rep.relo_fitness[v], want)
-        assert n_same >= 3
 
 
 def test_icp_fitness_bit_exact(gpu_ctx, orc, synth):

@@ -194,6 +194,38 @@ def test_newton_direction_is_the_minimum_norm_solution(orc):
     assert np.allclose(orc.ndt_newton(H, g), -g / np.diag(H))
 
 
+def test_newton_paths_agree(orc):
+    """The canonical Newton solve (elimination when well conditioned, pseudo-inverse otherwise; shared with the device)
+    against the pure pseudo-inverse (JacobiSVD semantics): same direction to ~1e-10 on Hessians shaped like the NDT ones
+    (translation block ~1e3, rotation block ~1e5, indefinite far from the optimum)."""
+    rng = np.random.default_rng(11)
+    S = np.diag([30.0, 30.0, 30.0, 300.0, 300.0, 300.0])
+    for k in range(50):
+        A = rng.normal(size=(6, 6)); H = S @ (A @ A.T - (1.5 if k % 3 == 0 else 0.0) * np.eye(6)) @ S; g = S @ rng.normal(size=6) * 10
+        a = orc.ndt_newton(H, g); b = orc.ndt_newton_pinv(H, g)
+        assert np.allclose(a, b, rtol=1e-8, atol=1e-12 * np.abs(b).max()), (k, a, b)
+    # singular: both drop the null space (the elimination refuses the tiny pivot)
+    B = rng.normal(size=(6, 3)); H = B @ B.T; g = B @ rng.normal(size=3)
+    assert np.allclose(orc.ndt_newton(H, g), orc.ndt_newton_pinv(H, g), rtol=1e-9, atol=1e-12)
+
+
+def test_canonical_summation_order(orc, synth, ndt_scene):
+    """The 28 sums are added in ONE fixed order (1024-point tiles, 8 warps of 4 x 32 points, hits dealt to 32 accumulators,
+    butterfly, warps, tiles -- oracle/ndt_oracle.cpp derivative_sweep): bit-identical for every thread count, and equal to the
+    plain ascending-point-order sums up to double rounding."""
+    sub, src, truth = ndt_scene
+    tg = orc.NdtTarget(sub, 1.0)
+    rng = np.random.default_rng(2)
+    for search in (0, 1, 2):
+        for n in (len(src), 1024, 1025, 37):
+            p = orc.ndt_matrix_to_pose(guess_matrix(synth, truth + np.r_[rng.uniform(-0.03, 0.03, 3), rng.uniform(-0.5, 0.5, 3)]))
+            ref = orc.ndt_derivatives(tg, src[:n], p, orc.NdtOpts(resolution=1.0, search=search, threads=1))
+            for th in (2, 3, 8):
+                assert np.array_equal(ref, orc.ndt_derivatives(tg, src[:n], p, orc.NdtOpts(resolution=1.0, search=search, threads=th)))
+            seq = orc.ndt_derivatives_sequential(tg, src[:n], p, orc.NdtOpts(resolution=1.0, search=search))
+            assert np.allclose(ref, seq, rtol=1e-12, atol=1e-12 * np.abs(seq).max())
+
+
 def test_more_thuente_trial_values(orc):
     """trialValueSelectionMT (More & Thuente 1994, section 4): case 1 picks the cubic minimiser when it is closer to a_l
     than the quadratic one, else their mean; the cubic / quadratic / secant minimisers are checked on polynomials whose

@@ -506,6 +506,7 @@ def run_ndt(args):
     opts = liloc_b200.NdtOpts(trans_eps=0.01, search=0, n_align=w["n_align"])
     res = float(args.resolution)
     ctx = liloc_b200.Context(device=local, max_scan_points=32 * 1800, max_raw_points=1 << 20)
+    parallel.comm_init(ctx)
     pinned_t = {t: torch.from_numpy(np.ascontiguousarray(w["targets"][t])).pin_memory() for t in my_t}
     pinned_s = {x: torch.from_numpy(np.ascontiguousarray(w["sources"][x])).pin_memory() for x in my_s}
     h2d_t = sum(v.numel() * 4 for v in pinned_t.values()); h2d_s = sum(v.numel() * 4 for v in pinned_s.values())
@@ -550,15 +551,15 @@ def run_ndt(args):
     t_e2e, rows2, _, st2, _, ev_e2e = timed(True)
     assert np.array_equal(rows, rows2)               # same work, same answers
     t_dev_max = parallel.max_over_ranks(t_dev, dev); t_e2e_max = parallel.max_over_ranks(t_e2e, dev)
-    sweep_ms = parallel.max_over_ranks(st["sweep_ms"], dev)
-    alg = parallel.sum_over_ranks(st["alg_bytes"], dev); launches = parallel.sum_over_ranks(st["sweep_launches"], dev)
+    sweep_ms = parallel.max_over_ranks(st["kernel_ms"], dev)
+    alg = parallel.sum_over_ranks(st["alg_bytes"], dev); launches = parallel.sum_over_ranks(st["launches"], dev)
     job_sweeps = parallel.sum_over_ranks(st["job_sweeps"], dev)
     if rank != 0:
         ctx.close(); return
     peak, peak_src = load_peaks()
     value, e2e = n * args.steps / t_dev_max, n * args.steps / t_e2e_max
     # roofline of k_ndt_sweep: algorithmic bytes of this rank's launches / their CUDA-event time
-    ach = st["alg_bytes"] / (st["sweep_ms"] * 1e-3) / 1e9 if st["sweep_ms"] > 0 else None
+    ach = st["alg_bytes"] / (st["kernel_ms"] * 1e-3) / 1e9 if st["kernel_ms"] > 0 else None
     truth_hits = None
     cpu = cpu_baseline_ndt(w, args) if (world == 1 and not args.no_cpu) else None
     # Not part of value / e2e: the latency of ONE registration call the way the relo-mode frame makes it (a single job:
@@ -596,10 +597,12 @@ def run_ndt(args):
         "device_s": {"value_pass": ev_dev, "e2e_pass": ev_e2e},
         "roofline": {"bound": "hbm", "kernel": "k_ndt_align, derivative-sweep phases (persistent cooperative kernel: one launch per batch)", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
-                     "avg_sweep_phase_us": st["sweep_ms"] * 1e3 / max(st["sweep_phases"], 1), "sweep_phases_per_step": st["sweep_phases"] / args.steps,
-                     "sweep_share_of_step": sweep_ms * 1e-3 / t_dev_max,
-                     "per_round_us": {"sweep": st["sweep_ms"] * 1e3 / max(st["sweep_phases"], 1), "update": st["update_ms"] * 1e3 / max(st["sweep_phases"], 1),
-                                      "compaction": st["compact_ms"] * 1e3 / max(st["sweep_phases"], 1)},
+                     "kernel_ms_per_step": st["kernel_ms"] / args.steps, "kernel_share_of_step": sweep_ms * 1e-3 / t_dev_max,
+                     "blocks": st["blocks"] / max(st["launches"], 1), "tickets_per_step": st["tickets"] / args.steps, "updates_per_step": st["updates"] / args.steps,
+                     "max_job_sweeps": st["max_job_sweeps"],
+                     "block_time_share": {k: st[f"block_{k}_ms"] / max(st["kernel_ms"] * st["blocks"] / max(st["launches"], 1), 1e-9) for k in ("sweep", "update", "wait")},
+                     "us_per_ticket": st["block_sweep_ms"] * 1e3 / max(st["tickets"], 1), "us_per_update": st["block_update_ms"] * 1e3 / max(st["updates"], 1),
+                     "update_cycles_per_update": {k: v / max(st["updates"], 1) for k, v in zip(("reduce_load", "state_machine", "pose_tables", "store_publish"), st["update_cycles"])},
                      "alg_bytes_per_step_all_ranks": alg / args.steps,
                      "note": "algorithmic bytes = sweeps x (16 P + 36 P c + 224) per job (SURVEY 8d); the leaf gather is served by L2, the per-point math is float with double accumulation"},
         "single_call": single,

@@ -223,6 +223,37 @@ int liloc_ndt_target_size(liloc_ctx* ctx, int target_id);      /* points of the 
 int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts_body, int n, int on_device);
 int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs);
 int liloc_ndt_clear(liloc_ctx* ctx);
+
+/* ---- multi-GPU: one process (or thread) and one context per GPU -------------------------------------------------------
+ * What shards on this path is naturally independent work: relocalisation hypotheses
+ * (src/mapOptmization.cpp:261-305 run for many initial poses), one scan against K prior submaps and offline batches of
+ * (scan, submap, guess) triples (include/egoOptimization/anchorOptimize.hpp:382-421).  Every rank runs its share with NO
+ * data-path collective; the only exchange is one ncclAllGather of 8 floats per item on the context's stream:
+ *   row = {roll, pitch, yaw, x, y, z (RotMtoEuler of the final transform, include/math_tools.h:92-111),
+ *          score / n_source (trans_probability), iterations}
+ * packed on the device by the block that retires the job -- no host staging.  NCCL is bound at run time (dlopen of
+ * libnccl.so.2); the launcher distributes the 128-byte unique id (MPI, torch.distributed, a file ...). */
+#define LILOC_COMM_ID_BYTES 128
+#define LILOC_SHARD_BLOCKS 0          /* contiguous blocks of the item list (lists sorted by submap: grids stay local) */
+#define LILOC_SHARD_ROUND_ROBIN 1     /* items rank, rank + world, ... (lists whose cost correlates with position) */
+int liloc_comm_unique_id(void* id128);                                        /* rank 0: ncclGetUniqueId */
+int liloc_comm_init(liloc_ctx* ctx, int rank, int world, const void* id128);   /* ncclCommInitRank on the context's device; world 1: no NCCL */
+int liloc_comm_destroy(liloc_ctx* ctx);
+/* The share of `rank` under a policy: item indices in the order their rows travel (returns the count; out may be NULL).
+ * Pure index arithmetic: needs neither a context nor a device. */
+int liloc_shard_indices(int n_items, int rank, int world, int policy, int* out, int cap);
+/* gathered rows [world][per_rank][8] (rank-major, each rank's share in liloc_shard_indices order) -> rows_out[n_items][8] */
+int liloc_unshard_rows(const float* rows_all, int n_items, int world, int per_rank, int policy, float* rows_out);
+int liloc_comm_rank(const liloc_ctx* ctx);
+int liloc_comm_world(const liloc_ctx* ctx);
+/* `items` is the FULL list, identical on every rank; targets / sources named by a rank's share must be resident in its
+ * context.  rows_out[n_items][8] comes back complete on every rank.  local_outs (may be NULL): full results of this
+ * rank's share, in share order.  Without liloc_comm_init (world 1) the whole list runs here. */
+int liloc_ndt_align_batch_sharded(liloc_ctx* ctx, const liloc_ndt_job* items, int n_items, const liloc_ndt_opts* opts, int policy,
+                                  float* rows_out, liloc_ndt_out* local_outs);
+/* The gather alone: every rank contributes n_local <= per_rank rows of 8 floats (host), rows_all[world][per_rank][8] comes
+ * back on every rank (short shares zero-padded).  Used for the per-frame results of lio replicas. */
+int liloc_gather_results(liloc_ctx* ctx, const float* rows_local, int n_local, int per_rank, float* rows_all);
 /* leaf records of a target (tests): means[3n] double, icovs[9n] float, counts[n], keys[n] (voxel index) */
 int liloc_ndt_target_get(liloc_ctx* ctx, int target_id, double* means, float* icovs, int* counts, int* keys, int cap);
 /* one derivative sweep at pose p6 = [tx,ty,tz,rx,ry,rz] (tests): out28 = score, gradient[6], Hessian upper[21] */
@@ -244,14 +275,17 @@ int liloc_icp_fitness(liloc_ctx* ctx, const liloc_point* cloud1, int n1, const f
                       const liloc_point* cloud2, int n2, const float* pose6_2, float* score_out);
 int liloc_icp_fitness_resident(liloc_ctx* ctx, int kf_id, const float* pose6_kf, int ndt_source_id, const float* pose6_src, float* score_out);
 
-/* Cumulative NDT counters since liloc_create / liloc_ndt_stats_reset.  A batch is ONE launch of the persistent
- * kernel k_ndt_align; sweep_phases counts its lock-step derivative sweeps, sweep_ms their device time (%globaltimer
- * around each sweep phase incl. its grid barrier, recorded only while timing is enabled); alg_bytes are the
- * ALGORITHMIC bytes of SURVEY.md 8(d): per derivative sweep and job 16 P + 36 P c + 224 (P source points, c cells). */
+/* Cumulative NDT counters since liloc_create / liloc_ndt_stats_reset.  A batch is ONE launch of the persistent,
+ * queue-driven kernel k_ndt_align (no per-sweep launches, no grid barriers): a ticket is a run of 1024-point tiles of one
+ * derivative sweep of one job; the block that completes a sweep runs the job's Newton / More-Thuente step and publishes
+ * the next sweep's tickets.  The *_ms fields are recorded only while timing is enabled (%globaltimer): kernel_ms = first
+ * block's start .. last block's end, block_*_ms = summed over the `blocks` of the launches.  alg_bytes are the ALGORITHMIC
+ * bytes of SURVEY.md 8(d): per derivative sweep and job 16 P + 36 P c + 224 (P source points, c cells per point). */
 typedef struct {
-    long long batches, jobs, sweep_launches, sweep_phases, job_sweeps;
-    double sweep_ms, alg_bytes;
-    double update_ms, compact_ms;   /* device time of the per-job state-machine phases and of the active-list compaction */
+    long long batches, jobs, launches, blocks, tickets, updates, job_sweeps, max_job_sweeps;
+    double kernel_ms, alg_bytes;
+    double block_sweep_ms, block_update_ms, block_wait_ms;
+    double update_cycles[4];        /* SM cycles inside the updates: reduce + load, state machine, pose tables, store + publish */
 } liloc_ndt_stats;
 int liloc_ndt_stats_get(const liloc_ctx* ctx, liloc_ndt_stats* out);
 int liloc_ndt_stats_reset(liloc_ctx* ctx);

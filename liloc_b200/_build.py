@@ -57,7 +57,7 @@ def build_gpu(force: bool = False) -> str:
     target = os.path.join(PKG, "libliloc_gpu.so")
     srcs = _glob(os.path.join(PKG, "csrc"), (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "liloc_gpu.h")]
     if force or not _newer(target, srcs):
-        _run([_nvcc(), *NVCC_FLAGS, "-o", target, os.path.join(PKG, "csrc", "liloc_gpu.cu")])
+        _run([_nvcc(), *NVCC_FLAGS, "-o", target, os.path.join(PKG, "csrc", "liloc_gpu.cu"), "-ldl"])
     return target
 
 

@@ -113,8 +113,9 @@ class NdtOpts(C.Structure):
 
 
 class NdtStats(C.Structure):
-    _fields_ = [(k, C.c_longlong) for k in ("batches", "jobs", "sweep_launches", "sweep_phases", "job_sweeps")] + \
-               [(k, C.c_double) for k in ("sweep_ms", "alg_bytes", "update_ms", "compact_ms")]
+    _fields_ = [(k, C.c_longlong) for k in ("batches", "jobs", "launches", "blocks", "tickets", "updates", "job_sweeps", "max_job_sweeps")] + \
+               [(k, C.c_double) for k in ("kernel_ms", "alg_bytes", "block_sweep_ms", "block_update_ms", "block_wait_ms")] + \
+               [("update_cycles", C.c_double * 4)]
 
 
 class NdtJob(C.Structure):
@@ -206,6 +207,15 @@ def _load() -> C.CDLL:
         "liloc_ndt_stats_get": (C.c_int, [P, C.POINTER(NdtStats)]),
         "liloc_ndt_stats_reset": (C.c_int, [P]),
         "liloc_debug_line": (C.c_int, [P, P, P, C.c_int, P, P]),
+        "liloc_comm_unique_id": (C.c_int, [P]),
+        "liloc_comm_init": (C.c_int, [P, C.c_int, C.c_int, P]),
+        "liloc_comm_destroy": (C.c_int, [P]),
+        "liloc_shard_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int]),
+        "liloc_unshard_rows": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
+        "liloc_comm_rank": (C.c_int, [P]),
+        "liloc_comm_world": (C.c_int, [P]),
+        "liloc_ndt_align_batch_sharded": (C.c_int, [P, C.POINTER(NdtJob), C.c_int, C.POINTER(NdtOpts), C.c_int, P, C.POINTER(NdtOut)]),
+        "liloc_gather_results": (C.c_int, [P, P, C.c_int, C.c_int, P]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -221,7 +231,41 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_last_timing liloc_set_timing liloc_kernel_launches liloc_last_trace liloc_last_clocks liloc_ndt_target_put liloc_ndt_source_put liloc_ndt_align_batch liloc_ndt_clear liloc_ndt_target_get liloc_ndt_derivatives liloc_stats_get liloc_stats_reset liloc_stream liloc_debug_lm6 liloc_debug_plane "
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
-           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance").split()
+           "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance "
+           "liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results").split()
+
+
+COMM_ID_BYTES = 128
+SHARD_BLOCKS, SHARD_ROUND_ROBIN = 0, 1
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0); the launcher hands the 128 bytes to every rank."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.liloc_comm_unique_id(buf)
+    if rc != 0:
+        raise LilocError(rc, (lib.liloc_last_error(None) or b"").decode())
+    return buf.raw
+
+
+def shard_indices(n_items: int, rank: int, world: int, round_robin: bool = False) -> np.ndarray:
+    """liloc_shard_indices: the items of `rank`, in the order their rows travel."""
+    out = np.zeros(max((n_items + world - 1) // world, 1), np.int32)
+    n = lib.liloc_shard_indices(n_items, rank, world, SHARD_ROUND_ROBIN if round_robin else SHARD_BLOCKS, _ptr(out), len(out))
+    if n < 0:
+        raise LilocError(n, "liloc_shard_indices: bad arguments")
+    return out[:n].astype(np.int64)
+
+
+def unshard_rows(rows_all: np.ndarray, n_items: int, round_robin: bool = False) -> np.ndarray:
+    """liloc_unshard_rows: gathered (world, per_rank, 8) rows -> (n_items, 8) in item order."""
+    a = np.ascontiguousarray(rows_all, np.float32)
+    world, per = a.shape[0], a.shape[1]
+    out = np.zeros((n_items, 8), np.float32)
+    rc = lib.liloc_unshard_rows(_ptr(a), n_items, world, per, SHARD_ROUND_ROBIN if round_robin else SHARD_BLOCKS, _ptr(out))
+    if rc != 0:
+        raise LilocError(rc, "liloc_unshard_rows: bad arguments")
+    return out
 
 
 def _cloud(a) -> np.ndarray:
@@ -553,7 +597,7 @@ class Context:
         lib.liloc_ndt_stats_get(self._h, C.byref(st))
         if reset:
             lib.liloc_ndt_stats_reset(self._h)
-        return {k: getattr(st, k) for k, _ in NdtStats._fields_}
+        return {k: (list(getattr(st, k)) if k == "update_cycles" else getattr(st, k)) for k, _ in NdtStats._fields_}
 
     def ndt_clear(self) -> None:
         self._chk(lib.liloc_ndt_clear(self._h))
@@ -573,6 +617,50 @@ class Context:
         self._chk(lib.liloc_ndt_align_batch(self._h, C.cast(jobs.ctypes.data, C.POINTER(NdtJob)), J, C.byref(o),
                                             C.cast(outs.ctypes.data, C.POINTER(NdtOut))))
         return (outs["T"].reshape(J, 4, 4).copy(), outs["score"].copy(), outs["iterations"].copy(), outs["converged"].copy(), outs["sweeps"].copy())
+
+    @staticmethod
+    def _pack_jobs(target_ids, source_ids, guesses):
+        g = np.asarray(guesses, np.float32)
+        J = len(g)
+        jobs = np.zeros(J, _NDT_JOB_DT)
+        jobs["target_id"] = np.asarray(target_ids, np.int32)
+        jobs["source_id"] = np.asarray(source_ids, np.int32)
+        m = np.tile(np.eye(4, dtype=np.float32), (J, 1, 1))
+        m[:, : g.shape[1], :] = g
+        jobs["guess"] = m.reshape(J, 16)
+        return jobs
+
+    # ---- multi-GPU (liloc_comm_*, liloc_ndt_align_batch_sharded, liloc_gather_results) ----
+    def comm_init(self, rank: int, world: int, unique_id: bytes | None) -> None:
+        buf = C.create_string_buffer(unique_id or b"", COMM_ID_BYTES)
+        self._chk(lib.liloc_comm_init(self._h, rank, world, buf if world > 1 else None))
+
+    def comm_destroy(self) -> None:
+        self._chk(lib.liloc_comm_destroy(self._h))
+
+    def comm_world(self) -> tuple[int, int]:
+        return lib.liloc_comm_rank(self._h), lib.liloc_comm_world(self._h)
+
+    def ndt_align_batch_sharded(self, target_ids, source_ids, guesses, opts: NdtOpts | None = None, round_robin: bool = False, want_local: bool = False):
+        """The FULL item list on every rank; this rank runs its share, one ncclAllGather of 8 floats per item.
+        Returns rows (n_items, 8) = {roll, pitch, yaw, x, y, z, score / n_source, iterations} (+ this rank's liloc_ndt_out records)."""
+        jobs = self._pack_jobs(target_ids, source_ids, guesses)
+        n = len(jobs)
+        rows = np.zeros((n, 8), np.float32)
+        o = opts or NdtOpts()
+        rank, world = self.comm_world()
+        outs = np.zeros((n + world - 1) // world, _NDT_OUT_DT) if want_local else None
+        self._chk(lib.liloc_ndt_align_batch_sharded(self._h, C.cast(jobs.ctypes.data, C.POINTER(NdtJob)), n, C.byref(o), SHARD_ROUND_ROBIN if round_robin else SHARD_BLOCKS,
+                                                    _ptr(rows), C.cast(outs.ctypes.data, C.POINTER(NdtOut)) if want_local else None))
+        return (rows, outs) if want_local else rows
+
+    def gather_results(self, rows_local: np.ndarray, per_rank: int) -> np.ndarray:
+        """All-gather of this rank's (n_local <= per_rank, 8) rows -> (world, per_rank, 8) on every rank."""
+        r = np.ascontiguousarray(rows_local, np.float32).reshape(-1, 8)
+        _, world = self.comm_world()
+        out = np.zeros((world, per_rank, 8), np.float32)
+        self._chk(lib.liloc_gather_results(self._h, _ptr(r) if len(r) else None, len(r), per_rank, _ptr(out)))
+        return out
 
     def ndt_target_get(self, target_id: int):
         n = lib.liloc_ndt_target_get(self._h, target_id, None, None, None, None, 0)

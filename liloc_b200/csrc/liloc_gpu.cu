@@ -32,6 +32,7 @@
 #include "s2m.cuh"
 #include "ndt.cuh"
 #include "deskew.cuh"
+#include "nccl_shim.h"
 
 using namespace liloc;
 
@@ -166,11 +167,20 @@ struct liloc_ctx {
     int* d_ndt_active = nullptr;
     bool ndt_views_dirty = true;
     liloc_ndt_stats ndt_stats{};
-    DevBuf<int> ndt_active;
-    DevBuf<NdtPoseCache> ndt_pose;
-    int* d_ndt_counters = nullptr;       // 3 ints
-    unsigned long long* d_ndt_ns = nullptr;
+    DevBuf<NdtHot> ndt_hot;
+    DevBuf<NdtSync> ndt_sync;
+    DevBuf<unsigned long long> ndt_q;    // [0..3] head / tail / finished / error words, then the ticket ring
+    DevBuf<float> ndt_rows;              // packed results {pose6, score / n, iterations} of the last batch, 8 floats per job
+    unsigned long long* d_ndt_prof = nullptr;   // 8 words (ndt.cuh NdtAlignArgs::prof)
     int ndt_max_blocks = 0;
+
+    // multi-GPU: one communicator per context (one context per GPU / process); the only collective is the all-gather of
+    // packed result rows
+    NcclShim::comm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf<float> gather_send, gather_recv;
+    float* h_gather = nullptr;           // pinned staging of the gathered rows
+    size_t h_gather_cap = 0;             // floats
 
     // de-skew (imageProjection): raw sweep in, de-skewed cloud out.  Two output slots: the current sweep (what
     // LILOC_SCAN_DESKEWED refers to) and one staged ahead of it (LILOC_DESKEW_AHEAD), so that the next sweep can be uploaded
@@ -639,8 +649,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deskew, kDeskewThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_deskew cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->dk_blocks_per_sm = per_sm >= 2 ? 2 : 1;
-    CUB_(cudaMalloc(&c->d_ndt_counters, 4 * sizeof(int)));
-    CUB_(cudaMalloc(&c->d_ndt_ns, 3 * sizeof(unsigned long long)));
+    CUB_(cudaMalloc(&c->d_ndt_prof, 16 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_sm_scratch, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMemset(c->d_sm_scratch, 0, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMalloc(&c->d_dk_imu, 4 * kImuMax * sizeof(double)));
@@ -704,7 +713,10 @@ void liloc_destroy(liloc_ctx* c) {
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
     fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
     fr(c->ndt_descs.p);
-    fr(c->ndt_active.p); fr(c->ndt_pose.p); fr(c->d_ndt_counters); fr(c->d_ndt_ns);
+    fr(c->ndt_hot.p); fr(c->ndt_sync.p); fr(c->ndt_q.p); fr(c->ndt_rows.p); fr(c->d_ndt_prof);
+    fr(c->gather_send.p); fr(c->gather_recv.p);
+    if (c->h_gather) cudaFreeHost(c->h_gather);
+    if (c->comm) { nccl().CommDestroy(c->comm); c->comm = nullptr; }
     if (c->h_info) cudaFreeHost(c->h_info);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {c->stream2, c->stream3, c->stream}) if (st) cudaStreamDestroy(st);
@@ -1472,7 +1484,7 @@ extern "C" {
 
 // Voxel-Gaussian grid of the n points at ctx->tmp_pts (already on the device, or assembled there by the pipeline when
 // kf != nullptr): voxel keys + stable sort (k_voxel_pipeline, sort_only), one leaf per voxel run, dense cell table.
-static int ndt_target_build(liloc_ctx* ctx, int target_id, int n, float resolution, const VgProb* assemble, int* n_leaves_out) {
+static int ndt_target_build_into(liloc_ctx* ctx, liloc_ctx::NdtTargetHost& T, int n, float resolution, const VgProb* assemble, int* n_leaves_out) {
     int rc;
     {
         PipeArgs pa{};
@@ -1485,7 +1497,6 @@ static int ndt_target_build(liloc_ctx* ctx, int target_id, int n, float resoluti
     CU(cudaMemcpyAsync(&vp, ctx->fc[0].vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (vp.overflow) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_target_put: leaf size too small for the target extent (PCL overflow guard)");
-    liloc_ctx::NdtTargetHost& T = ctx->ndt_targets[target_id];
     int divb[3];
     divb[0] = vp.mul[1]; divb[1] = vp.mul[1] ? vp.mul[2] / vp.mul[1] : 1;
     divb[2] = (int)floorf(vp.mx[2] * vp.inv_leaf) - vp.minb[2] + 1;
@@ -1502,9 +1513,24 @@ static int ndt_target_build(liloc_ctx* ctx, int target_id, int n, float resoluti
     T.n_leaves = nl; T.resolution = resolution; T.n_points = n;
     T.view.table = T.table.p; T.view.leaves = T.leaves.p; T.view.inv_leaf = vp.inv_leaf;
     for (int a = 0; a < 3; ++a) { T.view.minb[a] = vp.minb[a]; T.view.divb[a] = divb[a]; T.view.maxb[a] = vp.minb[a] + divb[a] - 1; }
-    ctx->ndt_views_dirty = true;
     if (n_leaves_out) *n_leaves_out = nl;
     return LILOC_OK;
+}
+
+// A failed build must not leave a half-made target behind (its view would be dereferenced on the device): the entry of
+// `target_id` is replaced on success and removed on failure.
+static int ndt_target_build(liloc_ctx* ctx, int target_id, int n, float resolution, const VgProb* assemble, int* n_leaves_out) {
+    liloc_ctx::NdtTargetHost& T = ctx->ndt_targets[target_id];
+    T.view = NdtTargetView{};
+    ctx->ndt_views_dirty = true;
+    const int rc = ndt_target_build_into(ctx, T, n, resolution, assemble, n_leaves_out);
+    if (rc != LILOC_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        if (T.table.p) cudaFree(T.table.p);
+        if (T.leaves.p) cudaFree(T.leaves.p);
+        ctx->ndt_targets.erase(target_id);
+    }
+    return rc;
 }
 
 int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts, int n, float resolution, int* n_leaves_out) {
@@ -1585,71 +1611,100 @@ int liloc_ndt_clear(liloc_ctx* ctx) {
     return LILOC_OK;
 }
 
-int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs) {
-    ENTER(ctx);
-    if (n_jobs <= 0 || !jobs || !outs) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: bad arguments");
-    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
+// One batch of alignments = one launch of the queue-driven persistent kernel (ndt.cuh).  hj: host copies of the job
+// records, filled on return when `fetch_jobs`; the packed 8-float rows stay in ctx->ndt_rows (device) for the gather.
+static int ndt_run_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* o, std::vector<NdtJob>& hj, bool fetch_jobs) {
     int rc;
     if ((rc = ndt_sync_views(ctx))) return rc;
-    std::vector<NdtJob> hj((size_t)n_jobs);
+    if (n_jobs > kNdtMaxJobs) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_align_batch: more than %d jobs in one batch", kNdtMaxJobs);
+    hj.assign((size_t)n_jobs, NdtJob{});
     int max_n = 0;
+    long long total_tiles = 0;
     float resolution = -1.f;
     for (int j = 0; j < n_jobs; ++j) {
         auto ti = ctx->ndt_targets.find(jobs[j].target_id);
         auto si = ctx->ndt_sources.find(jobs[j].source_id);
         if (ti == ctx->ndt_targets.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown target id %d", jobs[j].target_id);
         if (si == ctx->ndt_sources.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown source id %d", jobs[j].source_id);
+        if (!ti->second.view.table) return fail(ctx, LILOC_ERR_STATE, "ndt_align_batch: target id %d was not built", jobs[j].target_id);
         if (resolution < 0.f) resolution = ti->second.resolution;
         else if (resolution != ti->second.resolution) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: all targets of one batch must share the resolution");
-        std::memset(&hj[j], 0, sizeof(NdtJob));
         hj[j].target = ti->second.slot; hj[j].source = si->second.slot;
         hj[j].n_tiles = (si->second.view.n + kNdtTile - 1) / kNdtTile;
+        if (hj[j].n_tiles > kNdtMaxTilesPerJob) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_align_batch: source %d has more than %d points", jobs[j].source_id, kNdtMaxTilesPerJob * kNdtTile);
         std::memcpy(hj[j].guess, jobs[j].guess, 12 * sizeof(float));     // top 3 rows of the row-major 4x4
         if (si->second.view.n > max_n) max_n = si->second.view.n;
+        total_tiles += hj[j].n_tiles;
     }
     const NdtOptsDev od = ndt_opts_dev(o, resolution);
     const int tiles = (max_n + kNdtTile - 1) / kNdtTile;
+    long long blocks = total_tiles < ctx->ndt_max_blocks ? total_tiles : ctx->ndt_max_blocks;
+    if (blocks < 1) blocks = 1;
+    size_t cap = 1024;
+    while (cap < 2 * ((size_t)total_tiles + (size_t)blocks)) cap *= 2;
     if ((rc = ensure(ctx, ctx->d_jobs, (size_t)n_jobs))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_partial, (size_t)n_jobs * tiles * kNdtSums))) return rc;
-    if ((rc = ensure(ctx, ctx->ndt_active, (size_t)2 * n_jobs))) return rc;
-    if ((rc = ensure(ctx, ctx->ndt_pose, (size_t)n_jobs))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_hot, (size_t)n_jobs))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_sync, (size_t)n_jobs))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_rows, (size_t)n_jobs * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->ndt_q, 4 + cap))) return rc;
     CU(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
-    CU(cudaMemsetAsync(ctx->d_ndt_ns, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->ndt_q.p, 0, (4 + cap) * sizeof(unsigned long long), ctx->stream));     // counters + every ticket tag
+    if (ctx->timing) {
+        CU(cudaMemsetAsync(ctx->d_ndt_prof, 0xFF, sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_ndt_prof + 1, 0, 15 * sizeof(unsigned long long), ctx->stream));
+    }
     NdtAlignArgs aa{};
     aa.jobs = ctx->d_jobs.p; aa.n_jobs = n_jobs; aa.targets = ctx->d_tviews.p; aa.sources = ctx->d_sviews.p; aa.o = od;
-    aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.pose = ctx->ndt_pose.p; aa.active = ctx->ndt_active.p; aa.counters = ctx->d_ndt_counters;
-    aa.sweep_ns = ctx->timing ? ctx->d_ndt_ns : nullptr;
-    // worst case per align pass: first sweep + (max_iterations + 2) x (1 + 10) line-search sweeps
-    aa.max_sweeps = od.n_align * (1 + (od.max_iterations + 2) * 11);
-    {
-        long long work = (long long)n_jobs * tiles;
-        long long blocks = work < ctx->ndt_max_blocks ? work : ctx->ndt_max_blocks;
-        if (blocks < 1) blocks = 1;
-        void* args[] = {&aa};
-        CU(cudaLaunchCooperativeKernel((void*)k_ndt_align, dim3((unsigned)blocks), dim3(kNdtThreads), args, 0, ctx->stream));
-        ++ctx->launches;
+    aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.hot = ctx->ndt_hot.p; aa.sync = ctx->ndt_sync.p;
+    unsigned* qw = reinterpret_cast<unsigned*>(ctx->ndt_q.p);
+    aa.q.head = qw; aa.q.tail = qw + 2; aa.q.finished = reinterpret_cast<int*>(qw + 4); aa.q.error = reinterpret_cast<int*>(qw + 6);
+    aa.q.ring = ctx->ndt_q.p + 4; aa.q.mask = (unsigned)(cap - 1);
+    aa.rows = ctx->ndt_rows.p;
+    aa.prof = ctx->timing ? ctx->d_ndt_prof : nullptr;
+    k_ndt_align<<<(unsigned)blocks, kNdtThreads, 0, ctx->stream>>>(aa); KCHECK();
+    unsigned long long h_q[4] = {0, 0, 0, 0}, h_prof[16] = {0};
+    CU(cudaMemcpyAsync(h_q, ctx->ndt_q.p, sizeof(h_q), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->timing) CU(cudaMemcpyAsync(h_prof, ctx->d_ndt_prof, sizeof(h_prof), cudaMemcpyDeviceToHost, ctx->stream));
+    if (fetch_jobs) {
+        CU(cudaMemcpyAsync(hj.data(), ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
     }
-    int h_counters[3] = {0, 0, 0};
-    unsigned long long h_ns[3] = {0, 0, 0};
-    CU(cudaMemcpyAsync(h_counters, ctx->d_ndt_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(h_ns, ctx->d_ndt_ns, sizeof(h_ns), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(hj.data(), ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
+    if ((int)(h_q[3] & 0xFFFFFFFFu) != 0) return fail(ctx, LILOC_ERR_CUDA, "ndt_align_batch: a block gave up waiting for a ticket (queue stalled)");
+    if ((int)(h_q[2] & 0xFFFFFFFFu) != n_jobs) return fail(ctx, LILOC_ERR_CUDA, "ndt_align_batch: %d of %d jobs retired", (int)(h_q[2] & 0xFFFFFFFFu), n_jobs);
     {
         liloc_ndt_stats& ns = ctx->ndt_stats;
-        ns.batches += 1; ns.jobs += n_jobs; ns.sweep_launches += 1; ns.sweep_phases += h_counters[2];
-        ns.sweep_ms += (double)h_ns[0] * 1e-6; ns.update_ms += (double)h_ns[1] * 1e-6; ns.compact_ms += (double)h_ns[2] * 1e-6;
-        const int cells = od.search == 2 ? 27 : (od.search == 1 ? 7 : 1);
-        for (int j = 0; j < n_jobs; ++j) {
-            const double P = (double)ctx->ndt_sources[jobs[j].source_id].view.n;
-            ns.job_sweeps += hj[j].total_sweeps;
-            // per sweep and job, the scan once (16 P), a (mean, inverse covariance) gather per point and
-            // cell (36 P c) and 28 doubles out
-            ns.alg_bytes += (double)hj[j].total_sweeps * (16.0 * P + 36.0 * P * cells + 224.0);
+        ns.batches += 1; ns.jobs += n_jobs; ns.launches += 1; ns.blocks += blocks;
+        if (ctx->timing) {
+            ns.kernel_ms += h_prof[1] > h_prof[0] ? (double)(h_prof[1] - h_prof[0]) * 1e-6 : 0.0;
+            ns.block_sweep_ms += (double)h_prof[2] * 1e-6; ns.block_update_ms += (double)h_prof[3] * 1e-6; ns.block_wait_ms += (double)h_prof[4] * 1e-6;
+            ns.tickets += (long long)h_prof[5]; ns.updates += (long long)h_prof[6];
+            for (int k = 0; k < 4; ++k) ns.update_cycles[k] += (double)h_prof[8 + k];
+        }
+        if (fetch_jobs) {
+            const int cells = od.search == 2 ? 27 : (od.search == 1 ? 7 : 1);
+            for (int j = 0; j < n_jobs; ++j) {
+                const double P = (double)ctx->ndt_sources[jobs[j].source_id].view.n;
+                ns.job_sweeps += hj[j].total_sweeps;
+                if (hj[j].total_sweeps > ns.max_job_sweeps) ns.max_job_sweeps = hj[j].total_sweeps;
+                // per sweep and job, the scan once (16 P), a (mean, inverse covariance) gather per point and
+                // cell (36 P c) and 28 doubles out
+                ns.alg_bytes += (double)hj[j].total_sweeps * (16.0 * P + 36.0 * P * cells + 224.0);
+            }
         }
     }
+    return LILOC_OK;
+}
+
+int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs) {
+    ENTER(ctx);
+    if (n_jobs <= 0 || !jobs || !outs) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: bad arguments");
+    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
+    std::vector<NdtJob> hj;
+    int rc;
+    if ((rc = ndt_run_batch(ctx, jobs, n_jobs, o, hj, true))) return rc;
     for (int j = 0; j < n_jobs; ++j) {
         liloc_ndt_out& r = outs[j];
         std::memcpy(r.T, hj[j].Tfinal, 12 * sizeof(float));
@@ -1657,6 +1712,145 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
         r.score = hj[j].score; r.iterations = hj[j].total_iterations; r.converged = hj[j].converged; r.sweeps = hj[j].total_sweeps;
         r.n_source = ctx->ndt_sources[jobs[j].source_id].view.n;
     }
+    return LILOC_OK;
+}
+
+// ---- multi-GPU: sharded batches + the final gather (SURVEY.md 8b liloc_gather_results, 8e) ---------------------------------
+int liloc_comm_unique_id(void* id128) {
+    if (!id128) return LILOC_ERR_ARG;
+    const std::string e = nccl().load();
+    if (!e.empty()) { g_create_error = e; return LILOC_ERR_STATE; }
+    NcclShim::unique_id id;
+    const int r = nccl().GetUniqueId(&id);
+    if (r != 0) { g_create_error = std::string("ncclGetUniqueId: ") + nccl().GetErrorString(r); return LILOC_ERR_CUDA; }
+    std::memcpy(id128, &id, sizeof(id));
+    return LILOC_OK;
+}
+
+int liloc_comm_init(liloc_ctx* ctx, int rank, int world, const void* id128) {
+    ENTER(ctx);
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) return fail(ctx, LILOC_ERR_ARG, "comm_init: bad arguments");
+    if (ctx->comm) { nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    if (world == 1) return LILOC_OK;
+    const std::string e = nccl().load();
+    if (!e.empty()) return fail(ctx, LILOC_ERR_STATE, "comm_init: %s", e.c_str());
+    NcclShim::unique_id id;
+    std::memcpy(&id, id128, sizeof(id));
+    const int r = nccl().CommInitRank(&ctx->comm, world, id, rank);
+    if (r != 0) { ctx->comm = nullptr; return fail(ctx, LILOC_ERR_CUDA, "ncclCommInitRank: %s", nccl().GetErrorString(r)); }
+    return LILOC_OK;
+}
+
+int liloc_comm_destroy(liloc_ctx* ctx) {
+    ENTER(ctx);
+    if (ctx->comm) { CU(cudaStreamSynchronize(ctx->stream)); nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ctx->comm_rank = 0; ctx->comm_world = 1;
+    return LILOC_OK;
+}
+
+// the share of `rank`: item indices in the order their rows travel (no context, no device: pure index arithmetic)
+int liloc_shard_indices(int n_items, int rank, int world, int policy, int* out, int cap) {
+    if (n_items < 0 || world < 1 || rank < 0 || rank >= world || (policy != LILOC_SHARD_BLOCKS && policy != LILOC_SHARD_ROUND_ROBIN)) return LILOC_ERR_ARG;
+    int n = 0;
+    if (policy == LILOC_SHARD_ROUND_ROBIN) {
+        for (int i = rank; i < n_items; i += world, ++n) if (out && n < cap) out[n] = i;
+    } else {
+        const int base = n_items / world, rem = n_items % world;
+        const int lo = rank * base + (rank < rem ? rank : rem), hi = lo + base + (rank < rem ? 1 : 0);
+        for (int i = lo; i < hi; ++i, ++n) if (out && n < cap) out[n] = i;
+    }
+    return n;
+}
+
+// gathered rows [world][per_rank][8] (rank-major, share order) -> rows_out[n_items][8] in item order
+int liloc_unshard_rows(const float* rows_all, int n_items, int world, int per_rank, int policy, float* rows_out) {
+    if (n_items < 0 || world < 1 || per_rank < 0 || (n_items > 0 && (!rows_all || !rows_out)) || (long long)per_rank * world < n_items) return LILOC_ERR_ARG;
+    std::vector<int> idx((size_t)(per_rank > 0 ? per_rank : 1));
+    for (int r = 0; r < world; ++r) {
+        const int n = liloc_shard_indices(n_items, r, world, policy, idx.data(), per_rank);
+        if (n < 0 || n > per_rank) return LILOC_ERR_ARG;
+        for (int k = 0; k < n; ++k) std::memcpy(rows_out + (size_t)idx[k] * 8, rows_all + ((size_t)r * per_rank + k) * 8, 8 * sizeof(float));
+    }
+    return LILOC_OK;
+}
+
+int liloc_comm_rank(const liloc_ctx* ctx) { return ctx ? ctx->comm_rank : LILOC_ERR_ARG; }
+int liloc_comm_world(const liloc_ctx* ctx) { return ctx ? ctx->comm_world : LILOC_ERR_ARG; }
+
+// all-gather of `per_rank` rows of 8 floats from every rank's device buffer `d_send` -> host rows_all[world][per_rank][8]
+static int gather_rows_dev(liloc_ctx* ctx, const float* d_send, int per_rank, float* rows_all) {
+    const int W = ctx->comm_world;
+    const size_t cnt = (size_t)per_rank * 8;
+    int rc;
+    if (cnt == 0) return LILOC_OK;
+    if (cnt * W > ctx->h_gather_cap) {
+        if (ctx->h_gather) { CU(cudaFreeHost(ctx->h_gather)); ctx->h_gather = nullptr; ctx->h_gather_cap = 0; }
+        size_t cap = 4096; while (cap < cnt * W) cap *= 2;
+        CU(cudaMallocHost(&ctx->h_gather, cap * sizeof(float)));
+        ctx->h_gather_cap = cap;
+    }
+    const float* src = d_send;
+    if (W > 1) {
+        if (!ctx->comm) return fail(ctx, LILOC_ERR_STATE, "gather: liloc_comm_init was not called");
+        if ((rc = ensure(ctx, ctx->gather_recv, cnt * W))) return rc;
+        const int r = nccl().AllGather(d_send, ctx->gather_recv.p, cnt, NcclShim::kFloat, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, LILOC_ERR_CUDA, "ncclAllGather: %s", nccl().GetErrorString(r));
+        src = ctx->gather_recv.p;
+    }
+    CU(cudaMemcpyAsync(ctx->h_gather, src, cnt * W * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (long long)(cnt * W * sizeof(float));
+    std::memcpy(rows_all, ctx->h_gather, cnt * W * sizeof(float));
+    return LILOC_OK;
+}
+
+int liloc_gather_results(liloc_ctx* ctx, const float* rows_local, int n_local, int per_rank, float* rows_all) {
+    ENTER(ctx);
+    if (per_rank < 0 || n_local < 0 || n_local > per_rank || (n_local > 0 && !rows_local) || (per_rank > 0 && !rows_all)) return fail(ctx, LILOC_ERR_ARG, "gather_results: bad arguments");
+    if (per_rank == 0) return LILOC_OK;
+    int rc;
+    if ((rc = ensure(ctx, ctx->gather_send, (size_t)per_rank * 8))) return rc;
+    CU(cudaMemsetAsync(ctx->gather_send.p, 0, (size_t)per_rank * 8 * sizeof(float), ctx->stream));
+    if (n_local > 0) CU(cudaMemcpyAsync(ctx->gather_send.p, rows_local, (size_t)n_local * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (long long)n_local * 32;
+    return gather_rows_dev(ctx, ctx->gather_send.p, per_rank, rows_all);
+}
+
+int liloc_ndt_align_batch_sharded(liloc_ctx* ctx, const liloc_ndt_job* items, int n_items, const liloc_ndt_opts* opts, int policy,
+                                  float* rows_out, liloc_ndt_out* local_outs) {
+    ENTER(ctx);
+    if (n_items <= 0 || !items || !rows_out || (policy != LILOC_SHARD_BLOCKS && policy != LILOC_SHARD_ROUND_ROBIN)) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch_sharded: bad arguments");
+    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
+    const int W = ctx->comm_world, R = ctx->comm_rank;
+    const int per = (n_items + W - 1) / W;
+    // this rank's share, in the order its rows are sent
+    std::vector<liloc_ndt_job> mine;
+    auto share_of = [&](int r, std::vector<int>& idx) {
+        idx.resize((size_t)per);
+        idx.resize((size_t)liloc_shard_indices(n_items, r, W, policy, idx.data(), per));
+    };
+    std::vector<int> idx;
+    share_of(R, idx);
+    for (int i : idx) mine.push_back(items[i]);
+    int rc;
+    if ((rc = ensure(ctx, ctx->ndt_rows, (size_t)per * 8))) return rc;
+    std::vector<NdtJob> hj;
+    if (!mine.empty()) {
+        if ((rc = ndt_run_batch(ctx, mine.data(), (int)mine.size(), o, hj, local_outs != nullptr || ctx->timing))) return rc;
+        if (local_outs) for (size_t j = 0; j < mine.size(); ++j) {
+            liloc_ndt_out& r = local_outs[j];
+            std::memcpy(r.T, hj[j].Tfinal, 12 * sizeof(float));
+            r.T[12] = 0.f; r.T[13] = 0.f; r.T[14] = 0.f; r.T[15] = 1.f;
+            r.score = hj[j].score; r.iterations = hj[j].total_iterations; r.converged = hj[j].converged; r.sweeps = hj[j].total_sweeps;
+            r.n_source = ctx->ndt_sources[mine[j].source_id].view.n;
+        }
+    }
+    if ((int)mine.size() < per)         // pad rows of a short share
+        CU(cudaMemsetAsync(ctx->ndt_rows.p + mine.size() * 8, 0, ((size_t)per - mine.size()) * 8 * sizeof(float), ctx->stream));
+    std::vector<float> all((size_t)W * per * 8);
+    if ((rc = gather_rows_dev(ctx, ctx->ndt_rows.p, per, all.data()))) return rc;
+    if (liloc_unshard_rows(all.data(), n_items, W, per, policy, rows_out) != LILOC_OK) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch_sharded: unshard failed");
     return LILOC_OK;
 }
 

@@ -390,15 +390,15 @@ struct NdtSweepShared {
 // One tile (kNdtTile source points) of one derivative sweep of a job at its trial pose: cell look-ups, warp-level
 // compaction of the (point, leaf) hits, float per-hit terms with double accumulation in registers, then ONE
 // warp-shuffle + shared-memory reduction per tile -> 28 doubles at `out`.  All threads of the block call this together.
-template <bool kPoseInGlobal>
+// kPoseStaged: the caller already put the pose tables into sh.pc (and synchronised); otherwise they are copied from `pc`.
+template <bool kPoseStaged>
 LILOC_DEV void ndt_sweep_tile(const NdtPoseCache* __restrict__ pc, const NdtTargetView& tg, const NdtSourceView& src, const NdtOptsDev& o,
                               const int tile, NdtSweepShared& sh, double* __restrict__ out) {
-    __syncthreads();                                      // sh may still be read by the previous tile's tail
-    if (threadIdx.x < kNdtPoseFloats) {                   // written by another block in the previous round: read through L2
-        const float* src_f = reinterpret_cast<const float*>(pc) + threadIdx.x;
-        reinterpret_cast<float*>(&sh.pc)[threadIdx.x] = kPoseInGlobal ? __ldcg(src_f) : *src_f;
+    __syncthreads();                                      // sh.red / sh.hits may still be read by the previous tile's tail
+    if (!kPoseStaged) {
+        if (threadIdx.x < kNdtPoseFloats) reinterpret_cast<float*>(&sh.pc)[threadIdx.x] = reinterpret_cast<const float*>(pc)[threadIdx.x];
+        __syncthreads();
     }
-    __syncthreads();
     double acc[kNdtSums];
 #pragma unroll
     for (int k = 0; k < kNdtSums; ++k) acc[k] = 0.0;
@@ -642,8 +642,10 @@ LILOC_DEV void ndt_newton_solve(const double* Hup, const double* g, double* dp) 
     }
 }
 
-// One step of computeTransformation / computeStepLengthMT given the sums of the sweep at J.x_t.
-__device__ __noinline__ void ndt_job_step(NdtJob& J, const double* sums, const NdtOptsDev& o) {
+// One step of computeTransformation / computeStepLengthMT given the sums of the sweep at J.x_t.  Returns true when a NEW
+// trial pose x_t was set (the caller then evaluates T(x_t) -- final_transformation_ of the line search -- and the angle
+// tables for the next sweep); the 3x4 transform itself is not computed here (six double sin / cos on one lane).
+__device__ __noinline__ bool ndt_job_step(NdtJob& J, const double* sums, const NdtOptsDev& o) {
     const double mu = 1.e-4, nu = 0.9;
     ++J.sweeps;
     J.score = sums[0];
@@ -676,16 +678,15 @@ __device__ __noinline__ void ndt_job_step(NdtJob& J, const double* sums, const N
                 else J.a_t = ndt_trial_value(J.a_l, J.f_l, J.g_l, J.a_u, J.f_u, J.g_u, J.a_t, phi_t, d_phi_t);
                 J.a_t = fmin(J.a_t, o.step_max); J.a_t = fmax(J.a_t, o.step_min);
                 for (int i = 0; i < 6; ++i) J.x_t[i] = J.p[i] + J.dir[i] * J.a_t;
-                ndt_pose_to_matrix(J.x_t, J.Tfinal);
                 J.phase = NDT_LS_LOOP;
-                return;                                   // next sweep at the new trial point
+                return true;                              // next sweep at the new trial point
             }
             need_check = false;
             // line search finished: accept a_t
             for (int i = 0; i < 6; ++i) J.p[i] += J.dir[i] * J.a_t;
             const bool conv = J.nr_iterations > o.max_iterations || (J.nr_iterations && (fabs(J.a_t) < o.eps));
             J.nr_iterations++;
-            if (conv) { J.converged = 1; J.phase = NDT_DONE; return; }
+            if (conv) { J.converged = 1; J.phase = NDT_DONE; return false; }
         }
         // Newton direction from the latest sums (they belong to the current p)
         double dp[6];
@@ -693,7 +694,7 @@ __device__ __noinline__ void ndt_job_step(NdtJob& J, const double* sums, const N
         double norm = 0.0;
         for (int i = 0; i < 6; ++i) norm += dp[i] * dp[i];
         norm = sqrt(norm);
-        if (norm == 0 || norm != norm) { J.converged = (norm == norm) ? 1 : 0; J.phase = NDT_DONE; return; }
+        if (norm == 0 || norm != norm) { J.converged = (norm == norm) ? 1 : 0; J.phase = NDT_DONE; return false; }
         for (int i = 0; i < 6; ++i) J.dir[i] = dp[i] / norm;
         J.phi_0 = -J.score;
         J.d_phi_0 = 0.0;
@@ -703,7 +704,7 @@ __device__ __noinline__ void ndt_job_step(NdtJob& J, const double* sums, const N
                 J.a_t = 0.0;
                 const bool conv = J.nr_iterations > o.max_iterations || (J.nr_iterations && (0.0 < o.eps));
                 J.nr_iterations++;
-                if (conv) { J.converged = 1; J.phase = NDT_DONE; return; }
+                if (conv) { J.converged = 1; J.phase = NDT_DONE; return false; }
                 continue;
             }
             J.d_phi_0 *= -1;
@@ -717,11 +718,11 @@ __device__ __noinline__ void ndt_job_step(NdtJob& J, const double* sums, const N
         J.a_t = norm;
         J.a_t = fmin(J.a_t, o.step_max); J.a_t = fmax(J.a_t, o.step_min);
         for (int i = 0; i < 6; ++i) J.x_t[i] = J.p[i] + J.dir[i] * J.a_t;
-        ndt_pose_to_matrix(J.x_t, J.Tfinal);
         J.phase = NDT_LS_FIRST;
-        return;
+        return true;
     }
     J.phase = NDT_DONE;                                   // unreachable in practice (guard)
+    return false;
 }
 
 // start (or restart, for the second of the reference's two back-to-back align calls) from a 3x4 guess
@@ -733,13 +734,45 @@ LILOC_DEV void ndt_job_begin(NdtJob& J, const float* guess12) {
     J.nr_iterations = 0; J.converged = 0; J.sweeps = 0; J.step_iterations = 0; J.open_interval = 1; J.interval_converged = 0;
 }
 
-// ---- the whole batch of alignments as ONE persistent cooperative kernel ------------------------------------------------
-// Jobs advance in lock-step: a sweep phase (every (active job, point tile) pair is one work item, spread over all
-// blocks), a grid barrier, an update phase (one warp per active job: fixed-order reduction of the tile partials and
-// one step of the Newton / More-Thuente state machine), a barrier, and the compaction of the active-job list.  The
-// host launches once and reads the results back: no polling, no per-sweep launches.  (Letting the block that finishes
-// a job's last tile run that job's update was measured and is slower: the serial state machine stalls the block's
-// remaining tiles.)
+// ---- the whole batch of alignments as ONE persistent kernel driven by a ticket queue ----------------------------------------
+// Round 1 ran the batch in lock-step (sweep phase / grid barrier / update phase / grid barrier / compaction): every round
+// waited for its slowest job, and a batch lasted as many rounds as its longest job needs whatever the number of GPUs
+// (profiles/frame_latency_r01.md).  Now jobs advance INDEPENDENTLY:
+//   * a ticket = (job, first tile, tile count); tickets sit in a ring in global memory; a block claims the next ticket
+//     with ONE atomicAdd on `head` and waits for that slot to be published (entries are tagged with their ticket number, so
+//     a block may hold a ticket that does not exist yet -- that is how idle blocks wait for work);
+//   * the block sweeps the ticket's tiles (ndt_sweep_tile: 28 doubles per tile into `partial`), then adds the tile count to
+//     the job's arrival counter; the block that completes the sweep (all tiles arrived) reduces the tile partials in tile
+//     order (the canonical summation order shared with the oracle), runs ONE step of the Newton / More-Thuente state
+//     machine on a shared-memory copy of the job and either publishes the tickets of the job's next sweep or retires the job;
+//   * no grid barrier, no cooperative launch, no compaction: a job's sweep starts as soon as its previous one is
+//     reduced, on whatever blocks are free.  Ticket granularity adapts: whole jobs while there are several unfinished
+//     jobs per block (no atomics inside a sweep), single tiles when blocks would otherwise idle (a job's sweep then
+//     spreads over up to n_tiles blocks).
+// Results are independent of the schedule: every sum has a fixed order.
+struct NdtSync { int done; int pad; };        // per job: tiles of the current sweep already in `partial`
+
+struct NdtQueue {
+    unsigned long long* ring;      // [cap] (ticket + 1) << 32 | 1 << 31 | job << 10 | first tile
+    unsigned mask;                 // cap - 1, cap a power of two >= the tiles of all jobs + the blocks of the launch
+    unsigned* head;                // next ticket to hand out
+    unsigned* tail;                // tickets published so far
+    int* finished;                 // jobs retired
+    int* error;                    // a wait gave up (1) -- every block leaves
+};
+constexpr int kNdtMaxTilesPerJob = 1024;      // 10 bits of a ring entry (1 M source points)
+constexpr int kNdtMaxJobs = 1 << 21;
+
+struct NdtJobView {                // the constant part of what a tile needs of its job
+    NdtTargetView tg;
+    const float4* pts; int n; int n_tiles;
+};
+// Everything a ticket needs, contiguous: ONE L2 round trip per ticket (104 threads, one word each) instead of the dependent
+// chain job -> source / target views -> pose tables.  view: written once in the prologue; grain, pc: by every update.
+struct NdtHot { NdtJobView view; int grain; int pad; NdtPoseCache pc; };
+constexpr int kNdtHotWords = sizeof(NdtHot) / sizeof(int);
+static_assert(sizeof(NdtHot) % sizeof(int) == 0 && kNdtHotWords <= kNdtThreads, "NdtHot is staged by one word per thread");
+
 struct NdtAlignArgs {
     NdtJob* jobs;
     int n_jobs;
@@ -748,137 +781,264 @@ struct NdtAlignArgs {
     NdtOptsDev o;
     int tiles_max;                 // ceil(max source size / kNdtTile)
     double* partial;               // [n_jobs][tiles_max][kNdtSums]
-    NdtPoseCache* pose;            // [n_jobs] transform + angle tables of every job's current trial pose
-    int* active;                   // [2][n_jobs] double-buffered list of unfinished jobs
-    int* counters;                 // [0..1] list lengths, [2] sweep phases executed
-    unsigned long long* sweep_ns;  // [0] accumulated time of the sweep phases, [1] update phases, [2] compaction phases (block 0; optional)
-    int max_sweeps;
+    NdtHot* hot;                   // [n_jobs] view + ticket granularity + transform / angle tables of the job's current trial pose
+    NdtSync* sync;                 // [n_jobs]
+    NdtQueue q;
+    float* rows;                   // [n_jobs][8] packed results {roll, pitch, yaw, x, y, z, score / n, iterations} or nullptr
+    unsigned long long* prof;      // optional: [0] first block start, [1] last block end (globaltimer ns), [2] sum over blocks of
+                                   // sweep time, [3] update time, [4] time waiting for a ticket, [5] tickets, [6] updates,
+                                   // [8..11] SM cycles inside the updates: reduce + load, state machine, pose tables, store + publish
 };
 
-__global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ NdtSweepShared sh;
-    __shared__ int s_scan[kNdtThreads / 32];
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-    for (int j = gtid; j < a.n_jobs; j += gsize) {
-        NdtJob& J = a.jobs[j];
-        J.align_pass = 0; J.total_iterations = 0; J.total_sweeps = 0;
-        ndt_job_begin(J, J.guess);
-        ndt_pose_cache_fill(J.x_t, &a.pose[j]);
-        a.active[j] = j;
+LILOC_DEV unsigned long long ndt_ld_entry(const unsigned long long* p) { return *((const volatile unsigned long long*)p); }
+
+// publish the tickets of one sweep of `job` (whole warp; lane 0's values are used)
+LILOC_DEV void ndt_publish(const NdtAlignArgs& a, int job, int n_tiles, int grain) {
+    const int lane = threadIdx.x & 31;
+    const int n_tick = (n_tiles + grain - 1) / grain;
+    __threadfence();                                      // job state, pose tables, arrival counter before the tickets
+    __syncwarp();
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.q.tail, (unsigned)n_tick);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < n_tick; i += 32) {
+        const unsigned t = base + (unsigned)i;
+        const unsigned long long e = ((unsigned long long)(t + 1u) << 32) | 0x80000000ull | ((unsigned long long)job << 10) | (unsigned long long)(i * grain);
+        *((volatile unsigned long long*)&a.q.ring[t & a.q.mask]) = e;
     }
-    if (gtid == 0) { a.counters[0] = a.n_jobs; a.counters[1] = 0; a.counters[2] = 0; a.counters[3] = 0; }
-    grid.sync();
-    unsigned long long sweep_ns = 0, update_ns = 0, compact_ns = 0;
-    int cur = 0;
-    int fin_seen = 0;                                       // finished jobs at the last compaction
-    for (int it = 0; it < a.max_sweeps; ++it) {
-        const int n_active = *((volatile int*)&a.counters[cur]);
-        if (n_active == 0) break;
-        const int* act = a.active + (size_t)cur * a.n_jobs;
-        // ---- sweep ----
-        unsigned long long t0 = 0;
-        if (a.sweep_ns && gtid == 0) t0 = global_ns();
-        const long long n_work = (long long)n_active * a.tiles_max;
-        for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int job = act[w / a.tiles_max], tile = (int)(w % a.tiles_max);
-            const NdtJob& J = a.jobs[job];
-            const NdtSourceView src = a.sources[J.source];
-            if (tile * kNdtTile >= src.n) continue;
-            ndt_sweep_tile<true>(&a.pose[job], a.targets[J.target], src, a.o, tile, sh, a.partial + ((size_t)job * a.tiles_max + tile) * kNdtSums);
-        }
-        grid.sync();
-        if (a.sweep_ns && gtid == 0) { const unsigned long long t1 = global_ns(); sweep_ns += t1 - t0; t0 = t1; }
-        // ---- update: one warp per active job (all jobs in parallel; the state machine itself is serial) ----
-        const int lane = threadIdx.x & 31;
-        const int nwarps = gsize >> 5;
-        // spread the jobs over the SMs first: warp k of the grid -> block k % gridDim.x
-        for (int k = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; k < n_active; k += nwarps) {
-            const int job = act[k];
-            NdtJob& J = a.jobs[job];
-            const int n_tiles = J.n_tiles;
-            double v = 0.0;
-            if (lane < kNdtSums) {
-                const double* pj = a.partial + (size_t)job * a.tiles_max * kNdtSums + lane;
-                // 16 (predicated) loads in flight per trip -- an L2 round trip is ~0.5 us --, summed in tile order
+}
+
+// Tiles per ticket.  A ticket costs a claim, a 416-byte descriptor load and an arrival (~2-3 us) on top of its tiles
+// (~3.7 us each), so tickets should be long -- but a sweep cut into few tickets cannot spread over idle blocks, and the
+// longest job's chain of sweeps is what a small batch waits for.  Aim at ~4 tickets in flight per block over the
+// unfinished jobs: whole sweeps while jobs are plentiful, single tiles once fewer jobs than blocks remain.
+LILOC_DEV int ndt_grain_for(int active_jobs, int n_tiles, int grid) {
+    long long g = ((long long)active_jobs * n_tiles) / (4ll * grid);
+    if (g < 1) g = 1;
+    if (g > n_tiles) g = n_tiles;
+    return (int)g;
+}
+LILOC_DEV int ndt_grain(const NdtAlignArgs& a, int n_tiles) {
+    return ndt_grain_for(a.n_jobs - *((volatile int*)a.q.finished), n_tiles, (int)gridDim.x);
+}
+
+// RotMtoEuler (include/math_tools.h:92-111) of the rotation block + translation -> [roll, pitch, yaw, x, y, z], evaluated in
+// double and rounded to float (what liloc_b200/relo.py::matrices_to_pose6 does on the host)
+LILOC_DEV void ndt_pack_row(const NdtJob& J, int n_source, float* row) {
+    const double r00 = J.Tfinal[0], r10 = J.Tfinal[4], r20 = J.Tfinal[8], r21 = J.Tfinal[9], r22 = J.Tfinal[10], r11 = J.Tfinal[5], r12 = J.Tfinal[6];
+    const double sy = sqrt(r00 * r00 + r10 * r10);
+    double roll, pitch, yaw;
+    if (sy >= 1e-6) { roll = atan2(r21, r22); pitch = atan2(-r20, sy); yaw = atan2(r10, r00); }
+    else { roll = atan2(-r12, r11); pitch = atan2(-r20, sy); yaw = 0.0; }
+    row[0] = (float)roll; row[1] = (float)pitch; row[2] = (float)yaw;
+    row[3] = J.Tfinal[3]; row[4] = J.Tfinal[7]; row[5] = J.Tfinal[11];
+    row[6] = (float)(J.score / (double)(n_source > 0 ? n_source : 1));
+    row[7] = (float)J.total_iterations;
+}
+
+struct NdtUpdateShared { NdtJob job; double sums[kNdtSums]; };
+
+// The block that completed a job's sweep: fixed-order reduction + one state-machine step + publish / retire (warp 0).
+LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& us) {
+    const int lane = threadIdx.x & 31;
+    const bool prof = a.prof != nullptr && lane == 0;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (prof) c0 = clock64();
+    NdtHot* hot = &a.hot[job];
+    const NdtJobView* vw = &hot->view;
+    const int n_tiles = __ldcg(&vw->n_tiles);
+    int jw[(sizeof(NdtJob) / sizeof(int) + 31) / 32];     // the job state, 32 lanes wide: in flight together with the partial sums
+    {
+        const int* src = reinterpret_cast<const int*>(&a.jobs[job]);
+#pragma unroll
+        for (int u = 0; u < (int)(sizeof(jw) / sizeof(int)); ++u) { const int i = lane + 32 * u; jw[u] = i < (int)(sizeof(NdtJob) / sizeof(int)) ? __ldcg(src + i) : 0; }
+    }
+    if (lane < kNdtSums) {
+        const double* pj = a.partial + (size_t)job * a.tiles_max * kNdtSums + lane;
+        double v = 0.0;
+        // 16 (predicated) loads in flight per trip -- an L2 round trip is ~0.5 us --, summed in tile order
 #pragma unroll 1
-                for (int t = 0; t < n_tiles; t += 16) {
-                    double w[16];
+        for (int t = 0; t < n_tiles; t += 16) {
+            double w[16];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) w[u] = (t + u < n_tiles) ? __ldcg(&pj[(size_t)(t + u) * kNdtSums]) : 0.0;
+            for (int u = 0; u < 16; ++u) w[u] = (t + u < n_tiles) ? __ldcg(&pj[(size_t)(t + u) * kNdtSums]) : 0.0;
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) if (t + u < n_tiles) v += w[u];
-                }
-            }
-            double sums[kNdtSums];
-#pragma unroll
-            for (int q = 0; q < kNdtSums; ++q) {
-                int lo = __double2loint(v), hi = __double2hiint(v);
-                lo = __shfl_sync(0xffffffffu, lo, q); hi = __shfl_sync(0xffffffffu, hi, q);
-                sums[q] = __hiloint2double(hi, lo);
-            }
-            double xt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            bool go = false;
-            if (lane == 0) {
-                // The state machine touches dozens of fields in dependent order: run it on a local copy (one batch of
-                // loads, one of stores) instead of paying an L2 round trip per field.
-                NdtJob L = J;
-                ndt_job_step(L, sums, a.o);
-                if (L.phase == NDT_DONE) {
-                    L.total_iterations += L.nr_iterations; L.total_sweeps += L.sweeps;
-                    if (L.align_pass + 1 < a.o.n_align) {     // registration->align() again from the previous result (:282-290)
-                        const int pass = L.align_pass + 1;
-                        float g[12];
-                        for (int i = 0; i < 12; ++i) g[i] = L.Tfinal[i];
-                        ndt_job_begin(L, g);
-                        L.align_pass = pass;
-                    }
-                }
-                go = L.phase != NDT_DONE;
-                if (!go) atomicAdd(&a.counters[3], 1);         // the job leaves the active list: a compaction is due
-#pragma unroll
-                for (int i = 0; i < 6; ++i) xt[i] = L.x_t[i];
-                J = L;
-            }
-            __syncwarp();
-            ndt_pose_cache_fill_warp(xt, go, &a.pose[job]);   // the next sweep's transform and angle tables, six lanes for the sin / cos
+            for (int u = 0; u < 16; ++u) if (t + u < n_tiles) v += w[u];
         }
-        if (gtid == 0) a.counters[2] = it + 1;
-        grid.sync();
-        if (a.sweep_ns && gtid == 0) { const unsigned long long t1 = global_ns(); update_ns += t1 - t0; t0 = t1; }
-        // Nothing to compact while no job has finished (most rounds): the list, its length and `cur` stay as they are and
-        // the round ends here -- one barrier and ~3 us less.
-        const int fin = *((volatile int*)&a.counters[3]);
-        if (fin == fin_seen) continue;
-        fin_seen = fin;
-        // ---- compaction of the active list (block 0).  The order is preserved: neighbouring work items then stay
-        // neighbouring jobs (same submap, same scan -> shared L2 lines).  Appending with an atomic cursor from the update
-        // phase saves this phase and its barrier (~3 us per round) but scrambles the list: measured 7 % slower on the
-        // 8000-triple batch, 2 % faster on 256 hypotheses of one scan.
-        if (blockIdx.x == 0) {
-            int* nxt = a.active + (size_t)(cur ^ 1) * a.n_jobs;
-            int carry = 0;
-            for (int base = 0; base < n_active; base += kNdtThreads) {
-                const int k = base + threadIdx.x;
-                const int job = k < n_active ? act[k] : -1;
-                const bool keep = job >= 0 && ((volatile NdtJob*)a.jobs)[job].phase != NDT_DONE;
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) s_scan[threadIdx.x >> 5] = __popc(bal);
-                __syncthreads();
-                int wbase = 0, tot = 0;
-#pragma unroll
-                for (int w2 = 0; w2 < kNdtThreads / 32; ++w2) { if (w2 < (int)(threadIdx.x >> 5)) wbase += s_scan[w2]; tot += s_scan[w2]; }
-                if (keep) nxt[carry + wbase + __popc(bal & ((1u << lane) - 1u))] = job;
-                carry += tot;
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) { a.counters[cur ^ 1] = carry; a.counters[2] = it + 1; }
-        }
-        grid.sync();
-        if (a.sweep_ns && gtid == 0) compact_ns += global_ns() - t0;
-        cur ^= 1;
+        us.sums[lane] = v;
     }
-    if (a.sweep_ns && gtid == 0) { a.sweep_ns[0] += sweep_ns; a.sweep_ns[1] += update_ns; a.sweep_ns[2] += compact_ns; }
+    {
+        int* dst = reinterpret_cast<int*>(&us.job);
+#pragma unroll
+        for (int u = 0; u < (int)(sizeof(jw) / sizeof(int)); ++u) { const int i = lane + 32 * u; if (i < (int)(sizeof(NdtJob) / sizeof(int))) dst[i] = jw[u]; }
+    }
+    __syncwarp();
+    if (prof) c1 = clock64();
+    bool new_trial = false, go = false, restart = false;
+    double xt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (lane == 0) {
+        NdtJob& L = us.job;
+        new_trial = ndt_job_step(L, us.sums, a.o);
+        if (L.phase == NDT_DONE) {
+            L.total_iterations += L.nr_iterations; L.total_sweeps += L.sweeps;
+            if (L.align_pass + 1 < a.o.n_align) {         // registration->align() again from the previous result (:282-290)
+                const int pass = L.align_pass + 1;
+                float g[12];
+                for (int i = 0; i < 12; ++i) g[i] = L.Tfinal[i];
+                ndt_job_begin(L, g);
+                L.align_pass = pass;
+                restart = true;
+            }
+        }
+        go = L.phase != NDT_DONE;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xt[i] = L.x_t[i];
+    }
+    go = __shfl_sync(0xffffffffu, go ? 1 : 0, 0) != 0;
+    new_trial = __shfl_sync(0xffffffffu, new_trial ? 1 : 0, 0) != 0;
+    (void)restart;
+    if (prof) c2 = clock64();
+    NdtPoseCache* pc = &hot->pc;
+    ndt_pose_cache_fill_warp(xt, go, pc);                 // the next sweep's transform and angle tables, six lanes for the sin / cos
+    __syncwarp();
+    if (prof) c3 = clock64();
+    if (lane == 0 && new_trial) {                         // final_transformation_ = T(x_t) of the line search's latest trial
+#pragma unroll
+        for (int i = 0; i < 12; ++i) us.job.Tfinal[i] = pc->T[i];
+    }
+    __syncwarp();
+    {
+        int* dst = reinterpret_cast<int*>(&a.jobs[job]);
+        const int* src = reinterpret_cast<const int*>(&us.job);
+        for (int i = lane; i < (int)(sizeof(NdtJob) / sizeof(int)); i += 32) dst[i] = src[i];
+    }
+    if (go) {
+        int grain = 1;
+        if (lane == 0) {
+            grain = ndt_grain(a, n_tiles);
+            *((volatile int*)&a.sync[job].done) = 0;
+            *((volatile int*)&hot->grain) = grain;
+        }
+        grain = __shfl_sync(0xffffffffu, grain, 0);
+        ndt_publish(a, job, n_tiles, grain);
+    } else {
+        if (lane == 0 && a.rows) ndt_pack_row(us.job, __ldcg(&vw->n), a.rows + (size_t)job * 8);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(a.q.finished, 1);
+    }
+    if (prof) {         // SM clock cycles of the four parts of an update: reduce + load, state machine, pose tables, store + publish
+        const long long c4 = clock64();
+        atomicAdd(&a.prof[8], (unsigned long long)(c1 - c0)); atomicAdd(&a.prof[9], (unsigned long long)(c2 - c1));
+        atomicAdd(&a.prof[10], (unsigned long long)(c3 - c2)); atomicAdd(&a.prof[11], (unsigned long long)(c4 - c3));
+    }
+}
+
+__global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
+    __shared__ NdtSweepShared sh;
+    __shared__ NdtUpdateShared us;
+    __shared__ NdtJobView s_view;
+    __shared__ int s_ticket, s_last, s_grain, s_pad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long t_sweep = 0, t_update = 0, t_wait = 0, n_tick = 0, n_upd = 0, t_begin = 0;
+    const bool prof = a.prof != nullptr && threadIdx.x == 0;
+    if (prof) { t_begin = global_ns(); atomicMin(&a.prof[0], t_begin); }
+    // ---- prologue: one warp per job -- state, pose tables, view, first tickets.  No barrier: consumers wait on ticket tags.
+    {
+        const int gwarp = warp * gridDim.x + blockIdx.x, nwarps = (kNdtThreads / 32) * gridDim.x;
+        for (int j = gwarp; j < a.n_jobs; j += nwarps) {
+            NdtJob& J = a.jobs[j];
+            double xt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            int n_tiles = 0;
+            if (lane == 0) {
+                J.align_pass = 0; J.total_iterations = 0; J.total_sweeps = 0;
+                ndt_job_begin(J, J.guess);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) xt[i] = J.x_t[i];
+                const NdtSourceView sv = a.sources[J.source];
+                NdtJobView v;
+                v.tg = a.targets[J.target]; v.pts = sv.pts; v.n = sv.n; v.n_tiles = (sv.n + kNdtTile - 1) / kNdtTile;
+                a.hot[j].view = v;
+                n_tiles = v.n_tiles;
+            }
+            n_tiles = __shfl_sync(0xffffffffu, n_tiles, 0);
+            ndt_pose_cache_fill_warp(xt, true, &a.hot[j].pc);
+            int grain = 1;
+            if (lane == 0) {
+                grain = ndt_grain_for(a.n_jobs, n_tiles, (int)gridDim.x);
+                a.sync[j].done = 0; a.hot[j].grain = grain; a.hot[j].pad = 0;
+            }
+            grain = __shfl_sync(0xffffffffu, grain, 0);
+            ndt_publish(a, j, n_tiles, grain);
+        }
+    }
+    // ---- consumer loop
+    for (;;) {
+        if (threadIdx.x == 0) {
+            unsigned long long t0 = 0;
+            if (prof) t0 = global_ns();
+            const unsigned my = atomicAdd(a.q.head, 1u);
+            const unsigned long long* slot = &a.q.ring[my & a.q.mask];
+            const unsigned long long want = ((unsigned long long)(my + 1u) << 32) | 0x80000000ull;
+            int ticket = -1;
+            for (long long spin = 0;; ++spin) {
+                const unsigned long long e = ndt_ld_entry(slot);
+                if ((e & 0xFFFFFFFF80000000ull) == want) { ticket = (int)(e & 0x7FFFFFFFull); break; }
+                if ((spin & 15) == 15) {
+                    if (*((volatile int*)a.q.finished) >= a.n_jobs || *((volatile int*)a.q.error)) break;
+                    if (spin > (1ll << 26)) { atomicExch(a.q.error, 1); break; }        // ~ seconds: something is wrong, leave
+                    __nanosleep(spin < 256 ? 20 : 200);
+                }
+            }
+            s_ticket = ticket;
+            if (prof) t_wait += global_ns() - t0;
+        }
+        __syncthreads();
+        const int ticket = s_ticket;
+        if (ticket < 0) break;
+        const int job = ticket >> 10, tile0 = ticket & 1023;
+        // the job's view, ticket granularity and pose tables (written by other blocks: through L2), one word per thread
+        if (threadIdx.x < kNdtHotWords) {
+            const int w = __ldcg(reinterpret_cast<const int*>(&a.hot[job]) + threadIdx.x);
+            constexpr int kViewWords = sizeof(NdtJobView) / sizeof(int);
+            if (threadIdx.x < kViewWords) reinterpret_cast<int*>(&s_view)[threadIdx.x] = w;
+            else if (threadIdx.x == kViewWords) s_grain = w;
+            else if (threadIdx.x == kViewWords + 1) s_pad = w;
+            else reinterpret_cast<int*>(&sh.pc)[threadIdx.x - kViewWords - 2] = w;
+        }
+        __syncthreads();
+        unsigned long long t1 = 0;
+        if (prof) t1 = global_ns();
+        const NdtSourceView src{s_view.pts, s_view.n};
+        const int n_tiles = s_view.n_tiles;
+        int t_end = tile0 + s_grain;
+        if (t_end > n_tiles) t_end = n_tiles;
+        for (int t = tile0; t < t_end; ++t) {
+            double* out = a.partial + ((size_t)job * a.tiles_max + t) * kNdtSums;
+            ndt_sweep_tile<true>(nullptr, s_view.tg, src, a.o, t, sh, out);
+        }
+        __syncthreads();                                  // every thread's partial sums are written ...
+        if (threadIdx.x == 0) {
+            const int cnt = t_end - tile0;
+            __threadfence();                              // ... and ordered before the arrival (cumulative over the barrier above)
+            const int before = atomicAdd(&a.sync[job].done, cnt);
+            s_last = (before + cnt == n_tiles) ? 1 : 0;
+            if (prof) { const unsigned long long t2 = global_ns(); t_sweep += t2 - t1; t1 = t2; ++n_tick; }
+        }
+        __syncthreads();
+        if (s_last) {
+            if (warp == 0) {
+                __threadfence();
+                ndt_job_update(a, job, us);
+            }
+            if (prof) { t_update += global_ns() - t1; ++n_upd; }
+        }
+    }
+    if (prof) {
+        atomicMax(&a.prof[1], global_ns());
+        atomicAdd(&a.prof[2], t_sweep); atomicAdd(&a.prof[3], t_update); atomicAdd(&a.prof[4], t_wait);
+        atomicAdd(&a.prof[5], n_tick); atomicAdd(&a.prof[6], n_upd);
+    }
 }
 
 }  // namespace liloc

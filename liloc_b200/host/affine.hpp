@@ -10,25 +10,34 @@ struct Affine3f {
 
     static Affine3f Identity() { Affine3f a{}; a.m[0][0] = a.m[1][1] = a.m[2][2] = 1.f; return a; }
 
+    // Eigen evaluates a fixed-size 3-term dot product as a0 + (a1 + a2) (Redux.h, redux_novec_unroller splits [0,1) | [1,3))
+    static float sum3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+
+    // Eigen::Transform * Transform (transform_transform_product_impl): linear = L1 L2, translation = L1 t2 + t1
     Affine3f operator*(const Affine3f& b) const {
         Affine3f r{};
         for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) r.m[i][j] = m[i][0] * b.m[0][j] + m[i][1] * b.m[1][j] + m[i][2] * b.m[2][j];
-            r.m[i][3] = m[i][0] * b.m[0][3] + m[i][1] * b.m[1][3] + m[i][2] * b.m[2][3] + m[i][3];
+            for (int j = 0; j < 3; ++j) r.m[i][j] = sum3(m[i][0] * b.m[0][j], m[i][1] * b.m[1][j], m[i][2] * b.m[2][j]);
+            r.m[i][3] = sum3(m[i][0] * b.m[0][3], m[i][1] * b.m[1][3], m[i][2] * b.m[2][3]) + m[i][3];
         }
         return r;
     }
 
-    // Eigen::Transform<float,3,Affine>::inverse(): general 3x3 inverse of the linear part
+    // Eigen::Transform<float,3,Affine>::inverse(): the 3x3 cofactor inverse of the linear part (InverseImpl.h compute_inverse
+    // <., ., 3>: cofactors of column 0 give the determinant), translation = (-inverse) * t
+    float cofactor(int i, int j) const {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+    }
     Affine3f inverse() const {
-        const float a = m[0][0], b = m[0][1], c = m[0][2], d = m[1][0], e = m[1][1], f = m[1][2], g = m[2][0], h = m[2][1], i = m[2][2];
-        const float det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-        const float inv = 1.0f / det;
+        const float c0[3] = {cofactor(0, 0), cofactor(1, 0), cofactor(2, 0)};
+        const float det = sum3(c0[0] * m[0][0], c0[1] * m[1][0], c0[2] * m[2][0]);
+        const float invdet = 1.0f / det;
         Affine3f r{};
-        r.m[0][0] = (e * i - f * h) * inv; r.m[0][1] = (c * h - b * i) * inv; r.m[0][2] = (b * f - c * e) * inv;
-        r.m[1][0] = (f * g - d * i) * inv; r.m[1][1] = (a * i - c * g) * inv; r.m[1][2] = (c * d - a * f) * inv;
-        r.m[2][0] = (d * h - e * g) * inv; r.m[2][1] = (b * g - a * h) * inv; r.m[2][2] = (a * e - b * d) * inv;
-        for (int k = 0; k < 3; ++k) r.m[k][3] = -(r.m[k][0] * m[0][3] + r.m[k][1] * m[1][3] + r.m[k][2] * m[2][3]);
+        for (int k = 0; k < 3; ++k) r.m[0][k] = c0[k] * invdet;
+        for (int k = 0; k < 3; ++k) r.m[1][k] = cofactor(k, 1) * invdet;
+        for (int k = 0; k < 3; ++k) r.m[2][k] = cofactor(k, 2) * invdet;
+        for (int i = 0; i < 3; ++i) r.m[i][3] = sum3((-r.m[i][0]) * m[0][3], (-r.m[i][1]) * m[1][3], (-r.m[i][2]) * m[2][3]);
         return r;
     }
 };

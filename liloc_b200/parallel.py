@@ -36,6 +36,20 @@ def init(backend: str | None = None):
     return rank, world, local
 
 
+def comm_init(ctx) -> None:
+    """Give a liloc context its NCCL communicator (liloc_comm_init): rank 0 creates the unique id through the C ABI, the
+    launcher's process group (torch.distributed) only carries those 128 bytes to the other ranks."""
+    rank, world, _ = env_world()
+    if world == 1:
+        ctx.comm_init(0, 1, None)
+        return
+    import torch.distributed as dist
+    from . import abi
+    ids = [abi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(rank, world, ids[0])
+
+
 def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block [lo, hi) of n_items owned by `rank`; blocks differ by at most one item."""
     base, rem = divmod(n_items, world)

@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import parallel
-from .abi import Context, NdtOpts
+from .abi import Context, NdtOpts, shard_indices
 
 
 def euler_to_matrix(roll: float, pitch: float, yaw: float, x: float, y: float, z: float) -> np.ndarray:
@@ -64,33 +64,25 @@ def hypothesis_grid(center6, n_yaw: int = 16, n_xy: int = 16, xy_radius: float =
     return np.stack(out)
 
 
-def align_sharded(ctx: Context, target_ids, source_ids, guesses, opts: NdtOpts | None = None, device=None, round_robin: bool = False):
-    """Run this rank's share of the items and all-gather the packed results.
+def align_sharded(ctx: Context, target_ids, source_ids, guesses, opts: NdtOpts | None = None, device=None, round_robin: bool = False,
+                  want_local: bool = True):
+    """Run this rank's share of the items and all-gather the packed results -- all inside the C ABI
+    (liloc_ndt_align_batch_sharded): the kernel packs {pose6, score / n, iterations} on the device, one ncclAllGather on
+    the context's stream, one device-to-host copy.  The context must have been given its communicator
+    (parallel.comm_init) when WORLD_SIZE > 1.
 
     Every rank passes the SAME full item list; targets / sources named by a rank's items must already be resident in
     its context (liloc_ndt_target_put / liloc_ndt_source_put).  Contiguous blocks by default; round_robin for lists
     whose cost correlates with position.  Returns (rows (n_items, 8) = pose6, score / n_source, iterations; local dict)."""
-    rank, world, _ = parallel.env_world()
+    rank, world = ctx.comm_world()
     n = len(guesses)
-    if round_robin:
-        mine = parallel.shard_round_robin(n, rank, world)
-    else:
-        lo, hi = parallel.shard_range(n, rank, world)
-        mine = np.arange(lo, hi)
+    mine = shard_indices(n, rank, world, round_robin)
     local = {"items": mine, "T": np.zeros((0, 4, 4), np.float32), "sweeps": np.zeros(0, np.int64), "iterations": np.zeros(0, np.int64)}
-    rows = np.zeros((len(mine), parallel.RESULT_WIDTH), np.float32)
-    if len(mine):
-        T, score, iters, conv, sweeps = ctx.ndt_align_batch(np.asarray(target_ids)[mine], np.asarray(source_ids)[mine],
-                                                            np.asarray(guesses)[mine], opts)
-        poses = matrices_to_pose6(T)
-        rows = parallel.pack_results(poses, score, iters)
-        local.update(T=T, sweeps=sweeps, iterations=iters, converged=conv, score=score)
-    if round_robin and world > 1:
-        # gather_results assumes contiguous blocks: gather in rank-major order, then undo the permutation
-        per = parallel.gather_padded(rows, (n + world - 1) // world, device)
-        full = np.zeros((n, parallel.RESULT_WIDTH), np.float32)
-        for r in range(world):
-            idx = parallel.shard_round_robin(n, r, world)
-            full[idx] = per[r, : len(idx)]
-        return full, local
-    return parallel.gather_results(rows, n, device), local
+    if want_local:
+        rows, outs = ctx.ndt_align_batch_sharded(target_ids, source_ids, guesses, opts, round_robin=round_robin, want_local=True)
+        outs = outs[: len(mine)]
+        local.update(T=outs["T"].reshape(-1, 4, 4).copy(), sweeps=outs["sweeps"].copy(), iterations=outs["iterations"].copy(),
+                     converged=outs["converged"].copy(), score=outs["score"].copy())
+    else:
+        rows = ctx.ndt_align_batch_sharded(target_ids, source_ids, guesses, opts, round_robin=round_robin)
+    return rows, local

@@ -23,31 +23,27 @@ if _TESTS not in sys.path:
 import oracle_lib as orc  # noqa: E402
 
 
-def _rot(r, p, y):
-    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
-    return np.array([[cy * cp, cy * sp * sr - sy * cr, sy * sr + cy * sp * cr],
-                     [sy * cp, cy * cr + sy * sp * sr, sy * sp * cr - cy * sr],
-                     [-sp, cp * sr, cp * cr]])
-
-
-def _T(p):
-    M = np.eye(4)
-    M[:3, :3] = _rot(float(p[0]), float(p[1]), float(p[2]))
-    M[:3, 3] = p[3:6]
-    return M
-
-
-def _pose_of(T):
-    return np.array([np.arctan2(T[2, 1], T[2, 2]), np.arcsin(-T[2, 0]), np.arctan2(T[1, 0], T[0, 0]), T[0, 3], T[1, 3], T[2, 3]], np.float32)
+def yaml_param(yaml_name: str, key: str) -> float:
+    """A ParamServer key (include/utility.h:195-304) of config/<yaml_name>, read with PyYAML: the CPU arms must not map the
+    product's shared libraries (liloc_b200.host_api.yaml_param would load libliloc_host.so -> libliloc_gpu.so)."""
+    import yaml
+    path = yaml_name if os.path.isabs(yaml_name) else os.path.join(os.path.dirname(_HERE), "config", yaml_name)
+    doc = yaml.safe_load(open(path))
+    # the reference reads every real-valued key used here into a `float` member (include/utility.h:256-301)
+    as_member = (lambda v: float(v)) if key in ("numberOfCores", "mappingProcessInterval") else (lambda v: float(np.float32(v)))
+    for section in doc.values():
+        if isinstance(section, dict) and key in section:
+            return as_member(section[key])
+    if key in doc:
+        return as_member(doc[key])
+    raise KeyError(f"{yaml_name}:{key}")
 
 
 class Params:
-    """The ParamServer keys the lio callback reads; values from config/*.yaml via liloc_b200.host_api.yaml_param
-    (the parser is host glue, not part of the measured path)."""
+    """The ParamServer keys the lio callback reads, from config/*.yaml (the parser is host glue, not part of the measured path)."""
 
     def __init__(self, yaml: str):
-        from liloc_b200 import host_api
-        g = lambda k: host_api.yaml_param(yaml, k)
+        g = lambda k: yaml_param(yaml, k)
         self.scan_leaf = np.float32(g("mappingSurfLeafSize"))
         self.map_leaf = np.float32(g("surroundingKeyframeMapLeafSize"))
         self.radius = np.float32(g("surroundingKeyframeSearchRadius"))
@@ -109,8 +105,7 @@ class RefLio:
             if self.last_odom is None:
                 self.last_odom = np.array(odom6, np.float32)
             else:
-                Tf = _T(self.pose) @ np.linalg.inv(_T(self.last_odom)) @ _T(odom6)
-                self.pose = _pose_of(Tf)
+                self.pose = orc.update_initial_guess(self.pose, self.last_odom, odom6)      # :865-883, float32 like the reference
                 self.last_odom = np.array(odom6, np.float32)
             sel = self._select(stamp)
             pts = np.concatenate([self.key_clouds[i] for i in sel])
@@ -126,10 +121,7 @@ class RefLio:
         # saveFrame / saveLIOKeyFramesAndFactor
         save = True
         if self.key_poses:
-            Tb = np.linalg.inv(_T(self.key_poses[-1])) @ _T(self.pose)
-            b = _pose_of(Tb)
-            save = not (abs(b[0]) < self.p.add_angle and abs(b[1]) < self.p.add_angle and abs(b[2]) < self.p.add_angle
-                        and np.sqrt(b[3] ** 2 + b[4] ** 2 + b[5] ** 2) < self.p.add_dist)
+            save = orc.save_frame(self.key_poses[-1], self.pose, self.p.add_angle, self.p.add_dist)          # :1245-1264
         if save:
             if ds is None:
                 ds = orc.voxelgrid(scan_raw, self.p.scan_leaf)

@@ -76,6 +76,9 @@ def _load():
     L.orc_deskew.restype = C.c_int
     L.orc_deskew.argtypes = [P, P, C.c_int, C.POINTER(DeskewParams), P]
     L.orc_orientation_times.argtypes = [P, C.c_int, P]
+    L.orc_update_initial_guess.argtypes = [P, P, P, P]
+    L.orc_save_frame.restype = C.c_int
+    L.orc_save_frame.argtypes = [P, P, C.c_float, C.c_float]
     return L
 
 
@@ -104,6 +107,20 @@ def _p(a):
 
 def num_threads() -> int:
     return lib.orc_num_threads()
+
+
+def update_initial_guess(pose6, last_odom6, odom6) -> np.ndarray:
+    """updateInitialGuess, odometry-increment branch (src/mapOptmization.cpp:865-883), float32 / Eigen order."""
+    a, b, c = (np.ascontiguousarray(v, np.float32).reshape(6) for v in (pose6, last_odom6, odom6))
+    out = np.zeros(6, np.float32)
+    lib.orc_update_initial_guess(_p(a), _p(b), _p(c), _p(out))
+    return out
+
+
+def save_frame(last_key6, pose6, angle_threshold, dist_threshold) -> bool:
+    """saveFrame (src/mapOptmization.cpp:1245-1264)."""
+    a, b = (np.ascontiguousarray(v, np.float32).reshape(6) for v in (last_key6, pose6))
+    return bool(lib.orc_save_frame(_p(a), _p(b), float(angle_threshold), float(dist_threshold)))
 
 
 def pose_to_T(pose6) -> np.ndarray:

@@ -243,3 +243,54 @@ def test_extract_nearby_fast_equals_plain():
                     assert np.array_equal(a, b), (case, k, a, b)
                     n_cases += 1
     assert n_cases > 150
+
+
+def test_host_class_against_ref_pipeline_differentially(orc, synth):
+    """The C++ host class's updateInitialGuess (:865-883), extractNearby (:902-934) and saveFrame (:1245-1264) against the
+    CPU pipeline the bench times (oracle/ref_pipeline.py RefLio, float32 Eigen-order restatements in oracle/host_oracle.cpp):
+    the same guess bits, the same keyframe selection and the same keyframe decisions over a winding 400-frame trajectory
+    (no device: the registration result is replaced by a known pose near the guess on both sides)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_pipeline as rp
+    rng = np.random.default_rng(5)
+    for yaml in ("nclt.yaml", "lio_sam_default.yaml"):
+        P = rp.Params(yaml)
+        lio = rp.RefLio(P, threads=1)
+        n = 400
+        truth = synth.trajectory_loop(n, radius_xy=(30.0, 18.0)).astype(np.float64)
+        odom = truth + np.cumsum(rng.normal(0, [1e-4, 1e-4, 3e-4, 2e-3, 2e-3, 5e-4], (n, 6)), axis=0)     # drifting odometry
+        n_kf = n_sel_checked = 0
+        with _host(yaml) as m:
+            for f in range(n):
+                stamp = 100.0 + f * (P.time_interval + 0.01)
+                ci = host_api.CloudInfo()
+                ci.stamp = stamp; ci.odomAvailable = 1
+                ci.initialGuessRoll, ci.initialGuessPitch, ci.initialGuessYaw = [float(np.float32(v)) for v in odom[f, :3]]
+                ci.initialGuessX, ci.initialGuessY, ci.initialGuessZ = [float(np.float32(v)) for v in odom[f, 3:]]
+                # --- updateInitialGuess
+                got = m.debug_update_initial_guess(ci)
+                if lio.key_poses:
+                    o32 = np.array([ci.initialGuessRoll, ci.initialGuessPitch, ci.initialGuessYaw, ci.initialGuessX, ci.initialGuessY, ci.initialGuessZ], np.float32)
+                    if lio.last_odom is None:
+                        lio.last_odom = o32
+                    else:
+                        lio.pose = orc.update_initial_guess(lio.pose, lio.last_odom, o32)
+                        lio.last_odom = o32
+                    assert np.array_equal(got, lio.pose), (yaml, f, got, lio.pose)
+                    # --- extractNearby
+                    sel = lio._select(stamp)
+                    assert np.array_equal(m.debug_extract_nearby(stamp), np.asarray(sel, np.int32)), (yaml, f)
+                    n_sel_checked += 1
+                # --- "registration": both sides land on the same pose near the truth
+                reg = (truth[f] + rng.normal(0, [1e-4, 1e-4, 2e-4, 5e-3, 5e-3, 1e-3])).astype(np.float32)
+                m.debug_set_pose(reg); lio.pose = reg.copy()
+                # --- saveFrame
+                save = m.debug_save_frame()
+                want = True if not lio.key_poses else orc.save_frame(lio.key_poses[-1], lio.pose, P.add_angle, P.add_dist)
+                assert save == want, (yaml, f)
+                if save:
+                    m.debug_add_keypose(reg, stamp)
+                    lio.key_poses.append(reg.copy()); lio.key_times.append(stamp); lio.key_clouds.append(None)
+                    n_kf += 1
+        assert n_kf > 40 and n_sel_checked > 350, (n_kf, n_sel_checked)

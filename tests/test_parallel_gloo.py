@@ -23,6 +23,11 @@ def test_shard_ranges_cover_everything():
             assert seen == list(range(n))
             rr = np.concatenate([parallel.shard_round_robin(n, r, world) for r in range(world)])
             assert sorted(rr.tolist()) == list(range(n))
+            # the C ABI's own partition (liloc_shard_indices) is the same one
+            from liloc_b200 import abi
+            for r in range(world):
+                assert abi.shard_indices(n, r, world, False).tolist() == list(range(*parallel.shard_range(n, r, world)))
+                assert abi.shard_indices(n, r, world, True).tolist() == parallel.shard_round_robin(n, r, world).tolist()
 
 
 WORKER = textwrap.dedent("""
@@ -85,27 +90,27 @@ RELO_WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np
     sys.path.insert(0, ROOT_DIR)
-    from liloc_b200 import parallel, relo
+    from liloc_b200 import abi, parallel, relo
     rank, world, _ = parallel.init("gloo")
-
-    class FakeCtx:            # stands in for the device context: the result of an item is a function of the item alone
-        def ndt_align_batch(self, tids, sids, guesses, opts):
-            J = len(guesses)
-            T = np.array(guesses, np.float32).copy()
-            T[:, 0, 3] += np.asarray(tids, np.float32) + 0.5 * np.asarray(sids, np.float32)
-            return T, np.arange(J) * 0.0 + T[:, 1, 3], (np.asarray(tids) % 7).astype(np.int64), np.ones(J, np.int64), np.full(J, 9)
-
+    # The host side of liloc_ndt_align_batch_sharded without a device: the share of each rank (liloc_shard_indices), a REAL
+    # two-process all-gather of the padded per-rank blocks (gloo here, ncclAllGather on the GPUs) and the de-interleave
+    # (liloc_unshard_rows) -- the result of an item is a function of the item alone, so the gathered table is checkable.
     n = 37
     tids, sids = np.arange(n) % 5, np.arange(n) % 3
     guesses = np.stack([relo.euler_to_matrix(0, 0, 0.01 * i, float(i), 2.0 * i, 1.0) for i in range(n)])
+    per = (n + world - 1) // world
     for rr in (False, True):
-        rows, loc = relo.align_sharded(FakeCtx(), tids, sids, guesses, None, None, round_robin=rr)
-        assert rows.shape == (n, 8)
-        want_x = np.arange(n) + tids + 0.5 * sids
-        assert np.allclose(rows[:, 3], want_x) and np.allclose(rows[:, 4], 2.0 * np.arange(n)) and np.array_equal(rows[:, 7], tids % 7)
-        mine = loc["items"]
+        mine = abi.shard_indices(n, rank, world, rr)
         assert len(mine) in (n // world, n // world + 1)
         assert (mine[1] - mine[0] == world) if rr else (mine[1] - mine[0] == 1)
+        T = guesses[mine].copy()
+        T[:, 0, 3] += tids[mine] + 0.5 * sids[mine]
+        rows = parallel.pack_results(relo.matrices_to_pose6(T), T[:, 1, 3], tids[mine] % 7)
+        gathered = parallel.gather_padded(rows, per)
+        full = abi.unshard_rows(gathered, n, rr)
+        assert full.shape == (n, 8)
+        want_x = np.arange(n) + tids + 0.5 * sids
+        assert np.allclose(full[:, 3], want_x) and np.allclose(full[:, 4], 2.0 * np.arange(n)) and np.array_equal(full[:, 7], tids % 7)
     print("rank", rank, "ok")
 """)
 

@@ -13,8 +13,16 @@ parameters, lio mode, a 1000-frame sequence pushed through mapOptimization::lase
           its own replica sequence (different seed) -- weak scaling; the only collective is the final
           all-gather of packed poses.  value = frames of all ranks / max-over-ranks time.
 
+The same JSON line also carries (the headline metric / value stay the lio ones):
+  ndt            BASELINE configs[3] (256 relocalisation hypotheses x 2 align), configs[4]a (one scan vs 64 prior submaps)
+                 and configs[4]b (8000 offline triples) -- the work that DOES shard -- partitioned over the N ranks inside
+                 the C ABI (liloc_ndt_align_batch_sharded: device-side result packing, one ncclAllGather), >= 20 steps each
+  extra.latency  N = 1: p50 per-frame latency of the C++ host class next to the CPU port on the SAME frames at the two
+                 scales the north_star names (VLP-16 vs a 50-keyframe local map, Mid-360-shaped scans vs a ~1 M-point map)
+  parity_*       the GPU host class against the CPU port on the frames the cpu_baseline leg processed
+
 `--impl reference` times the reference's CPU path (the oracle restatement, oracle/ref_pipeline.py, OpenMP on
-all host cores) on a bounded sample of the same workload; rank 0 only.
+all host cores) on a bounded sample of the same workload; rank 0 only.  It never loads the product's libraries.
 """
 from __future__ import annotations
 
@@ -40,6 +48,18 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
 METRIC = "scan2map_registrations_per_s"
 UNIT = "registrations/s"
 YAML = "nclt.yaml"
+
+
+def lio_config(args) -> dict:
+    """`config` of the line -- identical, key for key, in the GPU arm and in the reference arm."""
+    return {"workload": f"configs[1]: synthetic HDL-32E NCLT-shaped lio sequence, {args.frames} frames, {YAML} parameters, lio mode",
+            "frames": args.frames, "yaml": YAML, "max_iters": 20, "stride": 2, "seed": args.seed, "sensor": "HDL-32E 32 x 1800",
+            "step": "GPU arm: one pass over all frames of the sequence (every rank its own replica sequence); reference arm: a bounded "
+                    "sample of `ref_frames` consecutive frames of the same sequence per step, the map built by the frames before "
+                    "(cpu_baseline.sample says which)",
+            "ref_frames": args.ref_frames,
+            "l2": "GPU arm: flushed (256 MiB fill) between timed passes; reference arm: n/a (CPU)",
+            "timer": "host clock bracketed by device synchronisation, max over ranks; CUDA-event cross-check in device_s"}
 
 
 def host_threads(orc) -> int:
@@ -120,15 +140,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def make_workload(n_frames: int, seed: int, n_total: int | None = None):
-    from liloc_b200 import synth, host_api
-    dt = host_api.yaml_param(YAML, "timeInterval") + 0.01     # every frame passes the rate gate (:257)
+def make_workload(n_frames: int, seed: int, n_total: int | None = None, time_interval: float | None = None):
+    from liloc_b200 import synth
+    if time_interval is None:
+        from liloc_b200 import host_api
+        time_interval = host_api.yaml_param(YAML, "timeInterval")
+    dt = time_interval + 0.01                                  # every frame passes the rate gate (:257)
     return synth.make_sequence(synth.HDL32, n_frames, seed=seed, dt=dt, n_total=n_total)
 
 
 # ---------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU reference arm: oracle restatement of the reference's lio callback, OpenMP on all host cores."""
+    """CPU reference arm: oracle restatement of the reference's lio callback, OpenMP on all host cores.  Imports nothing
+    that maps libliloc_gpu.so / libliloc_host.so (liloc_b200's binding is loaded lazily; the yaml is read with PyYAML)."""
     from liloc_b200 import parallel
     rank, world, _ = parallel.env_world()
     if rank != 0:
@@ -138,7 +162,7 @@ def run_reference(args):
     threads = host_threads(orc)
     per_step = args.ref_frames
     total = (args.warmup + args.steps) * per_step
-    seq = make_workload(max(total, 2), args.seed, n_total=args.frames)   # head of the same 1000-frame sequence
+    seq = make_workload(max(total, 2), args.seed, n_total=args.frames, time_interval=rp.yaml_param(YAML, "timeInterval"))   # head of the same sequence
     lio = rp.RefLio(rp.Params(YAML), threads=threads)
     f = 0
     for _ in range(args.warmup):
@@ -157,8 +181,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "p50_frame_ms": float(np.percentile(lat, 50)), "p95_frame_ms": float(np.percentile(lat, 95)),
-        "config": {"workload": "configs[1]: HDL-32E NCLT-shaped lio sequence, nclt.yaml", "frames_per_step": per_step, "yaml": YAML,
-                   "max_iters": 20, "stride": 2, "l2": "n/a (CPU)"},
+        "config": lio_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"nproc": os.cpu_count()},
@@ -173,16 +196,54 @@ def cpu_baseline_sample(seq, n_sample: int, budget_s: float):
     threads = host_threads(orc)
     lio = rp.RefLio(rp.Params(YAML), threads=threads)
     warm = min(10, max(len(seq.scans) // 4, 1))
+    recs = []
     for f in range(warm):
-        lio.handle(seq.stamps[f], seq.odom[f], seq.scans[f])
+        recs.append(lio.handle(seq.stamps[f], seq.odom[f], seq.scans[f]))
     t0, n = time.perf_counter(), 0
     for f in range(warm, min(len(seq.scans), warm + n_sample)):
-        lio.handle(seq.stamps[f], seq.odom[f], seq.scans[f]); n += 1
+        recs.append(lio.handle(seq.stamps[f], seq.odom[f], seq.scans[f])); n += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    lat = [r["ms"] for r in recs[warm:] if r.get("processed") and r.get("iters", 0) > 0]
     return {"value": n / dt if dt > 0 else None, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"frames {warm}..{warm + n - 1} of the benchmark sequence after {warm} warm-up frames ({n} frames, {dt:.1f} s)"}
+            "p50_frame_ms": float(np.percentile(lat, 50)) if lat else None,
+            "sample": f"frames {warm}..{warm + n - 1} of the benchmark sequence after {warm} warm-up frames ({n} frames, {dt:.1f} s)"}, recs
+
+
+def _rot_zyx(r, p, y):
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, sy * sr + cy * sp * cr], [sy * cp, cy * cr + sy * sp * sr, sy * sp * cr - cy * sr], [-sp, cp * sr, cp * cr]])
+
+
+def parity_check(reps, recs) -> dict:
+    """The GPU host class (reps, liloc_host_report per frame) against the CPU port (recs, RefLio per frame) on the frames both
+    processed: pose within the north_star tolerance (1e-4 m; rotation-matrix entries 1e-5 ~ 1e-5 rad), iterations,
+    correspondences, map / scan sizes and keyframe ids exact."""
+    n = 0
+    max_t = max_r = 0.0
+    mism = []
+    for f, rec in enumerate(recs):
+        rep = reps[f]
+        if not rec.get("processed"):
+            if rep.processed:
+                mism.append((f, "processed"))
+            continue
+        if not rep.processed:
+            mism.append((f, "processed")); continue
+        n += 1
+        gp, cp = np.array(rep.pose, np.float64), np.asarray(rec["pose"], np.float64)
+        max_t = max(max_t, float(np.abs(gp[3:] - cp[3:]).max()))
+        max_r = max(max_r, float(np.abs(_rot_zyx(*gp[:3]) - _rot_zyx(*cp[:3])).max()))
+        if (rep.iters, rep.n_sel) != (rec.get("iters", 0), rec.get("n_sel", 0)):
+            mism.append((f, "iters/n_sel", rep.iters, rep.n_sel, rec.get("iters"), rec.get("n_sel")))
+        if rec.get("iters", 0) > 0 and (rep.map_points, rep.q_all) != (rec["M"], rec["Q"]):
+            mism.append((f, "sizes", rep.map_points, rep.q_all, rec["M"], rec["Q"]))
+        if rep.keyframe_id != rec.get("keyframe_id", -1):
+            mism.append((f, "keyframe_id", rep.keyframe_id, rec.get("keyframe_id", -1)))
+    ok = not mism and max_t <= 1e-4 and max_r <= 1e-5
+    return {"parity_checked_frames": n, "parity_max_err": {"translation_m": max_t, "rotation": max_r},
+            "parity_mismatches": len(mism), "parity_first_mismatches": [list(map(str, m)) for m in mism[:4]], "parity_ok": bool(ok)}
 
 
 def make_deskew_inputs(seq, sizes, offs):
@@ -374,7 +435,18 @@ def run_ours(args):
     gathered = parallel.gather_results(rows, F * world, dev)
     assert gathered.shape[0] == F * world and hi - lo == F
 
+    m_sizes = {"n_scan": int(np.mean(sizes)), "q_all": int(np.mean([r.q_all for r in reps if r.processed])),
+               "map_points": int(np.mean([r.map_points for r in reps if r.map_points > 0])),
+               "keyframes_selected": float(np.mean([r.n_selected_keyframes for r in reps if r.n_selected_keyframes > 0])),
+               "keyframes_total": m.num_keyframes()}
+    # ---- the work that shards (BASELINE configs[3], configs[4]): every rank takes part
+    ndt = None
+    if not args.no_ndt:
+        del l2_flush, dev_scans
+        torch.cuda.empty_cache()
+        ndt = ndt_sections(args, rank, world, local, dev)
     if rank != 0:
+        m.close()
         return
     value = frames_all / t_dev_max
     e2e = frames_all / t_e2e_max
@@ -391,7 +463,7 @@ def run_ours(args):
     scan_gbs = st_dev["alg_bytes_scan"] / (st_dev["scan_ms"] * 1e-3) / 1e9 if st_dev["scan_ms"] > 0 else None
     traffic = None
     try:            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))["k_voxel_pipeline_local_map"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))["k_voxel_pipeline_local_map"]["dram_bytes_per_launch"]
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": "k_voxel_pipeline, local-map launch (assemble + VoxelGrid + search grid; persistent cooperative, one launch per frame)",
@@ -408,7 +480,12 @@ def run_ours(args):
                            "avg_launch_us": st_dev["s2m_ms"] * 1e3 / max(st_dev["s2m_launches"], 1),
                            "avg_iters_per_launch": st_dev["s2m_iters"] / max(st_dev["s2m_launches"], 1)},
             "k_voxel_pipeline_scan": {"achieved": scan_gbs, "frac": (scan_gbs / peak) if scan_gbs else None}}
-    cpu = cpu_baseline_sample(seq, args.cpu_frames, args.cpu_budget) if (world == 1 and not args.no_cpu) else None
+    cpu, parity = None, {}
+    if world == 1 and not args.no_cpu:
+        cpu, recs = cpu_baseline_sample(seq, args.cpu_frames, args.cpu_budget)
+        parity = parity_check(reps, recs)
+        if parity["parity_max_err"]["translation_m"] > 1e-3 or parity["parity_max_err"]["rotation"] > 1e-4:
+            raise SystemExit(f"bench.py: the GPU host class and the CPU port disagree: {json.dumps(parity)}")
     its = [r.iters for r in reps if r.processed and r.iters > 0]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -416,13 +493,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "p50_frame_ms": float(np.percentile(lat_dev, 50)), "p95_frame_ms": float(np.percentile(lat_dev, 95)),
         "e2e_p50_frame_ms": float(np.percentile(lat_e2e, 50)), "e2e_p95_frame_ms": float(np.percentile(lat_e2e, 95)),
-        "config": {"workload": "configs[1]: HDL-32E NCLT-shaped lio sequence, nclt.yaml, one replica sequence per GPU",
-                   "frames_per_step": F, "yaml": YAML, "max_iters": 20, "stride": 2, "seed": args.seed,
-                   "l2": "flushed (256 MiB fill) between timed passes", "timer": "host clock bracketed by device synchronisation; CUDA-event cross-check in device_s",
-                   "sizes": {"n_scan": int(np.mean(sizes)), "q_all": int(np.mean([r.q_all for r in reps if r.processed])),
-                             "map_points": int(np.mean([r.map_points for r in reps if r.map_points > 0])),
-                             "keyframes_selected": float(np.mean([r.n_selected_keyframes for r in reps if r.n_selected_keyframes > 0])),
-                             "iters": float(np.mean(its)), "keyframes_total": m.num_keyframes()}},
+        "config": lio_config(args),
+        "sizes": dict(m_sizes, iters=float(np.mean(its)), frames_per_step=F),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"] / args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / args.steps},
         "gpu_launches": int(launches_all),
         "device_s": {"value_pass": ev_dev, "e2e_pass": ev_e2e},
@@ -437,9 +509,13 @@ def run_ours(args):
                         "note": "the frame fed the raw sweep (imageProjection's de-skew + filters on the device, f3); not part of value / e2e"},
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         "host": {"nproc": os.cpu_count()},
+        "ndt": ndt,
     }
-    emit(json.dumps(out))
+    out.update(parity)
     m.close()
+    if world == 1 and not args.no_cpu and not args.no_latency:
+        out["extra"] = {"latency": latency_extras(local)}
+    emit(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -490,43 +566,41 @@ def make_ndt_workload(args):
             "desc": f"configs[4]b: offline batch of {n} (scan, submap, guess) triples over {n_sub} submaps / {len(sources)} scans"}
 
 
-def run_ndt(args):
+def ndt_one(args, name, ctx, rank, world, local, dev, steps, warmup, do_cpu, single_call):
+    """One sharded NDT workload on the ranks of this launch -> its result dict (rank 0) or None."""
     import torch
     import liloc_b200
-    from liloc_b200 import parallel, relo
-    rank, world, local = parallel.init()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- liloc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    w = make_ndt_workload(args)
+    from liloc_b200 import abi, parallel, relo
+    wa = argparse.Namespace(**vars(args))
+    wa.workload, wa.seed = name, {"relo": 4000, "jfgo": 5000, "batch": 5001}[name]
+    if name != args.workload:
+        wa.items = 0
+    w = make_ndt_workload(wa)
     n = len(w["guesses"])
-    mine = parallel.shard_round_robin(n, rank, world) if w["round_robin"] else np.arange(*parallel.shard_range(n, rank, world))
+    mine = abi.shard_indices(n, rank, world, w["round_robin"])
     my_t = sorted(set(int(t) for t in w["tid"][mine])); my_s = sorted(set(int(x) for x in w["sid"][mine]))
     opts = liloc_b200.NdtOpts(trans_eps=0.01, search=0, n_align=w["n_align"])
     res = float(args.resolution)
-    ctx = liloc_b200.Context(device=local, max_scan_points=32 * 1800, max_raw_points=1 << 20)
-    parallel.comm_init(ctx)
+    ctx.ndt_clear()
     pinned_t = {t: torch.from_numpy(np.ascontiguousarray(w["targets"][t])).pin_memory() for t in my_t}
     pinned_s = {x: torch.from_numpy(np.ascontiguousarray(w["sources"][x])).pin_memory() for x in my_s}
     h2d_t = sum(v.numel() * 4 for v in pinned_t.values()); h2d_s = sum(v.numel() * 4 for v in pinned_s.values())
-
-    def put_targets():
-        return [ctx.ndt_target_put(t, pinned_t[t].numpy(), res) for t in my_t]
 
     def put_sources():
         for x in my_s:
             ctx.ndt_source_put(x, pinned_s[x].numpy())
 
-    def align():
-        return relo.align_sharded(ctx, w["tid"], w["sid"], w["guesses"], opts, dev, round_robin=w["round_robin"])
+    def align(local_outs=False):
+        return relo.align_sharded(ctx, w["tid"], w["sid"], w["guesses"], opts, dev, round_robin=w["round_robin"], want_local=local_outs)
 
-    t0 = time.perf_counter(); leaves = put_targets(); torch.cuda.synchronize(); target_build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    leaves = [ctx.ndt_target_put(t, pinned_t[t].numpy(), res) for t in my_t]
+    torch.cuda.synchronize(); target_build_s = time.perf_counter() - t0
     put_sources()
     ctx.set_timing(True)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ext = torch.cuda.ExternalStream(liloc_b200.lib.liloc_stream(ctx._h), device=dev)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         align()
 
     def timed(e2e: bool):
@@ -534,39 +608,41 @@ def run_ndt(args):
         ctx.ndt_stats(reset=True)
         sampler = ClockSampler(local); sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tt, rows, loc = 0.0, None, None
+        per, rows = [], None
         ev0.record(ext)
-        for _ in range(args.steps):
+        for _ in range(steps):
             l2_flush.fill_(1); torch.cuda.synchronize(); parallel.barrier()
             t0 = time.perf_counter()
             if e2e:                                  # per step: the scans go up from pinned host memory, results come back;
                 put_sources()                        # the prior-session submap grids stay resident (loaded once per session)
-            rows, loc = align()
+            rows, _ = align()
             torch.cuda.synchronize()
-            tt += time.perf_counter() - t0
+            per.append(time.perf_counter() - t0)
         ev1.record(ext); torch.cuda.synchronize(); parallel.barrier()
-        return tt, rows, loc, ctx.ndt_stats(), sampler.finish(), ev0.elapsed_time(ev1) * 1e-3
+        return per, rows, ctx.ndt_stats(), sampler.finish(), ev0.elapsed_time(ev1) * 1e-3
 
-    t_dev, rows, loc, st, clocks, ev_dev = timed(False)
-    t_e2e, rows2, _, st2, _, ev_e2e = timed(True)
+    per_dev, rows, st, clocks, ev_dev = timed(False)
+    per_e2e, rows2, st2, _, ev_e2e = timed(True)
     assert np.array_equal(rows, rows2)               # same work, same answers
-    t_dev_max = parallel.max_over_ranks(t_dev, dev); t_e2e_max = parallel.max_over_ranks(t_e2e, dev)
-    sweep_ms = parallel.max_over_ranks(st["kernel_ms"], dev)
+    # max over ranks of every step (the slowest rank ends the step), then the sum
+    t_dev_max = sum(parallel.max_over_ranks(t, dev) for t in per_dev)
+    t_e2e_max = sum(parallel.max_over_ranks(t, dev) for t in per_e2e)
+    kernel_ms = parallel.max_over_ranks(st["kernel_ms"], dev)
     alg = parallel.sum_over_ranks(st["alg_bytes"], dev); launches = parallel.sum_over_ranks(st["launches"], dev)
     job_sweeps = parallel.sum_over_ranks(st["job_sweeps"], dev)
+    max_job_sweeps = parallel.max_over_ranks(st["max_job_sweeps"], dev)
     if rank != 0:
-        ctx.close(); return
+        return None
     peak, peak_src = load_peaks()
-    value, e2e = n * args.steps / t_dev_max, n * args.steps / t_e2e_max
-    # roofline of k_ndt_sweep: algorithmic bytes of this rank's launches / their CUDA-event time
+    value, e2e = n * steps / t_dev_max, n * steps / t_e2e_max
+    # roofline of the batch kernel: algorithmic bytes of this rank's launches / their device time
     ach = st["alg_bytes"] / (st["kernel_ms"] * 1e-3) / 1e9 if st["kernel_ms"] > 0 else None
-    truth_hits = None
-    cpu = cpu_baseline_ndt(w, args) if (world == 1 and not args.no_cpu) else None
+    blocks = st["blocks"] / max(st["launches"], 1)
+    cpu = cpu_baseline_ndt(w, wa, budget_s=min(args.cpu_budget, 6.0)) if do_cpu else None
     # Not part of value / e2e: the latency of ONE registration call the way the relo-mode frame makes it (a single job:
-    # upload the scan, align, read the pose back), measured on rank 0's first item -- the per-frame case, where the
-    # per-round overhead of the state machine matters more than the sweep throughput.
+    # upload the scan, align, read the pose back), measured on rank 0's first item -- the per-frame case.
     single = None
-    if rank == 0 and len(mine) > 0:
+    if single_call and len(mine) > 0:
         i0 = int(mine[0]); t0_, s0_ = int(w["tid"][i0]), int(w["sid"][i0])
         lat = []
         for r_ in range(25):
@@ -577,39 +653,163 @@ def run_ndt(args):
                 lat.append((time.perf_counter() - ta) * 1e3)
         single = {"p50_ms": float(np.percentile(lat, 50)), "n_align": w["n_align"],
                   "note": "one (scan, submap, guess) job per call, scan uploaded from pinned host memory inside the call"}
-    out = {
-        "metric": NDT_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_dev_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
-        "data": "synthetic",
-        "config": {"workload": w["desc"], "items": n, "resolution": res, "search": "DIRECT1", "n_align": w["n_align"], "seed": args.seed,
-                   "sharding": ("round-robin" if w["round_robin"] else "contiguous blocks") + " over ranks, no data-path collective; one all-gather of 8 floats per item",
-                   "l2": "flushed (256 MiB fill) before every step", "timer": "host clock bracketed by device synchronisation, max over ranks; CUDA-event cross-check in device_s",
+    return {
+        "metric": NDT_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t_dev_max * 1e3 / steps, "p50_step_ms": float(np.percentile(per_dev, 50) * 1e3), "scaling": "strong", "dtype": "f32/f64",
+        "config": {"workload": w["desc"], "items": n, "resolution": res, "search": "DIRECT1", "n_align": w["n_align"], "seed": wa.seed,
+                   "sharding": ("round-robin" if w["round_robin"] else "contiguous blocks") + " over ranks inside liloc_ndt_align_batch_sharded, no data-path collective; "
+                               "results packed on the device, one ncclAllGather of 8 floats per item, one D2H",
+                   "l2": "flushed (256 MiB fill) before every step", "timer": "host clock around the C-ABI call bracketed by device synchronisation; per step max over ranks",
                    "sizes": {"target_points": int(np.mean([len(v) for v in w["targets"].values()])), "source_points": int(np.mean([len(v) for v in w["sources"].values()])),
                              "targets_rank0": len(my_t), "sources_rank0": len(my_s), "leaves": int(np.mean(leaves)) if leaves else 0,
-                             "sweeps_per_item": job_sweeps / max(n * args.steps, 1), "iterations_per_item": float(np.mean(rows[:, 7]))},
+                             "sweeps_per_item": job_sweeps / max(n * steps, 1), "max_sweeps_of_one_item": max_job_sweeps, "iterations_per_item": float(np.mean(rows[:, 7]))},
                    "target_build_s_rank0": target_build_s},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": float(h2d_s + n * 72), "d2h_bytes_per_step": float(n * 152),
-                "note": "per step every rank uploads its scans and the guesses and reads the results back; the prior-session submap grids "
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": t_e2e_max * 1e3 / steps, "h2d_bytes_per_step": float(h2d_s + len(mine) * 376), "d2h_bytes_per_step": float(n * 32 + len(mine) * 376),
+                "note": "per step every rank uploads its scans and job records and reads the gathered rows back; the prior-session submap grids "
                         "are resident (built once per session: target_build_s_rank0, h2d_bytes_targets_rank0) -- the CPU reference rebuilds "
                         "the grid in every setInputTarget (anchorOptimize.hpp:394)",
                 "h2d_bytes_targets_rank0": float(h2d_t)},
         "gpu_launches": int(launches),
         "device_s": {"value_pass": ev_dev, "e2e_pass": ev_e2e},
-        "roofline": {"bound": "hbm", "kernel": "k_ndt_align, derivative-sweep phases (persistent cooperative kernel: one launch per batch)", "achieved": ach, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_ndt_align (queue-driven persistent kernel: one launch per batch, no grid barriers)", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
-                     "kernel_ms_per_step": st["kernel_ms"] / args.steps, "kernel_share_of_step": sweep_ms * 1e-3 / t_dev_max,
-                     "blocks": st["blocks"] / max(st["launches"], 1), "tickets_per_step": st["tickets"] / args.steps, "updates_per_step": st["updates"] / args.steps,
-                     "max_job_sweeps": st["max_job_sweeps"],
-                     "block_time_share": {k: st[f"block_{k}_ms"] / max(st["kernel_ms"] * st["blocks"] / max(st["launches"], 1), 1e-9) for k in ("sweep", "update", "wait")},
+                     "kernel_ms_per_step_rank0": st["kernel_ms"] / steps, "kernel_share_of_step": kernel_ms * 1e-3 / t_dev_max,
+                     "blocks": blocks, "tickets_per_step": st["tickets"] / steps, "updates_per_step": st["updates"] / steps,
+                     "block_time_share": {k: st[f"block_{k}_ms"] / max(st["kernel_ms"] * blocks, 1e-9) for k in ("sweep", "update", "wait")},
                      "us_per_ticket": st["block_sweep_ms"] * 1e3 / max(st["tickets"], 1), "us_per_update": st["block_update_ms"] * 1e3 / max(st["updates"], 1),
                      "update_cycles_per_update": {k: v / max(st["updates"], 1) for k, v in zip(("reduce_load", "state_machine", "pose_tables", "store_publish"), st["update_cycles"])},
-                     "alg_bytes_per_step_all_ranks": alg / args.steps,
-                     "note": "algorithmic bytes = sweeps x (16 P + 36 P c + 224) per job (SURVEY 8d); the leaf gather is served by L2, the per-point math is float with double accumulation"},
-        "single_call": single,
-        "cpu_baseline": cpu, "clocks": clocks, "host": {"nproc": os.cpu_count()},
+                     "alg_bytes_per_step_all_ranks": alg / steps,
+                     "note": "algorithmic bytes = sweeps x (16 P + 36 P c + 224) per job (SURVEY 8d); the leaf gather is served by L2, the per-point math is float with "
+                             "double accumulation: the kernel is instruction-issue bound, the HBM fraction is nominal"},
+        "single_call": single, "cpu_baseline": cpu, "clocks": clocks,
     }
-    emit(json.dumps(out))
+
+
+def _static_scene(name):
+    """Seeded keyframe sets for extra.latency: the scene the reference's class would hold after driving there.  Keyframe
+    poses are laid out so that extractNearby (:902-934) selects them all by its own rules (radius 20 m around the LAST key
+    pose, one keyframe per surroundingKeyframeDensity voxel); the last-added key pose is the one next to the test scan."""
+    from liloc_b200 import synth
+    if name == "vlp16_50kf":
+        world = synth.make_world(size_xy=(120.0, 80.0), n_pillars=40, seed=1000)
+        xs, ys = np.arange(-9.0, 10.0, 2.0), np.array([-8.0, -4.0, 0.0, 4.0, 8.0])                 # 5 rows x 10, 2 m apart (density 2.0)
+        poses = [np.array([0.0, 0.0, 0.0 if j % 2 == 0 else np.pi, x if j % 2 == 0 else -x, y, 1.8]) for j, y in enumerate(ys) for x in xs]
+        centre = int(np.argmin([abs(p[3] - 1.0) + abs(p[4]) for p in poses]))
+        poses.append(poses.pop(centre))
+        return {"yaml": "lio_sam_default.yaml", "world": world, "kf_sensor": synth.VLP16, "scan_sensor": synth.VLP16, "kf_leaf": 0.2, "poses": np.array(poses),
+                "test_pose": np.array([0.004, -0.003, 0.02, 1.3, 0.2, 1.8]), "seed": 1000,
+                "desc": "VLP-16 (16 x 1800) scan against the local map of 50 keyframes, lio_sam_default.yaml (scan leaf 0.2, map leaf 0.5, stride 2, <= 20 iterations)"}
+    if name == "mid360_1m":
+        world = synth.make_world(size_xy=(200.0, 150.0), height=25.0, n_pillars=60, seed=3000)
+        xs = np.arange(-20.0, 20.01, 0.5)                                                            # 81 keyframes 0.5 m apart (density 0.5)
+        poses = [np.array([0.0, 0.0, 0.0, x, 0.0, 1.8]) for x in xs]
+        poses.append(poses.pop(len(poses) // 2))
+        dense = synth.Sensor("mid360x", 1, 1, 40000, -7.0, 52.0, 0.5, 100.0)       # denser than one Mid-360 frame so that the map reaches ~1 M points
+        return {"yaml": "lio_sam_mid360.yaml", "world": world, "kf_sensor": dense, "scan_sensor": synth.MID360, "kf_leaf": None, "poses": np.array(poses),
+                "test_pose": np.array([0.003, 0.002, -0.01, 0.2, 0.1, 1.8]), "seed": 3000,
+                "desc": "Mid-360-shaped scan (20 000 rays) against a ~1 M-point local map (81 un-thinned dense keyframes 0.5 m apart), lio_sam_mid360.yaml (leaves 0.2)"}
+    raise KeyError(name)
+
+
+def latency_extras(local):
+    """N = 1 only: p50 per-frame latency (reg_time, src/mapOptmization.cpp:307-318) of the C++ host class next to the CPU port
+    on the SAME frames of a static scene, at the two scales the north_star's >= 10x target names.  Both sides go through
+    updateInitialGuess -> extractNearby -> extractCloud -> downsample -> scan2MapOptimization -> saveFrame; the results are
+    compared (north_star tolerance)."""
+    import oracle_lib as orc
+    import ref_pipeline as rp
+    from liloc_b200 import abi, host_api, synth
+    out = {}
+    threads = host_threads(orc)
+    for name in ("vlp16_50kf", "mid360_1m"):
+        sc = _static_scene(name)
+        K = len(sc["poses"])
+        P = rp.Params(sc["yaml"])
+        kfs = []
+        for k in range(K):
+            c = synth.scan(sc["world"], sc["poses"][k], sc["kf_sensor"], sc["seed"] + k)
+            kfs.append(orc.voxelgrid(c, sc["kf_leaf"]) if sc["kf_leaf"] else c)
+        poses32 = sc["poses"].astype(np.float32)
+        scan = np.ascontiguousarray(synth.scan(sc["world"], sc["test_pose"], sc["scan_sensor"], sc["seed"] + 999))
+        guess = synth.perturb(sc["test_pose"], sc["seed"]).astype(np.float32)
+        reps_n = 12 if name == "vlp16_50kf" else 6
+        # ---- GPU: the host class with the seeded session
+        with host_api.MapOptimization(sc["yaml"], "lio", device=local) as m:
+            ctx = abi.Context.borrow(m.ctx_handle(), local)
+            for k in range(K):
+                ctx.keyframe_put(k, kfs[k])
+                m.debug_add_keypose(poses32[k], -1000.0 + k)
+            stamps = 10.0 + (P.time_interval + 0.05) * np.arange(reps_n + 3)
+            infos = host_api.make_infos([scan] * len(stamps), np.repeat(guess[None], len(stamps), 0), stamps)
+            g_lat, g_rep = [], None
+            for i in range(len(stamps)):
+                m.debug_set_pose(guess)
+                r = m.handle(infos[i])
+                if r.processed != 1 or r.status < 0:
+                    raise SystemExit(f"bench.py latency_extras({name}): frame failed (status {r.status})")
+                if i >= 3:
+                    g_lat.append(r.reg_ms)
+                g_rep = r
+            g_first = None
+        # ---- CPU port: the same session, the same calls
+        lio = rp.RefLio(P, threads=threads)
+        lio.key_poses = [p.copy() for p in poses32]; lio.key_times = [-1000.0 + k for k in range(K)]; lio.key_clouds = list(kfs)
+        c_lat, c_rec = [], None
+        n_cpu = 4 if name == "vlp16_50kf" else 3
+        for i in range(n_cpu):
+            lio.pose = guess.copy()
+            rec = lio.handle(float(stamps[i]), guess, scan)
+            if i >= 1:
+                c_lat.append(rec["ms"])
+            c_rec = rec
+            if i == 0:
+                g_first = rec
+        # parity on the frame both ran first with identical state (the host class's frame 0 == the CPU port's frame 0)
+        gp, cp = np.array(g_rep.pose, np.float64), np.asarray(c_rec["pose"], np.float64)
+        out[name] = {"config": sc["desc"], "gpu_p50_ms": float(np.percentile(g_lat, 50)), "cpu_p50_ms": float(np.percentile(c_lat, 50)), "cpu_cores": threads,
+                     "speedup_p50": float(np.percentile(c_lat, 50) / np.percentile(g_lat, 50)),
+                     "frames": {"gpu": len(g_lat), "cpu": len(c_lat)},
+                     "sizes": {"keyframes_selected": int(g_rep.n_selected_keyframes), "n_raw": int(sum(len(kfs[i]) for i in c_rec.get("sel", []))), "map_points": int(g_rep.map_points), "n_scan": len(scan),
+                               "q_all": int(g_rep.q_all), "iters": int(g_rep.iters), "n_sel": int(g_rep.n_sel)},
+                     "parity": {"iters": [int(g_rep.iters), int(c_rec["iters"])], "n_sel": [int(g_rep.n_sel), int(c_rec["n_sel"])],
+                                "map_points": [int(g_rep.map_points), int(c_rec["M"])],
+                                "translation_m": float(np.abs(gp[3:] - cp[3:]).max()), "rotation": float(np.abs(_rot_zyx(*gp[:3]) - _rot_zyx(*cp[:3])).max())},
+                     "how": "liloc_host_handle (C++ mapOptimization::laserCloudInfoHandler) vs oracle/ref_pipeline.RefLio.handle on the same seeded session; "
+                            "scan in pageable host memory on both sides; GPU p50 over the frames after 3 warm-up frames"}
+    return out
+
+
+def ndt_sections(args, rank, world, local, dev):
+    """configs[3], configs[4]a, configs[4]b at this launch's N, in one context with its NCCL communicator."""
+    import liloc_b200
+    from liloc_b200 import parallel
+    ctx = liloc_b200.Context(device=local, max_scan_points=32 * 1800, max_raw_points=1 << 20)
+    parallel.comm_init(ctx)
+    out = {}
+    steps = max(args.steps, 20)
+    for key, name in (("relo_256_hypotheses", "relo"), ("jfgo_64_submaps", "jfgo"), ("batch_8000_triples", "batch")):
+        out[key] = ndt_one(args, name, ctx, rank, world, local, dev, steps, 3, do_cpu=(world == 1 and not args.no_cpu), single_call=(name != "batch"))
     ctx.close()
+    return out if rank == 0 else None
+
+
+def run_ndt(args):
+    """`--workload relo | jfgo | batch` alone: the same section as a line of its own."""
+    import torch
+    import liloc_b200
+    from liloc_b200 import parallel
+    rank, world, local = parallel.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- liloc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = liloc_b200.Context(device=local, max_scan_points=32 * 1800, max_raw_points=1 << 20)
+    parallel.comm_init(ctx)
+    out = ndt_one(args, args.workload, ctx, rank, world, local, dev, args.steps, args.warmup, do_cpu=(world == 1 and not args.no_cpu), single_call=True)
+    ctx.close()
+    if rank == 0:
+        out.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic", "host": {"nproc": os.cpu_count()}})
+        emit(json.dumps(out))
 
 
 def cpu_baseline_ndt(w, args, max_items=None, budget_s=None):
@@ -689,6 +889,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=300, help="cpu_baseline: at most this many frames")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="cpu_baseline: seconds of CPU work")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ndt", action="store_true", help="lio line without the sharded NDT sections")
+    ap.add_argument("--no-latency", action="store_true", help="lio line without extra.latency")
     ap.add_argument("--workload", choices=["lio", "relo", "jfgo", "batch"], default="lio",
                     help="lio = configs[1] (default, headline); relo = configs[3]; jfgo / batch = configs[4]")
     ap.add_argument("--items", type=int, default=0, help="relo: hypotheses (256); batch: triples (8000)")

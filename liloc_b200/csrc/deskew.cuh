@@ -126,7 +126,9 @@ LILOC_DEV void find_rotation(const double* s_time, const double* __restrict__ im
 // filters of projectPointCloud (:654-668)
 LILOC_DEV bool deskew_keep(const DeskewArgs& a, int i, const float4 p, int ring) {
     const float range = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
-    if (range < a.rmin || range > a.rmax) return false;
+    // written so that a non-finite point fails (NaN compares false): the reference refuses non-dense clouds altogether
+    // (src/imageProjection.cpp:395-399); for finite input this is the same test as `range < min || range > max` (:655)
+    if (!(range >= a.rmin && range <= a.rmax)) return false;
     if (ring < 0 || ring >= a.n_scan) return false;
     if (ring % a.ds_rate != 0) return false;
     if (i % a.pf_num != 0) return false;

@@ -98,7 +98,7 @@ struct HostFrameInfo {     // pinned, written by async D2H
     int dk_n[2];                         // de-skewed points of the two sweep slots
     unsigned long long dk_marks[3];      // de-skew launch: block 0 at start / after the barrier / end
     unsigned done_seq;                   // written last by the registration kernel: sequence number of the finished frame
-    int pipe_error;                      // set by the point-cloud pipeline when a look-back wait gave up
+    int pipe_error;                      // set by the point-cloud pipeline: 1 a look-back wait gave up, 2 a non-finite input point
 };
 
 }  // namespace
@@ -112,7 +112,7 @@ struct liloc_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
     std::string err;
     long long launches = 0;
-    bool pipe_failed = false;            // a pipeline launch reported a look-back time-out since the last check
+    int pipe_failed = 0;                 // error code of a pipeline launch that failed since the last check (0: none)
     unsigned pipe_epoch = 0;             // launch counter of the point-cloud pipeline (tags its look-back words)
 
     // keyframe arena
@@ -555,14 +555,23 @@ int s2m_collect(liloc_ctx* ctx, float* pose6, liloc_s2m_result* res, const liloc
     return r.skipped ? LILOC_SKIPPED : LILOC_OK;
 }
 
+// After a synchronisation behind a pipeline launch: did the launch report a failure (mapped host word)?  A failed launch
+// leaves no usable map / scan / memoised key behind: a later liloc_scan2map must not run on half-made state.
+int pipe_check(liloc_ctx* ctx) {
+    const int e = ctx->h_info->pipe_error;
+    if (!e) return 0;
+    ctx->h_info->pipe_error = 0;
+    if (e == 2) { ctx->err = "a point with a non-finite coordinate in an input cloud (all input coordinates must be finite)"; ctx->pipe_failed = LILOC_ERR_ARG; }
+    else { ctx->err = "point-cloud pipeline: a look-back wait gave up (results of this call are not valid)"; ctx->pipe_failed = LILOC_ERR_CUDA; }
+    for (FeatClass& fc : ctx->fc) { fc.have_map = false; fc.have_scan = false; fc.M = -1; fc.Q_all = -1; }
+    for (auto& k : ctx->map_key) k.valid = false;
+    return ctx->pipe_failed;
+}
+
 // pick up the device-side counts after a synchronisation
 void class_collect(liloc_ctx* ctx, int cls, bool map, bool scan) {
     FeatClass& fc = ctx->fc[cls];
-    if (ctx->h_info->pipe_error) {           // sticky until read: surfaces through liloc_last_error of the next failing call
-        ctx->h_info->pipe_error = 0;
-        ctx->err = "point-cloud pipeline: a look-back wait gave up (results of this call are not valid)";
-        ctx->pipe_failed = true;
-    }
+    pipe_check(ctx);
     if (map) fc.M = ctx->h_info->c[cls].M;
     if (scan) { fc.Q_all = ctx->h_info->c[cls].Q_all; fc.q_prev = fc.Q_all; }
 }
@@ -816,7 +825,7 @@ int liloc_localmap_build_class(liloc_ctx* ctx, int cls, const int* kf_ids, const
     if ((rc = class_fetch(ctx, cls, ctx->stream, true, false))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, true, false);
-    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
+    if (ctx->pipe_failed) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     if (M_out) *M_out = ctx->fc[cls].M;
     if (n_raw_out) *n_raw_out = ctx->fc[cls].n_raw;
     return LILOC_OK;
@@ -845,7 +854,7 @@ int liloc_localmap_set_class(liloc_ctx* ctx, int cls, const liloc_point* pts, in
     CU(cudaStreamSynchronize(ctx->stream));
     fc.have_map = true;
     class_collect(ctx, cls, true, false);
-    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
+    if (ctx->pipe_failed) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     if (M_out) *M_out = fc.M;
     return LILOC_OK;
 }
@@ -882,7 +891,7 @@ static int scan_put_impl(liloc_ctx* ctx, int cls, const liloc_point* pts, int n,
     if ((rc = class_fetch(ctx, cls, ctx->stream, false, true))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     class_collect(ctx, cls, false, true);
-    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
+    if (ctx->pipe_failed) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     if (on_device == LILOC_SCAN_DESKEWED) { liloc_ctx::DkSweep& S = ctx->dk[ctx->dk_cur]; S.n = ctx->h_info->dk_n[ctx->dk_cur]; ctx->fc[cls].n_scan_last = S.n; }
     if (cls == LILOC_SURF) ctx->corner_scan_current = false;      // a new frame starts with its surf scan
     else ctx->corner_scan_current = true;
@@ -1100,7 +1109,11 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
                          (K == 0 || (std::memcmp(key.ids.data(), in->kf_ids, K * sizeof(int)) == 0 &&
                                      std::memcmp(key.poses.data(), in->kf_poses6, K * 6 * sizeof(float)) == 0));
         if (hit) { ++ctx->map_cache_hits; continue; }
-        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[pm.n_prob], &pm))) return rc;
+        if ((rc = localmap_problem(ctx, cls, ctx->stream, in->kf_ids, in->kf_poses6, in->K, in->map_leaf[cls], &pm.prob[pm.n_prob], &pm))) {
+            // the scans were staged (and their upload enqueued) but no pipeline launch will follow: they are not usable
+            for (int c2 = 0; c2 < ncls; ++c2) { ctx->fc[c2].have_scan = false; ctx->fc[c2].Q_all = -1; }
+            return rc;
+        }
         ++pm.n_prob;
         if (ctx->map_cache) {
             key.ids.assign(in->kf_ids, in->kf_ids + K); key.poses.assign(in->kf_poses6, in->kf_poses6 + 6 * K);
@@ -1152,7 +1165,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
         if (map_launched) ctx->stats.alg_bytes_map += 16.0 * fc.n_raw + 16.0 * (fc.M > 0 ? fc.M : 0);
         ctx->stats.alg_bytes_scan += 16.0 * fc.n_scan_last + 16.0 * (fc.Q_all > 0 ? fc.Q_all : 0);
     }
-    if (ctx->pipe_failed) { ctx->pipe_failed = false; return LILOC_ERR_CUDA; }
+    if (ctx->pipe_failed) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     return s2m_collect(ctx, pose6, res, o);
 }
 
@@ -1197,6 +1210,7 @@ int liloc_voxelgrid(liloc_ctx* ctx, const liloc_point* in, int n, float leaf, li
     int m = 0;
     CU(cudaMemcpyAsync(&m, ctx->tmp_i.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (pipe_check(ctx)) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     *m_out = m;
     if (m > cap) return fail(ctx, LILOC_ERR_CAPACITY, "voxelgrid: cap %d < m %d", cap, m);
     if (m > 0) CU(cudaMemcpyAsync(out, outb.p, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1364,6 +1378,7 @@ int liloc_globalmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6
     int m = 0;
     CU(cudaMemcpyAsync(&m, ax.vg_map.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (pipe_check(ctx)) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     *M_out = m;
     if (out) {
         if (m > cap) return fail(ctx, LILOC_ERR_CAPACITY, "globalmap_build: cap %d < M %d", cap, m);
@@ -1409,6 +1424,7 @@ int icp_fitness_dev(liloc_ctx* ctx, const float4* d1, int n1, const float* pose6
     k_seq_mean<<<1, 32, 0, ctx->stream>>>(ctx->aux_d2.p, n1, ctx->aux_d2.p + n1); KCHECK();
     CU(cudaMemcpyAsync(score_out, ctx->aux_d2.p + n1, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (pipe_check(ctx)) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     return LILOC_OK;
 }
 
@@ -1496,6 +1512,7 @@ static int ndt_target_build_into(liloc_ctx* ctx, liloc_ctx::NdtTargetHost& T, in
     VgParams vp;
     CU(cudaMemcpyAsync(&vp, ctx->fc[0].vg_map.d_vp, sizeof(VgParams), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (pipe_check(ctx)) { const int e = ctx->pipe_failed; ctx->pipe_failed = 0; return e; }
     if (vp.overflow) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_target_put: leaf size too small for the target extent (PCL overflow guard)");
     int divb[3];
     divb[0] = vp.mul[1]; divb[1] = vp.mul[1] ? vp.mul[2] / vp.mul[1] : 1;

@@ -792,15 +792,17 @@ struct NdtAlignArgs {
 
 LILOC_DEV unsigned long long ndt_ld_entry(const unsigned long long* p) { return *((const volatile unsigned long long*)p); }
 
-// publish the tickets of one sweep of `job` (whole warp; lane 0's values are used)
-LILOC_DEV void ndt_publish(const NdtAlignArgs& a, int job, int n_tiles, int grain) {
+// Publish the tickets of one sweep of `job` (whole warp).  The ticket numbers are reserved first (ndt_reserve, lane 0): the
+// atomic's round trip then overlaps whatever the warp still has to write; consumers wait on the tags, not on `tail`.
+LILOC_DEV unsigned ndt_reserve(const NdtAlignArgs& a, int n_tiles, int grain) {
+    return atomicAdd(a.q.tail, (unsigned)((n_tiles + grain - 1) / grain));
+}
+LILOC_DEV void ndt_publish(const NdtAlignArgs& a, int job, int n_tiles, int grain, unsigned base_lane0) {
     const int lane = threadIdx.x & 31;
     const int n_tick = (n_tiles + grain - 1) / grain;
     __threadfence();                                      // job state, pose tables, arrival counter before the tickets
     __syncwarp();
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(a.q.tail, (unsigned)n_tick);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned base = __shfl_sync(0xffffffffu, base_lane0, 0);
     for (int i = lane; i < n_tick; i += 32) {
         const unsigned t = base + (unsigned)i;
         const unsigned long long e = ((unsigned long long)(t + 1u) << 32) | 0x80000000ull | ((unsigned long long)job << 10) | (unsigned long long)(i * grain);
@@ -856,14 +858,14 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
     if (lane < kNdtSums) {
         const double* pj = a.partial + (size_t)job * a.tiles_max * kNdtSums + lane;
         double v = 0.0;
-        // 16 (predicated) loads in flight per trip -- an L2 round trip is ~0.5 us --, summed in tile order
+        // 32 (predicated) loads in flight per trip -- an L2 round trip is ~0.5 us and a VLP-16 scan is 29 tiles --, summed in tile order
 #pragma unroll 1
-        for (int t = 0; t < n_tiles; t += 16) {
-            double w[16];
+        for (int t = 0; t < n_tiles; t += 32) {
+            double w[32];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) w[u] = (t + u < n_tiles) ? __ldcg(&pj[(size_t)(t + u) * kNdtSums]) : 0.0;
+            for (int u = 0; u < 32; ++u) w[u] = (t + u < n_tiles) ? __ldcg(&pj[(size_t)(t + u) * kNdtSums]) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) if (t + u < n_tiles) v += w[u];
+            for (int u = 0; u < 32; ++u) if (t + u < n_tiles) v += w[u];
         }
         us.sums[lane] = v;
     }
@@ -874,7 +876,9 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
     }
     __syncwarp();
     if (prof) c1 = clock64();
-    bool new_trial = false, go = false, restart = false;
+    bool new_trial = false, go = false;
+    int grain = 1;
+    unsigned base = 0;
     double xt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (lane == 0) {
         NdtJob& L = us.job;
@@ -887,16 +891,18 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
                 for (int i = 0; i < 12; ++i) g[i] = L.Tfinal[i];
                 ndt_job_begin(L, g);
                 L.align_pass = pass;
-                restart = true;
             }
         }
         go = L.phase != NDT_DONE;
 #pragma unroll
         for (int i = 0; i < 6; ++i) xt[i] = L.x_t[i];
+        if (go) {                                         // ticket numbers and granularity of the next sweep: reserved now, the
+            grain = ndt_grain(a, n_tiles);                // round trip of the atomic overlaps the pose tables and the stores
+            base = ndt_reserve(a, n_tiles, grain);
+        }
     }
     go = __shfl_sync(0xffffffffu, go ? 1 : 0, 0) != 0;
     new_trial = __shfl_sync(0xffffffffu, new_trial ? 1 : 0, 0) != 0;
-    (void)restart;
     if (prof) c2 = clock64();
     NdtPoseCache* pc = &hot->pc;
     ndt_pose_cache_fill_warp(xt, go, pc);                 // the next sweep's transform and angle tables, six lanes for the sin / cos
@@ -913,14 +919,12 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
         for (int i = lane; i < (int)(sizeof(NdtJob) / sizeof(int)); i += 32) dst[i] = src[i];
     }
     if (go) {
-        int grain = 1;
         if (lane == 0) {
-            grain = ndt_grain(a, n_tiles);
             *((volatile int*)&a.sync[job].done) = 0;
             *((volatile int*)&hot->grain) = grain;
         }
         grain = __shfl_sync(0xffffffffu, grain, 0);
-        ndt_publish(a, job, n_tiles, grain);
+        ndt_publish(a, job, n_tiles, grain, base);
     } else {
         if (lane == 0 && a.rows) ndt_pack_row(us.job, __ldcg(&vw->n), a.rows + (size_t)job * 8);
         __threadfence();
@@ -938,7 +942,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
     __shared__ NdtSweepShared sh;
     __shared__ NdtUpdateShared us;
     __shared__ NdtJobView s_view;
-    __shared__ int s_ticket, s_last, s_grain, s_pad;
+    __shared__ int s_ticket, s_last, s_grain;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long t_sweep = 0, t_update = 0, t_wait = 0, n_tick = 0, n_upd = 0, t_begin = 0;
     const bool prof = a.prof != nullptr && threadIdx.x == 0;
@@ -964,12 +968,14 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
             n_tiles = __shfl_sync(0xffffffffu, n_tiles, 0);
             ndt_pose_cache_fill_warp(xt, true, &a.hot[j].pc);
             int grain = 1;
+            unsigned base = 0;
             if (lane == 0) {
                 grain = ndt_grain_for(a.n_jobs, n_tiles, (int)gridDim.x);
+                base = ndt_reserve(a, n_tiles, grain);
                 a.sync[j].done = 0; a.hot[j].grain = grain; a.hot[j].pad = 0;
             }
             grain = __shfl_sync(0xffffffffu, grain, 0);
-            ndt_publish(a, j, n_tiles, grain);
+            ndt_publish(a, j, n_tiles, grain, base);
         }
     }
     // ---- consumer loop
@@ -1003,8 +1009,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
             constexpr int kViewWords = sizeof(NdtJobView) / sizeof(int);
             if (threadIdx.x < kViewWords) reinterpret_cast<int*>(&s_view)[threadIdx.x] = w;
             else if (threadIdx.x == kViewWords) s_grain = w;
-            else if (threadIdx.x == kViewWords + 1) s_pad = w;
-            else reinterpret_cast<int*>(&sh.pc)[threadIdx.x - kViewWords - 2] = w;
+            else if (threadIdx.x > kViewWords + 1) reinterpret_cast<int*>(&sh.pc)[threadIdx.x - kViewWords - 2] = w;
         }
         __syncthreads();
         unsigned long long t1 = 0;

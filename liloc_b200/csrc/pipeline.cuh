@@ -81,10 +81,11 @@ struct PipeArgs {
     unsigned epoch;              // launch counter: tags the look-back words, so they never need clearing
     KfDesc inline_descs[kInlineDescs];
     unsigned long long* marks;   // optional: %globaltimer (ns) at every phase boundary, written by block 0 (latency breakdown)
-    int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters + the sort-block counter
-    int* error_flag;             // mapped host word: set when a look-back wait gives up (the host then reports an error)
+    int* sm_scratch;             // kSmScratch zeroed ints per launch in flight: per-SM arrival counters, the sort-block counter, the abort word
+    int* error_flag;             // mapped host word: 1 when a look-back wait gave up, 2 when an input point was not finite
 };
-constexpr int kSmScratch = 513;
+constexpr int kSmAbort = 513;         // index of the abort word in sm_scratch
+constexpr int kSmScratch = 514;
 
 LILOC_DEV int prob_n(const VgProb& q) { return q.n_dev ? min(__ldg(q.n_dev), q.n) : q.n; }
 
@@ -211,6 +212,10 @@ union PipeSmem { PipeSmemSort sort; PipeSmemRun run; int hist[256]; };
 LILOC_DEV void pipe_bbox(const PipeArgs& a, const VgProb& q) {
     const KfDesc* __restrict__ descs = q.inline1 ? &a.inline_descs[q.inline1 - 1] : q.descs;
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    // Input coordinates must be finite (include/liloc_gpu.h; the reference shuts down on a non-dense cloud,
+    // src/imageProjection.cpp:395-399).  A NaN / Inf would leave the bounding box yet still get a voxel key and a search
+    // cell -- out-of-range indices further down.  It is detected here, where every point passes once, and aborts the launch.
+    bool bad = false;
     if (q.K > 0) {
         __shared__ int s_k0;
         for (int tile = blockIdx.x; tile * kAsmTile < prob_n(q); tile += gridDim.x) {
@@ -249,6 +254,7 @@ LILOC_DEV void pipe_bbox(const PipeArgs& a, const VgProb& q) {
                 if (d[j]) {
                     const float4 o = apply_T(d[j]->T, p[j]);
                     q.raw[i] = o;
+                    bad |= !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z));
                     mn[0] = fminf(mn[0], o.x); mx[0] = fmaxf(mx[0], o.x);
                     mn[1] = fminf(mn[1], o.y); mx[1] = fmaxf(mx[1], o.y);
                     mn[2] = fminf(mn[2], o.z); mx[2] = fmaxf(mx[2], o.z);
@@ -258,11 +264,13 @@ LILOC_DEV void pipe_bbox(const PipeArgs& a, const VgProb& q) {
     } else {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prob_n(q); i += gridDim.x * blockDim.x) {
             const float4 p = __ldg(&q.pts[i]);
+            bad |= !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
             mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
             mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
             mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
         }
     }
+    if (bad) atomicOr(&a.sm_scratch[kSmAbort], 1);
     block_minmax_commit(mn, mx, q.enc);
     // histogram buffers 1 and 2 must be zero when the first scatter pass accumulates into them
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kHistStride; i += gridDim.x * blockDim.x) q.hist[kHistStride + i] = 0;
@@ -555,6 +563,15 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     for (int p = 0; p < np; ++p) pipe_bbox(a, a.prob[p]);                                   // P0
     grid.sync();
     PIPE_MARK();                                                                          // 1 after assemble + bbox
+    if (__ldcg(&a.sm_scratch[kSmAbort]) != 0) {                                             // a non-finite input point: nothing below may run
+        grid.sync();                                                                       // every block has read the word
+        if (blockIdx.x == 0) {
+            for (int i = threadIdx.x; i < kSmScratch; i += kPipeThreads) a.sm_scratch[i] = 0;
+            if (threadIdx.x < 6 * np) { const int p = threadIdx.x / 6, w = threadIdx.x % 6; a.prob[p].enc[w] = w < 3 ? 0xFFFFFFFFu : 0u; }
+            if (threadIdx.x == 0 && a.error_flag) *(volatile int*)a.error_flag = 2;
+        }
+        return;
+    }
 
     if (threadIdx.x == 0) s_nsort = min(__ldcg(&a.sm_scratch[512]), kSortBlocksMax);
     if (threadIdx.x < np) {                                                               // P1

@@ -500,13 +500,16 @@ int mapOptimization::searchNearestSubMap(float x, float y, float z) const {
     return best;
 }
 
-// kdtreeSearchVertex_->radiusSearch(pose, 5.0) over the submap's vertices, ascending distance, first three
-// (dataLoader.hpp:366-389; the extra skip rule there only concerns vertices added by addNewPrior, which is out of scope)
+// kdtreeSearchVertex_->radiusSearch(pose, 5.0), ascending distance, first three (dataLoader.hpp:366-389).  The reference
+// searches subMapVertexCloudVec_[map_id] -- but generateSubMaps pushes the SAME, never cleared `vertexCloud` pointer for
+// every submap (:311-325), so each entry is the whole prior trajectory and the ids are key-pose indices: near a submap
+// border the vertices of the neighbouring submap are found too.  Mirrored here: all prior key poses are searched.  (The
+// extra skip rule of :376-380 only concerns vertices added by addNewPrior during the session.)
 std::vector<int> mapOptimization::searchVertexes(int submap, float x, float y, float z) const {
+    (void)submap;
     std::vector<std::pair<float, int>> hits;
     const PointType q{x, y, z, 0.f};
-    for (int k = 0; k < prior_.submap_count[submap]; ++k) {
-        const int id = prior_.submap_first[submap] + k;
+    for (int id = 0; id < (int)prior_.KeyPoses6D.size(); ++id) {
         const PointTypePose& p = prior_.KeyPoses6D[id];
         const float d = sqDist(q, PointType{p.x, p.y, p.z, 0.f});
         if (d < 25.0f) hits.push_back({d, id});

@@ -33,6 +33,24 @@ def test_reference_arm_lio_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms describe the workload with the very same `config` object (bench.lio_config)
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.lio_config(argparse.Namespace(frames=40, seed=2000, ref_frames=3))
+
+
+def test_reference_arm_does_not_map_the_product_libraries():
+    """The CPU arm must not load libliloc_gpu.so / libliloc_host.so (it imports liloc_b200.parallel and .synth only; the
+    package binding is lazy and the yaml is read with PyYAML)."""
+    code = ("import sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--ref-frames', '2', '--frames', '40'];"
+            f"sys.path.insert(0, {ROOT!r}); import bench; bench.main();"
+            "m = open('/proc/self/maps').read(); import os; os.write(2, ('LIBS ' + ' '.join(sorted({l.split('/')[-1] for l in m.splitlines() if 'libliloc' in l})) + '\\n').encode())")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, LILOC_BENCH_QUICK="1"), cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    libs = [l for l in r.stderr.splitlines() if l.startswith("LIBS ")][-1].split()[1:]
+    assert "libliloc_gpu.so" not in libs and "libliloc_host.so" not in libs, libs
+    assert "libliloc_oracle.so" in libs
 
 
 def test_reference_arm_ndt_line():

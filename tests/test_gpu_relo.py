@@ -101,9 +101,11 @@ def test_relo_mode_through_host_class(orc, synth):
             assert np.abs(got[3:] - Tm[:, 3]).max() <= 1e-4
             assert np.abs(synth.rot_zyx(*[float(v) for v in got[:3]]) - Tm[:, :3]).max() <= 1e-5
             assert np.abs(got[3:5] - cur[f][3:5]).max() < 0.2       # NDT at 1 m resolution with eps 0.01: decimetre-level
-            # prior vertices within 5 m (at most 3, nearest first) and their ICP fitness against the matched scan
-            d2 = ((prior_traj[lo:lo + 10, 3:].astype(np.float32) - pose[3:]) ** 2).sum(1)
-            near = [lo + int(k) for k in np.argsort(d2, kind="stable") if d2[k] < 25.0][:3]
+            # prior vertices within 5 m (at most 3, nearest first; over the WHOLE prior trajectory -- every entry of the
+            # reference's subMapVertexCloudVec_ is the same never-cleared cloud, dataLoader.hpp:311-325) and their ICP fitness
+            # against the matched scan
+            d2 = ((prior_traj[:, 3:].astype(np.float32) - pose[3:]) ** 2).sum(1)
+            near = [int(k) for k in np.argsort(d2, kind="stable") if d2[k] < 25.0][:3]
             assert rep.relo_n_vertices == len(near) and list(rep.relo_vertex)[: len(near)] == near
             for v, vid in enumerate(near):
                 want = orc.icp_fitness(prior_clouds[vid], prior_traj[vid].astype(np.float32), scans[f], got, threads=8)

@@ -439,6 +439,12 @@ def run_ours(args):
                "map_points": int(np.mean([r.map_points for r in reps if r.map_points > 0])),
                "keyframes_selected": float(np.mean([r.n_selected_keyframes for r in reps if r.n_selected_keyframes > 0])),
                "keyframes_total": m.num_keyframes()}
+    # ---- throughput mode (north_star "batches of frames"): S independent sequences per GPU, each with its own
+    # host object, context and streams, driven by S host threads (one frame uses a fraction of the SMs; frames of ONE sequence
+    # are sequentially dependent, frames of different sequences are not).  Not part of value / e2e.
+    conc = None
+    if not args.no_concurrent:
+        conc = concurrent_sequences(args, local, dev, infos_dev, infos_host, l2_flush, reps)
     # ---- the work that shards (BASELINE configs[3], configs[4]): every rank takes part
     ndt = None
     if not args.no_ndt:
@@ -509,7 +515,7 @@ def run_ours(args):
                         "note": "the frame fed the raw sweep (imageProjection's de-skew + filters on the device, f3); not part of value / e2e"},
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         "host": {"nproc": os.cpu_count()},
-        "ndt": ndt,
+        "ndt": ndt, "concurrent_sequences": conc,
     }
     out.update(parity)
     m.close()
@@ -683,6 +689,64 @@ def ndt_one(args, name, ctx, rank, world, local, dev, steps, warmup, do_cpu, sin
                              "double accumulation: the kernel is instruction-issue bound, the HBM fraction is nominal"},
         "single_call": single, "cpu_baseline": cpu, "clocks": clocks,
     }
+
+
+def concurrent_sequences(args, local, dev, infos_dev, infos_host, l2_flush, reps_ref):
+    """S replicas of the benchmark sequence at once on one GPU: S `mapOptimization` objects (S contexts, 3 streams each), one
+    host thread per object (the C call releases the GIL).  Every replica must reproduce the single-sequence poses bit for bit."""
+    import threading
+    import torch
+    from liloc_b200 import host_api, parallel
+    out = {}
+    objs = []
+    F = len(infos_dev)
+    for S in (1, 2, 4, 8):
+        while len(objs) < S:
+            objs.append(host_api.MapOptimization(YAML, "lio", device=local))
+        res = {}
+
+        def one_round(infos):
+            for m in objs[:S]:
+                m.reset()
+            l2_flush.fill_(1)
+            torch.cuda.synchronize()
+            got = [None] * S
+            lat = [None] * S
+
+            def work(k):
+                got[k] = objs[k].run(infos)
+
+            th = [threading.Thread(target=work, args=(k,)) for k in range(S)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, got
+
+        for label, infos in (("value", infos_dev), ("e2e", infos_host)):
+            one_round(infos)                                   # warm-up (allocations of the new contexts)
+            steps = max(2, min(args.steps, 5))
+            tt, got = 0.0, None
+            for _ in range(steps):
+                parallel.barrier()
+                dt, got = one_round(infos)
+                tt += dt
+            tt = parallel.max_over_ranks(tt, dev)
+            n_proc = sum(1 for r in got[0] if r.processed)
+            frames = parallel.sum_over_ranks(n_proc * S * steps, dev)
+            lat = [r.reg_ms for g in got for r in g if r.processed and r.iters > 0]
+            same = all(tuple(a.pose) == tuple(b.pose) and a.iters == b.iters for g in got for a, b in zip(g, reps_ref))
+            if not same:
+                raise SystemExit(f"bench.py: a concurrent replica (S={S}) does not reproduce the single-sequence poses")
+            res[label] = {"registrations_per_s": frames / tt, "p50_frame_ms": float(np.percentile(lat, 50)), "p95_frame_ms": float(np.percentile(lat, 95))}
+        out[f"S={S}"] = res
+    for m in objs:
+        m.close()
+    out["note"] = ("S replicas of the same sequence processed concurrently on every GPU of the launch (registrations/s summed over ranks); "
+                   "poses bit-identical to the single-sequence run")
+    return out
 
 
 def _static_scene(name):
@@ -891,6 +955,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ndt", action="store_true", help="lio line without the sharded NDT sections")
     ap.add_argument("--no-latency", action="store_true", help="lio line without extra.latency")
+    ap.add_argument("--no-concurrent", action="store_true", help="lio line without the S-concurrent-sequences throughput mode")
     ap.add_argument("--workload", choices=["lio", "relo", "jfgo", "batch"], default="lio",
                     help="lio = configs[1] (default, headline); relo = configs[3]; jfgo / batch = configs[4]")
     ap.add_argument("--items", type=int, default=0, help="relo: hypotheses (256); batch: triples (8000)")

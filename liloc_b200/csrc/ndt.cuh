@@ -820,9 +820,7 @@ LILOC_DEV int ndt_grain_for(int active_jobs, int n_tiles, int grid) {
     if (g > n_tiles) g = n_tiles;
     return (int)g;
 }
-LILOC_DEV int ndt_grain(const NdtAlignArgs& a, int n_tiles) {
-    return ndt_grain_for(a.n_jobs - *((volatile int*)a.q.finished), n_tiles, (int)gridDim.x);
-}
+
 
 // RotMtoEuler (include/math_tools.h:92-111) of the rotation block + translation -> [roll, pitch, yaw, x, y, z], evaluated in
 // double and rounded to float (what liloc_b200/relo.py::matrices_to_pose6 does on the host)
@@ -849,6 +847,8 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
     NdtHot* hot = &a.hot[job];
     const NdtJobView* vw = &hot->view;
     const int n_tiles = __ldcg(&vw->n_tiles);
+    int finished = 0;                                     // read now: in flight together with everything below
+    if (lane == 0) finished = *((volatile int*)a.q.finished);
     int jw[(sizeof(NdtJob) / sizeof(int) + 31) / 32];     // the job state, 32 lanes wide: in flight together with the partial sums
     {
         const int* src = reinterpret_cast<const int*>(&a.jobs[job]);
@@ -897,7 +897,7 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
 #pragma unroll
         for (int i = 0; i < 6; ++i) xt[i] = L.x_t[i];
         if (go) {                                         // ticket numbers and granularity of the next sweep: reserved now, the
-            grain = ndt_grain(a, n_tiles);                // round trip of the atomic overlaps the pose tables and the stores
+            grain = ndt_grain_for(a.n_jobs - finished, n_tiles, (int)gridDim.x);      // round trip of the atomic overlaps the pose tables and the stores
             base = ndt_reserve(a, n_tiles, grain);
         }
     }

@@ -171,10 +171,11 @@ LILOC_DEV int block_sum_256(int v) {                        // all 256 threads; 
 LILOC_DEV void pipe_publish(unsigned long long* state, int tile, int total, unsigned epoch) {
     if (threadIdx.x == 0) atomicExch(&state[tile], ((unsigned long long)epoch << 32) | (unsigned)total);
 }
-LILOC_DEV int pipe_lookback(unsigned long long* state, int tile, int total, unsigned epoch, int* error_flag, bool publish = true) {
+// sum of the published totals of tiles [lo, tile)
+LILOC_DEV int pipe_lookback(unsigned long long* state, int tile, int total, unsigned epoch, int* error_flag, bool publish = true, int lo = 0) {
     if (publish) pipe_publish(state, tile, total, epoch);
     int part = 0;
-    for (int u = threadIdx.x; u < tile; u += kPipeThreads) {
+    for (int u = lo + threadIdx.x; u < tile; u += kPipeThreads) {
         unsigned long long w;
         int spins = 0;
         do { w = *((volatile unsigned long long*)&state[u]); } while ((unsigned)(w >> 32) != epoch && ++spins < (1 << 22));
@@ -205,7 +206,9 @@ struct PipeSmemSort {
     unsigned short cnt[kSortUnits][256];           // items of digit d in unit u (zero between tiles)
     unsigned short pre[kSortUnits][256];           // exclusive prefix of cnt over the units
 };
-struct PipeSmemRun { unsigned key[kRunTile]; float4 pt[kRunTile]; unsigned prev; };
+// a tile of sorted pairs plus a halo of the following kRunHalo pairs: a voxel run that starts in the tile continues there
+constexpr int kRunHalo = 512;
+struct PipeSmemRun { unsigned key[kRunTile + kRunHalo]; float4 pt[kRunTile + kRunHalo]; unsigned prev; };
 union PipeSmem { PipeSmemSort sort; PipeSmemRun run; int hist[256]; };
 
 // ---- P0 -------------------------------------------------------------------------------------------------------
@@ -417,13 +420,22 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
             pipe_publish(q.tile_state, tile, block_sum_256(c), epoch);
         }
     }
+    // A block's later tiles do not sum the head counts of ALL earlier tiles again (tile 800 of a 836 k-point map: four
+    // dependent L2 round trips per tile, O(tiles^2) loads in total): the offset of the block's previous tile is carried
+    // and only the tiles in between are added -- at most one word per thread, one round trip.
+    int prev_tile = -1, prev_end = 0;                           // prev_end = run heads in tiles [0, prev_tile]
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * kRunTile;
         const int cnt = min(kRunTile, n - base);
+        // The tile AND the kRunHalo pairs behind it are gathered into shared memory by all threads.  A run that straddles the
+        // end of the tile used to be continued by its head thread alone through dependent global loads (key -> index ->
+        // point: three L2 round trips per element, ~1.5 us each) -- every tile has such a run, and on maps where a voxel
+        // collects points of many keyframes that tail was the longest piece of the phase.
+        const int ext = min(kRunTile + kRunHalo, n - base);     // pairs available in shared memory
 #pragma unroll
-        for (int j = 0; j < kRunPerThread; ++j) {
+        for (int j = 0; j < (kRunTile + kRunHalo) / kPipeThreads; ++j) {
             const int l = j * kPipeThreads + threadIdx.x;
-            if (l < cnt) {
+            if (l < ext) {
                 sm.run.key[l] = skeys[base + l];
                 sm.run.pt[l] = q.pts[svals[base + l]];
             }
@@ -443,7 +455,8 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
         }
         int total;
         const int local_rank = block_exclusive_scan_256(c, &total);
-        const int tile_offset = pipe_lookback(q.tile_state, tile, total, epoch, error_flag, !ahead);      // run heads in all earlier tiles
+        const int tile_offset = prev_end + pipe_lookback(q.tile_state, tile, total, epoch, error_flag, !ahead, prev_tile + 1);      // run heads in all earlier tiles
+        prev_tile = tile; prev_end = tile_offset + total;
         int rank = tile_offset + local_rank;
         if (tile == n_tiles - 1 && threadIdx.x == 0) *q.count = tile_offset + total;
 #pragma unroll
@@ -460,8 +473,8 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
                 float4 pp[4]; bool same[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int ee = min(e + u, cnt - 1);
-                    same[u] = (e + u < cnt) && sm.run.key[ee] == key;
+                    const int ee = min(e + u, ext - 1);
+                    same[u] = (e + u < ext) && sm.run.key[ee] == key;
                     pp[u] = sm.run.pt[ee];
                 }
 #pragma unroll
@@ -471,12 +484,21 @@ LILOC_DEV void pipe_centroids(const VgProb& q, const GridParams& gp, PipeSmem& s
                 }
             }
             int len = e - l;
-            if (e == cnt) {                              // run may continue in the next tile(s)
-                int gi = base + cnt;
-                while (gi < n && skeys[gi] == key) {
-                    const float4 p = q.pts[svals[gi]];
-                    sx += p.x; sy += p.y; sz += p.z; sw += p.w;
-                    ++gi; ++len;
+            if (e == ext) {                              // longer than the halo: the rest from global memory, four pairs per trip
+                int gi = base + ext;
+                bool go_on = gi < n;
+                while (go_on) {
+                    unsigned kk[4]; float4 pg[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) kk[u] = (gi + u < n) ? skeys[gi + u] : ~key;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pg[u] = (gi + u < n && kk[u] == key) ? q.pts[svals[gi + u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (go_on && gi + u < n && kk[u] == key) { sx += pg[u].x; sy += pg[u].y; sz += pg[u].z; sw += pg[u].w; ++len; }
+                        else go_on = false;
+                    }
+                    gi += 4;
                 }
             }
             const float fc = (float)len;
@@ -510,6 +532,7 @@ LILOC_DEV void pipe_cells_count_direct(const VgProb& q, const GridParams& gp) {
 LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsigned epoch, int* error_flag) {
     const int n = gp.ncells;
     const int n_tiles = (n + kScanTile - 1) / kScanTile;
+    int prev_tile = -1, prev_end = 0;                           // carried like in pipe_centroids
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * kScanTile + threadIdx.x * kScanPerThread;
         int v[kScanPerThread];
@@ -518,7 +541,9 @@ LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsi
         for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? q.cell_counts[base + j] : 0; c += v[j]; }
         int total;
         const int local = block_exclusive_scan_256(c, &total);
-        int run = pipe_lookback(q.grid_state, tile, total, epoch, error_flag) + local;
+        const int tile_offset = prev_end + pipe_lookback(q.grid_state, tile, total, epoch, error_flag, true, prev_tile + 1);
+        prev_tile = tile; prev_end = tile_offset + total;
+        int run = tile_offset + local;
 #pragma unroll
         for (int j = 0; j < kScanPerThread; ++j) {
             if (base + j < n) { q.cell_start[base + j] = run; q.cell_counts[base + j] = run; }

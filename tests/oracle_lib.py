@@ -214,6 +214,17 @@ def surf_pass(map_pts, scan_ds, pose6, stride=2, kdtree=False, threads=1, want_k
     return out + ((idx5, d2) if want_knn else ())
 
 
+def lm_step(ori, coef, iter_count, pose6, state: LmState | None = None, min_sel=50):
+    """LMOptimization (src/mapOptmization.cpp:1061-1181) on explicit correspondences.  Returns (rc, pose, AtA, AtB, state):
+    rc -1 fewer than min_sel correspondences (pose untouched), 0 updated, 1 updated and converged."""
+    o, c = _c(ori), _c(coef)
+    p = np.array(pose6, np.float32).reshape(6).copy()
+    st = state if state is not None else LmState()
+    AtA, AtB = np.zeros(36, np.float32), np.zeros(6, np.float32)
+    rc = lib.orc_lm_step(_p(o), _p(c), len(o), int(iter_count), int(min_sel), _p(p), C.byref(st), _p(AtA), _p(AtB))
+    return rc, p, AtA.reshape(6, 6), AtB, st
+
+
 def scan2map(map_pts, scan_ds, pose6, opts: S2mOpts | None = None, state: LmState | None = None):
     m, s = _c(map_pts), _c(scan_ds)
     p = np.array(pose6, np.float32).reshape(6).copy()

@@ -152,3 +152,32 @@ def test_ndt_errors(gpu_ctx):
     from liloc_b200 import LilocError
     with pytest.raises(LilocError):
         gpu_ctx.ndt_align_batch([999], [999], [np.eye(4, dtype=np.float32)])
+
+
+def test_device_against_the_numpy_golden(gpu_ctx):
+    """The device against the oracle-independent golden vectors (tests/golden/make_golden_ndt.py): leaves, the float32
+    restatement's sums, the float64 symbolic sums and the float64 registration."""
+    import os
+    from liloc_b200 import NdtOpts
+    from test_ndt_golden import pose_to_guess
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ndt_np.npz"))
+    pad = lambda a: np.ascontiguousarray(np.c_[a, np.zeros(len(a), np.float32)], np.float32)
+    gpu_ctx.ndt_clear()
+    n = gpu_ctx.ndt_target_put(0, pad(g["target"]), float(g["resolution"]))
+    means, icovs, counts, keys = gpu_ctx.ndt_target_get(0)
+    assert n == len(g["leaf_means"]) and np.array_equal(counts, g["leaf_counts"])
+    assert np.allclose(means, g["leaf_means"], rtol=0, atol=1e-12)
+    assert np.allclose(icovs, g["leaf_icovs"].reshape(-1, 9).astype(np.float32), rtol=2e-6, atol=0)
+    gpu_ctx.ndt_source_put(0, pad(g["source"]))
+    gpu_ctx.ndt_source_put(1, pad(g["source_safe"]))
+    for p, w32, w64 in zip(g["poses"], g["sums_f32"], g["sums_f64_safe"]):
+        got = gpu_ctx.ndt_derivatives(0, 0, p, NdtOpts(search=0))
+        assert np.allclose(got, w32, rtol=1e-12, atol=1e-12 * np.abs(w32).max())
+        got = gpu_ctx.ndt_derivatives(0, 1, p, NdtOpts(search=0))
+        assert np.abs(got - w64).max() <= 1e-4 * np.abs(w64).max()
+    guesses = np.stack([pose_to_guess(p) for p in g["guesses"]])
+    T, score, iters, conv, sweeps = gpu_ctx.ndt_align_batch([0] * 3, [0] * 3, guesses, NdtOpts(trans_eps=float(g["trans_eps"]), search=0))
+    assert np.array_equal(iters, g["final_iterations"]) and conv.all()
+    for j in range(3):
+        want = pose_to_guess(g["finals"][j])
+        assert np.abs(T[j, :3, 3] - want[:, 3]).max() <= 1e-5 and np.abs(T[j, :3, :3] - want[:, :3]).max() <= 1e-5

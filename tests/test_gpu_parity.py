@@ -346,3 +346,61 @@ def test_errors_are_codes_not_exceptions_from_c(gpu_ctx):
     with pytest.raises(LilocError) as e:
         gpu_ctx.localmap_build([123456], np.zeros((1, 6), np.float32), 0.4)
     assert e.value.code < 0 and "unknown keyframe" in str(e.value)
+
+
+def test_non_finite_input_is_rejected_and_the_context_survives(gpu_ctx, orc, synth, scene_small):
+    """A NaN / Inf coordinate in any cloud that passes the point-cloud pipeline (keyframe, scan, VoxelGrid input, NDT target)
+    is an argument error, never an out-of-range write: it leaves the bounding box but would still get a voxel key and a search
+    cell.  The map is put far from the origin (cell_coord(NaN) = -g0 is then out of range).  After each refused call the same
+    context runs a good frame and reproduces the earlier result bit for bit.  The de-skew filters drop such points."""
+    from liloc_b200 import LilocError, NdtOpts
+    sc = scene_small
+    shift = np.array([0, 0, 0, 700.0, -450.0, 30.0], np.float32)
+    poses = sc.kf_poses + shift
+    guess = (sc.guess + shift).astype(np.float32)
+    K = len(sc.kf_clouds)
+
+    def good_frame():
+        gpu_ctx.keyframe_clear()
+        for k, c in enumerate(sc.kf_clouds):
+            gpu_ctx.keyframe_put(k, c)
+        pose, res, rc = gpu_ctx.frame(list(range(K)), poses, sc.map_leaf, sc.scan_raw, sc.scan_leaf, guess)
+        return pose, (res.iters, res.n_sel, res.converged, res.map_points, res.q_all), rc
+
+    p0, r0, rc0 = good_frame()
+    assert rc0 == 0 and r0[0] > 0
+    for bad_value in (np.nan, np.inf, -np.inf):
+        # (1) a bad point in a keyframe cloud
+        bad_kf = sc.kf_clouds[2].copy(); bad_kf[len(bad_kf) // 2, 1] = bad_value
+        gpu_ctx.keyframe_put(900, bad_kf)
+        with pytest.raises(LilocError) as e:
+            gpu_ctx.frame([0, 1, 900, 3], poses[[0, 1, 2, 3]], sc.map_leaf, sc.scan_raw, sc.scan_leaf, guess)
+        assert e.value.code == -1 and "finite" in str(e.value)
+        with pytest.raises(LilocError):                       # a failed frame leaves no usable map / scan behind
+            gpu_ctx.scan2map(guess)
+        assert good_frame() [1] == r0
+        # (2) a bad point in the scan
+        bad_scan = sc.scan_raw.copy(); bad_scan[7, 2] = bad_value
+        with pytest.raises(LilocError) as e:
+            gpu_ctx.frame(list(range(K)), poses, sc.map_leaf, bad_scan, sc.scan_leaf, guess)
+        assert e.value.code == -1
+        # (3) kernel-level VoxelGrid and an NDT target
+        with pytest.raises(LilocError):
+            gpu_ctx.voxelgrid(bad_scan, 0.4)
+        with pytest.raises(LilocError):
+            gpu_ctx.ndt_target_put(77, bad_scan, 1.0)
+        with pytest.raises(LilocError):                       # the failed build left no half-made target behind
+            gpu_ctx.ndt_align_batch([77], [77], [np.eye(4, dtype=np.float32)], NdtOpts())
+        p1, r1, rc1 = good_frame()
+        assert rc1 == 0 and r1 == r0 and np.array_equal(p1, p0)
+    assert np.array_equal(gpu_ctx.voxelgrid(sc.scan_raw, 0.4), orc.voxelgrid(sc.scan_raw, 0.4))
+    # (4) de-skew: the range filter refuses non-finite points
+    sw = synth.raw_sweep(sc.scan_raw, synth.VLP16, seed=3)
+    it, ir = orc.imu_integrate(sw["imu_stamps"], sw["imu_gyro"], sw["time_scan_end"])
+    n_ok = gpu_ctx.deskew(sw["pts"], sw["ring"], sw["time"], it, ir, sw["time_scan_cur"], n_scan=16, point_filter_num=1)
+    pts = sw["pts"].copy(); pts[5, 0] = np.nan; pts[6, 1] = np.inf; pts[9, 2] = -np.inf
+    keep = np.ones(len(pts), bool); keep[[5, 6, 9]] = False
+    n_bad = gpu_ctx.deskew(pts, sw["ring"], sw["time"], it, ir, sw["time_scan_cur"], n_scan=16, point_filter_num=1)
+    ref = orc.deskew(sw["pts"], sw["ring"], sw["time"], it, ir, sw["time_scan_cur"], n_scan=16, point_filter_num=1)
+    kept_ref = orc.deskew(sw["pts"][keep], sw["ring"][keep], sw["time"][keep], it, ir, sw["time_scan_cur"], n_scan=16, point_filter_num=1)
+    assert n_ok == len(ref) and n_bad == len(kept_ref) and np.isfinite(gpu_ctx.deskewed_get()).all()

@@ -94,6 +94,10 @@ const char* liloc_version(void);
 int liloc_keyframe_put(liloc_ctx* ctx, int kf_id, const liloc_point* pts_body, int n);
 /* thisSurfKeyFrame = copy of laserCloudSurfLastDS (:1382,1454): device-to-device, no host traffic */
 int liloc_keyframe_put_from_scan(liloc_ctx* ctx, int kf_id);
+/* priorSession_->keyCloudVec_.push_back(copy of curCloud_) in AnchorOptimization::addNewPrior (include/egoOptimization/
+ * anchorOptimize.hpp:279-282, :318-321): the FULL de-skewed scan of the current frame (laserCloudSurfLast,
+ * src/mapOptmization.cpp:1342) becomes keyframe kf_id, device-to-device */
+int liloc_keyframe_put_from_raw_scan(liloc_ctx* ctx, int kf_id);
 int liloc_keyframe_size(liloc_ctx* ctx, int kf_id);    /* points, or <0 if unknown id */
 int liloc_keyframe_clear(liloc_ctx* ctx);              /* laserCloudMapContainer.clear() + new session */
 
@@ -219,6 +223,10 @@ int liloc_ndt_target_put(liloc_ctx* ctx, int target_id, const liloc_point* pts_m
  * keeps the submap un-down-sampled (:332-336) -- and become NDT target `target_id`.  Nothing crosses PCIe. */
 int liloc_ndt_target_put_keyframes(liloc_ctx* ctx, int target_id, const int* kf_ids, const float* poses6, int K, float resolution,
                                    int* n_leaves_out, int* n_points_out);
+/* The submap AnchorOptimization::addNewPrior cuts after every submap_size keyframes it added (anchorOptimize.hpp:341-377):
+ * like generateSubMaps, but voxel-filtered at filter_leaf (0.2, :363-367) before it becomes the NDT target. */
+int liloc_ndt_target_put_keyframes_filtered(liloc_ctx* ctx, int target_id, const int* kf_ids, const float* poses6, int K, float filter_leaf,
+                                            float resolution, int* n_leaves_out, int* n_points_out);
 int liloc_ndt_target_size(liloc_ctx* ctx, int target_id);      /* points of the target cloud, or <0 if unknown id */
 int liloc_ndt_source_put(liloc_ctx* ctx, int source_id, const liloc_point* pts_body, int n, int on_device);
 int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs);

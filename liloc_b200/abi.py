@@ -207,6 +207,8 @@ def _load() -> C.CDLL:
         "liloc_ndt_stats_get": (C.c_int, [P, C.POINTER(NdtStats)]),
         "liloc_ndt_stats_reset": (C.c_int, [P]),
         "liloc_debug_line": (C.c_int, [P, P, P, C.c_int, P, P]),
+        "liloc_keyframe_put_from_raw_scan": (C.c_int, [P, C.c_int]),
+        "liloc_ndt_target_put_keyframes_filtered": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, C.c_float, ip, ip]),
         "liloc_comm_unique_id": (C.c_int, [P]),
         "liloc_comm_init": (C.c_int, [P, C.c_int, C.c_int, P]),
         "liloc_comm_destroy": (C.c_int, [P]),
@@ -232,7 +234,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
            "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance "
-           "liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results").split()
+           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results").split()
 
 
 COMM_ID_BYTES = 128

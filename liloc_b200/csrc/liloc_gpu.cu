@@ -778,6 +778,26 @@ int liloc_keyframe_put_from_scan(liloc_ctx* ctx, int kf_id) {
     return LILOC_OK;
 }
 
+// priorSession_->keyCloudVec_.push_back(copy of curCloud_) (anchorOptimize.hpp:279-282, :318-321): curCloud_ is
+// laserCloudSurfLast, the FULL de-skewed scan (src/mapOptmization.cpp:1342) -- device-to-device from wherever the current
+// frame's raw scan lives (the upload buffer, the caller's device cloud or the de-skew slot).
+int liloc_keyframe_put_from_raw_scan(liloc_ctx* ctx, int kf_id) {
+    ENTER(ctx);
+    FeatClass& s = ctx->fc[0];
+    if (!s.scan_src_last || s.n_scan_last <= 0) return fail(ctx, LILOC_ERR_STATE, "keyframe_put_from_raw_scan: no scan");
+    const int n = s.n_scan_last;
+    int rc;
+    if ((rc = ensure(ctx, ctx->arena, ctx->arena_used + (size_t)n, true))) return rc;
+    liloc_ctx::KfEntry e{};
+    e.off[0] = ctx->arena_used; e.n[0] = n; e.off[1] = ctx->arena_used + (size_t)n; e.n[1] = 0;
+    CU(cudaStreamSynchronize(ctx->stream2));         // the scan branch of the frame that brought the scan
+    CU(cudaMemcpyAsync(ctx->arena.p + e.off[0], s.scan_src_last, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->kf.count(kf_id)) for (auto& k : ctx->map_key) k.valid = false;
+    ctx->kf[kf_id] = e;
+    ctx->arena_used += (size_t)n;
+    return LILOC_OK;
+}
+
 int liloc_keyframe_size(liloc_ctx* ctx, int kf_id) {
     if (!ctx) return LILOC_ERR_ARG;
     auto it = ctx->kf.find(kf_id);
@@ -1586,6 +1606,23 @@ int liloc_ndt_target_put_keyframes(liloc_ctx* ctx, int target_id, const int* kf_
     asmb.arena = ctx->arena.p; asmb.descs = ctx->ndt_descs.p; asmb.K = K;
     if (n_points_out) *n_points_out = (int)total;
     return ndt_target_build(ctx, target_id, (int)total, resolution, &asmb, n_leaves_out);
+}
+
+// The submap addNewPrior cuts after every submap_size added keyframes (anchorOptimize.hpp:341-377): transform + concatenate
+// like generateSubMaps, but this one IS voxel-filtered (downSizeFilterSurf at 0.2 writes into `submap` itself, :363-367)
+// before it becomes an NDT target.  Two pipeline launches on the device: assemble + VoxelGrid(filter_leaf) in the
+// auxiliary buffers, then keys + sort of the filtered cloud at `resolution`.
+int liloc_ndt_target_put_keyframes_filtered(liloc_ctx* ctx, int target_id, const int* kf_ids, const float* poses6, int K, float filter_leaf,
+                                            float resolution, int* n_leaves_out, int* n_points_out) {
+    ENTER(ctx);
+    if (K <= 0 || !kf_ids || !poses6 || !(resolution > 0.f) || !(filter_leaf > 0.f)) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put_keyframes_filtered: bad arguments");
+    int M = 0, rc;
+    if ((rc = liloc_globalmap_build(ctx, kf_ids, poses6, K, filter_leaf, nullptr, 0, &M))) return rc;
+    if (M <= 0) return fail(ctx, LILOC_ERR_ARG, "ndt_target_put_keyframes_filtered: empty submap");
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)M))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_pts.p, ctx->aux.map.p, (size_t)M * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n_points_out) *n_points_out = M;
+    return ndt_target_build(ctx, target_id, M, resolution, nullptr, n_leaves_out);
 }
 
 int liloc_ndt_target_size(liloc_ctx* ctx, int target_id) {

@@ -33,6 +33,7 @@ struct liloc_host_report {               // mirror of liloc_host::FrameReport
     float relo_pose[6];
     int relo_n_vertices, relo_vertex[3];
     float relo_fitness[3];
+    int prior_added, prior_new_submap;
 };
 
 static thread_local std::string g_err;
@@ -56,6 +57,7 @@ static void to_report(const liloc_host::FrameReport& r, liloc_host_report* o) {
     std::memcpy(o->relo_pose, r.relo_pose, sizeof(o->relo_pose));
     o->relo_n_vertices = r.relo_n_vertices;
     std::memcpy(o->relo_vertex, r.relo_vertex, sizeof(o->relo_vertex)); std::memcpy(o->relo_fitness, r.relo_fitness, sizeof(o->relo_fitness));
+    o->prior_added = r.prior_added; o->prior_new_submap = r.prior_new_submap;
 }
 
 static liloc_host::CloudInfo to_info(const liloc_host_cloud_info& m) {

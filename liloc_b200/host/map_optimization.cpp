@@ -423,6 +423,7 @@ bool mapOptimization::loadPriorSession(const PointTypePose* keyPoses, int n, con
     if (n <= 0 || !keyPoses || !clouds || !offsets) { error_ = "loadPriorSession: bad arguments"; return false; }
     prior_ = PriorSession{};
     prior_.KeyPoses6D.assign(keyPoses, keyPoses + n);
+    prior_.prior_size = n; prior_.end = n;
     for (int i = 0; i < n; ++i) {                                               // loadKeyCloud (dataLoader.hpp:283-304)
         const long long cnt = offsets[i + 1] - offsets[i];
         if (liloc_keyframe_put(ctx_, kPriorKeyframeBase + i, clouds + offsets[i], (int)cnt) < 0) { error_ = liloc_last_error(ctx_); return false; }
@@ -447,6 +448,7 @@ bool mapOptimization::loadPriorSession(const PointTypePose* keyPoses, int n, con
             }
             prior_.SubMapCenteriod.push_back(PointType{x / (float)count, y / (float)count, z / (float)count, (float)sid});
             prior_.submap_first.push_back(first); prior_.submap_count.push_back(count); prior_.submap_points.push_back(pts);
+            prior_.submap_vertexes.emplace_back();      // the shared vertex cloud
             first = i + 1; count = 0; x = y = z = 0.f; ids.clear(); poses.clear();
         }
     }
@@ -501,23 +503,88 @@ int mapOptimization::searchNearestSubMap(float x, float y, float z) const {
 }
 
 // kdtreeSearchVertex_->radiusSearch(pose, 5.0), ascending distance, first three (dataLoader.hpp:366-389).  The reference
-// searches subMapVertexCloudVec_[map_id] -- but generateSubMaps pushes the SAME, never cleared `vertexCloud` pointer for
-// every submap (:311-325), so each entry is the whole prior trajectory and the ids are key-pose indices: near a submap
-// border the vertices of the neighbouring submap are found too.  Mirrored here: all prior key poses are searched.  (The
-// extra skip rule of :376-380 only concerns vertices added by addNewPrior during the session.)
+// searches subMapVertexCloudVec_[map_id].  For the submaps of the LOADED session that is one and the same cloud:
+// generateSubMaps pushes the same, never cleared `vertexCloud` pointer for every submap (:311-325), so each entry is the whole
+// loaded trajectory -- near a submap border the vertices of the neighbouring submap are found too.  A submap cut by
+// addNewPrior has a vertex cloud of its own (anchorOptimize.hpp:343-361).  Vertices this session added within the last 10 key
+// poses are skipped (:376-380; the test is `intensity > prior_size`, so the very first added pose is not).
 std::vector<int> mapOptimization::searchVertexes(int submap, float x, float y, float z) const {
-    (void)submap;
     std::vector<std::pair<float, int>> hits;
     const PointType q{x, y, z, 0.f};
-    for (int id = 0; id < (int)prior_.KeyPoses6D.size(); ++id) {
+    auto consider = [&](int id) {
         const PointTypePose& p = prior_.KeyPoses6D[id];
         const float d = sqDist(q, PointType{p.x, p.y, p.z, 0.f});
         if (d < 25.0f) hits.push_back({d, id});
-    }
+    };
+    const std::vector<int>& own = prior_.submap_vertexes[submap];
+    if (own.empty()) for (int id = 0; id < prior_.prior_size; ++id) consider(id);
+    else for (int id : own) consider(id);
     std::sort(hits.begin(), hits.end());
+    const int curNew = (int)prior_.KeyPoses6D.size();
     std::vector<int> out;
-    for (const auto& h : hits) { if ((int)out.size() == 3) break; out.push_back(h.second); }
+    int count = 0;
+    for (const auto& h : hits) {
+        if (h.second > prior_.prior_size && std::abs(curNew - h.second) <= 10) continue;
+        if (++count > 3) break;
+        out.push_back(h.second);
+    }
     return out;
+}
+
+// AnchorOptimization::addNewPrior, cloud side (anchorOptimize.hpp:272-380).  Called when fewer than two prior vertices are
+// within reach (:387-390): the frame's pose and its FULL scan (curCloud_ = laserCloudSurfLast) join the prior session --
+// at once after a frame that did match (first_add), otherwise only after the saveFrame-style motion gate against the last
+// added pose -- and after every submap_size additions past the first a new submap is cut from them: transformed,
+// concatenated, voxel-filtered at 0.2 (this one is: :363-367) and gridded for NDT.  The GTSAM factors of the function
+// stay out of scope.
+bool mapOptimization::addNewPrior() {
+    PriorSession& ps = prior_;
+    const PointTypePose cur{transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5], (float)ps.KeyPoses6D.size(),
+                            transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2], timeLaserInfoCur};
+    auto append = [&]() -> bool {
+        const int id = (int)ps.KeyPoses6D.size();
+        if (liloc_keyframe_put_from_raw_scan(ctx_, kPriorKeyframeBase + id) < 0) { error_ = liloc_last_error(ctx_); return false; }
+        ps.KeyPoses6D.push_back(cur);
+        ps.increNodePtIds.push_back(id);
+        ++ps.count;
+        ps.first_add = false;
+        ps.lastPose = cur;
+        rep_.prior_added = id;
+        return true;
+    };
+    if (ps.first_add) return append();
+    const Affine3f transStart = getTransformation(ps.lastPose.x, ps.lastPose.y, ps.lastPose.z, ps.lastPose.roll, ps.lastPose.pitch, ps.lastPose.yaw);
+    const Affine3f transBetween = transStart.inverse() * trans2Affine3f(transformTobeMapped);
+    float x, y, z, roll, pitch, yaw;
+    getTranslationAndEulerAngles(transBetween, x, y, z, roll, pitch, yaw);
+    if (std::abs(roll) < surroundingkeyframeAddingAngleThreshold && std::abs(pitch) < surroundingkeyframeAddingAngleThreshold &&
+        std::abs(yaw) < surroundingkeyframeAddingAngleThreshold && std::sqrt(x * x + y * y + z * z) < surroundingkeyframeAddingDistThreshold)
+        return true;
+    if (!append()) return false;
+    if (ps.count % ps.submap_size == 0) {                                        // :341-377
+        std::vector<int> ids, vertexes; std::vector<float> poses;
+        float xx = 0.f, xy = 0.f, xz = 0.f;
+        for (int i = ps.end; i < (int)ps.KeyPoses6D.size(); ++i) {
+            const PointTypePose& p = ps.KeyPoses6D[i];
+            ids.push_back(kPriorKeyframeBase + i); vertexes.push_back(i);
+            const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+            poses.insert(poses.end(), pose6, pose6 + 6);
+            xx += p.x; xy += p.y; xz += p.z;
+        }
+        const int sid = (int)ps.SubMapCenteriod.size();
+        int leaves = 0, pts = 0;
+        if (liloc_ndt_target_put_keyframes_filtered(ctx_, sid, ids.data(), poses.data(), (int)ids.size(), 0.2f, ndtResolution, &leaves, &pts) < 0) {
+            error_ = liloc_last_error(ctx_); return false;
+        }
+        const float n = (float)ps.submap_size;                                   // divided by submap_size, not by the count (:355-358)
+        ps.SubMapCenteriod.push_back(PointType{xx / n, xy / n, xz / n, (float)sid});
+        ps.submap_first.push_back(ps.end); ps.submap_count.push_back((int)ids.size()); ps.submap_points.push_back(pts);
+        ps.submap_vertexes.push_back(vertexes);
+        ps.end = (int)ps.KeyPoses6D.size();
+        ps.count = 0;
+        rep_.prior_new_submap = sid;
+    }
+    return true;
 }
 
 // registration->setInputTarget(submap) / setInputSource(laserCloudSurfLast) / align x n_align / getFinalTransformation
@@ -563,7 +630,13 @@ void mapOptimization::saveRELOKeyFramesAndFactor() {
         const int submap = searchNearestSubMap(transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
         const std::vector<int> vertexes = searchVertexes(submap, transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
         rep_.relo_n_vertices = (int)vertexes.size();
-        if (vertexes.size() > 1) {                 // `usingVertexes_->size() <= 1` => addNewPrior() instead of matching (:387-390)
+        if (vertexes.size() <= 1) {                // `usingVertexes_->size() <= 1` => addNewPrior() instead of matching (:387-390)
+            if (liloc_ndt_source_put(ctx_, /*source_id=*/0, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device) < 0 || !addNewPrior()) {
+                if (error_.empty()) error_ = liloc_last_error(ctx_);
+                rep_.status = LILOC_ERR_CUDA; return;
+            }
+        } else {
+            prior_.first_add = true;               // :392
             float out6[6]; int it = 0, conv = 0;
             if (ndtAlign(submap, transformTobeMapped, 1, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); rep_.status = LILOC_ERR_CUDA; return; }
             rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
@@ -571,6 +644,9 @@ void mapOptimization::saveRELOKeyFramesAndFactor() {
             // per prior vertex: getICPFitnessScore(its key cloud at its prior pose, the scan at the matched pose), capped
             // at 2 (:427-446).  Both clouds are already on the device.
             for (size_t v = 0; v < vertexes.size(); ++v) {
+                rep_.relo_vertex[v] = vertexes[v];
+                // vertices this session added carry no fitness score (:431-434)
+                if (std::find(prior_.increNodePtIds.begin(), prior_.increNodePtIds.end(), vertexes[v]) != prior_.increNodePtIds.end()) { rep_.relo_fitness[v] = -1.f; continue; }
                 const PointTypePose& p = prior_.KeyPoses6D[vertexes[v]];
                 const float pose_i[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
                 float score = 0.f;
@@ -578,7 +654,7 @@ void mapOptimization::saveRELOKeyFramesAndFactor() {
                     error_ = liloc_last_error(ctx_); rep_.status = LILOC_ERR_CUDA; return;
                 }
                 if (score > 2) score = 2;
-                rep_.relo_vertex[v] = vertexes[v]; rep_.relo_fitness[v] = score;
+                rep_.relo_fitness[v] = score;
             }
         }
     }

@@ -52,6 +52,9 @@ struct FrameReport {                             // what the reference would pub
     int relo_n_vertices = 0;                     // prior vertices within 5 m of the pose (usingVertexes_, at most 3)
     int relo_vertex[3] = {-1, -1, -1};           // their prior keyframe ids
     float relo_fitness[3] = {0, 0, 0};           // getICPFitnessScore of each vertex' key cloud against the matched scan, capped at 2
+                                                 // (-1: a vertex this session added itself, no score, anchorOptimize.hpp:431-434)
+    int prior_added = -1;                        // addNewPrior appended this frame to the prior session under this key-pose id
+    int prior_new_submap = -1;                   // ... and cut this new submap from the last submap_size additions
 };
 
 // What mapOptimization keeps of the prior session (dataManager::Session, include/dataManager/dataLoader.hpp:128-391):
@@ -62,6 +65,15 @@ struct PriorSession {
     std::vector<int> submap_first, submap_count; // keyframe range of each submap
     std::vector<int> submap_points;              // points of each submap cloud
     int submap_size = 10;
+    // ---- growth of the prior map during the session: AnchorOptimization::addNewPrior (anchorOptimize.hpp:272-380) ----
+    int prior_size = 0;                          // key poses of the session as loaded (dataLoader.hpp:186)
+    std::vector<std::vector<int>> submap_vertexes;   // per submap: key-pose ids of ITS vertex cloud; empty = the loader's shared cloud
+                                                     // (every loaded submap sees all prior_size loaded key poses, dataLoader.hpp:311-325)
+    bool first_add = true;                       // member first_add (:51): the next addNewPrior adds unconditionally
+    PointTypePose lastPose{};                    // static lastPose of addNewPrior
+    int end = 0;                                 // static end: first key pose of the submap being collected
+    int count = 0;                               // static count: key poses added since the last cut
+    std::vector<int> increNodePtIds;             // key poses added by this session (increNodePtIds_)
 };
 
 class mapOptimization : public ParamServer {
@@ -125,6 +137,8 @@ public:
     bool relocalizeInit();                                                      // :261-305
     void saveRELOKeyFramesAndFactor();                                          // :1336-1389 (+ anchorOptimize.hpp:382-407)
     const PriorSession& prior() const { return prior_; }
+    // AnchorOptimization::addNewPrior, cloud side (anchorOptimize.hpp:272-380): the current frame joins the prior map
+    bool addNewPrior();
     static constexpr int kPriorKeyframeBase = 1 << 24;                          // device keyframe ids of the prior session
 
     Affine3f trans2Affine3f(const float t[6]) { return getTransformation(t[3], t[4], t[5], t[0], t[1], t[2]); }   // :404-406

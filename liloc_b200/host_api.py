@@ -27,7 +27,8 @@ class Report(C.Structure):
                 ("q_all", C.c_int), ("map_points", C.c_int), ("n_raw", C.c_int), ("n_selected_keyframes", C.c_int),
                 ("keyframe_id", C.c_int), ("reg_ms", C.c_double),
                 ("relo_initialized", C.c_int), ("relo_submap", C.c_int), ("relo_iterations", C.c_int), ("relo_converged", C.c_int),
-                ("relo_pose", C.c_float * 6), ("relo_n_vertices", C.c_int), ("relo_vertex", C.c_int * 3), ("relo_fitness", C.c_float * 3)]
+                ("relo_pose", C.c_float * 6), ("relo_n_vertices", C.c_int), ("relo_vertex", C.c_int * 3), ("relo_fitness", C.c_float * 3),
+                ("prior_added", C.c_int), ("prior_new_submap", C.c_int)]
 
 
 def _load():
@@ -108,6 +109,7 @@ def _load():
 
 
 _lib = None
+PRIOR_KEYFRAME_BASE = 1 << 24      # mapOptimization::kPriorKeyframeBase: device keyframe ids of the prior session's key clouds
 
 
 def euler_to_matrix(pose6) -> np.ndarray:

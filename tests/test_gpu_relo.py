@@ -172,3 +172,140 @@ def test_session_round_trip_lio_save_then_relocalise(tmp_path, orc, synth):
 
 
 import os  # noqa: E402
+
+
+class _PriorModel:
+    """Reference model of the cloud side of AnchorOptimization::addScanMatchingFactor / addNewPrior and of
+    Session::searchNearestSubMapAndVertex (include/egoOptimization/anchorOptimize.hpp:272-421, include/dataManager/
+    dataLoader.hpp:350-390), written from those lines: which prior vertices a frame finds, when the frame joins the prior
+    session instead of being matched, and when a new submap is cut."""
+
+    def __init__(self, orc, prior_traj32, add_angle, add_dist, submap_size=10):
+        self.orc, self.add_angle, self.add_dist, self.submap_size = orc, add_angle, add_dist, submap_size
+        self.poses = [p.copy() for p in prior_traj32]          # KeyPoses6D_ as [roll, pitch, yaw, x, y, z]
+        self.prior_size = len(self.poses)
+        n_sub = (self.prior_size + submap_size - 1) // submap_size
+        self.vertexes = [None] * n_sub                         # None: the loader's shared vertex cloud (all loaded key poses)
+        self.first_add, self.last_pose, self.end, self.count, self.added = True, None, self.prior_size, 0, []
+
+    def search_vertexes(self, submap, pose):
+        ids = range(self.prior_size) if self.vertexes[submap] is None else self.vertexes[submap]
+        q = pose[3:].astype(np.float32)
+        hits = []
+        for i in ids:
+            d = self.poses[i][3:].astype(np.float32) - q
+            d2 = np.float32(np.float32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+            if d2 < np.float32(25.0):
+                hits.append((d2, i))
+        hits.sort()
+        cur_new, out = len(self.poses), []
+        for _, i in hits:
+            if i > self.prior_size and abs(cur_new - i) <= 10:
+                continue
+            if len(out) == 3:
+                break
+            out.append(i)
+        return out
+
+    def add_new_prior(self, pose):
+        """Returns (added id or -1, ids of a newly cut submap or None)."""
+        if not self.first_add and not self.orc.save_frame(self.last_pose, pose, self.add_angle, self.add_dist):
+            return -1, None
+        was_first = self.first_add
+        i = len(self.poses)
+        self.poses.append(pose.copy()); self.added.append(i); self.count += 1
+        self.first_add, self.last_pose = False, pose.copy()
+        if not was_first and self.count % self.submap_size == 0:
+            ids = list(range(self.end, len(self.poses)))
+            self.vertexes.append(ids)
+            self.end, self.count = len(self.poses), 0
+            return i, ids
+        return i, None
+
+
+def test_prior_map_grows_where_the_session_leaves_it(orc, synth):
+    """addScanMatchingFactor with fewer than two prior vertices in reach calls addNewPrior (anchorOptimize.hpp:387-390): the
+    session drives out of the prior map, its frames (pose + FULL scan) join the prior session, after ten additions past the
+    first a new, voxel-filtered submap is cut on the device, and the frames after that are matched against it.  Checked
+    frame by frame against a model of those reference lines and against the oracle (submap grid bit for bit, NDT poses)."""
+    from liloc_b200 import abi, host_api
+    world = synth.make_world(size_xy=(90.0, 70.0), n_pillars=24, seed=21)
+    world[:, [2, 5]] -= 1.8
+    n_prior = 20
+    prior_traj = synth.trajectory_line(n_prior, step=1.0, x0=-10, height=0.0)
+    prior_clouds = [synth.scan(world, prior_traj[k], synth.VLP16, 2100 + k) for k in range(n_prior)]
+    keyposes7 = np.c_[prior_traj, 50.0 + np.arange(n_prior)]
+    # the session starts at prior keyframe 9, drives off sideways (+y) 1.25 m per frame out of the prior map, turns round and
+    # comes back next to its own track: by then the vertices it added on the way out are more than ten additions old (the
+    # reference skips younger ones, dataLoader.hpp:376-380) and the new submap is what it gets matched against
+    n_out, n_back = 17, 10
+    cur = np.repeat(prior_traj[9:10], 3 + n_out + n_back, axis=0)
+    cur[3:3 + n_out, 4] += 1.25 * (1 + np.arange(n_out))
+    cur[3 + n_out:, 4] += 1.25 * (n_out - 1 - np.arange(n_back))
+    cur[3 + n_out:, 3] += 0.4
+    cur[:, 2] += 0.01
+    scans = [synth.scan(world, cur[k], synth.VLP16, 8800 + k) for k in range(len(cur))]
+    with host_api.MapOptimization("lio_sam_default.yaml", "relo", device=0) as m:
+        res, eps = np.float32(m.param("ndtResolution")), np.float32(m.param("ndtEpsilon"))
+        model = _PriorModel(orc, prior_traj.astype(np.float32), np.float32(m.param("surroundingkeyframeAddingAngleThreshold")),
+                            np.float32(m.param("surroundingkeyframeAddingDistThreshold")))
+        assert m.load_prior_session(keyposes7, prior_clouds) == 2
+        ctx = abi.Context.borrow(m.ctx_handle(), 0)
+        m.initialpose(cur[0][3] + 0.2, cur[0][4] - 0.1, cur[0][2] + 0.02)
+        infos = host_api.make_infos(scans, cur.astype(np.float32), 700.0 + 0.25 * np.arange(len(cur)))
+        o = orc.NdtOpts(resolution=float(res), trans_eps=float(eps), search=0, threads=8)
+        added, new_submaps, matched_new = [], [], 0
+        key_clouds = {i: prior_clouds[i] for i in range(n_prior)}
+        for f in range(len(cur)):
+            rep = m.handle(infos[f])
+            assert rep.processed == 1 and rep.status == 0, (f, rep.status)
+            if f == 0:
+                assert rep.relo_initialized == 1
+                continue
+            pose = np.array(rep.pose, np.float32)
+            n_sub = len(model.vertexes)
+            cents = np.array([m.submap_info(s)["centroid"] for s in range(n_sub)])
+            sid = int(np.argmin(((cents - pose[3:]) ** 2).sum(1)))
+            want = model.search_vertexes(sid, pose)
+            assert rep.relo_n_vertices == len(want) and list(rep.relo_vertex)[: len(want)] == want, (f, want, list(rep.relo_vertex))
+            if len(want) <= 1:
+                aid, cut = model.add_new_prior(pose)
+                assert rep.prior_added == aid, (f, rep.prior_added, aid)
+                if aid >= 0:
+                    added.append(aid); key_clouds[aid] = scans[f]
+                    assert ctx.keyframe_size(host_api.PRIOR_KEYFRAME_BASE + aid) == len(scans[f])
+                if cut is not None:
+                    new_sid = len(model.vertexes) - 1
+                    assert rep.prior_new_submap == new_sid
+                    new_submaps.append(new_sid)
+                    # the new submap: transform + concatenate + VoxelGrid(0.2) (:341-367), then the NDT grid -- bit for bit
+                    sub = orc.voxelgrid(np.concatenate([orc.transform_cloud(key_clouds[i], model.poses[i], threads=8) for i in cut]), 0.2)
+                    info = m.submap_info(new_sid)
+                    assert (info["first"], info["count"], info["points"]) == (cut[0], len(cut), len(sub))
+                    acc = np.zeros(3, np.float32)                                        # centroid: float sums / submap_size (:355-358)
+                    for i in cut:
+                        acc = (acc + model.poses[i][3:].astype(np.float32)).astype(np.float32)
+                    assert np.array_equal(info["centroid"], (acc / np.float32(10)).astype(np.float32))
+                    means, icovs, counts, keys = ctx.ndt_target_get(new_sid)
+                    rm, ri, rc = orc.NdtTarget(sub, res).leaves()
+                    assert np.array_equal(means, rm) and np.array_equal(icovs, ri) and np.array_equal(counts, rc)
+                else:
+                    assert rep.prior_new_submap == -1
+            else:
+                model.first_add = True
+                assert rep.prior_added == -1 and rep.relo_submap == sid
+                ids = range(10 * sid, min(10 * sid + 10, n_prior)) if model.vertexes[sid] is None else model.vertexes[sid]
+                sub = np.concatenate([orc.transform_cloud(key_clouds[i], model.poses[i], threads=8) for i in ids])
+                if model.vertexes[sid] is not None:
+                    sub = orc.voxelgrid(sub, 0.2); matched_new += 1
+                Tm, rr = orc.ndt_align(orc.NdtTarget(sub, res), scans[f], _guess_matrix(synth, pose), o)
+                got = np.array(rep.relo_pose, np.float32)
+                assert rep.relo_iterations == rr.iterations and rep.relo_converged == rr.converged
+                assert np.abs(got[3:] - Tm[:, 3]).max() <= 1e-4 and np.abs(synth.rot_zyx(*[float(v) for v in got[:3]]) - Tm[:, :3]).max() <= 1e-5
+                for v, vid in enumerate(want):                       # vertices this session added carry no fitness score (:431-434)
+                    if vid in model.added:
+                        assert rep.relo_fitness[v] == -1.0
+                    else:
+                        wf = orc.icp_fitness(key_clouds[vid], model.poses[vid], scans[f], got, threads=8)
+                        assert rep.relo_fitness[v] == np.float32(min(wf, 2.0))
+        assert len(added) >= 11 and len(new_submaps) >= 1 and matched_new >= 2, (added, new_submaps, matched_new)

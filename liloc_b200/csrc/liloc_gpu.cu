@@ -130,6 +130,7 @@ struct liloc_ctx {
     int max_cells = 1 << 24;
     long long sort_redos = 0;
     bool wide_maps = true;               // local-map launch with two blocks per SM (LILOC_PIPE_NARROW=1 in the environment: one)
+    long long wide_min = 100000;         // ... for local maps above this many raw points (LILOC_PIPE_WIDE_MIN in the environment)
     bool map_cache = false;              // liloc_config.map_cache
     long long map_cache_hits = 0;
     struct MapKey { std::vector<int> ids; std::vector<float> poses; float leaf = 0.f; bool valid = false; } map_key[kClasses];
@@ -336,7 +337,7 @@ int prob_voxelgrid(liloc_ctx* ctx, VgInst& vi, const float4* d_pts, int n, float
     if ((rc = ensure(ctx, vi.keys_b, cap))) return rc;
     if ((rc = ensure(ctx, vi.vals_a, cap))) return rc;
     if ((rc = ensure(ctx, vi.vals_b, cap))) return rc;
-    if ((rc = ensure(ctx, vi.hist, (size_t)3 * kHistStride))) return rc;
+    if ((rc = ensure(ctx, vi.hist, (size_t)kHistInts))) return rc;
     if ((rc = ensure_zeroed(ctx, vi.tile_state, (size_t)(n / kRunTile) + 2))) return rc;
     *q = VgProb{};
     q->pts = d_pts; q->n = n; q->leaf = leaf;
@@ -601,6 +602,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     c->map_cache = cfg->map_cache != 0;
     { const char* e = getenv("LILOC_PIPE_NARROW"); c->wide_maps = !(e && e[0] == '1'); }
     { const char* e = getenv("LILOC_NO_POLL"); c->poll_result = !(e && e[0] == '1'); }
+    { const char* e = getenv("LILOC_PIPE_WIDE_MIN"); if (e && *e) c->wide_min = atoll(e); }
     ctx = c;
     auto bail = [&](int rc) { g_create_error = c->err; liloc_destroy(c); return rc; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
@@ -1142,7 +1144,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     }
     // measured (profiles/frame_latency_r01.md): two blocks per SM pay off for the streaming phases above ~1.5 M raw
     // points (Mid-360 map: 394 -> 332 us); below that one block per SM is as fast or faster (centroid gathers)
-    const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > 1500000;
+    const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > ctx->wide_min;
     const bool map_launched = pm.n_prob > 0;
     if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks_host : nullptr, wide))) return rc;
     // The scan launch is issued AFTER the map launch: its upload was enqueued first (above) and takes longer than the host
@@ -1394,7 +1396,7 @@ int liloc_globalmap_build(liloc_ctx* ctx, const int* kf_ids, const float* poses6
     if ((rc = prob_voxelgrid(ctx, ax.vg_map, ax.raw.p, (int)total, leaf, &ax.map, &q))) return rc;
     q.arena = ctx->arena.p; q.descs = ax.descs.p; q.K = total > 0 ? K : 0; q.raw = ax.raw.p;
     pa.n_prob = 1;
-    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr, total > 1500000))) return rc;
+    if ((rc = pipe_launch(ctx, ctx->stream, pa, nullptr, ctx->wide_maps && total > ctx->wide_min))) return rc;
     int m = 0;
     CU(cudaMemcpyAsync(&m, ax.vg_map.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -31,10 +31,13 @@ namespace liloc {
 namespace cg = cooperative_groups;
 
 constexpr int kPipeThreads = 256;
-constexpr int kSortBlocksMax = 148;                       // blocks that take part in the sort (one per SM)
+constexpr int kSortBlocksMax = 296;                       // blocks that can take part in the sort (every block of a two-per-SM launch)
+constexpr int kSortBlocksSmall = 148;                     // ... below kSortTwoLevelMin items: one block per SM
+constexpr int kSortTwoLevelMin = 1200000;                 // items from which the sort runs on every block with two-level offsets
 constexpr int kSortRounds = 4;
 constexpr int kSortTile = kPipeThreads * kSortRounds;     // 1024 items
 constexpr int kHistStride = kSortBlocksMax * 256;         // ints per histogram buffer (three rotate)
+constexpr int kHistInts = 3 * kHistStride + 256;          // + the digit totals of the pass being scattered
 constexpr int kMaxProbs = 4;
 
 struct VgProb {
@@ -51,7 +54,7 @@ struct VgProb {
     // scratch
     unsigned* keys[2];
     unsigned* vals[2];
-    int* hist;                 // 3 * kHistStride
+    int* hist;                 // kHistInts: 3 rotating block-histogram buffers + 256 digit totals
     unsigned long long* tile_state;   // ceil(n / kRunTile) + 1 look-back words (epoch << 32 | run heads of the tile)
     unsigned* enc;             // 6 ordered-uint min / max; re-armed by the kernel for the next launch
     VgParams* vp;              // out (diagnostics; the bounding box)
@@ -185,9 +188,15 @@ LILOC_DEV int pipe_lookback(unsigned long long* state, int tile, int total, unsi
     return block_sum_256(part);
 }
 
-// The sort runs on at most one block per SM (more blocks only add histogram rows for every block to read).  With two
-// blocks per SM resident, WHICH blocks sort is decided at run time: the first block to arrive on an SM takes a sort
-// index (s_sort_idx), the others get -1; s_nsort = number of sorting blocks.
+// Two ways to get a block's digit offsets, chosen per launch from the problem sizes (uniform over the grid):
+//  * small sorts (< kSortTwoLevelMin items): at most one sorting block per SM, and every sorting block reads every busy
+//    block's histogram row (O(nb^2) L2 reads: 3.5 us per pass at 107 blocks) -- no extra phase, no extra barrier.  With two
+//    blocks per SM resident, WHICH blocks sort is decided at run time: the first block to arrive on an SM takes a sort index.
+//  * large sorts: every block sorts (half the tiles per block and pass); the row reads would double with the blocks, so the
+//    offsets are computed ONCE per pass by a phase of their own (pipe_sort_offsets: one warp per digit scans that digit's
+//    column over the blocks, in place) for one more grid barrier per pass.  Measured (profiles/frame_latency_r02.md): the
+//    2.3 M-point Mid-360 map sorts in 148 us instead of 182 us; at 219 k / 836 k points the extra barriers cost more than
+//    the shorter scatter saves (49 vs 39 us, 78 vs 74 us), hence the threshold.
 struct SortGeom { int C, nb; };                            // items per sorting block (whole tiles), busy sort blocks
 LILOC_DEV SortGeom sort_geom(int n, int nsort) {
     SortGeom g;
@@ -311,8 +320,35 @@ LILOC_DEV void pipe_keys(const VgProb& q, const VgParams& vp, int npass, PipeSme
     __syncthreads();
 }
 
-// ---- one radix pass: offsets, stable in-tile ranking, scatter, next histogram --------------------------------------
-LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm, const int sidx, const int nsort) {
+// ---- digit offsets of a pass: per digit, the exclusive prefix of its counts over the blocks (in place) and its total --------
+// One warp per digit; all loads of a lane are issued before the scan (a dependent loop would pay an L2 round trip per 32 blocks).
+LILOC_DEV void pipe_sort_offsets(const VgProb& q, int pass, const int nsort) {
+    const SortGeom g = sort_geom(prob_n(q), nsort);
+    int* __restrict__ hcur = q.hist + (pass % 3) * kHistStride;
+    int* __restrict__ tot = q.hist + 3 * kHistStride;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * (kPipeThreads / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (kPipeThreads / 32);
+    constexpr int kTrips = (kSortBlocksMax + 31) / 32;
+    for (int d = gwarp; d < 256; d += nwarps) {
+        int v[kTrips];
+#pragma unroll
+        for (int u = 0; u < kTrips; ++u) { const int b = u * 32 + lane; v[u] = b < g.nb ? __ldcg(&hcur[b * 256 + d]) : 0; }
+        int run = 0;
+#pragma unroll
+        for (int u = 0; u < kTrips; ++u) {
+            int inc = v[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int b = u * 32 + lane;
+            if (b < g.nb) hcur[b * 256 + d] = run + inc - v[u];
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) tot[d] = run;
+    }
+}
+
+// ---- one radix pass: stable in-tile ranking, scatter, next histogram ------------------------------------------------
+LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm, const int sidx, const int nsort, const bool two_level) {
     const SortGeom g = sort_geom(prob_n(q), nsort);
     if (sidx < 0 || sidx >= g.nb) return;
     const int src = (npass + 1 + pass) & 1, dst = src ^ 1;
@@ -326,7 +362,15 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
     const int shift = pass * 8;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // digit offsets of this block: all lower digits of every block + this digit of the blocks before
-    {
+    if (two_level) {        // scan of the digit totals + this block's row, turned into exclusive prefixes by pipe_sort_offsets
+        const int tot = __ldcg(&q.hist[3 * kHistStride + t]);
+        const int pre = __ldcg(&hcur[sidx * 256 + t]);
+        int total;
+        const int excl = block_exclusive_scan_256(tot, &total);
+        sm.sort.offs[t] = excl + pre;
+#pragma unroll
+        for (int u = 0; u < kSortUnits; ++u) sm.sort.cnt[u][t] = 0;
+    } else {
         int pre = 0, tot = 0;
 #pragma unroll 1
         for (int b = 0; b < g.nb; b += 16) {                    // 16 independent (predicated) loads in flight per thread:
@@ -574,12 +618,19 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     __shared__ int s_npass[kMaxProbs];
     const int np = a.n_prob;
     __shared__ int s_sort_idx, s_nsort;
-    if (threadIdx.x == 0) {                      // the first block to arrive on an SM becomes that SM's sorting block
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        const int slot = atomicAdd(&a.sm_scratch[smid & 511u], 1);
+    // sort mode of the launch (uniform over the grid: problem sizes and the grid size only)
+    bool two_level = false;
+    for (int p = 0; p < np; ++p) two_level |= a.prob[p].n >= kSortTwoLevelMin && !a.prob[p].grid_only;
+    if (threadIdx.x == 0) {
         int idx = -1;
-        if (slot == 0) { idx = atomicAdd(&a.sm_scratch[512], 1); if (idx >= kSortBlocksMax) idx = -1; }
+        if (two_level) {
+            idx = (int)blockIdx.x < kSortBlocksMax ? (int)blockIdx.x : -1;
+        } else {                                 // the first block to arrive on an SM becomes that SM's sorting block
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int slot = atomicAdd(&a.sm_scratch[smid & 511u], 1);
+            if (slot == 0) { idx = atomicAdd(&a.sm_scratch[512], 1); if (idx >= kSortBlocksSmall) idx = -1; }
+        }
         s_sort_idx = idx;
     }
     int mark = 0;
@@ -598,7 +649,6 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
         return;
     }
 
-    if (threadIdx.x == 0) s_nsort = min(__ldcg(&a.sm_scratch[512]), kSortBlocksMax);
     if (threadIdx.x < np) {                                                               // P1
         const VgProb& q = a.prob[threadIdx.x];
         const VgParams vp = vg_params_compute(q.enc, q.leaf, prob_n(q));
@@ -612,14 +662,20 @@ __global__ void __launch_bounds__(kPipeThreads, 3) k_voxel_pipeline(const __grid
     __syncthreads();
     int max_pass = 0;
     for (int p = 0; p < np; ++p) max_pass = max(max_pass, s_npass[p]);
+    if (threadIdx.x == 0) s_nsort = two_level ? min((int)gridDim.x, kSortBlocksMax) : min(__ldcg(&a.sm_scratch[512]), kSortBlocksSmall);
+    __syncthreads();
     const int sidx = s_sort_idx, nsort = s_nsort;
     for (int p = 0; p < np; ++p) if (prob_n(a.prob[p]) > 0 && !a.prob[p].grid_only) pipe_keys(a.prob[p], s_vp[p], s_npass[p], sm, sidx, nsort);
     grid.sync();
-    if (blockIdx.x == 0) for (int i = threadIdx.x; i < kSmScratch; i += kPipeThreads) a.sm_scratch[i] = 0;   // re-armed for the next launch
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < kSmAbort; i += kPipeThreads) a.sm_scratch[i] = 0;   // re-armed for the next launch
     PIPE_MARK();                                                                          // 2 after keys
 
-    for (int pass = 0; pass < max_pass; ++pass) {                                         // radix passes
-        for (int p = 0; p < np; ++p) if (pass < s_npass[p]) pipe_sort_pass(a.prob[p], s_npass[p], pass, sm, sidx, nsort);
+    for (int pass = 0; pass < max_pass; ++pass) {                                         // radix passes: (digit offsets,) rank + scatter
+        if (two_level) {
+            for (int p = 0; p < np; ++p) if (pass < s_npass[p]) pipe_sort_offsets(a.prob[p], pass, nsort);
+            grid.sync();
+        }
+        for (int p = 0; p < np; ++p) if (pass < s_npass[p]) pipe_sort_pass(a.prob[p], s_npass[p], pass, sm, sidx, nsort, two_level);
         grid.sync();
     }
     if (blockIdx.x == 0 && threadIdx.x < 6 * np) {                                        // re-arm the bounding boxes

@@ -630,6 +630,7 @@ void mapOptimization::saveRELOKeyFramesAndFactor() {
         const int submap = searchNearestSubMap(transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
         const std::vector<int> vertexes = searchVertexes(submap, transformTobeMapped[3], transformTobeMapped[4], transformTobeMapped[5]);
         rep_.relo_n_vertices = (int)vertexes.size();
+        for (size_t v = 0; v < vertexes.size(); ++v) rep_.relo_vertex[v] = vertexes[v];
         if (vertexes.size() <= 1) {                // `usingVertexes_->size() <= 1` => addNewPrior() instead of matching (:387-390)
             if (liloc_ndt_source_put(ctx_, /*source_id=*/0, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device) < 0 || !addNewPrior()) {
                 if (error_.empty()) error_ = liloc_last_error(ctx_);

@@ -174,6 +174,7 @@ struct liloc_ctx {
     DevBuf<float> ndt_rows;              // packed results {pose6, score / n, iterations} of the last batch, 8 floats per job
     unsigned long long* d_ndt_prof = nullptr;   // 8 words (ndt.cuh NdtAlignArgs::prof)
     int ndt_max_blocks = 0;
+    int ndt_grain_div = 2;               // tickets aimed at per block (LILOC_NDT_GRAIN_DIV in the environment: diagnostics)
 
     // multi-GPU: one communicator per context (one context per GPU / process); the only collective is the all-gather of
     // packed result rows
@@ -603,6 +604,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     { const char* e = getenv("LILOC_PIPE_NARROW"); c->wide_maps = !(e && e[0] == '1'); }
     { const char* e = getenv("LILOC_NO_POLL"); c->poll_result = !(e && e[0] == '1'); }
     { const char* e = getenv("LILOC_PIPE_WIDE_MIN"); if (e && *e) c->wide_min = atoll(e); }
+    { const char* e = getenv("LILOC_NDT_GRAIN_DIV"); if (e && *e && atoi(e) > 0) c->ndt_grain_div = atoi(e); }
     ctx = c;
     auto bail = [&](int rc) { g_create_error = c->err; liloc_destroy(c); return rc; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, LILOC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(LILOC_ERR_CUDA); } } while (0)
@@ -1719,6 +1721,7 @@ static int ndt_run_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, 
     aa.q.ring = ctx->ndt_q.p + 4; aa.q.mask = (unsigned)(cap - 1);
     aa.rows = ctx->ndt_rows.p;
     aa.prof = ctx->timing ? ctx->d_ndt_prof : nullptr;
+    aa.grain_div = ctx->ndt_grain_div;
     k_ndt_align<<<(unsigned)blocks, kNdtThreads, 0, ctx->stream>>>(aa); KCHECK();
     unsigned long long h_q[4] = {0, 0, 0, 0}, h_prof[16] = {0};
     CU(cudaMemcpyAsync(h_q, ctx->ndt_q.p, sizeof(h_q), cudaMemcpyDeviceToHost, ctx->stream));

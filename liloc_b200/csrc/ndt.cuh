@@ -785,6 +785,7 @@ struct NdtAlignArgs {
     NdtSync* sync;                 // [n_jobs]
     NdtQueue q;
     float* rows;                   // [n_jobs][8] packed results {roll, pitch, yaw, x, y, z, score / n, iterations} or nullptr
+    int grain_div;                 // tickets aimed at per block over the unfinished jobs (ndt_grain_for)
     unsigned long long* prof;      // optional: [0] first block start, [1] last block end (globaltimer ns), [2] sum over blocks of
                                    // sweep time, [3] update time, [4] time waiting for a ticket, [5] tickets, [6] updates,
                                    // [8..11] SM cycles inside the updates: reduce + load, state machine, pose tables, store + publish
@@ -812,10 +813,10 @@ LILOC_DEV void ndt_publish(const NdtAlignArgs& a, int job, int n_tiles, int grai
 
 // Tiles per ticket.  A ticket costs a claim, a 416-byte descriptor load and an arrival (~2-3 us) on top of its tiles
 // (~3.7 us each), so tickets should be long -- but a sweep cut into few tickets cannot spread over idle blocks, and the
-// longest job's chain of sweeps is what a small batch waits for.  Aim at ~4 tickets in flight per block over the
+// longest job's chain of sweeps is what a small batch waits for.  Aim at ~`div` tickets in flight per block over the
 // unfinished jobs: whole sweeps while jobs are plentiful, single tiles once fewer jobs than blocks remain.
-LILOC_DEV int ndt_grain_for(int active_jobs, int n_tiles, int grid) {
-    long long g = ((long long)active_jobs * n_tiles) / (4ll * grid);
+LILOC_DEV int ndt_grain_for(int active_jobs, int n_tiles, int grid, int div) {
+    long long g = ((long long)active_jobs * n_tiles) / ((long long)div * grid);
     if (g < 1) g = 1;
     if (g > n_tiles) g = n_tiles;
     return (int)g;
@@ -897,7 +898,7 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
 #pragma unroll
         for (int i = 0; i < 6; ++i) xt[i] = L.x_t[i];
         if (go) {                                         // ticket numbers and granularity of the next sweep: reserved now, the
-            grain = ndt_grain_for(a.n_jobs - finished, n_tiles, (int)gridDim.x);      // round trip of the atomic overlaps the pose tables and the stores
+            grain = ndt_grain_for(a.n_jobs - finished, n_tiles, (int)gridDim.x, a.grain_div);      // round trip of the atomic overlaps the pose tables and the stores
             base = ndt_reserve(a, n_tiles, grain);
         }
     }
@@ -970,7 +971,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
             int grain = 1;
             unsigned base = 0;
             if (lane == 0) {
-                grain = ndt_grain_for(a.n_jobs, n_tiles, (int)gridDim.x);
+                grain = ndt_grain_for(a.n_jobs, n_tiles, (int)gridDim.x, a.grain_div);
                 base = ndt_reserve(a, n_tiles, grain);
                 a.sync[j].done = 0; a.hot[j].grain = grain; a.hot[j].pad = 0;
             }

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -172,7 +173,10 @@ struct liloc_ctx {
     DevBuf<NdtSync> ndt_sync;
     DevBuf<unsigned long long> ndt_q;    // [0..3] head / tail / finished / error words, then the ticket ring
     DevBuf<float> ndt_rows;              // packed results {pose6, score / n, iterations} of the last batch, 8 floats per job
-    unsigned long long* d_ndt_prof = nullptr;   // 8 words (ndt.cuh NdtAlignArgs::prof)
+    unsigned long long* h_ndt_hdr = nullptr;    // pinned copy of the queue header (counters + profile words) of the last batch
+    NdtJob* h_ndt_jobs = nullptr;               // pinned staging of the job records (up and, when asked for, back)
+    size_t h_ndt_jobs_cap = 0;
+    int ndt_pending_jobs = 0, ndt_pending_blocks = 0, ndt_pending_cells = 1;
     int ndt_max_blocks = 0;
     int ndt_grain_div = 2;               // tickets aimed at per block (LILOC_NDT_GRAIN_DIV in the environment: diagnostics)
 
@@ -662,7 +666,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deskew, kDeskewThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_deskew cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->dk_blocks_per_sm = per_sm >= 2 ? 2 : 1;
-    CUB_(cudaMalloc(&c->d_ndt_prof, 16 * sizeof(unsigned long long)));
+    CUB_(cudaMallocHost(&c->h_ndt_hdr, 32 * sizeof(unsigned long long)));
     CUB_(cudaMalloc(&c->d_sm_scratch, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMemset(c->d_sm_scratch, 0, 2 * kSmScratch * sizeof(int)));
     CUB_(cudaMalloc(&c->d_dk_imu, 4 * kImuMax * sizeof(double)));
@@ -726,7 +730,9 @@ void liloc_destroy(liloc_ctx* c) {
     for (auto& kv : c->ndt_sources) fr(kv.second.own.p);
     fr(c->d_tviews.p); fr(c->d_sviews.p); fr(c->d_jobs.p); fr(c->ndt_partial.p); fr(c->d_ndt_active);
     fr(c->ndt_descs.p);
-    fr(c->ndt_hot.p); fr(c->ndt_sync.p); fr(c->ndt_q.p); fr(c->ndt_rows.p); fr(c->d_ndt_prof);
+    fr(c->ndt_hot.p); fr(c->ndt_sync.p); fr(c->ndt_q.p); fr(c->ndt_rows.p);
+    if (c->h_ndt_hdr) cudaFreeHost(c->h_ndt_hdr);
+    if (c->h_ndt_jobs) cudaFreeHost(c->h_ndt_jobs);
     fr(c->gather_send.p); fr(c->gather_recv.p);
     if (c->h_gather) cudaFreeHost(c->h_gather);
     if (c->comm) { nccl().CommDestroy(c->comm); c->comm = nullptr; }
@@ -1669,29 +1675,50 @@ int liloc_ndt_clear(liloc_ctx* ctx) {
     return LILOC_OK;
 }
 
-// One batch of alignments = one launch of the queue-driven persistent kernel (ndt.cuh).  hj: host copies of the job
-// records, filled on return when `fetch_jobs`; the packed 8-float rows stay in ctx->ndt_rows (device) for the gather.
-static int ndt_run_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* o, std::vector<NdtJob>& hj, bool fetch_jobs) {
+// One batch of alignments = one launch of the queue-driven persistent kernel (ndt.cuh), in two halves so that a caller can
+// put the gather between them and synchronise ONCE:
+//   ndt_enqueue_batch  job records up (pinned staging), queue memory cleared, the kernel, the queue header (counters +
+//                      profile words) and -- when `fetch_jobs` -- the job records back into pinned staging; nothing waits
+//   ndt_finish_batch   after the caller synchronised the stream: error words, counters, job records
+// The packed 8-float rows stay in ctx->ndt_rows (device) for the gather.
+constexpr int kNdtHdrWords = 4 + 16;      // head / tail / finished / error, then the 16 profile words; the ticket ring follows
+
+static int ndt_enqueue_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* o, bool fetch_jobs) {
     int rc;
     if ((rc = ndt_sync_views(ctx))) return rc;
     if (n_jobs > kNdtMaxJobs) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_align_batch: more than %d jobs in one batch", kNdtMaxJobs);
-    hj.assign((size_t)n_jobs, NdtJob{});
+    if ((size_t)n_jobs > ctx->h_ndt_jobs_cap) {
+        if (ctx->h_ndt_jobs) { CU(cudaFreeHost(ctx->h_ndt_jobs)); ctx->h_ndt_jobs = nullptr; ctx->h_ndt_jobs_cap = 0; }
+        size_t cap = 256; while (cap < (size_t)n_jobs) cap *= 2;
+        CU(cudaMallocHost(&ctx->h_ndt_jobs, cap * sizeof(NdtJob)));
+        ctx->h_ndt_jobs_cap = cap;
+    }
+    NdtJob* hj = ctx->h_ndt_jobs;
+    std::memset(hj, 0, (size_t)n_jobs * sizeof(NdtJob));
     int max_n = 0;
     long long total_tiles = 0;
     float resolution = -1.f;
+    int last_t = INT_MIN, last_s = INT_MIN;
+    const liloc_ctx::NdtTargetHost* tp = nullptr; const liloc_ctx::NdtSourceHost* sp = nullptr;
     for (int j = 0; j < n_jobs; ++j) {
-        auto ti = ctx->ndt_targets.find(jobs[j].target_id);
-        auto si = ctx->ndt_sources.find(jobs[j].source_id);
-        if (ti == ctx->ndt_targets.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown target id %d", jobs[j].target_id);
-        if (si == ctx->ndt_sources.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown source id %d", jobs[j].source_id);
-        if (!ti->second.view.table) return fail(ctx, LILOC_ERR_STATE, "ndt_align_batch: target id %d was not built", jobs[j].target_id);
-        if (resolution < 0.f) resolution = ti->second.resolution;
-        else if (resolution != ti->second.resolution) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: all targets of one batch must share the resolution");
-        hj[j].target = ti->second.slot; hj[j].source = si->second.slot;
-        hj[j].n_tiles = (si->second.view.n + kNdtTile - 1) / kNdtTile;
+        if (jobs[j].target_id != last_t || !tp) {           // neighbouring jobs mostly share their target / source: one hash look-up per change
+            auto ti = ctx->ndt_targets.find(jobs[j].target_id);
+            if (ti == ctx->ndt_targets.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown target id %d", jobs[j].target_id);
+            tp = &ti->second; last_t = jobs[j].target_id;
+        }
+        if (jobs[j].source_id != last_s || !sp) {
+            auto si = ctx->ndt_sources.find(jobs[j].source_id);
+            if (si == ctx->ndt_sources.end()) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: unknown source id %d", jobs[j].source_id);
+            sp = &si->second; last_s = jobs[j].source_id;
+        }
+        if (!tp->view.table) return fail(ctx, LILOC_ERR_STATE, "ndt_align_batch: target id %d was not built", jobs[j].target_id);
+        if (resolution < 0.f) resolution = tp->resolution;
+        else if (resolution != tp->resolution) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: all targets of one batch must share the resolution");
+        hj[j].target = tp->slot; hj[j].source = sp->slot;
+        hj[j].n_tiles = (sp->view.n + kNdtTile - 1) / kNdtTile;
         if (hj[j].n_tiles > kNdtMaxTilesPerJob) return fail(ctx, LILOC_ERR_CAPACITY, "ndt_align_batch: source %d has more than %d points", jobs[j].source_id, kNdtMaxTilesPerJob * kNdtTile);
         std::memcpy(hj[j].guess, jobs[j].guess, 12 * sizeof(float));     // top 3 rows of the row-major 4x4
-        if (si->second.view.n > max_n) max_n = si->second.view.n;
+        if (sp->view.n > max_n) max_n = sp->view.n;
         total_tiles += hj[j].n_tiles;
     }
     const NdtOptsDev od = ndt_opts_dev(o, resolution);
@@ -1705,65 +1732,56 @@ static int ndt_run_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, 
     if ((rc = ensure(ctx, ctx->ndt_hot, (size_t)n_jobs))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_sync, (size_t)n_jobs))) return rc;
     if ((rc = ensure(ctx, ctx->ndt_rows, (size_t)n_jobs * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->ndt_q, 4 + cap))) return rc;
-    CU(cudaMemcpyAsync(ctx->d_jobs.p, hj.data(), (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ensure(ctx, ctx->ndt_q, kNdtHdrWords + cap))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_jobs.p, hj, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
-    CU(cudaMemsetAsync(ctx->ndt_q.p, 0, (4 + cap) * sizeof(unsigned long long), ctx->stream));     // counters + every ticket tag
-    if (ctx->timing) {
-        CU(cudaMemsetAsync(ctx->d_ndt_prof, 0xFF, sizeof(unsigned long long), ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_ndt_prof + 1, 0, 15 * sizeof(unsigned long long), ctx->stream));
-    }
+    CU(cudaMemsetAsync(ctx->ndt_q.p, 0, (kNdtHdrWords + cap) * sizeof(unsigned long long), ctx->stream));     // counters, profile words, every ticket tag
     NdtAlignArgs aa{};
     aa.jobs = ctx->d_jobs.p; aa.n_jobs = n_jobs; aa.targets = ctx->d_tviews.p; aa.sources = ctx->d_sviews.p; aa.o = od;
     aa.tiles_max = tiles; aa.partial = ctx->ndt_partial.p; aa.hot = ctx->ndt_hot.p; aa.sync = ctx->ndt_sync.p;
     unsigned* qw = reinterpret_cast<unsigned*>(ctx->ndt_q.p);
     aa.q.head = qw; aa.q.tail = qw + 2; aa.q.finished = reinterpret_cast<int*>(qw + 4); aa.q.error = reinterpret_cast<int*>(qw + 6);
-    aa.q.ring = ctx->ndt_q.p + 4; aa.q.mask = (unsigned)(cap - 1);
+    aa.q.ring = ctx->ndt_q.p + kNdtHdrWords; aa.q.mask = (unsigned)(cap - 1);
     aa.rows = ctx->ndt_rows.p;
-    aa.prof = ctx->timing ? ctx->d_ndt_prof : nullptr;
+    aa.prof = ctx->timing ? ctx->ndt_q.p + 4 : nullptr;
     aa.grain_div = ctx->ndt_grain_div;
     k_ndt_align<<<(unsigned)blocks, kNdtThreads, 0, ctx->stream>>>(aa); KCHECK();
-    unsigned long long h_q[4] = {0, 0, 0, 0}, h_prof[16] = {0};
-    CU(cudaMemcpyAsync(h_q, ctx->ndt_q.p, sizeof(h_q), cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->timing) CU(cudaMemcpyAsync(h_prof, ctx->d_ndt_prof, sizeof(h_prof), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_ndt_hdr, ctx->ndt_q.p, kNdtHdrWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     if (fetch_jobs) {
-        CU(cudaMemcpyAsync(hj.data(), ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(hj, ctx->d_jobs.p, (size_t)n_jobs * sizeof(NdtJob), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += (long long)n_jobs * (long long)sizeof(NdtJob);
     }
-    CU(cudaStreamSynchronize(ctx->stream));
-    if ((int)(h_q[3] & 0xFFFFFFFFu) != 0) return fail(ctx, LILOC_ERR_CUDA, "ndt_align_batch: a block gave up waiting for a ticket (queue stalled)");
-    if ((int)(h_q[2] & 0xFFFFFFFFu) != n_jobs) return fail(ctx, LILOC_ERR_CUDA, "ndt_align_batch: %d of %d jobs retired", (int)(h_q[2] & 0xFFFFFFFFu), n_jobs);
-    {
-        liloc_ndt_stats& ns = ctx->ndt_stats;
-        ns.batches += 1; ns.jobs += n_jobs; ns.launches += 1; ns.blocks += blocks;
-        if (ctx->timing) {
-            ns.kernel_ms += h_prof[1] > h_prof[0] ? (double)(h_prof[1] - h_prof[0]) * 1e-6 : 0.0;
-            ns.block_sweep_ms += (double)h_prof[2] * 1e-6; ns.block_update_ms += (double)h_prof[3] * 1e-6; ns.block_wait_ms += (double)h_prof[4] * 1e-6;
-            ns.tickets += (long long)h_prof[5]; ns.updates += (long long)h_prof[6];
-            for (int k = 0; k < 4; ++k) ns.update_cycles[k] += (double)h_prof[8 + k];
-        }
-        if (fetch_jobs) {
-            const int cells = od.search == 2 ? 27 : (od.search == 1 ? 7 : 1);
-            for (int j = 0; j < n_jobs; ++j) {
-                const double P = (double)ctx->ndt_sources[jobs[j].source_id].view.n;
-                ns.job_sweeps += hj[j].total_sweeps;
-                if (hj[j].total_sweeps > ns.max_job_sweeps) ns.max_job_sweeps = hj[j].total_sweeps;
-                // per sweep and job, the scan once (16 P), a (mean, inverse covariance) gather per point and
-                // cell (36 P c) and 28 doubles out
-                ns.alg_bytes += (double)hj[j].total_sweeps * (16.0 * P + 36.0 * P * cells + 224.0);
-            }
-        }
+    ctx->ndt_pending_jobs = n_jobs; ctx->ndt_pending_blocks = (int)blocks;
+    ctx->ndt_pending_cells = od.search == 2 ? 27 : (od.search == 1 ? 7 : 1);
+    return LILOC_OK;
+}
+
+// after the stream was synchronised
+static int ndt_finish_batch(liloc_ctx* ctx) {
+    const unsigned long long* h = ctx->h_ndt_hdr;
+    const int n_jobs = ctx->ndt_pending_jobs;
+    if ((int)(h[3] & 0xFFFFFFFFu) != 0) return fail(ctx, LILOC_ERR_CUDA, "ndt_align_batch: a block gave up waiting for a ticket (queue stalled)");
+    if ((int)(h[2] & 0xFFFFFFFFu) != n_jobs) return fail(ctx, LILOC_ERR_CUDA, "ndt_align_batch: %d of %d jobs retired", (int)(h[2] & 0xFFFFFFFFu), n_jobs);
+    liloc_ndt_stats& ns = ctx->ndt_stats;
+    ns.batches += 1; ns.jobs += n_jobs; ns.launches += 1; ns.blocks += ctx->ndt_pending_blocks;
+    if (ctx->timing) {
+        const unsigned long long* pr = h + 4;
+        const unsigned long long t0 = ~pr[0];
+        ns.kernel_ms += pr[1] > t0 ? (double)(pr[1] - t0) * 1e-6 : 0.0;
+        ns.block_sweep_ms += (double)pr[2] * 1e-6; ns.block_update_ms += (double)pr[3] * 1e-6; ns.block_wait_ms += (double)pr[4] * 1e-6;
+        ns.tickets += (long long)pr[5]; ns.updates += (long long)pr[6];
+        for (int k = 0; k < 4; ++k) ns.update_cycles[k] += (double)pr[8 + k];
+        ns.job_sweeps += (long long)pr[12];
+        if ((long long)pr[13] > ns.max_job_sweeps) ns.max_job_sweeps = (long long)pr[13];
+        // per sweep and job, the scan once (16 P), a (mean, inverse covariance) gather per point and cell (36 P c)
+        // and 28 doubles out; pr[14] = sum over jobs of sweeps x P
+        ns.alg_bytes += (double)pr[14] * (16.0 + 36.0 * ctx->ndt_pending_cells) + (double)pr[12] * 224.0;
     }
     return LILOC_OK;
 }
 
-int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs) {
-    ENTER(ctx);
-    if (n_jobs <= 0 || !jobs || !outs) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: bad arguments");
-    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
-    std::vector<NdtJob> hj;
-    int rc;
-    if ((rc = ndt_run_batch(ctx, jobs, n_jobs, o, hj, true))) return rc;
+static void ndt_fill_outs(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, liloc_ndt_out* outs) {
+    const NdtJob* hj = ctx->h_ndt_jobs;
     for (int j = 0; j < n_jobs; ++j) {
         liloc_ndt_out& r = outs[j];
         std::memcpy(r.T, hj[j].Tfinal, 12 * sizeof(float));
@@ -1771,6 +1789,17 @@ int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs,
         r.score = hj[j].score; r.iterations = hj[j].total_iterations; r.converged = hj[j].converged; r.sweeps = hj[j].total_sweeps;
         r.n_source = ctx->ndt_sources[jobs[j].source_id].view.n;
     }
+}
+
+int liloc_ndt_align_batch(liloc_ctx* ctx, const liloc_ndt_job* jobs, int n_jobs, const liloc_ndt_opts* opts, liloc_ndt_out* outs) {
+    ENTER(ctx);
+    if (n_jobs <= 0 || !jobs || !outs) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch: bad arguments");
+    const liloc_ndt_opts* o = opts ? opts : &kDefaultNdtOpts;
+    int rc;
+    if ((rc = ndt_enqueue_batch(ctx, jobs, n_jobs, o, true))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if ((rc = ndt_finish_batch(ctx))) return rc;
+    ndt_fill_outs(ctx, jobs, n_jobs, outs);
     return LILOC_OK;
 }
 
@@ -1894,21 +1923,16 @@ int liloc_ndt_align_batch_sharded(liloc_ctx* ctx, const liloc_ndt_job* items, in
     for (int i : idx) mine.push_back(items[i]);
     int rc;
     if ((rc = ensure(ctx, ctx->ndt_rows, (size_t)per * 8))) return rc;
-    std::vector<NdtJob> hj;
-    if (!mine.empty()) {
-        if ((rc = ndt_run_batch(ctx, mine.data(), (int)mine.size(), o, hj, local_outs != nullptr || ctx->timing))) return rc;
-        if (local_outs) for (size_t j = 0; j < mine.size(); ++j) {
-            liloc_ndt_out& r = local_outs[j];
-            std::memcpy(r.T, hj[j].Tfinal, 12 * sizeof(float));
-            r.T[12] = 0.f; r.T[13] = 0.f; r.T[14] = 0.f; r.T[15] = 1.f;
-            r.score = hj[j].score; r.iterations = hj[j].total_iterations; r.converged = hj[j].converged; r.sweeps = hj[j].total_sweeps;
-            r.n_source = ctx->ndt_sources[mine[j].source_id].view.n;
-        }
-    }
+    // enqueue everything -- the batch kernel, the padding of a short share, the all-gather, the copies back -- and wait ONCE
+    if (!mine.empty() && (rc = ndt_enqueue_batch(ctx, mine.data(), (int)mine.size(), o, local_outs != nullptr))) return rc;
     if ((int)mine.size() < per)         // pad rows of a short share
         CU(cudaMemsetAsync(ctx->ndt_rows.p + mine.size() * 8, 0, ((size_t)per - mine.size()) * 8 * sizeof(float), ctx->stream));
     std::vector<float> all((size_t)W * per * 8);
-    if ((rc = gather_rows_dev(ctx, ctx->ndt_rows.p, per, all.data()))) return rc;
+    if ((rc = gather_rows_dev(ctx, ctx->ndt_rows.p, per, all.data()))) return rc;          // synchronises the stream
+    if (!mine.empty()) {
+        if ((rc = ndt_finish_batch(ctx))) return rc;
+        if (local_outs) ndt_fill_outs(ctx, mine.data(), (int)mine.size(), local_outs);
+    }
     if (liloc_unshard_rows(all.data(), n_items, W, per, policy, rows_out) != LILOC_OK) return fail(ctx, LILOC_ERR_ARG, "ndt_align_batch_sharded: unshard failed");
     return LILOC_OK;
 }

@@ -786,9 +786,10 @@ struct NdtAlignArgs {
     NdtQueue q;
     float* rows;                   // [n_jobs][8] packed results {roll, pitch, yaw, x, y, z, score / n, iterations} or nullptr
     int grain_div;                 // tickets aimed at per block over the unfinished jobs (ndt_grain_for)
-    unsigned long long* prof;      // optional: [0] first block start, [1] last block end (globaltimer ns), [2] sum over blocks of
+    unsigned long long* prof;      // optional (zeroed by the host): [0] ~(first block start) (complemented: a maximum of a zeroed word), [1] last block end (globaltimer ns), [2] sum over blocks of
                                    // sweep time, [3] update time, [4] time waiting for a ticket, [5] tickets, [6] updates,
-                                   // [8..11] SM cycles inside the updates: reduce + load, state machine, pose tables, store + publish
+                                   // [8..11] SM cycles inside the updates: reduce + load, state machine, pose tables, store + publish,
+                                   // [12] sweeps of all retired jobs, [13] sweeps of the longest job, [14] sum of sweeps x source points
 };
 
 LILOC_DEV unsigned long long ndt_ld_entry(const unsigned long long* p) { return *((const volatile unsigned long long*)p); }
@@ -928,6 +929,10 @@ LILOC_DEV void ndt_job_update(const NdtAlignArgs& a, int job, NdtUpdateShared& u
         ndt_publish(a, job, n_tiles, grain, base);
     } else {
         if (lane == 0 && a.rows) ndt_pack_row(us.job, __ldcg(&vw->n), a.rows + (size_t)job * 8);
+        if (lane == 0 && a.prof) {                        // what the host's counters need of a retired job: no job records travel back for them
+            const unsigned long long sw = (unsigned long long)us.job.total_sweeps;
+            atomicAdd(&a.prof[12], sw); atomicMax(&a.prof[13], sw); atomicAdd(&a.prof[14], sw * (unsigned long long)__ldcg(&vw->n));
+        }
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(a.q.finished, 1);
@@ -947,7 +952,7 @@ __global__ void __launch_bounds__(kNdtThreads, 2) k_ndt_align(NdtAlignArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long t_sweep = 0, t_update = 0, t_wait = 0, n_tick = 0, n_upd = 0, t_begin = 0;
     const bool prof = a.prof != nullptr && threadIdx.x == 0;
-    if (prof) { t_begin = global_ns(); atomicMin(&a.prof[0], t_begin); }
+    if (prof) { t_begin = global_ns(); atomicMax(&a.prof[0], ~t_begin); }
     // ---- prologue: one warp per job -- state, pose tables, view, first tickets.  No barrier: consumers wait on ticket tags.
     {
         const int gwarp = warp * gridDim.x + blockIdx.x, nwarps = (kNdtThreads / 32) * gridDim.x;

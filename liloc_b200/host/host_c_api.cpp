@@ -34,6 +34,7 @@ struct liloc_host_report {               // mirror of liloc_host::FrameReport
     int relo_n_vertices, relo_vertex[3];
     float relo_fitness[3];
     int prior_added, prior_new_submap;
+    int relo_hypothesis; float relo_score;
 };
 
 static thread_local std::string g_err;
@@ -58,6 +59,7 @@ static void to_report(const liloc_host::FrameReport& r, liloc_host_report* o) {
     o->relo_n_vertices = r.relo_n_vertices;
     std::memcpy(o->relo_vertex, r.relo_vertex, sizeof(o->relo_vertex)); std::memcpy(o->relo_fitness, r.relo_fitness, sizeof(o->relo_fitness));
     o->prior_added = r.prior_added; o->prior_new_submap = r.prior_new_submap;
+    o->relo_hypothesis = r.relo_hypothesis; o->relo_score = r.relo_score;
 }
 
 static liloc_host::CloudInfo to_info(const liloc_host_cloud_info& m) {
@@ -127,6 +129,11 @@ int liloc_host_save_g2o(const char* path, const double* keyposes7, int n) {
     return liloc_host::saveSessionGraph(path, kp, e) ? 0 : -1;
 }
 
+void liloc_host_set_relo_hypotheses(void* h, int n_yaw, int n_xy, float radius) { static_cast<mapOptimization*>(h)->setReloHypotheses(n_yaw, n_xy, radius); }
+int liloc_host_comm_init(void* h, int rank, int world, const void* id128) { return static_cast<mapOptimization*>(h)->commInit(rank, world, id128); }
+void liloc_host_hypothesis_pose(const float* center6, int n_yaw, int n_xy, float radius, int hyp, float* out6) {
+    mapOptimization::hypothesisPose(center6, n_yaw, n_xy, radius, hyp, out6);
+}
 void liloc_host_initialpose(void* h, float x, float y, float yaw) { static_cast<mapOptimization*>(h)->initialposeHandler(x, y, yaw); }
 int liloc_host_submap_info(void* h, int s, float* centroid3, int* first, int* count, int* points) {
     const auto& p = static_cast<mapOptimization*>(h)->prior();

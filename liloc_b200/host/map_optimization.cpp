@@ -607,17 +607,64 @@ int mapOptimization::ndtAlign(int submap, const float guess6[6], int n_align, fl
     return 0;
 }
 
+int mapOptimization::commInit(int rank, int world, const void* id128) {
+    if (!ctx_) { error_ = "no device context"; return LILOC_ERR_STATE; }
+    const int rc = liloc_comm_init(ctx_, rank, world, id128);
+    if (rc < 0) error_ = liloc_last_error(ctx_);
+    return rc;
+}
+
+// Hypothesis h of n_yaw * n_xy around `center6`: yaw offset 2 pi (h / n_xy) / n_yaw; position k = h % n_xy on a sunflower
+// spiral (r = radius sqrt(k / n_xy), angle k x the golden angle; k = 0 is the centre itself).  Deterministic, so every
+// rank (and the tests) builds the same list.
+void mapOptimization::hypothesisPose(const float center6[6], int n_yaw, int n_xy, float radius, int h, float out6[6]) {
+    const int iy = h / n_xy, k = h % n_xy;
+    const double golden = 2.399963229728653;
+    const double r = (double)radius * std::sqrt((double)k / (double)n_xy), a = golden * (double)k;
+    for (int i = 0; i < 6; ++i) out6[i] = center6[i];
+    out6[2] = (float)((double)center6[2] + 6.283185307179586 * (double)iy / (double)n_yaw);
+    out6[3] = (float)((double)center6[3] + r * std::cos(a));
+    out6[4] = (float)((double)center6[4] + r * std::sin(a));
+}
+
 bool mapOptimization::relocalizeInit() {
     if (!ctx_) { error_ = "no device context"; return false; }
     if (prior_.SubMapCenteriod.empty()) { error_ = "relo mode: no prior session loaded"; return false; }
-    const int submap = searchNearestSubMap(transformTobeMappedInit[3], transformTobeMappedInit[4], transformTobeMappedInit[5]);   // :267-270
-    float out6[6];
-    int it = 0, conv = 0;
-    if (ndtAlign(submap, transformTobeMappedInit, /*n_align=*/2, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); return false; }   // :273-287
-    std::memcpy(transformTobeMappedInit, out6, sizeof(out6));                   // :291-296
-    systemInitialized = true; poseInitialized = true;                          // :298-299
-    rep_.relo_initialized = 1; rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
-    std::memcpy(rep_.relo_pose, out6, sizeof(out6));
+    const int H = relo_n_yaw_ * relo_n_xy_;
+    if (H <= 1) {
+        const int submap = searchNearestSubMap(transformTobeMappedInit[3], transformTobeMappedInit[4], transformTobeMappedInit[5]);   // :267-270
+        float out6[6];
+        int it = 0, conv = 0;
+        if (ndtAlign(submap, transformTobeMappedInit, /*n_align=*/2, out6, &it, &conv) < 0) { error_ = liloc_last_error(ctx_); return false; }   // :273-287
+        std::memcpy(transformTobeMappedInit, out6, sizeof(out6));                   // :291-296
+        systemInitialized = true; poseInitialized = true;                          // :298-299
+        rep_.relo_initialized = 1; rep_.relo_submap = submap; rep_.relo_iterations = it; rep_.relo_converged = conv;
+        std::memcpy(rep_.relo_pose, out6, sizeof(out6));
+        return true;
+    }
+    // every hypothesis = the reference's init (:267-290) from another starting pose; sharded over the ranks inside the C ABI
+    if (liloc_ndt_source_put(ctx_, /*source_id=*/0, cloudInfo.cloud_deskewed, cloudInfo.cloud_size, cloudInfo.cloud_on_device) < 0) { error_ = liloc_last_error(ctx_); return false; }
+    std::vector<liloc_ndt_job> items((size_t)H);
+    for (int h = 0; h < H; ++h) {
+        float g6[6];
+        hypothesisPose(transformTobeMappedInit, relo_n_yaw_, relo_n_xy_, relo_radius_, h, g6);
+        items[h].target_id = searchNearestSubMap(g6[3], g6[4], g6[5]);
+        items[h].source_id = 0;
+        eulerToMatrix4(g6[0], g6[1], g6[2], g6[3], g6[4], g6[5], items[h].guess);
+    }
+    liloc_ndt_opts o{};
+    o.step_size = 0.1; o.outlier_ratio = 0.55; o.trans_eps = ndtEpsilon; o.max_iterations = 35;
+    o.search = regMethod == "DIRECT7" ? LILOC_NDT_DIRECT7 : (regMethod == "KDTREE" ? LILOC_NDT_KDTREE : LILOC_NDT_DIRECT1);
+    o.n_align = 2;
+    std::vector<float> rows((size_t)H * 8);
+    if (liloc_ndt_align_batch_sharded(ctx_, items.data(), H, &o, LILOC_SHARD_ROUND_ROBIN, rows.data(), nullptr) < 0) { error_ = liloc_last_error(ctx_); return false; }
+    int best = 0;
+    for (int h = 1; h < H; ++h) if (rows[(size_t)h * 8 + 6] > rows[(size_t)best * 8 + 6]) best = h;      // trans_probability: higher is better
+    std::memcpy(transformTobeMappedInit, &rows[(size_t)best * 8], 6 * sizeof(float));
+    systemInitialized = true; poseInitialized = true;
+    rep_.relo_initialized = 1; rep_.relo_submap = items[best].target_id; rep_.relo_iterations = (int)rows[(size_t)best * 8 + 7]; rep_.relo_converged = 1;
+    rep_.relo_hypothesis = best; rep_.relo_score = rows[(size_t)best * 8 + 6];
+    std::memcpy(rep_.relo_pose, &rows[(size_t)best * 8], 6 * sizeof(float));
     return true;
 }
 

@@ -53,6 +53,8 @@ struct FrameReport {                             // what the reference would pub
     int relo_vertex[3] = {-1, -1, -1};           // their prior keyframe ids
     float relo_fitness[3] = {0, 0, 0};           // getICPFitnessScore of each vertex' key cloud against the matched scan, capped at 2
                                                  // (-1: a vertex this session added itself, no score, anchorOptimize.hpp:431-434)
+    int relo_hypothesis = -1;                    // multi-hypothesis init: index of the winning hypothesis
+    float relo_score = 0.f;                      // ... and its trans_probability (score / points)
     int prior_added = -1;                        // addNewPrior appended this frame to the prior session under this key-pose id
     int prior_new_submap = -1;                   // ... and cut this new submap from the last submap_size additions
 };
@@ -135,6 +137,14 @@ public:
     int searchNearestSubMap(float x, float y, float z) const;                   // dataLoader.hpp:350-357 (1-NN on the centroids)
     std::vector<int> searchVertexes(int submap, float x, float y, float z) const;   // dataLoader.hpp:366-389 (radius 5 m, at most 3)
     bool relocalizeInit();                                                      // :261-305
+    // Multi-hypothesis relocalisation (north_star; not in the reference, whose /initialpose fixes only x, y and yaw, :764-769):
+    // n_yaw yaw offsets over the full circle x n_xy positions on a spiral of `radius` around the given pose, every
+    // hypothesis through the reference's 2 x align against the submap nearest to it, the best trans_probability wins.
+    // The hypotheses are sharded over the ranks of the context's communicator (liloc_comm_init through commInit):
+    // liloc_ndt_align_batch_sharded -- every rank ends up with the same winner.  n_yaw * n_xy == 1 is the reference's init.
+    void setReloHypotheses(int n_yaw, int n_xy, float radius) { relo_n_yaw_ = n_yaw < 1 ? 1 : n_yaw; relo_n_xy_ = n_xy < 1 ? 1 : n_xy; relo_radius_ = radius; }
+    int commInit(int rank, int world, const void* id128);
+    static void hypothesisPose(const float center6[6], int n_yaw, int n_xy, float radius, int h, float out6[6]);
     void saveRELOKeyFramesAndFactor();                                          // :1336-1389 (+ anchorOptimize.hpp:382-407)
     const PriorSession& prior() const { return prior_; }
     // AnchorOptimization::addNewPrior, cloud side (anchorOptimize.hpp:272-380): the current frame joins the prior map
@@ -169,6 +179,8 @@ private:
     std::vector<HitScratch> hit_scratch_;
     FrameReport rep_;
     PriorSession prior_;
+    int relo_n_yaw_ = 1, relo_n_xy_ = 1;
+    float relo_radius_ = 2.0f;
     int ndtAlign(int submap, const float guess6[6], int n_align, float out6[6], int* iterations, int* converged);
 };
 

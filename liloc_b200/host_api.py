@@ -28,7 +28,7 @@ class Report(C.Structure):
                 ("keyframe_id", C.c_int), ("reg_ms", C.c_double),
                 ("relo_initialized", C.c_int), ("relo_submap", C.c_int), ("relo_iterations", C.c_int), ("relo_converged", C.c_int),
                 ("relo_pose", C.c_float * 6), ("relo_n_vertices", C.c_int), ("relo_vertex", C.c_int * 3), ("relo_fitness", C.c_float * 3),
-                ("prior_added", C.c_int), ("prior_new_submap", C.c_int)]
+                ("prior_added", C.c_int), ("prior_new_submap", C.c_int), ("relo_hypothesis", C.c_int), ("relo_score", C.c_float)]
 
 
 def _load():
@@ -53,6 +53,10 @@ def _load():
     L.liloc_host_load_prior.restype = C.c_int
     L.liloc_host_load_prior.argtypes = [P, P, C.c_int, P, P]
     L.liloc_host_initialpose.argtypes = [P, C.c_float, C.c_float, C.c_float]
+    L.liloc_host_set_relo_hypotheses.argtypes = [P, C.c_int, C.c_int, C.c_float]
+    L.liloc_host_comm_init.restype = C.c_int
+    L.liloc_host_comm_init.argtypes = [P, C.c_int, C.c_int, P]
+    L.liloc_host_hypothesis_pose.argtypes = [P, C.c_int, C.c_int, C.c_float, C.c_int, P]
     L.liloc_host_load_prior_dir.restype = C.c_int
     L.liloc_host_load_prior_dir.argtypes = [P, C.c_char_p]
     L.liloc_host_save_session.restype = C.c_int
@@ -110,6 +114,14 @@ def _load():
 
 _lib = None
 PRIOR_KEYFRAME_BASE = 1 << 24      # mapOptimization::kPriorKeyframeBase: device keyframe ids of the prior session's key clouds
+
+
+def hypothesis_pose(center6, n_yaw: int, n_xy: int, radius: float, h: int) -> np.ndarray:
+    """mapOptimization::hypothesisPose: hypothesis h of the multi-hypothesis relocalisation init."""
+    c = np.ascontiguousarray(center6, np.float32).reshape(6)
+    out = np.zeros(6, np.float32)
+    lib().liloc_host_hypothesis_pose(c.ctypes.data, int(n_yaw), int(n_xy), float(radius), int(h), out.ctypes.data)
+    return out
 
 
 def euler_to_matrix(pose6) -> np.ndarray:
@@ -228,6 +240,16 @@ class MapOptimization:
         return reps
 
     # ---- relo mode ----
+    def set_relo_hypotheses(self, n_yaw: int, n_xy: int, radius: float = 2.0) -> None:
+        """Multi-hypothesis relocalisation init (n_yaw * n_xy hypotheses, sharded over the ranks of comm_init)."""
+        lib().liloc_host_set_relo_hypotheses(self._h, int(n_yaw), int(n_xy), float(radius))
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes | None) -> None:
+        buf = C.create_string_buffer(unique_id or b"", 128)
+        rc = lib().liloc_host_comm_init(self._h, int(rank), int(world), buf if world > 1 else None)
+        if rc < 0:
+            raise RuntimeError("comm_init: " + (lib().liloc_host_error(self._h) or b"").decode())
+
     def load_prior_session(self, keyposes7, clouds) -> int:
         """Prior session: key poses (n, 7) [roll, pitch, yaw, x, y, z, time] + their key clouds (body frame).
         Returns the number of submaps (dataLoader.hpp generateSubMaps, every 10 keyframes)."""

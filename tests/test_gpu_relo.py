@@ -309,3 +309,60 @@ def test_prior_map_grows_where_the_session_leaves_it(orc, synth):
                         wf = orc.icp_fitness(key_clouds[vid], model.poses[vid], scans[f], got, threads=8)
                         assert rep.relo_fitness[v] == np.float32(min(wf, 2.0))
         assert len(added) >= 11 and len(new_submaps) >= 1 and matched_new >= 2, (added, new_submaps, matched_new)
+
+
+def _hypothesis_scene(synth):
+    world = synth.make_world(size_xy=(80.0, 40.0), n_pillars=16, seed=13)
+    world[:, [2, 5]] -= 1.8
+    n_prior = 20
+    prior_traj = synth.trajectory_line(n_prior, step=1.0, x0=-10, height=0.0)
+    prior_clouds = [synth.scan(world, prior_traj[k], synth.VLP16, 1300 + k) for k in range(n_prior)]
+    truth = prior_traj[7].copy(); truth[3] += 0.3; truth[4] += 0.4; truth[2] += 0.05
+    scan = synth.scan(world, truth, synth.VLP16, 7800)
+    return prior_traj, prior_clouds, truth, scan
+
+
+def test_multi_hypothesis_relocalisation_init(orc, synth):
+    """The /initialpose is 1.3 m and a quarter turn off: the reference's single init (2 x align from that pose) does not find
+    the pose; 8 yaw x 6 position hypotheses, each through the same 2 x align (src/mapOptmization.cpp:267-290), sharded inside
+    the C ABI, do.  The winner and its pose are the oracle's for the same hypothesis list."""
+    from liloc_b200 import host_api
+    prior_traj, prior_clouds, truth, scan = _hypothesis_scene(synth)
+    keyposes7 = np.c_[prior_traj, 100.0 + np.arange(len(prior_traj))]
+    n_yaw, n_xy, radius = 8, 6, 2.0
+    init = np.array([0, 0, truth[2] + np.pi / 2 + 0.1, truth[3] + 1.0, truth[4] - 0.8, 0], np.float32)
+    odom = truth.astype(np.float32)[None]
+    with host_api.MapOptimization("lio_sam_default.yaml", "relo", device=0) as m:
+        res, eps = np.float32(m.param("ndtResolution")), np.float32(m.param("ndtEpsilon"))
+        assert m.load_prior_session(keyposes7, prior_clouds) == 2
+        # the reference's init alone
+        m.initialpose(init[3], init[4], init[2])
+        rep1 = m.handle(host_api.make_infos([scan], odom, np.array([500.0]))[0])
+        assert rep1.relo_initialized == 1
+        single = np.array(rep1.relo_pose, np.float32)
+        assert np.abs(single[3:5] - truth[3:5]).max() > 0.5 or abs(single[2] - truth[2]) > 0.2       # did not find it
+        # with hypotheses
+        m.reset()
+        assert m.load_prior_session(keyposes7, prior_clouds) == 2
+        m.set_relo_hypotheses(n_yaw, n_xy, radius)
+        m.initialpose(init[3], init[4], init[2])
+        rep = m.handle(host_api.make_infos([scan], odom, np.array([600.0]))[0])
+        assert rep.processed == 1 and rep.relo_initialized == 1
+        got = np.array(rep.relo_pose, np.float32)
+        assert np.abs(got[3:5] - truth[3:5]).max() < 0.1 and abs(got[2] - truth[2]) < 0.02, (got, truth)
+        cents = np.array([m.submap_info(s)["centroid"] for s in range(2)])
+    # oracle over the same hypothesis list
+    o = orc.NdtOpts(resolution=float(res), trans_eps=float(eps), search=0, threads=8)
+    subs = [orc.NdtTarget(np.concatenate([orc.transform_cloud(prior_clouds[k], prior_traj[k].astype(np.float32), threads=8) for k in range(10 * s, 10 * s + 10)]), res) for s in range(2)]
+    best, best_score, best_T = -1, -1e30, None
+    for h in range(n_yaw * n_xy):
+        g6 = host_api.hypothesis_pose(init, n_yaw, n_xy, radius, h)
+        sid = int(np.argmin(((cents - g6[3:]) ** 2).sum(1)))
+        T = host_api.euler_to_matrix(g6)[:3].copy()
+        for _ in range(2):
+            T, rr = orc.ndt_align(subs[sid], scan, T, o)
+        sc = np.float32(rr.score / len(scan))
+        if sc > best_score:
+            best, best_score, best_T = h, sc, T
+    assert rep.relo_hypothesis == best and abs(rep.relo_score - best_score) <= 1e-6 * abs(best_score)
+    assert np.abs(got[3:] - best_T[:, 3]).max() <= 1e-4 and np.abs(synth.rot_zyx(*[float(v) for v in got[:3]]) - best_T[:, :3]).max() <= 1e-5

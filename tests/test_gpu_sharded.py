@@ -115,3 +115,61 @@ def test_two_rank_sharded_align_nccl(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o[-3000:]
         assert f"rank {r} ok" in o
+
+
+HOST_WORKER = textwrap.dedent("""
+    import os, sys, time
+    import numpy as np
+    sys.path.insert(0, ROOT_DIR); sys.path.insert(0, os.path.join(ROOT_DIR, "tests"))
+    rank, world, idfile = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    from liloc_b200 import abi, host_api, synth
+    from test_gpu_relo import _hypothesis_scene
+    uid = None
+    if world > 1:
+        if rank == 0:
+            uid = abi.comm_unique_id()
+            with open(idfile + ".tmp", "wb") as f:
+                f.write(uid)
+            os.replace(idfile + ".tmp", idfile)
+        else:
+            for _ in range(600):
+                if os.path.exists(idfile):
+                    break
+                time.sleep(0.1)
+            uid = open(idfile, "rb").read()
+    prior_traj, prior_clouds, truth, scan = _hypothesis_scene(synth)
+    keyposes7 = np.c_[prior_traj, 100.0 + np.arange(len(prior_traj))]
+    init = np.array([0, 0, truth[2] + np.pi / 2 + 0.1, truth[3] + 1.0, truth[4] - 0.8, 0], np.float32)
+    with host_api.MapOptimization("lio_sam_default.yaml", "relo", device=rank) as m:
+        m.comm_init(rank, world, uid)
+        m.load_prior_session(keyposes7, prior_clouds)
+        m.set_relo_hypotheses(8, 6, 2.0)
+        m.initialpose(init[3], init[4], init[2])
+        rep = m.handle(host_api.make_infos([scan], truth.astype(np.float32)[None], np.array([600.0]))[0])
+        assert rep.processed == 1 and rep.relo_initialized == 1
+        print("RESULT", rank, rep.relo_hypothesis, " ".join(repr(float(v)) for v in rep.relo_pose), repr(float(rep.relo_score)))
+""")
+
+
+def test_host_class_multi_hypothesis_init_on_two_gpus(tmp_path):
+    """The C++ host class on two GPUs: each process one `mapOptimization` with its context's communicator; the 48 hypotheses of
+    the relocalisation init are split between the ranks inside liloc_ndt_align_batch_sharded and both ranks end up with the
+    same winner -- the one a single GPU finds."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    script = tmp_path / "host_worker.py"
+    script.write_text(HOST_WORKER.replace("ROOT_DIR", repr(ROOT)))
+
+    def run(world):
+        idfile = str(tmp_path / f"id_{world}.bin")
+        procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), idfile], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for r in range(world)]
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        res = []
+        for p, o in zip(procs, outs):
+            assert p.returncode == 0, o[-3000:]
+            res.append([l for l in o.splitlines() if l.startswith("RESULT")][-1].split()[2:])
+        return res
+    one = run(1)[0]
+    two = run(2)
+    assert two[0] == two[1] == one, (one, two)

@@ -175,6 +175,12 @@ typedef struct {
     int scan_on_device;
 } liloc_frame_in;
 int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res);
+/* Replaying a recorded sequence (the reference plays a bag: the next cloud_info is already in the subscriber queue, :254's
+ * queue of 5), the caller may name the NEXT frame's surf scan before making the current frame's call: its host->device copy
+ * is then enqueued on a side stream behind the current frame's launches and overlaps that frame's kernels, and the next
+ * liloc_frame / liloc_frame_features with this very (pointer, n) and scan_on_device = 0 finds it uploaded.  The host
+ * memory must stay unchanged until that call returns.  A hint no frame consumes costs one wasted copy, never a wrong scan. */
+int liloc_scan_prefetch(liloc_ctx* ctx, const liloc_point* next_scan, int n);
 typedef struct { int q_corner, map_points_corner, tiles_corner, tiles_surf, sort_redos; int reserved[3]; } liloc_s2m_extra;
 int liloc_last_s2m_extra(liloc_ctx* ctx, liloc_s2m_extra* out);
 

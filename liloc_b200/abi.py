@@ -186,6 +186,7 @@ def _load() -> C.CDLL:
         "liloc_debug_plane": (C.c_int, [P, P, C.c_int, P]),
         "liloc_frame_features": (C.c_int, [P, C.POINTER(FrameIn), P, C.POINTER(S2mOpts), C.POINTER(S2mResult)]),
         "liloc_last_s2m_extra": (C.c_int, [P, C.POINTER(S2mExtra)]),
+        "liloc_scan_prefetch": (C.c_int, [P, P, C.c_int]),
         "liloc_keyframe_put_features": (C.c_int, [P, C.c_int, P, C.c_int, P, C.c_int]),
         "liloc_keyframe_size_class": (C.c_int, [P, C.c_int, C.c_int]),
         "liloc_localmap_build_class": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_float, ip, ip]),
@@ -234,7 +235,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
            "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance "
-           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results").split()
+           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results liloc_scan_prefetch").split()
 
 
 COMM_ID_BYTES = 128
@@ -469,6 +470,12 @@ class Context:
         rc = self._chk(lib.liloc_frame(self._h, _ptr(ids), _ptr(poses), len(ids), map_leaf, sp, n, on_dev, scan_leaf,
                                        _ptr(pose), C.byref(o), C.byref(res)))
         return pose, res, rc
+
+    def scan_prefetch(self, scan: np.ndarray) -> None:
+        """liloc_scan_prefetch: `scan` (a C-contiguous float32 (n, 4) array the caller keeps alive and unchanged) is the NEXT
+        frame's surf scan; pass the very same array to that frame() call."""
+        assert scan.dtype == np.float32 and scan.flags.c_contiguous and scan.ndim == 2 and scan.shape[1] == 4
+        self._chk(lib.liloc_scan_prefetch(self._h, scan.ctypes.data, len(scan)))
 
     def frame_features(self, kf_ids, poses6, map_leafs, scans, scan_leafs, pose6, opts: S2mOpts | None = None,
                        scan_dev_ptrs=None, n_scans=None) -> tuple[np.ndarray, S2mResult, int]:

@@ -200,6 +200,19 @@ struct liloc_ctx {
         cudaEvent_t ev_done = nullptr;   // recorded behind the de-skew launch
     } dk[2];
     int dk_cur = -1, dk_staged = -1;
+    // liloc_scan_prefetch: the NEXT frame's surf scan (host memory) goes up on stream3 behind the current frame's launches,
+    // into one of two buffers (the other may be the current frame's scan)
+    struct ScanPrefetch {
+        DevBuf<float4> buf[2];
+        const liloc_point* hint = nullptr;   // hinted host cloud whose copy is not enqueued yet (nullptr: none)
+        int hint_n = 0;
+        const liloc_point* host = nullptr;   // host cloud whose copy is enqueued and not consumed yet (ev says when it is done)
+        int n = 0;
+        bool issued = false;
+        int slot = 0;                        // ... into buf[slot]
+        int in_use = -1;                     // buffer the frame in flight reads (-1: none)
+        cudaEvent_t ev = nullptr;
+    } pf;
     DevBuf<float4> dk_pts;
     DevBuf<int2> dk_rt;
     DevBuf<int> dk_tiles;
@@ -467,10 +480,19 @@ int scan_problem(liloc_ctx* ctx, int cls, cudaStream_t st, const liloc_point* pt
     fc.have_scan = false; fc.Q_all = -1;
     const float4* src = reinterpret_cast<const float4*>(pts);
     if (mode == LILOC_SCAN_HOST && n > 0) {
-        if ((rc = ensure(ctx, fc.scan_raw, (size_t)n))) return rc;
-        CU(cudaMemcpyAsync(fc.scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
-        ctx->stats.h2d_bytes += (long long)n * (long long)sizeof(float4);
-        src = fc.scan_raw.p;
+        liloc_ctx::ScanPrefetch& pf = ctx->pf;
+        if (cls == LILOC_SURF && pf.issued && pf.host == pts && pf.n == n) {
+            // uploaded ahead by liloc_scan_prefetch (bytes counted there): wait for that copy instead of making one
+            CU(cudaStreamWaitEvent(st, pf.ev, 0));
+            src = pf.buf[pf.slot].p;
+            pf.in_use = pf.slot; pf.issued = false;
+        } else {
+            if (cls == LILOC_SURF) pf.in_use = -1;
+            if ((rc = ensure(ctx, fc.scan_raw, (size_t)n))) return rc;
+            CU(cudaMemcpyAsync(fc.scan_raw.p, pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+            ctx->stats.h2d_bytes += (long long)n * (long long)sizeof(float4);
+            src = fc.scan_raw.p;
+        }
     }
     fc.scan_src_last = src; fc.scan_leaf_last = leaf;
     if ((rc = prob_voxelgrid(ctx, fc.vg_scan, src, n, leaf, &fc.scan, q))) return rc;
@@ -618,6 +640,7 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     CUB_(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&c->pf.ev, cudaEventDisableTiming));
     for (FeatClass* fcp : {&c->fc[0], &c->fc[1], &c->aux}) {
         FeatClass& fc = *fcp;
         for (VgInst* vi : {&fc.vg_map, &fc.vg_scan}) {
@@ -718,6 +741,8 @@ void liloc_destroy(liloc_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+    if (c->pf.ev) cudaEventDestroy(c->pf.ev);
+    fr(c->pf.buf[0].p); fr(c->pf.buf[1].p);
     fr(c->d_marks); fr(c->d_sm_scratch);
     fr(c->dk_pts.p); fr(c->dk_rt.p); fr(c->dk_tiles.p); fr(c->d_dk_imu);
     for (auto& S : c->dk) { fr(S.out.p); fr(S.d_n); if (S.ev_done) cudaEventDestroy(S.ev_done); }
@@ -1111,6 +1136,31 @@ static int frame_wait(liloc_ctx* ctx) {
     return 0;
 }
 
+// liloc_scan_prefetch's copy: on stream3 (nothing of a host-scan frame runs there), into the buffer the frame in flight
+// does not read.  The buffer it overwrites was last read two frames ago, and every frame ends with a host wait.
+static int prefetch_issue(liloc_ctx* ctx) {
+    liloc_ctx::ScanPrefetch& pf = ctx->pf;
+    if (!pf.hint) return 0;
+    const int slot = pf.in_use == 0 ? 1 : 0;         // an upload nobody consumed may be overwritten: it is replaced here
+    int rc;
+    if ((rc = ensure(ctx, pf.buf[slot], (size_t)pf.hint_n))) return rc;
+    CU(cudaMemcpyAsync(pf.buf[slot].p, pf.hint, (size_t)pf.hint_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream3));
+    CU(cudaEventRecord(pf.ev, ctx->stream3));
+    ctx->stats.h2d_bytes += (long long)pf.hint_n * (long long)sizeof(float4);
+    pf.host = pf.hint; pf.n = pf.hint_n; pf.slot = slot; pf.issued = true;
+    pf.hint = nullptr;
+    return 0;
+}
+
+int liloc_scan_prefetch(liloc_ctx* ctx, const liloc_point* pts, int n) {
+    ENTER(ctx);
+    if (n < 0 || (n > 0 && !pts)) return fail(ctx, LILOC_ERR_ARG, "scan_prefetch: bad arguments");
+    liloc_ctx::ScanPrefetch& pf = ctx->pf;
+    if (pf.issued && pf.host == pts && pf.n == n) { pf.hint = nullptr; return LILOC_OK; }      // already on its way
+    pf.hint = n > 0 ? pts : nullptr; pf.hint_n = n;
+    return LILOC_OK;
+}
+
 int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6, const liloc_s2m_opts* opts, liloc_s2m_result* res) {
     ENTER(ctx);
     if (!pose6 || !in) return fail(ctx, LILOC_ERR_ARG, "frame: null argument");
@@ -1162,6 +1212,7 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     CU(cudaEventRecord(ctx->ev_join2, ctx->stream2));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));                                         // join
     if ((rc = s2m_enqueue(ctx, pose6, o))) return rc;
+    if ((rc = prefetch_issue(ctx))) return rc;       // the hinted next scan goes up while this frame computes
     if ((rc = frame_wait(ctx))) return rc;           // the frame's only host synchronisation
     {   // counts come back inside the result struct
         const S2mResult& r = ctx->h_info->res;

@@ -82,7 +82,11 @@ int liloc_host_handle(void* h, const liloc_host_cloud_info* msg, liloc_host_repo
 
 // F callbacks back to back (what ros::spin() does with a queue of messages)
 int liloc_host_run(void* h, const liloc_host_cloud_info* msgs, int F, liloc_host_report* outs) {
+    auto* m = static_cast<mapOptimization*>(h);
     for (int i = 0; i < F; ++i) {
+        // the next message is already in the queue: its scan goes up while this frame's kernels run (liloc_scan_prefetch)
+        if (i + 1 < F && !msgs[i + 1].cloud_on_device && msgs[i + 1].cloud_size > 0)
+            liloc_scan_prefetch(m->context(), msgs[i + 1].cloud_deskewed, msgs[i + 1].cloud_size);
         const int rc = liloc_host_handle(h, msgs + i, outs ? outs + i : nullptr);
         if (rc < 0) return rc;
     }

@@ -341,6 +341,44 @@ def test_map_cache_is_output_identical(gpu_ctx, orc, synth):
     assert got == ref
 
 
+def test_scan_prefetch_is_output_identical(gpu_ctx, orc, synth):
+    """liloc_scan_prefetch: the next frame's scan uploaded behind the current frame's launches.  Every output equals the
+    run without hints -- also when a hint names a scan no frame consumes, when the hinted array is not the one the next frame
+    passes, and when one array is hinted twice."""
+    world = synth.make_world(seed=29)
+    traj = synth.trajectory_line(10, step=0.4, x0=-2)
+    sensor, scan_leaf, map_leaf = synth.VLP16, 0.4, 0.5
+    kfs = [orc.voxelgrid(synth.scan(world, traj[k], sensor, 2900 + k), scan_leaf) for k in range(3)]
+    scans = [np.ascontiguousarray(synth.scan(world, traj[k], sensor, 2900 + k), dtype=np.float32) for k in range(3, 10)]
+    decoy = np.ascontiguousarray(scans[0][::-1])
+
+    def run(hints):
+        gpu_ctx.keyframe_clear()
+        for k, c in enumerate(kfs):
+            gpu_ctx.keyframe_put(k, c)
+        ids, poses = [0, 1, 2], traj[:3].astype(np.float32)
+        gpu_ctx.stats_reset()
+        out = []
+        for j, raw in enumerate(scans):
+            if hints and j + 1 < len(scans):
+                nxt = scans[j + 1]
+                if j == 2:
+                    nxt = decoy                              # a hint the next frame does not honour
+                gpu_ctx.scan_prefetch(nxt)
+                if j == 4:
+                    gpu_ctx.scan_prefetch(nxt)               # twice: still one upload
+            pose, res, rc = gpu_ctx.frame(ids, poses, map_leaf, raw, scan_leaf, synth.perturb(traj[3 + j], 90 + j, dt=0.05, dr=0.01))
+            out.append((rc, pose.tobytes(), res.iters, res.n_sel, res.converged, res.map_points, res.q_all, gpu_ctx.scan_ds_get().tobytes()))
+        return out, gpu_ctx.stats()
+
+    ref, st0 = run(False)
+    got, st1 = run(True)
+    assert got == ref
+    scan_bytes = sum(len(s) for s in scans) * 16
+    extra = st1["h2d_bytes"] - st0["h2d_bytes"]
+    assert st0["h2d_bytes"] >= scan_bytes and extra == len(decoy) * 16      # only the unconsumed hint cost a copy
+
+
 def test_errors_are_codes_not_exceptions_from_c(gpu_ctx):
     from liloc_b200 import LilocError
     with pytest.raises(LilocError) as e:

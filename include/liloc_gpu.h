@@ -55,7 +55,11 @@ typedef struct {
                                their poses and the leaf size are bit-identical (the result is a pure function of those
                                inputs, so outputs do not change; the reference recomputes every frame).  See also
                                liloc_set_map_cache. */
-    int reserved[4];
+    int share;              /* [0 -> 1] this context is one of `share` contexts (sequences) driving the same GPU at once, one
+                               host thread each: every launch takes 1 / share of the blocks it would otherwise use, so that
+                               the frames of the sequences are co-resident (throughput mode; results are unchanged).  0: the
+                               LILOC_SHARE environment variable, else 1.  See also liloc_set_share. */
+    int reserved[3];
 } liloc_config;
 
 /* scan2MapOptimization knobs.  Reference values in brackets. */
@@ -85,6 +89,7 @@ typedef struct {
 
 /* ---- lifetime: allocateMemory() :213-244, VoxelGrid set-up :158-160 ------------------------- */
 int  liloc_create(const liloc_config* cfg, liloc_ctx** out);
+int  liloc_set_share(liloc_ctx* ctx, int share);     /* returns the previous value; takes effect from the next launch */
 void liloc_destroy(liloc_ctx* ctx);
 const char* liloc_last_error(const liloc_ctx* ctx);   /* ctx may be NULL: last create() error */
 const char* liloc_version(void);

@@ -24,7 +24,7 @@ class LilocError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("max_scan_points", C.c_int), ("max_raw_points", C.c_int), ("map_cache", C.c_int),
-                ("reserved", C.c_int * 4)]
+                ("share", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class S2mOpts(C.Structure):
@@ -199,6 +199,7 @@ def _load() -> C.CDLL:
         "liloc_debug_eigen3": (C.c_int, [P, P, C.c_int, P, P]),
         "liloc_last_marks": (C.c_int, [P, P, C.c_int]),
         "liloc_set_map_cache": (C.c_longlong, [P, C.c_int]),
+        "liloc_set_share": (C.c_int, [P, C.c_int]),
         "liloc_keyframe_get": (C.c_int, [P, C.c_int, C.c_int, P, C.c_int, ip]),
         "liloc_globalmap_build": (C.c_int, [P, P, P, C.c_int, C.c_float, P, C.c_int, ip]),
         "liloc_icp_fitness": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P, fp]),
@@ -235,7 +236,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
            "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance "
-           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results liloc_scan_prefetch").split()
+           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results liloc_scan_prefetch liloc_set_share").split()
 
 
 COMM_ID_BYTES = 128
@@ -285,8 +286,9 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
 class Context:
     """One liloc_ctx (one GPU, one stream).  Mirrors the calls mapOptimization makes per frame."""
 
-    def __init__(self, device: int = 0, max_scan_points: int = 32 * 1800, max_raw_points: int = 1 << 20, map_cache: bool = False):
-        cfg = _Config(device, max_scan_points, max_raw_points, int(map_cache))
+    def __init__(self, device: int = 0, max_scan_points: int = 32 * 1800, max_raw_points: int = 1 << 20, map_cache: bool = False,
+                 share: int = 0):
+        cfg = _Config(device, max_scan_points, max_raw_points, int(map_cache), int(share))
         h = C.c_void_p()
         rc = lib.liloc_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -714,6 +716,10 @@ class Context:
         out = np.zeros((32, 16), np.float32)
         n = lib.liloc_last_trace(self._h, _ptr(out), iters)
         return out[:n]
+
+    def set_share(self, share: int) -> int:
+        """liloc_set_share: this context is one of `share` contexts driving the GPU concurrently; returns the previous value."""
+        return int(lib.liloc_set_share(self._h, int(share)))
 
     def set_map_cache(self, on: bool) -> int:
         """Local-map memoisation on / off; returns the number of frames that have reused their map so far."""

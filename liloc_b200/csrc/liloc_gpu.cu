@@ -149,6 +149,8 @@ struct liloc_ctx {
     unsigned frame_seq = 0;                      // sequence number of the last enqueued registration
     bool poll_result = true;                     // wait for a frame by polling done_seq (LILOC_NO_POLL=1: cudaStreamSynchronize)
     int s2m_max_blocks = 0;
+    int s2m_blocks_full = 0, pipe_blocks_full = 0, pipe_blocks_wide_full = 0;   // launch sizes of a context that has the GPU to itself
+    int share = 1;                       // liloc_set_share: this context is one of `share` driving the GPU concurrently
     int pipe_blocks = 0;                 // blocks of a narrow point-cloud pipeline launch (one per SM)
     int pipe_blocks_wide = 0;            // blocks of a wide one (two per SM when three fit, so wide + narrow co-reside)
     int* d_sm_scratch = nullptr;             // 2 x kSmScratch ints, zero between launches (pipeline.cuh)
@@ -612,6 +614,18 @@ const char* liloc_version(void) { return "liloc_b200 0.2 (sm_100a)"; }
 
 const char* liloc_last_error(const liloc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+// S contexts sharing one GPU (concurrent sequences, one host thread each): the cooperative launches of one frame fill the
+// co-residency capacity of the device on their own (2 + 1 pipeline blocks per SM, 2 registration blocks per SM), so launches
+// of the other contexts queue behind them; with 1 / S of the blocks each, the launches of S frames are resident together.
+// Results do not depend on the launch size (every sum has a fixed order).
+static void apply_share(liloc_ctx* c, int S) {
+    if (S < 1) S = 1;
+    c->share = S;
+    c->s2m_max_blocks = std::max(1, c->s2m_blocks_full / S);
+    c->pipe_blocks = std::max(1, c->pipe_blocks_full / S);
+    c->pipe_blocks_wide = std::max(1, c->pipe_blocks_wide_full / S);
+}
+
 int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     liloc_ctx* ctx = nullptr;       // CU() reports into g_create_error while ctx == nullptr
     if (!cfg || !out) return fail(nullptr, LILOC_ERR_ARG, "liloc_create: null argument");
@@ -683,6 +697,12 @@ int liloc_create(const liloc_config* cfg, liloc_ctx** out) {
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_voxel_pipeline cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->pipe_blocks = c->num_sms;
     c->pipe_blocks_wide = per_sm >= 3 ? 2 * c->num_sms : c->num_sms;      // wide (2 per SM) + narrow (1 per SM) must co-reside
+    c->s2m_blocks_full = c->s2m_max_blocks; c->pipe_blocks_full = c->pipe_blocks; c->pipe_blocks_wide_full = c->pipe_blocks_wide;
+    {
+        int share = cfg->share;
+        if (share <= 0) { const char* e = std::getenv("LILOC_SHARE"); share = e ? std::atoi(e) : 1; }
+        apply_share(c, share);
+    }
     CUB_(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ndt_align, kNdtThreads, 0));
     if (per_sm < 1) { fail(c, LILOC_ERR_CUDA, "k_ndt_align cannot be resident"); return bail(LILOC_ERR_CUDA); }
     c->ndt_max_blocks = per_sm * c->num_sms;
@@ -2052,6 +2072,13 @@ int liloc_last_marks(liloc_ctx* ctx, unsigned long long* out, int cap) {
     const int n = cap < 2 * kPipeMarks + kS2mMarks ? cap : 2 * kPipeMarks + kS2mMarks;
     std::memcpy(out, ctx->h_info->marks, (size_t)n * sizeof(unsigned long long));
     return n;
+}
+
+int liloc_set_share(liloc_ctx* ctx, int share) {
+    if (!ctx) return LILOC_ERR_ARG;
+    const int prev = ctx->share;
+    apply_share(ctx, share);
+    return prev;
 }
 
 long long liloc_set_map_cache(liloc_ctx* ctx, int enabled) {

@@ -133,6 +133,8 @@ int liloc_host_save_g2o(const char* path, const double* keyposes7, int n) {
     return liloc_host::saveSessionGraph(path, kp, e) ? 0 : -1;
 }
 
+// throughput mode: this object is one of `share` objects (sequences) processed concurrently on its GPU (liloc_set_share)
+int liloc_host_set_share(void* h, int share) { return liloc_set_share(static_cast<mapOptimization*>(h)->context(), share); }
 void liloc_host_set_relo_hypotheses(void* h, int n_yaw, int n_xy, float radius) { static_cast<mapOptimization*>(h)->setReloHypotheses(n_yaw, n_xy, radius); }
 int liloc_host_comm_init(void* h, int rank, int world, const void* id128) { return static_cast<mapOptimization*>(h)->commInit(rank, world, id128); }
 void liloc_host_hypothesis_pose(const float* center6, int n_yaw, int n_xy, float radius, int hyp, float* out6) {

@@ -54,6 +54,7 @@ def _load():
     L.liloc_host_load_prior.argtypes = [P, P, C.c_int, P, P]
     L.liloc_host_initialpose.argtypes = [P, C.c_float, C.c_float, C.c_float]
     L.liloc_host_set_relo_hypotheses.argtypes = [P, C.c_int, C.c_int, C.c_float]
+    L.liloc_host_set_share.argtypes = [P, C.c_int]; L.liloc_host_set_share.restype = C.c_int
     L.liloc_host_comm_init.restype = C.c_int
     L.liloc_host_comm_init.argtypes = [P, C.c_int, C.c_int, P]
     L.liloc_host_hypothesis_pose.argtypes = [P, C.c_int, C.c_int, C.c_float, C.c_int, P]
@@ -238,6 +239,11 @@ class MapOptimization:
         if rc < 0:
             raise RuntimeError(f"liloc_host_run failed ({rc}): " + (lib().liloc_host_error(self._h) or b"").decode())
         return reps
+
+    def set_share(self, share: int) -> int:
+        """Throughput mode: this object is one of `share` objects processed concurrently on its GPU, one host thread each
+        (liloc_set_share: 1 / share of the blocks per launch so that the frames of the sequences are co-resident)."""
+        return int(lib().liloc_host_set_share(self._h, int(share)))
 
     # ---- relo mode ----
     def set_relo_hypotheses(self, n_yaw: int, n_xy: int, radius: float = 2.0) -> None:

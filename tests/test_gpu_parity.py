@@ -379,6 +379,36 @@ def test_scan_prefetch_is_output_identical(gpu_ctx, orc, synth):
     assert st0["h2d_bytes"] >= scan_bytes and extra == len(decoy) * 16      # only the unconsumed hint cost a copy
 
 
+def test_share_is_output_identical(gpu_ctx, orc, synth):
+    """liloc_set_share (throughput mode: 1 / S of the blocks per launch): the launch size changes, no output does --
+    VoxelGrid, local map, search grid and the registration have fixed summation orders."""
+    world = synth.make_world(seed=31)
+    traj = synth.trajectory_line(8, step=0.4, x0=-2)
+    sensor, scan_leaf, map_leaf = synth.HDL32, 0.4, 0.4
+    kfs = [orc.voxelgrid(synth.scan(world, traj[k], sensor, 3100 + k), scan_leaf) for k in range(4)]
+    scans = [synth.scan(world, traj[k], sensor, 3100 + k) for k in range(4, 8)]
+
+    def run(share):
+        assert gpu_ctx.set_share(share) >= 1
+        gpu_ctx.keyframe_clear()
+        for k, c in enumerate(kfs):
+            gpu_ctx.keyframe_put(k, c)
+        ids, poses = [0, 1, 2, 3], traj[:4].astype(np.float32)
+        out = []
+        for j, raw in enumerate(scans):
+            pose, res, rc = gpu_ctx.frame(ids, poses, map_leaf, raw, scan_leaf, synth.perturb(traj[4 + j], 40 + j, dt=0.05, dr=0.01))
+            out.append((rc, pose.tobytes(), res.iters, res.n_sel, res.converged, res.map_points, res.q_all,
+                        gpu_ctx.localmap_get().tobytes(), gpu_ctx.scan_ds_get().tobytes()))
+        return out
+
+    try:
+        ref = run(1)
+        for share in (3, 8, 64, 1000):                      # 1000: one block per launch
+            assert run(share) == ref, share
+    finally:
+        assert gpu_ctx.set_share(1) == 1000
+
+
 def test_errors_are_codes_not_exceptions_from_c(gpu_ctx):
     from liloc_b200 import LilocError
     with pytest.raises(LilocError) as e:

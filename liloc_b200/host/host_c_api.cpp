@@ -108,6 +108,14 @@ int liloc_host_load_prior_dir(void* h, const char* dir) {
     return m->loadPriorSessionDir(dir ? dir : "") ? (int)m->prior().SubMapCenteriod.size() : -1;
 }
 int liloc_host_save_session(void* h, const char* dir) { return static_cast<mapOptimization*>(h)->saveSession(dir ? dir : "") ? 0 : -1; }
+// ... at req.resolution (save_mapRequest / save_sessionRequest)
+int liloc_host_save_session_res(void* h, const char* dir, float resolution) { return static_cast<mapOptimization*>(h)->saveSession(dir ? dir : "", resolution) ? 0 : -1; }
+int liloc_host_save_poses_pcd(const char* path, const double* keyposes7, int n) {
+    std::vector<liloc_host::PointTypePose> kp((size_t)(n > 0 ? n : 0));
+    for (int i = 0; i < n; ++i) { const double* r = keyposes7 + 7 * i; kp[i] = liloc_host::PointTypePose{(float)r[3], (float)r[4], (float)r[5], (float)i, (float)r[0], (float)r[1], (float)r[2], r[6]}; }
+    std::string e;
+    return liloc_host::savePosesPCDBinary(path, kp, e) ? 0 : -1;
+}
 
 // session file format, host only (no device context needed): parse a PCD / a g2o; used by the CPU tests
 int liloc_host_load_pcd(const char* path, liloc_point* out, int cap, char* err, int err_cap) {

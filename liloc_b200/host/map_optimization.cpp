@@ -467,23 +467,59 @@ bool mapOptimization::loadPriorSessionDir(const std::string& dir) {
     return loadPriorSession(kp.data(), (int)kp.size(), flat.data(), offs.data());
 }
 
-bool mapOptimization::saveSession(const std::string& dir) {
+// save_map (lio, :419-541) / save_session (relo, :543-635) at `resolution` (req.resolution).  Which session: the reference's
+// save_session writes data_loader's key poses and key clouds -- the PRIOR session including everything addNewPrior joined --
+// and refuses to run outside relo mode; save_map writes the current session's cloudKeyPoses6D / surfCloudKeyFrames.  Both
+// lay out the same directory.  Every key cloud goes through VoxelGrid(resolution) into PCDs/<i>.pcd; globalMap.pcd is ALL key
+// clouds, transformed by their key poses, concatenated in key order and filtered at `resolution` (:590-619).
+// resolution == 0: the reference never assigns surfCloudDS / globalMapCloudDS then and writes empty clouds; here the key
+// clouds are written as they are and the global map is filtered at mappingSurfLeafSize (the filter's standing leaf).
+bool mapOptimization::saveSession(const std::string& dir, float resolution) {
     if (!ctx_) { error_ = "no device context"; return false; }
+    if (resolution < 0.f || resolution != resolution) { error_ = "saveSession: bad resolution"; return false; }
     std::error_code ec;
     std::filesystem::create_directories(dir + "/PCDs", ec);
     if (ec) { error_ = "cannot create " + dir + "/PCDs: " + ec.message(); return false; }
-    if (!saveSessionGraph(dir + "/singlesession_posegraph.g2o", cloudKeyPoses6D, error_)) return false;
-    std::vector<liloc_point> buf;
-    for (int k = 0; k < (int)cloudKeyPoses6D.size(); ++k) {
-        int n = 0;
-        if (liloc_keyframe_get(ctx_, LILOC_SURF, k, nullptr, 0, &n) < 0) { error_ = liloc_last_error(ctx_); return false; }
-        buf.resize((size_t)(n > 0 ? n : 1));
-        if (liloc_keyframe_get(ctx_, LILOC_SURF, k, buf.data(), n, &n) < 0) { error_ = liloc_last_error(ctx_); return false; }
-        if (!savePCDBinary(dir + "/PCDs/" + std::to_string(k) + ".pcd", buf.data(), n, error_)) return false;
+    const bool prior = mode == ModeType::RELO && !prior_.KeyPoses6D.empty();
+    const std::vector<PointTypePose>& keyPoses = prior ? prior_.KeyPoses6D : cloudKeyPoses6D;
+    const int id0 = prior ? kPriorKeyframeBase : 0;
+    if (!saveSessionGraph(dir + "/singlesession_posegraph.g2o", keyPoses, error_)) return false;
+    if (!savePosesPCDBinary(dir + "/transformations.pcd", keyPoses, error_)) return false;
+    if (!prior) {                                     // save_map also writes the key positions (:437)
+        std::vector<liloc_point> traj;
+        for (const PointType& p : cloudKeyPoses3D) traj.push_back(liloc_point{p.x, p.y, p.z, p.intensity});
+        if (!savePCDBinary(dir + "/trajectory.pcd", traj.data(), (int)traj.size(), error_)) return false;
     }
-    std::vector<liloc_point> gm;                      // globalMap.pcd (:612-621)
-    if (!publishGlobalMap(gm)) return false;
-    return savePCDBinary(dir + "/globalMap.pcd", gm.data(), (int)gm.size(), error_);
+    std::vector<liloc_point> buf, ds;
+    std::vector<int> ids; std::vector<float> poses;
+    long long total = 0;
+    for (int k = 0; k < (int)keyPoses.size(); ++k) {
+        int n = 0;
+        if (liloc_keyframe_get(ctx_, LILOC_SURF, id0 + k, nullptr, 0, &n) < 0) { error_ = liloc_last_error(ctx_); return false; }
+        buf.resize((size_t)(n > 0 ? n : 1));
+        if (liloc_keyframe_get(ctx_, LILOC_SURF, id0 + k, buf.data(), n, &n) < 0) { error_ = liloc_last_error(ctx_); return false; }
+        const liloc_point* out = buf.data();
+        int m = n;
+        if (resolution != 0.f && n > 0) {
+            ds.resize((size_t)n);
+            if (liloc_voxelgrid(ctx_, buf.data(), n, resolution, ds.data(), n, &m) < 0) { error_ = liloc_last_error(ctx_); return false; }
+            out = ds.data();
+        }
+        if (!savePCDBinary(dir + "/PCDs/" + std::to_string(k) + ".pcd", out, m, error_)) return false;
+        const PointTypePose& p = keyPoses[k];
+        const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+        ids.push_back(id0 + k); poses.insert(poses.end(), pose6, pose6 + 6);
+        total += n;
+    }
+    const float leaf = resolution != 0.f ? resolution : mappingSurfLeafSize;
+    std::vector<liloc_point> gm;
+    int M = 0;
+    if (!ids.empty() && total > 0) {
+        if (liloc_globalmap_build(ctx_, ids.data(), poses.data(), (int)ids.size(), leaf, nullptr, 0, &M) < 0) { error_ = liloc_last_error(ctx_); return false; }
+        gm.resize((size_t)(M > 0 ? M : 1));
+        if (M > 0 && liloc_globalmap_build(ctx_, ids.data(), poses.data(), (int)ids.size(), leaf, gm.data(), M, &M) < 0) { error_ = liloc_last_error(ctx_); return false; }
+    }
+    return savePCDBinary(dir + "/globalMap.pcd", gm.data(), M, error_);
 }
 
 void mapOptimization::initialposeHandler(float x, float y, float yaw) {        // :755-769: only x, y and yaw are taken

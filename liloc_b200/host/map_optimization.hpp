@@ -132,7 +132,7 @@ public:
     // dataLoader.hpp:207-304), and the writer of that format for the current session (save_session / save_map,
     // :420-635: pose graph + one PCD per keyframe; nothing is deleted, unlike the reference's `rm -r`).
     bool loadPriorSessionDir(const std::string& session_dir);
-    bool saveSession(const std::string& session_dir);
+    bool saveSession(const std::string& session_dir, float resolution = 0.f);
     void initialposeHandler(float x, float y, float yaw);                       // :755-769
     int searchNearestSubMap(float x, float y, float z) const;                   // dataLoader.hpp:350-357 (1-NN on the centroids)
     std::vector<int> searchVertexes(int submap, float x, float y, float z) const;   // dataLoader.hpp:366-389 (radius 5 m, at most 3)

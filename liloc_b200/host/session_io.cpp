@@ -178,6 +178,25 @@ bool savePCDBinary(const std::string& path, const liloc_point* pts, int n, std::
     return true;
 }
 
+bool savePosesPCDBinary(const std::string& path, const std::vector<PointTypePose>& kp, std::string& err) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) { err = "cannot write " + path; return false; }
+    const size_t n = kp.size();
+    f << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z _ intensity roll pitch yaw time _\n"
+      << "SIZE 4 4 4 1 4 4 4 4 8 1\nTYPE F F F U F F F F F U\nCOUNT 1 1 1 4 1 1 1 1 1 8\n"
+      << "WIDTH " << n << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << n << "\nDATA binary\n";
+    for (const PointTypePose& p : kp) {
+        unsigned char rec[48] = {0};
+        const float head[3] = {p.x, p.y, p.z};
+        const float one = 1.0f;                               // PCL_ADD_POINT4D: data[3] = 1
+        const float mid[4] = {p.intensity, p.roll, p.pitch, p.yaw};
+        std::memcpy(rec, head, 12); std::memcpy(rec + 12, &one, 4); std::memcpy(rec + 16, mid, 16); std::memcpy(rec + 32, &p.time, 8);
+        f.write(reinterpret_cast<const char*>(rec), 48);
+    }
+    if (!f) { err = "write failed: " + path; return false; }
+    return true;
+}
+
 bool loadSessionGraph(const std::string& g2o_path, std::vector<PointTypePose>& keyPoses, std::string& err) {
     keyPoses.clear();
     std::ifstream f(g2o_path);

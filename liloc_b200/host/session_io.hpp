@@ -23,6 +23,10 @@ bool loadPCD(const std::string& path, std::vector<liloc_point>& out, std::string
 // pcl::io::savePCDFileBinary<pcl::PointXYZI> (fields x y z intensity, 16 bytes per point, DATA binary)
 bool savePCDBinary(const std::string& path, const liloc_point* pts, int n, std::string& err);
 
+// pcl::io::savePCDFileBinary<PointTypePose> (transformations.pcd, :438 / :564): PointXYZIRPYT as PCL lays it out -- 48 bytes
+// per pose {x y z pad4 intensity roll pitch yaw time(double) pad8}, the padding declared as `_` fields (include/utility.h:87-103)
+bool savePosesPCDBinary(const std::string& path, const std::vector<PointTypePose>& keyPoses, std::string& err);
+
 // Session::loadSessionGraph + initKeyPoses (dataLoader.hpp:207-268): the vertices in ascending id order as key poses
 // (roll / pitch / yaw from the quaternion like gtsam::Rot3::roll/pitch/yaw, intensity = node id).
 bool loadSessionGraph(const std::string& g2o_path, std::vector<PointTypePose>& keyPoses, std::string& err);

@@ -62,6 +62,10 @@ def _load():
     L.liloc_host_load_prior_dir.argtypes = [P, C.c_char_p]
     L.liloc_host_save_session.restype = C.c_int
     L.liloc_host_save_session.argtypes = [P, C.c_char_p]
+    L.liloc_host_save_session_res.restype = C.c_int
+    L.liloc_host_save_session_res.argtypes = [P, C.c_char_p, C.c_float]
+    L.liloc_host_save_poses_pcd.restype = C.c_int
+    L.liloc_host_save_poses_pcd.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int]
     L.liloc_host_load_pcd.restype = C.c_int
     L.liloc_host_load_pcd.argtypes = [C.c_char_p, P, C.c_int, C.c_char_p, C.c_int]
     L.liloc_host_save_pcd.restype = C.c_int
@@ -274,8 +278,9 @@ class MapOptimization:
             raise RuntimeError("loadPriorSessionDir: " + (lib().liloc_host_error(self._h) or b"").decode())
         return n
 
-    def save_session(self, session_dir: str) -> None:
-        if lib().liloc_host_save_session(self._h, session_dir.encode()) != 0:
+    def save_session(self, session_dir: str, resolution: float = 0.0) -> None:
+        """save_map (lio) / save_session (relo: the prior session with what this session joined to it) at req.resolution."""
+        if lib().liloc_host_save_session_res(self._h, session_dir.encode(), float(resolution)) != 0:
             raise RuntimeError("saveSession: " + (lib().liloc_host_error(self._h) or b"").decode())
 
     def initialpose(self, x: float, y: float, yaw: float):

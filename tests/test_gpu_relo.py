@@ -158,6 +158,24 @@ def test_session_round_trip_lio_save_then_relocalise(tmp_path, orc, synth):
     k = kf_ids[3]
     assert np.array_equal(host_api.load_pcd(os.path.join(sdir, "PCDs", f"{k}.pcd")), orc.voxelgrid(seq.scans[frames_of_kf[3]], 0.2))
     assert len(host_api.load_pcd(os.path.join(sdir, "globalMap.pcd"))) > 1000
+    # transformations.pcd: the key poses as PCL writes PointXYZIRPYT (48-byte records behind the header)
+    raw = open(os.path.join(sdir, "transformations.pcd"), "rb").read()
+    body = raw[raw.index(b"DATA binary\n") + len(b"DATA binary\n"):]
+    assert len(body) == 48 * n_kf
+    rec = np.frombuffer(body, np.dtype([("xyz", "<f4", 3), ("one", "<f4"), ("irpy", "<f4", 4), ("time", "<f8"), ("pad", "V8")]))
+    assert np.array_equal(rec["xyz"], kp[:, 3:6].astype(np.float32)) and np.array_equal(rec["irpy"][:, 1:], kp[:, :3].astype(np.float32))
+    assert np.array_equal(rec["irpy"][:, 0], np.arange(n_kf, dtype=np.float32)) and np.all(rec["one"] == 1.0)
+    assert len(host_api.load_pcd(os.path.join(sdir, "trajectory.pcd"))) == n_kf
+    # the same session at req.resolution = 0.5: every key cloud and the all-keyframe global map through VoxelGrid(0.5)
+    sdir5 = str(tmp_path / "session_05")
+    with host_api.MapOptimization("lio_sam_default.yaml", "lio", device=0) as m:
+        m.run(host_api.make_infos(seq.scans, seq.odom, seq.stamps))
+        m.save_session(sdir5, resolution=0.5)
+    full = [host_api.load_pcd(os.path.join(sdir, "PCDs", f"{i}.pcd")) for i in range(n_kf)]
+    for i in (0, 3, n_kf - 1):
+        assert np.array_equal(host_api.load_pcd(os.path.join(sdir5, "PCDs", f"{i}.pcd")), orc.voxelgrid(full[i], 0.5))
+    world_cloud = np.concatenate([orc.transform_cloud(full[i], kp[i, :6].astype(np.float32), threads=8) for i in range(n_kf)])
+    assert np.array_equal(host_api.load_pcd(os.path.join(sdir5, "globalMap.pcd")), orc.voxelgrid(world_cloud, 0.5))
     # new session in relo mode against the saved one: scan of frame 12, /initialpose 0.4 m / 0.04 rad off its lio pose
     f = 12
     truth = np.array(reps[f].pose, np.float32)
@@ -223,7 +241,7 @@ class _PriorModel:
         return i, None
 
 
-def test_prior_map_grows_where_the_session_leaves_it(orc, synth):
+def test_prior_map_grows_where_the_session_leaves_it(tmp_path, orc, synth):
     """addScanMatchingFactor with fewer than two prior vertices in reach calls addNewPrior (anchorOptimize.hpp:387-390): the
     session drives out of the prior map, its frames (pose + FULL scan) join the prior session, after ten additions past the
     first a new, voxel-filtered submap is cut on the device, and the frames after that are matched against it.  Checked
@@ -309,6 +327,20 @@ def test_prior_map_grows_where_the_session_leaves_it(orc, synth):
                         wf = orc.icp_fitness(key_clouds[vid], model.poses[vid], scans[f], got, threads=8)
                         assert rep.relo_fitness[v] == np.float32(min(wf, 2.0))
         assert len(added) >= 11 and len(new_submaps) >= 1 and matched_new >= 2, (added, new_submaps, matched_new)
+        # save_session (:543-635) writes the PRIOR session with what this one joined to it
+        sdir = str(tmp_path / "grown")
+        m.save_session(sdir)
+        n_all = n_prior + len(added)
+        back = host_api.load_g2o(os.path.join(sdir, "singlesession_posegraph.g2o"))
+        assert len(back) == n_all == len(os.listdir(os.path.join(sdir, "PCDs")))
+        want_p = np.array([model.poses[i] for i in range(n_all)], np.float32)
+        dang = (back[:, :3] - want_p[:, :3] + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(back[:, 3:6] - want_p[:, 3:]).max() < 5e-6 and np.abs(dang).max() < 5e-6
+        for i in (0, n_prior - 1, added[0], added[-1]):
+            assert np.array_equal(host_api.load_pcd(os.path.join(sdir, "PCDs", f"{i}.pcd")), key_clouds[i])
+        leaf = np.float32(m.param("mappingSurfLeafSize"))
+        allc = np.concatenate([orc.transform_cloud(key_clouds[i], model.poses[i], threads=8) for i in range(n_all)])
+        assert np.array_equal(host_api.load_pcd(os.path.join(sdir, "globalMap.pcd")), orc.voxelgrid(allc, leaf))
 
 
 def _hypothesis_scene(synth):

@@ -128,6 +128,29 @@ def _lzf_compress(data: bytes) -> bytes:
     return bytes(out)
 
 
+def test_transformations_pcd_layout(tmp_path):
+    """transformations.pcd (src/mapOptmization.cpp:438, :564): PointXYZIRPYT (include/utility.h:87-103) the way
+    pcl::io::savePCDFileBinary lays a registered point struct out -- raw 48-byte records, padding declared as `_` fields."""
+    from liloc_b200 import host_api
+    rng = np.random.default_rng(5)
+    kp = np.c_[rng.uniform(-3, 3, (7, 3)), rng.uniform(-50, 50, (7, 3)), 1.7e9 + np.arange(7) * 0.1]
+    path = str(tmp_path / "transformations.pcd")
+    assert host_api.lib().liloc_host_save_poses_pcd(path.encode(), kp.ctypes.data_as(host_api.C.POINTER(host_api.C.c_double)), len(kp)) == 0
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"DATA binary\n", 1)
+    lines = dict(l.split(" ", 1) for l in head.decode().splitlines() if not l.startswith("#"))
+    assert lines["FIELDS"] == "x y z _ intensity roll pitch yaw time _" and lines["SIZE"] == "4 4 4 1 4 4 4 4 8 1"
+    assert lines["TYPE"] == "F F F U F F F F F U" and lines["COUNT"] == "1 1 1 4 1 1 1 1 1 8"
+    assert lines["POINTS"] == "7" and lines["WIDTH"] == "7" and lines["HEIGHT"] == "1"
+    assert sum(int(a) * int(b) for a, b in zip(lines["SIZE"].split(), lines["COUNT"].split())) == 48 and len(body) == 48 * 7
+    rec = np.frombuffer(body, np.dtype([("xyz", "<f4", 3), ("one", "<f4"), ("irpy", "<f4", 4), ("time", "<f8"), ("pad", "V8")]))
+    assert np.array_equal(rec["xyz"], kp[:, 3:6].astype(np.float32)) and np.array_equal(rec["irpy"][:, 1:], kp[:, :3].astype(np.float32))
+    assert np.array_equal(rec["time"], kp[:, 6]) and np.array_equal(rec["irpy"][:, 0], np.arange(7, dtype=np.float32))
+    # the PCD reader of this repo takes it as a cloud of the key positions (x y z intensity; the rest skipped)
+    pts = host_api.load_pcd(path)
+    assert np.array_equal(pts[:, :3], kp[:, 3:6].astype(np.float32)) and np.array_equal(pts[:, 3], np.arange(7, dtype=np.float32))
+
+
 def test_pcd_binary_compressed(tmp_path):
     """pcl::io::savePCDFileBinaryCompressed: sizes + LZF stream over the field-major block."""
     import struct

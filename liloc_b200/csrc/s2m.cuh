@@ -36,6 +36,8 @@ constexpr int kNSums = 28;               // 21 (upper J^T J) + 6 (J^T r) + 1 (co
 constexpr int kRedGroups = kS2mThreads / kNSums;   // 9 groups of 28 threads for the cross-block reduction
 constexpr int kSumsPerWarp = (kNSums + kS2mWarps - 1) / kS2mWarps;      // 4: warp w reduces sums 4w .. 4w+3 of a tile
 static_assert(kQPB == 32, "the tile sums map one query row to one lane");
+constexpr int kBatchTiles = kS2mThreads / kQPB;   // tiles whose plane / line fits run together: one fit per thread
+constexpr int kBatchQ = kBatchTiles * kQPB;
 
 struct S2mState {                        // members isDegenerate / matP (src/mapOptmization.cpp:90-91)
     int is_degenerate;
@@ -538,7 +540,11 @@ struct S2mShared {
     float pose[6];
     float sc[6];
     Trig trig;
-    float row[kQPB][8];        // 6 Jacobian entries, rhs, valid (1.0 / 0.0)
+    float row[kBatchQ][9];     // 6 Jacobian entries, rhs, valid (1.0 / 0.0); padded to 9 words (one row per lane, no bank conflicts)
+    float4 ori[kBatchQ];       // the batch's queries, body frame
+    int nn[kBatchQ][5];        // ... their five neighbours (indices into the class's local map)
+    int qk[kBatchQ];           // ... their index among the class's queries, -1: slot not in use
+    unsigned char qcls[kBatchQ], qok[kBatchQ];   // ... class; 1 when five neighbours lie within 1 m
     double sums[kNSums];
     double red[kRedGroups][kNSums];
     float X[6];
@@ -549,55 +555,62 @@ struct S2mShared {
     int n_sel;
 };
 
-// Residual rows for one tile of queries of class `cls` into shared memory (phases A and B).  A group of
-// kKnnLanes lanes owns one query: cooperative kNN, then lane 0 of the group does the fit and the Jacobian row.
-// Returns through coeff_out/flag_out as well when they are non-null (k_feature_pass).
-LILOC_DEV void s2m_tile_rows(S2mShared& sh, const int cls, const int tile, const int nq,
-                             float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
+// Phase A for one tile of queries of class `cls`: a group of kKnnLanes lanes owns one query (cooperative exact 5-NN); the
+// neighbour indices go to batch slots [slot0, slot0 + kQPB) in shared memory.
+LILOC_DEV void s2m_tile_knn(S2mShared& sh, const int cls, const int tile, const int nq, const int slot0) {
     const FeatView& f = sh.fv[cls];
     const int s = threadIdx.x / kKnnLanes, sub = threadIdx.x % kKnnLanes;
     const int qk = tile * kQPB + s;
     const bool active = qk < nq;
     float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
     if (active) { ori = __ldg(&f.scan[qk * f.stride]); sel = apply_T(sh.T, ori); }
-#ifdef LILOC_S2M_PROFILE
-    if (threadIdx.x == 0) sh.dbg[0] = clock64();
-#endif
     const Knn5 r = knn5_group<kKnnLanes>(f.grid, sh.gp[cls], sel, sub, active);
-#ifdef LILOC_S2M_PROFILE
-    if (threadIdx.x == 0) sh.dbg[1] = clock64();
-#endif
     if (sub == 0) {
-        float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float valid = 0.f;
-        float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && r.i[4] != 0x7fffffff && r.d[4] < 1.0f) {
-            float nb[5][3];
+        const int slot = slot0 + s;
+        sh.qk[slot] = active ? qk : -1;
+        sh.qcls[slot] = (unsigned char)cls;
+        sh.qok[slot] = (active && r.i[4] != 0x7fffffff && r.d[4] < 1.0f) ? 1 : 0;
+        sh.ori[slot] = ori;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float4 p = __ldg(&f.map[r.i[j]]);
-                nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
-            }
-            float4 c;
-            const bool keep = cls ? corner_residual(nb, r.d[4], sel, &c) : surf_residual(nb, r.d[4], ori, sel, &c);
-            if (keep) { coeff = c; jacobian_row(sh.trig, ori, c, row); valid = 1.f; }
-        }
-        if (valid == 0.f) {
-#pragma unroll
-            for (int j = 0; j < 7; ++j) row[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 7; ++j) sh.row[s][j] = row[j];
-        sh.row[s][7] = valid;
-        if (coeff_out && active) { coeff_out[qk * f.stride] = coeff; flag_out[qk * f.stride] = valid != 0.f ? 1 : 0; }
+        for (int j = 0; j < 5; ++j) sh.nn[slot][j] = r.i[j];
     }
-#ifdef LILOC_S2M_PROFILE
-    if (threadIdx.x == 0) sh.dbg[2] = clock64();
-#endif
-    __syncthreads();
-#ifdef LILOC_S2M_PROFILE
-    if (threadIdx.x == 0) sh.dbg[3] = clock64();
-#endif
+}
+
+// Phase B for a batch of `nslots` queries: ONE THREAD PER QUERY does the plane (or line) fit, the gates and the Jacobian row.
+// The fit is a ~3 us chain of dependent IEEE divisions and square roots whatever the number of lanes that walk it; run behind
+// every tile's 5-NN on one lane of eight it was paid once per tile (two tiles per block on cfg 1: 2 x 2.9 us per iteration),
+// here once per batch of up to kBatchTiles tiles, with all lanes of the fitting warps busy.
+// Writes coeff_out / flag_out as well when they are non-null (k_feature_pass).
+LILOC_DEV void s2m_batch_rows(S2mShared& sh, const int nslots, float4* __restrict__ coeff_out, unsigned char* __restrict__ flag_out) {
+    const int slot = threadIdx.x;
+    if (slot >= nslots) return;
+    float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float valid = 0.f;
+    float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int qk = sh.qk[slot];
+    const int cls = sh.qcls[slot];
+    const FeatView& f = sh.fv[cls];
+    if (qk >= 0 && sh.qok[slot]) {
+        const float4 ori = sh.ori[slot];
+        const float4 sel = apply_T(sh.T, ori);
+        float nb[5][3];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 p = __ldg(&f.map[sh.nn[slot][j]]);
+            nb[j][0] = p.x; nb[j][1] = p.y; nb[j][2] = p.z;
+        }
+        float4 c;
+        const bool keep = cls ? corner_residual(nb, 0.f, sel, &c) : surf_residual(nb, 0.f, ori, sel, &c);      // the 1 m gate is in qok
+        if (keep) { coeff = c; jacobian_row(sh.trig, ori, c, row); valid = 1.f; }
+    }
+    if (valid == 0.f) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) row[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) sh.row[slot][j] = row[j];
+    sh.row[slot][7] = valid;
+    if (coeff_out && qk >= 0) { coeff_out[qk * f.stride] = coeff; flag_out[qk * f.stride] = valid != 0.f ? 1 : 0; }
 }
 
 // Stage the class views and the device-resident grid geometry in shared memory (once per kernel).
@@ -665,17 +678,36 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
             double acc[kSumsPerWarp];                        // lane 0 of every warp: running sums over this block's tiles
 #pragma unroll
             for (int u = 0; u < kSumsPerWarp; ++u) acc[u] = 0.0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int cls = tile < n_tiles_c ? 1 : 0;      // corner tiles first (combineOptimizationCoeffs order)
-                s2m_tile_rows(sh, cls, cls ? tile : tile - n_tiles_c, cls ? nq_c : nq, nullptr, nullptr);
-                {
+            for (int tile0 = blockIdx.x; tile0 < n_tiles; tile0 += kBatchTiles * gridDim.x) {
+                int nb = 0;                                    // tiles of this batch
+#ifdef LILOC_S2M_PROFILE
+                if (threadIdx.x == 0) sh.dbg[0] = clock64();
+#endif
+                for (int tile = tile0; tile < n_tiles && nb < kBatchTiles; tile += gridDim.x, ++nb) {
+                    const int cls = tile < n_tiles_c ? 1 : 0;  // corner tiles first (combineOptimizationCoeffs order)
+                    s2m_tile_knn(sh, cls, cls ? tile : tile - n_tiles_c, cls ? nq_c : nq, nb * kQPB);
+                }
+#ifdef LILOC_S2M_PROFILE
+                if (threadIdx.x == 0) sh.dbg[1] = clock64();
+#endif
+                __syncthreads();
+                s2m_batch_rows(sh, nb * kQPB, nullptr, nullptr);
+#ifdef LILOC_S2M_PROFILE
+                if (threadIdx.x == 0) sh.dbg[2] = clock64();
+#endif
+                __syncthreads();
+#ifdef LILOC_S2M_PROFILE
+                if (threadIdx.x == 0) sh.dbg[3] = clock64();
+#endif
+                for (int i = 0; i < nb; ++i) {                 // tile sums, tiles in ascending order as before
                     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                    const float* r = sh.row[i * kQPB + lane];
                     double v[kSumsPerWarp];
 #pragma unroll
                     for (int u = 0; u < kSumsPerWarp; ++u) {
                         const int k = warp * kSumsPerWarp + u;
                         v[u] = 0.0;
-                        if (k < kNSums) v[u] = (double)sh.row[lane][c_sum_a[k]] * (double)sh.row[lane][c_sum_c[k]];
+                        if (k < kNSums) v[u] = (double)r[c_sum_a[k]] * (double)r[c_sum_c[k]];
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -839,7 +871,9 @@ k_feature_pass(S2mArgs a, int cls, const float* __restrict__ pose6, float4* __re
     const int n_tiles = (nq + kQPB - 1) / kQPB;
     s2m_refresh_transform(sh);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        s2m_tile_rows(sh, cls, tile, nq, coeff_out, flag_out);
+        s2m_tile_knn(sh, cls, tile, nq, 0);
+        __syncthreads();
+        s2m_batch_rows(sh, kQPB, coeff_out, flag_out);
         __syncthreads();
     }
 }

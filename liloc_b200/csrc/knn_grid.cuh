@@ -63,18 +63,37 @@ LILOC_DEV void top5_insert(Knn5& t, float d, int i) {
 // merged with five rounds of (d2, index) arg-min over xor-shuffles.  On return every lane of the group
 // holds the same result.  Far fewer instructions than one warp per query: the map is a surface, so a
 // 27-cell neighbourhood holds only ~100-250 candidates.
+// `bound`: an upper bound of the fifth neighbour's squared distance, when the caller has one (the registration kernel: the
+// largest distance to the five neighbours of the previous iteration, which are five distinct map points); 3.4e38 otherwise.
+// Cells that cannot hold a point with d2 <= bound and d2 < 1 are not read: of a cell the query sees its nearest face, and the
+// lower bound lb = ((ex^2) + (ey^2)) + (ez^2) of the face distances is evaluated in the operation order of dist2, so -- float
+// subtraction, multiplication and addition being monotone -- lb <= dist2(q, p) holds in float for every p of the cell.  A point
+// with d2 > bound is not among the five smallest (d2, index) and one with d2 >= 1 is never inserted: the result is unchanged.
 template <int L>
-LILOC_DEV Knn5 knn5_group(const GridView& g, const GridParams& gp, const float4 q, const int sub, const bool active) {
+LILOC_DEV Knn5 knn5_group(const GridView& g, const GridParams& gp, const float4 q, const int sub, const bool active, const float bound = 3.4e38f) {
     const int cx = cell_coord(q.x, gp.inv_cell, gp.g0[0]);
     const int cy = cell_coord(q.y, gp.inv_cell, gp.g0[1]);
     const int cz = cell_coord(q.z, gp.inv_cell, gp.g0[2]);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gp.dim[0] - 1);
+    // squared distance to the nearest face of the cells at offset -1 / 0 / +1 (cell edges are powers of two: exact coordinates)
+    const float edge = 1.0f / gp.inv_cell;
+    float sx[3], sy[3], sz[3];
+    {
+        const float ox = (float)(cx + gp.g0[0]) * edge, oy = (float)(cy + gp.g0[1]) * edge, oz = (float)(cz + gp.g0[2]) * edge;
+        const float xl = q.x - ox, xr = (ox + edge) - q.x, yl = q.y - oy, yr = (oy + edge) - q.y, zl = q.z - oz, zr = (oz + edge) - q.z;
+        sx[0] = xl * xl; sx[1] = 0.f; sx[2] = xr * xr;
+        sy[0] = yl * yl; sy[1] = 0.f; sy[2] = yr * yr;
+        sz[0] = zl * zl; sz[1] = 0.f; sz[2] = zr * zr;
+    }
     int rs[9], re[9];
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
         const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
         rs[r] = 0; re[r] = 0;
-        if (active && yy >= 0 && yy < gp.dim[1] && zz >= 0 && zz < gp.dim[2] && x0 <= x1) {
+        const float lb_l = (sx[0] + sy[r % 3]) + sz[r / 3], lb_c = (sx[1] + sy[r % 3]) + sz[r / 3], lb_r = (sx[2] + sy[r % 3]) + sz[r / 3];
+        const bool need_c = lb_c <= bound && lb_c < 1.0f;
+        const int xa = (lb_l <= bound && lb_l < 1.0f) ? cx - 1 : cx, xb = (lb_r <= bound && lb_r < 1.0f) ? cx + 1 : cx;
+        const int x0 = max(xa, 0), x1 = min(xb, gp.dim[0] - 1);
+        if (active && need_c && yy >= 0 && yy < gp.dim[1] && zz >= 0 && zz < gp.dim[2] && x0 <= x1) {
             const int base = (zz * gp.dim[1] + yy) * gp.dim[0];
             rs[r] = __ldg(&g.cell_start[base + x0]);
             re[r] = __ldg(&g.cell_start[base + x1 + 1]);

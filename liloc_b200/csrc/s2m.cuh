@@ -557,14 +557,26 @@ struct S2mShared {
 
 // Phase A for one tile of queries of class `cls`: a group of kKnnLanes lanes owns one query (cooperative exact 5-NN); the
 // neighbour indices go to batch slots [slot0, slot0 + kQPB) in shared memory.
-LILOC_DEV void s2m_tile_knn(S2mShared& sh, const int cls, const int tile, const int nq, const int slot0) {
+// `seeded`: the slots hold this tile's queries and their neighbours of the previous iteration (a block whose tiles fit one batch
+// sees the same queries in every iteration): the distances to those five points bound the search (knn5_group).
+LILOC_DEV void s2m_tile_knn(S2mShared& sh, const int cls, const int tile, const int nq, const int slot0, const bool seeded = false) {
     const FeatView& f = sh.fv[cls];
     const int s = threadIdx.x / kKnnLanes, sub = threadIdx.x % kKnnLanes;
     const int qk = tile * kQPB + s;
     const bool active = qk < nq;
     float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
     if (active) { ori = __ldg(&f.scan[qk * f.stride]); sel = apply_T(sh.T, ori); }
-    const Knn5 r = knn5_group<kKnnLanes>(f.grid, sh.gp[cls], sel, sub, active);
+    float bound = 3.4e38f;
+    if (seeded) {                                     // uniform over the block
+        float d = 0.f;
+        const bool have = active && sh.qok[slot0 + s] != 0;
+        if (have && sub < 5) d = dist2(sel, __ldg(&f.map[sh.nn[slot0 + s][sub]]));
+#pragma unroll
+        for (int o = kKnnLanes / 2; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+        if (have) bound = d;
+        __syncwarp();                                 // the slot is rewritten below by lane 0 of the group
+    }
+    const Knn5 r = knn5_group<kKnnLanes>(f.grid, sh.gp[cls], sel, sub, active, bound);
     if (sub == 0) {
         const int slot = slot0 + s;
         sh.qk[slot] = active ? qk : -1;
@@ -669,6 +681,7 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
 #else
 #define S2M_CLK(i)
 #endif
+    const bool one_batch = (long long)blockIdx.x + (long long)kBatchTiles * gridDim.x >= n_tiles;      // all tiles of this block in one batch
     if (!skipped) {
         for (int iter = 0; iter < a.max_iters; ++iter) {
             S2M_CLK(0)
@@ -685,7 +698,7 @@ __global__ void __launch_bounds__(kS2mThreads, LILOC_S2M_MINBLOCKS) k_scan2map(S
 #endif
                 for (int tile = tile0; tile < n_tiles && nb < kBatchTiles; tile += gridDim.x, ++nb) {
                     const int cls = tile < n_tiles_c ? 1 : 0;  // corner tiles first (combineOptimizationCoeffs order)
-                    s2m_tile_knn(sh, cls, cls ? tile : tile - n_tiles_c, cls ? nq_c : nq, nb * kQPB);
+                    s2m_tile_knn(sh, cls, cls ? tile : tile - n_tiles_c, cls ? nq_c : nq, nb * kQPB, iter > 0 && one_batch);
                 }
 #ifdef LILOC_S2M_PROFILE
                 if (threadIdx.x == 0) sh.dbg[1] = clock64();

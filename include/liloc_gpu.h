@@ -321,6 +321,10 @@ int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries_map, int nq, int* idx5
  * laserCloudOriSurfFlag[i] and coefficient coeffSelSurfVec[i]; arrays have Q_all entries. */
 int liloc_surf_pass(liloc_ctx* ctx, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag);
 int liloc_knn5_class(liloc_ctx* ctx, int cls, const liloc_point* queries_map, int nq, int* idx5, float* d2_5, int* found);
+/* Test surface: liloc_knn5_class with bounds[i] = an upper bound of query i's fifth squared distance (what the registration
+ * kernel derives from the previous iteration's neighbours to skip cells; knn_grid.cuh).  With a valid bound the result is
+ * the unbounded one. */
+int liloc_debug_knn5_bounded(liloc_ctx* ctx, int cls, const liloc_point* queries_map, int nq, const float* bounds, int* idx5, float* d2_5, int* found);
 /* surfOptimization (cls 0) / upstream cornerOptimization (cls 1) at a fixed pose, like liloc_surf_pass. */
 int liloc_feature_pass(liloc_ctx* ctx, int cls, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag);
 /* pcl::getTransformation as the device evaluates it: top 3x4 block, row-major. */

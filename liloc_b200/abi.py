@@ -172,6 +172,7 @@ def _load() -> C.CDLL:
         "liloc_set_timing": (C.c_int, [P, C.c_int]),
         "liloc_kernel_launches": (C.c_longlong, [P]),
         "liloc_last_trace": (C.c_int, [P, P, C.c_int]),
+        "liloc_debug_knn5_bounded": (C.c_int, [P, C.c_int, P, C.c_int, P, P, P, P]),
         "liloc_ndt_target_put": (C.c_int, [P, C.c_int, P, C.c_int, C.c_float, ip]),
         "liloc_ndt_source_put": (C.c_int, [P, C.c_int, P, C.c_int, C.c_int]),
         "liloc_ndt_align_batch": (C.c_int, [P, C.POINTER(NdtJob), C.c_int, C.POINTER(NdtOpts), C.POINTER(NdtOut)]),
@@ -236,7 +237,7 @@ EXPORTS = ("liloc_create liloc_destroy liloc_last_error liloc_version liloc_keyf
            "liloc_frame_features liloc_last_s2m_extra liloc_keyframe_put_features liloc_keyframe_size_class "
            "liloc_localmap_build_class liloc_localmap_set_class liloc_localmap_get_class liloc_scan_put_class "
            "liloc_scan_ds_get_class liloc_knn5_class liloc_feature_pass liloc_debug_eigen3 liloc_debug_line liloc_last_marks liloc_ndt_stats_get liloc_ndt_stats_reset liloc_ndt_target_put_keyframes liloc_ndt_target_size liloc_set_map_cache liloc_icp_fitness liloc_icp_fitness_resident liloc_globalmap_build liloc_keyframe_get liloc_deskew liloc_deskewed_get liloc_last_deskew_ms liloc_last_deskew_marks liloc_deskew_advance "
-           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results liloc_scan_prefetch liloc_set_share").split()
+           "liloc_keyframe_put_from_raw_scan liloc_ndt_target_put_keyframes_filtered liloc_comm_unique_id liloc_comm_init liloc_comm_destroy liloc_shard_indices liloc_unshard_rows liloc_comm_rank liloc_comm_world liloc_ndt_align_batch_sharded liloc_gather_results liloc_scan_prefetch liloc_set_share liloc_debug_knn5_bounded").split()
 
 
 COMM_ID_BYTES = 128
@@ -520,6 +521,15 @@ class Context:
         d2 = np.empty((len(q), 5), np.float32)
         found = np.empty(len(q), np.int32)
         self._chk(lib.liloc_knn5_class(self._h, cls, _ptr(q), len(q), _ptr(idx), _ptr(d2), _ptr(found)))
+        return idx, d2, found
+
+    def knn5_bounded(self, queries_map, bounds, cls: int = 0) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        q = _cloud(queries_map)
+        b = np.ascontiguousarray(bounds, np.float32).reshape(len(q))
+        idx = np.empty((len(q), 5), np.int32)
+        d2 = np.empty((len(q), 5), np.float32)
+        found = np.empty(len(q), np.int32)
+        self._chk(lib.liloc_debug_knn5_bounded(self._h, cls, _ptr(q), len(q), _ptr(b), _ptr(idx), _ptr(d2), _ptr(found)))
         return idx, d2, found
 
     def feature_pass(self, cls: int, pose6, stride: int, q_all: int) -> tuple[np.ndarray, np.ndarray]:

@@ -158,7 +158,8 @@ constexpr int kKnnLanes = 8;     // lanes per query in the registration kernels
 // Standalone kNN kernel behind liloc_knn5 (kernel-level parity tests): the same group search the
 // registration kernel uses.
 __global__ void __launch_bounds__(256)
-k_knn5(const float4* __restrict__ queries, int nq, GridView g, int* __restrict__ idx5, float* __restrict__ d2, int* __restrict__ found) {
+k_knn5(const float4* __restrict__ queries, int nq, GridView g, int* __restrict__ idx5, float* __restrict__ d2, int* __restrict__ found,
+       const float* __restrict__ bounds = nullptr) {
     const int sub = threadIdx.x % kKnnLanes;
     const GridParams gp = *g.p;
     const int groups_per_grid = (gridDim.x * blockDim.x) / kKnnLanes;
@@ -166,7 +167,7 @@ k_knn5(const float4* __restrict__ queries, int nq, GridView g, int* __restrict__
     for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kKnnLanes; qi < nq_pad; qi += groups_per_grid) {
         const bool active = qi < nq;
         const float4 q = active ? __ldg(&queries[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const Knn5 r = knn5_group<kKnnLanes>(g, gp, q, sub, active);
+        const Knn5 r = knn5_group<kKnnLanes>(g, gp, q, sub, active, (bounds && active) ? __ldg(&bounds[qi]) : 3.4e38f);
         if (active && sub == 0) {
             int f = 0;
 #pragma unroll

@@ -1342,6 +1342,28 @@ int liloc_knn5(liloc_ctx* ctx, const liloc_point* queries, int nq, int* idx5, fl
     return liloc_knn5_class(ctx, LILOC_SURF, queries, nq, idx5, d2_5, found);
 }
 
+// liloc_knn5_class with the caller's upper bound of every query's fifth squared distance (the pruning the registration kernel
+// applies from its second iteration on); test surface.
+int liloc_debug_knn5_bounded(liloc_ctx* ctx, int cls, const liloc_point* queries, int nq, const float* bounds, int* idx5, float* d2_5, int* found) {
+    ENTER(ctx);
+    if (bad_class(cls) || nq < 0 || (nq > 0 && (!queries || !bounds || !idx5 || !d2_5 || !found))) return fail(ctx, LILOC_ERR_ARG, "knn5_bounded: bad arguments");
+    FeatClass& fc = ctx->fc[cls];
+    if (!fc.have_map) return fail(ctx, LILOC_ERR_STATE, "knn5_bounded: no local map");
+    if (nq == 0) return LILOC_OK;
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmp_pts, (size_t)nq))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_i, (size_t)nq * 6))) return rc;
+    if ((rc = ensure(ctx, ctx->tmp_f, (size_t)nq * 6))) return rc;
+    CU(cudaMemcpyAsync(ctx->tmp_pts.p, queries, (size_t)nq * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->tmp_f.p + (size_t)nq * 5, bounds, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_knn5<<<blocks_for(ctx, (long long)nq * kKnnLanes, 256), 256, 0, ctx->stream>>>(ctx->tmp_pts.p, nq, grid_view(fc), ctx->tmp_i.p, ctx->tmp_f.p, ctx->tmp_i.p + (size_t)nq * 5, ctx->tmp_f.p + (size_t)nq * 5); KCHECK();
+    CU(cudaMemcpyAsync(idx5, ctx->tmp_i.p, (size_t)nq * 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(found, ctx->tmp_i.p + (size_t)nq * 5, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(d2_5, ctx->tmp_f.p, (size_t)nq * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LILOC_OK;
+}
+
 int liloc_feature_pass(liloc_ctx* ctx, int cls, const float* pose6, int stride, liloc_point* coeff, unsigned char* flag) {
     ENTER(ctx);
     if (bad_class(cls) || !pose6 || stride < 1 || !coeff || !flag) return fail(ctx, LILOC_ERR_ARG, "feature_pass: bad arguments");

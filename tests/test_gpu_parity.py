@@ -176,6 +176,38 @@ def test_knn5_exact_ties_by_index(gpu_ctx, orc):
     assert _knn_compare(gpu_ctx, orc, map_ds, q) > 300
 
 
+def test_knn5_pruned_by_a_bound_is_the_unbounded_search(gpu_ctx, orc, scene_hdl):
+    """The registration kernel skips search cells whose nearest face lies beyond a bound on the fifth neighbour's distance
+    (knn_grid.cuh).  With any valid bound -- down to the fifth distance itself, where a cell's lower bound can EQUAL the bound
+    and ties are decided by the point index -- the neighbours must be those of the unbounded search, bit for bit."""
+    s = scene_hdl
+    raw = np.concatenate([orc.transform_cloud(c, p) for c, p in zip(s.kf_clouds, s.kf_poses)])
+    gpu_ctx.localmap_set(raw, s.map_leaf)
+    rng = np.random.default_rng(11)
+    q = orc.transform_cloud(orc.voxelgrid(s.scan_raw, s.scan_leaf), s.guess)
+    # lattice map with exact ties as a second case
+    g = (np.arange(-12, 13) * 0.25).astype(np.float32)
+    lat = np.stack(np.meshgrid(g, g, g[:6], indexing="ij"), -1).reshape(-1, 3)
+    lat = np.c_[lat[rng.permutation(len(lat))], np.zeros(len(lat))].astype(np.float32)
+    ql = np.c_[rng.integers(-12, 13, (400, 3)) * 0.25 + 0.125 * rng.integers(0, 2, (400, 3)), np.zeros(400)].astype(np.float32)
+    ql[:, 2] = (rng.integers(-12, -6, 400) * 0.25 + 0.125 * rng.integers(0, 2, 400)).astype(np.float32)
+    for cloud, leaf, queries in ((None, None, q), (lat, 0.1, ql)):
+        if cloud is not None:
+            gpu_ctx.localmap_set(cloud, leaf)
+        idx, d2, found = gpu_ctx.knn5(queries)
+        full = found == 5
+        assert full.sum() > 100
+        d5 = np.where(full, d2[:, 4], np.float32(1.0)).astype(np.float32)
+        for bounds in (d5,                                                   # the tightest valid bound
+                       np.nextafter(d5, np.float32(np.inf)),
+                       d5 * np.float32(1.5),
+                       np.where(rng.random(len(d5)) < 0.5, d5, np.float32(3.4e38))):
+            b = np.where(full, bounds, np.float32(3.4e38)).astype(np.float32)
+            idx_b, d2_b, found_b = gpu_ctx.knn5_bounded(queries, b)
+            assert np.array_equal(found_b, found)
+            assert np.array_equal(idx_b, idx) and np.array_equal(d2_b.view(np.uint32), d2.view(np.uint32))
+
+
 def test_knn5_tiny_maps(gpu_ctx, orc):
     for n in (1, 4, 5, 6):
         rng = np.random.default_rng(n)

@@ -39,7 +39,7 @@ struct GridView {
 LILOC_DEV int cell_coord(float v, float inv_cell, int g0) { return (int)floorf(v * inv_cell) - g0; }
 
 constexpr int kScanThreads = 256;
-constexpr int kScanPerThread = 8;
+constexpr int kScanPerThread = 16;   // four int4 loads in flight per thread
 constexpr int kScanTile = kScanThreads * kScanPerThread;     // cells per block and step of the cell-count scan (pipeline.cuh)
 
 // ---- exact 5-NN, one warp per query ---------------------------------------------------------------

@@ -595,6 +595,10 @@ int pipe_check(liloc_ctx* ctx) {
     else { ctx->err = "point-cloud pipeline: a look-back wait gave up (results of this call are not valid)"; ctx->pipe_failed = LILOC_ERR_CUDA; }
     for (FeatClass& fc : ctx->fc) { fc.have_map = false; fc.have_scan = false; fc.M = -1; fc.Q_all = -1; }
     for (auto& k : ctx->map_key) k.valid = false;
+    if (e != 2) {      // a launch that gave up half-way may have left search-cell counters behind (the kernel counts them back to zero itself)
+        for (FeatClass& fc : ctx->fc) if (fc.cell_counts.p) cudaMemsetAsync(fc.cell_counts.p, 0, fc.cell_counts.cap * sizeof(int), ctx->stream);
+        if (ctx->aux.cell_counts.p) cudaMemsetAsync(ctx->aux.cell_counts.p, 0, ctx->aux.cell_counts.cap * sizeof(int), ctx->stream);
+    }
     return ctx->pipe_failed;
 }
 

@@ -65,7 +65,7 @@ struct VgProb {
     int build_grid;
     int max_cells;
     GridParams* gp;
-    int* cell_counts;          // all-zero outside [0, previous ncells) on entry; scatter cursor on exit
+    int* cell_counts;          // all zero between launches: counted up in R2, counted down to zero again in G3
     int* cell_start;
     unsigned long long* grid_state;   // look-back words of the cell-count scan
     float4* cpts;
@@ -286,10 +286,6 @@ LILOC_DEV void pipe_bbox(const PipeArgs& a, const VgProb& q) {
     block_minmax_commit(mn, mx, q.enc);
     // histogram buffers 1 and 2 must be zero when the first scatter pass accumulates into them
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kHistStride; i += gridDim.x * blockDim.x) q.hist[kHistStride + i] = 0;
-    if (q.build_grid) {                           // clear what the previous build left in the cell counters
-        const int prev = q.gp->ncells;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prev; i += gridDim.x * blockDim.x) q.cell_counts[i] = 0;
-    }
 }
 
 // ---- P1: keys + histogram of the first pass ----------------------------------------------------------------------
@@ -579,24 +575,48 @@ LILOC_DEV void pipe_cells_scan(const VgProb& q, const GridParams& gp, const unsi
     int prev_tile = -1, prev_end = 0;                           // carried like in pipe_centroids
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * kScanTile + threadIdx.x * kScanPerThread;
+        const bool whole = base + kScanPerThread <= n;          // cell_counts / cell_start are 16-byte aligned and base is a multiple of 16
         int v[kScanPerThread];
+        if (whole) {
+#pragma unroll
+            for (int u = 0; u < kScanPerThread / 4; ++u) {
+                const int4 w = __ldcg(reinterpret_cast<const int4*>(q.cell_counts + base) + u);
+                v[4 * u] = w.x; v[4 * u + 1] = w.y; v[4 * u + 2] = w.z; v[4 * u + 3] = w.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanPerThread; ++j) v[j] = (base + j < n) ? __ldcg(&q.cell_counts[base + j]) : 0;
+        }
         int c = 0;
 #pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) { v[j] = (base + j < n) ? q.cell_counts[base + j] : 0; c += v[j]; }
+        for (int j = 0; j < kScanPerThread; ++j) c += v[j];
         int total;
         const int local = block_exclusive_scan_256(c, &total);
         const int tile_offset = prev_end + pipe_lookback(q.grid_state, tile, total, epoch, error_flag, true, prev_tile + 1);
         prev_tile = tile; prev_end = tile_offset + total;
         int run = tile_offset + local;
+        if (whole) {
 #pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            if (base + j < n) { q.cell_start[base + j] = run; q.cell_counts[base + j] = run; }
-            run += v[j];
-            if (base + j == n - 1) q.cell_start[n] = run;
+            for (int u = 0; u < kScanPerThread / 4; ++u) {
+                int4 w;
+                w.x = run; run += v[4 * u]; w.y = run; run += v[4 * u + 1]; w.z = run; run += v[4 * u + 2]; w.w = run; run += v[4 * u + 3];
+                reinterpret_cast<int4*>(q.cell_start + base)[u] = w;
+            }
+            if (base + kScanPerThread == n) q.cell_start[n] = run;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanPerThread; ++j) {
+                if (base + j < n) q.cell_start[base + j] = run;
+                run += v[j];
+                if (base + j == n - 1) q.cell_start[n] = run;
+            }
         }
     }
 }
 
+// The counters are counted DOWN while the points take their places: the order inside a cell is arbitrary either way (the 5-NN
+// is a total order over (d2, index)), and every counter is back at zero when the phase ends -- nothing to clear for the next
+// build (the previous version cleared ncells counters in phase P0 and wrote a cursor array in G2: 8 MB per frame at 1 M cells).
 LILOC_DEV void pipe_cells_scatter(const VgProb& q, const GridParams& gp) {
     const int M = *q.count;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
@@ -604,7 +624,8 @@ LILOC_DEV void pipe_cells_scatter(const VgProb& q, const GridParams& gp) {
         const int cx = cell_coord(p.x, gp.inv_cell, gp.g0[0]);
         const int cy = cell_coord(p.y, gp.inv_cell, gp.g0[1]);
         const int cz = cell_coord(p.z, gp.inv_cell, gp.g0[2]);
-        const int pos = atomicAdd(&q.cell_counts[(cz * gp.dim[1] + cy) * gp.dim[0] + cx], 1);
+        const int cell = (cz * gp.dim[1] + cy) * gp.dim[0] + cx;
+        const int pos = __ldcg(&q.cell_start[cell]) + atomicSub(&q.cell_counts[cell], 1) - 1;
         q.cpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
     }
 }

@@ -367,15 +367,41 @@ LILOC_DEV void pipe_sort_pass(const VgProb& q, int npass, int pass, PipeSmem& sm
 #pragma unroll
         for (int u = 0; u < kSortUnits; ++u) sm.sort.cnt[u][t] = 0;
     } else {
-        int pre = 0, tot = 0;
+        // Warp w reads rows w, w + 8, ... whole (a lane: eight digits = two 16-byte loads, kRowsInFlight rows in flight), the eight
+        // warps' partial sums meet in shared memory: 4x fewer load instructions and half the dependent round trips of the version
+        // where thread t walked column t of every row.
+        constexpr int kRowsInFlight = 4;
+        int tot8[8], pre8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { tot8[j] = 0; pre8[j] = 0; }
 #pragma unroll 1
-        for (int b = 0; b < g.nb; b += 16) {                    // 16 independent (predicated) loads in flight per thread:
-            int v[16];                                          // a scalar tail loop would pay one L2 latency per row
+        for (int b = warp; b < g.nb; b += 8 * kRowsInFlight) {
+            int4 a[kRowsInFlight][2];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = (b + u < g.nb) ? hcur[(b + u) * 256 + t] : 0;
+            for (int u = 0; u < kRowsInFlight; ++u) {
+                const int bb = b + 8 * u;
+                a[u][0] = make_int4(0, 0, 0, 0); a[u][1] = make_int4(0, 0, 0, 0);
+                if (bb < g.nb) {
+                    a[u][0] = __ldcg(reinterpret_cast<const int4*>(hcur + bb * 256 + 8 * lane));
+                    a[u][1] = __ldcg(reinterpret_cast<const int4*>(hcur + bb * 256 + 8 * lane) + 1);
+                }
+            }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) { tot += v[u]; pre += (b + u < sidx) ? v[u] : 0; }
+            for (int u = 0; u < kRowsInFlight; ++u) {
+                const int v[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
+                const bool before = b + 8 * u < sidx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { tot8[j] += v[j]; pre8[j] += before ? v[j] : 0; }
+            }
         }
+        int* stage = reinterpret_cast<int*>(&sm.sort.pre[0][0]);        // 2 x 8 x 256 ints: free until the first tile's prefix step
+        static_assert(sizeof(sm.sort.pre) >= 2 * 8 * 256 * sizeof(int), "staging of the warps' partial digit sums");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { stage[warp * 256 + 8 * lane + j] = tot8[j]; stage[2048 + warp * 256 + 8 * lane + j] = pre8[j]; }
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { tot += stage[w * 256 + t]; pre += stage[2048 + w * 256 + t]; }
         int total;
         const int excl = block_exclusive_scan_256(tot, &total);
         sm.sort.offs[t] = excl + pre;

@@ -75,7 +75,7 @@ LILOC_DEV Knn5 knn5_group(const GridView& g, const GridParams& gp, const float4 
     const int cy = cell_coord(q.y, gp.inv_cell, gp.g0[1]);
     const int cz = cell_coord(q.z, gp.inv_cell, gp.g0[2]);
     // squared distance to the nearest face of the cells at offset -1 / 0 / +1 (cell edges are powers of two: exact coordinates)
-    const float edge = 1.0f / gp.inv_cell;
+    const float edge = __int_as_float(0x7f000000 - __float_as_int(gp.inv_cell));      // 1 / inv_cell for a power of two, without a division
     float sx[3], sy[3], sz[3];
     {
         const float ox = (float)(cx + gp.g0[0]) * edge, oy = (float)(cy + gp.g0[1]) * edge, oz = (float)(cz + gp.g0[2]) * edge;

@@ -67,5 +67,31 @@ def traffic(path):
     print(json.dumps(res, indent=1))
 
 
+def stalls(path, top=16):
+    """Warp-state samples per CUDA source line (needs --import-source on and -lineinfo): the lines where the warps wait."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    fname, hdr, rows = "?", None, []
+    for r in csv.reader(out.splitlines()):
+        if len(r) >= 2 and r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+        elif len(r) > 10 and r[0] == "Line No":
+            hdr = r
+        elif hdr and len(r) == len(hdr) and r[0].strip().isdigit():
+            g = lambda k: int(float(r[hdr.index(k)] or 0)) if r[hdr.index(k)] not in ("-", "") else 0
+            rows.append((g("# Samples"), g("stall_barrier"), g("stall_long_sb"), g("stall_wait"), g("stall_short_sb"), g("stall_branch_resolving"),
+                         g("Instructions Executed"), f"{fname}:{r[0]}", r[1].strip()[:56]))
+    merged = {}                                   # several captured launches of the kernel: one entry per source line
+    for x in rows:
+        m = merged.setdefault(x[7], [0, 0, 0, 0, 0, 0, 0, x[7], x[8]])
+        for i in range(7):
+            m[i] += x[i]
+    rows = [tuple(v) for v in merged.values()]
+    tot = sum(x[0] for x in rows) or 1
+    print(f"total samples {tot} barrier {sum(x[1] for x in rows)} long_sb {sum(x[2] for x in rows)} wait {sum(x[3] for x in rows)} "
+          f"short {sum(x[4] for x in rows)} branch {sum(x[5] for x in rows)}")
+    for x in sorted(rows, reverse=True)[:top]:
+        print(f"{100 * x[0] / tot:5.1f}% bar={x[1]:6d} lsb={x[2]:6d} wait={x[3]:6d} ssb={x[4]:5d} br={x[5]:5d} inst={x[6]:9d}  {x[7]}  {x[8]}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic, "stalls": stalls}[sys.argv[1]](sys.argv[2])

@@ -479,7 +479,7 @@ def run_ours(args):
                              "no CUDA events inside a frame (one between two launches costs ~2.5 us of device time); the timed region "
                              "as a whole is bracketed by CUDA events on the library's stream (device_s)", "alg_bytes_per_launch": st_dev["alg_bytes_map"] / n_fr,
             "note": "latency-bound, not bandwidth-bound: ~10 dependent phases separated by grid barriers over an L2-resident working set "
-                    "(SURVEY 8d); phase-by-phase latency in profiles/frame_latency_r01.md",
+                    "(SURVEY 8d); phase-by-phase latency in profiles/frame_latency_r02.md (round 1: frame_latency_r01.md)",
             "per_frame_us": {"local_map_launch": map_ms * 1e3 / n_fr, "scan_launch(concurrent)": st_dev["scan_ms"] * 1e3 / n_fr,
                              "scan2map_launch": st_dev["s2m_ms"] * 1e3 / n_fr, "frame_device_total": st_dev["total_ms"] * 1e3 / n_fr},
             "k_scan2map": {"achieved": s2m_gbs, "frac": (s2m_gbs / peak) if s2m_gbs else None,

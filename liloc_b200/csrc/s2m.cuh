@@ -5,12 +5,13 @@
 // The pose, the 6x6 normal equations, the degeneracy projector and the convergence test never leave
 // the device: one grid barrier per Gauss-Newton iteration, zero host round trips.
 //
-// Per iteration, per tile of kQPB scan points:
-//   A  one warp per query: transform by the current pose, exact 5-NN in the search grid (knn_grid.cuh)
-//   B  one thread per query: 5x3 pivoted-Householder plane fit (Eigen colPivHouseholderQr semantics),
+// Per iteration, per batch of up to kBatchTiles tiles of kQPB scan points (all the tiles of a block on the usual launch):
+//   A  per tile, eight lanes per query: transform by the current pose, exact 5-NN in the search grid (knn_grid.cuh), bounded from
+//      the second iteration on by the distances to the previous iteration's neighbours; neighbour indices -> shared memory
+//   B  per batch, ONE THREAD per query: 5x3 pivoted-Householder plane fit (Eigen colPivHouseholderQr semantics) or line fit,
 //      validity gates, weight, Jacobian row (LOAM Euler form)            -> shared memory
-//   C  28 threads: the 21 + 6 unique J^T J | J^T r sums and the correspondence count, accumulated in
-//      double from exact float*float products in ascending query order  -> one partial per block
+//   C  per tile, in tile order: the 21 + 6 unique J^T J | J^T r sums and the correspondence count, accumulated in double from
+//      exact float*float products by a fixed shuffle tree                -> one partial per block
 //   -- grid barrier --
 //   D  every block redundantly: fixed-order reduction of the block partials, float32 Householder QR
 //      solve of the 6x6, (iteration 0) Jacobi eigen-decomposition + degeneracy projector, pose update,

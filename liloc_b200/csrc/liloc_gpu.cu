@@ -1193,26 +1193,14 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     const int dev = in->scan_on_device;
     int rc;
     const int ncls = corner ? 2 : 1;
-    // scans: H2D + VoxelGrid on stream2, so the copy overlaps the map pipeline on the main stream.  A scan that has to be
-    // uploaded inside this call is staged first (its copy is the longest thing in front of the scan launch); one that is
-    // already on the device (resident, de-skewed, or uploaded ahead by liloc_scan_prefetch) is staged AFTER the map launch:
-    // the staging is host time the map kernel does not have to wait for.
-    // (The fork event is recorded in front of the map launch either way: behind it, the scan launch would wait for the map kernel.)
-    PipeArgs ps{}, pm{};
+    // scans: H2D + VoxelGrid on stream2, so the copy overlaps the map pipeline on the main stream
     CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    auto stage_scans = [&]() -> int {
-        for (int cls = 0; cls < ncls; ++cls) {
-            const int rc2 = scan_problem(ctx, cls, ctx->stream2, in->scan[cls], in->n_scan[cls],
-                                         (dev == LILOC_SCAN_DESKEWED && cls != LILOC_SURF) ? LILOC_SCAN_HOST : dev, in->scan_leaf[cls], &ps.prob[cls]);
-            if (rc2) return rc2;
-        }
-        ps.n_prob = ncls;
-        return 0;
-    };
-    const liloc_ctx::ScanPrefetch& pf0 = ctx->pf;
-    const bool scan_uploads_now = corner || (dev == LILOC_SCAN_HOST && !(pf0.issued && pf0.host == in->scan[0] && pf0.n == in->n_scan[0]));
-    if (scan_uploads_now && (rc = stage_scans())) return rc;
+    PipeArgs ps{}, pm{};
+    for (int cls = 0; cls < ncls; ++cls)
+        if ((rc = scan_problem(ctx, cls, ctx->stream2, in->scan[cls], in->n_scan[cls],
+                               (dev == LILOC_SCAN_DESKEWED && cls != LILOC_SURF) ? LILOC_SCAN_HOST : dev, in->scan_leaf[cls], &ps.prob[cls]))) return rc;
+    ps.n_prob = ncls;
     // No CUDA events inside a frame, not even with timing on: an event record between two launches costs ~2.5 us of
     // device time each (measured: 151 -> 145 us per frame without the two around the join).  The phase durations come
     // from the %globaltimer marks block 0 of every launch writes into mapped host memory.
@@ -1241,7 +1229,6 @@ int liloc_frame_features(liloc_ctx* ctx, const liloc_frame_in* in, float* pose6,
     const bool wide = ctx->wide_maps && (long long)ctx->fc[0].n_raw + (corner ? ctx->fc[1].n_raw : 0) > ctx->wide_min;
     const bool map_launched = pm.n_prob > 0;
     if ((rc = pipe_launch(ctx, ctx->stream, pm, ctx->timing ? ctx->d_marks_host : nullptr, wide))) return rc;
-    if (!scan_uploads_now && (rc = stage_scans())) return rc;
     // The scan launch is issued AFTER the map launch: its upload was enqueued first (above) and takes longer than the host
     // needs to get here, while the map launch -- the longer branch when the scan is already on the device -- would
     // otherwise start a launch-call later.
